@@ -1,0 +1,254 @@
+"""oracle/make_golden.py -- pin the oracle: run the REFERENCE's own code on seeded inputs
+and store inputs + outputs as small fixtures under tests/golden/.
+
+Run here (the build container, where /root/reference is mounted):
+    python oracle/make_golden.py
+It imports, UNMODIFIED, from /root/reference:
+    lib/modeling/heads.py   (cls_iou_model, CIM_layer)            -- runs on CPU tensors
+    lib/utils/mask_utils.py (mask_iou, mask_asymmetric_iou)       -- behind a 3-line shim that
+        makes `chainer.backends.cuda.get_array_module` return numpy (chainer/cupy are absent)
+The fixtures travel to the GPU box; /root/reference does not.  While generating, every
+fixture is also replayed through the oracle restatement and any mismatch aborts.
+"""
+import io
+import os
+import sys
+import types
+import contextlib
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get("CIM_REFERENCE", "/root/reference")
+GOLD = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+
+from cim_b200 import synth                      # noqa: E402
+from oracle import heads_oracle, mask_oracle    # noqa: E402
+
+
+def load_reference():
+    chainer = types.ModuleType("chainer")
+    backends = types.ModuleType("chainer.backends")
+    cuda = types.ModuleType("chainer.backends.cuda")
+    cuda.get_array_module = lambda *a: np
+    backends.cuda = cuda
+    chainer.backends = backends
+    sys.modules.update({"chainer": chainer, "chainer.backends": backends,
+                        "chainer.backends.cuda": cuda})
+    sys.path.insert(0, os.path.join(REF, "lib"))
+    import importlib.util
+
+    def imp(name, rel):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    return imp("ref_heads", "lib/modeling/heads.py"), imp("ref_mask_utils", "lib/utils/mask_utils.py")
+
+
+def u16(a):
+    return np.ascontiguousarray(a).view(np.uint16)
+
+
+def reference_maps(ref_mu, masks):
+    """tools/pre/create_cob_iou.py:43-48 / create_cob_asy_iou.py:43-51 with numpy for cupy."""
+    n = len(masks)
+    iou_cols, asy_cols = [], []
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for j in range(n):
+            iou_cols.append(ref_mu.mask_iou(masks, np.expand_dims(masks[j], axis=0)))
+            asy_cols.append(ref_mu.mask_asymmetric_iou(masks, np.expand_dims(masks[j], axis=0)))
+    return (np.concatenate(iou_cols, axis=1).astype(np.float16),
+            np.concatenate(asy_cols, axis=1).astype(np.float16))
+
+
+def make_mask_fixture(ref_mu):
+    params = synth.proposal_params(40, size=64, seed=11)
+    masks = synth.rasterize(params).numpy()
+    masks[5] = masks[4]                # identical pair -> IoU exactly 1
+    masks[7] = 0                       # empty mask -> 0/0 = NaN row/column
+    masks[9] = 1                       # full mask contains everything
+    iou, asy = reference_maps(ref_mu, masks)
+    o_iou, o_asy = mask_oracle.mask_overlap_maps(masks)
+    assert np.array_equal(u16(iou), u16(o_iou)) and np.array_equal(u16(asy), u16(o_asy))
+    l_iou, l_asy = mask_oracle.mask_overlap_maps_literal(masks)
+    assert np.array_equal(u16(iou), u16(l_iou)) and np.array_equal(u16(asy), u16(l_asy))
+    np.savez_compressed(os.path.join(GOLD, "mask_overlap.npz"),
+                        masks_bits=np.packbits(masks.reshape(40, -1), axis=1, bitorder="little"),
+                        hw=np.int64(64 * 64), iou_u16=u16(iou), asy_u16=u16(asy))
+    print("mask_overlap.npz: N=40, NaN entries:", int(np.isnan(iou.astype(np.float32)).sum()))
+
+
+def scores_for(ref_heads, r, c1, seed, sharp):
+    """Plausible head outputs: the reference's own cls_iou_model on random features."""
+    torch.manual_seed(seed)
+    model = ref_heads.cls_iou_model(64, c1, 3)
+    x = torch.randn(r, 64) * sharp
+    with torch.no_grad():
+        return model, x, model(x)
+
+
+def heads_cases():
+    cases = [
+        # name, R, C, mask px, seed, layer thresholds (cls_thr, iou_thr), anti-noise, using_CIM, score sharpness
+        ("voc_r300_l0", 300, 20, 64, 21, (0.25, 0.5), True, True, 4.0),
+        ("voc_r300_l1", 300, 20, 64, 22, (0.35, 0.6), True, True, 4.0),
+        ("voc_r300_l2_nosample", 300, 20, 64, 23, (0.45, 0.7), False, True, 4.0),
+        ("coco_r257", 257, 80, 48, 24, (0.25, 0.5), True, True, 6.0),
+        ("voc_r120_mist", 120, 20, 48, 25, (0.25, 0.5), True, False, 4.0),
+        ("voc_r96_dups", 96, 20, 32, 26, (0.35, 0.6), True, True, 4.0),
+        ("voc_r64_none", 64, 20, 32, 27, (0.25, 0.5), True, True, 4.0),
+        ("voc_r128_nan", 128, 20, 32, 28, (0.25, 0.5), True, True, 4.0),
+        ("voc_r160_edges", 160, 20, 48, 29, (0.35, 0.6), True, True, 4.0),
+    ]
+    return cases
+
+
+def poison_maps(name, iou, asy, cls_thr, iou_thr, seed):
+    """Adversarial map entries: NaNs, and values sitting exactly on / one ulp around the
+    float16 images of the thresholds the heads compare against."""
+    rng = np.random.RandomState(seed)
+    iou, asy = iou.copy(), asy.copy()
+    if "nan" in name:
+        for m in (iou, asy):
+            m[rng.rand(*m.shape) < 0.02] = np.float16("nan")
+    if "edges" in name:
+        for m, thrs in ((iou, (cls_thr, iou_thr)), (asy, (0.85,))):
+            for t in thrs:
+                t16 = np.float16(t)
+                for v in (t16, np.nextafter(t16, np.float16(0)), np.nextafter(t16, np.float16(1))):
+                    m[rng.rand(*m.shape) < 0.03] = v
+    return iou, asy
+
+
+def make_heads_fixtures(ref_heads, ref_mu, cases=None, save=True):
+    cases = cases or heads_cases()
+    out = {}
+    for name, r, c, px, seed, (cls_thr, iou_thr), anti, using_cim, sharp in cases:
+        params = synth.proposal_params(r, size=px, seed=seed)
+        masks = synth.rasterize(params).numpy()
+        if "dups" in name:                       # duplicated proposals -> tied IoU columns, IoU == 1
+            masks[10:20] = masks[0:10]
+            masks[40] = 0                        # an empty proposal -> NaN row/col in both maps
+        iou, asy = mask_oracle.mask_overlap_maps(masks)
+        if "none" in name:                       # nothing can be mined: nobody contains anybody
+            asy = np.zeros_like(asy)
+        iou, asy = poison_maps(name, iou, asy, cls_thr, iou_thr, seed)
+        labels = synth.image_labels(c, 2 if c == 20 else 4, seed)
+        _, _, (p_cls, p_det, r_cls, r_iou) = scores_for(ref_heads, r, c + 1, seed, sharp)
+        # layer 0 consumes (predict_cls, predict_det); later layers (ref_cls, ref_iou)
+        if name.endswith("l1") or name.endswith("l2_nosample"):
+            s_cls, s_det = r_cls[0], r_iou[0]
+        else:
+            s_cls, s_det = p_cls, p_det
+        rois = synth.rois_from_params(params)
+        with contextlib.redirect_stdout(io.StringIO()):
+            layer = ref_heads.CIM_layer(p_seed=0.1, cls_thr=cls_thr, iou_thr=iou_thr,
+                                        Anti_noise_sampling=anti)
+        t_iou, t_asy = torch.from_numpy(iou), torch.from_numpy(asy)
+        np.random.seed(3)
+        ref_out = layer(s_cls, s_det, rois, labels, t_iou, t_asy, using_CIM=using_cim)
+        np.random.seed(3)
+        ora_out = heads_oracle.cim_layer_forward(
+            s_cls.numpy(), s_det.numpy(), labels.numpy(), iou, asy, p_seed=0.1, cls_thr=cls_thr,
+            iou_thr=iou_thr, con_thr=0.85, anti_noise_sampling=anti, using_cim=using_cim)
+        pre = name + "/"
+        out[pre + "cls"] = s_cls.numpy()
+        out[pre + "det"] = s_det.numpy()
+        out[pre + "labels"] = labels.numpy()
+        out[pre + "iou_u16"] = u16(iou)
+        out[pre + "asy_u16"] = u16(asy)
+        out[pre + "params"] = np.array([0.1, cls_thr, iou_thr, 0.85, float(anti), float(using_cim), 3.0])
+        if ref_out[0] is None:
+            assert ora_out[0] is None, name
+            out[pre + "none"] = np.int64(1)
+            print(f"{name}: reference returned (None, None, None)")
+            continue
+        pl, pi, lw = (t.numpy() for t in ref_out)
+        assert pi.dtype == np.float16
+        assert np.array_equal(pl, ora_out[0]), name
+        assert np.array_equal(u16(pi), u16(ora_out[1])), name
+        assert np.array_equal(lw.view(np.uint32), ora_out[2].view(np.uint32)), name
+        # also pin the mining stage on its own (CIM_label / MIST_label outputs)
+        if using_cim:
+            _, g_lab, g_w, g_idx, flag = layer.CIM_label(s_cls, s_det, rois[:, 1:], labels, t_iou, t_asy)
+            o_cls, o_w, o_flag, _ = heads_oracle.cim_label(s_cls.numpy(), s_det.numpy(), labels.numpy(),
+                                                           iou, asy, 0.1, cls_thr, 0.85)
+            assert np.array_equal(flag.numpy().reshape(-1), o_flag), name
+            out[pre + "asy_iou_flag"] = flag.numpy().reshape(-1)
+        else:
+            _, g_lab, g_w, g_idx = layer.MIST_label(s_cls * s_det, rois[:, 1:], labels, t_iou)
+            o_cls, o_w = heads_oracle.mist_label((s_cls * s_det).numpy(), labels.numpy(), iou, 0.1, cls_thr)
+        assert np.array_equal(g_idx.numpy(), o_cls >= 0), name
+        assert np.array_equal(g_lab.numpy().argmax(1) - 1, o_cls[o_cls >= 0]), name
+        assert np.array_equal(g_w.numpy(), o_w[o_cls >= 0]), name
+        if not save:
+            continue
+        out[pre + "gt_idxs"] = g_idx.numpy()
+        out[pre + "gt_class"] = (g_lab.numpy().argmax(1) - 1).astype(np.int64)
+        out[pre + "gt_weights"] = g_w.numpy()
+        out[pre + "pseudo_labels"] = pl
+        out[pre + "pseudo_iou_u16"] = u16(pi)
+        out[pre + "loss_weights"] = lw
+        print(f"{name}: mined {int(g_idx.sum())} pseudo GT, fg rows {int((pl[:, 1:].sum(1) > 0).sum())}, "
+              f"bg rows {int(pl[:, 0].sum())}, ignored {int((pl.sum(1) == 0).sum())}, "
+              f"NaN iou labels {int(np.isnan(pi.astype(np.float32)).sum())}")
+    if save:
+        np.savez_compressed(os.path.join(GOLD, "cim_layer.npz"), **out)
+
+
+def fuzz(ref_heads, ref_mu, n):
+    """Oracle-vs-reference on n random cases that are NOT stored (extra pinning)."""
+    rng = np.random.RandomState(99)
+    kinds = ["plain", "nan", "edges", "dups"]
+    for i in range(n):
+        r = int(rng.randint(40, 260))
+        c = 20 if rng.rand() < 0.7 else 80
+        thr = [(0.25, 0.5), (0.35, 0.6), (0.45, 0.7)][i % 3]
+        name = f"fuzz{i}_{kinds[i % 4]}"
+        case = (name, r, c, int(rng.choice([32, 48])), 1000 + i, thr, bool(i % 2 == 0),
+                bool(i % 5 != 4), float(rng.choice([1.0, 4.0, 8.0])))
+        with contextlib.redirect_stdout(io.StringIO()):
+            make_heads_fixtures(ref_heads, ref_mu, [case], save=False)
+    print(f"fuzz: {n} random cases, oracle == reference bit for bit")
+
+
+def make_scoring_fixture(ref_heads):
+    out = {}
+    for name, r, c1, seed in [("voc", 77, 21, 5), ("coco", 33, 81, 6)]:
+        model, x, (p_cls, p_det, r_cls, r_iou) = scores_for(ref_heads, r, c1, seed, 3.0)
+        names = ["classifier", "detector"] + [f"refine_cls.{k}" for k in range(3)] + \
+                [f"refine_iou.{k}" for k in range(3)]
+        sd = model.state_dict()
+        w = np.stack([sd[n + ".weight"].numpy() for n in names])
+        b = np.stack([sd[n + ".bias"].numpy() for n in names])
+        ref = np.stack([p_cls.numpy(), p_det.numpy()] + [t.numpy() for t in r_cls] + [t.numpy() for t in r_iou])
+        o = heads_oracle.score_heads(x.numpy(), list(w), list(b))
+        ora = np.stack([o[0], o[1]] + o[2] + o[3])
+        err = np.abs(ora - ref).max() / np.abs(ref).max()
+        assert np.allclose(ora, ref, rtol=1e-5, atol=1e-8), err
+        out[name + "/x"] = x.numpy()
+        out[name + "/w"] = w
+        out[name + "/b"] = b
+        out[name + "/scores"] = ref
+        print(f"scoring {name}: oracle vs reference max rel err {err:.2e}")
+    np.savez_compressed(os.path.join(GOLD, "score_heads.npz"), **out)
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(4)
+    ref_heads, ref_mu = load_reference()
+    make_mask_fixture(ref_mu)
+    make_heads_fixtures(ref_heads, ref_mu)
+    make_scoring_fixture(ref_heads)
+    if "--fuzz" in sys.argv:
+        fuzz(ref_heads, ref_mu, int(sys.argv[sys.argv.index("--fuzz") + 1]))
+    print("golden fixtures written to", GOLD)
+
+
+if __name__ == "__main__":
+    main()
