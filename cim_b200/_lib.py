@@ -1,0 +1,96 @@
+"""ctypes binding of libcimhead.so (the C ABI declared in include/cimhead.h).
+
+There is no CPU or PyTorch fallback anywhere in this package: if the shared library has not
+been built, or a tensor is not on a CUDA device, the call raises.
+Build with `python -c "import __graft_entry__ as g; g.build()"` or `make -C cim_b200/csrc`.
+"""
+import ctypes as C
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcimhead.so")
+ABI_VERSION = 1
+MAX_LAYERS = 4
+
+_lock = threading.Lock()
+_lib = None
+
+
+class MineParams(C.Structure):
+    """cim_mine_params of include/cimhead.h (field order and types must match)."""
+    _fields_ = [
+        ("n_img", C.c_int), ("R", C.c_int), ("C", C.c_int), ("C1", C.c_int), ("n_layers", C.c_int),
+        ("det_cols", C.c_int), ("gt_cap", C.c_int), ("mode", C.c_int), ("keep_count", C.c_int),
+        ("big_thr", C.c_float), ("con_thr", C.c_float),
+        ("cls_thr", C.c_float * MAX_LAYERS), ("iou_thr", C.c_float * MAX_LAYERS),
+    ]
+
+
+_P, _I, _F, _SZ, _I64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_int64
+_SIGNATURES = {
+    "cim_abi_version": (C.c_int, []),
+    "cim_error_string": (C.c_char_p, [_I]),
+    "cim_roi_align_workspace_bytes": (_SZ, [_I]),
+    "cim_roi_align_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P, _SZ, _P]),
+    "cim_roi_align_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P, _SZ, _P]),
+    "cim_roi_pool_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P]),
+    "cim_roi_pool_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "cim_mask_pack": (_I, [_P, _P, _I64, _I64, _I64, _P]),
+    "cim_mask_overlap_workspace_bytes": (_SZ, [_I, _I, _I64]),
+    "cim_mask_overlap": (_I, [_P, _I, _I, _I64, _P, _P, _P, _P, _P, _SZ, _P]),
+    "cim_score_heads_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
+    "cim_score_heads": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _SZ, _P]),
+    "cim_sizeof_mine_params": (_SZ, []),
+    "cim_mine_workspace_bytes": (_SZ, [C.POINTER(MineParams)]),
+    "cim_mine": (_I, [C.POINTER(MineParams), C.POINTER(_P), C.POINTER(_P), _P, _P, _P, _P, _P, _P, _P, _P,
+                      _P, _SZ, _P]),
+    "cim_assign": (_I, [C.POINTER(MineParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib():
+    """The loaded library; raises (loudly) if it has not been built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} is missing: the CUDA extension has not been built and this package "
+                        "has no fallback path.  Run `make -C cim_b200/csrc` (needs nvcc, sm_100a).")
+                handle = C.CDLL(LIB_PATH)
+                for name, (res, args) in _SIGNATURES.items():
+                    fn = getattr(handle, name)          # AttributeError if the symbol is missing
+                    fn.restype, fn.argtypes = res, args
+                if handle.cim_abi_version() != ABI_VERSION:
+                    raise RuntimeError("libcimhead.so ABI version mismatch; rebuild it")
+                if handle.cim_sizeof_mine_params() != C.sizeof(MineParams):
+                    raise RuntimeError("cim_mine_params layout mismatch between cimhead.h and _lib.py")
+                _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().cim_error_string(rc).decode()
+        raise RuntimeError(f"{what} failed with code {rc}: {msg}")
+
+
+def stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def require_cuda(t, name, dtype=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: cim_b200 has no CPU path")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    return t

@@ -1,0 +1,192 @@
+// mask_overlap.cu -- pairwise mask-proposal IoU and containment maps for sm_100a.
+//
+// Replaces lib/utils/mask_utils.py:6-18 (mask_iou) and :20-32 (mask_asymmetric_iou) of the
+// reference as driven by tools/pre/create_cob_iou.py:43-48 / create_cob_asy_iou.py:43-51
+// (N^2 pairs, two cupy reductions each, float16 cast, pickled, re-loaded every training step
+// at lib/modeling/model_builder.py:148-156).
+//
+//   inter[i,j] = |m_i & m_j|         exact integer
+//   iou[i,j]   = fp16( fp32(inter) / fp32(area_i + area_j - inter) )
+//   asy[i,j]   = fp16( fp32(inter) / fp32(area_j) )                  0/0 -> NaN like numpy
+//
+// The reference divides in float64 and stores into float32 before the float16 cast; for integer
+// operands below 2^24 the float64 quotient can never sit close enough to a float32 rounding
+// boundary for the double rounding to matter, so one IEEE fp32 division gives the same float32
+// (tests/test_oracle_masks.py checks this exhaustively for small counts).  The fp32 -> fp16 step
+// is kept as a second rounding exactly as in the reference.
+//
+// Kernels in this file:
+//   mask_pack_kernel      byte masks -> bit masks (32 pixels per word), HBM-bound streaming
+//   mask_area_kernel      per-mask popcount
+//   mask_overlap_popc     64x64 output tile per CTA over bit-packed rows: AND + POPC, only the
+//                         upper triangle of tiles is computed, the mirror tile is written from
+//                         the same counts (inter is symmetric, asy is not)
+#include "common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------- pack
+__device__ __forceinline__ uint32_t nibble_of(uint32_t four_bytes) {
+    // 0xFF per non-zero byte, keep bit i of byte i, add the bytes up in the top byte
+    uint32_t m = __vcmpne4(four_bytes, 0u) & 0x08040201u;
+    return (m * 0x01010101u) >> 24;
+}
+
+__global__ void mask_pack_kernel(const uint8_t *__restrict__ masks, uint32_t *__restrict__ packed,
+                                 long long n_masks, long long hw, long long words) {
+    const long long total = n_masks * words;
+    const bool vec = (hw % 16) == 0 && (((uintptr_t)masks) % 16) == 0;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long m = idx / words, w = idx - m * words;
+        const long long p0 = w * 32;
+        const uint8_t *src = masks + m * hw + p0;
+        uint32_t bits = 0;
+        if (vec && p0 + 32 <= hw) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4 *>(src));
+            const uint4 b = __ldg(reinterpret_cast<const uint4 *>(src) + 1);
+            bits = nibble_of(a.x) | (nibble_of(a.y) << 4) | (nibble_of(a.z) << 8) | (nibble_of(a.w) << 12) |
+                   (nibble_of(b.x) << 16) | (nibble_of(b.y) << 20) | (nibble_of(b.z) << 24) |
+                   (nibble_of(b.w) << 28);
+        } else {
+            for (int i = 0; i < 32; ++i)
+                if (p0 + i < hw && src[i] != 0) bits |= 1u << i;
+        }
+        packed[idx] = bits;
+    }
+}
+
+// ---------------------------------------------------------------------------------------- area
+__global__ void mask_area_kernel(const uint32_t *__restrict__ packed, int32_t *__restrict__ area,
+                                 long long n_masks, long long words) {
+    const long long m = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (m >= n_masks) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t *row = packed + m * words;
+    int s = 0;
+    for (long long w = lane; w < words; w += 32) s += __popc(__ldg(row + w));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) area[m] = s;
+}
+
+// --------------------------------------------------------------------------------- popc overlap
+constexpr int TS = 64;      // output tile side
+constexpr int KC = 32;      // words per k-chunk
+constexpr int KP = KC + 1;  // padded smem pitch
+
+__device__ __forceinline__ void write_pair(int32_t *inter, __half *iou, __half *asy, size_t idx, int I,
+                                           int a_row, int a_col) {
+    const float fi = (float)I;
+    if (inter) inter[idx] = I;
+    iou[idx] = __float2half_rn(__fdiv_rn(fi, (float)(a_row + a_col - I)));
+    asy[idx] = __float2half_rn(__fdiv_rn(fi, (float)a_col));
+}
+
+__global__ void __launch_bounds__(256)
+mask_overlap_popc_kernel(const uint32_t *__restrict__ packed, const int32_t *__restrict__ area_all,
+                         int n, long long words, int32_t *__restrict__ inter_all, __half *__restrict__ iou_all,
+                         __half *__restrict__ asy_all) {
+    __shared__ uint32_t As[TS][KP];
+    __shared__ uint32_t Bs[TS][KP];
+    const int img = blockIdx.y;
+    // linear id -> (ti, tj) with ti <= tj
+    const int nt = (n + TS - 1) / TS;
+    int ti = 0, rem = blockIdx.x;
+    while (rem >= nt - ti) { rem -= nt - ti; ++ti; }
+    const int tj = ti + rem;
+
+    const uint32_t *base = packed + (size_t)img * n * words;
+    const int32_t *area = area_all + (size_t)img * n;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    int acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0;
+
+    for (long long k0 = 0; k0 < words; k0 += KC) {
+        // 64 rows x 32 words per operand, 256 threads: 8 words each, coalesced along k
+#pragma unroll
+        for (int it = 0; it < (TS * KC) / 256; ++it) {
+            const int e = it * 256 + tid, row = e / KC, kk = e % KC;
+            const long long kw = k0 + kk;
+            const int ra = ti * TS + row, rb = tj * TS + row;
+            As[row][kk] = (ra < n && kw < words) ? __ldg(base + (size_t)ra * words + kw) : 0u;
+            Bs[row][kk] = (rb < n && kw < words) ? __ldg(base + (size_t)rb * words + kw) : 0u;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < KC; ++kk) {
+            uint32_t a[4], b[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) a[r] = As[ty + 16 * r][kk];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) b[c] = Bs[tx + 16 * c][kk];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] += __popc(a[r] & b[c]);
+        }
+        __syncthreads();
+    }
+
+    int32_t *inter = inter_all ? inter_all + (size_t)img * n * n : nullptr;
+    __half *iou = iou_all + (size_t)img * n * n;
+    __half *asy = asy_all + (size_t)img * n * n;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = ti * TS + ty + 16 * r;
+        if (i >= n) continue;
+        const int ai = area[i];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int j = tj * TS + tx + 16 * c;
+            if (j >= n) continue;
+            const int aj = area[j];
+            write_pair(inter, iou, asy, (size_t)i * n + j, acc[r][c], ai, aj);
+            if (ti != tj) write_pair(inter, iou, asy, (size_t)j * n + i, acc[r][c], aj, ai);
+        }
+    }
+}
+
+}  // namespace
+
+CIM_API int cim_mask_pack(const uint8_t *masks, uint32_t *packed, int64_t n_masks, int64_t hw, int64_t words,
+                          cim_stream_t stream) {
+    if (!masks || !packed || n_masks < 0 || hw <= 0 || words * 32 < hw) return CIM_ERR_ARG;
+    if (n_masks == 0) return CIM_OK;
+    const long long total = n_masks * words;
+    const int blocks = (int)min((long long)cim_num_sms() * 16, (total + 255) / 256);
+    mask_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(masks, packed, n_masks, hw, words);
+    return cim_launch_status();
+}
+
+CIM_API size_t cim_mask_overlap_workspace_bytes(int n_img, int n, int64_t words) {
+    (void)words;
+    return sizeof(int32_t) * (size_t)(n_img > 0 ? n_img : 0) * (size_t)(n > 0 ? n : 0) + 256;
+}
+
+CIM_API int cim_mask_overlap(const uint32_t *packed, int n_img, int n, int64_t words, int32_t *inter,
+                             int32_t *area, void *iou_f16, void *asy_f16, void *workspace, size_t ws_bytes,
+                             cim_stream_t stream) {
+    if (!packed || !iou_f16 || !asy_f16 || n_img < 0 || n < 0 || words <= 0) return CIM_ERR_ARG;
+    if (words * 32 >= (1LL << 24)) return CIM_ERR_SHAPE;      // counts must stay exact in fp32
+    if (n_img == 0 || n == 0) return CIM_OK;
+    if (n_img > 65535) return CIM_ERR_SHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!area) {
+        if (!workspace || ws_bytes < cim_mask_overlap_workspace_bytes(n_img, n, words)) return CIM_ERR_WORKSPACE;
+        area = reinterpret_cast<int32_t *>(workspace);
+    }
+    const long long n_masks = (long long)n_img * n;
+    mask_area_kernel<<<(unsigned)((n_masks + 7) / 8), 256, 0, st>>>(packed, area, n_masks, words);
+    int rc = cim_launch_status();
+    if (rc) return rc;
+    const int nt = (n + TS - 1) / TS;
+    dim3 grid((unsigned)(nt * (nt + 1) / 2), (unsigned)n_img);
+    mask_overlap_popc_kernel<<<grid, 256, 0, st>>>(packed, area, n, words, inter,
+                                                   reinterpret_cast<__half *>(iou_f16),
+                                                   reinterpret_cast<__half *>(asy_f16));
+    return cim_launch_status();
+}

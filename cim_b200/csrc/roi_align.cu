@@ -1,0 +1,641 @@
+// roi_align.cu -- RoIAlign forward / backward for sm_100a.
+//
+// Replaces mmcv.ops.RoIAlign at lib/modeling/model_builder.py:230-231 of the reference
+// (arithmetic: lib/modeling/roi_xfrom/roi_align/src/roi_align_kernel.cu:16-121 fwd,
+// :150-270 bwd, plus mmcv's `aligned` half-pixel shift).
+//
+// Design (DESIGN.md "RoIAlign"):
+//   1. roi_prep_kernel turns every ROI into a descriptor: per output bin and axis the first
+//      feature row/column touched, the number touched and the COLLAPSED bilinear weights
+//      (all samples of the bin folded into <= 8 taps per axis; the 2-D weight of a tap is the
+//      product of its row and column weight, already divided by the sample count).  It also
+//      checks that rois are grouped by image and records each image's ROI range.
+//   2. Tile kernels: a CTA keeps the [32 channels x H x W] feature (or gradient) tile of one
+//      image in shared memory (pitch odd => lane = channel is bank-conflict free) and sweeps
+//      the image's ROIs.
+//        forward : one warp per ROI, 7x7 outputs per lane staged in smem, written with one
+//                  6272-byte cp.async.bulk (UBLKCP) per (roi, 32 channels);
+//        backward: gradients of NBATCH ROIs arrive by cp.async.bulk + mbarrier; warp w owns
+//                  tile rows y == w (mod 8), so every tile address has exactly one writer and
+//                  ROIs are applied in index order: no atomics, bit-reproducible.
+//   3. Generic kernels (one thread per output element, sample by sample) take whatever the
+//      tile kernels cannot: other output sizes, feature maps too large for shared memory,
+//      bins wider than 8 taps, ROIs not grouped by image.
+#include "common.cuh"
+
+namespace {
+
+constexpr int PH = 7, PW = 7, NBIN = 49;
+constexpr int MAXT = 8;             // max collapsed taps per bin and axis in a descriptor
+constexpr int DESC_WORDS = 160;     // 640 B per ROI
+enum {
+    D_B = 0, D_FLAGY = 1, D_FLAGX = 2, D_TX = 3, D_Y0 = 4, D_Y1 = 5, D_XINC = 6,
+    D_YLO = 8, D_YN = 16, D_XLO = 24, D_XN = 32, D_WY = 40, D_WX = 96
+};
+constexpr int WS_HDR_BYTES = 256;   // word 0: "rois not grouped by image" flag
+constexpr int CH = 32;              // channels per tile (= lanes)
+constexpr int NW = 8;               // warps per tile CTA
+constexpr int STAGE_FLOATS = CH * NBIN;          // 1568 floats = 6272 B
+constexpr int NBATCH = 4;           // ROIs per backward staging batch
+
+struct RoiWs {
+    int *hdr;          // [64]
+    int *img_start;    // [B+1]
+    int *desc;         // [K][DESC_WORDS]
+};
+
+__host__ __device__ inline size_t ws_img_off() { return WS_HDR_BYTES; }
+__host__ __device__ inline size_t ws_desc_off(int B) {
+    size_t o = WS_HDR_BYTES + sizeof(int) * (size_t)(B + 1);
+    return (o + 15) & ~(size_t)15;
+}
+
+// ------------------------------------------------------------------------------------ prep
+// One sample coordinate, evaluated exactly like the reference expression
+//   start + p * bin + (s + .5f) * bin / grid          (roi_align_kernel.cu:103-108)
+// with every operation individually rounded (no FMA contraction), so that the integer
+// decisions (floor, border tests) agree with a plain C evaluation.
+__device__ __forceinline__ float sample_coord(float start, float bin, int p, int s, int grid) {
+    float a = __fadd_rn(start, __fmul_rn((float)p, bin));
+    float b = __fdiv_rn(__fmul_rn(__fadd_rn((float)s, .5f), bin), (float)grid);
+    return __fadd_rn(a, b);
+}
+
+__global__ void roi_prep_kernel(const float *__restrict__ rois, int K, int B, int H, int W,
+                                int oh, int ow, float scale, int sampling_ratio, int aligned,
+                                int *__restrict__ hdr, int *__restrict__ img_start,
+                                int *__restrict__ desc) {
+    int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    int k = gid >> 1, axis = gid & 1;          // axis 0 = y (rows), 1 = x (columns)
+    if (k >= K) return;
+    const float *r = rois + 5 * (size_t)k;
+    int *d = desc + (size_t)k * DESC_WORDS;
+    int b = (int)r[0];
+
+    if (axis == 0) {
+        d[D_B] = b;
+        // image ranges + grouping check (rois of one image must be contiguous, ascending)
+        int bprev = k > 0 ? (int)rois[5 * (size_t)(k - 1)] : -1;
+        if (k > 0 && b < bprev) atomicOr(hdr, 1);
+        int lo = max(bprev + 1, 0), hi = min(b, B);
+        if (k == 0) lo = 0;
+        for (int j = lo; j <= hi; ++j) img_start[j] = k;
+        if (k == K - 1)
+            for (int j = max(b + 1, 0); j <= B; ++j) img_start[j] = K;
+    }
+
+    const int nb = axis == 0 ? oh : ow;       // bins along this axis (7 on the tile path)
+    const int L = axis == 0 ? H : W;
+    const float off = aligned ? .5f : 0.f;
+    float c1 = __fsub_rn(__fmul_rn(r[1 + (axis == 0 ? 1 : 0)], scale), off);
+    float c2 = __fsub_rn(__fmul_rn(r[3 + (axis == 0 ? 1 : 0)], scale), off);
+    float ext = __fsub_rn(c2, c1);
+    if (!aligned) ext = fmaxf(ext, 1.f);
+    float bin = __fdiv_rn(ext, (float)nb);
+    int grid = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(__fdiv_rn(ext, (float)nb));
+
+    int flag = 0;
+    if (nb != 7 || grid > 64 || b < 0 || b >= B) flag = 1;
+
+    int lo_[7], n_[7];
+    float w_[7][MAXT];
+    int nmax = 0;
+    if (!flag) {
+        for (int p = 0; p < 7; ++p) {
+            int lo0 = -1, n = 0;
+            float w[MAXT];
+#pragma unroll
+            for (int i = 0; i < MAXT; ++i) w[i] = 0.f;
+            for (int s = 0; s < grid; ++s) {
+                float t = sample_coord(c1, bin, p, s, grid);
+                if (t < -1.f || t > (float)L) continue;
+                if (t <= 0.f) t = 0.f;
+                int l0 = (int)t, h0;
+                if (l0 >= L - 1) { h0 = l0 = L - 1; t = (float)l0; } else { h0 = l0 + 1; }
+                float fl = t - (float)l0, fh = 1.f - fl;
+                if (lo0 < 0) lo0 = l0;
+                int i0 = l0 - lo0, i1 = h0 - lo0;
+                if (i1 >= MAXT) { flag = 1; break; }
+                w[i0] += fh;
+                w[i1] += fl;
+                n = max(n, i1 + 1);
+            }
+            if (flag) break;
+            lo_[p] = lo0 < 0 ? 0 : lo0;
+            n_[p] = n;
+            nmax = max(nmax, n);
+            float g = (float)(grid > 0 ? grid : 1);
+#pragma unroll
+            for (int i = 0; i < MAXT; ++i) w_[p][i] = w[i] / g;
+        }
+    }
+
+    if (axis == 0) {
+        d[D_FLAGY] = flag;
+        int y0 = 1 << 30, y1 = 0;
+        for (int p = 0; p < 7; ++p) {
+            int lo = flag ? 0 : lo_[p], n = flag ? 0 : n_[p];
+            d[D_YLO + p] = lo;
+            d[D_YN + p] = n;
+            if (n > 0) { y0 = min(y0, lo); y1 = max(y1, lo + n); }
+            for (int i = 0; i < MAXT; ++i)
+                reinterpret_cast<float *>(d)[D_WY + p * MAXT + i] = flag ? 0.f : w_[p][i];
+        }
+        if (y1 == 0) y0 = 0;
+        d[D_Y0] = y0;
+        d[D_Y1] = y1;
+        d[D_YLO + 7] = 0;
+        d[D_YN + 7] = 0;
+    } else {
+        // tap class T in {2,3,4,6,8}: the x loops of the tile kernels are unrolled T times.
+        int T = nmax <= 2 ? 2 : nmax <= 3 ? 3 : nmax <= 4 ? 4 : nmax <= 6 ? 6 : 8;
+        if (W < T) flag = 1;
+        d[D_FLAGX] = flag;
+        d[D_TX] = T;
+        int inc = 1, prev = -1;
+        for (int p = 0; p < 7; ++p) {
+            int lo = flag ? 0 : lo_[p];
+            // shift the window left so that lo + T - 1 stays inside the row; the padding
+            // taps get weight 0 but must still address valid shared memory
+            int lo2 = min(lo, W - T);
+            if (lo2 < 0) lo2 = 0;
+            int sh = lo - lo2;
+            d[D_XLO + p] = lo2;
+            d[D_XN + p] = flag ? 0 : n_[p];
+            for (int i = 0; i < MAXT; ++i) {
+                int src = i - sh;
+                float v = (!flag && src >= 0 && src < MAXT) ? w_[p][src] : 0.f;
+                reinterpret_cast<float *>(d)[D_WX + p * MAXT + i] = v;
+            }
+            if (lo2 <= prev) inc = 0;
+            prev = lo2;
+        }
+        d[D_XINC] = inc;      // 1: window starts strictly increase -> taps of one l never alias
+        d[D_XLO + 7] = 0;
+        d[D_XN + 7] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------ tile: forward
+__device__ __forceinline__ void load_tile(float *tile, const float *__restrict__ src, int HW,
+                                          int pitch, int tid, int nthr) {
+    if ((HW & 3) == 0) {
+        const float4 *s4 = reinterpret_cast<const float4 *>(src);
+        int n4 = CH * HW / 4;
+        for (int e = tid; e < n4; e += nthr) {
+            float4 v = __ldg(s4 + e);
+            int idx = e * 4, c = idx / HW, p = idx - c * HW;
+            float *dst = tile + c * pitch + p;
+            dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+        }
+    } else {
+        for (int e = tid; e < CH * HW; e += nthr) {
+            int c = e / HW, p = e - c * HW;
+            tile[c * pitch + p] = __ldg(src + e);
+        }
+    }
+}
+
+template <int T>
+__device__ __forceinline__ void fwd_one_roi(const float *__restrict__ tile_c, int W,
+                                            const int *__restrict__ desc, int hdr,
+                                            float *__restrict__ stage_c, int lane) {
+    const unsigned full = 0xffffffffu;
+    float wx[PW][T];
+    int xo[PW];
+    const float *dwx = reinterpret_cast<const float *>(desc + D_WX);
+#pragma unroll
+    for (int pw = 0; pw < PW; ++pw) {
+        float4 a = __ldg(reinterpret_cast<const float4 *>(dwx + pw * MAXT));
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (T > 4) b = __ldg(reinterpret_cast<const float4 *>(dwx + pw * MAXT + 4));
+        float t8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int l = 0; l < T; ++l) wx[pw][l] = t8[l];
+        xo[pw] = __shfl_sync(full, hdr, D_XLO + pw);
+    }
+    // the 56 row weights live across the warp: lane i holds wy[i] and wy[32 + i]
+    const float *dwy = reinterpret_cast<const float *>(desc + D_WY);
+    float wyv0 = __ldg(dwy + lane);
+    float wyv1 = lane < 24 ? __ldg(dwy + 32 + lane) : 0.f;
+
+#pragma unroll 1
+    for (int ph = 0; ph < PH; ++ph) {
+        int ylo = __shfl_sync(full, hdr, D_YLO + ph);
+        int yn = __shfl_sync(full, hdr, D_YN + ph);
+        float acc[PW];
+#pragma unroll
+        for (int pw = 0; pw < PW; ++pw) acc[pw] = 0.f;
+        for (int k = 0; k < yn; ++k) {
+            int wi = ph * MAXT + k;
+            float wyk = __shfl_sync(full, wi < 32 ? wyv0 : wyv1, wi & 31);
+            const float *row = tile_c + (ylo + k) * W;
+#pragma unroll
+            for (int pw = 0; pw < PW; ++pw) {
+                float r = 0.f;
+#pragma unroll
+                for (int l = 0; l < T; ++l) r = fmaf(wx[pw][l], row[xo[pw] + l], r);
+                acc[pw] = fmaf(wyk, r, acc[pw]);
+            }
+        }
+#pragma unroll
+        for (int pw = 0; pw < PW; ++pw) stage_c[ph * PW + pw] = acc[pw];
+    }
+}
+
+__global__ void __launch_bounds__(NW * 32, 1)
+roi_align_fwd_tile_kernel(const float *__restrict__ feat, const int *__restrict__ hdr,
+                          const int *__restrict__ img_start, const int *__restrict__ descs,
+                          float *__restrict__ out, int B, int C, int H, int W, int pitch) {
+    extern __shared__ __align__(128) float smem[];
+    float *tile = smem;
+    float *stage = smem + (size_t)CH * pitch;
+    if (__ldg(hdr) != 0) return;              // rois not grouped by image: generic kernel runs
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int HW = H * W, nchunks = C / CH;
+    const int s0 = __ldg(img_start), sB = __ldg(img_start + B);
+    const long long U = (long long)nchunks * (sB - s0);     // (roi, chunk) units
+    long long u = U * blockIdx.x / gridDim.x;
+    const long long u_end = U * (blockIdx.x + 1) / gridDim.x;
+    float *stage_w = stage + warp * STAGE_FLOATS;
+    float *stage_c = stage_w + lane * NBIN;
+
+    int b = 0;
+    while (u < u_end) {
+        // locate the tile (image b, channel chunk ch) that unit u falls into
+        while (b < B && (long long)nchunks * (__ldg(img_start + b + 1) - s0) <= u) ++b;
+        const int is = __ldg(img_start + b), nroi = __ldg(img_start + b + 1) - is;
+        const long long base = (long long)nchunks * (is - s0);
+        const int ch = (int)((u - base) / nroi);
+        const int r0 = (int)((u - base) - (long long)ch * nroi);
+        const int r1 = (int)min((long long)nroi, r0 + (u_end - u));
+        const int c0 = ch * CH;
+
+        __syncthreads();                       // everyone is done with the previous tile
+        load_tile(tile, feat + ((size_t)b * C + c0) * HW, HW, pitch, tid, NW * 32);
+        __syncthreads();
+
+        const float *tile_c = tile + lane * pitch;
+        for (int r = r0 + warp; r < r1; r += NW) {
+            const int roi = is + r;
+            const int *desc = descs + (size_t)roi * DESC_WORDS;
+            const int h = __ldg(desc + lane);
+            const int flags = __shfl_sync(0xffffffffu, h, D_FLAGY) | __shfl_sync(0xffffffffu, h, D_FLAGX);
+            if (flags) continue;
+            if (lane == 0) bulk_wait_read<0>();   // previous bulk store has drained the stage
+            __syncwarp();
+            const int T = __shfl_sync(0xffffffffu, h, D_TX);
+            switch (T) {
+                case 2: fwd_one_roi<2>(tile_c, W, desc, h, stage_c, lane); break;
+                case 3: fwd_one_roi<3>(tile_c, W, desc, h, stage_c, lane); break;
+                case 4: fwd_one_roi<4>(tile_c, W, desc, h, stage_c, lane); break;
+                case 6: fwd_one_roi<6>(tile_c, W, desc, h, stage_c, lane); break;
+                default: fwd_one_roi<8>(tile_c, W, desc, h, stage_c, lane); break;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                bulk_s2g(out + ((size_t)roi * C + c0) * NBIN, stage_w, STAGE_FLOATS * 4);
+                bulk_commit();
+            }
+        }
+        u += r1 - r0;
+    }
+    if (lane == 0) bulk_wait_read<0>();
+}
+
+// ----------------------------------------------------------------------------- tile: backward
+template <int T, bool XINC>
+__device__ __forceinline__ void bwd_rows(float *__restrict__ tile_c, int W, const int *d,
+                                         const float *__restrict__ g, int y, int y1) {
+    float wx[PW][T];
+    int xo[PW], ylo[PH], yn[PH];
+    const float *dwx = reinterpret_cast<const float *>(d + D_WX);
+    const float *dwy = reinterpret_cast<const float *>(d + D_WY);
+    {
+        int4 a = *reinterpret_cast<const int4 *>(d + D_XLO), b = *reinterpret_cast<const int4 *>(d + D_XLO + 4);
+        xo[0] = a.x; xo[1] = a.y; xo[2] = a.z; xo[3] = a.w; xo[4] = b.x; xo[5] = b.y; xo[6] = b.z;
+        a = *reinterpret_cast<const int4 *>(d + D_YLO); b = *reinterpret_cast<const int4 *>(d + D_YLO + 4);
+        ylo[0] = a.x; ylo[1] = a.y; ylo[2] = a.z; ylo[3] = a.w; ylo[4] = b.x; ylo[5] = b.y; ylo[6] = b.z;
+        a = *reinterpret_cast<const int4 *>(d + D_YN); b = *reinterpret_cast<const int4 *>(d + D_YN + 4);
+        yn[0] = a.x; yn[1] = a.y; yn[2] = a.z; yn[3] = a.w; yn[4] = b.x; yn[5] = b.y; yn[6] = b.z;
+    }
+#pragma unroll
+    for (int pw = 0; pw < PW; ++pw) {
+        float4 a = *reinterpret_cast<const float4 *>(dwx + pw * MAXT);
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (T > 4) b = *reinterpret_cast<const float4 *>(dwx + pw * MAXT + 4);
+        float t8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int l = 0; l < T; ++l) wx[pw][l] = t8[l];
+    }
+    for (; y < y1; y += NW) {
+        float r[PW];
+#pragma unroll
+        for (int pw = 0; pw < PW; ++pw) r[pw] = 0.f;
+#pragma unroll
+        for (int ph = 0; ph < PH; ++ph) {
+            int dd = y - ylo[ph];
+            if (dd >= 0 && dd < yn[ph]) {
+                float w = dwy[ph * MAXT + dd];
+#pragma unroll
+                for (int pw = 0; pw < PW; ++pw) r[pw] = fmaf(w, g[ph * PW + pw], r[pw]);
+            }
+        }
+        float *row = tile_c + y * W;
+        if (XINC) {
+            // window starts strictly increase: the 7 taps of one l hit 7 distinct columns,
+            // so they can be loaded, updated and stored as a group
+#pragma unroll
+            for (int l = 0; l < T; ++l) {
+                float v[PW];
+#pragma unroll
+                for (int pw = 0; pw < PW; ++pw) v[pw] = row[xo[pw] + l];
+#pragma unroll
+                for (int pw = 0; pw < PW; ++pw) row[xo[pw] + l] = fmaf(wx[pw][l], r[pw], v[pw]);
+            }
+        } else {
+#pragma unroll
+            for (int pw = 0; pw < PW; ++pw)
+#pragma unroll
+                for (int l = 0; l < T; ++l) {
+                    volatile float *p = row + xo[pw] + l;
+                    *p = fmaf(wx[pw][l], r[pw], *p);
+                }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NW * 32, 1)
+roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restrict__ hdr,
+                          const int *__restrict__ img_start, const int *__restrict__ descs,
+                          float *__restrict__ grad_feat, int B, int C, int H, int W, int pitch) {
+    extern __shared__ __align__(128) float smem[];
+    float *tile = smem;
+    float *gbuf = smem + (size_t)CH * pitch;                          // [2][NBATCH][1568]
+    int *dbuf = reinterpret_cast<int *>(gbuf + 2 * NBATCH * STAGE_FLOATS);   // [2][NBATCH][160]
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(dbuf + 2 * NBATCH * DESC_WORDS);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int HW = H * W, nchunks = C / CH;
+    const int b = blockIdx.x / nchunks, c0 = (blockIdx.x % nchunks) * CH;
+
+    for (int e = tid; e < CH * pitch; e += NW * 32) tile[e] = 0.f;
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const int is = __ldg(img_start + b);
+    const int n = __ldg(hdr) != 0 ? 0 : __ldg(img_start + b + 1) - is;
+    const int nbatches = (n + NBATCH - 1) / NBATCH;
+
+    auto issue = [&](int bi) {
+        const int buf = bi & 1, first = bi * NBATCH, cnt = min(NBATCH, n - first);
+        mbar_expect_tx(&mbar[buf], (uint32_t)cnt * (STAGE_FLOATS * 4 + DESC_WORDS * 4));
+        for (int j = 0; j < cnt; ++j)
+            bulk_g2s(gbuf + (buf * NBATCH + j) * STAGE_FLOATS,
+                     grad_out + ((size_t)(is + first + j) * C + c0) * NBIN, STAGE_FLOATS * 4, &mbar[buf]);
+        bulk_g2s(dbuf + buf * NBATCH * DESC_WORDS, descs + (size_t)(is + first) * DESC_WORDS,
+                 (uint32_t)cnt * DESC_WORDS * 4, &mbar[buf]);
+    };
+    if (tid == 0 && nbatches > 0) issue(0);
+
+    float *tile_c = tile + lane * pitch;
+    for (int bi = 0; bi < nbatches; ++bi) {
+        const int buf = bi & 1;
+        if (tid == 0 && bi + 1 < nbatches) issue(bi + 1);   // its buffer was released by the
+                                                             // __syncthreads ending batch bi-1
+        mbar_wait(&mbar[buf], (bi >> 1) & 1);
+        const int cnt = min(NBATCH, n - bi * NBATCH);
+        for (int j = 0; j < cnt; ++j) {
+            const int *d = dbuf + (buf * NBATCH + j) * DESC_WORDS;
+            if (d[D_FLAGY] | d[D_FLAGX]) continue;
+            const int y0 = d[D_Y0], y1 = d[D_Y1];
+            int y = y0 + (((warp - y0) % NW) + NW) % NW;     // first row >= y0 this warp owns
+            if (y >= y1) continue;
+            const float *g = gbuf + (buf * NBATCH + j) * STAGE_FLOATS + lane * NBIN;
+            const int T = d[D_TX];
+            if (d[D_XINC]) {
+                switch (T) {
+                    case 2: bwd_rows<2, true>(tile_c, W, d, g, y, y1); break;
+                    case 3: bwd_rows<3, true>(tile_c, W, d, g, y, y1); break;
+                    case 4: bwd_rows<4, true>(tile_c, W, d, g, y, y1); break;
+                    case 6: bwd_rows<6, true>(tile_c, W, d, g, y, y1); break;
+                    default: bwd_rows<8, true>(tile_c, W, d, g, y, y1); break;
+                }
+            } else {
+                switch (T) {
+                    case 2: bwd_rows<2, false>(tile_c, W, d, g, y, y1); break;
+                    case 3: bwd_rows<3, false>(tile_c, W, d, g, y, y1); break;
+                    case 4: bwd_rows<4, false>(tile_c, W, d, g, y, y1); break;
+                    case 6: bwd_rows<6, false>(tile_c, W, d, g, y, y1); break;
+                    default: bwd_rows<8, false>(tile_c, W, d, g, y, y1); break;
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // every element of this (image, channel chunk) slab is written exactly once
+    float *dst = grad_feat + ((size_t)b * C + c0) * HW;
+    for (int e = tid; e < CH * HW; e += NW * 32) {
+        int c = e / HW, p = e - c * HW;
+        dst[e] = tile[c * pitch + p];
+    }
+}
+
+// ------------------------------------------------------------------------------- generic path
+struct Geom {
+    int b, gh, gw;
+    float ys, xs, bh, bw, count;
+};
+__device__ __forceinline__ Geom roi_geom(const float *__restrict__ r, float scale, int oh, int ow,
+                                         int sr, int aligned) {
+    Geom g;
+    const float off = aligned ? .5f : 0.f;
+    g.b = (int)r[0];
+    float x1 = __fsub_rn(__fmul_rn(r[1], scale), off), y1 = __fsub_rn(__fmul_rn(r[2], scale), off);
+    float x2 = __fsub_rn(__fmul_rn(r[3], scale), off), y2 = __fsub_rn(__fmul_rn(r[4], scale), off);
+    float rw = __fsub_rn(x2, x1), rh = __fsub_rn(y2, y1);
+    if (!aligned) { rw = fmaxf(rw, 1.f); rh = fmaxf(rh, 1.f); }
+    g.xs = x1; g.ys = y1;
+    g.bh = __fdiv_rn(rh, (float)oh);
+    g.bw = __fdiv_rn(rw, (float)ow);
+    g.gh = sr > 0 ? sr : (int)ceilf(__fdiv_rn(rh, (float)oh));
+    g.gw = sr > 0 ? sr : (int)ceilf(__fdiv_rn(rw, (float)ow));
+    float cnt = fmaxf((float)(g.gh * g.gw), 1.f);
+    g.count = cnt;
+    return g;
+}
+__device__ __forceinline__ bool corners(int H, int W, float y, float x, int &y0, int &y1, int &x0,
+                                        int &x1, float &w00, float &w01, float &w10, float &w11) {
+    if (y < -1.f || y > (float)H || x < -1.f || x > (float)W) return false;
+    if (y <= 0.f) y = 0.f;
+    if (x <= 0.f) x = 0.f;
+    y0 = (int)y; x0 = (int)x;
+    if (y0 >= H - 1) { y1 = y0 = H - 1; y = (float)y0; } else { y1 = y0 + 1; }
+    if (x0 >= W - 1) { x1 = x0 = W - 1; x = (float)x0; } else { x1 = x0 + 1; }
+    float ly = y - (float)y0, lx = x - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+    w00 = hy * hx; w01 = hy * lx; w10 = ly * hx; w11 = ly * lx;
+    return true;
+}
+
+// mode: 0 = every ROI; 1 = only ROIs the tile kernel skipped (flagged, or all if ungrouped)
+template <bool BWD>
+__global__ void roi_align_generic_kernel(const float *__restrict__ in, const float *__restrict__ rois,
+                                         float *__restrict__ outp, const int *__restrict__ hdr,
+                                         const int *__restrict__ descs, int mode, int B, int C, int H,
+                                         int W, int K, int oh, int ow, float scale, int sr, int aligned) {
+    const int k = blockIdx.x;
+    if (mode == 1 && __ldg(hdr) == 0) {
+        const int *d = descs + (size_t)k * DESC_WORDS;
+        if ((__ldg(d + D_FLAGY) | __ldg(d + D_FLAGX)) == 0) return;
+    }
+    const Geom g = roi_geom(rois + 5 * (size_t)k, scale, oh, ow, sr, aligned);
+    const int per_roi = C * oh * ow;
+    const bool valid_b = g.b >= 0 && g.b < B;
+    for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < per_roi; e += gridDim.y * blockDim.x) {
+        const int pw = e % ow, ph = (e / ow) % oh, c = e / (ow * oh);
+        const size_t oidx = (size_t)k * per_roi + e;
+        if (!valid_b) { if (!BWD) outp[oidx] = 0.f; continue; }
+        const size_t plane = ((size_t)g.b * C + c) * H * W;
+        float acc = 0.f;
+        const float top = BWD ? in[oidx] : 0.f;
+        for (int iy = 0; iy < g.gh; ++iy) {
+            const float y = sample_coord(g.ys, g.bh, ph, iy, g.gh);
+            for (int ix = 0; ix < g.gw; ++ix) {
+                const float x = sample_coord(g.xs, g.bw, pw, ix, g.gw);
+                int y0, y1, x0, x1; float a, b2, c2, d2;
+                if (!corners(H, W, y, x, y0, y1, x0, x1, a, b2, c2, d2)) continue;
+                if (BWD) {
+                    float *p = outp + plane;
+                    atomicAdd(p + y0 * W + x0, top * a / g.count);
+                    atomicAdd(p + y0 * W + x1, top * b2 / g.count);
+                    atomicAdd(p + y1 * W + x0, top * c2 / g.count);
+                    atomicAdd(p + y1 * W + x1, top * d2 / g.count);
+                } else {
+                    const float *p = in + plane;
+                    acc += a * __ldg(p + y0 * W + x0) + b2 * __ldg(p + y0 * W + x1) +
+                           c2 * __ldg(p + y1 * W + x0) + d2 * __ldg(p + y1 * W + x1);
+                }
+            }
+        }
+        if (!BWD) outp[oidx] = acc / g.count;
+    }
+}
+
+// ------------------------------------------------------------------------------------- host
+struct Plan {
+    bool tile;
+    int pitch;
+    size_t smem_fwd, smem_bwd;
+};
+static Plan make_plan(int C, int H, int W, int oh, int ow) {
+    Plan p{};
+    const int HW = H * W;
+    p.pitch = (HW & 1) ? HW : HW + 1;
+    p.smem_fwd = (size_t)CH * p.pitch * 4 + (size_t)NW * STAGE_FLOATS * 4;
+    p.smem_bwd = (size_t)CH * p.pitch * 4 + (size_t)2 * NBATCH * (STAGE_FLOATS + DESC_WORDS) * 4 + 16;
+    const size_t cap = (size_t)cim_max_smem_optin();
+    p.tile = oh == PH && ow == PW && (C % CH) == 0 && W >= MAXT && p.smem_fwd <= cap &&
+             p.smem_bwd <= cap && (((size_t)CH * p.pitch * 4) % 16 == 0);
+    return p;
+}
+
+static int check_args(const void *a, const void *rois, const void *c, int B, int C, int H, int W, int K,
+                      int oh, int ow, const void *ws, size_t ws_bytes) {
+    if (!a || !c || (K > 0 && !rois)) return CIM_ERR_ARG;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || K < 0 || oh <= 0 || ow <= 0) return CIM_ERR_ARG;
+    if ((long long)H * W > (1 << 24) || (long long)C * oh * ow > (1LL << 30)) return CIM_ERR_SHAPE;
+    if (!ws || ws_bytes < cim_roi_align_workspace_bytes(K)) return CIM_ERR_WORKSPACE;
+    if (!cim_aligned(ws, 16) || !cim_aligned(a, 16) || !cim_aligned(c, 16)) return CIM_ERR_ALIGN;
+    return CIM_OK;
+}
+
+static RoiWs carve(void *ws, int B) {
+    RoiWs w;
+    char *p = (char *)ws;
+    w.hdr = (int *)p;
+    w.img_start = (int *)(p + ws_img_off());
+    w.desc = (int *)(p + ws_desc_off(B));
+    return w;
+}
+
+static int run_prep(const float *rois, int B, int H, int W, int K, int oh, int ow, float scale, int sr,
+                    int aligned, const RoiWs &w, cudaStream_t st) {
+    cudaMemsetAsync(w.hdr, 0, WS_HDR_BYTES + sizeof(int) * (size_t)(B + 1), st);
+    if (K > 0) {
+        int threads = 128, blocks = (2 * K + threads - 1) / threads;
+        roi_prep_kernel<<<blocks, threads, 0, st>>>(rois, K, B, H, W, oh, ow, scale, sr, aligned, w.hdr,
+                                                    w.img_start, w.desc);
+    }
+    return cim_launch_status();
+}
+
+}  // namespace
+
+CIM_API size_t cim_roi_align_workspace_bytes(int K) {
+    // header + image ranges (up to 4096 images) + descriptors
+    return WS_HDR_BYTES + 4097 * sizeof(int) + 64 + (size_t)(K > 0 ? K : 0) * DESC_WORDS * 4;
+}
+
+CIM_API int cim_roi_align_fwd(const float *feat, const float *rois, float *out, int B, int C, int H, int W,
+                              int K, int oh, int ow, float scale, int sr, int aligned, void *ws,
+                              size_t ws_bytes, cim_stream_t stream) {
+    if (B > 4096) return CIM_ERR_SHAPE;
+    int rc = check_args(feat, rois, out, B, C, H, W, K, oh, ow, ws, ws_bytes);
+    if (rc) return rc;
+    if (K == 0) return CIM_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const Plan p = make_plan(C, H, W, oh, ow);
+    const RoiWs w = carve(ws, B);
+    const int per_roi = C * oh * ow;
+    dim3 ggrid((unsigned)K, (unsigned)min(64, (per_roi + 255) / 256));
+    if (!p.tile) {
+        roi_align_generic_kernel<false><<<ggrid, 256, 0, st>>>(feat, rois, out, nullptr, nullptr, 0, B, C, H, W,
+                                                               K, oh, ow, scale, sr, aligned);
+        return cim_launch_status();
+    }
+    if ((rc = run_prep(rois, B, H, W, K, oh, ow, scale, sr, aligned, w, st))) return rc;
+    cudaFuncSetAttribute(roi_align_fwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_fwd);
+    const long long units = (long long)(C / CH) * K;
+    const int grid = (int)min((long long)cim_num_sms(), units);
+    roi_align_fwd_tile_kernel<<<grid, NW * 32, p.smem_fwd, st>>>(feat, w.hdr, w.img_start, w.desc, out, B, C, H,
+                                                                  W, p.pitch);
+    if ((rc = cim_launch_status())) return rc;
+    roi_align_generic_kernel<false><<<ggrid, 256, 0, st>>>(feat, rois, out, w.hdr, w.desc, 1, B, C, H, W, K, oh,
+                                                           ow, scale, sr, aligned);
+    return cim_launch_status();
+}
+
+CIM_API int cim_roi_align_bwd(const float *grad_out, const float *rois, float *grad_feat, int B, int C, int H,
+                              int W, int K, int oh, int ow, float scale, int sr, int aligned, void *ws,
+                              size_t ws_bytes, cim_stream_t stream) {
+    if (B > 4096) return CIM_ERR_SHAPE;
+    int rc = check_args(grad_out, rois, grad_feat, B, C, H, W, K, oh, ow, ws, ws_bytes);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const Plan p = make_plan(C, H, W, oh, ow);
+    const RoiWs w = carve(ws, B);
+    const int per_roi = C * oh * ow;
+    dim3 ggrid((unsigned)max(K, 1), (unsigned)min(64, (per_roi + 255) / 256));
+    if (!p.tile || K == 0) {
+        cudaMemsetAsync(grad_feat, 0, sizeof(float) * (size_t)B * C * H * W, st);
+        if (K > 0)
+            roi_align_generic_kernel<true><<<ggrid, 256, 0, st>>>(grad_out, rois, grad_feat, nullptr, nullptr, 0,
+                                                                  B, C, H, W, K, oh, ow, scale, sr, aligned);
+        return cim_launch_status();
+    }
+    if ((rc = run_prep(rois, B, H, W, K, oh, ow, scale, sr, aligned, w, st))) return rc;
+    cudaFuncSetAttribute(roi_align_bwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bwd);
+    roi_align_bwd_tile_kernel<<<B * (C / CH), NW * 32, p.smem_bwd, st>>>(grad_out, w.hdr, w.img_start, w.desc,
+                                                                          grad_feat, B, C, H, W, p.pitch);
+    if ((rc = cim_launch_status())) return rc;
+    roi_align_generic_kernel<true><<<ggrid, 256, 0, st>>>(grad_out, rois, grad_feat, w.hdr, w.desc, 1, B, C, H, W,
+                                                          K, oh, ow, scale, sr, aligned);
+    return cim_launch_status();
+}

@@ -1,0 +1,251 @@
+"""CIM heads with the reference's Python surface, backed by libcimhead.so.
+
+Mirrors lib/modeling/heads.py of the reference:
+  * cls_iou_model (heads.py:168-219): same constructor, same parameter names (`classifier`,
+    `detector`, `refine_cls.k`, `refine_iou.k`, so reference checkpoints load), same forward
+    return convention; the 2+2K linear layers + softmax / column-softmax / sigmoid run as one
+    fused scoring call (cim_score_heads).
+  * CIM_layer (heads.py:222-503): same constructor and forward signature, same return
+    convention ((pseudo_labels, pseudo_iou_labels, loss_weights) or (None, None, None));
+    mining, mask NMS and assignment run in cim_mine / cim_assign.
+  * mine_and_assign(): the batched entry point (all images x all refinement layers in one go)
+    that model_builder.py:170-187 would call instead of looping over CIM_layer objects.
+
+Anti-noise sampling (heads.py:440-473) draws from numpy's GLOBAL RandomState on the host in the
+reference.  To reproduce its pseudo labels bit for bit the same np.random.choice calls are made
+here, in the same order (image-major, then layer, then ascending class), between the two device
+phases; that costs one small device->host->device hop per step.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+from torch import nn
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+
+
+# ------------------------------------------------------------------------------- scoring
+class ScoreHeadsFunction(Function):
+    """scores[h] = act_h(x @ W_h^T + b_h) for the 2+2K heads; see cim_score_heads in cimhead.h."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, n_img, k):
+        _lib.require_cuda(x, "seg_feature", torch.float32)
+        _lib.require_cuda(weight, "weight", torch.float32)
+        _lib.require_cuda(bias, "bias", torch.float32)
+        x, weight, bias = x.contiguous(), weight.contiguous(), bias.contiguous()
+        m, d = x.shape
+        nh, c1, _ = weight.shape
+        if m % n_img:
+            raise ValueError("rows of seg_feature must be n_img * R")
+        L = _lib.lib()
+        with torch.cuda.device(x.device):
+            scores = torch.empty((nh, m, c1), dtype=torch.float32, device=x.device)
+            ws = torch.empty(L.cim_score_heads_workspace_bytes(n_img, m // n_img, c1, k), dtype=torch.uint8,
+                             device=x.device)
+            rc = L.cim_score_heads(_lib.ptr(x), _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(scores), n_img,
+                                   m // n_img, d, c1, k, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(x.device))
+        _lib.check(rc, "cim_score_heads")
+        ctx.save_for_backward(x, weight, scores)
+        ctx.cfg = (n_img, k)
+        return scores
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad):
+        # Backward of the activations + the three GEMMs with torch ops (plumbing for now; the
+        # forward above is the path BASELINE.json names).
+        x, weight, s = ctx.saved_tensors
+        n_img, k = ctx.cfg
+        nh, m, c1 = s.shape
+        dz = torch.empty_like(s)
+        for h in range(nh):
+            g, y = grad[h], s[h]
+            if h == 1:                                   # softmax over the proposals of each image
+                g3, y3 = g.view(n_img, -1, c1), y.view(n_img, -1, c1)
+                dz[h] = (y3 * (g3 - (g3 * y3).sum(1, keepdim=True))).view(m, c1)
+            elif h < 2 + k:                              # softmax over classes
+                dz[h] = y * (g - (g * y).sum(-1, keepdim=True))
+            else:                                        # sigmoid
+                dz[h] = g * y * (1 - y)
+        dz2 = dz.permute(1, 0, 2).reshape(m, nh * c1)
+        w2 = weight.reshape(nh * c1, -1)
+        gx = dz2 @ w2 if ctx.needs_input_grad[0] else None
+        gw = (dz2.t() @ x).view_as(weight) if ctx.needs_input_grad[1] else None
+        gb = dz.sum(1) if ctx.needs_input_grad[2] else None
+        return gx, gw, gb, None, None
+
+
+class cls_iou_model(nn.Module):
+    """heads.cls_iou_model(dim_in, dim_out, refine_times, class_agnostic=False) (heads.py:168-219)."""
+
+    def __init__(self, dim_in, dim_out, refine_times, class_agnostic=False):
+        super().__init__()
+        self.classifier = nn.Linear(dim_in, dim_out)
+        self.detector = nn.Linear(dim_in, dim_out)
+        self.refine_cls = nn.ModuleList([nn.Linear(dim_in, dim_out) for _ in range(refine_times)])
+        self.refine_iou = nn.ModuleList([nn.Linear(dim_in, dim_out) for _ in range(refine_times)])
+
+    def detectron_weight_mapping(self):
+        return {name: name for name, _ in self.named_parameters()}, []
+
+    def _stacked(self):
+        layers = [self.classifier, self.detector, *self.refine_cls, *self.refine_iou]
+        return torch.stack([l.weight for l in layers]), torch.stack([l.bias for l in layers])
+
+    def forward_batched(self, seg_feature, n_img=1):
+        """seg_feature [n_img*R, D] -> scores [2+2K, n_img*R, C1] (detector softmax per image)."""
+        if seg_feature.dim() == 4:
+            seg_feature = seg_feature.squeeze(3).squeeze(2)
+        weight, bias = self._stacked()
+        return ScoreHeadsFunction.apply(seg_feature, weight, bias, n_img, len(self.refine_cls))
+
+    def forward(self, seg_feature):
+        k = len(self.refine_cls)
+        s = self.forward_batched(seg_feature, 1)
+        return s[0], s[1], [s[2 + i] for i in range(k)], [s[2 + k + i] for i in range(k)]
+
+
+# ------------------------------------------------------------------- mining + assignment
+def _anti_noise_keep(gt_cls, gt_w, present):
+    """heads.py:451-466 on the host: per present class (ascending) with at least one pseudo GT,
+    np.random.choice(class_idx, size=n, replace=True, p=w / w.sum()) from the GLOBAL numpy RNG;
+    the unique draws survive."""
+    keep = np.ones(gt_cls.shape[0], dtype=np.uint8)
+    for c in present:
+        class_idx = np.nonzero(gt_cls == c)[0]
+        if len(class_idx) == 0:
+            continue
+        prob = gt_w[class_idx]
+        drawn = np.random.choice(class_idx, size=len(class_idx), replace=True, p=prob / prob.sum())
+        keep[class_idx] = 0
+        keep[np.unique(drawn)] = 1
+    return keep
+
+
+def mine_and_assign(cls_scores, det_scores, labels, iou_map, asy_iou_map, cls_thr, iou_thr, p_seed=0.1,
+                    con_thr=0.85, anti_noise_sampling=True, using_cim=True):
+    """All images x all refinement layers of CIM_layer.forward in two device phases.
+
+    cls_scores / det_scores: lists (one per layer) of [n_img, R, C1] float32 CUDA tensors -- layer 0
+    gets (predict_cls, predict_det), layer l > 0 gets (ref_cls[l-1], ref_iou[l-1])
+    (model_builder.py:176-187).  labels [n_img, C]; iou_map / asy_iou_map [n_img, R, R] float16.
+    cls_thr / iou_thr: per-layer thresholds (model_builder.py:90-93).
+    Returns dict(pseudo_labels [L,n_img,R,C+1] f32, pseudo_iou_labels [L,n_img,R] f16,
+    loss_weights [L,n_img,R] f32, valid [L,n_img] uint8 (0 where the reference returns None),
+    asy_iou_flag [n_img,R] uint8, gt_count [L,n_img] int32)."""
+    n_layers = len(cls_scores)
+    if n_layers < 1 or n_layers > _lib.MAX_LAYERS:
+        raise ValueError(f"1..{_lib.MAX_LAYERS} layers supported")
+    cls_scores = [_lib.require_cuda(t, "cls_scores", torch.float32).contiguous() for t in cls_scores]
+    dev = cls_scores[0].device
+    n_img, R, c1 = cls_scores[0].shape
+    labels = _lib.require_cuda(labels, "labels").to(torch.float32).reshape(n_img, -1).contiguous()
+    n_cls = labels.shape[1]
+    if using_cim:
+        if asy_iou_map is None:
+            raise ValueError("CIM_label needs asy_iou_map (heads.py:383)")
+        det_scores = [_lib.require_cuda(t, "det_scores", torch.float32).contiguous() for t in det_scores]
+    elif det_scores is not None and det_scores[0] is not None:
+        det_scores = [_lib.require_cuda(t, "det_scores", torch.float32).contiguous() for t in det_scores]
+    else:
+        det_scores = None
+    if iou_map is None:
+        raise NotImplementedError("the box-IoU fallback of heads.py:287-289,375-377 is not on the CIM path")
+    iou_map = _lib.require_cuda(iou_map, "iou_map", torch.float16).contiguous()
+    if asy_iou_map is not None:
+        asy_iou_map = _lib.require_cuda(asy_iou_map, "asy_iou_map", torch.float16).contiguous()
+    if tuple(iou_map.shape) != (n_img, R, R):
+        raise ValueError("iou_map must be [n_img, R, R]")
+
+    p = _lib.MineParams()
+    p.n_img, p.R, p.C, p.C1, p.n_layers = n_img, R, n_cls, c1, n_layers
+    p.det_cols = det_scores[0].shape[-1] if det_scores is not None else c1
+    p.gt_cap = R
+    p.mode = 0 if using_cim else 1
+    p.keep_count = int(np.ceil(p_seed * R))                      # heads.py:332
+    p.big_thr = float(np.float32(0.9 * R))                       # heads.py:338
+    p.con_thr = con_thr
+    for l in range(n_layers):
+        p.cls_thr[l], p.iou_thr[l] = cls_thr[l], iou_thr[l]
+
+    L = _lib.lib()
+    PtrArr = C.c_void_p * n_layers
+    cls_ptrs = PtrArr(*[t.data_ptr() for t in cls_scores])
+    det_ptrs = PtrArr(*[t.data_ptr() for t in det_scores]) if det_scores is not None else None
+    with torch.cuda.device(dev):
+        st = _lib.stream_ptr(dev)
+        ws = torch.empty(max(L.cim_mine_workspace_bytes(C.byref(p)), 256), dtype=torch.uint8, device=dev)
+        gt_count = torch.empty((n_layers, n_img), dtype=torch.int32, device=dev)
+        gt_rows = torch.empty((n_layers, n_img, R), dtype=torch.int32, device=dev)
+        gt_class = torch.empty((n_layers, n_img, R), dtype=torch.int32, device=dev)
+        gt_weight = torch.empty((n_layers, n_img, R), dtype=torch.float32, device=dev)
+        asy_flag = torch.ones((n_img, R), dtype=torch.uint8, device=dev)
+        rc = L.cim_mine(C.byref(p), cls_ptrs, det_ptrs, _lib.ptr(labels), _lib.ptr(iou_map),
+                        _lib.ptr(asy_iou_map), _lib.ptr(gt_count), _lib.ptr(gt_rows), _lib.ptr(gt_class),
+                        _lib.ptr(gt_weight), _lib.ptr(asy_flag), _lib.ptr(ws), ws.numel(), st)
+        _lib.check(rc, "cim_mine")
+
+        gt_keep = None
+        if anti_noise_sampling:
+            counts = gt_count.cpu().numpy()                      # sync point (heads.py:453,457 sync too)
+            cap = int(counts.max()) if counts.size else 0
+            keep_host = np.ones((n_layers, n_img, R), dtype=np.uint8)
+            if cap > 0:
+                cls_h = gt_class[:, :, :cap].cpu().numpy()
+                w_h = gt_weight[:, :, :cap].cpu().numpy()
+                lab_h = labels.cpu().numpy()
+                for b in range(n_img):                            # the reference runs image by image,
+                    present = np.nonzero(lab_h[b])[0]             # layer by layer (model_builder.py:170)
+                    for l in range(n_layers):
+                        g = int(counts[l, b])
+                        if g:
+                            keep_host[l, b, :g] = _anti_noise_keep(cls_h[l, b, :g], w_h[l, b, :g], present)
+            gt_keep = torch.from_numpy(keep_host).to(dev, non_blocking=False)
+
+        pseudo_labels = torch.empty((n_layers, n_img, R, n_cls + 1), dtype=torch.float32, device=dev)
+        pseudo_iou = torch.empty((n_layers, n_img, R), dtype=torch.float16, device=dev)
+        loss_weights = torch.empty((n_layers, n_img, R), dtype=torch.float32, device=dev)
+        valid = torch.empty((n_layers, n_img), dtype=torch.uint8, device=dev)
+        rc = L.cim_assign(C.byref(p), _lib.ptr(iou_map), _lib.ptr(gt_count), _lib.ptr(gt_rows),
+                          _lib.ptr(gt_class), _lib.ptr(gt_weight), _lib.ptr(gt_keep), _lib.ptr(pseudo_labels),
+                          _lib.ptr(pseudo_iou), _lib.ptr(loss_weights), _lib.ptr(valid), st)
+        _lib.check(rc, "cim_assign")
+    return dict(pseudo_labels=pseudo_labels, pseudo_iou_labels=pseudo_iou, loss_weights=loss_weights,
+                valid=valid, asy_iou_flag=asy_flag, gt_count=gt_count, gt_rows=gt_rows, gt_class=gt_class,
+                gt_weight=gt_weight, gt_keep=gt_keep)
+
+
+class CIM_layer(nn.Module):
+    """heads.CIM_layer(p_seed=0.1, cls_thr=0.25, iou_thr=0.5, con_thr=0.85, Anti_noise_sampling=True)
+    (heads.py:222-235); forward signature and return convention of heads.py:409-503."""
+
+    def __init__(self, p_seed=0.1, cls_thr=0.25, iou_thr=0.5, con_thr=0.85, Anti_noise_sampling=True):
+        super().__init__()
+        self.p_seed = p_seed
+        self.cls_thr = cls_thr
+        self.nms_thr = cls_thr          # heads.py:227
+        self.iou_thr = iou_thr
+        self.con_thr = con_thr
+        self.Anti_noise_sampling = Anti_noise_sampling
+
+    @torch.no_grad()
+    def forward(self, predict_cls, predict_det, rois, labels, iou_map=None, asy_iou_map=None, using_CIM=True):
+        # rois only feed gt_boxes in the reference, which nothing downstream reads when maps are given
+        out = mine_and_assign([predict_cls.unsqueeze(0)],
+                              [predict_det.unsqueeze(0)] if predict_det is not None else None,
+                              labels.reshape(1, -1), iou_map.unsqueeze(0) if iou_map is not None else None,
+                              asy_iou_map.unsqueeze(0) if asy_iou_map is not None else None,
+                              [self.cls_thr], [self.iou_thr], p_seed=self.p_seed, con_thr=self.con_thr,
+                              anti_noise_sampling=self.Anti_noise_sampling, using_cim=using_CIM)
+        if int(out["valid"][0, 0].item()) == 0:                   # heads.py:429-430
+            return None, None, None
+        return out["pseudo_labels"][0, 0], out["pseudo_iou_labels"][0, 0], out["loss_weights"][0, 0]
+
+
+def refine_scores(ref_cls_score, ref_iou_score):
+    """testing_function of lib/modeling/model_builder.py:60-68: per head (cls * iou)[:, 1:]."""
+    return [(c * i)[:, 1:] for c, i in zip(ref_cls_score, ref_iou_score)]

@@ -1,0 +1,152 @@
+/*
+ * cimhead.h -- C ABI of libcimhead.so: the B200 (sm_100a) implementation of the CIM
+ * proposal-level hot path (ZechengLi19/CIM).
+ *
+ * Every entry point takes plain device pointers, sizes and scalars plus the CUDA stream to
+ * launch on.  Contract:
+ *   - the caller owns all memory (inputs, outputs, workspaces); the library never allocates,
+ *     frees, retains or synchronises; it only enqueues kernels on `stream`;
+ *   - re-entrant, no global mutable state (the reference calls its ops from one Python thread
+ *     per device, lib/nn/parallel/parallel_apply.py:37-59);
+ *   - return value: 0 on success, a negative CIM_ERR_* for bad arguments, or the positive
+ *     cudaError_t of a failed launch.  Nothing is printed, nothing calls exit() (the legacy
+ *     launchers do: lib/modeling/roi_xfrom/roi_align/src/roi_align_kernel.cu:135-139);
+ *   - there is no CPU path.
+ *
+ * Each declaration cites the reference interface it replaces.
+ */
+#ifndef CIMHEAD_H
+#define CIMHEAD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st *cim_stream_t;   /* == cudaStream_t */
+
+#define CIM_ABI_VERSION 1
+
+enum {
+    CIM_OK = 0,
+    CIM_ERR_ARG = -1,          /* null pointer / negative size / bad enum            */
+    CIM_ERR_SHAPE = -2,        /* shape outside what the kernels support             */
+    CIM_ERR_WORKSPACE = -3,    /* workspace missing or too small                     */
+    CIM_ERR_ALIGN = -4         /* pointer not aligned as documented                  */
+};
+
+int cim_abi_version(void);
+/* Static string for a return code of this library (negative: CIM_ERR_*, positive: CUDA). */
+const char *cim_error_string(int code);
+
+/* ------------------------------------------------------------------ ROI operators
+ * Replace mmcv.ops.RoIAlign / RoIPool as imported by lib/ops/__init__.py:6 and called at
+ * lib/modeling/model_builder.py:227-231 (`RoIAlign(resolution, spatial_scale,
+ * sampling_ratio)(feat, rois)`); arithmetic = lib/modeling/roi_xfrom/roi_align/src/
+ * roi_align_kernel.cu:16-121 (fwd) / :150-270 (bwd) plus mmcv's `aligned` half-pixel shift.
+ *   feat      [B,C,H,W] fp32 contiguous        rois [K,5] fp32 (batch_idx,x1,y1,x2,y2)
+ *   out       [K,C,oh,ow] fp32                 grad_feat [B,C,H,W] fp32 (fully overwritten)
+ * sampling_ratio <= 0 means adaptive: ceil(roi_extent / bins) samples per bin and axis.
+ * workspace: cim_roi_align_workspace_bytes(K) bytes, 16-byte aligned; contents are private.
+ * The forward and the backward of one autograd node may share the workspace. */
+size_t cim_roi_align_workspace_bytes(int K);
+int cim_roi_align_fwd(const float *feat, const float *rois, float *out,
+                      int B, int C, int H, int W, int K, int oh, int ow,
+                      float spatial_scale, int sampling_ratio, int aligned,
+                      void *workspace, size_t workspace_bytes, cim_stream_t stream);
+int cim_roi_align_bwd(const float *grad_out, const float *rois, float *grad_feat,
+                      int B, int C, int H, int W, int K, int oh, int ow,
+                      float spatial_scale, int sampling_ratio, int aligned,
+                      void *workspace, size_t workspace_bytes, cim_stream_t stream);
+
+/* RoIPool: lib/model/roi_pooling/src/roi_pooling_kernel.cu:24-93 (fwd), :128-203 (bwd).
+ * argmax [K,C,oh,ow] int32 = index inside the H*W plane, -1 for an empty bin. */
+int cim_roi_pool_fwd(const float *feat, const float *rois, float *out, int32_t *argmax,
+                     int B, int C, int H, int W, int K, int oh, int ow,
+                     float spatial_scale, cim_stream_t stream);
+int cim_roi_pool_bwd(const float *grad_out, const int32_t *argmax, const float *rois,
+                     float *grad_feat, int B, int C, int H, int W, int K, int oh, int ow,
+                     cim_stream_t stream);
+
+/* ------------------------------------------------------------------ mask overlap maps
+ * Replace lib/utils/mask_utils.py:6-18 (mask_iou) and :20-32 (mask_asymmetric_iou) as driven
+ * column by column and cast to float16 by tools/pre/create_cob_iou.py:43-48 and
+ * create_cob_asy_iou.py:43-51, and the per-step pickle loads that consume them
+ * (lib/modeling/model_builder.py:148-156).
+ *
+ * cim_mask_pack: byte masks [n_masks, hw] (any non-zero = inside) -> bit masks
+ *   [n_masks, words] uint32, bit (p & 31) of word (p >> 5) = pixel p; words >= ceil(hw/32),
+ *   padding bits are written as 0.
+ * cim_mask_overlap: for each of n_img images with n masks each (packed [n_img, n, words]):
+ *   inter [n_img,n,n] int32 (optional, may be NULL), area [n_img,n] int32 (optional),
+ *   iou  [n_img,n,n] fp16: inter / (area_i + area_j - inter)
+ *   asy  [n_img,n,n] fp16: inter / area_j                       (0/0 -> NaN, as the reference)
+ *   both computed as fp32 round-to-nearest division then fp32->fp16 round-to-nearest. */
+int cim_mask_pack(const uint8_t *masks, uint32_t *packed, int64_t n_masks, int64_t hw,
+                  int64_t words, cim_stream_t stream);
+size_t cim_mask_overlap_workspace_bytes(int n_img, int n, int64_t words);
+int cim_mask_overlap(const uint32_t *packed, int n_img, int n, int64_t words,
+                     int32_t *inter, int32_t *area, void *iou_f16, void *asy_f16,
+                     void *workspace, size_t workspace_bytes, cim_stream_t stream);
+
+/* ------------------------------------------------------------------ scoring heads
+ * Replace heads.cls_iou_model.forward (lib/modeling/heads.py:194-219): n_heads = 2 + 2*K
+ * linear layers over the same features, ordered [classifier, detector, refine_cls.0..K-1,
+ * refine_iou.0..K-1], followed by softmax over classes (classifier, refine_cls), softmax over
+ * the PROPOSALS of each image (detector, heads.py:203) and sigmoid (refine_iou).
+ *   x [n_img*R, D] fp32; weight [n_heads, C1, D]; bias [n_heads, C1];
+ *   scores [n_heads, n_img*R, C1] fp32.  workspace: cim_score_heads_workspace_bytes(). */
+size_t cim_score_heads_workspace_bytes(int n_img, int R, int C1, int K);
+int cim_score_heads(const float *x, const float *weight, const float *bias, float *scores,
+                    int n_img, int R, int D, int C1, int K,
+                    void *workspace, size_t workspace_bytes, cim_stream_t stream);
+
+/* ------------------------------------------------------------------ CIM mining + assignment
+ * Replace heads.CIM_layer (lib/modeling/heads.py:222-503) for n_img images x n_layers
+ * refinement layers in one go.  Layer l reads cls[l] / det[l] (device pointers, each
+ * [n_img, R, C1 or C]); the background column is dropped when C1 == C + 1 (heads.py:327-328).
+ * All float16 threshold tests are made in float16 against float16(thr), as torch does.
+ *
+ * Limits: R <= 10240, keep_count <= 1024, n_layers <= 4.  Scores are assumed finite and >= 0
+ * (they are softmax / sigmoid outputs).
+ *
+ * Phase 1 (cim_mine): seeds = top keep_count by class score, greedy mask NMS on iou_map,
+ *   containment mining on asy_map (mode 0 = CIM_label heads.py:318-407, mode 1 = MIST_label
+ *   heads.py:260-316), per-proposal arbitration between classes.  Outputs, per (layer, image):
+ *     gt_count [L, n_img] int32; gt_rows / gt_class / gt_weight [L, n_img, gt_cap]
+ *     (ascending proposal index, the order boolean-mask indexing gives at heads.py:405);
+ *     asy_flag [n_img, R] uint8 (asy_iou_flag, heads.py:338).
+ * Between the phases the host may drop pseudo GTs (anti-noise sampling, heads.py:440-473,
+ *   which draws from numpy's global RNG) by writing gt_keep [L, n_img, gt_cap] uint8.
+ * Phase 2 (cim_assign): heads.py:475-501 -> pseudo_labels [L, n_img, R, C+1] fp32,
+ *   pseudo_iou [L, n_img, R] fp16, loss_weights [L, n_img, R] fp32, valid [L, n_img] uint8
+ *   (0 where the reference returns (None, None, None), heads.py:429-430). */
+typedef struct {
+    int n_img, R, C, C1, n_layers;   /* C foreground classes; C1 = row length of cls/det   */
+    int det_cols;                    /* row length of det[l]: C1, C or 1 (class-agnostic)  */
+    int gt_cap;                      /* capacity of the gt_* lists per (layer, image)      */
+    int mode;                        /* 0 = CIM_label, 1 = MIST_label                      */
+    int keep_count;                  /* int(ceil(p_seed * R)), heads.py:332, host-evaluated */
+    float big_thr;                   /* float32(0.9 * R), heads.py:338, host-evaluated      */
+    float con_thr;
+    float cls_thr[4], iou_thr[4];    /* per layer; nms_thr == cls_thr (heads.py:227)       */
+} cim_mine_params;
+
+size_t cim_sizeof_mine_params(void);   /* lets a binding verify its struct layout */
+size_t cim_mine_workspace_bytes(const cim_mine_params *p);
+int cim_mine(const cim_mine_params *p, const float *const *cls, const float *const *det,
+             const float *labels /* [n_img, C] */, const void *iou_f16, const void *asy_f16,
+             int32_t *gt_count, int32_t *gt_rows, int32_t *gt_class, float *gt_weight,
+             uint8_t *asy_flag, void *workspace, size_t workspace_bytes, cim_stream_t stream);
+int cim_assign(const cim_mine_params *p, const void *iou_f16,
+               const int32_t *gt_count, const int32_t *gt_rows, const int32_t *gt_class,
+               const float *gt_weight, const uint8_t *gt_keep /* may be NULL = keep all */,
+               float *pseudo_labels, void *pseudo_iou_f16, float *loss_weights, uint8_t *valid,
+               cim_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CIMHEAD_H */

@@ -1,0 +1,43 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def golden_cim():
+    return np.load(os.path.join(GOLDEN, "cim_layer.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_masks():
+    return np.load(os.path.join(GOLDEN, "mask_overlap.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_scores():
+    return np.load(os.path.join(GOLDEN, "score_heads.npz"))
+
+
+def cim_case_names(npz):
+    return sorted({k.split("/")[0] for k in npz.files})

@@ -1,0 +1,96 @@
+"""mask_pack / mask_overlap kernels against the reference-generated fixture and the oracle:
+integer intersection counts and the fp16 maps are compared bit for bit."""
+import numpy as np
+import pytest
+import torch
+
+from cim_b200 import mask_ops, synth
+from oracle import mask_oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def u16(t):
+    return t.cpu().numpy().view(np.uint16)
+
+
+def check_against_oracle(masks_cpu):
+    n = masks_cpu.shape[0]
+    packed = mask_ops.mask_pack(masks_cpu.to(DEV))
+    iou, asy, inter, area = mask_ops.mask_overlap(packed, return_counts=True)
+    o_inter, o_area = mask_oracle.overlap_counts(masks_cpu.numpy())
+    np.testing.assert_array_equal(inter.cpu().numpy(), o_inter)
+    np.testing.assert_array_equal(area.cpu().numpy(), o_area)
+    o_iou, o_asy = mask_oracle.maps_from_counts(o_inter, o_area)
+    np.testing.assert_array_equal(u16(iou), o_iou.view(np.uint16))
+    np.testing.assert_array_equal(u16(asy), o_asy.view(np.uint16))
+    assert iou.shape == (n, n) and iou.dtype == torch.float16
+
+
+def test_reference_fixture_bit_exact(golden_masks):
+    hw = int(golden_masks["hw"])
+    masks = np.unpackbits(golden_masks["masks_bits"], axis=1, bitorder="little")[:, :hw]
+    t = torch.from_numpy(masks).view(-1, 64, 64)
+    packed = mask_ops.mask_pack(t.to(DEV))
+    # the packed layout is little-endian bit order: identical bytes to the fixture's packbits
+    np.testing.assert_array_equal(packed.cpu().numpy().view(np.uint8).reshape(len(masks), -1),
+                                  golden_masks["masks_bits"])
+    iou, asy = mask_ops.mask_overlap(packed)
+    np.testing.assert_array_equal(u16(iou), golden_masks["iou_u16"])       # includes NaN entries
+    np.testing.assert_array_equal(u16(asy), golden_masks["asy_u16"])
+
+
+@pytest.mark.parametrize("n,h,w", [(130, 64, 64), (65, 37, 50), (1, 8, 8), (200, 96, 96), (64, 5, 5)])
+def test_random_proposals_and_ragged_shapes(n, h, w):
+    if h == w and h in (64, 96):      # nested synthetic proposals
+        masks = synth.rasterize(synth.proposal_params(n, h, n))
+    else:                              # unstructured masks, hw not a multiple of 32
+        masks = (torch.rand(n, h, w, generator=torch.Generator().manual_seed(n)) < 0.4).to(torch.uint8)
+    masks = masks.contiguous()
+    if n > 8:
+        masks[3] = 0                 # empty mask -> NaN
+        masks[4] = 1                 # full mask
+        masks[6] = masks[5]          # duplicates -> IoU exactly 1
+        masks[7] = masks[7] * 255    # any non-zero byte counts as inside
+    check_against_oracle(masks)
+
+
+def test_bool_input_and_batched_images():
+    m = [synth.rasterize(synth.proposal_params(70, 64, 100 + b)) for b in range(3)]
+    batch = torch.stack(m).to(DEV)
+    packed = mask_ops.mask_pack(batch.bool())
+    assert packed.shape == (3, 70, 128)
+    iou, asy = mask_ops.mask_overlap(packed)
+    for b in range(3):
+        o_iou, o_asy = mask_oracle.mask_overlap_maps(m[b].numpy())
+        np.testing.assert_array_equal(u16(iou[b]), o_iou.view(np.uint16))
+        np.testing.assert_array_equal(u16(asy[b]), o_asy.view(np.uint16))
+
+
+def test_full_size_cfg2_properties():
+    """One image of BASELINE.json configs[1]: 2000 proposals, 512x512 masks."""
+    R = 2000
+    params = synth.proposal_params(R, 512, 1234)
+    masks = synth.rasterize(params, device=DEV)
+    packed = mask_ops.mask_pack(masks)
+    iou, asy, inter, area = mask_ops.mask_overlap(packed, return_counts=True)
+    assert torch.equal(area.long(), masks.view(R, -1).sum(1))
+    assert torch.equal(inter, inter.t())                                  # symmetric
+    assert torch.equal(inter.diagonal(), area)                             # |m & m| = |m|
+    assert bool((inter <= torch.minimum(area[:, None], area[None, :])).all())
+    assert bool((iou.diagonal() == 1).all())
+    # 24 random rows against exact integer counts computed independently with torch ops
+    rows = torch.randperm(R, generator=torch.Generator().manual_seed(0))[:24].to(DEV)
+    sub = masks[rows].view(24, -1).float()
+    want = torch.zeros(24, R, device=DEV)
+    flat = masks.view(R, -1)
+    for s in range(0, R, 250):
+        want[:, s:s + 250] = sub @ flat[s:s + 250].float().t()            # exact: counts < 2^24
+    assert torch.equal(inter[rows].float(), want)
+    o_iou, o_asy = mask_oracle.maps_from_counts(inter[rows].cpu().numpy()[:, rows.cpu().numpy()],
+                                                area[rows].cpu().numpy())
+    np.testing.assert_array_equal(u16(iou[rows][:, rows]), o_iou.view(np.uint16))
+    np.testing.assert_array_equal(u16(asy[rows][:, rows]), o_asy.view(np.uint16))
+    # containment really occurs in the synthetic hierarchy (heads.py:386 needs asy > 0.85)
+    assert int((asy > 0.85).sum().item()) > R

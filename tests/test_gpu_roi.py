@@ -1,0 +1,185 @@
+"""RoIAlign / RoIPool CUDA kernels (through the mmcv-style operator surface and the C ABI) against
+the oracle (oracle/roi_oracle.c), torchvision, and the reference's own vendored kernels
+(oracle/_ref, aligned=False).  Tolerance from BASELINE.json: 1e-5 relative in fp32."""
+import numpy as np
+import pytest
+import torch
+from torchvision.ops import roi_align as tv_roi_align
+
+from cim_b200 import ops, synth
+from oracle import roi_oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def close(got, want, rel=1e-5):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    scale = max(np.abs(want).max(), 1e-30)
+    err = np.abs(got - want).max() / scale
+    assert err <= rel, f"max err / max|ref| = {err:.3e}"
+
+
+def random_rois(seed, B, K, H, W, scale, wild=False, sort=True):
+    g = torch.Generator().manual_seed(seed)
+    b = torch.randint(0, B, (K,), generator=g).float()
+    if sort:
+        b = b.sort().values
+    sw, sh = W / scale, H / scale
+    x1 = torch.rand(K, generator=g) * sw * 0.8
+    y1 = torch.rand(K, generator=g) * sh * 0.8
+    w = torch.rand(K, generator=g) * sw * 0.6 + 0.5
+    h = torch.rand(K, generator=g) * sh * 0.6 + 0.5
+    if wild:
+        x1 -= sw * 0.3
+        y1 -= sh * 0.3
+        w[::7] = 0.01
+        h[::5] = 0.0
+        w[3::11] = sw * 3           # far wider than the map: > 8 taps per bin -> generic path
+    return torch.stack([b, x1, y1, x1 + w, y1 + h], 1)
+
+
+def run_both(feat, rois, scale, sr, aligned, out_size=7):
+    f = feat.to(DEV).requires_grad_(True)
+    r = rois.to(DEV)
+    out = ops.roi_align(f, r, out_size, scale, sr, "avg", aligned)
+    g = torch.randn(out.shape, generator=torch.Generator().manual_seed(77))
+    out.backward(g.to(DEV))
+    oh, ow = (out_size, out_size) if isinstance(out_size, int) else out_size
+    want = roi_oracle.roi_align_fwd(feat.numpy(), rois.numpy(), oh, ow, scale, sr, aligned)
+    want_g = roi_oracle.roi_align_bwd(g.numpy(), rois.numpy(), feat.shape, scale, sr, aligned)
+    return out.detach().cpu().numpy(), f.grad.cpu().numpy(), want, want_g
+
+
+@pytest.mark.parametrize("aligned", [True, False])
+@pytest.mark.parametrize("sr", [0, 2])
+@pytest.mark.parametrize("wild", [False, True])
+def test_tile_path_small(aligned, sr, wild):
+    feat = torch.randn(3, 64, 16, 20, generator=torch.Generator().manual_seed(1))
+    rois = random_rois(2, 3, 90, 16, 20, 0.25, wild)
+    out, gf, want, want_g = run_both(feat, rois, 0.25, sr, aligned)
+    close(out, want)
+    close(gf, want_g)
+
+
+def test_cfg1_resnet50_shape_against_oracle_and_torchvision():
+    """BASELINE.json configs[0]: R-50 VOC, one 512x512 image, 300 mask proposals."""
+    C, H, W, scale = synth.feature_shape("resnet50")
+    feat = torch.randn(1, C, H, W, generator=torch.Generator().manual_seed(1234))
+    rois = synth.rois_from_params(synth.proposal_params(300, 512, 1234))
+    out, gf, want, want_g = run_both(feat, rois, scale, 0, True)
+    close(out, want)
+    close(gf, want_g)
+    tv = tv_roi_align(feat, rois, (7, 7), scale, 0, True).numpy()
+    close(out, tv)
+
+
+@pytest.mark.parametrize("case", ["unsorted", "odd_channels", "out14", "out3x5", "big_map", "empty_image"])
+def test_generic_and_mixed_paths(case):
+    B, C, H, W, K, size, sort = 2, 32, 12, 12, 50, 7, True
+    if case == "unsorted":
+        sort = False
+    elif case == "odd_channels":
+        C = 5
+    elif case == "out14":
+        size = 14
+    elif case == "out3x5":
+        size = (3, 5)
+    elif case == "big_map":
+        H, W, C = 100, 120, 32          # 32 x 12000 floats do not fit in shared memory
+    feat = torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(5))
+    rois = random_rois(6, B, K, H, W, 0.5, wild=True, sort=sort)
+    if case == "empty_image":
+        rois[:, 0] = 1                   # image 0 has no ROI at all; its gradient slab must be zero
+    out, gf, want, want_g = run_both(feat, rois, 0.5, 0, True, size)
+    close(out, want)
+    close(gf, want_g)
+
+
+def test_no_rois():
+    feat = torch.randn(1, 32, 8, 8, device=DEV, requires_grad=True)
+    out = ops.RoIAlign(7, 0.5, 0)(feat, torch.zeros(0, 5, device=DEV))
+    assert out.shape == (0, 32, 7, 7)
+    out.sum().backward()
+    assert feat.grad.abs().sum().item() == 0
+
+
+def test_against_reference_vendored_kernels_aligned_false():
+    """oracle/_ref = lib/modeling/roi_xfrom/roi_align/src/roi_align_kernel.cu compiled as is."""
+    if roi_oracle.ref_lib() is None:
+        pytest.skip("oracle/_ref was not built")
+    B, C, H, W, scale = 2, 256, 32, 32, 1.0 / 16
+    feat = torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(3)).to(DEV)
+    rois = torch.cat([synth.rois_from_params(synth.proposal_params(500, 512, 40 + b), b) for b in range(B)]).to(DEV)
+    mine = ops.roi_align(feat, rois, 7, scale, 0, "avg", False)
+    ref = roi_oracle.ref_roi_align_fwd(feat, rois, 7, 7, scale, 0)
+    close(mine.cpu().numpy(), ref.cpu().numpy())
+    g = torch.randn_like(mine)
+    f2 = feat.clone().requires_grad_(True)
+    ops.roi_align(f2, rois, 7, scale, 0, "avg", False).backward(g)
+    ref_g = roi_oracle.ref_roi_align_bwd(g, rois, feat.shape, scale, 0)
+    close(f2.grad.cpu().numpy(), ref_g.cpu().numpy())
+
+
+def test_backward_is_bit_reproducible():
+    C, H, W, scale = 64, 32, 32, 1.0 / 16
+    rois = synth.rois_from_params(synth.proposal_params(400, 512, 7)).to(DEV)
+    g = torch.randn(400, C, 7, 7, device=DEV)
+    outs = []
+    for _ in range(3):
+        f = torch.zeros(1, C, H, W, device=DEV, requires_grad=True)
+        ops.roi_align(f, rois, 7, scale).backward(g)
+        outs.append(f.grad.clone())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+def test_full_size_cfg2_linearity_and_adjoint():
+    """BASELINE.json configs[1] (8 images x 2000 proposals, R-50): size-independent properties.
+    RoIAlign is linear in the features and its backward is the adjoint: <A f, g> == <f, A^T g>."""
+    C, H, W, scale = synth.feature_shape("resnet50")
+    B, R = 8, 2000
+    rois = torch.cat([synth.rois_from_params(synth.proposal_params(R, 512, 1234 + b), b) for b in range(B)]).to(DEV)
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    f1 = torch.randn(B, C, H, W, device=DEV, generator=gen)
+    f2 = torch.randn(B, C, H, W, device=DEV, generator=gen)
+    o1 = ops.roi_align(f1, rois, 7, scale)
+    o2 = ops.roi_align(f2, rois, 7, scale)
+    o12 = ops.roi_align(2.5 * f1 + f2, rois, 7, scale)
+    lin = (o12 - (2.5 * o1 + o2)).abs().max().item() / o12.abs().max().item()
+    assert lin < 1e-5, lin
+    del o2, o12
+    g = torch.randn(o1.shape, device=DEV, generator=gen)
+    f = f1.clone().requires_grad_(True)
+    ops.roi_align(f, rois, 7, scale).backward(g)
+    lhs = (o1.double() * g.double()).sum().item()
+    rhs = (f1.double() * f.grad.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), abs(rhs), (o1.double().abs() * g.double().abs()).sum().item())
+    # spot-check 64 random ROIs of the full run against the oracle
+    idx = torch.randperm(B * R, generator=torch.Generator().manual_seed(1))[:64].sort().values
+    want = roi_oracle.roi_align_fwd(f1.cpu().numpy(), rois[idx.to(DEV)].cpu().numpy(), 7, 7, scale, 0, True)
+    close(o1[idx.to(DEV)].cpu().numpy(), want)
+
+
+def test_roi_pool_exact_and_backward():
+    feat = torch.randn(2, 48, 20, 24, generator=torch.Generator().manual_seed(8))
+    rois = random_rois(9, 2, 70, 20, 24, 0.25, wild=True)
+    f = feat.to(DEV).requires_grad_(True)
+    out = ops.RoIPool(7, 0.25)(f, rois.to(DEV))
+    want, arg = roi_oracle.roi_pool_fwd(feat.numpy(), rois.numpy(), 7, 7, 0.25)
+    np.testing.assert_array_equal(out.detach().cpu().numpy(), want)          # max is exact
+    g = torch.randn(out.shape, generator=torch.Generator().manual_seed(4))
+    out.backward(g.to(DEV))
+    close(f.grad.cpu().numpy(), roi_oracle.roi_pool_bwd(g.numpy(), arg, rois.numpy(), feat.shape))
+    if roi_oracle.ref_lib() is not None:                                      # the vendored kernel itself
+        ref_out, _ = roi_oracle.ref_roi_pool_fwd(feat.to(DEV), rois.to(DEV), 7, 7, 0.25)
+        np.testing.assert_array_equal(out.detach().cpu().numpy(), ref_out.cpu().numpy())
+
+
+def test_errors_are_raised_not_printed():
+    f = torch.zeros(1, 32, 8, 8, device=DEV)
+    with pytest.raises(ValueError):
+        ops.roi_align(f, torch.zeros(4, 4, device=DEV), 7)           # rois.size(1) != 5
+    with pytest.raises(TypeError):
+        ops.roi_align(f.half(), torch.zeros(4, 5, device=DEV), 7)
+    with pytest.raises(NotImplementedError):
+        ops.roi_align(f, torch.zeros(4, 5, device=DEV), 7, 1.0, 0, "max")

@@ -1,0 +1,83 @@
+"""Host-side logic that needs no GPU: the mmcv import shim, operator surface, anti-noise sampling
+protocol and the parameters evaluated on the host."""
+import importlib
+import inspect
+import sys
+
+import numpy as np
+import torch
+
+from cim_b200 import heads, integration, ops, synth
+from oracle import heads_oracle
+
+
+def test_mmcv_shim_resolves_reference_import_line():
+    integration.install_mmcv_shim()
+    for m in [k for k in sys.modules if k == "mmcv" or k.startswith("mmcv.")]:
+        del sys.modules[m]
+    mod = importlib.import_module("mmcv.ops")
+    # lib/ops/__init__.py:6 of the reference
+    from mmcv.ops import RoIPool, RoIAlign, roi_pool, roi_align, nms, soft_nms  # noqa: F401
+    assert mod.RoIAlign is ops.RoIAlign and mod.RoIPool is ops.RoIPool
+
+
+def test_roi_module_signatures_match_mmcv():
+    sig = inspect.signature(ops.RoIAlign.__init__)
+    assert list(sig.parameters)[1:] == ["output_size", "spatial_scale", "sampling_ratio", "pool_mode", "aligned",
+                                        "use_torchvision"]
+    assert sig.parameters["aligned"].default is True and sig.parameters["sampling_ratio"].default == 0
+    m = ops.RoIAlign(7, 1.0 / 16, 0)          # the positional call of model_builder.py:230-231
+    assert m.output_size == (7, 7) and m.aligned is True and not list(m.parameters())
+    p = ops.RoIPool(7, 1.0 / 16)              # model_builder.py:228
+    assert p.output_size == (7, 7)
+
+
+def test_heads_surface_matches_reference_names():
+    m = heads.cls_iou_model(32, 21, 3)
+    names = sorted(n for n, _ in m.named_parameters())
+    want = sorted([f"{p}.{s}" for p in ["classifier", "detector"] + [f"refine_cls.{k}" for k in range(3)] +
+                   [f"refine_iou.{k}" for k in range(3)] for s in ("weight", "bias")])
+    assert names == want
+    mapping, orphans = m.detectron_weight_mapping()
+    assert sorted(mapping) == want and orphans == []
+    layer = heads.CIM_layer(p_seed=0.1, cls_thr=0.35, iou_thr=0.6, Anti_noise_sampling=False)
+    assert layer.nms_thr == layer.cls_thr == 0.35 and layer.con_thr == 0.85
+    assert list(inspect.signature(layer.forward).parameters) == [
+        "predict_cls", "predict_det", "rois", "labels", "iou_map", "asy_iou_map", "using_CIM"]
+
+
+def test_anti_noise_sampling_consumes_rng_like_the_oracle():
+    rng = np.random.RandomState(5)
+    gt_cls = rng.randint(0, 4, 40)
+    gt_w = rng.rand(40).astype(np.float32)
+    labels = np.zeros(20, np.float32)
+    labels[[0, 2, 3, 7]] = 1                      # class 1 is mined but "absent": must be left alone
+    np.random.seed(3)
+    a = heads._anti_noise_keep(gt_cls, gt_w, np.nonzero(labels)[0])
+    after_a = np.random.rand()
+    np.random.seed(3)
+    b = heads_oracle.anti_noise_keep(gt_cls, gt_w, labels)
+    after_b = np.random.rand()
+    assert a.astype(bool).tolist() == b.tolist() and after_a == after_b
+    assert a[gt_cls == 1].all()
+
+
+def test_host_evaluated_parameters():
+    for r in (64, 300, 2000, 4000, 257):
+        assert int(np.ceil(0.1 * r)) == {64: 7, 300: 30, 2000: 200, 4000: 400, 257: 26}[r]
+    assert float(np.float32(0.9 * 300)) == 270.0
+
+
+def test_synth_is_deterministic_and_nested():
+    p = synth.proposal_params(130, size=64, seed=9)
+    m1, m2 = synth.rasterize(p), synth.rasterize(p, chunk=7)
+    assert torch.equal(m1, m2) and m1.dtype == torch.uint8 and m1.sum((1, 2)).min() > 0
+    rois = synth.rois_from_params(p)
+    ys, xs = torch.nonzero(m1[3], as_tuple=True)
+    assert rois[3].tolist() == [0, xs.min(), ys.min(), xs.max() + 1, ys.max() + 1]
+    # proposals 5 and 5+64 share a seed ellipse: one contains the other
+    a, b = m1[5].bool(), m1[69].bool()
+    inter = (a & b).sum()
+    assert inter == min(a.sum(), b.sum())
+    down = synth.rasterize(p, out_size=16)
+    assert torch.equal(down, m1[:, ::4, ::4])
