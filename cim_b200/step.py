@@ -1,0 +1,184 @@
+"""CIMHeadStep -- one CIM head step for a batch of images with every buffer pre-allocated.
+
+This is the call a training loop makes per iteration once the backbone has produced its feature
+map and MaskFuse its 4096-d proposal features; it covers the span of
+Generalized_RCNN.forward / backward of the reference that BASELINE.json names
+(lib/modeling/model_builder.py:136-204 + the RoIAlign backward inside loss.backward(),
+tools/train.py:436):
+
+    RoIAlign forward            model_builder.py:230-231
+    mask IoU + containment maps model_builder.py:148-156 (there: two pickle loads per step)
+    scoring heads               model_builder.py:143
+    3 x mining + assignment     model_builder.py:170-187
+    RoIAlign backward           autograd of the first line
+
+All device work goes through the C ABI (include/cimhead.h) on the current CUDA stream.  The one
+host hop is the anti-noise sampling (heads.py:451-466, numpy global RNG); it is overlapped with
+the RoIAlign kernels, which do not depend on it.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .heads import _anti_noise_keep
+
+#: kernels (not memsets / copies) libcimhead launches in one run(): roi_align fwd 3 + bwd 3,
+#: mask area + overlap 2, scoring 3, mining 3, assignment 1
+KERNELS_PER_STEP = 15
+
+
+class CIMHeadStep:
+    def __init__(self, n_img, n_props, n_classes, feat_channels, feat_h, feat_w, spatial_scale, mask_words,
+                 feat_dim=4096, refine_times=3, p_seed=0.1, step_rate=0.1, con_thr=0.85, anti_noise_sampling=True,
+                 max_present=4, device="cuda:0", sampling_ratio=0, aligned=True):
+        self.dev = torch.device(device)
+        self.n_img, self.R, self.C, self.K = n_img, n_props, n_classes, refine_times
+        self.Cf, self.H, self.W, self.scale = feat_channels, feat_h, feat_w, float(spatial_scale)
+        self.words, self.D = mask_words, feat_dim
+        self.sr, self.aligned = int(sampling_ratio), int(bool(aligned))
+        self.anti = anti_noise_sampling
+        self.L = _lib.lib()
+        R, C1, nh, k = n_props, n_classes + 1, 2 + 2 * refine_times, refine_times
+        dev = self.dev
+        e = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
+        with torch.cuda.device(dev):
+            self.roi_out = e((n_img * R, feat_channels, 7, 7), torch.float32)
+            self.grad_feat = e((n_img, feat_channels, feat_h, feat_w), torch.float32)
+            self.roi_ws = e((self.L.cim_roi_align_workspace_bytes(n_img * R),), torch.uint8)
+            self.iou = e((n_img, R, R), torch.float16)
+            self.asy = e((n_img, R, R), torch.float16)
+            self.area = e((n_img, R), torch.int32)
+            self.scores = e((nh, n_img * R, C1), torch.float32)
+            self.score_ws = e((max(256, self.L.cim_score_heads_workspace_bytes(n_img, R, C1, k)),), torch.uint8)
+            p = _lib.MineParams()
+            p.n_img, p.R, p.C, p.C1, p.n_layers = n_img, R, n_classes, C1, k
+            p.det_cols, p.gt_cap, p.mode = C1, R, 0
+            p.keep_count = int(np.ceil(p_seed * R))                 # heads.py:332
+            p.big_thr = float(np.float32(0.9 * R))                  # heads.py:338
+            p.con_thr = con_thr
+            for l in range(k):                                      # model_builder.py:90-93
+                p.cls_thr[l], p.iou_thr[l] = 0.25 + step_rate * l, 0.5 + step_rate * l
+            self.p = p
+            self.mine_ws = e((max(256, self.L.cim_mine_workspace_bytes(C.byref(p))),), torch.uint8)
+            self.gt_count = e((k, n_img), torch.int32)
+            self.gt_rows = e((k, n_img, R), torch.int32)
+            self.gt_class = e((k, n_img, R), torch.int32)
+            self.gt_weight = e((k, n_img, R), torch.float32)
+            self.asy_flag = e((n_img, R), torch.uint8)
+            self.gt_keep = torch.ones((k, n_img, R), dtype=torch.uint8, device=dev)
+            self.pseudo_labels = e((k, n_img, R, C1), torch.float32)
+            self.pseudo_iou = e((k, n_img, R), torch.float16)
+            self.loss_weights = e((k, n_img, R), torch.float32)
+            self.valid = e((k, n_img), torch.uint8)
+        # host side of the sampling hop: at most max_present * keep_count pseudo GTs per (layer, image)
+        self.cap = min(R, max_present * p.keep_count)
+        pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+        self.h_count = pin((k, n_img), torch.int32)
+        self.h_class = pin((k, n_img, self.cap), torch.int32)
+        self.h_weight = pin((k, n_img, self.cap), torch.float32)
+        self.h_keep = pin((k, n_img, self.cap), torch.uint8)
+        self.ev = torch.cuda.Event()
+        # layer l reads (cls, det) = (predict_cls, predict_det) for l = 0, else (ref_cls[l-1], ref_iou[l-1])
+        s = self.scores.view(nh, n_img, R, C1)
+        cls_src = [s[0]] + [s[2 + l - 1] for l in range(1, k)]
+        det_src = [s[1]] + [s[2 + k + l - 1] for l in range(1, k)]
+        PtrArr = C.c_void_p * k
+        self.cls_ptrs = PtrArr(*[t.data_ptr() for t in cls_src])
+        self.det_ptrs = PtrArr(*[t.data_ptr() for t in det_src])
+
+    # -------------------------------------------------------------------------------------
+    def run(self, feat, rois, grad_out, packed_masks, seg_x, weight, bias, labels, labels_host):
+        """feat [n_img,Cf,H,W] f32, rois [n_img*R,5] f32 grouped by image, grad_out [n_img*R,Cf,7,7]
+        f32, packed_masks [n_img,R,words] i32, seg_x [n_img*R,D] f32, weight [2+2K,C+1,D],
+        bias [2+2K,C+1], labels [n_img,C] f32 (+ the same on the host as a numpy array).
+        Results land in self.roi_out, grad_feat, iou, asy, scores, pseudo_labels, pseudo_iou,
+        loss_weights, valid."""
+        L, p, dev = self.L, self.p, self.dev
+        P, n_img, R, k = _lib.ptr, self.n_img, self.R, self.K
+        st = _lib.stream_ptr(dev)
+        ck = _lib.check
+        ck(L.cim_mask_overlap(P(packed_masks), n_img, R, self.words, None, P(self.area), P(self.iou), P(self.asy),
+                              None, 0, st), "cim_mask_overlap")
+        ck(L.cim_score_heads(P(seg_x), P(weight), P(bias), P(self.scores), n_img, R, self.D, self.C + 1, k,
+                             P(self.score_ws), self.score_ws.numel(), st), "cim_score_heads")
+        ck(L.cim_mine(C.byref(p), self.cls_ptrs, self.det_ptrs, P(labels), P(self.iou), P(self.asy),
+                      P(self.gt_count), P(self.gt_rows), P(self.gt_class), P(self.gt_weight), P(self.asy_flag),
+                      P(self.mine_ws), self.mine_ws.numel(), st), "cim_mine")
+        if self.anti:
+            self.h_count.copy_(self.gt_count, non_blocking=True)
+            self.h_class.copy_(self.gt_class[:, :, :self.cap], non_blocking=True)
+            self.h_weight.copy_(self.gt_weight[:, :, :self.cap], non_blocking=True)
+            self.ev.record(torch.cuda.current_stream(dev))
+        ck(L.cim_roi_align_fwd(P(feat), P(rois), P(self.roi_out), n_img, self.Cf, self.H, self.W, n_img * R, 7, 7,
+                               self.scale, self.sr, self.aligned, P(self.roi_ws), self.roi_ws.numel(), st),
+           "cim_roi_align_fwd")
+        ck(L.cim_roi_align_bwd(P(grad_out), P(rois), P(self.grad_feat), n_img, self.Cf, self.H, self.W, n_img * R,
+                               7, 7, self.scale, self.sr, self.aligned, P(self.roi_ws), self.roi_ws.numel(), st),
+           "cim_roi_align_bwd")
+        keep = None
+        if self.anti:
+            self.ev.synchronize()                               # mining is done; RoIAlign still runs
+            counts = self.h_count.numpy()
+            cls_h, w_h, keep_h = self.h_class.numpy(), self.h_weight.numpy(), self.h_keep.numpy()
+            keep_h[:] = 1
+            for b in range(n_img):                              # reference order: image, layer, class
+                present = np.nonzero(labels_host[b])[0]
+                for l in range(k):
+                    g = int(counts[l, b])
+                    if g > self.cap:
+                        raise RuntimeError("more pseudo GTs than max_present * keep_count; raise max_present")
+                    if g:
+                        keep_h[l, b, :g] = _anti_noise_keep(cls_h[l, b, :g], w_h[l, b, :g], present)
+            self.gt_keep[:, :, :self.cap].copy_(self.h_keep, non_blocking=True)
+            keep = self.gt_keep
+        ck(L.cim_assign(C.byref(p), P(self.iou), P(self.gt_count), P(self.gt_rows), P(self.gt_class),
+                        P(self.gt_weight), P(keep), P(self.pseudo_labels), P(self.pseudo_iou),
+                        P(self.loss_weights), P(self.valid), st), "cim_assign")
+        return self
+
+    # -------------------------------------------------------------------------------------
+    def alloc_host_io(self):
+        """Pinned host buffers of the end-to-end call: inputs that originate on the host in the
+        reference's pipeline (rois, labels: lib/roi_data/minibatch.py:45-61; proposal masks:
+        the COB .mat files of tools/pre) and the step's results."""
+        k, n_img, R, C1 = self.K, self.n_img, self.R, self.C + 1
+        pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+        self.hi_rois = pin((n_img * R, 5), torch.float32)
+        self.hi_labels = pin((n_img, self.C), torch.float32)
+        self.hi_masks = pin((n_img, R, self.words), torch.int32)
+        self.ho_labels = pin((k, n_img, R, C1), torch.float32)
+        self.ho_iou = pin((k, n_img, R), torch.float16)
+        self.ho_weights = pin((k, n_img, R), torch.float32)
+        self.ho_valid = pin((k, n_img), torch.uint8)
+        self.ho_checksum = pin((2,), torch.float32)
+        with torch.cuda.device(self.dev):
+            self.di_rois = torch.empty((n_img * R, 5), dtype=torch.float32, device=self.dev)
+            self.di_labels = torch.empty((n_img, self.C), dtype=torch.float32, device=self.dev)
+            self.di_masks = torch.empty((n_img, R, self.words), dtype=torch.int32, device=self.dev)
+            self.d_checksum = torch.empty((2,), dtype=torch.float32, device=self.dev)
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in (self.hi_rois, self.hi_labels, self.hi_masks))
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in
+                             (self.ho_labels, self.ho_iou, self.ho_weights, self.ho_valid, self.ho_checksum))
+        self.d2h_bytes += sum(t.numel() * t.element_size() for t in (self.h_count, self.h_class, self.h_weight))
+        self.h2d_bytes += self.h_keep.numel()
+
+    def run_host(self, feat, grad_out, seg_x, weight, bias):
+        """End-to-end step: host rois / labels / bit-packed masks -> device, the step, results ->
+        host.  feat / seg_x / grad_out are produced on the device by the backbone, MaskFuse and
+        autograd in the real pipeline and therefore stay device tensors."""
+        self.di_rois.copy_(self.hi_rois, non_blocking=True)
+        self.di_labels.copy_(self.hi_labels, non_blocking=True)
+        self.di_masks.copy_(self.hi_masks, non_blocking=True)
+        self.run(feat, self.di_rois, grad_out, self.di_masks, seg_x, weight, bias, self.di_labels,
+                 self.hi_labels.numpy())
+        self.d_checksum[0] = self.roi_out.view(-1)[::4099].sum()
+        self.d_checksum[1] = self.grad_feat.view(-1)[::127].sum()
+        self.ho_labels.copy_(self.pseudo_labels, non_blocking=True)
+        self.ho_iou.copy_(self.pseudo_iou, non_blocking=True)
+        self.ho_weights.copy_(self.loss_weights, non_blocking=True)
+        self.ho_valid.copy_(self.valid, non_blocking=True)
+        self.ho_checksum.copy_(self.d_checksum, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        return self

@@ -82,6 +82,7 @@ void oracle_roi_align_fwd(const float *feat, const float *rois, float *out,
                           float scale, int sampling_ratio, int aligned)
 {
     (void)B;
+#pragma omp parallel for schedule(dynamic, 4)
     for (int k = 0; k < K; ++k) {
         roi_geom g;
         roi_geometry(rois + 5 * k, scale, oh, ow, sampling_ratio, aligned, &g);
@@ -116,10 +117,12 @@ void oracle_roi_align_bwd(const float *grad_out, const float *rois, float *grad_
                           float scale, int sampling_ratio, int aligned)
 {
     memset(grad_feat, 0, sizeof(float) * (size_t)B * C * H * W);
-    for (int k = 0; k < K; ++k) {
-        roi_geom g;
-        roi_geometry(rois + 5 * k, scale, oh, ow, sampling_ratio, aligned, &g);
-        for (int c = 0; c < C; ++c) {
+    /* channel-outer: every thread owns whole planes, ROIs still accumulate in index order */
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int c = 0; c < C; ++c) {
+        for (int k = 0; k < K; ++k) {
+            roi_geom g;
+            roi_geometry(rois + 5 * k, scale, oh, ow, sampling_ratio, aligned, &g);
             float *plane = grad_feat + ((size_t)g.b * C + c) * H * W;
             const float *go = grad_out + ((size_t)k * C + c) * oh * ow;
             for (int ph = 0; ph < oh; ++ph)
@@ -206,6 +209,7 @@ void oracle_roi_pool_bwd(const float *grad_out, const int32_t *argmax, const flo
  * literal Python double loop of the reference would take hours. */
 void oracle_mask_counts(const uint8_t *masks, int N, int64_t HW, int32_t *inter, int32_t *area)
 {
+#pragma omp parallel for schedule(dynamic, 1)
     for (int i = 0; i < N; ++i) {
         const uint8_t *a = masks + (size_t)i * HW;
         for (int j = i; j < N; ++j) {

@@ -6,6 +6,7 @@ import torch
 
 from cim_b200 import mask_ops, synth
 from oracle import mask_oracle
+from conftest import assert_f16_bits_equal
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -23,8 +24,8 @@ def check_against_oracle(masks_cpu):
     np.testing.assert_array_equal(inter.cpu().numpy(), o_inter)
     np.testing.assert_array_equal(area.cpu().numpy(), o_area)
     o_iou, o_asy = mask_oracle.maps_from_counts(o_inter, o_area)
-    np.testing.assert_array_equal(u16(iou), o_iou.view(np.uint16))
-    np.testing.assert_array_equal(u16(asy), o_asy.view(np.uint16))
+    assert_f16_bits_equal(u16(iou), o_iou.view(np.uint16))
+    assert_f16_bits_equal(u16(asy), o_asy.view(np.uint16))
     assert iou.shape == (n, n) and iou.dtype == torch.float16
 
 
@@ -37,8 +38,8 @@ def test_reference_fixture_bit_exact(golden_masks):
     np.testing.assert_array_equal(packed.cpu().numpy().view(np.uint8).reshape(len(masks), -1),
                                   golden_masks["masks_bits"])
     iou, asy = mask_ops.mask_overlap(packed)
-    np.testing.assert_array_equal(u16(iou), golden_masks["iou_u16"])       # includes NaN entries
-    np.testing.assert_array_equal(u16(asy), golden_masks["asy_u16"])
+    assert_f16_bits_equal(u16(iou), golden_masks["iou_u16"])       # includes NaN entries
+    assert_f16_bits_equal(u16(asy), golden_masks["asy_u16"])
 
 
 @pytest.mark.parametrize("n,h,w", [(130, 64, 64), (65, 37, 50), (1, 8, 8), (200, 96, 96), (64, 5, 5)])
@@ -64,8 +65,8 @@ def test_bool_input_and_batched_images():
     iou, asy = mask_ops.mask_overlap(packed)
     for b in range(3):
         o_iou, o_asy = mask_oracle.mask_overlap_maps(m[b].numpy())
-        np.testing.assert_array_equal(u16(iou[b]), o_iou.view(np.uint16))
-        np.testing.assert_array_equal(u16(asy[b]), o_asy.view(np.uint16))
+        assert_f16_bits_equal(u16(iou[b]), o_iou.view(np.uint16))
+        assert_f16_bits_equal(u16(asy[b]), o_asy.view(np.uint16))
 
 
 def test_full_size_cfg2_properties():
@@ -90,7 +91,7 @@ def test_full_size_cfg2_properties():
     assert torch.equal(inter[rows].float(), want)
     o_iou, o_asy = mask_oracle.maps_from_counts(inter[rows].cpu().numpy()[:, rows.cpu().numpy()],
                                                 area[rows].cpu().numpy())
-    np.testing.assert_array_equal(u16(iou[rows][:, rows]), o_iou.view(np.uint16))
-    np.testing.assert_array_equal(u16(asy[rows][:, rows]), o_asy.view(np.uint16))
+    assert_f16_bits_equal(u16(iou[rows][:, rows]), o_iou.view(np.uint16))
+    assert_f16_bits_equal(u16(asy[rows][:, rows]), o_asy.view(np.uint16))
     # containment really occurs in the synthetic hierarchy (heads.py:386 needs asy > 0.85)
     assert int((asy > 0.85).sum().item()) > R
