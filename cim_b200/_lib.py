@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcimhead.so")
 ABI_VERSION = 1
 MAX_LAYERS = 4
+OVERLAP_ALGOS = {"auto": 0, "popc": 1, "tensor": 2}
 
 _lock = threading.Lock()
 _lib = None
@@ -41,6 +42,7 @@ _SIGNATURES = {
     "cim_mask_pack": (_I, [_P, _P, _I64, _I64, _I64, _P]),
     "cim_mask_overlap_workspace_bytes": (_SZ, [_I, _I, _I64]),
     "cim_mask_overlap": (_I, [_P, _I, _I, _I64, _P, _P, _P, _P, _P, _SZ, _P]),
+    "cim_mask_overlap_algo": (_I, [_P, _I, _I, _I64, _P, _P, _P, _P, _P, _SZ, _I, _P]),
     "cim_score_heads_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
     "cim_score_heads": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _SZ, _P]),
     "cim_sizeof_mine_params": (_SZ, []),

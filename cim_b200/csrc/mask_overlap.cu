@@ -23,6 +23,11 @@
 //                         the same counts (inter is symmetric, asy is not)
 #include "common.cuh"
 
+// mask_overlap_tc.cu: the tcgen05 (tensor core) path for large problems
+bool cim_mask_overlap_tc_eligible(int n, long long words);
+int cim_mask_overlap_tc_launch(const uint32_t *packed, const int32_t *area, int n_img, int n, long long words,
+                               int32_t *inter, __half *iou, __half *asy, cudaStream_t st);
+
 namespace {
 
 // ---------------------------------------------------------------------------------------- pack
@@ -170,6 +175,14 @@ CIM_API size_t cim_mask_overlap_workspace_bytes(int n_img, int n, int64_t words)
 CIM_API int cim_mask_overlap(const uint32_t *packed, int n_img, int n, int64_t words, int32_t *inter,
                              int32_t *area, void *iou_f16, void *asy_f16, void *workspace, size_t ws_bytes,
                              cim_stream_t stream) {
+    return cim_mask_overlap_algo(packed, n_img, n, words, inter, area, iou_f16, asy_f16, workspace, ws_bytes,
+                                 CIM_OVERLAP_AUTO, stream);
+}
+
+CIM_API int cim_mask_overlap_algo(const uint32_t *packed, int n_img, int n, int64_t words, int32_t *inter,
+                                  int32_t *area, void *iou_f16, void *asy_f16, void *workspace, size_t ws_bytes,
+                                  int algo, cim_stream_t stream) {
+    if (algo != CIM_OVERLAP_AUTO && algo != CIM_OVERLAP_POPC && algo != CIM_OVERLAP_TENSOR) return CIM_ERR_ARG;
     if (!packed || !iou_f16 || !asy_f16 || n_img < 0 || n < 0 || words <= 0) return CIM_ERR_ARG;
     if (words * 32 >= (1LL << 24)) return CIM_ERR_SHAPE;      // counts must stay exact in fp32
     if (n_img == 0 || n == 0) return CIM_OK;
@@ -183,6 +196,12 @@ CIM_API int cim_mask_overlap(const uint32_t *packed, int n_img, int n, int64_t w
     mask_area_kernel<<<(unsigned)((n_masks + 7) / 8), 256, 0, st>>>(packed, area, n_masks, words);
     int rc = cim_launch_status();
     if (rc) return rc;
+    const bool tc_ok = cim_mask_overlap_tc_eligible(n, words) && cim_aligned(packed, 16);
+    if (algo == CIM_OVERLAP_TENSOR && !tc_ok) return CIM_ERR_SHAPE;
+    // the tensor path pays off once a 128 x 256 tile is reasonably full and K is long
+    if (algo == CIM_OVERLAP_TENSOR || (algo == CIM_OVERLAP_AUTO && tc_ok && n >= 256 && words >= 128))
+        return cim_mask_overlap_tc_launch(packed, area, n_img, n, words, inter, reinterpret_cast<__half *>(iou_f16),
+                                          reinterpret_cast<__half *>(asy_f16), st);
     const int nt = (n + TS - 1) / TS;
     dim3 grid((unsigned)(nt * (nt + 1) / 2), (unsigned)n_img);
     mask_overlap_popc_kernel<<<grid, 256, 0, st>>>(packed, area, n, words, inter,

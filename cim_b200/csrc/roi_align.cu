@@ -587,9 +587,9 @@ CIM_API int cim_roi_align_fwd(const float *feat, const float *rois, float *out, 
                               int K, int oh, int ow, float scale, int sr, int aligned, void *ws,
                               size_t ws_bytes, cim_stream_t stream) {
     if (B > 4096) return CIM_ERR_SHAPE;
+    if (K == 0 && feat && B > 0 && C > 0 && H > 0 && W > 0 && oh > 0 && ow > 0) return CIM_OK;   // empty output
     int rc = check_args(feat, rois, out, B, C, H, W, K, oh, ow, ws, ws_bytes);
     if (rc) return rc;
-    if (K == 0) return CIM_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const Plan p = make_plan(C, H, W, oh, ow);
     const RoiWs w = carve(ws, B);
@@ -616,6 +616,10 @@ CIM_API int cim_roi_align_bwd(const float *grad_out, const float *rois, float *g
                               int W, int K, int oh, int ow, float scale, int sr, int aligned, void *ws,
                               size_t ws_bytes, cim_stream_t stream) {
     if (B > 4096) return CIM_ERR_SHAPE;
+    if (K == 0 && grad_feat && B > 0 && C > 0 && H > 0 && W > 0) {                // no ROI: zero gradient
+        cudaMemsetAsync(grad_feat, 0, sizeof(float) * (size_t)B * C * H * W, (cudaStream_t)stream);
+        return cim_launch_status();
+    }
     int rc = check_args(grad_out, rois, grad_feat, B, C, H, W, K, oh, ow, ws, ws_bytes);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;

@@ -37,9 +37,10 @@ def mask_pack(masks):
     return packed
 
 
-def mask_overlap(packed, return_counts=False):
+def mask_overlap(packed, return_counts=False, algo="auto"):
     """Bit masks [N, words] or [n_img, N, words] (int32) -> (iou_map, asy_iou_map) float16
-    [.., N, N]; with return_counts also (inter int32 [.., N, N], area int32 [.., N])."""
+    [.., N, N]; with return_counts also (inter int32 [.., N, N], area int32 [.., N]).
+    algo: "auto" | "popc" (AND + POPC kernel) | "tensor" (tcgen05 int8 kernel)."""
     _lib.require_cuda(packed, "packed", torch.int32)
     squeeze = packed.dim() == 2
     if squeeze:
@@ -55,9 +56,10 @@ def mask_overlap(packed, return_counts=False):
     area = torch.empty((n_img, n), dtype=torch.int32, device=dev)
     inter = torch.empty((n_img, n, n), dtype=torch.int32, device=dev) if return_counts else None
     with torch.cuda.device(dev):
-        rc = L.cim_mask_overlap(_lib.ptr(packed), n_img, n, words, _lib.ptr(inter), _lib.ptr(area),
-                                _lib.ptr(iou), _lib.ptr(asy), None, 0, _lib.stream_ptr(dev))
-    _lib.check(rc, "cim_mask_overlap")
+        rc = L.cim_mask_overlap_algo(_lib.ptr(packed), n_img, n, words, _lib.ptr(inter), _lib.ptr(area),
+                                     _lib.ptr(iou), _lib.ptr(asy), None, 0, _lib.OVERLAP_ALGOS[algo],
+                                     _lib.stream_ptr(dev))
+    _lib.check(rc, "cim_mask_overlap_algo")
     outs = (iou, asy, inter, area) if return_counts else (iou, asy)
     return tuple(o.squeeze(0) for o in outs) if squeeze else outs
 

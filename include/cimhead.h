@@ -90,6 +90,14 @@ size_t cim_mask_overlap_workspace_bytes(int n_img, int n, int64_t words);
 int cim_mask_overlap(const uint32_t *packed, int n_img, int n, int64_t words,
                      int32_t *inter, int32_t *area, void *iou_f16, void *asy_f16,
                      void *workspace, size_t workspace_bytes, cim_stream_t stream);
+/* Same with an explicit kernel choice.  AUTO = tensor cores (tcgen05.mma.kind::i8 over bytes
+ * expanded from the bit masks in shared memory, exact S32 accumulation) for n >= 256 and
+ * words >= 128 with words % 4 == 0 and a 16-byte aligned `packed`, else the popcount kernel.
+ * TENSOR returns CIM_ERR_SHAPE when the problem cannot take that path. */
+enum { CIM_OVERLAP_AUTO = 0, CIM_OVERLAP_POPC = 1, CIM_OVERLAP_TENSOR = 2 };
+int cim_mask_overlap_algo(const uint32_t *packed, int n_img, int n, int64_t words,
+                          int32_t *inter, int32_t *area, void *iou_f16, void *asy_f16,
+                          void *workspace, size_t workspace_bytes, int algo, cim_stream_t stream);
 
 /* ------------------------------------------------------------------ scoring heads
  * Replace heads.cls_iou_model.forward (lib/modeling/heads.py:194-219): n_heads = 2 + 2*K

@@ -95,3 +95,36 @@ def test_full_size_cfg2_properties():
     assert_f16_bits_equal(u16(asy[rows][:, rows]), o_asy.view(np.uint16))
     # containment really occurs in the synthetic hierarchy (heads.py:386 needs asy > 0.85)
     assert int((asy > 0.85).sum().item()) > R
+
+
+@pytest.mark.parametrize("n,side,n_img", [(300, 64, 1), (513, 64, 2), (256, 128, 1), (777, 32, 1), (64, 64, 3)])
+def test_tensor_core_path_equals_popc_and_oracle(n, side, n_img):
+    """tcgen05.mma.kind::i8 kernel vs the AND+POPC kernel vs the oracle: integer counts and both
+    fp16 maps bit-exact, including partial tiles, empty / full / duplicate masks."""
+    imgs = []
+    for b in range(n_img):
+        m = synth.rasterize(synth.proposal_params(n, side, 900 + 7 * b + n))
+        m[1] = 0
+        m[2] = 1
+        m[n - 1] = m[0]
+        imgs.append(m)
+    packed = mask_ops.mask_pack(torch.stack(imgs).to(DEV))
+    t_iou, t_asy, t_inter, t_area = mask_ops.mask_overlap(packed, return_counts=True, algo="tensor")
+    p_iou, p_asy, p_inter, p_area = mask_ops.mask_overlap(packed, return_counts=True, algo="popc")
+    assert torch.equal(t_inter, p_inter) and torch.equal(t_area, p_area)
+    assert_f16_bits_equal(u16(t_iou), u16(p_iou))
+    assert_f16_bits_equal(u16(t_asy), u16(p_asy))
+    for b in range(n_img):
+        o_inter, o_area = mask_oracle.overlap_counts(imgs[b].numpy())
+        np.testing.assert_array_equal(t_inter[b].cpu().numpy(), o_inter)
+        o_iou, o_asy = mask_oracle.maps_from_counts(o_inter, o_area)
+        assert_f16_bits_equal(u16(t_iou[b]), o_iou.view(np.uint16))
+        assert_f16_bits_equal(u16(t_asy[b]), o_asy.view(np.uint16))
+
+
+def test_tensor_path_rejects_what_it_cannot_take():
+    packed = mask_ops.mask_pack(torch.ones(70, 5, 5, dtype=torch.uint8, device=DEV))      # 1 word per mask
+    with pytest.raises(RuntimeError, match="shape"):
+        mask_ops.mask_overlap(packed, algo="tensor")
+    iou, _ = mask_ops.mask_overlap(packed, algo="auto")                                    # falls back to popc
+    assert bool((iou == 1).all())
