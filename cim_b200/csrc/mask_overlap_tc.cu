@@ -83,9 +83,16 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, int (&v)[32]) {
 // 32 mask bits -> 32 operand bytes (8 words): word g, byte b = 0xFF iff bit 8b+g is set.
 // (w << (7-g)) moves bit 8b+g to the top of byte b; PRMT selector 0xBA98 replicates each byte's
 // sign bit over the byte.
+// (inline PTX: the __byte_perm intrinsic masks the selector to 3 bits per byte and would drop the
+// replicate flag.)
+__device__ __forceinline__ uint32_t sign_bytes(uint32_t x) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(0u), "r"(0xBA98u));
+    return r;
+}
 __device__ __forceinline__ void expand32(uint32_t w, uint32_t (&o)[8]) {
 #pragma unroll
-    for (int g = 0; g < 8; ++g) o[g] = __byte_perm(w << (7 - g), 0u, 0xBA98u);
+    for (int g = 0; g < 8; ++g) o[g] = sign_bytes(w << (7 - g));
 }
 
 __device__ __forceinline__ __half2 pack_ratio2(int i0, int d0, int i1, int d1) {
