@@ -607,8 +607,9 @@ CIM_API int cim_roi_align_fwd(const float *feat, const float *rois, float *out, 
     roi_align_fwd_tile_kernel<<<grid, NW * 32, p.smem_fwd, st>>>(feat, w.hdr, w.img_start, w.desc, out, B, C, H,
                                                                   W, p.pitch);
     if ((rc = cim_launch_status())) return rc;
-    roi_align_generic_kernel<false><<<ggrid, 256, 0, st>>>(feat, rois, out, w.hdr, w.desc, 1, B, C, H, W, K, oh,
-                                                           ow, scale, sr, aligned);
+    // leftover pass: one CTA per ROI, which exits at once unless the tile kernel skipped that ROI
+    roi_align_generic_kernel<false><<<dim3((unsigned)K, 1), 256, 0, st>>>(feat, rois, out, w.hdr, w.desc, 1, B, C, H,
+                                                                          W, K, oh, ow, scale, sr, aligned);
     return cim_launch_status();
 }
 
@@ -639,7 +640,7 @@ CIM_API int cim_roi_align_bwd(const float *grad_out, const float *rois, float *g
     roi_align_bwd_tile_kernel<<<B * (C / CH), NW * 32, p.smem_bwd, st>>>(grad_out, w.hdr, w.img_start, w.desc,
                                                                           grad_feat, B, C, H, W, p.pitch);
     if ((rc = cim_launch_status())) return rc;
-    roi_align_generic_kernel<true><<<ggrid, 256, 0, st>>>(grad_out, rois, grad_feat, w.hdr, w.desc, 1, B, C, H, W,
-                                                          K, oh, ow, scale, sr, aligned);
+    roi_align_generic_kernel<true><<<dim3((unsigned)K, 1), 256, 0, st>>>(grad_out, rois, grad_feat, w.hdr, w.desc, 1,
+                                                                         B, C, H, W, K, oh, ow, scale, sr, aligned);
     return cim_launch_status();
 }
