@@ -8,12 +8,17 @@
 // Operands never exist as bytes in HBM: masks stay bit-packed (32 px / word).  Per K-block of
 // 128 pixels, 12 expander warps read 16 B of each of the tile's 128 + 256 mask rows and turn
 // every bit into a byte 0x00 / 0xFF with PRMT's sign-replicate mode (one PRMT per 4 pixels) --
-// 0xFF is -1 as INT8, so a pixel common to both masks contributes (-1)*(-1) = +1.  The bytes are
-// stored straight into the canonical K-major SWIZZLE_128B layout the UMMA smem descriptors expect
-// (8-row x 128 B atoms, 16 B chunk index XOR row%8), a 4-stage mbarrier ring hands stages to the
-// single MMA-issuing thread (M = 128, N = 256, K = 32 per instruction, 4 per stage), and
-// tcgen05.commit returns the stage.  The pixel -> K-slot order inside a K-block is a fixed
-// permutation (the same for both operands), which a contraction does not care about.
+// 0xFF is -1 as INT8, so a pixel common to both masks contributes (-1)*(-1) = +1.
+//   * The 256 B-operand rows are stored straight into the canonical K-major SWIZZLE_128B layout
+//     the UMMA smem descriptor expects (8-row x 128 B atoms, 16 B chunk index XOR row % 8).
+//   * The 128 A-operand rows never touch shared memory: each thread writes its row's 128 bytes
+//     into tensor memory with one tcgen05.st.32x32b.x32 (lane = row, 32 columns per K-block) and
+//     the MMA takes A from TMEM.  The first version staged A in smem as well and was bound by the
+//     shared-memory port (L1 83 %, tensor pipe 45 %: profiles/r1_ncu_full_v1.txt).
+// A 6-stage mbarrier ring hands stages to the single MMA-issuing thread (M = 128, N = 256, K = 32
+// per instruction, 4 per stage) and tcgen05.commit returns the stage.  The pixel -> K-slot order
+// inside a K-block is a fixed permutation (the same for both operands), which a contraction does
+// not care about.
 //
 // Only tiles touching the upper triangle are computed; the epilogue reads the accumulator from
 // TMEM (tcgen05.ld), applies iou = I / (a_i + a_j - I), asy = I / a_j in fp32 -> fp16, and writes
@@ -25,16 +30,17 @@ namespace {
 constexpr int TM = 128;                 // tile rows   (UMMA M)
 constexpr int TN = 256;                 // tile cols   (UMMA N)
 constexpr int KB = 128;                 // pixels (= operand bytes per row) per K-block: one SW128 atom
-constexpr int STAGES = 4;
-constexpr int A_BYTES = TM * KB;        // 16 KB
-constexpr int B_BYTES = TN * KB;        // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int STAGES = 6;
+constexpr int B_BYTES = TN * KB;        // 32 KB of expanded B operand per stage (smem)
+constexpr int STAGE_BYTES = B_BYTES;
+constexpr int A_COLS = KB / 4;          // 32 TMEM columns of expanded A operand per stage
 constexpr int EXP_WARPS = (TM + TN) / 32;          // 12 expander warps, one operand row per thread
 constexpr int MMA_WARP = EXP_WARPS;                // warp 12 issues the MMAs and owns TMEM
 constexpr int THREADS = (EXP_WARPS + 1) * 32;      // 416
 constexpr int EPI_WARPS = 8;                       // warps 0..7 drain the accumulator
 constexpr int SPITCH = TN + 1;                     // int32 pitch of the transpose buffer
-constexpr int TMEM_COLS = 256;
+constexpr int TMEM_COLS = 512;                     // accumulator: columns 0..255, A stages: 256 + 32 s
+constexpr int TMEM_A0 = TN;
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 128;
 
 // tcgen05 instruction descriptor (cute::UMMA::InstrDescriptor): S32 accumulate, INT8 x INT8,
@@ -58,13 +64,26 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void tc_mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate), "r"(0u)
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(IDESC), "r"(accumulate), "r"(0u)
         : "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+        "%29,%30,%31,%32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+        "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+        "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, int (&v)[32]) {
     asm volatile(
@@ -140,34 +159,57 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
 
     if (warp < EXP_WARPS) {
         // ------------------------------------------------------------------ expanders
-        const bool is_a = tid < TM;
+        const bool is_a = tid < TM;                           // warps 0..3: A rows = TMEM lanes 32w..32w+31
         const int lr = is_a ? tid : tid - TM;                 // row inside the A / B tile
         const int grow = (is_a ? row0 : col0) + lr;           // mask index inside the image
         const bool valid = grow < n;
         const uint4 *src = reinterpret_cast<const uint4 *>(packed + ((size_t)img * n + (valid ? grow : 0)) * words);
-        const uint32_t row_off = (is_a ? 0 : A_BYTES) + (lr >> 3) * 1024 + (lr & 7) * 128;
+        const uint32_t row_off = (lr >> 3) * 1024 + (lr & 7) * 128;
         const uint32_t sw = lr & 7;
-        uint4 cur = make_uint4(0u, 0u, 0u, 0u);
-        if (valid) cur = __ldg(src);
-        for (int kb = 0; kb < nkb; ++kb) {
-            uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
-            if (valid && kb + 1 < nkb) nxt = __ldg(src + kb + 1);
-            const int s = kb % STAGES;
-            if (kb >= STAGES) mbar_wait(&empty[s], ((kb / STAGES) - 1) & 1);
-            unsigned char *rowp = stages + (size_t)s * STAGE_BYTES + row_off;
-            const uint32_t pw[4] = {cur.x, cur.y, cur.z, cur.w};
+        const uint32_t a_lane = tmem_base + ((uint32_t)(32 * warp) << 16) + TMEM_A0;
+        const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+        uint4 cur[2] = {zero4, zero4};                         // two K-blocks = one 32 B sector per row
+        if (valid) { cur[0] = __ldg(src); if (nkb > 1) cur[1] = __ldg(src + 1); }
+        for (int kb2 = 0; kb2 < nkb; kb2 += 2) {
+            uint4 nxt[2] = {zero4, zero4};
+            if (valid && kb2 + 2 < nkb) nxt[0] = __ldg(src + kb2 + 2);
+            if (valid && kb2 + 3 < nkb) nxt[1] = __ldg(src + kb2 + 3);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint32_t o[8];
-                expand32(pw[q], o);
-                // 16 B chunks 2q and 2q+1 of the 128 B row, XOR-swizzled with row % 8
-                *reinterpret_cast<uint4 *>(rowp + (((2 * q) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-                *reinterpret_cast<uint4 *>(rowp + (((2 * q + 1) ^ sw) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+            for (int h = 0; h < 2; ++h) {
+                const int kb = kb2 + h;
+                if (kb >= nkb) break;
+                const int s = kb % STAGES;
+                if (kb >= STAGES) mbar_wait(&empty[s], ((kb / STAGES) - 1) & 1);
+                const uint32_t pw[4] = {cur[h].x, cur[h].y, cur[h].z, cur[h].w};
+                if (is_a) {
+                    uint32_t o[32];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t t[8];
+                        expand32(pw[q], t);
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) o[q * 8 + g] = t[g];
+                    }
+                    tc_st32(a_lane + (uint32_t)(s * A_COLS), o);     // includes tcgen05.wait::st
+                    tc_fence_before();
+                } else {
+                    unsigned char *rowp = stages + (size_t)s * STAGE_BYTES + row_off;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t o[8];
+                        expand32(pw[q], o);
+                        // 16 B chunks 2q and 2q+1 of the 128 B row, XOR-swizzled with row % 8
+                        *reinterpret_cast<uint4 *>(rowp + (((2 * q) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                        *reinterpret_cast<uint4 *>(rowp + (((2 * q + 1) ^ sw) << 4)) =
+                            make_uint4(o[4], o[5], o[6], o[7]);
+                    }
+                    fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[s]);
             }
-            fence_proxy_async_smem();           // generic-proxy stores -> visible to the tensor core
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[s]);
-            cur = nxt;
+            cur[0] = nxt[0];
+            cur[1] = nxt[1];
         }
     } else {
         // ------------------------------------------------------------------ MMA issuer
@@ -176,11 +218,11 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
             mbar_wait(&full[s], (kb / STAGES) & 1);
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t a_addr = smem_u32(stages + (size_t)s * STAGE_BYTES);
-                const uint64_t ad = smem_desc(a_addr), bd = smem_desc(a_addr + A_BYTES);
+                const uint64_t bd = smem_desc(smem_u32(stages + (size_t)s * STAGE_BYTES));
+                const uint32_t a_t = tmem_base + TMEM_A0 + (uint32_t)(s * A_COLS);
 #pragma unroll
-                for (int k = 0; k < KB / 32; ++k)       // K = 32 bytes per instruction: +2 in 16 B units
-                    tc_mma_i8(tmem_base, ad + 2 * k, bd + 2 * k, (kb | k) != 0);
+                for (int k = 0; k < KB / 32; ++k)       // K = 32 bytes: 8 TMEM columns of A, +2 (x16 B) of B
+                    tc_mma_i8_ts(tmem_base, a_t + 8 * k, bd + 2 * k, (kb | k) != 0);
                 tc_commit(&empty[s]);                    // arrives when the MMAs above have read the stage
                 if (kb == nkb - 1) tc_commit(accum_full);
             }

@@ -13,11 +13,16 @@
 //   2. Tile kernels: a CTA keeps the [32 channels x H x W] feature (or gradient) tile of one
 //      image in shared memory (pitch odd => lane = channel is bank-conflict free) and sweeps
 //      the image's ROIs.
-//        forward : one warp per ROI, 7x7 outputs per lane staged in smem, written with one
-//                  6272-byte cp.async.bulk (UBLKCP) per (roi, 32 channels);
-//        backward: gradients of NBATCH ROIs arrive by cp.async.bulk + mbarrier; warp w owns
-//                  tile rows y == w (mod 8), so every tile address has exactly one writer and
-//                  ROIs are applied in index order: no atomics, bit-reproducible.
+//        forward : persistent, one CTA per SM, (roi, chunk) units split evenly; a warp owns one
+//                  ROI at a time, its descriptor is prefetched into smem with cp.async (LDGSTS)
+//                  one ROI ahead; ROW SWEEP: each feature value of the ROI window is loaded once,
+//                  the 7 column sums of a row are added into the output rows whose window holds
+//                  that row (49 accumulators in registers); the 32 x 49 outputs are staged in
+//                  smem and leave with one 6272-byte cp.async.bulk (UBLKCP) per (roi, 32 ch).
+//        backward: gradients + descriptors of the ROIs stream through an 8-slot mbarrier ring
+//                  (cp.async.bulk, no CTA-wide barrier); warp w of 16 owns the tile row pairs
+//                  (y >> 1) % 16 == w, so every tile address has exactly one writer and ROIs are
+//                  applied in index order: no atomics, bit-reproducible.
 //   3. Generic kernels (one thread per output element, sample by sample) take whatever the
 //      tile kernels cannot: other output sizes, feature maps too large for shared memory,
 //      bins wider than 8 taps, ROIs not grouped by image.
@@ -34,9 +39,7 @@ enum {
 };
 constexpr int WS_HDR_BYTES = 256;   // word 0: "rois not grouped by image" flag
 constexpr int CH = 32;              // channels per tile (= lanes)
-constexpr int NW = 8;               // warps per tile CTA
 constexpr int STAGE_FLOATS = CH * NBIN;          // 1568 floats = 6272 B
-constexpr int NBATCH = 4;           // ROIs per backward staging batch
 
 struct RoiWs {
     int *hdr;          // [64]
@@ -196,60 +199,88 @@ __device__ __forceinline__ void load_tile(float *tile, const float *__restrict__
     }
 }
 
+// 16-byte async copy global -> shared (LDGSTS), per-thread completion groups
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// One ROI x 32 channels (lane = channel).  Row sweep: every feature value of the ROI's window is
+// loaded from the smem tile once; the 7 column sums of a row are formed with the register-resident
+// column weights and then added into the (at most 2-3) output rows whose window contains this
+// feature row.  All control flow depends only on the descriptor, i.e. is warp-uniform.
 template <int T>
-__device__ __forceinline__ void fwd_one_roi(const float *__restrict__ tile_c, int W,
-                                            const int *__restrict__ desc, int hdr,
-                                            float *__restrict__ stage_c, int lane) {
-    const unsigned full = 0xffffffffu;
+__device__ __forceinline__ void fwd_rows(const float *__restrict__ tile_c, int W, const int *__restrict__ d,
+                                         float *__restrict__ stage_c, float *stage_w, int lane) {
     float wx[PW][T];
-    int xo[PW];
-    const float *dwx = reinterpret_cast<const float *>(desc + D_WX);
+    int xo[PW], ylo[PH], yhi[PH];
+    const float *dwx = reinterpret_cast<const float *>(d + D_WX);
+    const float *dwy = reinterpret_cast<const float *>(d + D_WY);
+    {
+        int4 a = *reinterpret_cast<const int4 *>(d + D_XLO), b = *reinterpret_cast<const int4 *>(d + D_XLO + 4);
+        xo[0] = a.x; xo[1] = a.y; xo[2] = a.z; xo[3] = a.w; xo[4] = b.x; xo[5] = b.y; xo[6] = b.z;
+        a = *reinterpret_cast<const int4 *>(d + D_YLO); b = *reinterpret_cast<const int4 *>(d + D_YLO + 4);
+        ylo[0] = a.x; ylo[1] = a.y; ylo[2] = a.z; ylo[3] = a.w; ylo[4] = b.x; ylo[5] = b.y; ylo[6] = b.z;
+        a = *reinterpret_cast<const int4 *>(d + D_YN); b = *reinterpret_cast<const int4 *>(d + D_YN + 4);
+        yhi[0] = ylo[0] + a.x; yhi[1] = ylo[1] + a.y; yhi[2] = ylo[2] + a.z; yhi[3] = ylo[3] + a.w;
+        yhi[4] = ylo[4] + b.x; yhi[5] = ylo[5] + b.y; yhi[6] = ylo[6] + b.z;
+    }
 #pragma unroll
     for (int pw = 0; pw < PW; ++pw) {
-        float4 a = __ldg(reinterpret_cast<const float4 *>(dwx + pw * MAXT));
+        float4 a = *reinterpret_cast<const float4 *>(dwx + pw * MAXT);
         float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (T > 4) b = __ldg(reinterpret_cast<const float4 *>(dwx + pw * MAXT + 4));
+        if (T > 4) b = *reinterpret_cast<const float4 *>(dwx + pw * MAXT + 4);
         float t8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
         for (int l = 0; l < T; ++l) wx[pw][l] = t8[l];
-        xo[pw] = __shfl_sync(full, hdr, D_XLO + pw);
     }
-    // the 56 row weights live across the warp: lane i holds wy[i] and wy[32 + i]
-    const float *dwy = reinterpret_cast<const float *>(desc + D_WY);
-    float wyv0 = __ldg(dwy + lane);
-    float wyv1 = lane < 24 ? __ldg(dwy + 32 + lane) : 0.f;
+    float acc[PH][PW];
+#pragma unroll
+    for (int ph = 0; ph < PH; ++ph)
+#pragma unroll
+        for (int pw = 0; pw < PW; ++pw) acc[ph][pw] = 0.f;
 
+    const int y0 = d[D_Y0], y1 = d[D_Y1];
 #pragma unroll 1
-    for (int ph = 0; ph < PH; ++ph) {
-        int ylo = __shfl_sync(full, hdr, D_YLO + ph);
-        int yn = __shfl_sync(full, hdr, D_YN + ph);
-        float acc[PW];
+    for (int y = y0; y < y1; ++y) {
+        const float *row = tile_c + y * W;
+        float r[PW];
 #pragma unroll
-        for (int pw = 0; pw < PW; ++pw) acc[pw] = 0.f;
-        for (int k = 0; k < yn; ++k) {
-            int wi = ph * MAXT + k;
-            float wyk = __shfl_sync(full, wi < 32 ? wyv0 : wyv1, wi & 31);
-            const float *row = tile_c + (ylo + k) * W;
+        for (int pw = 0; pw < PW; ++pw) {
+            float t = 0.f;
 #pragma unroll
-            for (int pw = 0; pw < PW; ++pw) {
-                float r = 0.f;
-#pragma unroll
-                for (int l = 0; l < T; ++l) r = fmaf(wx[pw][l], row[xo[pw] + l], r);
-                acc[pw] = fmaf(wyk, r, acc[pw]);
-            }
+            for (int l = 0; l < T; ++l) t = fmaf(wx[pw][l], row[xo[pw] + l], t);
+            r[pw] = t;
         }
 #pragma unroll
-        for (int pw = 0; pw < PW; ++pw) stage_c[ph * PW + pw] = acc[pw];
+        for (int ph = 0; ph < PH; ++ph) {
+            if (y >= ylo[ph] && y < yhi[ph]) {
+                const float w = dwy[ph * MAXT + (y - ylo[ph])];
+#pragma unroll
+                for (int pw = 0; pw < PW; ++pw) acc[ph][pw] = fmaf(w, r[pw], acc[ph][pw]);
+            }
+        }
     }
+    if (lane == 0) bulk_wait_read<0>();            // the previous bulk store has drained this stage
+    __syncwarp();
+#pragma unroll
+    for (int ph = 0; ph < PH; ++ph)
+#pragma unroll
+        for (int pw = 0; pw < PW; ++pw) stage_c[ph * PW + pw] = acc[ph][pw];
+    (void)stage_w;
 }
 
-__global__ void __launch_bounds__(NW * 32, 1)
+__global__ void __launch_bounds__(384, 1)
 roi_align_fwd_tile_kernel(const float *__restrict__ feat, const int *__restrict__ hdr,
                           const int *__restrict__ img_start, const int *__restrict__ descs,
                           float *__restrict__ out, int B, int C, int H, int W, int pitch) {
     extern __shared__ __align__(128) float smem[];
+    const int nw = blockDim.x >> 5;
     float *tile = smem;
-    float *stage = smem + (size_t)CH * pitch;
+    float *stage = smem + (size_t)CH * pitch;                                    // [nw][1568]
+    int *dslots = reinterpret_cast<int *>(stage + (size_t)nw * STAGE_FLOATS);   // [nw][2][160]
     if (__ldg(hdr) != 0) return;              // rois not grouped by image: generic kernel runs
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -260,6 +291,16 @@ roi_align_fwd_tile_kernel(const float *__restrict__ feat, const int *__restrict_
     const long long u_end = U * (blockIdx.x + 1) / gridDim.x;
     float *stage_w = stage + warp * STAGE_FLOATS;
     float *stage_c = stage_w + lane * NBIN;
+    int *my_slots = dslots + warp * 2 * DESC_WORDS;
+
+    // descriptor prefetch: 640 B = 40 x 16 B per ROI, lanes 0..31 + lanes 0..7 again
+    auto prefetch = [&](int roi, int slot) {
+        const int *src = descs + (size_t)roi * DESC_WORDS;
+        int *dst = my_slots + slot * DESC_WORDS;
+        cp_async16(dst + lane * 4, src + lane * 4);
+        if (lane < 8) cp_async16(dst + (32 + lane) * 4, src + (32 + lane) * 4);
+        cp_async_commit();
+    };
 
     int b = 0;
     while (u < u_end) {
@@ -272,33 +313,37 @@ roi_align_fwd_tile_kernel(const float *__restrict__ feat, const int *__restrict_
         const int r1 = (int)min((long long)nroi, r0 + (u_end - u));
         const int c0 = ch * CH;
 
+        int r = r0 + warp, slot = 0;
+        if (r < r1) prefetch(is + r, 0);       // overlaps the tile load below
         __syncthreads();                       // everyone is done with the previous tile
-        load_tile(tile, feat + ((size_t)b * C + c0) * HW, HW, pitch, tid, NW * 32);
+        load_tile(tile, feat + ((size_t)b * C + c0) * HW, HW, pitch, tid, blockDim.x);
         __syncthreads();
 
         const float *tile_c = tile + lane * pitch;
-        for (int r = r0 + warp; r < r1; r += NW) {
+        while (r < r1) {
+            const int rn = r + nw;
+            if (rn < r1) { prefetch(is + rn, slot ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+            __syncwarp();
+            const int *d = my_slots + slot * DESC_WORDS;
             const int roi = is + r;
-            const int *desc = descs + (size_t)roi * DESC_WORDS;
-            const int h = __ldg(desc + lane);
-            const int flags = __shfl_sync(0xffffffffu, h, D_FLAGY) | __shfl_sync(0xffffffffu, h, D_FLAGX);
-            if (flags) continue;
-            if (lane == 0) bulk_wait_read<0>();   // previous bulk store has drained the stage
-            __syncwarp();
-            const int T = __shfl_sync(0xffffffffu, h, D_TX);
-            switch (T) {
-                case 2: fwd_one_roi<2>(tile_c, W, desc, h, stage_c, lane); break;
-                case 3: fwd_one_roi<3>(tile_c, W, desc, h, stage_c, lane); break;
-                case 4: fwd_one_roi<4>(tile_c, W, desc, h, stage_c, lane); break;
-                case 6: fwd_one_roi<6>(tile_c, W, desc, h, stage_c, lane); break;
-                default: fwd_one_roi<8>(tile_c, W, desc, h, stage_c, lane); break;
+            if ((d[D_FLAGY] | d[D_FLAGX]) == 0) {
+                switch (d[D_TX]) {
+                    case 2: fwd_rows<2>(tile_c, W, d, stage_c, stage_w, lane); break;
+                    case 3: fwd_rows<3>(tile_c, W, d, stage_c, stage_w, lane); break;
+                    case 4: fwd_rows<4>(tile_c, W, d, stage_c, stage_w, lane); break;
+                    case 6: fwd_rows<6>(tile_c, W, d, stage_c, stage_w, lane); break;
+                    default: fwd_rows<8>(tile_c, W, d, stage_c, stage_w, lane); break;
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    bulk_s2g(out + ((size_t)roi * C + c0) * NBIN, stage_w, STAGE_FLOATS * 4);
+                    bulk_commit();
+                }
             }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-                bulk_s2g(out + ((size_t)roi * C + c0) * NBIN, stage_w, STAGE_FLOATS * 4);
-                bulk_commit();
-            }
+            __syncwarp();                      // slot is re-filled two iterations from now
+            slot ^= 1;
+            r = rn;
         }
         u += r1 - r0;
     }
@@ -306,9 +351,14 @@ roi_align_fwd_tile_kernel(const float *__restrict__ feat, const int *__restrict_
 }
 
 // ----------------------------------------------------------------------------- tile: backward
+constexpr int NWB = 16;             // consumer warps of the backward CTA; warp w owns row pairs
+                                    // {y : (y >> 1) % 16 == w}
+constexpr int NS = 8;               // ring slots (one ROI each: 32 x 49 gradients + its descriptor)
+constexpr int SLOT_FLOATS = STAGE_FLOATS + DESC_WORDS;
+
 template <int T, bool XINC>
 __device__ __forceinline__ void bwd_rows(float *__restrict__ tile_c, int W, const int *d,
-                                         const float *__restrict__ g, int y, int y1) {
+                                         const float *__restrict__ g, int warp, int y0, int y1) {
     float wx[PW][T];
     int xo[PW], ylo[PH], yn[PH];
     const float *dwx = reinterpret_cast<const float *>(d + D_WX);
@@ -330,119 +380,147 @@ __device__ __forceinline__ void bwd_rows(float *__restrict__ tile_c, int W, cons
 #pragma unroll
         for (int l = 0; l < T; ++l) wx[pw][l] = t8[l];
     }
-    for (; y < y1; y += NW) {
-        float r[PW];
+    // the row pairs this warp owns: 2*warp + 32*m, clipped to the ROI's rows [y0, y1)
+    for (int yb = 2 * warp; yb < y1; yb += 2 * NWB) {
+#pragma unroll 1
+        for (int y = max(yb, y0); y < min(yb + 2, y1); ++y) {
+            float r[PW];
 #pragma unroll
-        for (int pw = 0; pw < PW; ++pw) r[pw] = 0.f;
+            for (int pw = 0; pw < PW; ++pw) r[pw] = 0.f;
 #pragma unroll
-        for (int ph = 0; ph < PH; ++ph) {
-            int dd = y - ylo[ph];
-            if (dd >= 0 && dd < yn[ph]) {
-                float w = dwy[ph * MAXT + dd];
+            for (int ph = 0; ph < PH; ++ph) {
+                int dd = y - ylo[ph];
+                if (dd >= 0 && dd < yn[ph]) {
+                    float w = dwy[ph * MAXT + dd];
 #pragma unroll
-                for (int pw = 0; pw < PW; ++pw) r[pw] = fmaf(w, g[ph * PW + pw], r[pw]);
+                    for (int pw = 0; pw < PW; ++pw) r[pw] = fmaf(w, g[ph * PW + pw], r[pw]);
+                }
             }
-        }
-        float *row = tile_c + y * W;
-        if (XINC) {
-            // window starts strictly increase: the 7 taps of one l hit 7 distinct columns,
-            // so they can be loaded, updated and stored as a group
-#pragma unroll
-            for (int l = 0; l < T; ++l) {
-                float v[PW];
-#pragma unroll
-                for (int pw = 0; pw < PW; ++pw) v[pw] = row[xo[pw] + l];
-#pragma unroll
-                for (int pw = 0; pw < PW; ++pw) row[xo[pw] + l] = fmaf(wx[pw][l], r[pw], v[pw]);
-            }
-        } else {
-#pragma unroll
-            for (int pw = 0; pw < PW; ++pw)
+            float *row = tile_c + y * W;
+            if (XINC) {
+                // window starts strictly increase: the 7 taps of one l hit 7 distinct columns,
+                // so they can be loaded, updated and stored as a group
 #pragma unroll
                 for (int l = 0; l < T; ++l) {
-                    volatile float *p = row + xo[pw] + l;
-                    *p = fmaf(wx[pw][l], r[pw], *p);
+                    float v[PW];
+#pragma unroll
+                    for (int pw = 0; pw < PW; ++pw) v[pw] = row[xo[pw] + l];
+#pragma unroll
+                    for (int pw = 0; pw < PW; ++pw) row[xo[pw] + l] = fmaf(wx[pw][l], r[pw], v[pw]);
                 }
+            } else {
+#pragma unroll
+                for (int pw = 0; pw < PW; ++pw)
+#pragma unroll
+                    for (int l = 0; l < T; ++l) {
+                        volatile float *p = row + xo[pw] + l;
+                        *p = fmaf(wx[pw][l], r[pw], *p);
+                    }
+            }
         }
     }
 }
 
-__global__ void __launch_bounds__(NW * 32, 1)
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(NWB * 32, 1)
 roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restrict__ hdr,
                           const int *__restrict__ img_start, const int *__restrict__ descs,
                           float *__restrict__ grad_feat, int B, int C, int H, int W, int pitch) {
     extern __shared__ __align__(128) float smem[];
     float *tile = smem;
-    float *gbuf = smem + (size_t)CH * pitch;                          // [2][NBATCH][1568]
-    int *dbuf = reinterpret_cast<int *>(gbuf + 2 * NBATCH * STAGE_FLOATS);   // [2][NBATCH][160]
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(dbuf + 2 * NBATCH * DESC_WORDS);
+    float *ring = smem + (size_t)CH * pitch;                                   // [NS][1568 grads + 160 desc]
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)NS * SLOT_FLOATS);
+    uint64_t *empty = full + NS;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int HW = H * W, nchunks = C / CH;
     const int b = blockIdx.x / nchunks, c0 = (blockIdx.x % nchunks) * CH;
 
-    for (int e = tid; e < CH * pitch; e += NW * 32) tile[e] = 0.f;
+    for (int e = tid; e < CH * pitch; e += NWB * 32) tile[e] = 0.f;
     if (tid == 0) {
-        mbar_init(&mbar[0], 1);
-        mbar_init(&mbar[1], 1);
+        for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWB); }
         fence_mbar_init();
     }
     __syncthreads();
 
     const int is = __ldg(img_start + b);
     const int n = __ldg(hdr) != 0 ? 0 : __ldg(img_start + b + 1) - is;
-    const int nbatches = (n + NBATCH - 1) / NBATCH;
 
-    auto issue = [&](int bi) {
-        const int buf = bi & 1, first = bi * NBATCH, cnt = min(NBATCH, n - first);
-        mbar_expect_tx(&mbar[buf], (uint32_t)cnt * (STAGE_FLOATS * 4 + DESC_WORDS * 4));
-        for (int j = 0; j < cnt; ++j)
-            bulk_g2s(gbuf + (buf * NBATCH + j) * STAGE_FLOATS,
-                     grad_out + ((size_t)(is + first + j) * C + c0) * NBIN, STAGE_FLOATS * 4, &mbar[buf]);
-        bulk_g2s(dbuf + buf * NBATCH * DESC_WORDS, descs + (size_t)(is + first) * DESC_WORDS,
-                 (uint32_t)cnt * DESC_WORDS * 4, &mbar[buf]);
+    // producer duty (lane 0 of warp 0): ROI j goes to slot j % NS once every warp has released
+    // ROI j - NS.  `must` = the ROI warp 0 itself is about to read: then the wait is blocking.
+    int issued = 0;
+    auto produce = [&](int want, int must) {
+        while (issued < want && issued < n) {
+            const int s = issued % NS;
+            if (issued >= NS) {
+                const uint32_t par = ((issued / NS) - 1) & 1;
+                if (issued <= must) mbar_wait(&empty[s], par);
+                else if (!mbar_test(&empty[s], par)) break;
+            }
+            float *slot = ring + (size_t)s * SLOT_FLOATS;
+            mbar_expect_tx(&full[s], (STAGE_FLOATS + DESC_WORDS) * 4);
+            bulk_g2s(slot, grad_out + ((size_t)(is + issued) * C + c0) * NBIN, STAGE_FLOATS * 4, &full[s]);
+            bulk_g2s(slot + STAGE_FLOATS, descs + (size_t)(is + issued) * DESC_WORDS, DESC_WORDS * 4, &full[s]);
+            ++issued;
+        }
     };
-    if (tid == 0 && nbatches > 0) issue(0);
+    if (tid == 0) produce(NS, -1);
 
     float *tile_c = tile + lane * pitch;
-    for (int bi = 0; bi < nbatches; ++bi) {
-        const int buf = bi & 1;
-        if (tid == 0 && bi + 1 < nbatches) issue(bi + 1);   // its buffer was released by the
-                                                             // __syncthreads ending batch bi-1
-        mbar_wait(&mbar[buf], (bi >> 1) & 1);
-        const int cnt = min(NBATCH, n - bi * NBATCH);
-        for (int j = 0; j < cnt; ++j) {
-            const int *d = dbuf + (buf * NBATCH + j) * DESC_WORDS;
-            if (d[D_FLAGY] | d[D_FLAGX]) continue;
-            const int y0 = d[D_Y0], y1 = d[D_Y1];
-            int y = y0 + (((warp - y0) % NW) + NW) % NW;     // first row >= y0 this warp owns
-            if (y >= y1) continue;
-            const float *g = gbuf + (buf * NBATCH + j) * STAGE_FLOATS + lane * NBIN;
+    for (int i = 0; i < n; ++i) {
+        if (tid == 0) produce(i + NS, i);
+        const int s = i % NS;
+        mbar_wait(&full[s], (i / NS) & 1);
+        const float *slot = ring + (size_t)s * SLOT_FLOATS;
+        const int *d = reinterpret_cast<const int *>(slot + STAGE_FLOATS);
+        const int2 yr = *reinterpret_cast<const int2 *>(d + D_Y0);
+        const int y0 = yr.x, y1 = yr.y;
+        // does this warp own a row of [y0, y1)?  pairs 2w + 32m
+        bool mine = false;
+        for (int yb = 2 * warp; yb < y1; yb += 2 * NWB) mine |= (yb + 2 > y0);
+        if (mine && (d[D_FLAGY] | d[D_FLAGX]) == 0) {
+            const float *g = slot + lane * NBIN;
             const int T = d[D_TX];
             if (d[D_XINC]) {
                 switch (T) {
-                    case 2: bwd_rows<2, true>(tile_c, W, d, g, y, y1); break;
-                    case 3: bwd_rows<3, true>(tile_c, W, d, g, y, y1); break;
-                    case 4: bwd_rows<4, true>(tile_c, W, d, g, y, y1); break;
-                    case 6: bwd_rows<6, true>(tile_c, W, d, g, y, y1); break;
-                    default: bwd_rows<8, true>(tile_c, W, d, g, y, y1); break;
+                    case 2: bwd_rows<2, true>(tile_c, W, d, g, warp, y0, y1); break;
+                    case 3: bwd_rows<3, true>(tile_c, W, d, g, warp, y0, y1); break;
+                    case 4: bwd_rows<4, true>(tile_c, W, d, g, warp, y0, y1); break;
+                    case 6: bwd_rows<6, true>(tile_c, W, d, g, warp, y0, y1); break;
+                    default: bwd_rows<8, true>(tile_c, W, d, g, warp, y0, y1); break;
                 }
             } else {
                 switch (T) {
-                    case 2: bwd_rows<2, false>(tile_c, W, d, g, y, y1); break;
-                    case 3: bwd_rows<3, false>(tile_c, W, d, g, y, y1); break;
-                    case 4: bwd_rows<4, false>(tile_c, W, d, g, y, y1); break;
-                    case 6: bwd_rows<6, false>(tile_c, W, d, g, y, y1); break;
-                    default: bwd_rows<8, false>(tile_c, W, d, g, y, y1); break;
+                    case 2: bwd_rows<2, false>(tile_c, W, d, g, warp, y0, y1); break;
+                    case 3: bwd_rows<3, false>(tile_c, W, d, g, warp, y0, y1); break;
+                    case 4: bwd_rows<4, false>(tile_c, W, d, g, warp, y0, y1); break;
+                    case 6: bwd_rows<6, false>(tile_c, W, d, g, warp, y0, y1); break;
+                    default: bwd_rows<8, false>(tile_c, W, d, g, warp, y0, y1); break;
                 }
             }
         }
-        __syncthreads();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cta(&empty[s]);       // this warp is done reading slot s
     }
+    __syncthreads();
 
     // every element of this (image, channel chunk) slab is written exactly once
     float *dst = grad_feat + ((size_t)b * C + c0) * HW;
-    for (int e = tid; e < CH * HW; e += NW * 32) {
+    for (int e = tid; e < CH * HW; e += NWB * 32) {
         int c = e / HW, p = e - c * HW;
         dst[e] = tile[c * pitch + p];
     }
@@ -531,16 +609,21 @@ __global__ void roi_align_generic_kernel(const float *__restrict__ in, const flo
 // ------------------------------------------------------------------------------------- host
 struct Plan {
     bool tile;
-    int pitch;
+    int pitch, fwd_warps;
     size_t smem_fwd, smem_bwd;
 };
 static Plan make_plan(int C, int H, int W, int oh, int ow) {
     Plan p{};
     const int HW = H * W;
     p.pitch = (HW & 1) ? HW : HW + 1;
-    p.smem_fwd = (size_t)CH * p.pitch * 4 + (size_t)NW * STAGE_FLOATS * 4;
-    p.smem_bwd = (size_t)CH * p.pitch * 4 + (size_t)2 * NBATCH * (STAGE_FLOATS + DESC_WORDS) * 4 + 16;
     const size_t cap = (size_t)cim_max_smem_optin();
+    // forward: as many warps (12 ... 4) as fit next to the tile: per warp one output stage and two
+    // descriptor slots
+    const size_t per_warp = (size_t)STAGE_FLOATS * 4 + 2 * DESC_WORDS * 4;
+    p.fwd_warps = 12;
+    while (p.fwd_warps > 4 && (size_t)CH * p.pitch * 4 + p.fwd_warps * per_warp > cap) p.fwd_warps -= 2;
+    p.smem_fwd = (size_t)CH * p.pitch * 4 + p.fwd_warps * per_warp;
+    p.smem_bwd = (size_t)CH * p.pitch * 4 + (size_t)NS * SLOT_FLOATS * 4 + 2 * NS * 8;
     p.tile = oh == PH && ow == PW && (C % CH) == 0 && W >= MAXT && p.smem_fwd <= cap &&
              p.smem_bwd <= cap && (((size_t)CH * p.pitch * 4) % 16 == 0);
     return p;
@@ -604,8 +687,8 @@ CIM_API int cim_roi_align_fwd(const float *feat, const float *rois, float *out, 
     cudaFuncSetAttribute(roi_align_fwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_fwd);
     const long long units = (long long)(C / CH) * K;
     const int grid = (int)min((long long)cim_num_sms(), units);
-    roi_align_fwd_tile_kernel<<<grid, NW * 32, p.smem_fwd, st>>>(feat, w.hdr, w.img_start, w.desc, out, B, C, H,
-                                                                  W, p.pitch);
+    roi_align_fwd_tile_kernel<<<grid, p.fwd_warps * 32, p.smem_fwd, st>>>(feat, w.hdr, w.img_start, w.desc, out, B,
+                                                                           C, H, W, p.pitch);
     if ((rc = cim_launch_status())) return rc;
     // leftover pass: one CTA per ROI, which exits at once unless the tile kernel skipped that ROI
     roi_align_generic_kernel<false><<<dim3((unsigned)K, 1), 256, 0, st>>>(feat, rois, out, w.hdr, w.desc, 1, B, C, H,
@@ -637,8 +720,8 @@ CIM_API int cim_roi_align_bwd(const float *grad_out, const float *rois, float *g
     }
     if ((rc = run_prep(rois, B, H, W, K, oh, ow, scale, sr, aligned, w, st))) return rc;
     cudaFuncSetAttribute(roi_align_bwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bwd);
-    roi_align_bwd_tile_kernel<<<B * (C / CH), NW * 32, p.smem_bwd, st>>>(grad_out, w.hdr, w.img_start, w.desc,
-                                                                          grad_feat, B, C, H, W, p.pitch);
+    roi_align_bwd_tile_kernel<<<B * (C / CH), NWB * 32, p.smem_bwd, st>>>(grad_out, w.hdr, w.img_start, w.desc,
+                                                                           grad_feat, B, C, H, W, p.pitch);
     if ((rc = cim_launch_status())) return rc;
     roi_align_generic_kernel<true><<<dim3((unsigned)K, 1), 256, 0, st>>>(grad_out, rois, grad_feat, w.hdr, w.desc, 1,
                                                                          B, C, H, W, K, oh, ow, scale, sr, aligned);
