@@ -142,7 +142,9 @@ class CIMHeadStep:
     def alloc_host_io(self):
         """Pinned host buffers of the end-to-end call: inputs that originate on the host in the
         reference's pipeline (rois, labels: lib/roi_data/minibatch.py:45-61; proposal masks:
-        the COB .mat files of tools/pre) and the step's results."""
+        the COB .mat files of tools/pre) and the step's results.  Device-side input buffers are
+        DOUBLE buffered and filled on a separate copy stream, so the host->device copy of step
+        i+1 overlaps the kernels of step i (what a prefetching data loader does)."""
         k, n_img, R, C1 = self.K, self.n_img, self.R, self.C + 1
         pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
         self.hi_rois = pin((n_img * R, 5), torch.float32)
@@ -154,25 +156,52 @@ class CIMHeadStep:
         self.ho_valid = pin((k, n_img), torch.uint8)
         self.ho_checksum = pin((2,), torch.float32)
         with torch.cuda.device(self.dev):
-            self.di_rois = torch.empty((n_img * R, 5), dtype=torch.float32, device=self.dev)
-            self.di_labels = torch.empty((n_img, self.C), dtype=torch.float32, device=self.dev)
-            self.di_masks = torch.empty((n_img, R, self.words), dtype=torch.int32, device=self.dev)
-            self.d_checksum = torch.empty((2,), dtype=torch.float32, device=self.dev)
+            dv = lambda shape, dt: torch.empty(shape, dtype=dt, device=self.dev)
+            self.di = [dict(rois=dv((n_img * R, 5), torch.float32), labels=dv((n_img, self.C), torch.float32),
+                            masks=dv((n_img, R, self.words), torch.int32), ready=torch.cuda.Event(),
+                            free=torch.cuda.Event()) for _ in range(2)]
+            self.d_checksum = dv((2,), torch.float32)
+            self.copy_stream = torch.cuda.Stream(device=self.dev)
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in (self.hi_rois, self.hi_labels, self.hi_masks))
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in
                              (self.ho_labels, self.ho_iou, self.ho_weights, self.ho_valid, self.ho_checksum))
         self.d2h_bytes += sum(t.numel() * t.element_size() for t in (self.h_count, self.h_class, self.h_weight))
         self.h2d_bytes += self.h_keep.numel()
+        self._slot = 0
+        self._staged = False
 
-    def run_host(self, feat, grad_out, seg_x, weight, bias):
+    def stage_host_inputs(self):
+        """Enqueue the host->device copy of the CURRENT contents of hi_rois / hi_labels / hi_masks
+        into the idle device buffer, on the copy stream.  Call it for step i+1 before (or while)
+        step i computes; run_host() consumes the staged buffer."""
+        buf = self.di[self._slot ^ 1] if self._staged else self.di[self._slot]
+        buf["labels_host"] = self.hi_labels.numpy().copy()    # the sampling hop needs them on the host
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(buf["free"])          # its previous consumer has finished
+            buf["rois"].copy_(self.hi_rois, non_blocking=True)
+            buf["labels"].copy_(self.hi_labels, non_blocking=True)
+            buf["masks"].copy_(self.hi_masks, non_blocking=True)
+            buf["ready"].record(self.copy_stream)
+        return self
+
+    def run_host(self, feat, grad_out, seg_x, weight, bias, prefetch_next=True):
         """End-to-end step: host rois / labels / bit-packed masks -> device, the step, results ->
         host.  feat / seg_x / grad_out are produced on the device by the backbone, MaskFuse and
-        autograd in the real pipeline and therefore stay device tensors."""
-        self.di_rois.copy_(self.hi_rois, non_blocking=True)
-        self.di_labels.copy_(self.hi_labels, non_blocking=True)
-        self.di_masks.copy_(self.hi_masks, non_blocking=True)
-        self.run(feat, self.di_rois, grad_out, self.di_masks, seg_x, weight, bias, self.di_labels,
-                 self.hi_labels.numpy())
+        autograd in the real pipeline and therefore stay device tensors.
+        With prefetch_next the copy of the NEXT step's inputs (whatever is in the pinned input
+        buffers now) is enqueued on the copy stream first, so it overlaps this step's kernels;
+        every call therefore moves one full set of inputs host->device."""
+        cur_stream = torch.cuda.current_stream(self.dev)
+        if not self._staged:                                   # first call: nothing was prefetched
+            self.stage_host_inputs()
+            self._staged = True
+        buf = self.di[self._slot]
+        if prefetch_next:
+            self.stage_host_inputs()                           # goes to the other buffer
+        cur_stream.wait_event(buf["ready"])
+        self.run(feat, buf["rois"], grad_out, buf["masks"], seg_x, weight, bias, buf["labels"],
+                 buf["labels_host"])
+        buf["free"].record(cur_stream)
         self.d_checksum[0] = self.roi_out.view(-1)[::4099].sum()
         self.d_checksum[1] = self.grad_feat.view(-1)[::127].sum()
         self.ho_labels.copy_(self.pseudo_labels, non_blocking=True)
@@ -180,5 +209,9 @@ class CIMHeadStep:
         self.ho_weights.copy_(self.loss_weights, non_blocking=True)
         self.ho_valid.copy_(self.valid, non_blocking=True)
         self.ho_checksum.copy_(self.d_checksum, non_blocking=True)
-        torch.cuda.current_stream(self.dev).synchronize()
+        cur_stream.synchronize()                               # the host reads the results every step
+        if prefetch_next:
+            self._slot ^= 1
+        else:
+            self._staged = False
         return self
