@@ -15,8 +15,12 @@
 //     into tensor memory with one tcgen05.st.32x32b.x32 (lane = row, 32 columns per K-block) and
 //     the MMA takes A from TMEM.  The first version staged A in smem as well and was bound by the
 //     shared-memory port (L1 83 %, tensor pipe 45 %: profiles/r1_ncu_full_v1.txt).
-// A 6-stage mbarrier ring hands stages to the single MMA-issuing thread (M = 128, N = 256, K = 32
-// per instruction, 4 per stage) and tcgen05.commit returns the stage.  The pixel -> K-slot order
+//   * Each expanded B stage (128 rows) is used by TWO A tiles (2 x 128 rows, two accumulators):
+//     at M = 128 the UMMA reads its B operand at 64 B/clk, expanding B at the same rate would
+//     take the other half of the 128 B/clk shared-memory port (second version: L1 85 %, tensor
+//     pipe 58 %: profiles/r1_ncu_full_v2.txt); reusing the stage halves the store traffic.
+// A 4-stage mbarrier ring hands stages to the single MMA-issuing thread (M = 128, N = 128, K = 32
+// per instruction, 2 x 4 per stage) and tcgen05.commit returns the stage.  The pixel -> K-slot order
 // inside a K-block is a fixed permutation (the same for both operands), which a contraction does
 // not care about.
 //
@@ -27,25 +31,28 @@
 
 namespace {
 
-constexpr int TM = 128;                 // tile rows   (UMMA M)
-constexpr int TN = 256;                 // tile cols   (UMMA N)
+constexpr int TM = 256;                 // tile rows: two UMMA M = 128 sub-tiles sharing every B stage
+constexpr int TN = 128;                 // tile cols   (UMMA N)
+constexpr int UM = 128;                 // UMMA M
 constexpr int KB = 128;                 // pixels (= operand bytes per row) per K-block: one SW128 atom
-constexpr int STAGES = 6;
-constexpr int B_BYTES = TN * KB;        // 32 KB of expanded B operand per stage (smem)
+constexpr int STAGES = 4;
+constexpr int B_BYTES = TN * KB;        // 16 KB of expanded B operand per stage (smem)
 constexpr int STAGE_BYTES = B_BYTES;
-constexpr int A_COLS = KB / 4;          // 32 TMEM columns of expanded A operand per stage
+constexpr int A_COLS = KB / 4;          // 32 TMEM columns of expanded A operand per stage and sub-tile
 constexpr int EXP_WARPS = (TM + TN) / 32;          // 12 expander warps, one operand row per thread
 constexpr int MMA_WARP = EXP_WARPS;                // warp 12 issues the MMAs and owns TMEM
 constexpr int THREADS = (EXP_WARPS + 1) * 32;      // 416
-constexpr int EPI_WARPS = 8;                       // warps 0..7 drain the accumulator
+constexpr int EPI_WARPS = 8;                       // warps 0..7 drain the two accumulators
 constexpr int SPITCH = TN + 1;                     // int32 pitch of the transpose buffer
-constexpr int TMEM_COLS = 512;                     // accumulator: columns 0..255, A stages: 256 + 32 s
-constexpr int TMEM_A0 = TN;
-constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 128;
+constexpr int TMEM_COLS = 512;                     // accumulators: 0..127 and 128..255; A stages: 256 + 64 s + 32 t
+constexpr int TMEM_A0 = 2 * TN;
+constexpr size_t SI_BYTES = (size_t)TM * SPITCH * 4;                 // 132 KB transpose buffer (epilogue)
+constexpr size_t RING_BYTES = (size_t)STAGES * STAGE_BYTES;          // 64 KB
+constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (SI_BYTES > RING_BYTES ? SI_BYTES : RING_BYTES) + 128;
 
 // tcgen05 instruction descriptor (cute::UMMA::InstrDescriptor): S32 accumulate, INT8 x INT8,
-// both operands K-major, N = 256, M = 128
-constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((TN >> 3) << 17) | ((TM >> 4) << 24);
+// both operands K-major, N = 128, M = 128
+constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((TN >> 3) << 17) | ((UM >> 4) << 24);
 
 // shared memory matrix descriptor (cute::UMMA::SmemDescriptor), K-major SWIZZLE_128B:
 // start address >> 4, LBO (unused for swizzled K-major) = 1, SBO = 1024 B between 8-row groups,
@@ -126,18 +133,18 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char *stages = smem;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * STAGE_BYTES);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (SI_BYTES > RING_BYTES ? SI_BYTES : RING_BYTES));
     uint64_t *empty = full + STAGES;
     uint64_t *accum_full = empty + STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_full + 1);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int img = blockIdx.x / tiles_per_img;
-    // linear tile id -> (ti, tj): row block ti (128 rows) pairs with column blocks tj >= ti / 2
+    // linear tile id -> (ti, tj): row block ti (256 rows) pairs with column blocks (128) tj >= 2 ti
     int ti = 0, rem = blockIdx.x % tiles_per_img;
     const int ncb = (n + TN - 1) / TN;
-    while (rem >= ncb - (ti >> 1)) { rem -= ncb - (ti >> 1); ++ti; }
-    const int tj = (ti >> 1) + rem;
+    while (rem >= ncb - 2 * ti) { rem -= ncb - 2 * ti; ++ti; }
+    const int tj = 2 * ti + rem;
     const int row0 = ti * TM, col0 = tj * TN;
 
     if (tid == 0) {
@@ -159,14 +166,14 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
 
     if (warp < EXP_WARPS) {
         // ------------------------------------------------------------------ expanders
-        const bool is_a = tid < TM;                           // warps 0..3: A rows = TMEM lanes 32w..32w+31
+        const bool is_a = tid < TM;                           // warps 0..7: sub-tile warp / 4, TMEM lanes 32 (warp % 4)..
         const int lr = is_a ? tid : tid - TM;                 // row inside the A / B tile
         const int grow = (is_a ? row0 : col0) + lr;           // mask index inside the image
         const bool valid = grow < n;
         const uint4 *src = reinterpret_cast<const uint4 *>(packed + ((size_t)img * n + (valid ? grow : 0)) * words);
         const uint32_t row_off = (lr >> 3) * 1024 + (lr & 7) * 128;
         const uint32_t sw = lr & 7;
-        const uint32_t a_lane = tmem_base + ((uint32_t)(32 * warp) << 16) + TMEM_A0;
+        const uint32_t a_lane = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + TMEM_A0 + (uint32_t)((warp >> 2) * A_COLS);
         const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
         uint4 cur[2] = {zero4, zero4};                         // two K-blocks = one 32 B sector per row
         if (valid) { cur[0] = __ldg(src); if (nkb > 1) cur[1] = __ldg(src + 1); }
@@ -190,7 +197,7 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
 #pragma unroll
                         for (int g = 0; g < 8; ++g) o[q * 8 + g] = t[g];
                     }
-                    tc_st32(a_lane + (uint32_t)(s * A_COLS), o);     // includes tcgen05.wait::st
+                    tc_st32(a_lane + (uint32_t)(s * 2 * A_COLS), o);  // includes tcgen05.wait::st
                     tc_fence_before();
                 } else {
                     unsigned char *rowp = stages + (size_t)s * STAGE_BYTES + row_off;
@@ -219,10 +226,13 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
             tc_fence_after();
             if (lane == 0) {
                 const uint64_t bd = smem_desc(smem_u32(stages + (size_t)s * STAGE_BYTES));
-                const uint32_t a_t = tmem_base + TMEM_A0 + (uint32_t)(s * A_COLS);
+                const uint32_t a_t = tmem_base + TMEM_A0 + (uint32_t)(s * 2 * A_COLS);
 #pragma unroll
-                for (int k = 0; k < KB / 32; ++k)       // K = 32 bytes: 8 TMEM columns of A, +2 (x16 B) of B
-                    tc_mma_i8_ts(tmem_base, a_t + 8 * k, bd + 2 * k, (kb | k) != 0);
+                for (int t = 0; t < 2; ++t)             // the two A sub-tiles share this B stage
+#pragma unroll
+                    for (int k = 0; k < KB / 32; ++k)   // K = 32 bytes: 8 TMEM columns of A, +2 (x16 B) of B
+                        tc_mma_i8_ts(tmem_base + (uint32_t)(t * TN), a_t + (uint32_t)(t * A_COLS + 8 * k), bd + 2 * k,
+                                     (kb | k) != 0);
                 tc_commit(&empty[s]);                    // arrives when the MMAs above have read the stage
                 if (kb == nkb - 1) tc_commit(accum_full);
             }
@@ -239,17 +249,17 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
     if (warp < EPI_WARPS) {
         mbar_wait(accum_full, 0);
         tc_fence_after();
-        const int rl = 32 * (warp & 3) + lane;                   // TMEM lane = tile row
+        const int sub = warp >> 2;                                // accumulator / A sub-tile
+        const int rl = UM * sub + 32 * (warp & 3) + lane;          // tile row
         const int r = row0 + rl;
         const int a_r = r < n ? area[r] : 0;
-        const int chalf = (warp >> 2) * (TN / 2);
 #pragma unroll 1
-        for (int cc = 0; cc < TN / 2; cc += 32) {
+        for (int cc = 0; cc < TN; cc += 32) {
             int v[32];
-            tc_ld32(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(chalf + cc), v);
-            const int cbase = col0 + chalf + cc;
+            tc_ld32(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(sub * TN + cc), v);
+            const int cbase = col0 + cc;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sI[rl * SPITCH + chalf + cc + j] = v[j];
+            for (int j = 0; j < 32; ++j) sI[rl * SPITCH + cc + j] = v[j];
             if (r < n) {
                 if (cbase + 32 <= n && (n & 7) == 0) {           // 16 B vector stores
                     uint4 *pi = reinterpret_cast<uint4 *>(iou + (size_t)r * n + cbase);
@@ -282,17 +292,18 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
         }
         tc_fence_before();
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-        // mirror block: out[c][r] for the columns whose own tile (c / 128, r / 256) is not computed,
-        // i.e. 256 * (ti / 2 + 1) <= 128 * (c / 128)
+        // mirror block out[c][r]: needed for the row sub-blocks (128 rows) whose own tile
+        // (row block r / 256, column block c / 128) is not computed, i.e. c / 128 < 2 * (r / 256)
         for (int cl = warp; cl < TN; cl += EPI_WARPS) {
             const int c = col0 + cl;
             if (c >= n) break;
-            if (TN * ((ti >> 1) + 1) > TM * (c / TM)) continue;
             const int a_c = area[c];
 #pragma unroll
             for (int h = 0; h < TM / 32; ++h) {
                 const int rl2 = h * 32 + lane, r2 = row0 + rl2;
                 if (r2 >= n) continue;
+                // element (c, r2) belongs to tile (c / 256, r2 / 128): computed iff r2 / 128 >= 2 * (c / 256)
+                if ((r2 / TN) >= 2 * (c / TM)) continue;
                 const int I = sI[rl2 * SPITCH + cl], a_r2 = area[r2];
                 const size_t o = (size_t)c * n + r2;
                 iou[o] = __float2half_rn(__fdiv_rn((float)I, (float)(a_c + a_r2 - I)));
@@ -321,7 +332,7 @@ int cim_mask_overlap_tc_launch(const uint32_t *packed, const int32_t *area, int 
                                int32_t *inter, __half *iou, __half *asy, cudaStream_t st) {
     const int nrb = (n + TM - 1) / TM, ncb = (n + TN - 1) / TN;
     int tiles = 0;
-    for (int i = 0; i < nrb; ++i) tiles += ncb - (i >> 1);
+    for (int i = 0; i < nrb; ++i) tiles += ncb - 2 * i;
     cudaFuncSetAttribute(mask_overlap_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     mask_overlap_tc_kernel<<<(unsigned)(tiles * n_img), THREADS, SMEM_BYTES, st>>>(packed, area, n, words, tiles,
                                                                                   inter, iou, asy);
