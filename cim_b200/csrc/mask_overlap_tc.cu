@@ -3,56 +3,63 @@
 // inter[i,j] = sum_p m_i[p] * m_j[p] is a dense R x HW x R contraction of 0/1 operands
 // (2.1 TFLOP per image at R = 2000, 512x512 masks), far too much for the
 // popcount pipe (mask_overlap.cu: 16 POPC lanes / clk / SM).  Here it runs as
-// tcgen05.mma.kind::i8 with S32 accumulation in TMEM, which is exact.
+// tcgen05.mma.kind::i8 (M = 128, N = 256, K = 32) with S32 accumulation in TMEM, which is exact.
 //
-// Operands never exist as bytes in HBM: masks stay bit-packed (32 px / word).  Per K-block of
-// 128 pixels, 12 expander warps read 16 B of each of the tile's 128 + 256 mask rows and turn
-// every bit into a byte 0x00 / 0xFF with PRMT's sign-replicate mode (one PRMT per 4 pixels) --
-// 0xFF is -1 as INT8, so a pixel common to both masks contributes (-1)*(-1) = +1.
-//   * The 256 B-operand rows are stored straight into the canonical K-major SWIZZLE_128B layout
-//     the UMMA smem descriptor expects (8-row x 128 B atoms, 16 B chunk index XOR row % 8).
-//   * The 128 A-operand rows never touch shared memory: each thread writes its row's 128 bytes
-//     into tensor memory with one tcgen05.st.32x32b.x32 (lane = row, 32 columns per K-block) and
-//     the MMA takes A from TMEM.  The first version staged A in smem as well and was bound by the
-//     shared-memory port (L1 83 %, tensor pipe 45 %: profiles/r1_ncu_full_v1.txt).
-//   * Each expanded B stage (128 rows) is used by TWO A tiles (2 x 128 rows, two accumulators):
-//     at M = 128 the UMMA reads its B operand at 64 B/clk, expanding B at the same rate would
-//     take the other half of the 128 B/clk shared-memory port (second version: L1 85 %, tensor
-//     pipe 58 %: profiles/r1_ncu_full_v2.txt); reusing the stage halves the store traffic.
-// A 4-stage mbarrier ring hands stages to the single MMA-issuing thread (M = 128, N = 128, K = 32
-// per instruction, 2 x 4 per stage) and tcgen05.commit returns the stage.  The pixel -> K-slot order
-// inside a K-block is a fixed permutation (the same for both operands), which a contraction does
-// not care about.
+// Operands never exist as bytes in HBM: masks stay bit-packed (32 px / word).  A bit becomes a
+// byte 0x00 / 0xFF with PRMT's sign-replicate mode (one PRMT per 4 pixels); 0xFF is -1 as INT8, so
+// a pixel common to both masks contributes (-1)*(-1) = +1.  The pixel -> K-slot order inside a
+// K-block is a fixed permutation, the same for both operands, which a contraction ignores.
 //
-// Only tiles touching the upper triangle are computed; the epilogue reads the accumulator from
-// TMEM (tcgen05.ld), applies iou = I / (a_i + a_j - I), asy = I / a_j in fp32 -> fp16, and writes
-// the mirror block through a shared-memory transpose (asy is not symmetric, I is).
+// Warp roles of one CTA (one 128 x 256 output tile, K = all pixels, 128 px per K-block):
+//   loader (1 warp)     cp.async (LDGSTS, L1 bypass) of 16 B per operand row and K-block into a
+//                       3-buffer smem staging ring, 4 K-blocks per group, completion through
+//                       cp.async.mbarrier.arrive.noinc.
+//   expanders (16)      two groups that ALTERNATE K-blocks, so the ALU phase (expand) of one group
+//                       overlaps the store + release-fence phase of the other:
+//                         A rows (128): one row per thread, written to TENSOR MEMORY with one
+//                           tcgen05.st.32x32b.x32 (lane = row, 32 columns per K-block);
+//                         B rows (256): two rows per thread, stored into the canonical K-major
+//                           SWIZZLE_128B smem layout (8-row x 128 B atoms, chunk ^= row % 8).
+//   MMA issuer (1)      waits for a stage, issues 4 x tcgen05.mma (A from TMEM, B from smem),
+//                       tcgen05.commit hands the stage back.
+//   epilogue            warps 0..7: tcgen05.ld, fp32 div.rn, cvt.rn.f16, 16 B stores; the mirror
+//                       block goes through a shared-memory transpose (asy is not symmetric).
+// History of this kernel, with the ncu evidence, is in DESIGN.md section 4.3.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 
-constexpr int TM = 256;                 // tile rows: two UMMA M = 128 sub-tiles sharing every B stage
-constexpr int TN = 128;                 // tile cols   (UMMA N)
-constexpr int UM = 128;                 // UMMA M
+constexpr int TM = 128, TN = 256;       // output tile = UMMA M x N
 constexpr int KB = 128;                 // pixels (= operand bytes per row) per K-block: one SW128 atom
-constexpr int STAGES = 4;
-constexpr int B_BYTES = TN * KB;        // 16 KB of expanded B operand per stage (smem)
-constexpr int STAGE_BYTES = B_BYTES;
-constexpr int A_COLS = KB / 4;          // 32 TMEM columns of expanded A operand per stage and sub-tile
-constexpr int EXP_WARPS = (TM + TN) / 32;          // 12 expander warps, one operand row per thread
-constexpr int MMA_WARP = EXP_WARPS;                // warp 12 issues the MMAs and owns TMEM
-constexpr int THREADS = (EXP_WARPS + 1) * 32;      // 416
-constexpr int EPI_WARPS = 8;                       // warps 0..7 drain the two accumulators
-constexpr int SPITCH = TN + 1;                     // int32 pitch of the transpose buffer
-constexpr int TMEM_COLS = 512;                     // accumulators: 0..127 and 128..255; A stages: 256 + 64 s + 32 t
-constexpr int TMEM_A0 = 2 * TN;
-constexpr size_t SI_BYTES = (size_t)TM * SPITCH * 4;                 // 132 KB transpose buffer (epilogue)
-constexpr size_t RING_BYTES = (size_t)STAGES * STAGE_BYTES;          // 64 KB
-constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (SI_BYTES > RING_BYTES ? SI_BYTES : RING_BYTES) + 128;
+constexpr int A_COLS = KB / 4;          // 32 TMEM columns of expanded A operand per stage
+constexpr int TMEM_COLS = 512;          // accumulator: columns 0..255; A stages: 256 + 32 s
+constexpr int TMEM_A0 = TN;
+constexpr int ROWS = TM + TN;           // operand rows per tile
+constexpr int GK = 4;                   // K-blocks per load group
+constexpr int NBUF = 3;                 // staging buffers [GK][ROWS][16 B]
+constexpr int BUF_BYTES = GK * ROWS * 16;
+constexpr int B_BYTES = TN * KB;        // 32 KB of expanded B operand per stage
+constexpr int NEXP = 16;                // expander warps: 0-3 A even, 4-7 A odd, 8-11 B even, 12-15 B odd K-blocks
+constexpr int MMA_WARP = NEXP, LOAD_WARP = NEXP + 1;
+constexpr int THREADS = (NEXP + 2) * 32;
+constexpr int EPI_WARPS = 8;
+constexpr int SPITCH = TN + 1;          // int32 pitch of the transpose buffer
+constexpr size_t SI_BYTES = (size_t)TM * SPITCH * 4;
 
-// tcgen05 instruction descriptor (cute::UMMA::InstrDescriptor): S32 accumulate, INT8 x INT8,
-// both operands K-major, N = 128, M = 128
-constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((TN >> 3) << 17) | ((UM >> 4) << 24);
+template <int STAGES_>
+struct Cfg {
+    static constexpr int STAGES = STAGES_;
+    static constexpr size_t RING_BYTES = (size_t)STAGES * B_BYTES + (size_t)NBUF * BUF_BYTES;
+    static constexpr size_t BODY_BYTES = SI_BYTES > RING_BYTES ? SI_BYTES : RING_BYTES;
+    static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + BODY_BYTES + 256;
+    static_assert(STAGES % 2 == 0, "the two expander groups own alternate stages");
+    static_assert(TN + STAGES * A_COLS <= TMEM_COLS, "TMEM budget");
+};
+
+// tcgen05 instruction descriptor (cute::UMMA::InstrDescriptor): S32 accumulate, INT8 x INT8, both
+// operands K-major, N = 256, M = 128
+constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((TN >> 3) << 17) | ((TM >> 4) << 24);
 
 // shared memory matrix descriptor (cute::UMMA::SmemDescriptor), K-major SWIZZLE_128B:
 // start address >> 4, LBO (unused for swizzled K-major) = 1, SBO = 1024 B between 8-row groups,
@@ -108,9 +115,8 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, int (&v)[32]) {
 
 // 32 mask bits -> 32 operand bytes (8 words): word g, byte b = 0xFF iff bit 8b+g is set.
 // (w << (7-g)) moves bit 8b+g to the top of byte b; PRMT selector 0xBA98 replicates each byte's
-// sign bit over the byte.
-// (inline PTX: the __byte_perm intrinsic masks the selector to 3 bits per byte and would drop the
-// replicate flag.)
+// sign bit over the byte.  Inline PTX: the __byte_perm intrinsic masks the selector to 3 bits per
+// byte and would drop the replicate flag.
 __device__ __forceinline__ uint32_t sign_bytes(uint32_t x) {
     uint32_t r;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(0u), "r"(0xBA98u));
@@ -120,36 +126,54 @@ __device__ __forceinline__ void expand32(uint32_t w, uint32_t (&o)[8]) {
 #pragma unroll
     for (int g = 0; g < 8; ++g) o[g] = sign_bytes(w << (7 - g));
 }
+// one operand row of a K-block (16 packed bytes) -> 128 operand bytes in the swizzled smem row
+__device__ __forceinline__ void expand_row_to_smem(const uint4 &p, unsigned char *stage, const uint32_t (&choff)[8]) {
+    const uint32_t pw[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t o[8];
+        expand32(pw[q], o);
+        *reinterpret_cast<uint4 *>(stage + choff[2 * q]) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4 *>(stage + choff[2 * q + 1]) = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+}
 
 __device__ __forceinline__ __half2 pack_ratio2(int i0, int d0, int i1, int d1) {
     return __halves2half2(__float2half_rn(__fdiv_rn((float)i0, (float)d0)),
                           __float2half_rn(__fdiv_rn((float)i1, (float)d1)));
 }
 
+template <class K>
 __global__ void __launch_bounds__(THREADS, 1)
 mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__restrict__ area_all, int n,
                        long long words, int tiles_per_img, int32_t *__restrict__ inter_all,
                        __half *__restrict__ iou_all, __half *__restrict__ asy_all) {
+    constexpr int STAGES = K::STAGES;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    unsigned char *stages = smem;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (SI_BYTES > RING_BYTES ? SI_BYTES : RING_BYTES));
-    uint64_t *empty = full + STAGES;
+    unsigned char *stages = smem;                                         // [STAGES][32 KB] expanded B
+    unsigned char *staging = stages + (size_t)STAGES * B_BYTES;           // [NBUF][GK][ROWS][16 B] packed bits
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + K::BODY_BYTES);  // [STAGES] stage expanded
+    uint64_t *empty = full + STAGES;                                      // [STAGES] stage consumed by the MMAs
     uint64_t *accum_full = empty + STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_full + 1);
+    uint64_t *loaded = accum_full + 1;             // [NBUF] staging buffer filled (32 loader lanes)
+    uint64_t *consumed = loaded + NBUF;            // [NBUF] staging buffer read by every expander warp
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(consumed + NBUF);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int img = blockIdx.x / tiles_per_img;
-    // linear tile id -> (ti, tj): row block ti (256 rows) pairs with column blocks (128) tj >= 2 ti
+    // linear tile id -> (ti, tj): row block ti (128 rows) pairs with the column blocks (256) that
+    // reach the diagonal or lie right of it: 256 (tj + 1) > 128 ti  <=>  tj >= ti / 2
     int ti = 0, rem = blockIdx.x % tiles_per_img;
     const int ncb = (n + TN - 1) / TN;
-    while (rem >= ncb - 2 * ti) { rem -= ncb - 2 * ti; ++ti; }
-    const int tj = 2 * ti + rem;
+    while (rem >= ncb - (ti >> 1)) { rem -= ncb - (ti >> 1); ++ti; }
+    const int tj = (ti >> 1) + rem;
     const int row0 = ti * TM, col0 = tj * TN;
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], EXP_WARPS); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], NEXP / 2); mbar_init(&empty[s], 1); }
         mbar_init(accum_full, 1);
+        for (int i = 0; i < NBUF; ++i) { mbar_init(&loaded[i], 32); mbar_init(&consumed[i], NEXP); }
         fence_mbar_init();
     }
     if (warp == MMA_WARP) {
@@ -163,60 +187,95 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int nkb = (int)(words / 4);
+    const int ngroups = (nkb + GK - 1) / GK;
 
-    if (warp < EXP_WARPS) {
+    if (warp < NEXP) {
         // ------------------------------------------------------------------ expanders
-        const bool is_a = tid < TM;                           // warps 0..7: sub-tile warp / 4, TMEM lanes 32 (warp % 4)..
-        const int lr = is_a ? tid : tid - TM;                 // row inside the A / B tile
-        const int grow = (is_a ? row0 : col0) + lr;           // mask index inside the image
-        const bool valid = grow < n;
-        const uint4 *src = reinterpret_cast<const uint4 *>(packed + ((size_t)img * n + (valid ? grow : 0)) * words);
-        const uint32_t row_off = (lr >> 3) * 1024 + (lr & 7) * 128;
-        const uint32_t sw = lr & 7;
-        const uint32_t a_lane = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + TMEM_A0 + (uint32_t)((warp >> 2) * A_COLS);
-        const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-        uint4 cur[2] = {zero4, zero4};                         // two K-blocks = one 32 B sector per row
-        if (valid) { cur[0] = __ldg(src); if (nkb > 1) cur[1] = __ldg(src + 1); }
-        for (int kb2 = 0; kb2 < nkb; kb2 += 2) {
-            uint4 nxt[2] = {zero4, zero4};
-            if (valid && kb2 + 2 < nkb) nxt[0] = __ldg(src + kb2 + 2);
-            if (valid && kb2 + 3 < nkb) nxt[1] = __ldg(src + kb2 + 3);
+        const bool is_a = warp < 8;
+        const int grp = (warp >> 2) & 1;                      // K-blocks kb == grp (mod 2)
+        const int q4 = warp & 3;
+        // A: tile row 32 q4 + lane (= TMEM lane).  B: tile rows 64 q4 + lane and + 32.
+        const int ra = 32 * q4 + lane;
+        const int rb0 = 64 * q4 + lane, rb1 = rb0 + 32;
+        const uint32_t a_lane = tmem_base + ((uint32_t)(32 * q4) << 16) + TMEM_A0;
+        uint32_t ch0[8], ch1[8];                              // swizzled chunk offsets of the two B rows
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            ch0[c] = (rb0 >> 3) * 1024 + (rb0 & 7) * 128 + ((c ^ (rb0 & 7)) << 4);
+            ch1[c] = (rb1 >> 3) * 1024 + (rb1 & 7) * 128 + ((c ^ (rb1 & 7)) << 4);
+        }
+        const int srow0 = is_a ? ra : TM + rb0, srow1 = TM + rb1;     // rows inside a staging buffer
+        for (int g = 0; g < ngroups; ++g) {
+            const int buf = g % NBUF;
+            mbar_wait(&loaded[buf], (g / NBUF) & 1);
+            // this thread's packed bits for its two K-blocks of the group: kk = grp and grp + 2
+            const unsigned char *sb = staging + (size_t)buf * BUF_BYTES;
+            uint4 p0[2], p1[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int kb = kb2 + h;
+                const int kk = grp + 2 * h;
+                p0[h] = *reinterpret_cast<const uint4 *>(sb + (kk * ROWS + srow0) * 16);
+                p1[h] = p0[h];
+                if (!is_a) p1[h] = *reinterpret_cast<const uint4 *>(sb + (kk * ROWS + srow1) * 16);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&consumed[buf]);     // the loader may refill this buffer
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int kb = g * GK + grp + 2 * h;
                 if (kb >= nkb) break;
                 const int s = kb % STAGES;
                 if (kb >= STAGES) mbar_wait(&empty[s], ((kb / STAGES) - 1) & 1);
-                const uint32_t pw[4] = {cur[h].x, cur[h].y, cur[h].z, cur[h].w};
                 if (is_a) {
+                    const uint32_t pw[4] = {p0[h].x, p0[h].y, p0[h].z, p0[h].w};
                     uint32_t o[32];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         uint32_t t[8];
                         expand32(pw[q], t);
 #pragma unroll
-                        for (int g = 0; g < 8; ++g) o[q * 8 + g] = t[g];
+                        for (int gg = 0; gg < 8; ++gg) o[q * 8 + gg] = t[gg];
                     }
-                    tc_st32(a_lane + (uint32_t)(s * 2 * A_COLS), o);  // includes tcgen05.wait::st
+                    tc_st32(a_lane + (uint32_t)(s * A_COLS), o);      // includes tcgen05.wait::st
                     tc_fence_before();
                 } else {
-                    unsigned char *rowp = stages + (size_t)s * STAGE_BYTES + row_off;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint32_t o[8];
-                        expand32(pw[q], o);
-                        // 16 B chunks 2q and 2q+1 of the 128 B row, XOR-swizzled with row % 8
-                        *reinterpret_cast<uint4 *>(rowp + (((2 * q) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-                        *reinterpret_cast<uint4 *>(rowp + (((2 * q + 1) ^ sw) << 4)) =
-                            make_uint4(o[4], o[5], o[6], o[7]);
-                    }
+                    unsigned char *stg = stages + (size_t)s * B_BYTES;
+                    expand_row_to_smem(p0[h], stg, ch0);
+                    expand_row_to_smem(p1[h], stg, ch1);
                     fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full[s]);
             }
-            cur[0] = nxt[0];
-            cur[1] = nxt[1];
+        }
+    } else if (warp == LOAD_WARP) {
+        // ------------------------------------------------------------------ loader
+        // lane l streams rows l, l + 32, ...; staging layout [kk][row][16 B] keeps both the LDGSTS
+        // writes and the expanders' LDS.128 reads conflict-free.  Rows past n and K-blocks past the
+        // end are zero-filled (src-size 0).
+        const uint32_t *img_base = packed + (size_t)img * n * words;
+        for (int g = 0; g < ngroups; ++g) {
+            const int buf = g % NBUF;
+            if (g >= NBUF) mbar_wait(&consumed[buf], ((g / NBUF) - 1) & 1);
+            unsigned char *dst = staging + (size_t)buf * BUF_BYTES;
+#pragma unroll 4
+            for (int t = lane; t < ROWS; t += 32) {
+                const int grow = t < TM ? row0 + t : col0 + (t - TM);
+                const bool rv = grow < n;
+                const uint32_t *rsrc = img_base + (size_t)(rv ? grow : 0) * words;
+#pragma unroll
+                for (int kk = 0; kk < GK; ++kk) {
+                    const int kb = g * GK + kk;
+                    const bool ok = rv && kb < nkb;
+                    const uint32_t nbytes = ok ? 16u : 0u;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
+                                     smem_u32(dst + (kk * ROWS + t) * 16)),
+                                 "l"(rsrc + (ok ? kb * 4 : 0)), "r"(nbytes)
+                                 : "memory");
+                }
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&loaded[buf]))
+                         : "memory");
         }
     } else {
         // ------------------------------------------------------------------ MMA issuer
@@ -225,14 +284,11 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
             mbar_wait(&full[s], (kb / STAGES) & 1);
             tc_fence_after();
             if (lane == 0) {
-                const uint64_t bd = smem_desc(smem_u32(stages + (size_t)s * STAGE_BYTES));
-                const uint32_t a_t = tmem_base + TMEM_A0 + (uint32_t)(s * 2 * A_COLS);
+                const uint64_t bd = smem_desc(smem_u32(stages + (size_t)s * B_BYTES));
+                const uint32_t a_t = tmem_base + TMEM_A0 + (uint32_t)(s * A_COLS);
 #pragma unroll
-                for (int t = 0; t < 2; ++t)             // the two A sub-tiles share this B stage
-#pragma unroll
-                    for (int k = 0; k < KB / 32; ++k)   // K = 32 bytes: 8 TMEM columns of A, +2 (x16 B) of B
-                        tc_mma_i8_ts(tmem_base + (uint32_t)(t * TN), a_t + (uint32_t)(t * A_COLS + 8 * k), bd + 2 * k,
-                                     (kb | k) != 0);
+                for (int k = 0; k < KB / 32; ++k)       // K = 32 bytes: 8 TMEM columns of A, +2 (x16 B) of B
+                    tc_mma_i8_ts(tmem_base, a_t + 8 * k, bd + 2 * k, (kb | k) != 0);
                 tc_commit(&empty[s]);                    // arrives when the MMAs above have read the stage
                 if (kb == nkb - 1) tc_commit(accum_full);
             }
@@ -241,7 +297,7 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
     }
 
     // ---------------------------------------------------------------------- epilogue
-    int32_t *sI = reinterpret_cast<int32_t *>(stages);          // [TM][SPITCH], reuses the stage ring
+    int32_t *sI = reinterpret_cast<int32_t *>(stages);          // [TM][SPITCH], reuses the rings
     const int32_t *area = area_all + (size_t)img * n;
     int32_t *inter = inter_all ? inter_all + (size_t)img * n * n : nullptr;
     __half *iou = iou_all + (size_t)img * n * n;
@@ -249,17 +305,17 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
     if (warp < EPI_WARPS) {
         mbar_wait(accum_full, 0);
         tc_fence_after();
-        const int sub = warp >> 2;                                // accumulator / A sub-tile
-        const int rl = UM * sub + 32 * (warp & 3) + lane;          // tile row
+        const int rl = 32 * (warp & 3) + lane;                   // TMEM lane = tile row
         const int r = row0 + rl;
         const int a_r = r < n ? area[r] : 0;
+        const int chalf = (warp >> 2) * (TN / 2);
 #pragma unroll 1
-        for (int cc = 0; cc < TN; cc += 32) {
+        for (int cc = 0; cc < TN / 2; cc += 32) {
             int v[32];
-            tc_ld32(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(sub * TN + cc), v);
-            const int cbase = col0 + cc;
+            tc_ld32(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(chalf + cc), v);
+            const int cbase = col0 + chalf + cc;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sI[rl * SPITCH + cc + j] = v[j];
+            for (int j = 0; j < 32; ++j) sI[rl * SPITCH + chalf + cc + j] = v[j];
             if (r < n) {
                 if (cbase + 32 <= n && (n & 7) == 0) {           // 16 B vector stores
                     uint4 *pi = reinterpret_cast<uint4 *>(iou + (size_t)r * n + cbase);
@@ -292,18 +348,17 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
         }
         tc_fence_before();
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-        // mirror block out[c][r]: needed for the row sub-blocks (128 rows) whose own tile
-        // (row block r / 256, column block c / 128) is not computed, i.e. c / 128 < 2 * (r / 256)
+        // mirror block out[c][r2]: written unless the tile that owns (c, r2), i.e. (c / 128, r2 / 256),
+        // is computed itself: 256 (r2 / 256 + 1) > 128 (c / 128); r2 / 256 == ti / 2 for the whole tile
         for (int cl = warp; cl < TN; cl += EPI_WARPS) {
             const int c = col0 + cl;
             if (c >= n) break;
+            if (TN * ((ti >> 1) + 1) > TM * (c / TM)) continue;
             const int a_c = area[c];
 #pragma unroll
             for (int h = 0; h < TM / 32; ++h) {
                 const int rl2 = h * 32 + lane, r2 = row0 + rl2;
                 if (r2 >= n) continue;
-                // element (c, r2) belongs to tile (c / 256, r2 / 128): computed iff r2 / 128 >= 2 * (c / 256)
-                if ((r2 / TN) >= 2 * (c / TM)) continue;
                 const int I = sI[rl2 * SPITCH + cl], a_r2 = area[r2];
                 const size_t o = (size_t)c * n + r2;
                 iou[o] = __float2half_rn(__fdiv_rn((float)I, (float)(a_c + a_r2 - I)));
@@ -321,20 +376,33 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
     }
 }
 
+using CfgDefault = Cfg<4>;
+
+template <class K>
+static int launch(const uint32_t *packed, const int32_t *area, int n_img, int n, long long words, int32_t *inter,
+                  __half *iou, __half *asy, cudaStream_t st) {
+    const int nrb = (n + TM - 1) / TM, ncb = (n + TN - 1) / TN;
+    int tiles = 0;
+    for (int i = 0; i < nrb; ++i) tiles += ncb - (i >> 1);
+    cudaFuncSetAttribute(mask_overlap_tc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES);
+    mask_overlap_tc_kernel<K><<<(unsigned)(tiles * n_img), THREADS, K::SMEM_BYTES, st>>>(packed, area, n, words, tiles,
+                                                                                        inter, iou, asy);
+    return cim_launch_status();
+}
+
 }  // namespace
 
 // true when the tensor-core path can take this problem (else the popcount kernel runs)
 bool cim_mask_overlap_tc_eligible(int n, long long words) {
-    return n >= 64 && words >= 4 && (words % 4) == 0 && (size_t)cim_max_smem_optin() >= SMEM_BYTES;
+    return n >= 64 && words >= 4 && (words % 4) == 0 && (size_t)cim_max_smem_optin() >= CfgDefault::SMEM_BYTES;
 }
 
 int cim_mask_overlap_tc_launch(const uint32_t *packed, const int32_t *area, int n_img, int n, long long words,
                                int32_t *inter, __half *iou, __half *asy, cudaStream_t st) {
-    const int nrb = (n + TM - 1) / TM, ncb = (n + TN - 1) / TN;
-    int tiles = 0;
-    for (int i = 0; i < nrb; ++i) tiles += ncb - 2 * i;
-    cudaFuncSetAttribute(mask_overlap_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-    mask_overlap_tc_kernel<<<(unsigned)(tiles * n_img), THREADS, SMEM_BYTES, st>>>(packed, area, n, words, tiles,
-                                                                                  inter, iou, asy);
-    return cim_launch_status();
+    // CIM_OVERLAP_VARIANT is a tuning aid (pipeline-depth experiments); unset = the default
+    const char *v = getenv("CIM_OVERLAP_VARIANT");
+    switch (v ? atoi(v) : 0) {
+        case 1: return launch<Cfg<2>>(packed, area, n_img, n, words, inter, iou, asy, st);
+        default: return launch<CfgDefault>(packed, area, n_img, n, words, inter, iou, asy, st);
+    }
 }
