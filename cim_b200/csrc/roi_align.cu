@@ -19,7 +19,7 @@
 //                  the 7 column sums of a row are added into the output rows whose window holds
 //                  that row (49 accumulators in registers); the 32 x 49 outputs are staged in
 //                  smem and leave with one 6272-byte cp.async.bulk (UBLKCP) per (roi, 32 ch).
-//        backward: gradients + descriptors of the ROIs stream through an 8-slot mbarrier ring
+//        backward: gradients + descriptors stream through a 3-slot mbarrier ring of 4 ROIs each
 //                  (cp.async.bulk, no CTA-wide barrier); warp w of 16 owns the tile row pairs
 //                  (y >> 1) % 16 == w, so every tile address has exactly one writer and ROIs are
 //                  applied in index order: no atomics, bit-reproducible.
@@ -34,7 +34,7 @@ constexpr int PH = 7, PW = 7, NBIN = 49;
 constexpr int MAXT = 8;             // max collapsed taps per bin and axis in a descriptor
 constexpr int DESC_WORDS = 160;     // 640 B per ROI
 enum {
-    D_B = 0, D_FLAGY = 1, D_FLAGX = 2, D_TX = 3, D_Y0 = 4, D_Y1 = 5, D_XINC = 6,
+    D_B = 0, D_FLAGY = 1, D_FLAGX = 2, D_TX = 3, D_Y0 = 4, D_Y1 = 5, D_XINC = 6, D_OWN = 7,
     D_YLO = 8, D_YN = 16, D_XLO = 24, D_XN = 32, D_WY = 40, D_WX = 96
 };
 constexpr int WS_HDR_BYTES = 256;   // word 0: "rois not grouped by image" flag
@@ -147,6 +147,10 @@ __global__ void roi_prep_kernel(const float *__restrict__ rois, int K, int B, in
         if (y1 == 0) y0 = 0;
         d[D_Y0] = y0;
         d[D_Y1] = y1;
+        // backward: which of the 16 warps own a row of [y0, y1)?  warp w owns the row pairs (y >> 1) % 16 == w
+        int own = 0;
+        for (int y = y0; y < y1 && own != 0xffff; ++y) own |= 1 << ((y >> 1) & 15);
+        d[D_OWN] = flag ? 0 : own;
         d[D_YLO + 7] = 0;
         d[D_YN + 7] = 0;
     } else {
@@ -352,9 +356,10 @@ roi_align_fwd_tile_kernel(const float *__restrict__ feat, const int *__restrict_
 
 // ----------------------------------------------------------------------------- tile: backward
 constexpr int NWB = 16;             // consumer warps of the backward CTA; warp w owns row pairs
-                                    // {y : (y >> 1) % 16 == w}
-constexpr int NS = 8;               // ring slots (one ROI each: 32 x 49 gradients + its descriptor)
-constexpr int SLOT_FLOATS = STAGE_FLOATS + DESC_WORDS;
+                                    // {y : (y >> 1) % 16 == w}  (D_OWN is computed for exactly this map)
+constexpr int NBR = 4;              // ROIs per ring slot: one full/empty barrier round per 4 ROIs
+constexpr int NS = 3;               // ring slots
+constexpr int SLOT_FLOATS = NBR * (STAGE_FLOATS + DESC_WORDS);
 
 template <int T, bool XINC>
 __device__ __forceinline__ void bwd_rows(float *__restrict__ tile_c, int W, const int *d,
@@ -442,7 +447,7 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
                           float *__restrict__ grad_feat, int B, int C, int H, int W, int pitch) {
     extern __shared__ __align__(128) float smem[];
     float *tile = smem;
-    float *ring = smem + (size_t)CH * pitch;                                   // [NS][1568 grads + 160 desc]
+    float *ring = smem + (size_t)CH * pitch;                 // [NS][NBR x 1568 grads | NBR x 160 desc words]
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)NS * SLOT_FLOATS);
     uint64_t *empty = full + NS;
 
@@ -460,11 +465,13 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
     const int is = __ldg(img_start + b);
     const int n = __ldg(hdr) != 0 ? 0 : __ldg(img_start + b + 1) - is;
 
-    // producer duty (lane 0 of warp 0): ROI j goes to slot j % NS once every warp has released
-    // ROI j - NS.  `must` = the ROI warp 0 itself is about to read: then the wait is blocking.
+    // producer duty (lane 0 of warp 0): batch j (NBR consecutive ROIs: gradients + descriptors) goes
+    // to slot j % NS once every warp has released batch j - NS.  `must` = the batch warp 0 itself is
+    // about to read: then the wait is blocking, otherwise it is only tried.
+    const int nbatch = (n + NBR - 1) / NBR;
     int issued = 0;
     auto produce = [&](int want, int must) {
-        while (issued < want && issued < n) {
+        while (issued < want && issued < nbatch) {
             const int s = issued % NS;
             if (issued >= NS) {
                 const uint32_t par = ((issued / NS) - 1) & 1;
@@ -472,28 +479,31 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
                 else if (!mbar_test(&empty[s], par)) break;
             }
             float *slot = ring + (size_t)s * SLOT_FLOATS;
-            mbar_expect_tx(&full[s], (STAGE_FLOATS + DESC_WORDS) * 4);
-            bulk_g2s(slot, grad_out + ((size_t)(is + issued) * C + c0) * NBIN, STAGE_FLOATS * 4, &full[s]);
-            bulk_g2s(slot + STAGE_FLOATS, descs + (size_t)(is + issued) * DESC_WORDS, DESC_WORDS * 4, &full[s]);
+            const int first = issued * NBR, cnt = min(NBR, n - first);
+            mbar_expect_tx(&full[s], (uint32_t)cnt * (STAGE_FLOATS + DESC_WORDS) * 4);
+            for (int j = 0; j < cnt; ++j)
+                bulk_g2s(slot + j * STAGE_FLOATS, grad_out + ((size_t)(is + first + j) * C + c0) * NBIN,
+                         STAGE_FLOATS * 4, &full[s]);
+            bulk_g2s(slot + NBR * STAGE_FLOATS, descs + (size_t)(is + first) * DESC_WORDS,
+                     (uint32_t)cnt * DESC_WORDS * 4, &full[s]);
             ++issued;
         }
     };
     if (tid == 0) produce(NS, -1);
 
     float *tile_c = tile + lane * pitch;
-    for (int i = 0; i < n; ++i) {
-        if (tid == 0) produce(i + NS, i);
-        const int s = i % NS;
-        mbar_wait(&full[s], (i / NS) & 1);
+    for (int bi = 0; bi < nbatch; ++bi) {
+        if (tid == 0) produce(bi + NS, bi);
+        const int s = bi % NS;
+        mbar_wait(&full[s], (bi / NS) & 1);
         const float *slot = ring + (size_t)s * SLOT_FLOATS;
-        const int *d = reinterpret_cast<const int *>(slot + STAGE_FLOATS);
-        const int2 yr = *reinterpret_cast<const int2 *>(d + D_Y0);
-        const int y0 = yr.x, y1 = yr.y;
-        // does this warp own a row of [y0, y1)?  pairs 2w + 32m
-        bool mine = false;
-        for (int yb = 2 * warp; yb < y1; yb += 2 * NWB) mine |= (yb + 2 > y0);
-        if (mine && (d[D_FLAGY] | d[D_FLAGX]) == 0) {
-            const float *g = slot + lane * NBIN;
+        const int cnt = min(NBR, n - bi * NBR);
+        for (int j = 0; j < cnt; ++j) {
+            const int *d = reinterpret_cast<const int *>(slot + NBR * STAGE_FLOATS) + j * DESC_WORDS;
+            if (((d[D_OWN] >> warp) & 1) == 0 || d[D_FLAGX] != 0) continue;   // not my rows / generic-path ROI
+            const int2 yr = *reinterpret_cast<const int2 *>(d + D_Y0);
+            const int y0 = yr.x, y1 = yr.y;
+            const float *g = slot + j * STAGE_FLOATS + lane * NBIN;
             const int T = d[D_TX];
             if (d[D_XINC]) {
                 switch (T) {
