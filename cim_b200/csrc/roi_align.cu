@@ -441,6 +441,16 @@ __device__ __forceinline__ void mbar_arrive_cta(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// 4 floats added to global memory with one reduction (RED.E.ADD.F32x4)
+__device__ __forceinline__ void red_add4(float *gptr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gptr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Persistent: one CTA per SM.  The (roi, channel-chunk) units of the whole batch are split evenly and
+// contiguously over the CTAs (like the forward), so a CTA works through 1-3 tile SEGMENTS: zero the
+// smem tile, apply the ROIs of the segment, add the tile to grad_feat with red.global.add.  grad_feat
+// is zeroed beforehand and every tile is touched by at most TWO CTAs (a CTA's share is larger than one
+// tile), i.e. each element is 0 + a (+ b): exact and independent of the order -> still bit-reproducible.
 __global__ void __launch_bounds__(NWB * 32, 1)
 roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restrict__ hdr,
                           const int *__restrict__ img_start, const int *__restrict__ descs,
@@ -450,89 +460,135 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
     float *ring = smem + (size_t)CH * pitch;                 // [NS][NBR x 1568 grads | NBR x 160 desc words]
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)NS * SLOT_FLOATS);
     uint64_t *empty = full + NS;
+    if (__ldg(hdr) != 0) return;              // rois not grouped by image: the generic kernel does it all
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int HW = H * W, nchunks = C / CH;
-    const int b = blockIdx.x / nchunks, c0 = (blockIdx.x % nchunks) * CH;
-
-    for (int e = tid; e < CH * pitch; e += NWB * 32) tile[e] = 0.f;
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWB); }
         fence_mbar_init();
     }
     __syncthreads();
 
-    const int is = __ldg(img_start + b);
-    const int n = __ldg(hdr) != 0 ? 0 : __ldg(img_start + b + 1) - is;
-
-    // producer duty (lane 0 of warp 0): batch j (NBR consecutive ROIs: gradients + descriptors) goes
-    // to slot j % NS once every warp has released batch j - NS.  `must` = the batch warp 0 itself is
-    // about to read: then the wait is blocking, otherwise it is only tried.
-    const int nbatch = (n + NBR - 1) / NBR;
-    int issued = 0;
-    auto produce = [&](int want, int must) {
-        while (issued < want && issued < nbatch) {
-            const int s = issued % NS;
-            if (issued >= NS) {
-                const uint32_t par = ((issued / NS) - 1) & 1;
-                if (issued <= must) mbar_wait(&empty[s], par);
-                else if (!mbar_test(&empty[s], par)) break;
-            }
-            float *slot = ring + (size_t)s * SLOT_FLOATS;
-            const int first = issued * NBR, cnt = min(NBR, n - first);
-            mbar_expect_tx(&full[s], (uint32_t)cnt * (STAGE_FLOATS + DESC_WORDS) * 4);
-            for (int j = 0; j < cnt; ++j)
-                bulk_g2s(slot + j * STAGE_FLOATS, grad_out + ((size_t)(is + first + j) * C + c0) * NBIN,
-                         STAGE_FLOATS * 4, &full[s]);
-            bulk_g2s(slot + NBR * STAGE_FLOATS, descs + (size_t)(is + first) * DESC_WORDS,
-                     (uint32_t)cnt * DESC_WORDS * 4, &full[s]);
-            ++issued;
-        }
-    };
-    if (tid == 0) produce(NS, -1);
-
+    const int s0 = __ldg(img_start), sB = __ldg(img_start + B);
+    const long long U = (long long)nchunks * (sB - s0);
+    // Even split of the units only if a CTA's share covers the largest tile (then a tile is shared by
+    // at most two CTAs and the merge is order-independent); otherwise whole tiles, round-robin.
+    int maxroi = 0;
+    for (int i = 0; i < B; ++i) maxroi = max(maxroi, __ldg(img_start + i + 1) - __ldg(img_start + i));
+    const bool split = U / gridDim.x >= maxroi;
+    long long u = split ? U * blockIdx.x / gridDim.x : 0;
+    const long long u_end = split ? U * (blockIdx.x + 1) / gridDim.x : 0;
+    int tile_id = blockIdx.x;                 // whole-tile mode: tiles blockIdx.x, + gridDim.x, ...
     float *tile_c = tile + lane * pitch;
-    for (int bi = 0; bi < nbatch; ++bi) {
-        if (tid == 0) produce(bi + NS, bi);
-        const int s = bi % NS;
-        mbar_wait(&full[s], (bi / NS) & 1);
-        const float *slot = ring + (size_t)s * SLOT_FLOATS;
-        const int cnt = min(NBR, n - bi * NBR);
-        for (int j = 0; j < cnt; ++j) {
-            const int *d = reinterpret_cast<const int *>(slot + NBR * STAGE_FLOATS) + j * DESC_WORDS;
-            if (((d[D_OWN] >> warp) & 1) == 0 || d[D_FLAGX] != 0) continue;   // not my rows / generic-path ROI
-            const int2 yr = *reinterpret_cast<const int2 *>(d + D_Y0);
-            const int y0 = yr.x, y1 = yr.y;
-            const float *g = slot + j * STAGE_FLOATS + lane * NBIN;
-            const int T = d[D_TX];
-            if (d[D_XINC]) {
-                switch (T) {
-                    case 2: bwd_rows<2, true>(tile_c, W, d, g, warp, y0, y1); break;
-                    case 3: bwd_rows<3, true>(tile_c, W, d, g, warp, y0, y1); break;
-                    case 4: bwd_rows<4, true>(tile_c, W, d, g, warp, y0, y1); break;
-                    case 6: bwd_rows<6, true>(tile_c, W, d, g, warp, y0, y1); break;
-                    default: bwd_rows<8, true>(tile_c, W, d, g, warp, y0, y1); break;
+    int gb = 0;                               // batches consumed so far (all segments): slot / phase bookkeeping
+    int issued = 0;                           // batches issued so far (producer thread only)
+    int b = 0;
+    while (true) {
+        int is, nroi, ch, r0, r1;
+        if (split) {
+            if (u >= u_end) break;
+            while (b < B && (long long)nchunks * (__ldg(img_start + b + 1) - s0) <= u) ++b;
+            is = __ldg(img_start + b);
+            nroi = __ldg(img_start + b + 1) - is;
+            const long long base = (long long)nchunks * (is - s0);
+            ch = (int)((u - base) / nroi);
+            r0 = (int)((u - base) - (long long)ch * nroi);
+            r1 = (int)min((long long)nroi, r0 + (u_end - u));
+            u += r1 - r0;
+        } else {
+            if (tile_id >= B * nchunks) break;
+            b = tile_id / nchunks;
+            ch = tile_id - b * nchunks;
+            tile_id += gridDim.x;
+            is = __ldg(img_start + b);
+            nroi = __ldg(img_start + b + 1) - is;
+            r0 = 0;
+            r1 = nroi;
+            if (nroi == 0) continue;          // its slab stays zero
+        }
+        const int c0 = ch * CH;
+        const int first_roi = is + r0, n = r1 - r0;
+        const int nbatch = (n + NBR - 1) / NBR, gb0 = gb;
+
+        for (int e = tid; e < CH * pitch; e += NWB * 32) tile[e] = 0.f;
+        __syncthreads();
+
+        // producer duty (lane 0 of warp 0): batch j of this segment (NBR consecutive ROIs: gradients +
+        // descriptors) goes to slot (gb0 + j) % NS once every warp has released the batch that used
+        // the slot before.  `must` = the batch warp 0 itself is about to read: blocking wait.
+        auto produce = [&](int want, int must) {
+            while (issued < want && issued < gb0 + nbatch) {
+                const int s = issued % NS;
+                if (issued >= NS) {
+                    const uint32_t par = ((issued / NS) - 1) & 1;
+                    if (issued <= must) mbar_wait(&empty[s], par);
+                    else if (!mbar_test(&empty[s], par)) break;
                 }
-            } else {
-                switch (T) {
-                    case 2: bwd_rows<2, false>(tile_c, W, d, g, warp, y0, y1); break;
-                    case 3: bwd_rows<3, false>(tile_c, W, d, g, warp, y0, y1); break;
-                    case 4: bwd_rows<4, false>(tile_c, W, d, g, warp, y0, y1); break;
-                    case 6: bwd_rows<6, false>(tile_c, W, d, g, warp, y0, y1); break;
-                    default: bwd_rows<8, false>(tile_c, W, d, g, warp, y0, y1); break;
+                float *slot = ring + (size_t)s * SLOT_FLOATS;
+                const int first = (issued - gb0) * NBR, cnt = min(NBR, n - first);
+                mbar_expect_tx(&full[s], (uint32_t)cnt * (STAGE_FLOATS + DESC_WORDS) * 4);
+                for (int j = 0; j < cnt; ++j)
+                    bulk_g2s(slot + j * STAGE_FLOATS, grad_out + ((size_t)(first_roi + first + j) * C + c0) * NBIN,
+                             STAGE_FLOATS * 4, &full[s]);
+                bulk_g2s(slot + NBR * STAGE_FLOATS, descs + (size_t)(first_roi + first) * DESC_WORDS,
+                         (uint32_t)cnt * DESC_WORDS * 4, &full[s]);
+                ++issued;
+            }
+        };
+        if (tid == 0) produce(gb0 + NS, -1);
+
+        for (int bi = 0; bi < nbatch; ++bi, ++gb) {
+            if (tid == 0) produce(gb + NS, gb);
+            const int s = gb % NS;
+            mbar_wait(&full[s], (gb / NS) & 1);
+            const float *slot = ring + (size_t)s * SLOT_FLOATS;
+            const int cnt = min(NBR, n - bi * NBR);
+            for (int j = 0; j < cnt; ++j) {
+                const int *d = reinterpret_cast<const int *>(slot + NBR * STAGE_FLOATS) + j * DESC_WORDS;
+                if (((d[D_OWN] >> warp) & 1) == 0 || d[D_FLAGX] != 0) continue;   // not my rows / generic-path ROI
+                const int2 yr = *reinterpret_cast<const int2 *>(d + D_Y0);
+                const int y0 = yr.x, y1 = yr.y;
+                const float *g = slot + j * STAGE_FLOATS + lane * NBIN;
+                const int T = d[D_TX];
+                if (d[D_XINC]) {
+                    switch (T) {
+                        case 2: bwd_rows<2, true>(tile_c, W, d, g, warp, y0, y1); break;
+                        case 3: bwd_rows<3, true>(tile_c, W, d, g, warp, y0, y1); break;
+                        case 4: bwd_rows<4, true>(tile_c, W, d, g, warp, y0, y1); break;
+                        case 6: bwd_rows<6, true>(tile_c, W, d, g, warp, y0, y1); break;
+                        default: bwd_rows<8, true>(tile_c, W, d, g, warp, y0, y1); break;
+                    }
+                } else {
+                    switch (T) {
+                        case 2: bwd_rows<2, false>(tile_c, W, d, g, warp, y0, y1); break;
+                        case 3: bwd_rows<3, false>(tile_c, W, d, g, warp, y0, y1); break;
+                        case 4: bwd_rows<4, false>(tile_c, W, d, g, warp, y0, y1); break;
+                        case 6: bwd_rows<6, false>(tile_c, W, d, g, warp, y0, y1); break;
+                        default: bwd_rows<8, false>(tile_c, W, d, g, warp, y0, y1); break;
+                    }
                 }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cta(&empty[s]);       // this warp is done reading slot s
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cta(&empty[s]);       // this warp is done reading slot s
-    }
-    __syncthreads();
+        __syncthreads();
 
-    // every element of this (image, channel chunk) slab is written exactly once
-    float *dst = grad_feat + ((size_t)b * C + c0) * HW;
-    for (int e = tid; e < CH * HW; e += NWB * 32) {
-        int c = e / HW, p = e - c * HW;
-        dst[e] = tile[c * pitch + p];
+        // tile -> grad_feat (+=): the slab is zero or holds the other CTA's partial sum
+        float *dst = grad_feat + ((size_t)b * C + c0) * HW;
+        if ((HW & 3) == 0) {
+            for (int e = tid * 4; e < CH * HW; e += NWB * 32 * 4) {
+                const int c = e / HW, p = e - c * HW;
+                const float *t = tile + c * pitch + p;
+                red_add4(dst + e, t[0], t[1], t[2], t[3]);
+            }
+        } else {
+            for (int e = tid; e < CH * HW; e += NWB * 32) {
+                const int c = e / HW, p = e - c * HW;
+                atomicAdd(dst + e, tile[c * pitch + p]);
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -730,8 +786,11 @@ CIM_API int cim_roi_align_bwd(const float *grad_out, const float *rois, float *g
     }
     if ((rc = run_prep(rois, B, H, W, K, oh, ow, scale, sr, aligned, w, st))) return rc;
     cudaFuncSetAttribute(roi_align_bwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bwd);
-    roi_align_bwd_tile_kernel<<<B * (C / CH), NWB * 32, p.smem_bwd, st>>>(grad_out, w.hdr, w.img_start, w.desc,
-                                                                           grad_feat, B, C, H, W, p.pitch);
+    cudaMemsetAsync(grad_feat, 0, sizeof(float) * (size_t)B * C * H * W, st);
+    const long long units = (long long)(C / CH) * K;
+    const int grid = (int)min((long long)cim_num_sms(), units);
+    roi_align_bwd_tile_kernel<<<grid, NWB * 32, p.smem_bwd, st>>>(grad_out, w.hdr, w.img_start, w.desc, grad_feat, B,
+                                                                   C, H, W, p.pitch);
     if ((rc = cim_launch_status())) return rc;
     roi_align_generic_kernel<true><<<dim3((unsigned)K, 1), 256, 0, st>>>(grad_out, rois, grad_feat, w.hdr, w.desc, 1,
                                                                          B, C, H, W, K, oh, ow, scale, sr, aligned);
