@@ -61,6 +61,38 @@ __global__ void mask_pack_kernel(const uint8_t *__restrict__ masks, uint32_t *__
     }
 }
 
+// ------------------------------------------------------------------------------- unpack crops
+// Wire format for proposal masks (host -> device): only the bounding box of every mask is sent.
+// crop row r, word k holds pixels (y0 + r, 32 * wx0 + 32 k .. + 31); it is OR-ed into the flat
+// bit-packed mask (pixel p = y * W + x -> bit p & 31 of word p >> 5) with a funnel shift when the
+// image width is not a multiple of 32.  One CTA per mask; `packed` is zeroed beforehand.
+__global__ void mask_unpack_crops_kernel(const uint32_t *__restrict__ crop_words, const int32_t *__restrict__ meta,
+                                         const long long *__restrict__ off, uint32_t *__restrict__ packed,
+                                         int H, int W, long long words) {
+    const long long m = blockIdx.x;
+    const int wx0 = meta[4 * m], y0 = meta[4 * m + 1], ww = meta[4 * m + 2], h = meta[4 * m + 3];
+    const uint32_t *src = crop_words + off[m];
+    uint32_t *dst = packed + m * words;
+    const bool aligned = (W & 31) == 0;
+    for (int e = threadIdx.x; e < ww * h; e += blockDim.x) {
+        const int r = e / ww, k = e - r * ww;
+        const int y = y0 + r, x = 32 * (wx0 + k);
+        if (y < 0 || y >= H || x < 0 || x >= W) continue;
+        uint32_t w = __ldg(src + e);
+        if (x + 32 > W) w &= (1u << (W - x)) - 1u;             // bits beyond the image row are dropped
+        if (w == 0u) continue;
+        const long long p = (long long)y * W + x;
+        const long long wi = p >> 5;
+        const int sh = (int)(p & 31);
+        if (aligned) {
+            dst[wi] = w;                                        // every output word has one source word
+        } else {
+            atomicOr(dst + wi, w << sh);
+            if (sh != 0 && (w >> (32 - sh)) != 0u) atomicOr(dst + wi + 1, w >> (32 - sh));
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------- area
 __global__ void mask_area_kernel(const uint32_t *__restrict__ packed, int32_t *__restrict__ area,
                                  long long n_masks, long long words) {
@@ -164,6 +196,21 @@ CIM_API int cim_mask_pack(const uint8_t *masks, uint32_t *packed, int64_t n_mask
     const long long total = n_masks * words;
     const int blocks = (int)min((long long)cim_num_sms() * 16, (total + 255) / 256);
     mask_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(masks, packed, n_masks, hw, words);
+    return cim_launch_status();
+}
+
+CIM_API int cim_mask_unpack_crops(const uint32_t *crop_words, const int32_t *crop_meta, const int64_t *crop_off,
+                                  uint32_t *packed, int64_t n_masks, int H, int W, int64_t words,
+                                  cim_stream_t stream) {
+    if (!crop_words || !crop_meta || !crop_off || !packed || n_masks < 0 || H <= 0 || W <= 0) return CIM_ERR_ARG;
+    if (words * 32 < (int64_t)H * W) return CIM_ERR_ARG;
+    if (n_masks == 0) return CIM_OK;
+    if (n_masks > 0x7fffffffLL) return CIM_ERR_SHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(packed, 0, sizeof(uint32_t) * (size_t)n_masks * words, st);
+    mask_unpack_crops_kernel<<<(unsigned)n_masks, 128, 0, st>>>(crop_words, crop_meta,
+                                                                reinterpret_cast<const long long *>(crop_off), packed,
+                                                                H, W, words);
     return cim_launch_status();
 }
 

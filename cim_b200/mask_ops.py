@@ -8,9 +8,102 @@ loads + H2D copies per training step that consume them (lib/modeling/model_build
     iou_map, asy_iou_map = mask_overlap(packed)  # float16 [..., N, N] each, the reference's dtype
 asy_iou_map[i, j] = |m_i & m_j| / |m_j| (how much of proposal j lies inside proposal i).
 """
+from dataclasses import dataclass
+
+import numpy as np
 import torch
 
 from . import _lib
+
+
+@dataclass
+class MaskCrops:
+    """Compact wire format of N proposal masks: bounding-box crops, bit-packed, 32-pixel aligned in x.
+    words [total] int32, meta [N,4] int32 = (wx0, y0, ww, h), off [N] int64 (word offset of each crop).
+    Host (numpy / pinned torch) or device tensors."""
+    words: torch.Tensor
+    meta: torch.Tensor
+    off: torch.Tensor
+    height: int
+    width: int
+
+    @property
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in (self.words, self.meta, self.off))
+
+
+def pack_crops_host(masks):
+    """numpy/CPU: uint8 / bool masks [N, H, W] -> MaskCrops (CPU tensors).  What a data-loader worker
+    would produce from the COB proposals instead of full-image byte masks."""
+    m = np.asarray(masks) != 0
+    n, h, w = m.shape
+    wpad = (w + 31) // 32 * 32
+    rows = np.zeros((n, h, wpad), dtype=bool)
+    rows[:, :, :w] = m
+    bits = np.packbits(rows, axis=2, bitorder="little").view("<u4").reshape(n, h, wpad // 32)   # word k = px 32k..
+    meta = np.zeros((n, 4), np.int32)
+    off = np.zeros(n, np.int64)
+    chunks, total = [], 0
+    for i in range(n):
+        ys, xs = np.nonzero(m[i].any(1))[0], np.nonzero(m[i].any(0))[0]
+        if len(ys) == 0:
+            off[i] = total
+            continue
+        y0, y1, wx0, wx1 = ys[0], ys[-1] + 1, xs[0] // 32, xs[-1] // 32 + 1
+        meta[i] = (wx0, y0, wx1 - wx0, y1 - y0)
+        off[i] = total
+        c = bits[i, y0:y1, wx0:wx1].reshape(-1)
+        chunks.append(c)
+        total += c.size
+    words = np.concatenate(chunks) if chunks else np.zeros(0, np.uint32)
+    return MaskCrops(torch.from_numpy(words.view(np.int32).copy()), torch.from_numpy(meta), torch.from_numpy(off),
+                     h, w)
+
+
+def crops_from_packed_host(packed, height, width):
+    """CPU: full bit masks [N, H*W/32] (int32, W % 32 == 0) -> MaskCrops, without going through
+    byte masks (used by bench.py to derive the wire format from its synthetic packed masks)."""
+    if width % 32:
+        raise ValueError("crops_from_packed_host needs width % 32 == 0; use pack_crops_host")
+    p = np.ascontiguousarray(packed.cpu().numpy() if isinstance(packed, torch.Tensor) else packed)
+    p = p.view(np.uint32).reshape(p.shape[0], height, width // 32)
+    n = p.shape[0]
+    nz = p != 0
+    row_any, col_any = nz.any(2), nz.any(1)
+    y0 = row_any.argmax(1)
+    y1 = height - row_any[:, ::-1].argmax(1)
+    x0 = col_any.argmax(1)
+    x1 = width // 32 - col_any[:, ::-1].argmax(1)
+    empty = ~row_any.any(1)
+    meta = np.stack([x0, y0, x1 - x0, y1 - y0], 1).astype(np.int32)
+    meta[empty] = 0
+    sizes = meta[:, 2].astype(np.int64) * meta[:, 3]
+    off = np.zeros(n, np.int64)
+    off[1:] = np.cumsum(sizes)[:-1]
+    words = np.empty(int(sizes.sum()), np.uint32)
+    for i in range(n):
+        if sizes[i]:
+            words[off[i]:off[i] + sizes[i]] = p[i, y0[i]:y1[i], x0[i]:x1[i]].reshape(-1)
+    return MaskCrops(torch.from_numpy(words.view(np.int32)), torch.from_numpy(meta), torch.from_numpy(off),
+                     height, width)
+
+
+def unpack_crops(crops, out=None):
+    """MaskCrops on the device -> full bit masks [N, ceil(H*W/32)] int32 (the input of mask_overlap)."""
+    _lib.require_cuda(crops.words, "crops.words", torch.int32)
+    _lib.require_cuda(crops.meta, "crops.meta", torch.int32)
+    _lib.require_cuda(crops.off, "crops.off", torch.int64)
+    n = crops.meta.shape[0]
+    words = (crops.height * crops.width + 31) // 32
+    dev = crops.words.device
+    if out is None:
+        out = torch.empty((n, words), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().cim_mask_unpack_crops(_lib.ptr(crops.words), _lib.ptr(crops.meta.contiguous()),
+                                              _lib.ptr(crops.off.contiguous()), _lib.ptr(out), n, crops.height,
+                                              crops.width, words, _lib.stream_ptr(dev))
+    _lib.check(rc, "cim_mask_unpack_crops")
+    return out
 
 
 def mask_pack(masks):

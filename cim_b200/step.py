@@ -139,7 +139,7 @@ class CIMHeadStep:
         return self
 
     # -------------------------------------------------------------------------------------
-    def alloc_host_io(self):
+    def alloc_host_io(self, mask_hw=None, crop_capacity_words=0):
         """Pinned host buffers of the end-to-end call: inputs that originate on the host in the
         reference's pipeline (rois, labels: lib/roi_data/minibatch.py:45-61; proposal masks:
         the COB .mat files of tools/pre) and the step's results.  Device-side input buffers are
@@ -149,7 +149,18 @@ class CIMHeadStep:
         pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
         self.hi_rois = pin((n_img * R, 5), torch.float32)
         self.hi_labels = pin((n_img, self.C), torch.float32)
-        self.hi_masks = pin((n_img, R, self.words), torch.int32)
+        # masks arrive either as full bit masks (hi_masks) or, with crop_capacity_words > 0, as
+        # bounding-box crops (mask_ops.MaskCrops: ~8x fewer bytes over PCIe) that the device unpacks
+        self.crop_cap = int(crop_capacity_words)
+        self.mask_hw = mask_hw
+        if self.crop_cap:
+            self.hi_masks = None
+            self.hi_crop_words = pin((self.crop_cap,), torch.int32)
+            self.hi_crop_meta = pin((n_img * R, 4), torch.int32)
+            self.hi_crop_off = pin((n_img * R,), torch.int64)
+            self.n_crop_words = 0
+        else:
+            self.hi_masks = pin((n_img, R, self.words), torch.int32)
         self.ho_labels = pin((k, n_img, R, C1), torch.float32)
         self.ho_iou = pin((k, n_img, R), torch.float16)
         self.ho_weights = pin((k, n_img, R), torch.float32)
@@ -160,15 +171,32 @@ class CIMHeadStep:
             self.di = [dict(rois=dv((n_img * R, 5), torch.float32), labels=dv((n_img, self.C), torch.float32),
                             masks=dv((n_img, R, self.words), torch.int32), ready=torch.cuda.Event(),
                             free=torch.cuda.Event()) for _ in range(2)]
+            if self.crop_cap:
+                for buf in self.di:
+                    buf.update(crop_words=dv((self.crop_cap,), torch.int32), crop_meta=dv((n_img * R, 4), torch.int32),
+                               crop_off=dv((n_img * R,), torch.int64))
             self.d_checksum = dv((2,), torch.float32)
             self.copy_stream = torch.cuda.Stream(device=self.dev)
-        self.h2d_bytes = sum(t.numel() * t.element_size() for t in (self.hi_rois, self.hi_labels, self.hi_masks))
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in (self.hi_rois, self.hi_labels))
+        if not self.crop_cap:
+            self.h2d_bytes += self.hi_masks.numel() * 4
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in
                              (self.ho_labels, self.ho_iou, self.ho_weights, self.ho_valid, self.ho_checksum))
         self.d2h_bytes += sum(t.numel() * t.element_size() for t in (self.h_count, self.h_class, self.h_weight))
         self.h2d_bytes += self.h_keep.numel()
         self._slot = 0
         self._staged = False
+
+    def set_host_crops(self, crops):
+        """Copy a MaskCrops (CPU) of the n_img * R proposal masks into the pinned input buffers."""
+        n = crops.words.numel()
+        if n > self.crop_cap:
+            raise ValueError(f"{n} crop words exceed the capacity {self.crop_cap}")
+        self.hi_crop_words[:n].copy_(crops.words)
+        self.hi_crop_meta.copy_(crops.meta)
+        self.hi_crop_off.copy_(crops.off)
+        self.n_crop_words = n
+        self.mask_hw = (crops.height, crops.width)
 
     def stage_host_inputs(self):
         """Enqueue the host->device copy of the CURRENT contents of hi_rois / hi_labels / hi_masks
@@ -180,7 +208,19 @@ class CIMHeadStep:
             self.copy_stream.wait_event(buf["free"])          # its previous consumer has finished
             buf["rois"].copy_(self.hi_rois, non_blocking=True)
             buf["labels"].copy_(self.hi_labels, non_blocking=True)
-            buf["masks"].copy_(self.hi_masks, non_blocking=True)
+            if self.crop_cap:
+                n = self.n_crop_words
+                buf["crop_words"][:n].copy_(self.hi_crop_words[:n], non_blocking=True)
+                buf["crop_meta"].copy_(self.hi_crop_meta, non_blocking=True)
+                buf["crop_off"].copy_(self.hi_crop_off, non_blocking=True)
+                rc = self.L.cim_mask_unpack_crops(_lib.ptr(buf["crop_words"]), _lib.ptr(buf["crop_meta"]),
+                                                  _lib.ptr(buf["crop_off"]), _lib.ptr(buf["masks"]),
+                                                  self.n_img * self.R, self.mask_hw[0], self.mask_hw[1], self.words,
+                                                  C.c_void_p(self.copy_stream.cuda_stream))
+                _lib.check(rc, "cim_mask_unpack_crops")
+                self.last_mask_h2d_bytes = n * 4 + self.hi_crop_meta.numel() * 4 + self.hi_crop_off.numel() * 8
+            else:
+                buf["masks"].copy_(self.hi_masks, non_blocking=True)
             buf["ready"].record(self.copy_stream)
         return self
 

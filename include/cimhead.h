@@ -86,6 +86,16 @@ int cim_roi_pool_bwd(const float *grad_out, const int32_t *argmax, const float *
  *   both computed as fp32 round-to-nearest division then fp32->fp16 round-to-nearest. */
 int cim_mask_pack(const uint8_t *masks, uint32_t *packed, int64_t n_masks, int64_t hw,
                   int64_t words, cim_stream_t stream);
+/* cim_mask_unpack_crops: the compact host->device wire format.  Proposal masks are sent as their
+ *   bounding-box crops (the reference cuts the same box out of every COB mask,
+ *   tools/pre/generate_7_7_voc.py:36-38): crop_meta [n_masks,4] int32 = (wx0, y0, ww, h) -- the crop
+ *   starts at pixel column 32*wx0, row y0 and is ww words wide, h rows high; crop_off [n_masks] int64
+ *   = offset (in words) of the crop inside crop_words; crop row r, word k, bit j = pixel
+ *   (y0 + r, 32*(wx0 + k) + j).  Output: the full bit masks [n_masks, words] cim_mask_overlap reads
+ *   (zero outside the crops).  H, W = mask height / width in pixels, words >= ceil(H*W/32). */
+int cim_mask_unpack_crops(const uint32_t *crop_words, const int32_t *crop_meta, const int64_t *crop_off,
+                          uint32_t *packed, int64_t n_masks, int H, int W, int64_t words,
+                          cim_stream_t stream);
 size_t cim_mask_overlap_workspace_bytes(int n_img, int n, int64_t words);
 int cim_mask_overlap(const uint32_t *packed, int n_img, int n, int64_t words,
                      int32_t *inter, int32_t *area, void *iou_f16, void *asy_f16,

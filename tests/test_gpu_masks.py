@@ -128,3 +128,25 @@ def test_tensor_path_rejects_what_it_cannot_take():
         mask_ops.mask_overlap(packed, algo="tensor")
     iou, _ = mask_ops.mask_overlap(packed, algo="auto")                                    # falls back to popc
     assert bool((iou == 1).all())
+
+
+@pytest.mark.parametrize("n,h,w", [(60, 64, 64), (33, 37, 50), (20, 96, 160)])
+def test_crop_wire_format_round_trip(n, h, w):
+    """bbox-cropped wire format -> device unpack == packing the full byte masks."""
+    g = torch.Generator().manual_seed(n)
+    masks = torch.zeros(n, h, w, dtype=torch.uint8)
+    for i in range(n):                         # random boxes with random content, some touching borders
+        y0, x0 = int(torch.randint(0, h - 1, (1,), generator=g)), int(torch.randint(0, w - 1, (1,), generator=g))
+        y1, x1 = int(torch.randint(y0 + 1, h + 1, (1,), generator=g)), int(torch.randint(x0 + 1, w + 1, (1,), generator=g))
+        masks[i, y0:y1, x0:x1] = (torch.rand(y1 - y0, x1 - x0, generator=g) < 0.6).to(torch.uint8)
+    masks[2] = 0                               # empty mask: empty crop
+    masks[3] = 1                               # full mask: crop = whole image
+    crops = mask_ops.pack_crops_host(masks.numpy())
+    dev_crops = mask_ops.MaskCrops(crops.words.to(DEV), crops.meta.to(DEV), crops.off.to(DEV), h, w)
+    got = mask_ops.unpack_crops(dev_crops)
+    want = mask_ops.mask_pack(masks.to(DEV))
+    assert torch.equal(got, want)
+    if w % 32 == 0:
+        again = mask_ops.crops_from_packed_host(want.cpu(), h, w)
+        assert torch.equal(again.words, crops.words) and torch.equal(again.meta, crops.meta)
+    assert crops.nbytes < masks.numel()        # smaller than byte masks by construction
