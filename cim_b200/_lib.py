@@ -41,7 +41,7 @@ _SIGNATURES = {
     "cim_roi_pool_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "cim_mask_pack": (_I, [_P, _P, _I64, _I64, _I64, _P]),
     "cim_mask_unpack_crops": (_I, [_P, _P, _P, _P, _I64, _I, _I, _I64, _P]),
-    "cim_mask_overlap_workspace_bytes": (_SZ, [_I, _I, _I64]),
+    "cim_mask_overlap_workspace_bytes": (_SZ, [_I, _I, _I64, _I]),
     "cim_mask_overlap": (_I, [_P, _I, _I, _I64, _P, _P, _P, _P, _P, _SZ, _P]),
     "cim_mask_overlap_algo": (_I, [_P, _I, _I, _I64, _P, _P, _P, _P, _P, _SZ, _I, _P]),
     "cim_score_heads_workspace_bytes": (_SZ, [_I, _I, _I, _I]),

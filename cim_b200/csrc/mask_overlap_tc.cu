@@ -22,8 +22,11 @@
 //                           SWIZZLE_128B smem layout (8-row x 128 B atoms, chunk ^= row % 8).
 //   MMA issuer (1)      waits for a stage, issues 4 x tcgen05.mma (A from TMEM, B from smem),
 //                       tcgen05.commit hands the stage back.
-//   epilogue            warps 0..7: tcgen05.ld, fp32 div.rn, cvt.rn.f16, 16 B stores; the mirror
-//                       block goes through a shared-memory transpose (asy is not symmetric).
+//   epilogue            the 16 expander warps: tcgen05.ld, fp32 div.rn, cvt.rn.f16 into smem tiles, then
+//                       contiguous global stores: tile rows (direct block) and tile columns (mirror
+//                       block; asy is not symmetric, so the mirror carries inter / area_row).
+// Tiles work in SORTED index space (mask_sort_kernel) and visit only the K-blocks where both operand
+// blocks are non-zero; the caller un-permutes the maps afterwards.
 // History of this kernel, with the ncu evidence, is in DESIGN.md section 4.3.
 #include "common.cuh"
 #include <cstdlib>
@@ -43,9 +46,7 @@ constexpr int B_BYTES = TN * KB;        // 32 KB of expanded B operand per stage
 constexpr int NEXP = 16;                // expander warps: 0-3 A even, 4-7 A odd, 8-11 B even, 12-15 B odd K-blocks
 constexpr int MMA_WARP = NEXP, LOAD_WARP = NEXP + 1;
 constexpr int THREADS = (NEXP + 2) * 32;
-constexpr int EPI_WARPS = 8;
-constexpr int SPITCH = TN + 1;          // int32 pitch of the transpose buffer
-constexpr size_t SI_BYTES = (size_t)TM * SPITCH * 4;
+constexpr size_t SI_BYTES = (size_t)(TM + TN) * 4 + 3 * (size_t)TM * 130 * 2;   // epilogue staging (aliases the rings)
 
 template <int STAGES_>
 struct Cfg {
@@ -145,9 +146,10 @@ __device__ __forceinline__ __half2 pack_ratio2(int i0, int d0, int i1, int d1) {
 
 template <class K>
 __global__ void __launch_bounds__(THREADS, 1)
-mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__restrict__ area_all, int n,
-                       long long words, int tiles_per_img, int32_t *__restrict__ inter_all,
-                       __half *__restrict__ iou_all, __half *__restrict__ asy_all) {
+mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__restrict__ area_all,
+                       const int32_t *__restrict__ perm_all, const int2 *__restrict__ range_a,
+                       const int2 *__restrict__ range_b, int n, long long words, int n_img,
+                       int32_t *__restrict__ inter_all, __half *__restrict__ iou_all, __half *__restrict__ asy_all) {
     constexpr int STAGES = K::STAGES;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -161,13 +163,19 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(consumed + NBUF);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int img = blockIdx.x / tiles_per_img;
-    // linear tile id -> (ti, tj): row block ti (128 rows) pairs with the column blocks (256) that
-    // reach the diagonal or lie right of it: 256 (tj + 1) > 128 ti  <=>  tj >= ti / 2
-    int ti = 0, rem = blockIdx.x % tiles_per_img;
-    const int ncb = (n + TN - 1) / TN;
-    while (rem >= ncb - (ti >> 1)) { rem -= ncb - (ti >> 1); ++ti; }
-    const int tj = (ti >> 1) + rem;
+    // tile id -> (d, img, ti), tj = ti / 2 + d: tiles are ordered by their distance d from the diagonal,
+    // over all images.  After the locality sort the K-range of a tile shrinks with d, so the longest
+    // tiles start first and the short ones fill the tail (tiles_per_img is unused by this order).
+    const int ncb = (n + TN - 1) / TN, nrb = (n + TM - 1) / TM;
+    int d = 0, rem = blockIdx.x;
+    for (;;) {
+        const int cnt = min(nrb, 2 * (ncb - d)) * n_img;      // row blocks ti with ti / 2 + d < ncb
+        if (rem < cnt) break;
+        rem -= cnt;
+        ++d;
+    }
+    const int per_img = min(nrb, 2 * (ncb - d));
+    const int img = rem / per_img, ti = rem - img * per_img, tj = (ti >> 1) + d;
     const int row0 = ti * TM, col0 = tj * TN;
 
     if (tid == 0) {
@@ -186,7 +194,13 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int nkb = (int)(words / 4);
+    // All indices below are SORTED positions (mask_sort_kernel); perm maps them to the stored masks.
+    // K-range of this tile: the K-blocks where both operand blocks have a non-zero row.
+    const int32_t *perm = perm_all + (size_t)img * n;
+    const int nrb_img = nrb;
+    const int2 ra_ = range_a[(size_t)img * nrb_img + ti], rb_ = range_b[(size_t)img * ncb + tj];
+    const int kb_lo = max(ra_.x, rb_.x);
+    const int nkb = max(0, min(min(ra_.y, rb_.y), (int)(words / 4)) - kb_lo);   // K-blocks this tile visits
     const int ngroups = (nkb + GK - 1) / GK;
 
     if (warp < NEXP) {
@@ -262,7 +276,7 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
             for (int t = lane; t < ROWS; t += 32) {
                 const int grow = t < TM ? row0 + t : col0 + (t - TM);
                 const bool rv = grow < n;
-                const uint32_t *rsrc = img_base + (size_t)(rv ? grow : 0) * words;
+                const uint32_t *rsrc = img_base + (size_t)(rv ? __ldg(perm + grow) : 0) * words;
 #pragma unroll
                 for (int kk = 0; kk < GK; ++kk) {
                     const int kb = g * GK + kk;
@@ -270,7 +284,7 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
                     const uint32_t nbytes = ok ? 16u : 0u;
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
                                      smem_u32(dst + (kk * ROWS + t) * 16)),
-                                 "l"(rsrc + (ok ? kb * 4 : 0)), "r"(nbytes)
+                                 "l"(rsrc + (ok ? (kb_lo + kb) * 4 : 0)), "r"(nbytes)
                                  : "memory");
                 }
             }
@@ -297,74 +311,97 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
     }
 
     // ---------------------------------------------------------------------- epilogue
-    int32_t *sI = reinterpret_cast<int32_t *>(stages);          // [TM][SPITCH], reuses the rings
+    // The 16 expander warps drain the accumulator: warp w reads TMEM lanes 32 (w % 4).. and, per pass of
+    // 128 columns, the 32-column slice w / 4.  Areas are cached in smem; the fp16 results (iou, asy and
+    // the mirror's asy) go to smem tiles first so that every global store is a contiguous segment:
+    // a row of the tile (direct block) or a column of it (mirror block, written transposed).
+    constexpr int EP = 130;                                       // half pitch (65 words: odd -> conflict-free)
+    int *areaR = reinterpret_cast<int *>(stages);                 // [128]
+    int *areaC = areaR + TM;                                      // [256]
+    __half *s_iou = reinterpret_cast<__half *>(areaC + TN);       // [128][EP]
+    __half *s_asy = s_iou + TM * EP;                              // [128][EP]  inter / area_col
+    __half *s_asyT = s_asy + TM * EP;                             // [128][EP]  inter / area_row (mirror block)
     const int32_t *area = area_all + (size_t)img * n;
     int32_t *inter = inter_all ? inter_all + (size_t)img * n * n : nullptr;
     __half *iou = iou_all + (size_t)img * n * n;
     __half *asy = asy_all + (size_t)img * n * n;
-    if (warp < EPI_WARPS) {
-        mbar_wait(accum_full, 0);
+    if (warp < NEXP) {
+        if (nkb > 0) mbar_wait(accum_full, 0);                   // empty K-range: nothing was accumulated
         tc_fence_after();
-        const int rl = 32 * (warp & 3) + lane;                   // TMEM lane = tile row
+        for (int i = tid; i < TM + TN; i += NEXP * 32) {
+            const int gidx = i < TM ? row0 + i : col0 + (i - TM);
+            areaR[i] = gidx < n ? area[perm[gidx]] : 0;           // areaC follows areaR in memory
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NEXP * 32) : "memory");
+        const int q4 = warp & 3, cs = warp >> 2;
+        const int rl = 32 * q4 + lane;                            // TMEM lane = tile row
         const int r = row0 + rl;
-        const int a_r = r < n ? area[r] : 0;
-        const int chalf = (warp >> 2) * (TN / 2);
+        const int a_r = areaR[rl];
+        const bool vec_ok = (n & 3) == 0;
 #pragma unroll 1
-        for (int cc = 0; cc < TN / 2; cc += 32) {
+        for (int pass = 0; pass < TN / 128; ++pass) {
+            const int cl0 = pass * 128 + cs * 32;                 // first tile column of this warp's slice
             int v[32];
-            tc_ld32(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(chalf + cc), v);
-            const int cbase = col0 + chalf + cc;
+            if (nkb > 0) {
+                tc_ld32(tmem_base + ((uint32_t)(32 * q4) << 16) + (uint32_t)cl0, v);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sI[rl * SPITCH + chalf + cc + j] = v[j];
-            if (r < n) {
-                if (cbase + 32 <= n && (n & 7) == 0) {           // 16 B vector stores
-                    uint4 *pi = reinterpret_cast<uint4 *>(iou + (size_t)r * n + cbase);
-                    uint4 *pa = reinterpret_cast<uint4 *>(asy + (size_t)r * n + cbase);
+                for (int j = 0; j < 32; ++j) v[j] = 0;
+            }
 #pragma unroll
-                    for (int j8 = 0; j8 < 4; ++j8) {
-                        __half2 hi[4], ha[4];
-#pragma unroll
-                        for (int j2 = 0; j2 < 4; ++j2) {
-                            const int j = j8 * 8 + j2 * 2;
-                            const int a0 = area[cbase + j], a1 = area[cbase + j + 1];
-                            hi[j2] = pack_ratio2(v[j], a_r + a0 - v[j], v[j + 1], a_r + a1 - v[j + 1]);
-                            ha[j2] = pack_ratio2(v[j], a0, v[j + 1], a1);
-                        }
-                        pi[j8] = *reinterpret_cast<uint4 *>(hi);
-                        pa[j8] = *reinterpret_cast<uint4 *>(ha);
-                    }
+            for (int j = 0; j < 32; ++j) {
+                const int a_c = areaC[cl0 + j];
+                const float fi = (float)v[j];
+                const int so = rl * EP + cs * 32 + j;
+                s_iou[so] = __float2half_rn(__fdiv_rn(fi, (float)(a_r + a_c - v[j])));
+                s_asy[so] = __float2half_rn(__fdiv_rn(fi, (float)a_c));
+                s_asyT[so] = __float2half_rn(__fdiv_rn(fi, (float)a_r));
+            }
+            // mirror needed?  (c, r) belongs to tile (c / 128, r / 256): computed itself iff
+            // 256 (ti / 2 + 1) > 128 (c / 128); c / 128 is constant over a pass
+            const int cpass = col0 + pass * 128;
+            const bool mirror = !(TN * ((ti >> 1) + 1) > TM * (cpass / TM));
+            if (inter && r < n) {                                 // integer counts: tests only, simple stores
+                for (int j = 0; j < 32 && col0 + cl0 + j < n; ++j) {
+                    inter[(size_t)r * n + col0 + cl0 + j] = v[j];
+                    if (mirror) inter[(size_t)(col0 + cl0 + j) * n + r] = v[j];
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NEXP * 32) : "memory");
+            // direct block: warp w writes tile rows w, w + 16, ...; a lane covers 4 consecutive columns
+            for (int rr = warp; rr < TM; rr += NEXP) {
+                const int gr = row0 + rr, gc = cpass + 4 * lane;
+                if (gr >= n || gc >= n) continue;
+                const uint32_t *pi = reinterpret_cast<const uint32_t *>(s_iou + rr * EP + 4 * lane);
+                const uint32_t *pa = reinterpret_cast<const uint32_t *>(s_asy + rr * EP + 4 * lane);
+                const size_t o = (size_t)gr * n + gc;
+                if (vec_ok && gc + 4 <= n) {
+                    *reinterpret_cast<uint2 *>(iou + o) = make_uint2(pi[0], pi[1]);
+                    *reinterpret_cast<uint2 *>(asy + o) = make_uint2(pa[0], pa[1]);
                 } else {
-                    for (int j = 0; j < 32; ++j) {
-                        const int c = cbase + j;
-                        if (c >= n) break;
-                        const int a_c = area[c];
-                        iou[(size_t)r * n + c] = __float2half_rn(__fdiv_rn((float)v[j], (float)(a_r + a_c - v[j])));
-                        asy[(size_t)r * n + c] = __float2half_rn(__fdiv_rn((float)v[j], (float)a_c));
+                    for (int e = 0; e < 4 && gc + e < n; ++e) {
+                        iou[o + e] = s_iou[rr * EP + 4 * lane + e];
+                        asy[o + e] = s_asy[rr * EP + 4 * lane + e];
                     }
                 }
-                if (inter)
-                    for (int j = 0; j < 32 && cbase + j < n; ++j) inter[(size_t)r * n + cbase + j] = v[j];
             }
-        }
-        tc_fence_before();
-        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-        // mirror block out[c][r2]: written unless the tile that owns (c, r2), i.e. (c / 128, r2 / 256),
-        // is computed itself: 256 (r2 / 256 + 1) > 128 (c / 128); r2 / 256 == ti / 2 for the whole tile
-        for (int cl = warp; cl < TN; cl += EPI_WARPS) {
-            const int c = col0 + cl;
-            if (c >= n) break;
-            if (TN * ((ti >> 1) + 1) > TM * (c / TM)) continue;
-            const int a_c = area[c];
+            // mirror block: warp w writes output rows (= tile columns) w, w + 16, ...; lanes cover the
+            // 128 tile rows in 4 strides of 32 (conflict-free transposed smem reads, 64 B global segments)
+            if (mirror) {
+                for (int cc = warp; cc < 128; cc += NEXP) {
+                    const int gc = cpass + cc;
+                    if (gc >= n) break;
 #pragma unroll
-            for (int h = 0; h < TM / 32; ++h) {
-                const int rl2 = h * 32 + lane, r2 = row0 + rl2;
-                if (r2 >= n) continue;
-                const int I = sI[rl2 * SPITCH + cl], a_r2 = area[r2];
-                const size_t o = (size_t)c * n + r2;
-                iou[o] = __float2half_rn(__fdiv_rn((float)I, (float)(a_c + a_r2 - I)));
-                asy[o] = __float2half_rn(__fdiv_rn((float)I, (float)a_r2));
-                if (inter) inter[o] = I;
+                    for (int h = 0; h < TM / 32; ++h) {
+                        const int rr = h * 32 + lane, gr = row0 + rr;
+                        if (gr >= n) continue;
+                        const size_t o = (size_t)gc * n + gr;
+                        iou[o] = s_iou[rr * EP + cc];
+                        asy[o] = s_asyT[rr * EP + cc];
+                    }
+                }
             }
+            asm volatile("bar.sync 1, %0;" ::"n"(NEXP * 32) : "memory");
         }
     }
     tc_fence_before();
@@ -379,14 +416,15 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
 using CfgDefault = Cfg<4>;
 
 template <class K>
-static int launch(const uint32_t *packed, const int32_t *area, int n_img, int n, long long words, int32_t *inter,
-                  __half *iou, __half *asy, cudaStream_t st) {
+static int launch(const uint32_t *packed, const int32_t *area, const int32_t *perm, const int2 *range_a,
+                  const int2 *range_b, int n_img, int n, long long words, int32_t *inter, __half *iou, __half *asy,
+                  cudaStream_t st) {
     const int nrb = (n + TM - 1) / TM, ncb = (n + TN - 1) / TN;
     int tiles = 0;
     for (int i = 0; i < nrb; ++i) tiles += ncb - (i >> 1);
     cudaFuncSetAttribute(mask_overlap_tc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES);
-    mask_overlap_tc_kernel<K><<<(unsigned)(tiles * n_img), THREADS, K::SMEM_BYTES, st>>>(packed, area, n, words, tiles,
-                                                                                        inter, iou, asy);
+    mask_overlap_tc_kernel<K><<<(unsigned)(tiles * n_img), THREADS, K::SMEM_BYTES, st>>>(
+        packed, area, perm, range_a, range_b, n, words, n_img, inter, iou, asy);
     return cim_launch_status();
 }
 
@@ -397,12 +435,13 @@ bool cim_mask_overlap_tc_eligible(int n, long long words) {
     return n >= 64 && words >= 4 && (words % 4) == 0 && (size_t)cim_max_smem_optin() >= CfgDefault::SMEM_BYTES;
 }
 
-int cim_mask_overlap_tc_launch(const uint32_t *packed, const int32_t *area, int n_img, int n, long long words,
-                               int32_t *inter, __half *iou, __half *asy, cudaStream_t st) {
+int cim_mask_overlap_tc_launch(const uint32_t *packed, const int32_t *area, const int32_t *perm, const int2 *range_a,
+                               const int2 *range_b, int n_img, int n, long long words, int32_t *inter, __half *iou,
+                               __half *asy, cudaStream_t st) {
     // CIM_OVERLAP_VARIANT is a tuning aid (pipeline-depth experiments); unset = the default
     const char *v = getenv("CIM_OVERLAP_VARIANT");
     switch (v ? atoi(v) : 0) {
-        case 1: return launch<Cfg<2>>(packed, area, n_img, n, words, inter, iou, asy, st);
-        default: return launch<CfgDefault>(packed, area, n_img, n, words, inter, iou, asy, st);
+        case 1: return launch<Cfg<2>>(packed, area, perm, range_a, range_b, n_img, n, words, inter, iou, asy, st);
+        default: return launch<CfgDefault>(packed, area, perm, range_a, range_b, n_img, n, words, inter, iou, asy, st);
     }
 }

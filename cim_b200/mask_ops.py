@@ -149,9 +149,11 @@ def mask_overlap(packed, return_counts=False, algo="auto"):
     area = torch.empty((n_img, n), dtype=torch.int32, device=dev)
     inter = torch.empty((n_img, n, n), dtype=torch.int32, device=dev) if return_counts else None
     with torch.cuda.device(dev):
+        ws = torch.empty(L.cim_mask_overlap_workspace_bytes(n_img, n, words, int(return_counts)), dtype=torch.uint8,
+                         device=dev)
         rc = L.cim_mask_overlap_algo(_lib.ptr(packed), n_img, n, words, _lib.ptr(inter), _lib.ptr(area),
-                                     _lib.ptr(iou), _lib.ptr(asy), None, 0, _lib.OVERLAP_ALGOS[algo],
-                                     _lib.stream_ptr(dev))
+                                     _lib.ptr(iou), _lib.ptr(asy), _lib.ptr(ws), ws.numel(),
+                                     _lib.OVERLAP_ALGOS[algo], _lib.stream_ptr(dev))
     _lib.check(rc, "cim_mask_overlap_algo")
     outs = (iou, asy, inter, area) if return_counts else (iou, asy)
     return tuple(o.squeeze(0) for o in outs) if squeeze else outs

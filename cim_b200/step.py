@@ -25,8 +25,8 @@ from . import _lib
 from .heads import _anti_noise_keep
 
 #: kernels (not memsets / copies) libcimhead launches in one run(): roi_align fwd 3 + bwd 3,
-#: mask area + overlap 2, scoring 3, mining 3, assignment 1
-KERNELS_PER_STEP = 15
+#: mask area + sort + overlap + 2 un-permutes = 5, scoring 3, mining 3, assignment 1
+KERNELS_PER_STEP = 18
 
 
 class CIMHeadStep:
@@ -50,6 +50,7 @@ class CIMHeadStep:
             self.iou = e((n_img, R, R), torch.float16)
             self.asy = e((n_img, R, R), torch.float16)
             self.area = e((n_img, R), torch.int32)
+            self.overlap_ws = e((self.L.cim_mask_overlap_workspace_bytes(n_img, R, mask_words, 0),), torch.uint8)
             self.scores = e((nh, n_img * R, C1), torch.float32)
             self.score_ws = e((max(256, self.L.cim_score_heads_workspace_bytes(n_img, R, C1, k)),), torch.uint8)
             p = _lib.MineParams()
@@ -100,7 +101,7 @@ class CIMHeadStep:
         st = _lib.stream_ptr(dev)
         ck = _lib.check
         ck(L.cim_mask_overlap(P(packed_masks), n_img, R, self.words, None, P(self.area), P(self.iou), P(self.asy),
-                              None, 0, st), "cim_mask_overlap")
+                              P(self.overlap_ws), self.overlap_ws.numel(), st), "cim_mask_overlap")
         ck(L.cim_score_heads(P(seg_x), P(weight), P(bias), P(self.scores), n_img, R, self.D, self.C + 1, k,
                              P(self.score_ws), self.score_ws.numel(), st), "cim_score_heads")
         ck(L.cim_mine(C.byref(p), self.cls_ptrs, self.det_ptrs, P(labels), P(self.iou), P(self.asy),

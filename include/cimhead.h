@@ -83,7 +83,10 @@ int cim_roi_pool_bwd(const float *grad_out, const int32_t *argmax, const float *
  *   inter [n_img,n,n] int32 (optional, may be NULL), area [n_img,n] int32 (optional),
  *   iou  [n_img,n,n] fp16: inter / (area_i + area_j - inter)
  *   asy  [n_img,n,n] fp16: inter / area_j                       (0/0 -> NaN, as the reference)
- *   both computed as fp32 round-to-nearest division then fp32->fp16 round-to-nearest. */
+ *   both computed as fp32 round-to-nearest division then fp32->fp16 round-to-nearest.
+ *   workspace: cim_mask_overlap_workspace_bytes(n_img, n, words, inter != NULL) bytes, 256-byte
+ *   aligned (the tensor-core path sorts the masks by position, works in sorted order and un-permutes
+ *   the maps at the end; it needs two temporary maps).  n <= 16384. */
 int cim_mask_pack(const uint8_t *masks, uint32_t *packed, int64_t n_masks, int64_t hw,
                   int64_t words, cim_stream_t stream);
 /* cim_mask_unpack_crops: the compact host->device wire format.  Proposal masks are sent as their
@@ -96,7 +99,7 @@ int cim_mask_pack(const uint8_t *masks, uint32_t *packed, int64_t n_masks, int64
 int cim_mask_unpack_crops(const uint32_t *crop_words, const int32_t *crop_meta, const int64_t *crop_off,
                           uint32_t *packed, int64_t n_masks, int H, int W, int64_t words,
                           cim_stream_t stream);
-size_t cim_mask_overlap_workspace_bytes(int n_img, int n, int64_t words);
+size_t cim_mask_overlap_workspace_bytes(int n_img, int n, int64_t words, int want_inter);
 int cim_mask_overlap(const uint32_t *packed, int n_img, int n, int64_t words,
                      int32_t *inter, int32_t *area, void *iou_f16, void *asy_f16,
                      void *workspace, size_t workspace_bytes, cim_stream_t stream);

@@ -47,6 +47,7 @@ def test_argument_validation_needs_no_gpu():
     assert L.cim_roi_pool_fwd(null, null, null, null, 1, 1, 1, 1, 1, 7, 7, 1.0, null) == -1
     assert L.cim_mask_pack(null, null, 1, 1, 1, null) == -1
     assert L.cim_mask_overlap(null, 1, 1, 1, null, null, null, null, null, 0, null) == -1
+    assert L.cim_mask_overlap_workspace_bytes(8, 2000, 8192, 0) > 2 * 8 * 2000 * 2000 * 2
     assert L.cim_score_heads(null, null, null, null, 1, 1, 1, 1, 1, null, 0, null) == -1
     p = _lib.MineParams()
     assert L.cim_mine_workspace_bytes(C.byref(p)) == 0          # all-zero params are invalid
