@@ -9,6 +9,13 @@
 //   heads 2+K..2+2K-1 (refine_iou): sigmoid                                      (heads.py:216)
 // fp32 FFMA accumulation (TF32 would miss the 1e-5 parity bar).
 #include "common.cuh"
+#include <cstdlib>
+
+// score_heads_tc.cu: 3xTF32 tcgen05 + TMA path
+bool cim_score_tc_eligible(long long M, int D, int C1, int n_ref);
+size_t cim_score_tc_workspace_bytes(int D, int C1, int n_ref);
+int cim_score_tc_launch(const float *x, const float *weight, const float *bias, float *scores, long long M, int D,
+                        int C1, int n_ref, void *workspace, cudaStream_t st);
 
 namespace {
 
@@ -151,14 +158,14 @@ score_col_softmax_kernel(float *__restrict__ det, int R, int C1) {
 
 }  // namespace
 
-CIM_API size_t cim_score_heads_workspace_bytes(int n_img, int R, int C1, int K) {
-    (void)n_img; (void)R; (void)C1; (void)K;
-    return 256;
+CIM_API size_t cim_score_heads_workspace_bytes(int n_img, int R, int D, int C1, int K) {
+    (void)n_img; (void)R;
+    if (D <= 0 || C1 <= 0 || K < 0) return 256;
+    return cim_score_tc_workspace_bytes(D, C1, K);          // W_hi / W_lo of the tensor-core path
 }
 
 CIM_API int cim_score_heads(const float *x, const float *weight, const float *bias, float *scores, int n_img,
                             int R, int D, int C1, int K, void *workspace, size_t ws_bytes, cim_stream_t stream) {
-    (void)workspace; (void)ws_bytes;
     if (!x || !weight || !bias || !scores) return CIM_ERR_ARG;
     if (n_img < 0 || R < 0 || D <= 0 || C1 <= 0 || K < 0 || K > 8) return CIM_ERR_ARG;
     if (n_img == 0 || R == 0) return CIM_OK;
@@ -168,6 +175,16 @@ CIM_API int cim_score_heads(const float *x, const float *weight, const float *bi
     const long long M = (long long)n_img * R;
     if (M > (1LL << 30)) return CIM_ERR_SHAPE;
     const int nheads = 2 + 2 * K, N = nheads * C1;
+    // tensor cores (3xTF32, fp32-accurate) when the shape allows and the caller gave the workspace;
+    // CIM_SCORE_FFMA=1 forces the FFMA kernel (tuning / A-B aid)
+    const char *force = getenv("CIM_SCORE_FFMA");
+    if (!(force && force[0] == '1') && cim_score_tc_eligible(M, D, C1, K) && workspace &&
+        ws_bytes >= cim_score_tc_workspace_bytes(D, C1, K)) {
+        int rc2 = cim_score_tc_launch(x, weight, bias, scores, M, D, C1, K, workspace, st);
+        if (rc2) return rc2;
+        score_col_softmax_kernel<<<dim3((unsigned)C1, (unsigned)n_img), 256, 0, st>>>(scores + (size_t)M * C1, R, C1);
+        return cim_launch_status();
+    }
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
     score_gemm_kernel<<<grid, 256, 0, st>>>(x, weight, bias, scores, (int)M, N, D, C1);
     int rc = cim_launch_status();

@@ -44,7 +44,7 @@ class ScoreHeadsFunction(Function):
         L = _lib.lib()
         with torch.cuda.device(x.device):
             scores = torch.empty((nh, m, c1), dtype=torch.float32, device=x.device)
-            ws = torch.empty(L.cim_score_heads_workspace_bytes(n_img, m // n_img, c1, k), dtype=torch.uint8,
+            ws = torch.empty(L.cim_score_heads_workspace_bytes(n_img, m // n_img, d, c1, k), dtype=torch.uint8,
                              device=x.device)
             rc = L.cim_score_heads(_lib.ptr(x), _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(scores), n_img,
                                    m // n_img, d, c1, k, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(x.device))

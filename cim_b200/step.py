@@ -52,7 +52,7 @@ class CIMHeadStep:
             self.area = e((n_img, R), torch.int32)
             self.overlap_ws = e((self.L.cim_mask_overlap_workspace_bytes(n_img, R, mask_words, 0),), torch.uint8)
             self.scores = e((nh, n_img * R, C1), torch.float32)
-            self.score_ws = e((max(256, self.L.cim_score_heads_workspace_bytes(n_img, R, C1, k)),), torch.uint8)
+            self.score_ws = e((max(256, self.L.cim_score_heads_workspace_bytes(n_img, R, feat_dim, C1, k)),), torch.uint8)
             p = _lib.MineParams()
             p.n_img, p.R, p.C, p.C1, p.n_layers = n_img, R, n_classes, C1, k
             p.det_cols, p.gt_cap, p.mode = C1, R, 0

@@ -118,8 +118,10 @@ int cim_mask_overlap_algo(const uint32_t *packed, int n_img, int n, int64_t word
  * refine_iou.0..K-1], followed by softmax over classes (classifier, refine_cls), softmax over
  * the PROPOSALS of each image (detector, heads.py:203) and sigmoid (refine_iou).
  *   x [n_img*R, D] fp32; weight [n_heads, C1, D]; bias [n_heads, C1];
- *   scores [n_heads, n_img*R, C1] fp32.  workspace: cim_score_heads_workspace_bytes(). */
-size_t cim_score_heads_workspace_bytes(int n_img, int R, int C1, int K);
+ *   scores [n_heads, n_img*R, C1] fp32.  workspace: cim_score_heads_workspace_bytes() bytes; with
+ *   it (and D % 32 == 0, C1 <= 96, n_img*R >= 128) the GEMM runs on the tensor cores as three TF32
+ *   products of hi/lo-split operands (fp32-accurate), otherwise as fp32 FFMA. */
+size_t cim_score_heads_workspace_bytes(int n_img, int R, int D, int C1, int K);
 int cim_score_heads(const float *x, const float *weight, const float *bias, float *scores,
                     int n_img, int R, int D, int C1, int K,
                     void *workspace, size_t workspace_bytes, cim_stream_t stream);
