@@ -8,6 +8,12 @@
 // and   x * w  ~=  x_hi w_hi + x_hi w_lo + x_lo w_hi      (the dropped x_lo w_lo term is ~2^-22),
 // three tcgen05.mma.kind::tf32 products accumulated in fp32 in tensor memory.
 //
+// The tensor core's fp32 accumulator TRUNCATES on every add (measured: the error of a single long
+// chain grows linearly with K, 4.5e-6 at K = 128 -> 9e-5 at K = 4096, tools/score_err.py), so
+// chains are kept short: K is cut into chunks of 128, each chunk accumulates from zero in one of
+// two TMEM accumulators, and the chunk sums are added in registers with round-to-nearest while
+// the next chunk is being multiplied.
+//
 // One CTA per 128 rows of x and per group of heads (all 8 heads at once when 8 (C+1) <= 256).
 //   warp 0      TMA producer: cp.async.bulk.tensor (SWIZZLE_128B) of the x tile [128 x 32 fp32] and
 //               of the W_hi / W_lo tiles [NT x 32] per k-block; mbarrier complete_tx.
@@ -27,6 +33,12 @@ constexpr int BK = 32;                   // fp32 elements per k-block = 128 B = 
 constexpr int NSTAGE = 2;
 constexpr int A_TILE = BM * BK * 4;      // 16 KB
 constexpr int THREADS_TC = 6 * 32;
+constexpr int NT = 176;                  // UMMA N = logit columns per CTA (8 heads x 21 = 168 for VOC)
+constexpr int W_TILE = NT * BK * 4;      // 22 KB
+constexpr int STAGE = 2 * A_TILE + 2 * W_TILE;            // x_hi | x_lo | W_hi | W_lo
+constexpr int CHK = 4;                   // k-blocks per accumulation chunk (K = 128)
+constexpr int LAG = 2;                   // a chunk is drained this many k-blocks after its last split
+constexpr int ZP = NT + 1;               // float pitch of the epilogue staging (odd: lanes = rows)
 
 __device__ __forceinline__ uint64_t smem_desc128(uint32_t saddr) {       // K-major SWIZZLE_128B, SBO 1024 B
     return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
@@ -68,6 +80,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // W -> (W_hi, W_lo), both exactly representable... W_hi in TF32, W_lo = W - W_hi (the MMA drops its
 // low mantissa bits, an error of 2^-21 |W|)
 __global__ void score_split_w_kernel(const float *__restrict__ w, float *__restrict__ w_hi, float *__restrict__ w_lo,
@@ -79,21 +104,18 @@ __global__ void score_split_w_kernel(const float *__restrict__ w, float *__restr
     }
 }
 
-// NCH = ceil(C1 / 32): 32-column TMEM loads per head
-template <int NCH>
 __global__ void __launch_bounds__(THREADS_TC, 1)
 score_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_whi,
                      const __grid_constant__ CUtensorMap tm_wlo, const float *__restrict__ bias,
-                     float *__restrict__ scores, int M, int D, int C1, int n_ref, int heads_per_tile, int NT) {
+                     float *__restrict__ scores, int M, int D, int C1, int n_ref, int heads_per_tile) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int W_TILE = NT * BK * 4;
-    const int STAGE = 2 * A_TILE + 2 * W_TILE;                 // x_hi | x_lo | W_hi | W_lo
     uint64_t *tma_full = reinterpret_cast<uint64_t *>(smem + (size_t)NSTAGE * STAGE);
     uint64_t *lo_ready = tma_full + NSTAGE;
     uint64_t *empty = lo_ready + NSTAGE;
-    uint64_t *accum_full = empty + NSTAGE;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_full + 1);
+    uint64_t *chunk_full = empty + NSTAGE;                      // [2] accumulator p holds a finished chunk
+    uint64_t *chunk_empty = chunk_full + 2;                     // [2] accumulator p has been drained
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(chunk_empty + 2);
     float *s_bias = reinterpret_cast<float *>(tmem_slot + 2);   // [heads_per_tile * C1]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -102,24 +124,24 @@ score_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     const int nheads = 2 + 2 * n_ref;
     const int nh = min(heads_per_tile, nheads - h0);
     const int n0 = h0 * C1;                                     // first row of W / first logit column
-    const int nkb = D / BK;
+    const int nkb = D / BK, nchunks = (nkb + CHK - 1) / CHK;
 
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(&tma_full[s], 1); mbar_init(&lo_ready[s], 4); mbar_init(&empty[s], 1); }
-        mbar_init(accum_full, 1);
+        for (int p = 0; p < 2; ++p) { mbar_init(&chunk_full[p], 1); mbar_init(&chunk_empty[p], 4); }
         fence_mbar_init();
     }
     for (int i = tid; i < nh * C1; i += THREADS_TC) s_bias[i] = bias[n0 + i];
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(256u)
+                     "r"(512u)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = *tmem_slot;                      // accumulator p at columns 256 p
     // instruction descriptor: F32 accumulate, TF32 x TF32, K-major, N = NT, M = 128
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
@@ -139,34 +161,62 @@ score_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % NSTAGE;
+            const int s = kb % NSTAGE, c = kb / CHK, p = c & 1;
+            if (kb % CHK == 0 && c >= 2) mbar_wait(&chunk_empty[p], ((c >> 1) - 1) & 1);   // accumulator p drained
             mbar_wait(&tma_full[s], (kb / NSTAGE) & 1);
             mbar_wait(&lo_ready[s], (kb / NSTAGE) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
-                const uint32_t base = smem_u32(smem + (size_t)s * STAGE);
+                const uint32_t base = smem_u32(smem + (size_t)s * STAGE), acc = tmem_base + 256u * p;
                 const uint64_t xh = smem_desc128(base), xl = smem_desc128(base + A_TILE);
                 const uint64_t wh = smem_desc128(base + 2 * A_TILE), wl = smem_desc128(base + 2 * A_TILE + W_TILE);
 #pragma unroll
                 for (int k = 0; k < BK / 8; ++k) {        // K = 8 tf32 = 32 B per instruction: +2 in 16 B units
-                    mma_tf32(tmem_base, xh + 2 * k, wh + 2 * k, idesc, (kb | k) != 0);
-                    mma_tf32(tmem_base, xh + 2 * k, wl + 2 * k, idesc, 1u);
-                    mma_tf32(tmem_base, xl + 2 * k, wh + 2 * k, idesc, 1u);
+                    mma_tf32(acc, xh + 2 * k, wh + 2 * k, idesc, ((kb % CHK) | k) != 0);   // a chunk starts from 0
+                    mma_tf32(acc, xh + 2 * k, wl + 2 * k, idesc, 1u);
+                    mma_tf32(acc, xl + 2 * k, wh + 2 * k, idesc, 1u);
                 }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                                  smem_u32(&empty[s]))
                              : "memory");
-                if (kb == nkb - 1)
+                if (kb % CHK == CHK - 1 || kb == nkb - 1)
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                                     smem_u32(accum_full))
+                                     smem_u32(&chunk_full[p]))
                                  : "memory");
             }
             __syncwarp();
         }
     } else {
-        // ------------------------------------------------------------------ hi / lo split of the x tile
+        // ------------------------------------------------------------------ split warps (+ chunk drains)
         const int row = tid - 64;                              // 0..127: one x row per thread
         const uint32_t row_off = (row >> 3) * 1024 + (row & 7) * 128, sw = row & 7;
+        const int q4 = warp & 3;                               // TMEM lane quarter this warp may read
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q4) << 16);
+        float acc[NT];                                         // logits of TMEM lane 32 q4 + lane, RN-accumulated
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[j] = 0.f;
+        auto drain = [&](int c) {
+            const int p = c & 1;
+            mbar_wait(&chunk_full[p], (c >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int cc = 0; cc < NT / 32; ++cc) {
+                float v[32];
+                tmem_ld32(lane_addr + 256u * p + 32u * cc, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += v[j];
+            }
+            if (NT % 32) {
+                float v[16];
+                tmem_ld16(lane_addr + 256u * p + (uint32_t)(NT / 32 * 32), v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[NT / 32 * 32 + j] += v[j];
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive1(&chunk_empty[p]);
+        };
+        int next_drain = 0;
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % NSTAGE;
             mbar_wait(&tma_full[s], (kb / NSTAGE) & 1);
@@ -187,47 +237,39 @@ score_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive1(&lo_ready[s]);
+            // drain the chunks whose last k-block was split LAG iterations ago (their MMAs are done or
+            // nearly done by now, so this does not hold up the split of the next stages)
+            while (next_drain < nchunks && min((next_drain + 1) * CHK, nkb) - 1 + LAG <= kb) drain(next_drain++);
         }
+        while (next_drain < nchunks) drain(next_drain++);
 
         // ------------------------------------------------------------------ epilogue
-        mbar_wait(accum_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int q4 = warp & 3;                               // TMEM lane quarter this warp may read
+        // every MMA has completed (the last chunk was drained): the stage memory is free.  Each thread
+        // parks its row in smem (so that the heads can be indexed at run time), adds the bias and applies
+        // the activation: softmax over classes / sigmoid; the detector head keeps its logits.
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        float *zrow = reinterpret_cast<float *>(smem) + (size_t)(32 * q4 + lane) * ZP;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) zrow[j] = acc[j];
         const int m = m0 + 32 * q4 + lane;
-        for (int hh = 0; hh < nh; ++hh) {
-            const int h = h0 + hh;
-            float z[NCH * 32];
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(32 * q4) << 16) + (uint32_t)(hh * C1 + 32 * c), v);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) z[c * 32 + j] = v[j];
-            }
-            if (m >= M) continue;
-            const float *bh = s_bias + hh * C1;
-            float *dst = scores + ((size_t)h * M + m) * C1;
-            const bool softmax = (h == 0) || (h >= 2 && h < 2 + n_ref);
-            if (softmax) {
-                float mx = -INFINITY;
-#pragma unroll
-                for (int j = 0; j < NCH * 32; ++j)
-                    if (j < C1) { z[j] += bh[j]; mx = fmaxf(mx, z[j]); }
-                float sum = 0.f;
-#pragma unroll
-                for (int j = 0; j < NCH * 32; ++j)
-                    if (j < C1) { z[j] = expf(z[j] - mx); sum += z[j]; }
-#pragma unroll
-                for (int j = 0; j < NCH * 32; ++j)
-                    if (j < C1) dst[j] = z[j] / sum;
-            } else if (h == 1) {                               // detector: logits, column softmax follows
-#pragma unroll
-                for (int j = 0; j < NCH * 32; ++j)
-                    if (j < C1) dst[j] = z[j] + bh[j];
-            } else {                                           // refine_iou: sigmoid
-#pragma unroll
-                for (int j = 0; j < NCH * 32; ++j)
-                    if (j < C1) dst[j] = 1.f / (1.f + expf(-(z[j] + bh[j])));
+        if (m < M) {
+            for (int hh = 0; hh < nh; ++hh) {
+                const int h = h0 + hh;
+                float *z = zrow + hh * C1;
+                const float *bh = s_bias + hh * C1;
+                float *dst = scores + ((size_t)h * M + m) * C1;
+                const bool softmax = (h == 0) || (h >= 2 && h < 2 + n_ref);
+                if (softmax) {
+                    float mx = -INFINITY;
+                    for (int j = 0; j < C1; ++j) { z[j] += bh[j]; mx = fmaxf(mx, z[j]); }
+                    float sum = 0.f;
+                    for (int j = 0; j < C1; ++j) { z[j] = expf(z[j] - mx); sum += z[j]; }
+                    for (int j = 0; j < C1; ++j) dst[j] = z[j] / sum;
+                } else if (h == 1) {                           // detector: logits, column softmax follows
+                    for (int j = 0; j < C1; ++j) dst[j] = z[j] + bh[j];
+                } else {                                       // refine_iou: sigmoid
+                    for (int j = 0; j < C1; ++j) dst[j] = 1.f / (1.f + expf(-(z[j] + bh[j])));
+                }
             }
         }
     }
@@ -235,7 +277,7 @@ score_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -269,7 +311,7 @@ bool make_map(CUtensorMap *map, const float *base, long long rows, long long col
 // can the tensor-core path take this shape?  (else score_heads.cu's FFMA kernel runs)
 bool cim_score_tc_eligible(long long M, int D, int C1, int n_ref) {
     (void)n_ref;
-    return M >= BM && (D % BK) == 0 && D >= BK && C1 >= 1 && C1 <= 96 && encode_tiled() != nullptr &&
+    return M >= BM && (D % BK) == 0 && D >= BK && C1 >= 1 && C1 <= NT && encode_tiled() != nullptr &&
            cim_max_smem_optin() >= 200 * 1024;
 }
 size_t cim_score_tc_workspace_bytes(int D, int C1, int n_ref) {
@@ -285,21 +327,16 @@ int cim_score_tc_launch(const float *x, const float *weight, const float *bias, 
     score_split_w_kernel<<<256, 256, 0, st>>>(weight, w_hi, w_lo, (long long)N * D);
     int rc = cim_launch_status();
     if (rc) return rc;
-    const int heads_per_tile = min(nheads, 256 / C1);
+    const int heads_per_tile = min(nheads, NT / C1);
     const int ntiles = (nheads + heads_per_tile - 1) / heads_per_tile;
-    const int NT = (heads_per_tile * C1 + 15) / 16 * 16;        // UMMA N: multiple of 16, <= 256
     CUtensorMap tx, twh, twl;
     if (!make_map(&tx, x, M, D, BM) || !make_map(&twh, w_hi, N, D, NT) || !make_map(&twl, w_lo, N, D, NT))
         return CIM_ERR_ARG;
-    const size_t stage = 2 * (size_t)A_TILE + 2 * (size_t)NT * BK * 4;
-    const size_t smem = 1024 + NSTAGE * stage + 256 + sizeof(float) * (size_t)heads_per_tile * C1;
+    const size_t body = (size_t)NSTAGE * STAGE > (size_t)BM * ZP * 4 ? (size_t)NSTAGE * STAGE : (size_t)BM * ZP * 4;
+    const size_t smem = 1024 + body + 256 + sizeof(float) * (size_t)heads_per_tile * C1;
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)ntiles);
-    const int nch = (C1 + 31) / 32;
-#define LAUNCH_TC(NCH)                                                                                             \
-    cudaFuncSetAttribute(score_gemm_tc_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
-    score_gemm_tc_kernel<NCH><<<grid, THREADS_TC, smem, st>>>(tx, twh, twl, bias, scores, (int)M, D, C1, n_ref,    \
-                                                               heads_per_tile, NT)
-    if (nch == 1) { LAUNCH_TC(1); } else if (nch == 2) { LAUNCH_TC(2); } else { LAUNCH_TC(3); }
-#undef LAUNCH_TC
+    cudaFuncSetAttribute(score_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    score_gemm_tc_kernel<<<grid, THREADS_TC, smem, st>>>(tx, twh, twl, bias, scores, (int)M, D, C1, n_ref,
+                                                         heads_per_tile);
     return cim_launch_status();
 }
