@@ -11,17 +11,21 @@
 //      product of its row and column weight, already divided by the sample count).  It also
 //      checks that rois are grouped by image and records each image's ROI range.
 //   2. Tile kernels: a CTA keeps the [32 channels x H x W] feature (or gradient) tile of one
-//      image in shared memory (pitch odd => lane = channel is bank-conflict free) and sweeps
-//      the image's ROIs.
+//      image in shared memory and sweeps the image's ROIs, lane = channel.  The tile is stored
+//      ROW-PAIR INTERLEAVED: rows 2p and 2p+1 of a channel alternate element by element, so one
+//      LDS.64 / STS.64 moves (f[2p][x], f[2p+1][x]) and one FFMA2 (fma.rn.f32x2, weight as the
+//      scalar-broadcast operand) does the arithmetic of both rows.  The channel pitch is 2 x odd
+//      words, which makes the 64-bit accesses of a warp bank-conflict free.
 //        forward : persistent, one CTA per SM, (roi, chunk) units split evenly; a warp owns one
 //                  ROI at a time, its descriptor is prefetched into smem with cp.async (LDGSTS)
-//                  one ROI ahead; ROW SWEEP: each feature value of the ROI window is loaded once,
-//                  the 7 column sums of a row are added into the output rows whose window holds
-//                  that row (49 accumulators in registers); the 32 x 49 outputs are staged in
-//                  smem and leave with one 6272-byte cp.async.bulk (UBLKCP) per (roi, 32 ch).
+//                  one ROI ahead; ROW-PAIR SWEEP: per row pair the 7 column sums (x pass) are
+//                  formed once and added into all 7 output rows with a dense, branch-free y pass
+//                  (per-warp smem table of the pair's 7 x 2 row weights); 49 float2 accumulators
+//                  (even row / odd row partial sums) in registers; the 32 x 49 outputs are staged
+//                  in smem and leave with one 6272-byte cp.async.bulk (UBLKCP) per (roi, 32 ch).
 //        backward: gradients + descriptors stream through a 3-slot mbarrier ring of 4 ROIs each
 //                  (cp.async.bulk, no CTA-wide barrier); warp w of 16 owns the tile row pairs
-//                  (y >> 1) % 16 == w, so every tile address has exactly one writer and ROIs are
+//                  p % 16 == w, so every tile address has exactly one writer and ROIs are
 //                  applied in index order: no atomics, bit-reproducible.
 //   3. Generic kernels (one thread per output element, sample by sample) take whatever the
 //      tile kernels cannot: other output sizes, feature maps too large for shared memory,
@@ -32,11 +36,13 @@ namespace {
 
 constexpr int PH = 7, PW = 7, NBIN = 49;
 constexpr int MAXT = 8;             // max collapsed taps per bin and axis in a descriptor
-constexpr int DESC_WORDS = 160;     // 640 B per ROI
+constexpr int WYP = MAXT + 2;       // row weights of a bin, padded: [0, w_0 .. w_7, 0]
+constexpr int DESC_WORDS = 168;     // 672 B per ROI
 enum {
     D_B = 0, D_FLAGY = 1, D_FLAGX = 2, D_TX = 3, D_Y0 = 4, D_Y1 = 5, D_XINC = 6, D_OWN = 7,
-    D_YLO = 8, D_YN = 16, D_XLO = 24, D_XN = 32, D_WY = 40, D_WX = 96
+    D_YLO = 8, D_YN = 16, D_XLO = 24, D_PHR = 32 /* 32 bytes */, D_WY = 40 /* [7][WYP] */, D_WX = 112 /* [7][MAXT] */
 };
+static_assert(D_WY + 7 * WYP <= D_WX && D_WX + 7 * MAXT == DESC_WORDS && (DESC_WORDS % 4) == 0, "descriptor layout");
 constexpr int WS_HDR_BYTES = 256;   // word 0: "rois not grouped by image" flag
 constexpr int CH = 32;              // channels per tile (= lanes)
 constexpr int STAGE_FLOATS = CH * NBIN;          // 1568 floats = 6272 B
@@ -141,18 +147,37 @@ __global__ void roi_prep_kernel(const float *__restrict__ rois, int K, int B, in
             d[D_YLO + p] = lo;
             d[D_YN + p] = n;
             if (n > 0) { y0 = min(y0, lo); y1 = max(y1, lo + n); }
-            for (int i = 0; i < MAXT; ++i)
-                reinterpret_cast<float *>(d)[D_WY + p * MAXT + i] = flag ? 0.f : w_[p][i];
+            float *wy = reinterpret_cast<float *>(d) + D_WY + p * WYP;
+            wy[0] = 0.f;
+            wy[WYP - 1] = 0.f;
+            for (int i = 0; i < MAXT; ++i) wy[1 + i] = flag ? 0.f : w_[p][i];
         }
         if (y1 == 0) y0 = 0;
         d[D_Y0] = y0;
         d[D_Y1] = y1;
-        // backward: which of the 16 warps own a row of [y0, y1)?  warp w owns the row pairs (y >> 1) % 16 == w
+        // backward: which of the 16 warps own a row of [y0, y1)?  warp w owns the row pairs p = y >> 1 with p % 16 == w
         int own = 0;
         for (int y = y0; y < y1 && own != 0xffff; ++y) own |= 1 << ((y >> 1) & 15);
         d[D_OWN] = flag ? 0 : own;
         d[D_YLO + 7] = 0;
         d[D_YN + 7] = 0;
+        // backward: byte j of D_PHR = first | count << 4 of the bins whose row window meets row pair
+        // (y0 >> 1) + j (windows are monotone in the bin index, so the set is a contiguous range)
+        unsigned char *phr = reinterpret_cast<unsigned char *>(d + D_PHR);
+        const int pb = y0 >> 1, pe = (y1 + 1) >> 1;
+        if (pe - pb > 32) {                       // more row pairs than the table holds (H > 64): generic path
+            d[D_FLAGY] = 1;
+            d[D_OWN] = 0;
+        }
+        for (int j = 0; j < 32; ++j) {
+            int first = 0, cnt = 0;
+            if (!flag && pb + j < pe)
+                for (int p = 0; p < 7; ++p) {
+                    const int rel = 2 * (pb + j) - lo_[p];       // window index of row 2 (pb + j)
+                    if (n_[p] > 0 && rel + 1 >= 0 && rel < n_[p]) { if (cnt == 0) first = p; cnt = p - first + 1; }
+                }
+            phr[j] = (unsigned char)(first | (cnt << 4));
+        }
     } else {
         // tap class T in {2,3,4,6,8}: the x loops of the tile kernels are unrolled T times.
         int T = nmax <= 2 ? 2 : nmax <= 3 ? 3 : nmax <= 4 ? 4 : nmax <= 6 ? 6 : 8;
@@ -168,7 +193,6 @@ __global__ void roi_prep_kernel(const float *__restrict__ rois, int K, int B, in
             if (lo2 < 0) lo2 = 0;
             int sh = lo - lo2;
             d[D_XLO + p] = lo2;
-            d[D_XN + p] = flag ? 0 : n_[p];
             for (int i = 0; i < MAXT; ++i) {
                 int src = i - sh;
                 float v = (!flag && src >= 0 && src < MAXT) ? w_[p][src] : 0.f;
@@ -179,28 +203,38 @@ __global__ void roi_prep_kernel(const float *__restrict__ rois, int K, int B, in
         }
         d[D_XINC] = inc;      // 1: window starts strictly increase -> taps of one l never alias
         d[D_XLO + 7] = 0;
-        d[D_XN + 7] = 0;
     }
 }
 
 // ------------------------------------------------------------------------------ tile: forward
-__device__ __forceinline__ void load_tile(float *tile, const float *__restrict__ src, int HW,
+// Tile layout (both directions): element (c, y, x) lives at tile[c * pitch + ((y >> 1) * W + x) * 2 + (y & 1)],
+// i.e. as float2 index c * pitch / 2 + (y >> 1) * W + x  ->  (f[2p][x], f[2p+1][x]).  H odd: the missing
+// row of the last pair is zero (its weights are zero too, but it must be finite).
+__device__ __forceinline__ int tile_off(int y, int x, int W) { return (((y >> 1) * W + x) << 1) + (y & 1); }
+
+__device__ __forceinline__ void load_tile(float *tile, const float *__restrict__ src, int H, int W,
                                           int pitch, int tid, int nthr) {
-    if ((HW & 3) == 0) {
+    const int HW = H * W;
+    if ((W & 3) == 0) {
         const float4 *s4 = reinterpret_cast<const float4 *>(src);
-        int n4 = CH * HW / 4;
+        const int n4 = CH * HW / 4;
         for (int e = tid; e < n4; e += nthr) {
-            float4 v = __ldg(s4 + e);
-            int idx = e * 4, c = idx / HW, p = idx - c * HW;
-            float *dst = tile + c * pitch + p;
-            dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+            const float4 v = __ldg(s4 + e);
+            const int idx = e * 4, c = idx / HW, rem = idx - c * HW, y = rem / W, x = rem - y * W;
+            float *dst = tile + c * pitch + tile_off(y, x, W);
+            dst[0] = v.x; dst[2] = v.y; dst[4] = v.z; dst[6] = v.w;
         }
     } else {
         for (int e = tid; e < CH * HW; e += nthr) {
-            int c = e / HW, p = e - c * HW;
-            tile[c * pitch + p] = __ldg(src + e);
+            const int c = e / HW, rem = e - c * HW, y = rem / W, x = rem - y * W;
+            tile[c * pitch + tile_off(y, x, W)] = __ldg(src + e);
         }
     }
+    if (H & 1)
+        for (int e = tid; e < CH * W; e += nthr) {
+            const int c = e / W, x = e - c * W;
+            tile[c * pitch + tile_off(H, x, W)] = 0.f;
+        }
 }
 
 // 16-byte async copy global -> shared (LDGSTS), per-thread completion groups
@@ -211,84 +245,122 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// One ROI x 32 channels (lane = channel).  Row sweep: every feature value of the ROI's window is
-// loaded from the smem tile once; the 7 column sums of a row are formed with the register-resident
-// column weights and then added into the (at most 2-3) output rows whose window contains this
-// feature row.  All control flow depends only on the descriptor, i.e. is warp-uniform.
+__device__ __forceinline__ float2 bcast2(float w) { return make_float2(w, w); }   // FFMA2 takes it as R.F32
+
+// One ROI x 32 channels (lane = channel), row-pair sweep.  Per pair p of the ROI's rows:
+//   x pass: r[pw] = sum_l wx[pw][l] * (f[2p][xo+l], f[2p+1][xo+l])        7T LDS.64 + 7T FFMA2
+//   y pass: (out[2q][pw], out[2q+1][pw]) += (wy[2q][y], wy[2q+1][y]) * r_y[pw]  for y = 2p, 2p+1 and ALL q:
+//           56 FFMA2 with r_y as the scalar-broadcast operand; the weights (mostly zero) come from the warp's
+//           dense per-row table wyd[y][8] -- no data-dependent branch in the loop, 28 float2 accumulators.
+// All control flow depends only on the descriptor (warp-uniform).  T >= 6 keeps the x weights in smem.
 template <int T>
-__device__ __forceinline__ void fwd_rows(const float *__restrict__ tile_c, int W, const int *__restrict__ d,
-                                         float *__restrict__ stage_c, float *stage_w, int lane) {
-    float wx[PW][T];
-    int xo[PW], ylo[PH], yhi[PH];
+__device__ __forceinline__ void fwd_pairs(const float *__restrict__ tile_c, int W, const int *__restrict__ d,
+                                          float *__restrict__ stage_c, const float4 *__restrict__ wyd, int lane) {
+    constexpr bool WREG = T <= 4;
+    constexpr int TR = WREG ? T : 1;
+    float wx[PW][TR];
+    int xo[PW];
     const float *dwx = reinterpret_cast<const float *>(d + D_WX);
-    const float *dwy = reinterpret_cast<const float *>(d + D_WY);
     {
         int4 a = *reinterpret_cast<const int4 *>(d + D_XLO), b = *reinterpret_cast<const int4 *>(d + D_XLO + 4);
         xo[0] = a.x; xo[1] = a.y; xo[2] = a.z; xo[3] = a.w; xo[4] = b.x; xo[5] = b.y; xo[6] = b.z;
-        a = *reinterpret_cast<const int4 *>(d + D_YLO); b = *reinterpret_cast<const int4 *>(d + D_YLO + 4);
-        ylo[0] = a.x; ylo[1] = a.y; ylo[2] = a.z; ylo[3] = a.w; ylo[4] = b.x; ylo[5] = b.y; ylo[6] = b.z;
-        a = *reinterpret_cast<const int4 *>(d + D_YN); b = *reinterpret_cast<const int4 *>(d + D_YN + 4);
-        yhi[0] = ylo[0] + a.x; yhi[1] = ylo[1] + a.y; yhi[2] = ylo[2] + a.z; yhi[3] = ylo[3] + a.w;
-        yhi[4] = ylo[4] + b.x; yhi[5] = ylo[5] + b.y; yhi[6] = ylo[6] + b.z;
     }
-#pragma unroll
-    for (int pw = 0; pw < PW; ++pw) {
-        float4 a = *reinterpret_cast<const float4 *>(dwx + pw * MAXT);
-        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (T > 4) b = *reinterpret_cast<const float4 *>(dwx + pw * MAXT + 4);
-        float t8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int l = 0; l < T; ++l) wx[pw][l] = t8[l];
-    }
-    float acc[PH][PW];
-#pragma unroll
-    for (int ph = 0; ph < PH; ++ph)
-#pragma unroll
-        for (int pw = 0; pw < PW; ++pw) acc[ph][pw] = 0.f;
-
-    const int y0 = d[D_Y0], y1 = d[D_Y1];
-#pragma unroll 1
-    for (int y = y0; y < y1; ++y) {
-        const float *row = tile_c + y * W;
-        float r[PW];
+    if (WREG) {
 #pragma unroll
         for (int pw = 0; pw < PW; ++pw) {
-            float t = 0.f;
+            const float4 a = *reinterpret_cast<const float4 *>(dwx + pw * MAXT);
+            const float t4[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-            for (int l = 0; l < T; ++l) t = fmaf(wx[pw][l], row[xo[pw] + l], t);
+            for (int l = 0; l < TR; ++l) wx[pw][l] = t4[l];
+        }
+    }
+    float2 acc[4][PW];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int pw = 0; pw < PW; ++pw) acc[q][pw] = make_float2(0.f, 0.f);
+
+    const int p0 = d[D_Y0] >> 1, p1 = (d[D_Y1] + 1) >> 1;
+    const float2 *tile2 = reinterpret_cast<const float2 *>(tile_c);
+#pragma unroll 1
+    for (int p = p0; p < p1; ++p) {
+        const float2 *row = tile2 + p * W;
+        float2 r[PW];
+#pragma unroll
+        for (int pw = 0; pw < PW; ++pw) {
+            float2 t = make_float2(0.f, 0.f);
+            if (WREG) {
+#pragma unroll
+                for (int l = 0; l < T; ++l) t = __ffma2_rn(bcast2(wx[pw][l]), row[xo[pw] + l], t);
+            } else {
+                const float4 a = *reinterpret_cast<const float4 *>(dwx + pw * MAXT);
+                const float4 b = *reinterpret_cast<const float4 *>(dwx + pw * MAXT + 4);
+                const float t8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int l = 0; l < T; ++l) t = __ffma2_rn(bcast2(t8[l]), row[xo[pw] + l], t);
+            }
             r[pw] = t;
         }
+        const float4 *wq = wyd + (p - p0) * 4;             // rows 2p (wq[0..1]) and 2p+1 (wq[2..3])
+        const float4 e0 = wq[0], e1 = wq[1], o0 = wq[2], o1 = wq[3];
+        const float2 we[4] = {make_float2(e0.x, e0.y), make_float2(e0.z, e0.w), make_float2(e1.x, e1.y),
+                              make_float2(e1.z, e1.w)};
+        const float2 wo[4] = {make_float2(o0.x, o0.y), make_float2(o0.z, o0.w), make_float2(o1.x, o1.y),
+                              make_float2(o1.z, o1.w)};
 #pragma unroll
-        for (int ph = 0; ph < PH; ++ph) {
-            if (y >= ylo[ph] && y < yhi[ph]) {
-                const float w = dwy[ph * MAXT + (y - ylo[ph])];
+        for (int q = 0; q < 4; ++q)
 #pragma unroll
-                for (int pw = 0; pw < PW; ++pw) acc[ph][pw] = fmaf(w, r[pw], acc[ph][pw]);
+            for (int pw = 0; pw < PW; ++pw) {
+                acc[q][pw] = __ffma2_rn(bcast2(r[pw].x), we[q], acc[q][pw]);
+                acc[q][pw] = __ffma2_rn(bcast2(r[pw].y), wo[q], acc[q][pw]);
             }
-        }
     }
     if (lane == 0) bulk_wait_read<0>();            // the previous bulk store has drained this stage
     __syncwarp();
 #pragma unroll
-    for (int ph = 0; ph < PH; ++ph)
+    for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int pw = 0; pw < PW; ++pw) stage_c[ph * PW + pw] = acc[ph][pw];
-    (void)stage_w;
+        for (int pw = 0; pw < PW; ++pw) {
+            stage_c[(2 * q) * PW + pw] = acc[q][pw].x;
+            if (q < 3) stage_c[(2 * q + 1) * PW + pw] = acc[q][pw].y;
+        }
 }
 
-__global__ void __launch_bounds__(384, 1)
+// The warp's dense y-weight table for one ROI: wyd[(y - 2 p0) * 8 + ph] = weight of tile row y in output row
+// ph (0 where row y is outside the bin's window; word 7 of a row is 0, it feeds the unused half of acc[3]).
+__device__ __forceinline__ void build_wyd(float *wyd, const int *__restrict__ d, int lane) {
+    const int p0 = d[D_Y0] >> 1, np = ((d[D_Y1] + 1) >> 1) - p0;
+    float4 *w4 = reinterpret_cast<float4 *>(wyd);
+    for (int i = lane; i < np * 4; i += 32) w4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+    const float *dwy = reinterpret_cast<const float *>(d + D_WY);
+    for (int t = lane; t < PH * MAXT; t += 32) {
+        const int ph = t >> 3, i = t & 7;
+        if (i < d[D_YN + ph]) {
+            const int y = d[D_YLO + ph] + i;
+            wyd[(y - 2 * p0) * 8 + ph] = dwy[ph * WYP + 1 + i];
+        }
+    }
+    __syncwarp();
+}
+
+constexpr int FWD_MAX_WARPS = 11;
+
+__global__ void __launch_bounds__(FWD_MAX_WARPS * 32, 1)
 roi_align_fwd_tile_kernel(const float *__restrict__ feat, const int *__restrict__ hdr,
                           const int *__restrict__ img_start, const int *__restrict__ descs,
-                          float *__restrict__ out, int B, int C, int H, int W, int pitch) {
+                          float *__restrict__ out, int B, int C, int H, int W, int pitch, int wyd_floats) {
     extern __shared__ __align__(128) float smem[];
     const int nw = blockDim.x >> 5;
     float *tile = smem;
     float *stage = smem + (size_t)CH * pitch;                                    // [nw][1568]
-    int *dslots = reinterpret_cast<int *>(stage + (size_t)nw * STAGE_FLOATS);   // [nw][2][160]
+    int *dslots = reinterpret_cast<int *>(stage + (size_t)nw * STAGE_FLOATS);   // [nw][2][DESC_WORDS]
+    float *wyds = reinterpret_cast<float *>(dslots + (size_t)nw * 2 * DESC_WORDS);   // [nw][wyd_floats]
     if (__ldg(hdr) != 0) return;              // rois not grouped by image: generic kernel runs
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int HW = H * W, nchunks = C / CH;
+    const int nchunks = C / CH;
+    const size_t HW = (size_t)H * W;
     const int s0 = __ldg(img_start), sB = __ldg(img_start + B);
     const long long U = (long long)nchunks * (sB - s0);     // (roi, chunk) units
     long long u = U * blockIdx.x / gridDim.x;
@@ -296,13 +368,14 @@ roi_align_fwd_tile_kernel(const float *__restrict__ feat, const int *__restrict_
     float *stage_w = stage + warp * STAGE_FLOATS;
     float *stage_c = stage_w + lane * NBIN;
     int *my_slots = dslots + warp * 2 * DESC_WORDS;
+    float *my_wyd = wyds + (size_t)warp * wyd_floats;
 
-    // descriptor prefetch: 640 B = 40 x 16 B per ROI, lanes 0..31 + lanes 0..7 again
+    // descriptor prefetch: 672 B = 42 x 16 B per ROI, lanes 0..31 + lanes 0..9 again
     auto prefetch = [&](int roi, int slot) {
         const int *src = descs + (size_t)roi * DESC_WORDS;
         int *dst = my_slots + slot * DESC_WORDS;
         cp_async16(dst + lane * 4, src + lane * 4);
-        if (lane < 8) cp_async16(dst + (32 + lane) * 4, src + (32 + lane) * 4);
+        if (lane < DESC_WORDS / 4 - 32) cp_async16(dst + (32 + lane) * 4, src + (32 + lane) * 4);
         cp_async_commit();
     };
 
@@ -320,7 +393,7 @@ roi_align_fwd_tile_kernel(const float *__restrict__ feat, const int *__restrict_
         int r = r0 + warp, slot = 0;
         if (r < r1) prefetch(is + r, 0);       // overlaps the tile load below
         __syncthreads();                       // everyone is done with the previous tile
-        load_tile(tile, feat + ((size_t)b * C + c0) * HW, HW, pitch, tid, blockDim.x);
+        load_tile(tile, feat + ((size_t)b * C + c0) * HW, H, W, pitch, tid, blockDim.x);
         __syncthreads();
 
         const float *tile_c = tile + lane * pitch;
@@ -331,12 +404,14 @@ roi_align_fwd_tile_kernel(const float *__restrict__ feat, const int *__restrict_
             const int *d = my_slots + slot * DESC_WORDS;
             const int roi = is + r;
             if ((d[D_FLAGY] | d[D_FLAGX]) == 0) {
+                build_wyd(my_wyd, d, lane);
+                const float4 *wyd4 = reinterpret_cast<const float4 *>(my_wyd);
                 switch (d[D_TX]) {
-                    case 2: fwd_rows<2>(tile_c, W, d, stage_c, stage_w, lane); break;
-                    case 3: fwd_rows<3>(tile_c, W, d, stage_c, stage_w, lane); break;
-                    case 4: fwd_rows<4>(tile_c, W, d, stage_c, stage_w, lane); break;
-                    case 6: fwd_rows<6>(tile_c, W, d, stage_c, stage_w, lane); break;
-                    default: fwd_rows<8>(tile_c, W, d, stage_c, stage_w, lane); break;
+                    case 2: fwd_pairs<2>(tile_c, W, d, stage_c, wyd4, lane); break;
+                    case 3: fwd_pairs<3>(tile_c, W, d, stage_c, wyd4, lane); break;
+                    case 4: fwd_pairs<4>(tile_c, W, d, stage_c, wyd4, lane); break;
+                    case 6: fwd_pairs<6>(tile_c, W, d, stage_c, wyd4, lane); break;
+                    default: fwd_pairs<8>(tile_c, W, d, stage_c, wyd4, lane); break;
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -361,20 +436,20 @@ constexpr int NBR = 4;              // ROIs per ring slot: one full/empty barrie
 constexpr int NS = 3;               // ring slots
 constexpr int SLOT_FLOATS = NBR * (STAGE_FLOATS + DESC_WORDS);
 
+// One ROI x 32 channels x the row pairs this warp owns.  Per owned pair p:
+//   y pass: r[pw] = sum_ph (wy[ph][2p], wy[ph][2p+1]) * g[ph][pw]   over the bins D_PHR lists for the pair
+//   x pass: (t[2p][xo+l], t[2p+1][xo+l]) += wx[pw][l] * r[pw]       7T x (LDS.64, FFMA2, STS.64)
 template <int T, bool XINC>
-__device__ __forceinline__ void bwd_rows(float *__restrict__ tile_c, int W, const int *d,
-                                         const float *__restrict__ g, int warp, int y0, int y1) {
+__device__ __forceinline__ void bwd_pairs(float *__restrict__ tile_c, int W, const int *d,
+                                          const float *__restrict__ g, int warp, int y0, int y1) {
     float wx[PW][T];
-    int xo[PW], ylo[PH], yn[PH];
+    int xo[PW];
     const float *dwx = reinterpret_cast<const float *>(d + D_WX);
     const float *dwy = reinterpret_cast<const float *>(d + D_WY);
+    const unsigned char *phr = reinterpret_cast<const unsigned char *>(d + D_PHR);
     {
         int4 a = *reinterpret_cast<const int4 *>(d + D_XLO), b = *reinterpret_cast<const int4 *>(d + D_XLO + 4);
         xo[0] = a.x; xo[1] = a.y; xo[2] = a.z; xo[3] = a.w; xo[4] = b.x; xo[5] = b.y; xo[6] = b.z;
-        a = *reinterpret_cast<const int4 *>(d + D_YLO); b = *reinterpret_cast<const int4 *>(d + D_YLO + 4);
-        ylo[0] = a.x; ylo[1] = a.y; ylo[2] = a.z; ylo[3] = a.w; ylo[4] = b.x; ylo[5] = b.y; ylo[6] = b.z;
-        a = *reinterpret_cast<const int4 *>(d + D_YN); b = *reinterpret_cast<const int4 *>(d + D_YN + 4);
-        yn[0] = a.x; yn[1] = a.y; yn[2] = a.z; yn[3] = a.w; yn[4] = b.x; yn[5] = b.y; yn[6] = b.z;
     }
 #pragma unroll
     for (int pw = 0; pw < PW; ++pw) {
@@ -385,43 +460,48 @@ __device__ __forceinline__ void bwd_rows(float *__restrict__ tile_c, int W, cons
 #pragma unroll
         for (int l = 0; l < T; ++l) wx[pw][l] = t8[l];
     }
-    // the row pairs this warp owns: 2*warp + 32*m, clipped to the ROI's rows [y0, y1)
-    for (int yb = 2 * warp; yb < y1; yb += 2 * NWB) {
+    float2 *tile2 = reinterpret_cast<float2 *>(tile_c);
+    const int pb = y0 >> 1, p1 = (y1 + 1) >> 1;
+    // first owned pair >= pb: pairs p with p % NWB == warp
+    int p = pb + ((warp - pb) & (NWB - 1));
 #pragma unroll 1
-        for (int y = max(yb, y0); y < min(yb + 2, y1); ++y) {
-            float r[PW];
+    for (; p < p1; p += NWB) {
+        float2 r[PW];
 #pragma unroll
-            for (int pw = 0; pw < PW; ++pw) r[pw] = 0.f;
+        for (int pw = 0; pw < PW; ++pw) r[pw] = make_float2(0.f, 0.f);
+        const int code = phr[p - pb];
+        const int ph_end = (code & 15) + (code >> 4);
+#pragma unroll 1
+        for (int ph = code & 15; ph < ph_end; ++ph) {
+            const int dd = 2 * p - d[D_YLO + ph];    // window index of row 2p, in [-1, yn): padded weights
+            const float2 w = make_float2(dwy[ph * WYP + dd + 1], dwy[ph * WYP + dd + 2]);
+            const float *gp = g + ph * PW;
 #pragma unroll
-            for (int ph = 0; ph < PH; ++ph) {
-                int dd = y - ylo[ph];
-                if (dd >= 0 && dd < yn[ph]) {
-                    float w = dwy[ph * MAXT + dd];
+            for (int pw = 0; pw < PW; ++pw) r[pw] = __ffma2_rn(bcast2(gp[pw]), w, r[pw]);
+        }
+        float2 *row = tile2 + p * W;
+        if (XINC) {
+            // window starts strictly increase: the 7 taps of one l hit 7 distinct columns,
+            // so they can be loaded, updated and stored as a group
 #pragma unroll
-                    for (int pw = 0; pw < PW; ++pw) r[pw] = fmaf(w, g[ph * PW + pw], r[pw]);
-                }
+            for (int l = 0; l < T; ++l) {
+                float2 v[PW];
+#pragma unroll
+                for (int pw = 0; pw < PW; ++pw) v[pw] = row[xo[pw] + l];
+#pragma unroll
+                for (int pw = 0; pw < PW; ++pw) row[xo[pw] + l] = __ffma2_rn(bcast2(wx[pw][l]), r[pw], v[pw]);
             }
-            float *row = tile_c + y * W;
-            if (XINC) {
-                // window starts strictly increase: the 7 taps of one l hit 7 distinct columns,
-                // so they can be loaded, updated and stored as a group
+        } else {
+#pragma unroll
+            for (int pw = 0; pw < PW; ++pw)
 #pragma unroll
                 for (int l = 0; l < T; ++l) {
-                    float v[PW];
-#pragma unroll
-                    for (int pw = 0; pw < PW; ++pw) v[pw] = row[xo[pw] + l];
-#pragma unroll
-                    for (int pw = 0; pw < PW; ++pw) row[xo[pw] + l] = fmaf(wx[pw][l], r[pw], v[pw]);
+                    volatile float2 *q = row + xo[pw] + l;
+                    float2 v;
+                    v.x = q->x; v.y = q->y;
+                    v = __ffma2_rn(bcast2(wx[pw][l]), r[pw], v);
+                    q->x = v.x; q->y = v.y;
                 }
-            } else {
-#pragma unroll
-                for (int pw = 0; pw < PW; ++pw)
-#pragma unroll
-                    for (int l = 0; l < T; ++l) {
-                        volatile float *p = row + xo[pw] + l;
-                        *p = fmaf(wx[pw][l], r[pw], *p);
-                    }
-            }
         }
     }
 }
@@ -457,7 +537,7 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
                           float *__restrict__ grad_feat, int B, int C, int H, int W, int pitch) {
     extern __shared__ __align__(128) float smem[];
     float *tile = smem;
-    float *ring = smem + (size_t)CH * pitch;                 // [NS][NBR x 1568 grads | NBR x 160 desc words]
+    float *ring = smem + (size_t)CH * pitch;                 // [NS][NBR x 1568 grads | NBR x DESC_WORDS]
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)NS * SLOT_FLOATS);
     uint64_t *empty = full + NS;
     if (__ldg(hdr) != 0) return;              // rois not grouped by image: the generic kernel does it all
@@ -544,28 +624,37 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
             mbar_wait(&full[s], (gb / NS) & 1);
             const float *slot = ring + (size_t)s * SLOT_FLOATS;
             const int cnt = min(NBR, n - bi * NBR);
-            for (int j = 0; j < cnt; ++j) {
-                const int *d = reinterpret_cast<const int *>(slot + NBR * STAGE_FLOATS) + j * DESC_WORDS;
-                if (((d[D_OWN] >> warp) & 1) == 0 || d[D_FLAGX] != 0) continue;   // not my rows / generic-path ROI
+            // which of the slot's ROIs touch a row pair of this warp (lane j looks at ROI j)
+            const int *dbase = reinterpret_cast<const int *>(slot + NBR * STAGE_FLOATS);
+            bool mine = false;
+            if (lane < cnt) {
+                const int2 ff = *reinterpret_cast<const int2 *>(dbase + lane * DESC_WORDS + D_XINC);   // (xinc, own)
+                mine = ((ff.y >> warp) & 1) != 0 && dbase[lane * DESC_WORDS + D_FLAGX] == 0;
+            }
+            unsigned todo = __ballot_sync(0xffffffffu, mine);
+            while (todo) {
+                const int j = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int *d = dbase + j * DESC_WORDS;
                 const int2 yr = *reinterpret_cast<const int2 *>(d + D_Y0);
                 const int y0 = yr.x, y1 = yr.y;
                 const float *g = slot + j * STAGE_FLOATS + lane * NBIN;
                 const int T = d[D_TX];
                 if (d[D_XINC]) {
                     switch (T) {
-                        case 2: bwd_rows<2, true>(tile_c, W, d, g, warp, y0, y1); break;
-                        case 3: bwd_rows<3, true>(tile_c, W, d, g, warp, y0, y1); break;
-                        case 4: bwd_rows<4, true>(tile_c, W, d, g, warp, y0, y1); break;
-                        case 6: bwd_rows<6, true>(tile_c, W, d, g, warp, y0, y1); break;
-                        default: bwd_rows<8, true>(tile_c, W, d, g, warp, y0, y1); break;
+                        case 2: bwd_pairs<2, true>(tile_c, W, d, g, warp, y0, y1); break;
+                        case 3: bwd_pairs<3, true>(tile_c, W, d, g, warp, y0, y1); break;
+                        case 4: bwd_pairs<4, true>(tile_c, W, d, g, warp, y0, y1); break;
+                        case 6: bwd_pairs<6, true>(tile_c, W, d, g, warp, y0, y1); break;
+                        default: bwd_pairs<8, true>(tile_c, W, d, g, warp, y0, y1); break;
                     }
                 } else {
                     switch (T) {
-                        case 2: bwd_rows<2, false>(tile_c, W, d, g, warp, y0, y1); break;
-                        case 3: bwd_rows<3, false>(tile_c, W, d, g, warp, y0, y1); break;
-                        case 4: bwd_rows<4, false>(tile_c, W, d, g, warp, y0, y1); break;
-                        case 6: bwd_rows<6, false>(tile_c, W, d, g, warp, y0, y1); break;
-                        default: bwd_rows<8, false>(tile_c, W, d, g, warp, y0, y1); break;
+                        case 2: bwd_pairs<2, false>(tile_c, W, d, g, warp, y0, y1); break;
+                        case 3: bwd_pairs<3, false>(tile_c, W, d, g, warp, y0, y1); break;
+                        case 4: bwd_pairs<4, false>(tile_c, W, d, g, warp, y0, y1); break;
+                        case 6: bwd_pairs<6, false>(tile_c, W, d, g, warp, y0, y1); break;
+                        default: bwd_pairs<8, false>(tile_c, W, d, g, warp, y0, y1); break;
                     }
                 }
             }
@@ -576,16 +665,16 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
 
         // tile -> grad_feat (+=): the slab is zero or holds the other CTA's partial sum
         float *dst = grad_feat + ((size_t)b * C + c0) * HW;
-        if ((HW & 3) == 0) {
+        if ((W & 3) == 0) {
             for (int e = tid * 4; e < CH * HW; e += NWB * 32 * 4) {
-                const int c = e / HW, p = e - c * HW;
-                const float *t = tile + c * pitch + p;
-                red_add4(dst + e, t[0], t[1], t[2], t[3]);
+                const int c = e / HW, rem = e - c * HW, y = rem / W, x = rem - y * W;
+                const float *t = tile + c * pitch + tile_off(y, x, W);
+                red_add4(dst + e, t[0], t[2], t[4], t[6]);
             }
         } else {
             for (int e = tid; e < CH * HW; e += NWB * 32) {
-                const int c = e / HW, p = e - c * HW;
-                atomicAdd(dst + e, tile[c * pitch + p]);
+                const int c = e / HW, rem = e - c * HW, y = rem / W, x = rem - y * W;
+                atomicAdd(dst + e, tile[c * pitch + tile_off(y, x, W)]);
             }
         }
         __syncthreads();
@@ -675,19 +764,20 @@ __global__ void roi_align_generic_kernel(const float *__restrict__ in, const flo
 // ------------------------------------------------------------------------------------- host
 struct Plan {
     bool tile;
-    int pitch, fwd_warps;
+    int pitch, fwd_warps, wyd_floats;
     size_t smem_fwd, smem_bwd;
 };
 static Plan make_plan(int C, int H, int W, int oh, int ow) {
     Plan p{};
-    const int HW = H * W;
-    p.pitch = (HW & 1) ? HW : HW + 1;
+    const int Hp = (H + 1) & ~1, words = Hp * W;       // rows padded to whole pairs
+    p.pitch = ((words >> 1) & 1) ? words : words + 2;  // pitch / 2 odd: conflict-free 64-bit accesses, lane = channel
+    p.wyd_floats = (Hp / 2) * 16;                      // dense y-weight table of one warp (forward)
     const size_t cap = (size_t)cim_max_smem_optin();
-    // forward: as many warps (12 ... 4) as fit next to the tile: per warp one output stage and two
-    // descriptor slots
-    const size_t per_warp = (size_t)STAGE_FLOATS * 4 + 2 * DESC_WORDS * 4;
-    p.fwd_warps = 12;
-    while (p.fwd_warps > 4 && (size_t)CH * p.pitch * 4 + p.fwd_warps * per_warp > cap) p.fwd_warps -= 2;
+    // forward: as many warps (11 ... 4) as fit next to the tile: per warp one output stage, two
+    // descriptor slots and the y-weight table
+    const size_t per_warp = (size_t)STAGE_FLOATS * 4 + 2 * DESC_WORDS * 4 + (size_t)p.wyd_floats * 4;
+    p.fwd_warps = FWD_MAX_WARPS;
+    while (p.fwd_warps > 4 && (size_t)CH * p.pitch * 4 + p.fwd_warps * per_warp > cap) --p.fwd_warps;
     p.smem_fwd = (size_t)CH * p.pitch * 4 + p.fwd_warps * per_warp;
     p.smem_bwd = (size_t)CH * p.pitch * 4 + (size_t)NS * SLOT_FLOATS * 4 + 2 * NS * 8;
     p.tile = oh == PH && ow == PW && (C % CH) == 0 && W >= MAXT && p.smem_fwd <= cap &&
@@ -754,7 +844,7 @@ CIM_API int cim_roi_align_fwd(const float *feat, const float *rois, float *out, 
     const long long units = (long long)(C / CH) * K;
     const int grid = (int)min((long long)cim_num_sms(), units);
     roi_align_fwd_tile_kernel<<<grid, p.fwd_warps * 32, p.smem_fwd, st>>>(feat, w.hdr, w.img_start, w.desc, out, B,
-                                                                           C, H, W, p.pitch);
+                                                                           C, H, W, p.pitch, p.wyd_floats);
     if ((rc = cim_launch_status())) return rc;
     // leftover pass: one CTA per ROI, which exits at once unless the tile kernel skipped that ROI
     roi_align_generic_kernel<false><<<dim3((unsigned)K, 1), 256, 0, st>>>(feat, rois, out, w.hdr, w.desc, 1, B, C, H,

@@ -1,0 +1,78 @@
+"""RoIAlign fwd / bwd micro-benchmark at the cfg2 shape (8 images x 2000 proposals, R-50 features),
+through the C ABI.  Prints device times (CUDA events, median of N) and the algorithmic HBM rate.
+Optional check against torchvision's CUDA roi_align on a subset (tool only; tests use the oracle).
+
+    python tools/roi_bench.py [--images 8] [--props 2000] [--backbone resnet50] [--iters 20] [--check]
+"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from cim_b200 import _lib, synth  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--images", type=int, default=8)
+    ap.add_argument("--props", type=int, default=2000)
+    ap.add_argument("--backbone", default="resnet50")
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--check", action="store_true")
+    a = ap.parse_args()
+    dev = torch.device("cuda:0")
+    Cf, H, W, scale = synth.feature_shape(a.backbone)
+    B, R = a.images, a.props
+    rois = torch.cat([synth.rois_from_params(synth.proposal_params(R, 512, 1234 + b), b) for b in range(B)]).to(dev)
+    g = torch.Generator(device=dev).manual_seed(1)
+    feat = torch.randn(B, Cf, H, W, device=dev, generator=g)
+    K = rois.size(0)
+    out = torch.empty(K, Cf, 7, 7, device=dev)
+    gout = torch.randn(K, Cf, 7, 7, device=dev, generator=g)
+    gfeat = torch.empty_like(feat)
+    L = _lib.lib()
+    ws = torch.empty(L.cim_roi_align_workspace_bytes(K), dtype=torch.uint8, device=dev)
+    st = _lib.stream_ptr(dev)
+
+    def fwd():
+        _lib.check(L.cim_roi_align_fwd(_lib.ptr(feat), _lib.ptr(rois), _lib.ptr(out), B, Cf, H, W, K, 7, 7, scale, 0, 1,
+                                       _lib.ptr(ws), ws.numel(), st), "fwd")
+
+    def bwd():
+        _lib.check(L.cim_roi_align_bwd(_lib.ptr(gout), _lib.ptr(rois), _lib.ptr(gfeat), B, Cf, H, W, K, 7, 7, scale, 0,
+                                       1, _lib.ptr(ws), ws.numel(), st), "bwd")
+
+    def timeit(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(a.iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    mb = (K * Cf * 49 * 4 + B * Cf * H * W * 4 + 20 * K) / 1e6
+    tf, tb = timeit(fwd), timeit(bwd)
+    print(f"roi_align fwd {tf:.3f} ms  {mb / tf:.1f} GB/s   bwd {tb:.3f} ms  {mb / tb:.1f} GB/s   ({mb:.0f} MB each)")
+
+    if a.check:
+        from torchvision.ops import roi_align as tv
+        sel = torch.arange(0, K, 7, device=dev)
+        want = tv(feat, rois[sel], 7, scale, 0, True)
+        err = (out[sel] - want).abs().max().item() / want.abs().max().item()
+        f2 = feat.clone().requires_grad_(True)
+        tv(f2, rois, 7, scale, 0, True).backward(gout)
+        errb = (gfeat - f2.grad).abs().max().item() / f2.grad.abs().max().item()
+        print(f"vs torchvision CUDA: fwd rel err {err:.2e}   bwd rel err {errb:.2e}")
+
+
+if __name__ == "__main__":
+    main()
