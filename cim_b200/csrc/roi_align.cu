@@ -31,6 +31,8 @@
 //      tile kernels cannot: other output sizes, feature maps too large for shared memory,
 //      bins wider than 8 taps, ROIs not grouped by image.
 #include "common.cuh"
+#include <algorithm>
+#include <cstdlib>
 
 namespace {
 
@@ -198,6 +200,7 @@ __global__ void roi_prep_kernel(const float *__restrict__ rois, int K, int B, in
                 float v = (!flag && src >= 0 && src < MAXT) ? w_[p][src] : 0.f;
                 reinterpret_cast<float *>(d)[D_WX + p * MAXT + i] = v;
             }
+
             if (lo2 <= prev) inc = 0;
             prev = lo2;
         }
@@ -345,6 +348,7 @@ __device__ __forceinline__ void build_wyd(float *wyd, const int *__restrict__ d,
 }
 
 constexpr int FWD_MAX_WARPS = 11;
+constexpr int FWD_DESC_WORDS = DESC_WORDS;
 
 __global__ void __launch_bounds__(FWD_MAX_WARPS * 32, 1)
 roi_align_fwd_tile_kernel(const float *__restrict__ feat, const int *__restrict__ hdr,
@@ -354,8 +358,8 @@ roi_align_fwd_tile_kernel(const float *__restrict__ feat, const int *__restrict_
     const int nw = blockDim.x >> 5;
     float *tile = smem;
     float *stage = smem + (size_t)CH * pitch;                                    // [nw][1568]
-    int *dslots = reinterpret_cast<int *>(stage + (size_t)nw * STAGE_FLOATS);   // [nw][2][DESC_WORDS]
-    float *wyds = reinterpret_cast<float *>(dslots + (size_t)nw * 2 * DESC_WORDS);   // [nw][wyd_floats]
+    int *dslots = reinterpret_cast<int *>(stage + (size_t)nw * STAGE_FLOATS);   // [nw][2][FWD_DESC_WORDS]
+    float *wyds = reinterpret_cast<float *>(dslots + (size_t)nw * 2 * FWD_DESC_WORDS);   // [nw][wyd_floats]
     if (__ldg(hdr) != 0) return;              // rois not grouped by image: generic kernel runs
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -367,15 +371,15 @@ roi_align_fwd_tile_kernel(const float *__restrict__ feat, const int *__restrict_
     const long long u_end = U * (blockIdx.x + 1) / gridDim.x;
     float *stage_w = stage + warp * STAGE_FLOATS;
     float *stage_c = stage_w + lane * NBIN;
-    int *my_slots = dslots + warp * 2 * DESC_WORDS;
+    int *my_slots = dslots + warp * 2 * FWD_DESC_WORDS;
     float *my_wyd = wyds + (size_t)warp * wyd_floats;
 
     // descriptor prefetch: 672 B = 42 x 16 B per ROI, lanes 0..31 + lanes 0..9 again
     auto prefetch = [&](int roi, int slot) {
         const int *src = descs + (size_t)roi * DESC_WORDS;
-        int *dst = my_slots + slot * DESC_WORDS;
+        int *dst = my_slots + slot * FWD_DESC_WORDS;
         cp_async16(dst + lane * 4, src + lane * 4);
-        if (lane < DESC_WORDS / 4 - 32) cp_async16(dst + (32 + lane) * 4, src + (32 + lane) * 4);
+        if (lane < FWD_DESC_WORDS / 4 - 32) cp_async16(dst + (32 + lane) * 4, src + (32 + lane) * 4);
         cp_async_commit();
     };
 
@@ -401,7 +405,7 @@ roi_align_fwd_tile_kernel(const float *__restrict__ feat, const int *__restrict_
             const int rn = r + nw;
             if (rn < r1) { prefetch(is + rn, slot ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
             __syncwarp();
-            const int *d = my_slots + slot * DESC_WORDS;
+            const int *d = my_slots + slot * FWD_DESC_WORDS;
             const int roi = is + r;
             if ((d[D_FLAGY] | d[D_FLAGX]) == 0) {
                 build_wyd(my_wyd, d, lane);
@@ -492,16 +496,17 @@ __device__ __forceinline__ void bwd_pairs(float *__restrict__ tile_c, int W, con
                 for (int pw = 0; pw < PW; ++pw) row[xo[pw] + l] = __ffma2_rn(bcast2(wx[pw][l]), r[pw], v[pw]);
             }
         } else {
+            // windows may coincide (tiny ROIs): bins strictly in program order; the T taps of one bin
+            // are distinct columns
 #pragma unroll
-            for (int pw = 0; pw < PW; ++pw)
+            for (int pw = 0; pw < PW; ++pw) {
+                float2 v[T];
 #pragma unroll
-                for (int l = 0; l < T; ++l) {
-                    volatile float2 *q = row + xo[pw] + l;
-                    float2 v;
-                    v.x = q->x; v.y = q->y;
-                    v = __ffma2_rn(bcast2(wx[pw][l]), r[pw], v);
-                    q->x = v.x; q->y = v.y;
-                }
+                for (int l = 0; l < T; ++l) v[l] = row[xo[pw] + l];
+#pragma unroll
+                for (int l = 0; l < T; ++l) row[xo[pw] + l] = __ffma2_rn(bcast2(wx[pw][l]), r[pw], v[l]);
+                asm volatile("" ::: "memory");          // the next bin may alias these columns
+            }
         }
     }
 }
@@ -775,7 +780,7 @@ static Plan make_plan(int C, int H, int W, int oh, int ow) {
     const size_t cap = (size_t)cim_max_smem_optin();
     // forward: as many warps (11 ... 4) as fit next to the tile: per warp one output stage, two
     // descriptor slots and the y-weight table
-    const size_t per_warp = (size_t)STAGE_FLOATS * 4 + 2 * DESC_WORDS * 4 + (size_t)p.wyd_floats * 4;
+    const size_t per_warp = (size_t)STAGE_FLOATS * 4 + 2 * FWD_DESC_WORDS * 4 + (size_t)p.wyd_floats * 4;
     p.fwd_warps = FWD_MAX_WARPS;
     while (p.fwd_warps > 4 && (size_t)CH * p.pitch * 4 + p.fwd_warps * per_warp > cap) --p.fwd_warps;
     p.smem_fwd = (size_t)CH * p.pitch * 4 + p.fwd_warps * per_warp;
@@ -875,12 +880,12 @@ CIM_API int cim_roi_align_bwd(const float *grad_out, const float *rois, float *g
         return cim_launch_status();
     }
     if ((rc = run_prep(rois, B, H, W, K, oh, ow, scale, sr, aligned, w, st))) return rc;
-    cudaFuncSetAttribute(roi_align_bwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bwd);
     cudaMemsetAsync(grad_feat, 0, sizeof(float) * (size_t)B * C * H * W, st);
     const long long units = (long long)(C / CH) * K;
     const int grid = (int)min((long long)cim_num_sms(), units);
-    roi_align_bwd_tile_kernel<<<grid, NWB * 32, p.smem_bwd, st>>>(grad_out, w.hdr, w.img_start, w.desc, grad_feat, B,
-                                                                   C, H, W, p.pitch);
+    cudaFuncSetAttribute(roi_align_bwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bwd);
+    roi_align_bwd_tile_kernel<<<grid, NWB * 32, p.smem_bwd, st>>>(grad_out, w.hdr, w.img_start, w.desc, grad_feat,
+                                                                   B, C, H, W, p.pitch);
     if ((rc = cim_launch_status())) return rc;
     roi_align_generic_kernel<true><<<dim3((unsigned)K, 1), 256, 0, st>>>(grad_out, rois, grad_feat, w.hdr, w.desc, 1,
                                                                          B, C, H, W, K, oh, ow, scale, sr, aligned);
