@@ -177,51 +177,36 @@ def build_inputs(cfg, dev, seed_base):
     feat = torch.randn(n_img, Cf, H, W, device=dev, generator=gen)
     grad_out = torch.randn(n_img * R, Cf, 7, 7, device=dev, generator=gen)
     seg_x = torch.randn(n_img * R, 4096, device=dev, generator=gen)
-    rois, packed, labels = [], [], []
+    rois, packed, packed_flat, labels = [], [], [], []
+    kb_per_row = cfg["mask"] // 16 if mask_ops.tiled_ok(cfg["mask"], cfg["mask"]) else 0
     for b in range(n_img):
         params = synth.proposal_params(R, 512, seed_base + b)
         rois.append(synth.rois_from_params(params, b))
-        packed.append(mask_ops.mask_pack(synth.rasterize(params, device=dev, out_size=cfg["mask"])))
+        m = synth.rasterize(params, device=dev, out_size=cfg["mask"])
+        packed.append(mask_ops.mask_pack(m))                         # tiled 8 x 16 patches when the size allows
+        packed_flat.append(mask_ops.mask_pack(m, layout="flat").cpu())   # only to derive the host wire format
         labels.append(synth.image_labels(C, cfg["present"], seed_base + b))
     torch.manual_seed(0)
     model = heads.cls_iou_model(4096, C + 1, 3).to(dev)
     weight, bias = (t.detach().contiguous() for t in model._stacked())
     labels = torch.cat(labels)
     return dict(feat=feat, rois=torch.cat(rois).to(dev), grad_out=grad_out, packed=torch.stack(packed),
+                packed_flat=torch.stack(packed_flat), kb_per_row=kb_per_row,
                 seg_x=seg_x, weight=weight, bias=bias, labels=labels.to(dev), labels_host=labels.numpy(),
                 shape=(Cf, H, W, scale))
 
 
-def visited_kblocks(packed):
-    """Number of 128-pixel K-blocks the tensor-core overlap kernel visits (and the dense total): same
-    rule as mask_sort_kernel / mask_overlap_tc_kernel -- masks sorted by the centre of their non-zero
-    word range, 128 x 256 tiles on or right of the diagonal, K-range = intersection of the two blocks'
-    union ranges.  Evaluated with torch, outside any timed region."""
+def visited_kblocks(step, cfg):
+    """Number of 128-pixel K-blocks the tensor-core overlap kernel visited in its last launch (it leaves the
+    count in the first 8 bytes of its workspace, include/cimhead.h) and the dense total: 128 x 256 tiles on or
+    right of the diagonal x all K-blocks."""
     import torch
-    n_img, n, words = packed.shape
-    visited = total = 0
-    idx = torch.arange(words, device=packed.device)
-    for b in range(n_img):
-        nz = packed[b] != 0
-        any_ = nz.any(1)
-        lo = torch.where(nz, idx, words).min(1).values
-        hi = torch.where(nz, idx + 1, 0).max(1).values
-        lo = torch.where(any_, lo, 0)
-        order = torch.argsort(lo + hi, stable=True)
-        lo, hi, any_ = lo[order].cpu(), hi[order].cpu(), any_[order].cpu()
-
-        def blocks(size):
-            out = []
-            for s in range(0, n, size):
-                m = any_[s:s + size]
-                out.append((int(lo[s:s + size][m].min()) // 4, (int(hi[s:s + size][m].max()) + 3) // 4) if m.any() else (0, 0))
-            return out
-        ra, rb = blocks(128), blocks(256)
-        for i, (alo, ahi) in enumerate(ra):
-            for j in range(i // 2, len(rb)):
-                visited += max(0, min(ahi, rb[j][1], words // 4) - max(alo, rb[j][0]))
-                total += words // 4
-    return visited, total
+    torch.cuda.synchronize()
+    visited = int(step.overlap_ws[:8].view(torch.int64).item())
+    n, kblocks = cfg["R"], step.words // 4
+    nrb, ncb = (n + 127) // 128, (n + 255) // 256
+    tiles = sum(ncb - (i >> 1) for i in range(nrb))
+    return visited, tiles * cfg["n_img"] * kblocks
 
 
 def time_stages(step, inp, iters=5):
@@ -239,9 +224,9 @@ def time_stages(step, inp, iters=5):
         "roi_align_bwd": lambda: L.cim_roi_align_bwd(P(inp["grad_out"]), P(inp["rois"]), P(step.grad_feat), n_img,
                                                      step.Cf, step.H, step.W, n_img * R, 7, 7, step.scale, 0, 1,
                                                      P(step.roi_ws), step.roi_ws.numel(), st),
-        "mask_overlap": lambda: L.cim_mask_overlap(P(inp["packed"]), n_img, R, step.words, None, P(step.area),
-                                                   P(step.iou), P(step.asy), P(step.overlap_ws),
-                                                   step.overlap_ws.numel(), st),
+        "mask_overlap": lambda: L.cim_mask_overlap_ex(P(inp["packed"]), n_img, R, step.words, step.kb_per_row, None,
+                                                      P(step.area), P(step.iou), P(step.asy), P(step.overlap_ws),
+                                                      step.overlap_ws.numel(), 0, st),
         "score_heads": lambda: L.cim_score_heads(P(inp["seg_x"]), P(inp["weight"]), P(inp["bias"]), P(step.scores),
                                                  n_img, R, step.D, step.C + 1, step.K, P(step.score_ws),
                                                  step.score_ws.numel(), st),
@@ -314,7 +299,7 @@ def main():
     Cf, H, W, scale = inp["shape"]
     words = inp["packed"].shape[-1]
     step = CIMHeadStep(cfg["n_img"], cfg["R"], cfg["C"], Cf, H, W, scale, words, anti_noise_sampling=not args.no_anti_noise,
-                       max_present=max(4, 2 * cfg["present"]), device=dev)
+                       max_present=max(4, 2 * cfg["present"]), device=dev, mask_kb_per_row=inp["kb_per_row"])
     run = lambda: step.run(inp["feat"], inp["rois"], inp["grad_out"], inp["packed"], inp["seg_x"], inp["weight"],
                            inp["bias"], inp["labels"], inp["labels_host"])
     np.random.seed(3)
@@ -342,7 +327,8 @@ def main():
     # results read back to the host every step
     # host wire format of the proposal masks: bounding-box crops, bit-packed (mask_ops.MaskCrops)
     from cim_b200 import mask_ops
-    crops = mask_ops.crops_from_packed_host(inp["packed"].view(cfg["n_img"] * cfg["R"], -1), cfg["mask"], cfg["mask"])
+    crops = mask_ops.crops_from_packed_host(inp.pop("packed_flat").view(cfg["n_img"] * cfg["R"], -1), cfg["mask"],
+                                            cfg["mask"])
     step.alloc_host_io(mask_hw=(cfg["mask"], cfg["mask"]), crop_capacity_words=int(crops.words.numel() * 1.25) + 1024)
     step.hi_rois.copy_(inp["rois"])
     step.hi_labels.copy_(inp["labels"])
@@ -387,7 +373,7 @@ def main():
         # rate is given next to it.  Peak: int8 runs at twice the bf16 rate on sm_100;
         # MEASURED_PEAKS.json only has bf16, so peak = 2 x measured bf16 (burst: kernel timed alone).
         alg = float(cfg["R"]) ** 2 * cfg["mask"] ** 2 * cfg["n_img"]
-        visited, total = visited_kblocks(inp["packed"])
+        visited, total = visited_kblocks(step, cfg)
         executed = visited * 2.0 * 128 * 256 * 128
         secs = stage_ms[dominant] * 1e-3
         roofline.update({"bound": "tensor", "achieved": round(executed / secs / 1e12, 1),

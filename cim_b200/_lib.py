@@ -12,7 +12,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcimhead.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_LAYERS = 4
 OVERLAP_ALGOS = {"auto": 0, "popc": 1, "tensor": 2}
 
@@ -41,9 +41,12 @@ _SIGNATURES = {
     "cim_roi_pool_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "cim_mask_pack": (_I, [_P, _P, _I64, _I64, _I64, _P]),
     "cim_mask_unpack_crops": (_I, [_P, _P, _P, _P, _I64, _I, _I, _I64, _P]),
+    "cim_mask_pack_tiled": (_I, [_P, _P, _I64, _I, _I, _I64, _P]),
+    "cim_mask_unpack_crops_tiled": (_I, [_P, _P, _P, _P, _I64, _I, _I, _I64, _P]),
     "cim_mask_overlap_workspace_bytes": (_SZ, [_I, _I, _I64, _I]),
     "cim_mask_overlap": (_I, [_P, _I, _I, _I64, _P, _P, _P, _P, _P, _SZ, _P]),
     "cim_mask_overlap_algo": (_I, [_P, _I, _I, _I64, _P, _P, _P, _P, _P, _SZ, _I, _P]),
+    "cim_mask_overlap_ex": (_I, [_P, _I, _I, _I64, _I, _P, _P, _P, _P, _P, _SZ, _I, _P]),
     "cim_score_heads_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I]),
     "cim_score_heads": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _SZ, _P]),
     "cim_sizeof_mine_params": (_SZ, []),

@@ -25,9 +25,10 @@
 
 // mask_overlap_tc.cu: the tcgen05 (tensor core) path for large problems
 bool cim_mask_overlap_tc_eligible(int n, long long words);
-int cim_mask_overlap_tc_launch(const uint32_t *packed, const int32_t *area, const int32_t *perm, const int2 *range_a,
-                               const int2 *range_b, int n_img, int n, long long words, int32_t *inter, __half *iou,
-                               __half *asy, cudaStream_t st);
+int cim_mask_overlap_tc_launch(const uint32_t *packed, const int32_t *area, const int32_t *perm,
+                               const uint32_t *umap_a, const uint32_t *umap_b, int bw, unsigned long long *visited,
+                               const int32_t *tile_order, int n_img, int n, long long words, int32_t *inter,
+                               __half *iou, __half *asy, cudaStream_t st);
 
 namespace {
 
@@ -59,6 +60,63 @@ __global__ void mask_pack_kernel(const uint8_t *__restrict__ masks, uint32_t *__
                 if (p0 + i < hw && src[i] != 0) bits |= 1u << i;
         }
         packed[idx] = bits;
+    }
+}
+
+// Tiled layout ("8 x 16"): pixel (y, x) of an H x W mask (H % 8 == 0, W % 16 == 0) sits at flat position
+//   q = ((y >> 3) * (W >> 4) + (x >> 4)) * 128 + (y & 7) * 16 + (x & 15),   bit q & 31 of word q >> 5,
+// so 4 consecutive words (one 128-pixel K-block of the tensor-core overlap kernel) are one 8 x 16 pixel
+// patch.  Counts and overlaps do not depend on the pixel order; the patch order makes the set of K-blocks a
+// mask touches follow its 2-D footprint, which lets the overlap kernel skip far more of them.
+__device__ __forceinline__ uint32_t bits16_of(const uint4 a) {
+    return nibble_of(a.x) | (nibble_of(a.y) << 4) | (nibble_of(a.z) << 8) | (nibble_of(a.w) << 12);
+}
+__global__ void mask_pack_tiled_kernel(const uint8_t *__restrict__ masks, uint32_t *__restrict__ packed,
+                                       long long n_masks, int H, int W, long long words) {
+    const long long total = n_masks * words;
+    const long long used = (long long)H * W / 32;
+    const int bpr = W >> 4;
+    const bool vec = (((uintptr_t)masks) % 16) == 0;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long m = idx / words, w = idx - m * words;
+        uint32_t bits = 0;
+        if (w < used) {
+            const int blk = (int)(w >> 2), wi = (int)(w & 3), by = blk / bpr, bx = blk - by * bpr;
+            const uint8_t *src = masks + m * (long long)H * W + (long long)(8 * by + 2 * wi) * W + 16 * bx;
+            if (vec) {
+                bits = bits16_of(__ldg(reinterpret_cast<const uint4 *>(src))) |
+                       (bits16_of(__ldg(reinterpret_cast<const uint4 *>(src + W))) << 16);
+            } else {
+                for (int i = 0; i < 16; ++i) {
+                    if (src[i] != 0) bits |= 1u << i;
+                    if (src[W + i] != 0) bits |= 1u << (16 + i);
+                }
+            }
+        }
+        packed[idx] = bits;
+    }
+}
+
+// crop word (row y, pixels 32 X .. 32 X + 31) -> two 16-pixel halves = one half-word each in the tiled layout
+__global__ void mask_unpack_crops_tiled_kernel(const uint32_t *__restrict__ crop_words, const int32_t *__restrict__ meta,
+                                               const long long *__restrict__ off, uint32_t *__restrict__ packed,
+                                               int H, int W, long long words) {
+    const long long m = blockIdx.x;
+    const int wx0 = meta[4 * m], y0 = meta[4 * m + 1], ww = meta[4 * m + 2], h = meta[4 * m + 3];
+    const uint32_t *src = crop_words + off[m];
+    unsigned short *dst = reinterpret_cast<unsigned short *>(packed + m * words);
+    const int bpr = W >> 4;
+    for (int e = threadIdx.x; e < ww * h; e += blockDim.x) {
+        const int r = e / ww, k = e - r * ww;
+        const int y = y0 + r, x = 32 * (wx0 + k);
+        if (y < 0 || y >= H || x < 0 || x >= W) continue;
+        const uint32_t w = __ldg(src + e);
+        if (w == 0u) continue;
+        const long long blk = (long long)(y >> 3) * bpr + (x >> 4);
+        const int hw = ((y & 7) >> 1) * 2 + (y & 1);                 // half-word inside the block
+        if (w & 0xffffu) dst[blk * 8 + hw] = (unsigned short)(w & 0xffffu);
+        if ((w >> 16) && x + 16 < W) dst[(blk + 1) * 8 + hw] = (unsigned short)(w >> 16);
     }
 }
 
@@ -95,49 +153,90 @@ __global__ void mask_unpack_crops_kernel(const uint32_t *__restrict__ crop_words
 }
 
 // ---------------------------------------------------------------------------------------- area
-// per mask (one warp): popcount and the range [lo, hi) of words that hold any set bit
+// per mask (one warp): popcount; for the tensor path also the occupancy bitmap over K-blocks of 4 words
+// (bit kb & 31 of kbmap word kb >> 5) and the sort key inputs: kinfo = (any, a, b) with
+//   kb_per_row == 0 (flat pixel order):  a = first + last occupied K-block, b = 0
+//   kb_per_row  > 0 (tiled layout)    :  a = min + max block column, b = min + max block row
 __global__ void mask_area_kernel(const uint32_t *__restrict__ packed, int32_t *__restrict__ area,
-                                 int2 *__restrict__ krange, long long n_masks, long long words) {
+                                 uint32_t *__restrict__ kbmap, int4 *__restrict__ kinfo, long long n_masks,
+                                 long long words, int bw, int kb_per_row) {
     const long long m = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
     if (m >= n_masks) return;
     const int lane = threadIdx.x & 31;
     const uint32_t *row = packed + m * words;
-    int s = 0, lo = 0x7fffffff, hi = 0;
-    for (long long w = lane; w < words; w += 32) {
-        const uint32_t v = __ldg(row + w);
-        s += __popc(v);
-        if (v) { lo = min(lo, (int)w); hi = max(hi, (int)w + 1); }
+    int s = 0;
+    if (!kbmap) {                                    // popcount only (popc path)
+        for (long long w = lane; w < words; w += 32) s += __popc(__ldg(row + w));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) area[m] = s;
+        return;
+    }
+    // tensor path: words % 4 == 0 and 16-byte aligned rows; a lane takes one K-block (4 words) per round, so
+    // the ballot of "non-zero" IS the bitmap word of the round
+    int alo = 0x7fffffff, ahi = -1, blo = 0x7fffffff, bhi = -1;
+    const int nkb = (int)(words >> 2);
+    const uint4 *row4 = reinterpret_cast<const uint4 *>(row);
+    for (int j = 0; j < bw; ++j) {
+        const int kb = j * 32 + lane;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (kb < nkb) v = __ldg(row4 + kb);
+        s += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+        const bool nz = (v.x | v.y | v.z | v.w) != 0u;
+        const uint32_t bm = __ballot_sync(0xffffffffu, nz);
+        if (lane == 0) kbmap[m * bw + j] = bm;
+        if (nz) {
+            if (kb_per_row > 0) {
+                const int by = kb / kb_per_row, bx = kb - by * kb_per_row;
+                alo = min(alo, bx); ahi = max(ahi, bx); blo = min(blo, by); bhi = max(bhi, by);
+            } else {
+                alo = min(alo, kb); ahi = max(ahi, kb);
+            }
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         s += __shfl_xor_sync(0xffffffffu, s, o);
-        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        alo = min(alo, __shfl_xor_sync(0xffffffffu, alo, o));
+        ahi = max(ahi, __shfl_xor_sync(0xffffffffu, ahi, o));
+        blo = min(blo, __shfl_xor_sync(0xffffffffu, blo, o));
+        bhi = max(bhi, __shfl_xor_sync(0xffffffffu, bhi, o));
     }
     if (lane == 0) {
         area[m] = s;
-        if (krange) krange[m] = hi ? make_int2(lo, hi) : make_int2(0, 0);
+        kinfo[m] = ahi >= 0 ? make_int4(1, alo + ahi, bhi >= 0 ? blo + bhi : 0, 0) : make_int4(0, 0, 0, 0);
     }
 }
 
-// ------------------------------------------------------------------------- locality sort + ranges
-// One CTA per image.  Masks are sorted by the centre of their non-zero word range (= vertical
-// position, pixels are row-major), so the 128 / 256 masks of a tile block share a narrow range.
-// perm[k] = original index of the k-th mask in sorted order, inv = inverse.  For every block of
-// 128 (A operand) and 256 (B operand) sorted masks the union range is stored in K-blocks of 4 words;
-// a tile only has to visit the intersection of its two ranges: everywhere else one operand is all
-// zero.  (tools/ estimate: 0.36-0.43 of the K-blocks on the synthetic proposals.)
+// ------------------------------------------------------------------------- locality sort + unions
+// One CTA per image.  Masks are sorted by position so that the 128 / 256 masks of a tile block cover a small
+// part of the image: flat pixel order -> by the centre of the occupied K-block range (= vertical position);
+// tiled layout -> three vertical stripes by block-column centre, inside a stripe by block-row centre
+// (alternating direction, so neighbours in the order stay neighbours in the image).
+// perm[k] = original index of the k-th mask in sorted order, inv = inverse.  For every block of 128 (A
+// operand) and 256 (B operand) sorted masks the union of the masks' K-block bitmaps is stored; a tile only
+// has to visit the K-blocks set in BOTH unions: everywhere else one operand is all zero.
 __global__ void __launch_bounds__(1024)
-mask_sort_kernel(const int2 *__restrict__ krange_all, int n, int npad, int32_t *__restrict__ perm_all,
-                 int32_t *__restrict__ inv_all, int2 *__restrict__ range_a, int2 *__restrict__ range_b, int nrb,
-                 int ncb) {
+mask_sort_kernel(const int4 *__restrict__ kinfo_all, const uint32_t *__restrict__ kbmap_all, int n, int npad, int bw,
+                 int kb_per_row, int nkb, int32_t *__restrict__ perm_all, int32_t *__restrict__ inv_all,
+                 uint32_t *__restrict__ umap_a, uint32_t *__restrict__ umap_b, int nrb, int ncb) {
     extern __shared__ __align__(16) unsigned char sort_smem[];
     int *key = reinterpret_cast<int *>(sort_smem);        // [npad]
     int *idx = key + npad;                                // [npad]
     const int img = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
-    const int2 *kr = krange_all + (size_t)img * n;
+    const int4 *ki = kinfo_all + (size_t)img * n;
+    const int nby = kb_per_row > 0 ? (nkb + kb_per_row - 1) / kb_per_row : 0;
     for (int i = tid; i < npad; i += nthr) {
-        key[i] = i < n ? kr[i].x + kr[i].y : 0x7fffffff;
+        int k = 0x7fffffff;
+        if (i < n) {
+            const int4 v = ki[i];
+            if (!v.x) k = 0;                               // empty masks first
+            else if (kb_per_row > 0) {
+                const int st = min(2, (v.y * 3) / (2 * kb_per_row));
+                k = (st << 24) | ((st & 1) ? (2 * nby - v.z) : v.z);
+            } else k = v.y;
+        }
+        key[i] = k;
         idx[i] = i < n ? i : 0x7fffffff;
     }
     __syncthreads();
@@ -154,18 +253,89 @@ mask_sort_kernel(const int2 *__restrict__ krange_all, int n, int npad, int32_t *
         }
     int32_t *perm = perm_all + (size_t)img * n, *inv = inv_all + (size_t)img * n;
     for (int i = tid; i < n; i += nthr) { perm[i] = idx[i]; inv[idx[i]] = i; }
-    // block ranges (in K-blocks of 4 words); empty masks (hi == 0) do not count
-    for (int blk = tid; blk < nrb + ncb; blk += nthr) {
+    // union bitmaps: one (block, bitmap word) per thread
+    const uint32_t *kbm = kbmap_all + (size_t)img * n * bw;
+    for (int e = tid; e < (nrb + ncb) * bw; e += nthr) {
+        const int blk = e / bw, j = e - blk * bw;
         const bool is_a = blk < nrb;
         const int bs = is_a ? 128 : 256, b0 = (is_a ? blk : blk - nrb) * bs;
-        int lo = 0x7fffffff, hi = 0;
-        for (int i = b0; i < min(n, b0 + bs); ++i) {
-            const int2 r = kr[idx[i]];
-            if (r.y) { lo = min(lo, r.x); hi = max(hi, r.y); }
+        uint32_t u = 0;
+        for (int i = b0; i < min(n, b0 + bs); ++i) u |= kbm[(size_t)idx[i] * bw + j];
+        if (is_a) umap_a[((size_t)img * nrb + blk) * bw + j] = u;
+        else umap_b[((size_t)img * ncb + (blk - nrb)) * bw + j] = u;
+    }
+}
+
+// Longest tile first: the tiles of all images sorted by the number of K-blocks they visit (descending), so
+// that the 1-CTA-per-SM waves of the tensor kernel end together.  tile code = img << 16 | ti << 8 | tj.
+__global__ void __launch_bounds__(1024)
+mask_tile_order_kernel(const uint32_t *__restrict__ umap_a, const uint32_t *__restrict__ umap_b, int bw, int n_img,
+                       int nrb, int ncb, int ntiles, int npad, int32_t *__restrict__ order) {
+    extern __shared__ __align__(16) unsigned char sort_smem[];
+    int *key = reinterpret_cast<int *>(sort_smem);        // [npad] visited K-blocks (negated: ascending sort)
+    int *val = key + npad;                                // [npad] tile code
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    int per_img = 0;
+    for (int i = 0; i < nrb; ++i) per_img += ncb - (i >> 1);
+    for (int t = tid; t < npad; t += nthr) {
+        int k = 0x7fffffff, code = -1;
+        if (t < ntiles) {
+            const int img = t / per_img;
+            int rem = t - img * per_img, ti = 0;
+            while (rem >= ncb - (ti >> 1)) { rem -= ncb - (ti >> 1); ++ti; }
+            const int tj = (ti >> 1) + rem;
+            const uint32_t *ua = umap_a + ((size_t)img * nrb + ti) * bw, *ub = umap_b + ((size_t)img * ncb + tj) * bw;
+            int c = 0;
+            for (int j = 0; j < bw; ++j) c += __popc(ua[j] & ub[j]);
+            k = -c;
+            code = (img << 16) | (ti << 8) | tj;
         }
-        const int2 out = hi ? make_int2(lo >> 2, (hi + 3) >> 2) : make_int2(0, 0);
-        if (is_a) range_a[(size_t)img * nrb + blk] = out;
-        else range_b[(size_t)img * ncb + (blk - nrb)] = out;
+        key[t] = k;
+        val[t] = code;
+    }
+    __syncthreads();
+    for (int size = 2; size <= npad; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = tid; t < (npad >> 1); t += nthr) {
+                const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                const bool asc = (lo & size) == 0;
+                const int ka = key[lo], kb = key[hi], ia = val[lo], ib = val[hi];
+                const bool a_first = ka < kb || (ka == kb && ia < ib);
+                if (asc ? !a_first : a_first) { key[lo] = kb; key[hi] = ka; val[lo] = ib; val[hi] = ia; }
+            }
+            __syncthreads();
+        }
+    for (int t = tid; t < ntiles; t += nthr) order[t] = val[t];
+}
+
+// out[i][j] = tmp[inv[i]][inv[j]] for both fp16 maps: one CTA per output row, the source rows go through smem
+__global__ void __launch_bounds__(256)
+mask_unpermute2_kernel(const __half *__restrict__ tmp_a, const __half *__restrict__ tmp_b,
+                       const int32_t *__restrict__ inv_all, __half *__restrict__ out_a, __half *__restrict__ out_b,
+                       int n) {
+    extern __shared__ __align__(16) unsigned char unp_smem[];
+    __half *ra = reinterpret_cast<__half *>(unp_smem), *rb = ra + n;
+    const int i = blockIdx.x, img = blockIdx.y;
+    const int32_t *inv = inv_all + (size_t)img * n;
+    const size_t so = ((size_t)img * n + inv[i]) * n, d_o = ((size_t)img * n + i) * n;
+    if ((n & 7) == 0) {
+        const uint4 *sa = reinterpret_cast<const uint4 *>(tmp_a + so), *sb = reinterpret_cast<const uint4 *>(tmp_b + so);
+        for (int j = threadIdx.x; j < n / 8; j += blockDim.x) {
+            reinterpret_cast<uint4 *>(ra)[j] = __ldg(sa + j);
+            reinterpret_cast<uint4 *>(rb)[j] = __ldg(sb + j);
+        }
+    } else {
+        for (int j = threadIdx.x; j < n; j += blockDim.x) { ra[j] = tmp_a[so + j]; rb[j] = tmp_b[so + j]; }
+    }
+    __syncthreads();
+    if ((n & 1) == 0) {
+        for (int j = threadIdx.x; j < n / 2; j += blockDim.x) {
+            const int c0 = inv[2 * j], c1 = inv[2 * j + 1];
+            reinterpret_cast<__half2 *>(out_a + d_o)[j] = __halves2half2(ra[c0], ra[c1]);
+            reinterpret_cast<__half2 *>(out_b + d_o)[j] = __halves2half2(rb[c0], rb[c1]);
+        }
+    } else {
+        for (int j = threadIdx.x; j < n; j += blockDim.x) { out_a[d_o + j] = ra[inv[j]]; out_b[d_o + j] = rb[inv[j]]; }
     }
 }
 
@@ -277,6 +447,33 @@ CIM_API int cim_mask_pack(const uint8_t *masks, uint32_t *packed, int64_t n_mask
     return cim_launch_status();
 }
 
+CIM_API int cim_mask_pack_tiled(const uint8_t *masks, uint32_t *packed, int64_t n_masks, int H, int W, int64_t words,
+                                cim_stream_t stream) {
+    if (!masks || !packed || n_masks < 0 || H <= 0 || W <= 0 || words * 32 < (int64_t)H * W) return CIM_ERR_ARG;
+    if ((H & 7) || (W & 15)) return CIM_ERR_SHAPE;
+    if (n_masks == 0) return CIM_OK;
+    const long long total = n_masks * words;
+    const int blocks = (int)min((long long)cim_num_sms() * 16, (total + 255) / 256);
+    mask_pack_tiled_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(masks, packed, n_masks, H, W, words);
+    return cim_launch_status();
+}
+
+CIM_API int cim_mask_unpack_crops_tiled(const uint32_t *crop_words, const int32_t *crop_meta, const int64_t *crop_off,
+                                        uint32_t *packed, int64_t n_masks, int H, int W, int64_t words,
+                                        cim_stream_t stream) {
+    if (!crop_words || !crop_meta || !crop_off || !packed || n_masks < 0 || H <= 0 || W <= 0) return CIM_ERR_ARG;
+    if (words * 32 < (int64_t)H * W) return CIM_ERR_ARG;
+    if ((H & 7) || (W & 15)) return CIM_ERR_SHAPE;
+    if (n_masks == 0) return CIM_OK;
+    if (n_masks > 0x7fffffffLL) return CIM_ERR_SHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(packed, 0, sizeof(uint32_t) * (size_t)n_masks * words, st);
+    mask_unpack_crops_tiled_kernel<<<(unsigned)n_masks, 128, 0, st>>>(crop_words, crop_meta,
+                                                                      reinterpret_cast<const long long *>(crop_off),
+                                                                      packed, H, W, words);
+    return cim_launch_status();
+}
+
 CIM_API int cim_mask_unpack_crops(const uint32_t *crop_words, const int32_t *crop_meta, const int64_t *crop_off,
                                   uint32_t *packed, int64_t n_masks, int H, int W, int64_t words,
                                   cim_stream_t stream) {
@@ -294,26 +491,34 @@ CIM_API int cim_mask_unpack_crops(const uint32_t *crop_words, const int32_t *cro
 
 namespace {
 struct OverlapWs {
+    unsigned long long *visited;      // word 0 of the workspace: K-blocks visited by the tensor path (diagnostic)
     int32_t *area;
-    int2 *krange, *range_a, *range_b;
-    int32_t *perm, *inv, *tmp_inter;
+    int4 *kinfo;
+    uint32_t *kbmap, *umap_a, *umap_b;
+    int32_t *perm, *inv, *tmp_inter, *tile_order;
     __half *tmp_iou, *tmp_asy;
+    int bw;
     size_t bytes;
 };
 inline size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
-OverlapWs carve_overlap_ws(void *base, int n_img, int n, int want_inter) {
+OverlapWs carve_overlap_ws(void *base, int n_img, int n, long long words, int want_inter) {
     OverlapWs w{};
     const size_t nm = (size_t)(n_img > 0 ? n_img : 0) * (size_t)(n > 0 ? n : 0), nn = nm * (size_t)(n > 0 ? n : 0);
     const size_t nrb = (size_t)n_img * ((n + 127) / 128), ncb = (size_t)n_img * ((n + 255) / 256);
+    const long long nkb = (words + 3) / 4;
+    w.bw = (int)((nkb + 31) / 32);
     char *p = (char *)base;
     size_t o = 0;
     auto take = [&](size_t bytes) { char *q = p ? p + o : nullptr; o += up256(bytes); return q; };
+    w.visited = (unsigned long long *)take(8);
     w.area = (int32_t *)take(nm * 4);
-    w.krange = (int2 *)take(nm * 8);
+    w.kinfo = (int4 *)take(nm * 16);
+    w.kbmap = (uint32_t *)take(nm * w.bw * 4);
     w.perm = (int32_t *)take(nm * 4);
     w.inv = (int32_t *)take(nm * 4);
-    w.range_a = (int2 *)take(nrb * 8);
-    w.range_b = (int2 *)take(ncb * 8);
+    w.umap_a = (uint32_t *)take(nrb * w.bw * 4);
+    w.umap_b = (uint32_t *)take(ncb * w.bw * 4);
+    w.tile_order = (int32_t *)take(nrb * ((size_t)(n + 255) / 256) * 4);
     w.tmp_iou = (__half *)take(nn * 2);
     w.tmp_asy = (__half *)take(nn * 2);
     w.tmp_inter = want_inter ? (int32_t *)take(nn * 4) : nullptr;
@@ -323,22 +528,28 @@ OverlapWs carve_overlap_ws(void *base, int n_img, int n, int want_inter) {
 }  // namespace
 
 CIM_API size_t cim_mask_overlap_workspace_bytes(int n_img, int n, int64_t words, int want_inter) {
-    (void)words;
-    return carve_overlap_ws(nullptr, n_img, n, want_inter).bytes;
+    return carve_overlap_ws(nullptr, n_img, n, words, want_inter).bytes;
 }
 
 CIM_API int cim_mask_overlap(const uint32_t *packed, int n_img, int n, int64_t words, int32_t *inter,
                              int32_t *area, void *iou_f16, void *asy_f16, void *workspace, size_t ws_bytes,
                              cim_stream_t stream) {
-    return cim_mask_overlap_algo(packed, n_img, n, words, inter, area, iou_f16, asy_f16, workspace, ws_bytes,
-                                 CIM_OVERLAP_AUTO, stream);
+    return cim_mask_overlap_ex(packed, n_img, n, words, 0, inter, area, iou_f16, asy_f16, workspace, ws_bytes,
+                               CIM_OVERLAP_AUTO, stream);
 }
 
 CIM_API int cim_mask_overlap_algo(const uint32_t *packed, int n_img, int n, int64_t words, int32_t *inter,
                                   int32_t *area, void *iou_f16, void *asy_f16, void *workspace, size_t ws_bytes,
                                   int algo, cim_stream_t stream) {
+    return cim_mask_overlap_ex(packed, n_img, n, words, 0, inter, area, iou_f16, asy_f16, workspace, ws_bytes, algo,
+                               stream);
+}
+
+CIM_API int cim_mask_overlap_ex(const uint32_t *packed, int n_img, int n, int64_t words, int kb_per_row,
+                                int32_t *inter, int32_t *area, void *iou_f16, void *asy_f16, void *workspace,
+                                size_t ws_bytes, int algo, cim_stream_t stream) {
     if (algo != CIM_OVERLAP_AUTO && algo != CIM_OVERLAP_POPC && algo != CIM_OVERLAP_TENSOR) return CIM_ERR_ARG;
-    if (!packed || !iou_f16 || !asy_f16 || n_img < 0 || n < 0 || words <= 0) return CIM_ERR_ARG;
+    if (!packed || !iou_f16 || !asy_f16 || n_img < 0 || n < 0 || words <= 0 || kb_per_row < 0) return CIM_ERR_ARG;
     if (words * 32 >= (1LL << 24)) return CIM_ERR_SHAPE;      // counts must stay exact in fp32
     if (n_img == 0 || n == 0) return CIM_OK;
     if (n_img > 65535 || n > 16384) return CIM_ERR_SHAPE;
@@ -348,13 +559,14 @@ CIM_API int cim_mask_overlap_algo(const uint32_t *packed, int n_img, int n, int6
     // the tensor path pays off once a 128 x 256 tile is reasonably full and K is long
     const bool use_tc = algo == CIM_OVERLAP_TENSOR || (algo == CIM_OVERLAP_AUTO && tc_ok && n >= 256 && words >= 128);
     const size_t need = use_tc ? cim_mask_overlap_workspace_bytes(n_img, n, words, inter != nullptr)
-                               : (area ? 0 : up256(sizeof(int32_t) * (size_t)n_img * n) + 256);
+                               : (area ? 0 : 2 * up256(sizeof(int32_t) * (size_t)n_img * n) + 512);
     if (need && (!workspace || ws_bytes < need || !cim_aligned(workspace, 256))) return CIM_ERR_WORKSPACE;
-    const OverlapWs w = carve_overlap_ws(workspace, n_img, n, inter != nullptr);
+    const OverlapWs w = carve_overlap_ws(workspace, n_img, n, words, inter != nullptr);
     if (!area) area = w.area;
     const long long n_masks = (long long)n_img * n;
-    mask_area_kernel<<<(unsigned)((n_masks + 7) / 8), 256, 0, st>>>(packed, area, use_tc ? w.krange : nullptr, n_masks,
-                                                                    words);
+    mask_area_kernel<<<(unsigned)((n_masks + 7) / 8), 256, 0, st>>>(packed, area, use_tc ? w.kbmap : nullptr,
+                                                                    use_tc ? w.kinfo : nullptr, n_masks, words, w.bw,
+                                                                    kb_per_row);
     int rc = cim_launch_status();
     if (rc) return rc;
     __half *iou = reinterpret_cast<__half *>(iou_f16), *asy = reinterpret_cast<__half *>(asy_f16);
@@ -364,16 +576,33 @@ CIM_API int cim_mask_overlap_algo(const uint32_t *packed, int n_img, int n, int6
         const int nrb = (n + 127) / 128, ncb = (n + 255) / 256;
         const size_t smem_sort = (size_t)npad * 8;
         cudaFuncSetAttribute(mask_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sort);
-        mask_sort_kernel<<<n_img, 1024, smem_sort, st>>>(w.krange, n, npad, w.perm, w.inv, w.range_a, w.range_b, nrb,
-                                                         ncb);
+        mask_sort_kernel<<<n_img, 1024, smem_sort, st>>>(w.kinfo, w.kbmap, n, npad, w.bw, kb_per_row,
+                                                         (int)((words + 3) / 4), w.perm, w.inv, w.umap_a, w.umap_b,
+                                                         nrb, ncb);
         if ((rc = cim_launch_status())) return rc;
+        cudaMemsetAsync(w.visited, 0, 8, st);
+        int per_img = 0;
+        for (int i = 0; i < nrb; ++i) per_img += ncb - (i >> 1);
+        const long long ntiles = (long long)per_img * n_img;
+        const int32_t *order = nullptr;
+        if (ntiles <= 8192 && n_img < 32768 && nrb < 256 && ncb < 256) {     // else: the kernel's built-in order
+            int tpad = 1;
+            while (tpad < ntiles) tpad <<= 1;
+            if ((size_t)tpad * 8 > 48 * 1024)
+                cudaFuncSetAttribute(mask_tile_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tpad * 8);
+            mask_tile_order_kernel<<<1, 1024, (size_t)tpad * 8, st>>>(w.umap_a, w.umap_b, w.bw, n_img, nrb, ncb,
+                                                                      (int)ntiles, tpad, w.tile_order);
+            if ((rc = cim_launch_status())) return rc;
+            order = w.tile_order;
+        }
         // the tensor kernel works in sorted index space and writes sorted-order maps
-        rc = cim_mask_overlap_tc_launch(packed, area, w.perm, w.range_a, w.range_b, n_img, n, words, w.tmp_inter,
-                                        w.tmp_iou, w.tmp_asy, st);
+        rc = cim_mask_overlap_tc_launch(packed, area, w.perm, w.umap_a, w.umap_b, w.bw, w.visited, order, n_img, n,
+                                        words, w.tmp_inter, w.tmp_iou, w.tmp_asy, st);
         if (rc) return rc;
         dim3 g((unsigned)n, (unsigned)n_img);
-        mask_unpermute_kernel<__half><<<g, 256, (size_t)n * 2, st>>>(w.tmp_iou, w.inv, iou, n);
-        mask_unpermute_kernel<__half><<<g, 256, (size_t)n * 2, st>>>(w.tmp_asy, w.inv, asy, n);
+        if ((size_t)n * 4 > 48 * 1024)
+            cudaFuncSetAttribute(mask_unpermute2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, n * 4);
+        mask_unpermute2_kernel<<<g, 256, (size_t)n * 4, st>>>(w.tmp_iou, w.tmp_asy, w.inv, iou, asy, n);
         if (inter) {
             cudaFuncSetAttribute(mask_unpermute_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, n * 4);
             mask_unpermute_kernel<int32_t><<<g, 256, (size_t)n * 4, st>>>(w.tmp_inter, w.inv, inter, n);

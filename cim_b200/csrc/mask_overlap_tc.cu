@@ -26,7 +26,9 @@
 //                       contiguous global stores: tile rows (direct block) and tile columns (mirror
 //                       block; asy is not symmetric, so the mirror carries inter / area_row).
 // Tiles work in SORTED index space (mask_sort_kernel) and visit only the K-blocks where both operand
-// blocks are non-zero; the caller un-permutes the maps afterwards.
+// blocks are non-zero (AND of the blocks' union bitmaps; with the tiled 8 x 16 pixel layout of
+// cim_mask_pack_tiled a K-block is an image patch, so this follows the 2-D footprint of the masks);
+// the caller un-permutes the maps afterwards.
 // History of this kernel, with the ncu evidence, is in DESIGN.md section 4.3.
 #include "common.cuh"
 #include <cstdlib>
@@ -46,6 +48,7 @@ constexpr int B_BYTES = TN * KB;        // 32 KB of expanded B operand per stage
 constexpr int NEXP = 16;                // expander warps: 0-3 A even, 4-7 A odd, 8-11 B even, 12-15 B odd K-blocks
 constexpr int MMA_WARP = NEXP, LOAD_WARP = NEXP + 1;
 constexpr int THREADS = (NEXP + 2) * 32;
+constexpr int KMAP_WORDS = 512;         // smem copy of a tile's K-block bitmap (16384 K-blocks = 2 Mpixel masks)
 constexpr size_t SI_BYTES = (size_t)(TM + TN) * 4 + 3 * (size_t)TM * 130 * 2;   // epilogue staging (aliases the rings)
 
 template <int STAGES_>
@@ -53,7 +56,7 @@ struct Cfg {
     static constexpr int STAGES = STAGES_;
     static constexpr size_t RING_BYTES = (size_t)STAGES * B_BYTES + (size_t)NBUF * BUF_BYTES;
     static constexpr size_t BODY_BYTES = SI_BYTES > RING_BYTES ? SI_BYTES : RING_BYTES;
-    static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + BODY_BYTES + 256;
+    static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + BODY_BYTES + 256 + KMAP_WORDS * 4;
     static_assert(STAGES % 2 == 0, "the two expander groups own alternate stages");
     static_assert(TN + STAGES * A_COLS <= TMEM_COLS, "TMEM budget");
 };
@@ -147,9 +150,10 @@ __device__ __forceinline__ __half2 pack_ratio2(int i0, int d0, int i1, int d1) {
 template <class K>
 __global__ void __launch_bounds__(THREADS, 1)
 mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__restrict__ area_all,
-                       const int32_t *__restrict__ perm_all, const int2 *__restrict__ range_a,
-                       const int2 *__restrict__ range_b, int n, long long words, int n_img,
-                       int32_t *__restrict__ inter_all, __half *__restrict__ iou_all, __half *__restrict__ asy_all) {
+                       const int32_t *__restrict__ perm_all, const uint32_t *__restrict__ umap_a,
+                       const uint32_t *__restrict__ umap_b, int bw, unsigned long long *__restrict__ visited,
+                       const int32_t *__restrict__ tile_order, int n, long long words, int n_img, int32_t *__restrict__ inter_all, __half *__restrict__ iou_all,
+                       __half *__restrict__ asy_all) {
     constexpr int STAGES = K::STAGES;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -161,21 +165,28 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
     uint64_t *loaded = accum_full + 1;             // [NBUF] staging buffer filled (32 loader lanes)
     uint64_t *consumed = loaded + NBUF;            // [NBUF] staging buffer read by every expander warp
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(consumed + NBUF);
+    uint32_t *kmap = tmem_slot + 2;                // [KMAP_WORDS] AND of the two union bitmaps (loader)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // tile id -> (d, img, ti), tj = ti / 2 + d: tiles are ordered by their distance d from the diagonal,
     // over all images.  After the locality sort the K-range of a tile shrinks with d, so the longest
     // tiles start first and the short ones fill the tail (tiles_per_img is unused by this order).
     const int ncb = (n + TN - 1) / TN, nrb = (n + TM - 1) / TM;
-    int d = 0, rem = blockIdx.x;
-    for (;;) {
-        const int cnt = min(nrb, 2 * (ncb - d)) * n_img;      // row blocks ti with ti / 2 + d < ncb
-        if (rem < cnt) break;
-        rem -= cnt;
-        ++d;
+    int img, ti, tj;
+    if (tile_order) {                        // longest tile first (mask_tile_order_kernel)
+        const int code = __ldg(tile_order + blockIdx.x);
+        img = code >> 16; ti = (code >> 8) & 255; tj = code & 255;
+    } else {
+        int d = 0, rem = blockIdx.x;
+        for (;;) {
+            const int cnt = min(nrb, 2 * (ncb - d)) * n_img;      // row blocks ti with ti / 2 + d < ncb
+            if (rem < cnt) break;
+            rem -= cnt;
+            ++d;
+        }
+        const int per_img = min(nrb, 2 * (ncb - d));
+        img = rem / per_img; ti = rem - img * per_img; tj = (ti >> 1) + d;
     }
-    const int per_img = min(nrb, 2 * (ncb - d));
-    const int img = rem / per_img, ti = rem - img * per_img, tj = (ti >> 1) + d;
     const int row0 = ti * TM, col0 = tj * TN;
 
     if (tid == 0) {
@@ -195,13 +206,21 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // All indices below are SORTED positions (mask_sort_kernel); perm maps them to the stored masks.
-    // K-range of this tile: the K-blocks where both operand blocks have a non-zero row.
+    // K-blocks of this tile: those where BOTH operand blocks have a non-zero row (AND of the two union
+    // bitmaps).  Every warp counts them; only the loader needs their indices.
     const int32_t *perm = perm_all + (size_t)img * n;
-    const int nrb_img = nrb;
-    const int2 ra_ = range_a[(size_t)img * nrb_img + ti], rb_ = range_b[(size_t)img * ncb + tj];
-    const int kb_lo = max(ra_.x, rb_.x);
-    const int nkb = max(0, min(min(ra_.y, rb_.y), (int)(words / 4)) - kb_lo);   // K-blocks this tile visits
+    const uint32_t *ua = umap_a + ((size_t)img * nrb + ti) * bw, *ub = umap_b + ((size_t)img * ncb + tj) * bw;
+    int nkb = 0;
+    for (int j = lane; j < bw; j += 32) {
+        const uint32_t mj = __ldg(ua + j) & __ldg(ub + j);
+        nkb += __popc(mj);
+        if (warp == LOAD_WARP && j < KMAP_WORDS) kmap[j] = mj;      // the loader's private copy
+    }
+    __syncwarp();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nkb += __shfl_xor_sync(0xffffffffu, nkb, o);
     const int ngroups = (nkb + GK - 1) / GK;
+    if (tid == 0 && visited) atomicAdd(visited, (unsigned long long)nkb);
 
     if (warp < NEXP) {
         // ------------------------------------------------------------------ expanders
@@ -268,10 +287,22 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
         // writes and the expanders' LDS.128 reads conflict-free.  Rows past n and K-blocks past the
         // end are zero-filled (src-size 0).
         const uint32_t *img_base = packed + (size_t)img * n * words;
+        int bj = -1;                       // bitmap word being scanned and its bits not yet taken
+        uint32_t bm = 0;
         for (int g = 0; g < ngroups; ++g) {
             const int buf = g % NBUF;
             if (g >= NBUF) mbar_wait(&consumed[buf], ((g / NBUF) - 1) & 1);
             unsigned char *dst = staging + (size_t)buf * BUF_BYTES;
+            int kbs[GK];                   // the next GK visited K-blocks (warp-uniform)
+#pragma unroll
+            for (int kk = 0; kk < GK; ++kk) {
+                kbs[kk] = 0;
+                if (g * GK + kk < nkb) {
+                    while (bm == 0u) { ++bj; bm = bj < KMAP_WORDS ? kmap[bj] : (__ldg(ua + bj) & __ldg(ub + bj)); }
+                    kbs[kk] = 32 * bj + __ffs(bm) - 1;
+                    bm &= bm - 1;
+                }
+            }
 #pragma unroll 4
             for (int t = lane; t < ROWS; t += 32) {
                 const int grow = t < TM ? row0 + t : col0 + (t - TM);
@@ -284,7 +315,7 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
                     const uint32_t nbytes = ok ? 16u : 0u;
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
                                      smem_u32(dst + (kk * ROWS + t) * 16)),
-                                 "l"(rsrc + (ok ? (kb_lo + kb) * 4 : 0)), "r"(nbytes)
+                                 "l"(rsrc + (ok ? kbs[kk] * 4 : 0)), "r"(nbytes)
                                  : "memory");
                 }
             }
@@ -416,15 +447,15 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
 using CfgDefault = Cfg<4>;
 
 template <class K>
-static int launch(const uint32_t *packed, const int32_t *area, const int32_t *perm, const int2 *range_a,
-                  const int2 *range_b, int n_img, int n, long long words, int32_t *inter, __half *iou, __half *asy,
-                  cudaStream_t st) {
+static int launch(const uint32_t *packed, const int32_t *area, const int32_t *perm, const uint32_t *umap_a,
+                  const uint32_t *umap_b, int bw, unsigned long long *visited, const int32_t *tile_order, int n_img,
+                  int n, long long words, int32_t *inter, __half *iou, __half *asy, cudaStream_t st) {
     const int nrb = (n + TM - 1) / TM, ncb = (n + TN - 1) / TN;
     int tiles = 0;
     for (int i = 0; i < nrb; ++i) tiles += ncb - (i >> 1);
     cudaFuncSetAttribute(mask_overlap_tc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES);
     mask_overlap_tc_kernel<K><<<(unsigned)(tiles * n_img), THREADS, K::SMEM_BYTES, st>>>(
-        packed, area, perm, range_a, range_b, n, words, n_img, inter, iou, asy);
+        packed, area, perm, umap_a, umap_b, bw, visited, tile_order, n, words, n_img, inter, iou, asy);
     return cim_launch_status();
 }
 
@@ -435,13 +466,14 @@ bool cim_mask_overlap_tc_eligible(int n, long long words) {
     return n >= 64 && words >= 4 && (words % 4) == 0 && (size_t)cim_max_smem_optin() >= CfgDefault::SMEM_BYTES;
 }
 
-int cim_mask_overlap_tc_launch(const uint32_t *packed, const int32_t *area, const int32_t *perm, const int2 *range_a,
-                               const int2 *range_b, int n_img, int n, long long words, int32_t *inter, __half *iou,
-                               __half *asy, cudaStream_t st) {
+int cim_mask_overlap_tc_launch(const uint32_t *packed, const int32_t *area, const int32_t *perm,
+                               const uint32_t *umap_a, const uint32_t *umap_b, int bw, unsigned long long *visited,
+                               const int32_t *tile_order, int n_img, int n, long long words, int32_t *inter,
+                               __half *iou, __half *asy, cudaStream_t st) {
     // CIM_OVERLAP_VARIANT is a tuning aid (pipeline-depth experiments); unset = the default
     const char *v = getenv("CIM_OVERLAP_VARIANT");
     switch (v ? atoi(v) : 0) {
-        case 1: return launch<Cfg<2>>(packed, area, perm, range_a, range_b, n_img, n, words, inter, iou, asy, st);
-        default: return launch<CfgDefault>(packed, area, perm, range_a, range_b, n_img, n, words, inter, iou, asy, st);
+        case 1: return launch<Cfg<2>>(packed, area, perm, umap_a, umap_b, bw, visited, tile_order, n_img, n, words, inter, iou, asy, st);
+        default: return launch<CfgDefault>(packed, area, perm, umap_a, umap_b, bw, visited, tile_order, n_img, n, words, inter, iou, asy, st);
     }
 }

@@ -88,8 +88,19 @@ def crops_from_packed_host(packed, height, width):
                      height, width)
 
 
-def unpack_crops(crops, out=None):
-    """MaskCrops on the device -> full bit masks [N, ceil(H*W/32)] int32 (the input of mask_overlap)."""
+def tiled_ok(height, width):
+    """The 8 x 16 patch pixel order (cim_mask_pack_tiled) needs whole patches."""
+    return height % 8 == 0 and width % 16 == 0
+
+
+def _tag(packed, kb_per_row):
+    packed.cim_kb_per_row = kb_per_row      # read back by mask_overlap (plain attribute, lost on views / copies)
+    return packed
+
+
+def unpack_crops(crops, out=None, layout="auto"):
+    """MaskCrops on the device -> full bit masks [N, ceil(H*W/32)] int32 (the input of mask_overlap).
+    layout: "flat" (row-major pixels), "tiled" (8 x 16 patches) or "auto" (tiled whenever H % 8 == W % 16 == 0)."""
     _lib.require_cuda(crops.words, "crops.words", torch.int32)
     _lib.require_cuda(crops.meta, "crops.meta", torch.int32)
     _lib.require_cuda(crops.off, "crops.off", torch.int64)
@@ -98,16 +109,29 @@ def unpack_crops(crops, out=None):
     dev = crops.words.device
     if out is None:
         out = torch.empty((n, words), dtype=torch.int32, device=dev)
+    tiled = _want_tiled(layout, crops.height, crops.width)
+    L = _lib.lib()
+    fn = L.cim_mask_unpack_crops_tiled if tiled else L.cim_mask_unpack_crops
     with torch.cuda.device(dev):
-        rc = _lib.lib().cim_mask_unpack_crops(_lib.ptr(crops.words), _lib.ptr(crops.meta.contiguous()),
-                                              _lib.ptr(crops.off.contiguous()), _lib.ptr(out), n, crops.height,
-                                              crops.width, words, _lib.stream_ptr(dev))
+        rc = fn(_lib.ptr(crops.words), _lib.ptr(crops.meta.contiguous()), _lib.ptr(crops.off.contiguous()),
+                _lib.ptr(out), n, crops.height, crops.width, words, _lib.stream_ptr(dev))
     _lib.check(rc, "cim_mask_unpack_crops")
-    return out
+    return _tag(out, crops.width // 16 if tiled else 0)
 
 
-def mask_pack(masks):
-    """uint8/bool masks [..., H, W] (non-zero = inside) -> bit masks [..., ceil(H*W/32)] int32."""
+def _want_tiled(layout, height, width):
+    if layout not in ("auto", "flat", "tiled"):
+        raise ValueError("layout must be 'auto', 'flat' or 'tiled'")
+    if layout == "tiled" and not tiled_ok(height, width):
+        raise ValueError("the tiled layout needs H % 8 == 0 and W % 16 == 0")
+    return layout == "tiled" or (layout == "auto" and tiled_ok(height, width))
+
+
+def mask_pack(masks, layout="auto"):
+    """uint8/bool masks [..., H, W] (non-zero = inside) -> bit masks [..., ceil(H*W/32)] int32.
+    layout: "flat" = pixel p = y*W + x is bit p & 31 of word p >> 5; "tiled" = 8 x 16 pixel patches (see
+    include/cimhead.h), which lets the tensor-core overlap kernel skip the empty parts of the image; "auto" =
+    tiled whenever H % 8 == W % 16 == 0.  The overlap maps do not depend on the layout."""
     _lib.require_cuda(masks, "masks")
     if masks.dtype == torch.bool:
         masks = masks.view(torch.uint8)
@@ -123,18 +147,29 @@ def mask_pack(masks):
         n *= s
     words = (hw + 31) // 32
     packed = torch.empty(lead + (words,), dtype=torch.int32, device=masks.device)
+    height, width = masks.shape[-2], masks.shape[-1]
+    tiled = _want_tiled(layout, height, width)
     with torch.cuda.device(masks.device):
-        rc = _lib.lib().cim_mask_pack(_lib.ptr(masks), _lib.ptr(packed), n, hw, words,
-                                      _lib.stream_ptr(masks.device))
+        if tiled:
+            rc = _lib.lib().cim_mask_pack_tiled(_lib.ptr(masks), _lib.ptr(packed), n, height, width, words,
+                                                _lib.stream_ptr(masks.device))
+        else:
+            rc = _lib.lib().cim_mask_pack(_lib.ptr(masks), _lib.ptr(packed), n, hw, words,
+                                          _lib.stream_ptr(masks.device))
     _lib.check(rc, "cim_mask_pack")
-    return packed
+    return _tag(packed, width // 16 if tiled else 0)
 
 
-def mask_overlap(packed, return_counts=False, algo="auto"):
+def mask_overlap(packed, return_counts=False, algo="auto", kb_per_row=None, return_visited=False):
     """Bit masks [N, words] or [n_img, N, words] (int32) -> (iou_map, asy_iou_map) float16
     [.., N, N]; with return_counts also (inter int32 [.., N, N], area int32 [.., N]).
-    algo: "auto" | "popc" (AND + POPC kernel) | "tensor" (tcgen05 int8 kernel)."""
+    algo: "auto" | "popc" (AND + POPC kernel) | "tensor" (tcgen05 int8 kernel).
+    kb_per_row: W // 16 for masks in the tiled pixel order, 0 for flat; None = what mask_pack / unpack_crops
+    recorded on the tensor (0 if nothing was).  It only steers the locality sort of the tensor path.
+    return_visited: also return the number of K-blocks the tensor path visited (int, 0 on the popc path)."""
     _lib.require_cuda(packed, "packed", torch.int32)
+    if kb_per_row is None:
+        kb_per_row = int(getattr(packed, "cim_kb_per_row", 0))
     squeeze = packed.dim() == 2
     if squeeze:
         packed = packed.unsqueeze(0)
@@ -151,12 +186,17 @@ def mask_overlap(packed, return_counts=False, algo="auto"):
     with torch.cuda.device(dev):
         ws = torch.empty(L.cim_mask_overlap_workspace_bytes(n_img, n, words, int(return_counts)), dtype=torch.uint8,
                          device=dev)
-        rc = L.cim_mask_overlap_algo(_lib.ptr(packed), n_img, n, words, _lib.ptr(inter), _lib.ptr(area),
-                                     _lib.ptr(iou), _lib.ptr(asy), _lib.ptr(ws), ws.numel(),
-                                     _lib.OVERLAP_ALGOS[algo], _lib.stream_ptr(dev))
-    _lib.check(rc, "cim_mask_overlap_algo")
+        if return_visited:
+            ws[:8].zero_()
+        rc = L.cim_mask_overlap_ex(_lib.ptr(packed), n_img, n, words, int(kb_per_row), _lib.ptr(inter),
+                                   _lib.ptr(area), _lib.ptr(iou), _lib.ptr(asy), _lib.ptr(ws), ws.numel(),
+                                   _lib.OVERLAP_ALGOS[algo], _lib.stream_ptr(dev))
+    _lib.check(rc, "cim_mask_overlap_ex")
     outs = (iou, asy, inter, area) if return_counts else (iou, asy)
-    return tuple(o.squeeze(0) for o in outs) if squeeze else outs
+    outs = tuple(o.squeeze(0) for o in outs) if squeeze else outs
+    if return_visited:
+        outs = outs + (int(ws[:8].view(torch.int64).item()),)
+    return outs
 
 
 def mask_overlap_maps(masks):

@@ -32,11 +32,14 @@ KERNELS_PER_STEP = 18
 class CIMHeadStep:
     def __init__(self, n_img, n_props, n_classes, feat_channels, feat_h, feat_w, spatial_scale, mask_words,
                  feat_dim=4096, refine_times=3, p_seed=0.1, step_rate=0.1, con_thr=0.85, anti_noise_sampling=True,
-                 max_present=4, device="cuda:0", sampling_ratio=0, aligned=True):
+                 max_present=4, device="cuda:0", sampling_ratio=0, aligned=True, mask_kb_per_row=0):
         self.dev = torch.device(device)
         self.n_img, self.R, self.C, self.K = n_img, n_props, n_classes, refine_times
         self.Cf, self.H, self.W, self.scale = feat_channels, feat_h, feat_w, float(spatial_scale)
         self.words, self.D = mask_words, feat_dim
+        # pixel order of the packed masks given to run(): W // 16 for the tiled 8 x 16 layout
+        # (mask_ops.mask_pack's default whenever H % 8 == W % 16 == 0), 0 for flat row-major
+        self.kb_per_row = int(mask_kb_per_row)
         self.sr, self.aligned = int(sampling_ratio), int(bool(aligned))
         self.anti = anti_noise_sampling
         self.L = _lib.lib()
@@ -100,8 +103,9 @@ class CIMHeadStep:
         P, n_img, R, k = _lib.ptr, self.n_img, self.R, self.K
         st = _lib.stream_ptr(dev)
         ck = _lib.check
-        ck(L.cim_mask_overlap(P(packed_masks), n_img, R, self.words, None, P(self.area), P(self.iou), P(self.asy),
-                              P(self.overlap_ws), self.overlap_ws.numel(), st), "cim_mask_overlap")
+        ck(L.cim_mask_overlap_ex(P(packed_masks), n_img, R, self.words, self.kb_per_row, None, P(self.area),
+                                 P(self.iou), P(self.asy), P(self.overlap_ws), self.overlap_ws.numel(), 0, st),
+           "cim_mask_overlap_ex")
         ck(L.cim_score_heads(P(seg_x), P(weight), P(bias), P(self.scores), n_img, R, self.D, self.C + 1, k,
                              P(self.score_ws), self.score_ws.numel(), st), "cim_score_heads")
         ck(L.cim_mine(C.byref(p), self.cls_ptrs, self.det_ptrs, P(labels), P(self.iou), P(self.asy),
@@ -214,10 +218,10 @@ class CIMHeadStep:
                 buf["crop_words"][:n].copy_(self.hi_crop_words[:n], non_blocking=True)
                 buf["crop_meta"].copy_(self.hi_crop_meta, non_blocking=True)
                 buf["crop_off"].copy_(self.hi_crop_off, non_blocking=True)
-                rc = self.L.cim_mask_unpack_crops(_lib.ptr(buf["crop_words"]), _lib.ptr(buf["crop_meta"]),
-                                                  _lib.ptr(buf["crop_off"]), _lib.ptr(buf["masks"]),
-                                                  self.n_img * self.R, self.mask_hw[0], self.mask_hw[1], self.words,
-                                                  C.c_void_p(self.copy_stream.cuda_stream))
+                unpack = self.L.cim_mask_unpack_crops_tiled if self.kb_per_row else self.L.cim_mask_unpack_crops
+                rc = unpack(_lib.ptr(buf["crop_words"]), _lib.ptr(buf["crop_meta"]), _lib.ptr(buf["crop_off"]),
+                            _lib.ptr(buf["masks"]), self.n_img * self.R, self.mask_hw[0], self.mask_hw[1], self.words,
+                            C.c_void_p(self.copy_stream.cuda_stream))
                 _lib.check(rc, "cim_mask_unpack_crops")
                 self.last_mask_h2d_bytes = n * 4 + self.hi_crop_meta.numel() * 4 + self.hi_crop_off.numel() * 8
             else:

@@ -27,7 +27,7 @@ extern "C" {
 
 typedef struct CUstream_st *cim_stream_t;   /* == cudaStream_t */
 
-#define CIM_ABI_VERSION 1
+#define CIM_ABI_VERSION 2
 
 enum {
     CIM_OK = 0,
@@ -86,9 +86,20 @@ int cim_roi_pool_bwd(const float *grad_out, const int32_t *argmax, const float *
  *   both computed as fp32 round-to-nearest division then fp32->fp16 round-to-nearest.
  *   workspace: cim_mask_overlap_workspace_bytes(n_img, n, words, inter != NULL) bytes, 256-byte
  *   aligned (the tensor-core path sorts the masks by position, works in sorted order and un-permutes
- *   the maps at the end; it needs two temporary maps).  n <= 16384. */
+ *   the maps at the end; it needs two temporary maps).  n <= 16384.  After a tensor-path call the first
+ *   8 bytes of the workspace hold, as uint64, the number of 128-pixel K-blocks the tiles visited
+ *   (diagnostic: executed MMA work = that x 2*128*256*128).
+ * Pixel order.  Counts do not depend on the order of the pixels inside the bit rows, only on all masks of
+ *   a call using the same one.  cim_mask_pack / cim_mask_unpack_crops write the flat row-major order
+ *   (p = y*W + x).  cim_mask_pack_tiled / cim_mask_unpack_crops_tiled (H % 8 == 0, W % 16 == 0, else
+ *   CIM_ERR_SHAPE) write 8 x 16 pixel patches: q = ((y>>3)*(W>>4) + (x>>4))*128 + (y&7)*16 + (x&15);
+ *   the 4 words of a patch are one K-block of the tensor-core kernel, which skips every K-block where one
+ *   of the two operand blocks is empty -- with patches that follows the masks' 2-D footprint.  Pass
+ *   kb_per_row = W/16 to cim_mask_overlap_ex for tiled input (it only steers the locality sort; 0 = flat). */
 int cim_mask_pack(const uint8_t *masks, uint32_t *packed, int64_t n_masks, int64_t hw,
                   int64_t words, cim_stream_t stream);
+int cim_mask_pack_tiled(const uint8_t *masks, uint32_t *packed, int64_t n_masks, int H, int W,
+                        int64_t words, cim_stream_t stream);
 /* cim_mask_unpack_crops: the compact host->device wire format.  Proposal masks are sent as their
  *   bounding-box crops (the reference cuts the same box out of every COB mask,
  *   tools/pre/generate_7_7_voc.py:36-38): crop_meta [n_masks,4] int32 = (wx0, y0, ww, h) -- the crop
@@ -99,6 +110,9 @@ int cim_mask_pack(const uint8_t *masks, uint32_t *packed, int64_t n_masks, int64
 int cim_mask_unpack_crops(const uint32_t *crop_words, const int32_t *crop_meta, const int64_t *crop_off,
                           uint32_t *packed, int64_t n_masks, int H, int W, int64_t words,
                           cim_stream_t stream);
+int cim_mask_unpack_crops_tiled(const uint32_t *crop_words, const int32_t *crop_meta, const int64_t *crop_off,
+                                uint32_t *packed, int64_t n_masks, int H, int W, int64_t words,
+                                cim_stream_t stream);
 size_t cim_mask_overlap_workspace_bytes(int n_img, int n, int64_t words, int want_inter);
 int cim_mask_overlap(const uint32_t *packed, int n_img, int n, int64_t words,
                      int32_t *inter, int32_t *area, void *iou_f16, void *asy_f16,
@@ -111,6 +125,10 @@ enum { CIM_OVERLAP_AUTO = 0, CIM_OVERLAP_POPC = 1, CIM_OVERLAP_TENSOR = 2 };
 int cim_mask_overlap_algo(const uint32_t *packed, int n_img, int n, int64_t words,
                           int32_t *inter, int32_t *area, void *iou_f16, void *asy_f16,
                           void *workspace, size_t workspace_bytes, int algo, cim_stream_t stream);
+/* Same, for input in the tiled pixel order: kb_per_row = W / 16 (K-blocks per row of patches). */
+int cim_mask_overlap_ex(const uint32_t *packed, int n_img, int n, int64_t words, int kb_per_row,
+                        int32_t *inter, int32_t *area, void *iou_f16, void *asy_f16,
+                        void *workspace, size_t workspace_bytes, int algo, cim_stream_t stream);
 
 /* ------------------------------------------------------------------ scoring heads
  * Replace heads.cls_iou_model.forward (lib/modeling/heads.py:194-219): n_heads = 2 + 2*K

@@ -33,13 +33,51 @@ def test_reference_fixture_bit_exact(golden_masks):
     hw = int(golden_masks["hw"])
     masks = np.unpackbits(golden_masks["masks_bits"], axis=1, bitorder="little")[:, :hw]
     t = torch.from_numpy(masks).view(-1, 64, 64)
-    packed = mask_ops.mask_pack(t.to(DEV))
-    # the packed layout is little-endian bit order: identical bytes to the fixture's packbits
+    packed = mask_ops.mask_pack(t.to(DEV), layout="flat")
+    # the flat packed layout is little-endian bit order: identical bytes to the fixture's packbits
     np.testing.assert_array_equal(packed.cpu().numpy().view(np.uint8).reshape(len(masks), -1),
                                   golden_masks["masks_bits"])
-    iou, asy = mask_ops.mask_overlap(packed)
-    assert_f16_bits_equal(u16(iou), golden_masks["iou_u16"])       # includes NaN entries
-    assert_f16_bits_equal(u16(asy), golden_masks["asy_u16"])
+    for lay in ("flat", "tiled"):
+        iou, asy = mask_ops.mask_overlap(mask_ops.mask_pack(t.to(DEV), layout=lay))
+        assert_f16_bits_equal(u16(iou), golden_masks["iou_u16"])       # includes NaN entries
+        assert_f16_bits_equal(u16(asy), golden_masks["asy_u16"])
+
+
+@pytest.mark.parametrize("n,h,w", [(40, 64, 64), (9, 8, 16), (70, 24, 80)])
+def test_tiled_layout_is_the_documented_permutation(n, h, w):
+    """cim_mask_pack_tiled: pixel (y, x) -> q = ((y>>3)*(W>>4) + (x>>4))*128 + (y&7)*16 + (x&15) (cimhead.h)."""
+    masks = (torch.rand(n, h, w, generator=torch.Generator().manual_seed(n)) < 0.5).to(torch.uint8)
+    flat = mask_ops.mask_pack(masks.to(DEV), layout="flat").cpu().numpy()
+    tiled = mask_ops.mask_pack(masks.to(DEV), layout="tiled").cpu().numpy()
+    bits = np.unpackbits(flat.view(np.uint8), axis=1, bitorder="little")[:, :h * w]
+    y, x = np.divmod(np.arange(h * w), w)
+    q = ((y >> 3) * (w >> 4) + (x >> 4)) * 128 + (y & 7) * 16 + (x & 15)
+    want = np.zeros_like(bits)
+    want[:, q] = bits
+    got = np.unpackbits(tiled.view(np.uint8), axis=1, bitorder="little")[:, :h * w]
+    np.testing.assert_array_equal(got, want)
+    with pytest.raises(ValueError):
+        mask_ops.mask_pack(torch.zeros(2, 12, 16, dtype=torch.uint8, device=DEV), layout="tiled")
+
+
+@pytest.mark.parametrize("n,side,n_img", [(300, 64, 2), (700, 128, 1)])
+def test_flat_and_tiled_layouts_give_identical_maps(n, side, n_img):
+    imgs = torch.stack([synth.rasterize(synth.proposal_params(n, side, 40 + b)) for b in range(n_img)]).to(DEV)
+    outs = {}
+    for lay in ("flat", "tiled"):
+        for algo in ("tensor", "popc"):
+            outs[lay, algo] = mask_ops.mask_overlap(mask_ops.mask_pack(imgs, layout=lay), return_counts=True, algo=algo)
+    ref = outs["flat", "popc"]
+    for k, o in outs.items():
+        assert torch.equal(o[2], ref[2]) and torch.equal(o[3], ref[3]), k
+        assert_f16_bits_equal(u16(o[0]), u16(ref[0]))
+        assert_f16_bits_equal(u16(o[1]), u16(ref[1]))
+    # the diagnostic counter: visited K-blocks, at most tiles x K-blocks per mask
+    nrb, ncb = (n + 127) // 128, (n + 255) // 256
+    tiles = sum(ncb - (i >> 1) for i in range(nrb)) * n_img
+    for lay in ("flat", "tiled"):
+        v = mask_ops.mask_overlap(mask_ops.mask_pack(imgs, layout=lay), algo="tensor", return_visited=True)[-1]
+        assert 0 < v <= tiles * (side * side // 128)
 
 
 @pytest.mark.parametrize("n,h,w", [(130, 64, 64), (65, 37, 50), (1, 8, 8), (200, 96, 96), (64, 5, 5)])
@@ -143,9 +181,12 @@ def test_crop_wire_format_round_trip(n, h, w):
     masks[3] = 1                               # full mask: crop = whole image
     crops = mask_ops.pack_crops_host(masks.numpy())
     dev_crops = mask_ops.MaskCrops(crops.words.to(DEV), crops.meta.to(DEV), crops.off.to(DEV), h, w)
-    got = mask_ops.unpack_crops(dev_crops)
-    want = mask_ops.mask_pack(masks.to(DEV))
+    got = mask_ops.unpack_crops(dev_crops, layout="flat")
+    want = mask_ops.mask_pack(masks.to(DEV), layout="flat")
     assert torch.equal(got, want)
+    if mask_ops.tiled_ok(h, w):
+        assert torch.equal(mask_ops.unpack_crops(dev_crops, layout="tiled"), mask_ops.mask_pack(masks.to(DEV), layout="tiled"))
+        assert mask_ops.unpack_crops(dev_crops).cim_kb_per_row == w // 16
     if w % 32 == 0:
         again = mask_ops.crops_from_packed_host(want.cpu(), h, w)
         assert torch.equal(again.words, crops.words) and torch.equal(again.meta, crops.meta)
