@@ -196,6 +196,19 @@ def build_inputs(cfg, dev, seed_base):
                 shape=(Cf, H, W, scale))
 
 
+def measured_traffic(workload, stage):
+    """DRAM bytes per launch of the stage's main kernel from the committed ncu --set full capture
+    (profiles/traffic.json), or None when there is no capture for this workload / stage."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        if t.get("workload") != workload or stage not in t:
+            return None
+        return int(t[stage]["dram_read"] + t[stage]["dram_write"])
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def visited_kblocks(step, cfg):
     """Number of 128-pixel K-blocks the tensor-core overlap kernel visited in its last launch (it leaves the
     count in the first 8 bytes of its workspace, include/cimhead.h) and the dense total: 128 x 256 tiles on or
@@ -363,7 +376,8 @@ def main():
     dominant = max(stage_ms, key=stage_ms.get)
     total_bytes = sum(bytes_img.values())
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": table[dominant]["gb_per_s"], "peak": peaks["hbm_gbs"],
-                "unit": "GB/s", "frac": table[dominant]["hbm_frac"], "traffic": None, "peak_source": peaks["source"],
+                "unit": "GB/s", "frac": table[dominant]["hbm_frac"], "traffic": measured_traffic(args.workload, dominant),
+                "peak_source": peaks["source"],
                 "share_of_step": round(stage_ms[dominant] / sum(stage_ms.values()), 3)}
     if dominant == "mask_overlap":
         # a dense R x HW x R contraction of 0/1 operands: tensor-pipe bound.  Algorithmic
