@@ -2,7 +2,8 @@
 """bench.py -- CIM-head images/s on B200 (BASELINE.json metric).
 
 A step = one pass of the hot path over one batch of synthetic images:
-RoIAlign fwd + RoIAlign bwd + mask IoU/containment + scoring heads + 3 x (mining + assignment).
+RoIAlign fwd + RoIAlign bwd + mask IoU/containment + scoring heads fwd + bwd (head gradients, averaged
+over the ranks with one NCCL allreduce when N > 1) + 3 x (mining + assignment).
 Workload = BASELINE.json configs[1]: ResNet-50 VOC, 8 images x 2000 mask proposals per GPU
 (512x512 images -> 1024x32x32 features, 512x512 bit-packed proposal masks, 20 classes).
 
@@ -27,7 +28,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "CIM-head images/s (ROIAlign fwd+bwd + mask IoU + scoring + mining)"
+METRIC = "CIM-head images/s (ROIAlign fwd+bwd + mask IoU + scoring fwd+bwd + mining)"
 WORKLOADS = {
     # name: backbone, images per GPU, proposals, classes, present classes, mask side
     "cfg2_r50_voc_8x2000": dict(backbone="resnet50", n_img=8, R=2000, C=20, present=2, mask=512),
@@ -56,6 +57,9 @@ def algorithmic_bytes(cfg, Cf, H, W):
         "mask_overlap": R * hwm // 8 + 2 * R * R * 2,
         "score_heads": R * 4096 * 4 + 8 * (C + 1) * 4097 * 4 + 8 * R * (C + 1) * 4,
         "mine_assign": 3 * (2 * R * R * 2 + R * (C + 1) * 4 + R * 6),
+        # scoring backward: x read, grad_x written, scores and grad_scores read, weights read and head
+        # gradients written
+        "score_heads_bwd": 2 * R * 4096 * 4 + 2 * 8 * R * (C + 1) * 4 + 2 * 8 * (C + 1) * 4097 * 4,
     }
 
 
@@ -102,7 +106,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ CPU arm
-def cpu_reference(cfg, steps, warmup, sample_rois=128):
+def cpu_reference(cfg, steps, warmup, sample_rois=128, head_grads=True):
     """The reference's algorithm for the path, restated for CPU (oracle/), timed on the host cores
     on a BOUNDED sample of the workload: one image; RoIAlign fwd+bwd and the mask overlap on
     `sample_rois` of its R proposals (cost scaled by R / sample_rois: both are linear in the
@@ -125,6 +129,7 @@ def cpu_reference(cfg, steps, warmup, sample_rois=128):
     b = [np.zeros(C + 1, np.float32) for _ in range(8)]
     x = np.random.RandomState(2).randn(R, 4096).astype(np.float32)
     labels = synth.image_labels(C, cfg["present"], 1234).numpy()
+    g_scores = [np.random.RandomState(20 + i).randn(R, C + 1).astype(np.float32) for i in range(8)]
     from oracle import mask_oracle
     iou16, asy16 = mask_oracle.mask_overlap_maps(masks[:, ::max(1, masks.shape[1] // 4096)])   # setup only
 
@@ -142,6 +147,8 @@ def cpu_reference(cfg, steps, warmup, sample_rois=128):
         t_mask = time.perf_counter() - t0
         t0 = time.perf_counter()
         p_cls, p_det, r_cls, r_iou = heads_oracle.score_heads(x, w, b)
+        if head_grads:
+            heads_oracle.score_heads_bwd(x, w, b, g_scores)
         t_score = time.perf_counter() - t0
         t0 = time.perf_counter()
         cls_l, det_l = [p_cls, r_cls[0], r_cls[1]], [p_det, r_iou[0], r_iou[1]]
@@ -164,7 +171,8 @@ def cpu_reference(cfg, steps, warmup, sample_rois=128):
     sec = float(np.mean(per_image))
     return dict(images_per_s=1.0 / sec, sec_per_image=sec, cores=ncpu, wall_s=wall, parts=parts,
                 sample=f"1 image of {cfg['R']} proposals; RoIAlign fwd+bwd and mask overlap on {S} proposal rows "
-                       f"(x{R / S:.1f}), scoring + 3 mining layers at full size; numpy/OpenMP on all host cores")
+                       f"(x{R / S:.1f}), scoring {'fwd+bwd' if head_grads else 'fwd'} + 3 mining layers at full size; "
+                       f"numpy/OpenMP on all host cores")
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -190,7 +198,9 @@ def build_inputs(cfg, dev, seed_base):
     model = heads.cls_iou_model(4096, C + 1, 3).to(dev)
     weight, bias = (t.detach().contiguous() for t in model._stacked())
     labels = torch.cat(labels)
+    grad_scores = torch.randn(8, n_img * R, C + 1, device=dev, generator=gen)
     return dict(feat=feat, rois=torch.cat(rois).to(dev), grad_out=grad_out, packed=torch.stack(packed),
+                grad_scores=grad_scores,
                 packed_flat=torch.stack(packed_flat), kb_per_row=kb_per_row,
                 seg_x=seg_x, weight=weight, bias=bias, labels=labels.to(dev), labels_host=labels.numpy(),
                 shape=(Cf, H, W, scale))
@@ -243,6 +253,10 @@ def time_stages(step, inp, iters=5):
         "score_heads": lambda: L.cim_score_heads(P(inp["seg_x"]), P(inp["weight"]), P(inp["bias"]), P(step.scores),
                                                  n_img, R, step.D, step.C + 1, step.K, P(step.score_ws),
                                                  step.score_ws.numel(), st),
+        "score_heads_bwd": lambda: L.cim_score_heads_bwd(P(inp["seg_x"]), P(inp["weight"]), P(step.scores),
+                                                         P(inp["grad_scores"]), P(step.grad_seg_x), P(step.grad_weight),
+                                                         P(step.grad_bias), n_img, R, step.D, step.C + 1, step.K,
+                                                         P(step.score_bwd_ws), step.score_bwd_ws.numel(), st),
         "mine": lambda: L.cim_mine(C.byref(p), step.cls_ptrs, step.det_ptrs, P(inp["labels"]), P(step.iou),
                                    P(step.asy), P(step.gt_count), P(step.gt_rows), P(step.gt_class),
                                    P(step.gt_weight), P(step.asy_flag), P(step.mine_ws), step.mine_ws.numel(), st),
@@ -250,6 +264,8 @@ def time_stages(step, inp, iters=5):
                                        P(step.gt_weight), None, P(step.pseudo_labels), P(step.pseudo_iou),
                                        P(step.loss_weights), P(step.valid), st),
     }
+    if not step.head_grads:
+        del calls["score_heads_bwd"]
     out = {}
     for name, fn in calls.items():
         _lib.check(fn(), name)
@@ -273,6 +289,8 @@ def main():
     ap.add_argument("--workload", default="cfg2_r50_voc_8x2000", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-anti-noise", action="store_true")
+    ap.add_argument("--no-head-grads", action="store_true",
+                    help="leave the scoring backward (+ the allreduce of the head gradients) out of the step")
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -285,7 +303,7 @@ def main():
         if rank != 0:
             return
         steps, warmup = max(1, min(args.steps, 3)), 1          # bounded; one untimed pass warms BLAS / pages
-        r = cpu_reference(cfg, steps, warmup)
+        r = cpu_reference(cfg, steps, warmup, head_grads=not args.no_head_grads)
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": r["images_per_s"], "unit": "images/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * r["sec_per_image"],
@@ -300,7 +318,7 @@ def main():
 
     import torch
     from cim_b200 import dist as cdist
-    from cim_b200.step import CIMHeadStep, KERNELS_PER_STEP
+    from cim_b200.step import CIMHeadStep, KERNELS_HEAD_GRADS, KERNELS_PER_STEP
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     rank, world, local = cdist.init_from_env()
@@ -312,9 +330,11 @@ def main():
     Cf, H, W, scale = inp["shape"]
     words = inp["packed"].shape[-1]
     step = CIMHeadStep(cfg["n_img"], cfg["R"], cfg["C"], Cf, H, W, scale, words, anti_noise_sampling=not args.no_anti_noise,
-                       max_present=max(4, 2 * cfg["present"]), device=dev, mask_kb_per_row=inp["kb_per_row"])
+                       max_present=max(4, 2 * cfg["present"]), device=dev, mask_kb_per_row=inp["kb_per_row"],
+                       head_grads=not args.no_head_grads)
+    g_scores = None if args.no_head_grads else inp["grad_scores"]
     run = lambda: step.run(inp["feat"], inp["rois"], inp["grad_out"], inp["packed"], inp["seg_x"], inp["weight"],
-                           inp["bias"], inp["labels"], inp["labels_host"])
+                           inp["bias"], inp["labels"], inp["labels_host"], grad_scores=g_scores)
     np.random.seed(3)
     for _ in range(max(args.warmup, 3)):
         run()
@@ -346,7 +366,8 @@ def main():
     step.hi_rois.copy_(inp["rois"])
     step.hi_labels.copy_(inp["labels"])
     step.set_host_crops(crops)
-    run_host = lambda: step.run_host(inp["feat"], inp["grad_out"], inp["seg_x"], inp["weight"], inp["bias"])
+    run_host = lambda: step.run_host(inp["feat"], inp["grad_out"], inp["seg_x"], inp["weight"], inp["bias"],
+                                     grad_scores=g_scores)
     for _ in range(2):
         run_host()
     cdist.barrier()
@@ -366,6 +387,8 @@ def main():
         return
 
     bytes_img = algorithmic_bytes(cfg, Cf, H, W)
+    if args.no_head_grads:
+        del bytes_img["score_heads_bwd"]
     stage_ms = dict(stages)
     stage_ms["mine_assign"] = stage_ms.pop("mine") + stage_ms.pop("assign")
     table = {}
@@ -408,14 +431,18 @@ def main():
                                "features/seg_x/grad_out are device-produced",
                 "pipelining": "H2D of step i+1 on a copy stream overlaps the kernels of step i; results are read "
                               "back and the host synchronises every step"},
-        "gpu_launches": KERNELS_PER_STEP * args.steps,
+        "gpu_launches": (KERNELS_PER_STEP + (0 if args.no_head_grads else KERNELS_HEAD_GRADS)) * args.steps,
+        "collective": ("none (single process)" if world == 1 else
+                       f"NCCL allreduce (avg) of the {step.head_bucket.numel() * 4} B head-gradient bucket per step, "
+                       "inside the timed region, overlapped with the RoIAlign kernels") if not args.no_head_grads
+        else "none (head gradients excluded)",
         "roofline": roofline,
         "step_roofline": {"algorithmic_mb_per_image": round(total_bytes / 1e6, 1),
                           "hbm_frac": round(value / world * total_bytes / 1e9 / peaks["hbm_gbs"], 4)},
         "stages": table, "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference(cfg, 1, 0)
+        r = cpu_reference(cfg, 1, 0, head_grads=not args.no_head_grads)
         result["cpu_baseline"] = {"value": r["images_per_s"], "unit": "images/s", "cores": r["cores"], "kind": "port",
                                   "sample": r["sample"], "parts_s_per_image": r["parts"]}
     print(json.dumps(result))

@@ -75,3 +75,21 @@ def allreduce_mean_(tensors):
         t.copy_(flat[off:off + n].view_as(t))
         off += n
     return tensors
+
+
+def allreduce_mean_async_(bucket):
+    """Start averaging one flat gradient bucket over the ranks (in place) and return a callable that makes
+    the CURRENT stream wait for the result, or None in a single-process run.  NCCL runs the collective on
+    its own stream, so kernels launched between the two calls overlap with it."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return None
+    work = dist.all_reduce(bucket, op=dist.ReduceOp.AVG if dist.get_backend() == "nccl" else dist.ReduceOp.SUM,
+                           async_op=True)
+    world = dist.get_world_size()
+    nccl = dist.get_backend() == "nccl"
+
+    def finish():
+        work.wait()
+        if not nccl:
+            bucket.div_(world)
+    return finish

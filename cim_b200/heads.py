@@ -56,26 +56,25 @@ class ScoreHeadsFunction(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, grad):
-        # Backward of the activations + the three GEMMs with torch ops (plumbing for now; the
-        # forward above is the path BASELINE.json names).
+        """cim_score_heads_bwd: activation backward + grad_x / grad_weight / grad_bias in one call
+        (autograd of heads.py:194-219)."""
         x, weight, s = ctx.saved_tensors
         n_img, k = ctx.cfg
         nh, m, c1 = s.shape
-        dz = torch.empty_like(s)
-        for h in range(nh):
-            g, y = grad[h], s[h]
-            if h == 1:                                   # softmax over the proposals of each image
-                g3, y3 = g.view(n_img, -1, c1), y.view(n_img, -1, c1)
-                dz[h] = (y3 * (g3 - (g3 * y3).sum(1, keepdim=True))).view(m, c1)
-            elif h < 2 + k:                              # softmax over classes
-                dz[h] = y * (g - (g * y).sum(-1, keepdim=True))
-            else:                                        # sigmoid
-                dz[h] = g * y * (1 - y)
-        dz2 = dz.permute(1, 0, 2).reshape(m, nh * c1)
-        w2 = weight.reshape(nh * c1, -1)
-        gx = dz2 @ w2 if ctx.needs_input_grad[0] else None
-        gw = (dz2.t() @ x).view_as(weight) if ctx.needs_input_grad[1] else None
-        gb = dz.sum(1) if ctx.needs_input_grad[2] else None
+        d = x.shape[1]
+        grad = _lib.require_cuda(grad, "grad_scores", torch.float32).contiguous()
+        L = _lib.lib()
+        need_x, need_w, need_b = ctx.needs_input_grad[:3]
+        with torch.cuda.device(x.device):
+            gx = torch.empty_like(x) if need_x else None
+            gw = torch.empty_like(weight) if need_w else None
+            gb = torch.empty((nh, c1), dtype=torch.float32, device=x.device) if need_b else None
+            ws = torch.empty(L.cim_score_heads_bwd_workspace_bytes(n_img, m // n_img, d, c1, k), dtype=torch.uint8,
+                             device=x.device)
+            rc = L.cim_score_heads_bwd(_lib.ptr(x), _lib.ptr(weight), _lib.ptr(s), _lib.ptr(grad), _lib.ptr(gx),
+                                       _lib.ptr(gw), _lib.ptr(gb), n_img, m // n_img, d, c1, k, _lib.ptr(ws),
+                                       ws.numel(), _lib.stream_ptr(x.device))
+        _lib.check(rc, "cim_score_heads_bwd")
         return gx, gw, gb, None, None
 
 

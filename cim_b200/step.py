@@ -11,6 +11,9 @@ tools/train.py:436):
     scoring heads               model_builder.py:143
     3 x mining + assignment     model_builder.py:170-187
     RoIAlign backward           autograd of the first line
+    scoring heads backward      autograd of the third line (loss.backward(), tools/train.py:436) -> head
+                                gradients, all-reduced over the ranks of a data-parallel run
+                                (reference: comm.reduce_add_coalesced, lib/nn/parallel/_functions.py:39)
 
 All device work goes through the C ABI (include/cimhead.h) on the current CUDA stream.  The one
 host hop is the anti-noise sampling (heads.py:451-466, numpy global RNG); it is overlapped with
@@ -22,17 +25,21 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import dist as cdist
 from .heads import _anti_noise_keep
 
 #: kernels (not memsets / copies) libcimhead launches in one run(): roi_align fwd 3 + bwd 3,
 #: mask area + sort + overlap + 2 un-permutes = 5, scoring 3, mining 3, assignment 1
 KERNELS_PER_STEP = 18
+#: + with grad_scores: detector dot, activation backward, bias, W^T split, grad_x GEMM, grad_W GEMM, reduce
+KERNELS_HEAD_GRADS = 7
 
 
 class CIMHeadStep:
     def __init__(self, n_img, n_props, n_classes, feat_channels, feat_h, feat_w, spatial_scale, mask_words,
                  feat_dim=4096, refine_times=3, p_seed=0.1, step_rate=0.1, con_thr=0.85, anti_noise_sampling=True,
-                 max_present=4, device="cuda:0", sampling_ratio=0, aligned=True, mask_kb_per_row=0):
+                 max_present=4, device="cuda:0", sampling_ratio=0, aligned=True, mask_kb_per_row=0,
+                 head_grads=False):
         self.dev = torch.device(device)
         self.n_img, self.R, self.C, self.K = n_img, n_props, n_classes, refine_times
         self.Cf, self.H, self.W, self.scale = feat_channels, feat_h, feat_w, float(spatial_scale)
@@ -56,6 +63,15 @@ class CIMHeadStep:
             self.overlap_ws = e((self.L.cim_mask_overlap_workspace_bytes(n_img, R, mask_words, 0),), torch.uint8)
             self.scores = e((nh, n_img * R, C1), torch.float32)
             self.score_ws = e((max(256, self.L.cim_score_heads_workspace_bytes(n_img, R, feat_dim, C1, k)),), torch.uint8)
+            self.head_grads = bool(head_grads)
+            if self.head_grads:
+                # grad_weight and grad_bias share one buffer: the bucket of the data-parallel allreduce
+                self.head_bucket = e((nh * C1 * feat_dim + nh * C1,), torch.float32)
+                self.grad_weight = self.head_bucket[:nh * C1 * feat_dim].view(nh, C1, feat_dim)
+                self.grad_bias = self.head_bucket[nh * C1 * feat_dim:].view(nh, C1)
+                self.grad_seg_x = e((n_img * R, feat_dim), torch.float32)
+                self.score_bwd_ws = e((self.L.cim_score_heads_bwd_workspace_bytes(n_img, R, feat_dim, C1, k),),
+                                      torch.uint8)
             p = _lib.MineParams()
             p.n_img, p.R, p.C, p.C1, p.n_layers = n_img, R, n_classes, C1, k
             p.det_cols, p.gt_cap, p.mode = C1, R, 0
@@ -93,12 +109,15 @@ class CIMHeadStep:
         self.det_ptrs = PtrArr(*[t.data_ptr() for t in det_src])
 
     # -------------------------------------------------------------------------------------
-    def run(self, feat, rois, grad_out, packed_masks, seg_x, weight, bias, labels, labels_host):
+    def run(self, feat, rois, grad_out, packed_masks, seg_x, weight, bias, labels, labels_host, grad_scores=None):
         """feat [n_img,Cf,H,W] f32, rois [n_img*R,5] f32 grouped by image, grad_out [n_img*R,Cf,7,7]
         f32, packed_masks [n_img,R,words] i32, seg_x [n_img*R,D] f32, weight [2+2K,C+1,D],
         bias [2+2K,C+1], labels [n_img,C] f32 (+ the same on the host as a numpy array).
         Results land in self.roi_out, grad_feat, iou, asy, scores, pseudo_labels, pseudo_iou,
-        loss_weights, valid."""
+        loss_weights, valid.  With head_grads=True and grad_scores [2+2K, n_img*R, C+1] (dL/dscores, what
+        the losses' backward hands over) also grad_seg_x, grad_weight, grad_bias; in a multi-process run
+        the head-gradient bucket is averaged over the ranks (one NCCL allreduce, overlapped with the
+        RoIAlign kernels)."""
         L, p, dev = self.L, self.p, self.dev
         P, n_img, R, k = _lib.ptr, self.n_img, self.R, self.K
         st = _lib.stream_ptr(dev)
@@ -111,6 +130,12 @@ class CIMHeadStep:
         ck(L.cim_mine(C.byref(p), self.cls_ptrs, self.det_ptrs, P(labels), P(self.iou), P(self.asy),
                       P(self.gt_count), P(self.gt_rows), P(self.gt_class), P(self.gt_weight), P(self.asy_flag),
                       P(self.mine_ws), self.mine_ws.numel(), st), "cim_mine")
+        reduce_work = None
+        if self.head_grads and grad_scores is not None:
+            ck(L.cim_score_heads_bwd(P(seg_x), P(weight), P(self.scores), P(grad_scores), P(self.grad_seg_x),
+                                     P(self.grad_weight), P(self.grad_bias), n_img, R, self.D, self.C + 1, k,
+                                     P(self.score_bwd_ws), self.score_bwd_ws.numel(), st), "cim_score_heads_bwd")
+            reduce_work = cdist.allreduce_mean_async_(self.head_bucket)
         if self.anti:
             self.h_count.copy_(self.gt_count, non_blocking=True)
             self.h_class.copy_(self.gt_class[:, :, :self.cap], non_blocking=True)
@@ -141,6 +166,8 @@ class CIMHeadStep:
         ck(L.cim_assign(C.byref(p), P(self.iou), P(self.gt_count), P(self.gt_rows), P(self.gt_class),
                         P(self.gt_weight), P(keep), P(self.pseudo_labels), P(self.pseudo_iou),
                         P(self.loss_weights), P(self.valid), st), "cim_assign")
+        if reduce_work is not None:
+            reduce_work()                                       # current stream waits for the allreduce
         return self
 
     # -------------------------------------------------------------------------------------
@@ -229,7 +256,7 @@ class CIMHeadStep:
             buf["ready"].record(self.copy_stream)
         return self
 
-    def run_host(self, feat, grad_out, seg_x, weight, bias, prefetch_next=True):
+    def run_host(self, feat, grad_out, seg_x, weight, bias, prefetch_next=True, grad_scores=None):
         """End-to-end step: host rois / labels / bit-packed masks -> device, the step, results ->
         host.  feat / seg_x / grad_out are produced on the device by the backbone, MaskFuse and
         autograd in the real pipeline and therefore stay device tensors.
@@ -245,7 +272,7 @@ class CIMHeadStep:
             self.stage_host_inputs()                           # goes to the other buffer
         cur_stream.wait_event(buf["ready"])
         self.run(feat, buf["rois"], grad_out, buf["masks"], seg_x, weight, bias, buf["labels"],
-                 buf["labels_host"])
+                 buf["labels_host"], grad_scores=grad_scores)
         buf["free"].record(cur_stream)
         self.d_checksum[0] = self.roi_out.view(-1)[::4099].sum()
         self.d_checksum[1] = self.grad_feat.view(-1)[::127].sum()

@@ -27,7 +27,7 @@ extern "C" {
 
 typedef struct CUstream_st *cim_stream_t;   /* == cudaStream_t */
 
-#define CIM_ABI_VERSION 2
+#define CIM_ABI_VERSION 3
 
 enum {
     CIM_OK = 0,
@@ -143,6 +143,25 @@ size_t cim_score_heads_workspace_bytes(int n_img, int R, int D, int C1, int K);
 int cim_score_heads(const float *x, const float *weight, const float *bias, float *scores,
                     int n_img, int R, int D, int C1, int K,
                     void *workspace, size_t workspace_bytes, cim_stream_t stream);
+
+/* Backward of cim_score_heads = autograd of heads.cls_iou_model.forward (lib/modeling/heads.py:194-219; the
+ * reference gets it from eight nn.Linear backward calls + softmax / sigmoid backward, run by loss.backward(),
+ * tools/train.py:436).  grad_weight / grad_bias are the head gradients a data-parallel run all-reduces
+ * (reference: comm.reduce_add_coalesced, lib/nn/parallel/_functions.py:39).
+ *   scores       [n_heads, n_img*R, C1] fp32: the OUTPUT of cim_score_heads for the same x / weight / bias
+ *   grad_scores  [n_heads, n_img*R, C1] fp32: dL/dscores
+ *   grad_x       [n_img*R, D]      (may be NULL)     grad_weight [n_heads, C1, D] (may be NULL)
+ *   grad_bias    [n_heads, C1]     (may be NULL)     all fully overwritten.
+ * Activation backward: y (g - sum_classes g y) for classifier / refine_cls, y (g - sum over the proposals of
+ * the image of g y) for the detector, g y (1 - y) for refine_iou.  The two GEMMs run as 3xTF32 on the tensor
+ * cores (fp32-accurate) when n_img*R >= 128 and D % 4 == 0, as plain fp32 otherwise.  Deterministic (the
+ * split-M partial sums of grad_weight are added in a fixed order).
+ * workspace: cim_score_heads_bwd_workspace_bytes() bytes, required. */
+size_t cim_score_heads_bwd_workspace_bytes(int n_img, int R, int D, int C1, int K);
+int cim_score_heads_bwd(const float *x, const float *weight, const float *scores, const float *grad_scores,
+                        float *grad_x, float *grad_weight, float *grad_bias,
+                        int n_img, int R, int D, int C1, int K,
+                        void *workspace, size_t workspace_bytes, cim_stream_t stream);
 
 /* ------------------------------------------------------------------ CIM mining + assignment
  * Replace heads.CIM_layer (lib/modeling/heads.py:222-503) for n_img images x n_layers

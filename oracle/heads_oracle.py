@@ -59,6 +59,34 @@ def score_heads(x, weights, biases):
     return f(predict_cls), f(predict_det), [f(a) for a in ref_cls], [f(a) for a in ref_iou]
 
 
+def score_heads_bwd(x, weights, biases, grads):
+    """Backward of cls_iou_model.forward (autograd of heads.py:194-219) in float64.
+
+    grads: 2+2K arrays [R,C1] = dL/d(output) in the order of `weights`.  Returns
+    (grad_x [R,D], [grad_W_h [C1,D]], [grad_b_h [C1]]) as float32.  Pinned by oracle/make_golden.py
+    against torch autograd through the reference's own cls_iou_model."""
+    x = np.asarray(x, dtype=np.float64)
+    k = (len(weights) - 2) // 2
+    gx = np.zeros_like(x)
+    gws, gbs = [], []
+    for h, (w, b, g) in enumerate(zip(weights, biases, grads)):
+        w, g = np.asarray(w, np.float64), np.asarray(g, np.float64)
+        z = x @ w.T + np.asarray(b, np.float64)
+        if h == 1:                                    # softmax over proposals (:203)
+            y = _softmax(z, axis=0)
+            dz = y * (g - (g * y).sum(0, keepdims=True))
+        elif h < 2 + k:                               # softmax over classes (:200, :212)
+            y = _softmax(z, axis=-1)
+            dz = y * (g - (g * y).sum(-1, keepdims=True))
+        else:                                         # sigmoid (:216)
+            y = 1.0 / (1.0 + np.exp(-z))
+            dz = g * y * (1.0 - y)
+        gx += dz @ w
+        gws.append((dz.T @ x).astype(np.float32))
+        gbs.append(dz.sum(0).astype(np.float32))
+    return gx.astype(np.float32), gws, gbs
+
+
 def refine_scores(ref_cls, ref_iou):
     """testing_function (model_builder.py:60-68): per refinement head (cls*iou)[:,1:]."""
     return [(c * i)[:, 1:] for c, i in zip(ref_cls, ref_iou)]

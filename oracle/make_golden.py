@@ -234,6 +234,27 @@ def make_scoring_fixture(ref_heads):
         out[name + "/w"] = w
         out[name + "/b"] = b
         out[name + "/scores"] = ref
+        # backward through the reference's model (torch autograd, what loss.backward() runs, tools/train.py:436)
+        xg = x.clone().requires_grad_(True)
+        model.zero_grad()
+        o2 = model(xg)
+        flat = [o2[0], o2[1]] + list(o2[2]) + list(o2[3])
+        gen = torch.Generator().manual_seed(seed + 100)
+        gs = [torch.randn(t.shape, generator=gen) for t in flat]
+        sum((t * g).sum() for t, g in zip(flat, gs)).backward()
+        gsd = dict(model.named_parameters())
+        gw_ref = np.stack([gsd[n + ".weight"].grad.numpy() for n in names])
+        gb_ref = np.stack([gsd[n + ".bias"].grad.numpy() for n in names])
+        gx_o, gw_o, gb_o = heads_oracle.score_heads_bwd(x.numpy(), list(w), list(b), [g.numpy() for g in gs])
+        for got, want, what in ((gx_o, xg.grad.numpy(), "grad_x"), (np.stack(gw_o), gw_ref, "grad_w"),
+                                (np.stack(gb_o), gb_ref, "grad_b")):
+            e = np.abs(got - want).max() / max(np.abs(want).max(), 1e-3)
+            assert e < 1e-5, (what, e)
+            print(f"scoring bwd {name}: oracle vs reference {what} max err / max {e:.2e}")
+        out[name + "/grads"] = np.stack([g.numpy() for g in gs])
+        out[name + "/grad_x"] = xg.grad.numpy()
+        out[name + "/grad_w"] = gw_ref
+        out[name + "/grad_b"] = gb_ref
         print(f"scoring {name}: oracle vs reference max rel err {err:.2e}")
     np.savez_compressed(os.path.join(GOLD, "score_heads.npz"), **out)
 

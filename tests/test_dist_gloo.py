@@ -27,6 +27,11 @@ def _worker(rank, world, port, out):
     total = cdist.sum_over_ranks(len(mine))
     grads = [torch.full((3, 4), float(rank + 1)), torch.full((5,), float(10 * (rank + 1)))]
     cdist.allreduce_mean_(grads)
+    bucket = torch.full((11,), float(rank + 1))        # the step's head-gradient bucket path
+    finish = cdist.allreduce_mean_async_(bucket)
+    assert finish is not None
+    finish()
+    assert torch.equal(bucket, torch.full((11,), 1.5))
     out[rank] = (mine, slow, total, grads[0][0, 0].item(), grads[1][0].item())
     dist.destroy_process_group()
 
@@ -46,3 +51,4 @@ def test_two_rank_gloo():
 def test_single_process_is_a_noop():
     assert cdist.shard_images(3, 0, 1) == [0, 1, 2]
     assert cdist.max_over_ranks(0.25) == 0.25
+    assert cdist.allreduce_mean_async_(torch.ones(3)) is None
