@@ -18,6 +18,9 @@ def init_from_env(backend=None):
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
+        # NCCL prints its version banner (NCCL_DEBUG=VERSION/INFO) to stdout; rank 0's stdout carries
+        # exactly one JSON line in bench.py, so send NCCL's log to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
