@@ -206,6 +206,20 @@ int cim_assign(const cim_mine_params *p, const void *iou_f16,
                float *pseudo_labels, void *pseudo_iou_f16, float *loss_weights, uint8_t *valid,
                cim_stream_t stream);
 
+/* ------------------------------------------------------------------ test-time post-processing
+ * cim_test_scores: lib/core/test.py:130-133 over lib/modeling/model_builder.py:60-68 -- the K refinement
+ *   heads' (cls * iou)[:, 1:] summed in head order and divided by K.
+ *   scores [2+2K, M, C1] fp32 as written by cim_score_heads -> out [M, C1-1] fp32.
+ * cim_box_nms: the per-class body of lib/utils/mask_eval_utils.py:57-79 -- candidates scores[i][c] >
+ *   score_thresh, then the greedy NMS of lib/utils/cython_nms.pyx:37-87 ("+1" areas, float32 arithmetic,
+ *   suppression when overlap >= nms_thresh, boxes visited by descending score; equal scores by descending
+ *   index).  boxes [n,4] fp32 (x1,y1,x2,y2), 16-byte aligned; scores [n, score_stride] fp32, class c in
+ *   column c; keep [n_classes, n] uint8 = 1 where proposal i survives for class c (np.where(suppressed == 0)
+ *   + the candidate filter; ascending i is the reference's output order).  n <= 8192. */
+int cim_test_scores(const float *scores, float *out, int64_t M, int C1, int K, cim_stream_t stream);
+int cim_box_nms(const float *boxes, const float *scores, int n, int n_classes, int score_stride,
+                float score_thresh, float nms_thresh, uint8_t *keep, cim_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,6 +7,8 @@ It imports, UNMODIFIED, from /root/reference:
     lib/modeling/heads.py   (cls_iou_model, CIM_layer)            -- runs on CPU tensors
     lib/utils/mask_utils.py (mask_iou, mask_asymmetric_iou)       -- behind a 3-line shim that
         makes `chainer.backends.cuda.get_array_module` return numpy (chainer/cupy are absent)
+    lib/utils/cython_nms.pyx (nms)                                -- compiled into oracle/_ref by
+        oracle/build_ref_nms.py (two numpy type names respelled for numpy 2)
 The fixtures travel to the GPU box; /root/reference does not.  While generating, every
 fixture is also replayed through the oracle restatement and any mismatch aborts.
 """
@@ -259,13 +261,62 @@ def make_scoring_fixture(ref_heads):
     np.savez_compressed(os.path.join(GOLD, "score_heads.npz"), **out)
 
 
+def make_nms_fixture():
+    """Box NMS: the reference's own Cython `nms` (lib/utils/cython_nms.pyx, compiled unmodified apart from two
+    numpy type names by oracle/build_ref_nms.py) driven per class as mask_eval_utils.py:63-79 does."""
+    sys.path.insert(0, os.path.join(HERE, "_ref"))
+    import ref_cython_nms
+    from oracle import nms_oracle
+    out, rs = {}, np.random.RandomState(11)
+
+    def add(name, boxes, scores, score_thr, nms_thr):
+        boxes, scores = boxes.astype(np.float32), scores.astype(np.float32)
+        n, c = scores.shape
+        keep = np.zeros((c, n), np.uint8)
+        for j in range(c):
+            inds = np.where(scores[:, j] > score_thr)[0]
+            dets = np.hstack((boxes[inds], scores[inds, j][:, None])).astype(np.float32, copy=False)
+            if len(dets):
+                keep[j, inds[ref_cython_nms.nms(dets, np.float32(nms_thr))]] = 1
+        assert np.array_equal(keep, nms_oracle.class_keep(boxes, scores, score_thr, nms_thr)), name
+        out[name + "/boxes"], out[name + "/scores"], out[name + "/keep"] = boxes, scores, keep
+        out[name + "/params"] = np.array([score_thr, nms_thr], np.float64)
+        print(f"box nms {name}: n={n} classes={c} kept={int(keep.sum())}; oracle == reference")
+
+    def tie_free(n, c):                        # every column a permutation: no equal scores inside a class
+        return np.stack([(rs.permutation(n) + 1.0) / (n + 1) for _ in range(c)], 1) * rs.uniform(0.2, 1.0, (1, c))
+
+    for name, n, c, seed in [("voc_r300", 300, 20, 21), ("coco_r500", 500, 80, 22)]:
+        rois = synth.rois_from_params(synth.proposal_params(n, 512, seed)).numpy()[:, 1:]
+        sc = tie_free(n, c)
+        sc[rs.rand(n, c) < 0.3] = 0.0                                      # below SCORE_THRESH: not candidates
+        add(name, rois, sc, 1e-5, 0.3)
+    # integer boxes whose overlap lands exactly on the threshold (ovr >= thresh suppresses): 10x10 boxes
+    # shifted by 5 px: inter 50, union 150 -> 1/3; thresholds 1/3 (as float32) and just above it
+    grid = np.array([[x, y, x + 9, y + 9] for y in range(0, 40, 5) for x in range(0, 40, 5)], np.float32)
+    add("exact_third", grid, tie_free(len(grid), 3), 1e-5, float(np.float32(50.0) / np.float32(150.0)))
+    add("above_third", grid, tie_free(len(grid), 3), 1e-5, float(np.nextafter(np.float32(50.0) / np.float32(150.0), np.float32(1))))
+    dup = np.repeat(grid[:6], 3, axis=0)                                   # identical boxes: ovr == 1
+    add("duplicates", dup, tie_free(len(dup), 2), 1e-5, 0.3)
+    deg = grid[:12].copy()
+    deg[::3, 2] = deg[::3, 0] - 1                                          # x2 = x1 - 1: zero "+1" width
+    add("degenerate", deg, tie_free(len(deg), 2), 1e-5, 0.3)
+    add("single", grid[:1], np.array([[0.7, 0.0]]), 1e-5, 0.3)
+    add("none", grid[:9], np.zeros((9, 4)), 1e-5, 0.3)
+    np.savez_compressed(os.path.join(GOLD, "box_nms.npz"), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if "--only-nms" in sys.argv:
+        make_nms_fixture()
+        return
     torch.set_num_threads(4)
     ref_heads, ref_mu = load_reference()
     make_mask_fixture(ref_mu)
     make_heads_fixtures(ref_heads, ref_mu)
     make_scoring_fixture(ref_heads)
+    make_nms_fixture()
     if "--fuzz" in sys.argv:
         fuzz(ref_heads, ref_mu, int(sys.argv[sys.argv.index("--fuzz") + 1]))
     print("golden fixtures written to", GOLD)
