@@ -245,6 +245,60 @@ class CIM_layer(nn.Module):
         return out["pseudo_labels"][0, 0], out["pseudo_iou_labels"][0, 0], out["loss_weights"][0, 0]
 
 
+# ------------------------------------------------------------------------------- losses
+class HeadLossFunction(Function):
+    """cim_head_losses: the loss block of model_builder.py:170-202 (heads.cls_iou_loss per refinement layer +
+    heads.mil_bag_loss) forward AND backward in one launch.  Returns (total [n_img], losses [n_img, K+1, 3]);
+    only `total` = sum_l cls + iou_weight * sum_l iou + sum_l bag + mil_bag per image is differentiable."""
+
+    @staticmethod
+    def forward(ctx, scores, pseudo_labels, pseudo_iou, loss_weights, valid, labels, k, lmda0, lmda_rest, iou_weight):
+        _lib.require_cuda(scores, "scores", torch.float32)
+        _lib.require_cuda(pseudo_labels, "pseudo_labels", torch.float32)
+        _lib.require_cuda(pseudo_iou, "pseudo_iou_labels", torch.float16)
+        _lib.require_cuda(loss_weights, "loss_weights", torch.float32)
+        _lib.require_cuda(valid, "valid", torch.uint8)
+        scores, pseudo_labels, pseudo_iou = scores.contiguous(), pseudo_labels.contiguous(), pseudo_iou.contiguous()
+        loss_weights, valid = loss_weights.contiguous(), valid.contiguous()
+        n_layers, n_img, R, c1 = pseudo_labels.shape
+        labels = _lib.require_cuda(labels, "labels").to(torch.float32).reshape(n_img, c1 - 1).contiguous()
+        if tuple(scores.shape) != (2 + 2 * k, n_img * R, c1):
+            raise ValueError("scores must be [2+2K, n_img*R, C+1]")
+        with torch.cuda.device(scores.device):
+            losses = torch.empty((n_img, k + 1, 3), dtype=torch.float32, device=scores.device)
+            grad = torch.empty_like(scores)
+            rc = _lib.lib().cim_head_losses(_lib.ptr(scores), _lib.ptr(pseudo_labels), _lib.ptr(pseudo_iou),
+                                            _lib.ptr(loss_weights), _lib.ptr(valid), _lib.ptr(labels), _lib.ptr(losses),
+                                            _lib.ptr(grad), n_img, R, c1 - 1, k, n_layers, float(lmda0),
+                                            float(lmda_rest), float(iou_weight), 1.0, _lib.stream_ptr(scores.device))
+        _lib.check(rc, "cim_head_losses")
+        ctx.save_for_backward(grad)
+        ctx.shape = (n_img, R)
+        total = losses[:, :, 0].sum(1) + iou_weight * losses[:, :, 1].sum(1) + losses[:, :, 2].sum(1)
+        ctx.mark_non_differentiable(losses)
+        return total, losses
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_total, _g_losses):
+        (grad,) = ctx.saved_tensors
+        n_img, R = ctx.shape
+        nh, _, c1 = grad.shape
+        g = grad.view(nh, n_img, R, c1) * g_total.view(1, n_img, 1, 1)
+        return (g.view_as(grad),) + (None,) * 9
+
+
+def head_losses(scores, assigned, labels, k, lmda=(3.0, 1.0), iou_weight=3.0):
+    """Loss block for a batch: `scores` from cls_iou_model.forward_batched, `assigned` the dict returned by
+    mine_and_assign.  Returns dict(total [n_img] (differentiable), cls_loss, iou_loss, bag_loss [n_img] as
+    model_builder.py:198-202 accumulates them (iou_loss already x iou_weight), losses [n_img, K+1, 3])."""
+    total, losses = HeadLossFunction.apply(scores, assigned["pseudo_labels"], assigned["pseudo_iou_labels"],
+                                           assigned["loss_weights"], assigned["valid"], labels, k, lmda[0], lmda[1],
+                                           iou_weight)
+    return dict(total=total, losses=losses, cls_loss=losses[:, :, 0].sum(1), iou_loss=iou_weight * losses[:, :, 1].sum(1),
+                bag_loss=losses[:, :, 2].sum(1))
+
+
 def refine_scores(ref_cls_score, ref_iou_score):
     """testing_function of lib/modeling/model_builder.py:60-68: per head (cls * iou)[:, 1:]."""
     return [(c * i)[:, 1:] for c, i in zip(ref_cls_score, ref_iou_score)]

@@ -206,6 +206,28 @@ int cim_assign(const cim_mine_params *p, const void *iou_f16,
                float *pseudo_labels, void *pseudo_iou_f16, float *loss_weights, uint8_t *valid,
                cim_stream_t stream);
 
+/* ------------------------------------------------------------------ loss block (forward + backward)
+ * cim_head_losses: per image b and refinement layer l < n_layers with valid[l][b] != 0 (the reference skips a
+ *   layer whose CIM_layer returned None, lib/modeling/model_builder.py:189-190):
+ *   heads.cls_iou_loss(ref_cls[l], ref_iou[l], pseudo_labels, pseudo_iou_labels, lmda * loss_weights, labels)
+ *   (lib/modeling/heads.py:78-138, class-specific IoU branch, with loss_weight_bag_loss heads.py:43-74), and
+ *   once per image heads.mil_bag_loss(predict_cls, predict_det, labels) (heads.py:149-166).
+ *   scores        [2+2K, n_img*R, C+1] fp32 as written by cim_score_heads
+ *   pseudo_labels [n_layers, n_img, R, C+1] fp32, pseudo_iou [n_layers, n_img, R] fp16,
+ *   loss_weights  [n_layers, n_img, R] fp32, valid [n_layers, n_img] uint8 (outputs of cim_assign),
+ *   labels        [n_img, C] fp32 image labels;  lmda0 / lmda_rest: multiplier of loss_weights for layer 0 / the
+ *   others (3 / 1, model_builder.py:172,194).
+ *   losses      [n_img, K+1, 3] fp32: (cls_loss, iou_loss, bag_loss) per layer slot (zeros for skipped layers);
+ *               slot K holds (0, 0, mil_bag_loss).  The reference's totals are sum_l cls, iou_weight * sum_l iou
+ *               (iou_weight = 3, model_builder.py:199) and sum_l bag + mil_bag.
+ *   grad_scores [2+2K, n_img*R, C+1] fp32 (may be NULL): grad_scale * d(sum_l cls + iou_weight * sum_l iou +
+ *               sum_l bag + mil_bag of the row's image) / d scores, every element written.
+ * PCL_loss (heads.py:10-41) needs the dataset's cluster matrix and is not covered.  R <= 10240, C + 1 <= 1024. */
+int cim_head_losses(const float *scores, const float *pseudo_labels, const void *pseudo_iou_f16,
+                    const float *loss_weights, const uint8_t *valid, const float *labels, float *losses,
+                    float *grad_scores, int n_img, int R, int C, int K, int n_layers, float lmda0,
+                    float lmda_rest, float iou_weight, float grad_scale, cim_stream_t stream);
+
 /* ------------------------------------------------------------------ test-time post-processing
  * cim_test_scores: lib/core/test.py:130-133 over lib/modeling/model_builder.py:60-68 -- the K refinement
  *   heads' (cls * iou)[:, 1:] summed in head order and divided by K.

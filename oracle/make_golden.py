@@ -306,10 +306,70 @@ def make_nms_fixture():
     np.savez_compressed(os.path.join(GOLD, "box_nms.npz"), **out)
 
 
+def make_loss_fixture(ref_heads):
+    """Loss block: the reference's own heads.cls_iou_loss / heads.mil_bag_loss (imported unmodified) with
+    autograd, wired as model_builder.py:170-202, on the inputs + CIM_layer outputs of stored cim_layer cases."""
+    from oracle import loss_oracle
+    cim = np.load(os.path.join(GOLD, "cim_layer.npz"))
+    out = {}
+    for name in ["voc_r300_l0", "coco_r257", "voc_r128_nan", "voc_r64_none"]:
+        R, c1 = cim[f"{name}/cls"].shape
+        k = 3
+        torch.manual_seed(len(name))
+        model = ref_heads.cls_iou_model(64, c1, k)
+        x = torch.randn(R, 64) * 3
+        p_cls, p_det, r_cls, r_iou = model(x)
+        flat = [p_cls, p_det] + list(r_cls) + list(r_iou)
+        scores = torch.stack([t.detach() for t in flat]).clone()
+        scores[2, 0, 0], scores[2, 1, 1] = 0.0, 1.0                       # values outside the clamp range
+        leaf = scores.clone().requires_grad_(True)
+        labels = torch.from_numpy(cim[f"{name}/labels"]).float().reshape(1, -1)
+        none = f"{name}/none" in cim.files
+        # the same pseudo labels feed all three layers (what matters here is the loss arithmetic); layer 1 is
+        # marked invalid to cover the `continue` at model_builder.py:189-190
+        if none:
+            pl = np.zeros((R, c1), np.float32); pi = np.zeros(R, np.float16); lw = np.zeros(R, np.float32)
+        else:
+            pl, lw = cim[f"{name}/pseudo_labels"], cim[f"{name}/loss_weights"]
+            pi = cim[f"{name}/pseudo_iou_u16"].view(np.float16)
+        valid = np.array([[0 if none else 1], [0], [0 if none else 1]], np.uint8)
+        losses = torch.zeros(1, k + 1, 3)
+        total = torch.zeros(())
+        for l in range(k):
+            if not valid[l, 0]:
+                continue
+            lmda = 3 if l == 0 else 1
+            c, i, g = ref_heads.cls_iou_loss(leaf[2 + l], leaf[2 + k + l], torch.from_numpy(pl),
+                                             torch.from_numpy(pi), lmda * torch.from_numpy(lw), labels)
+            losses[0, l] = torch.stack([c.detach(), i.detach(), g.detach()])
+            total = total + c + 3 * i + g
+        mil = ref_heads.mil_bag_loss(leaf[0], leaf[1], labels)
+        losses[0, k, 2] = mil.detach()
+        (total + mil).backward()
+        pl3 = np.stack([pl] * k)[:, None]
+        pi3 = np.stack([pi] * k)[:, None]
+        lw3 = np.stack([lw] * k)[:, None]
+        o_loss, o_grad = loss_oracle.head_losses(scores.numpy(), pl3, pi3, lw3, valid, labels.numpy(), k)
+        fin = np.isfinite(leaf.grad.numpy())
+        e_l = np.nanmax(np.abs(o_loss - losses.numpy())) / max(np.nanmax(np.abs(losses.numpy())), 1e-3)
+        e_g = np.abs(o_grad - leaf.grad.numpy())[fin].max() / max(np.abs(leaf.grad.numpy()[fin]).max(), 1e-3)
+        assert e_l < 1e-5 and e_g < 1e-5, (name, e_l, e_g)
+        assert np.array_equal(np.isnan(o_grad), np.isnan(leaf.grad.numpy()))
+        print(f"losses {name}: oracle vs reference loss err {e_l:.1e}, grad err {e_g:.1e}, "
+              f"losses {losses.numpy()[0].sum(0)}")
+        for key, v in dict(scores=scores.numpy(), labels=labels.numpy(), pseudo_labels=pl3, pseudo_iou_u16=pi3.view(np.uint16),
+                           loss_weights=lw3, valid=valid, losses=losses.numpy(), grad=leaf.grad.numpy()).items():
+            out[f"{name}/{key}"] = v
+    np.savez_compressed(os.path.join(GOLD, "head_losses.npz"), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     if "--only-nms" in sys.argv:
         make_nms_fixture()
+        return
+    if "--only-losses" in sys.argv:
+        make_loss_fixture(load_reference()[0])
         return
     torch.set_num_threads(4)
     ref_heads, ref_mu = load_reference()
@@ -317,6 +377,7 @@ def main():
     make_heads_fixtures(ref_heads, ref_mu)
     make_scoring_fixture(ref_heads)
     make_nms_fixture()
+    make_loss_fixture(ref_heads)
     if "--fuzz" in sys.argv:
         fuzz(ref_heads, ref_mu, int(sys.argv[sys.argv.index("--fuzz") + 1]))
     print("golden fixtures written to", GOLD)
