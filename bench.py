@@ -2,8 +2,8 @@
 """bench.py -- CIM-head images/s on B200 (BASELINE.json metric).
 
 A step = one pass of the hot path over one batch of synthetic images:
-RoIAlign fwd + RoIAlign bwd + mask IoU/containment + scoring heads fwd + bwd (head gradients, averaged
-over the ranks with one NCCL allreduce when N > 1) + 3 x (mining + assignment).
+RoIAlign fwd + RoIAlign bwd + mask IoU/containment + scoring heads fwd + 3 x (mining + assignment) + the loss
+block (fwd + bwd) + scoring heads bwd (head gradients, averaged over the ranks with one NCCL allreduce when N > 1).
 Workload = BASELINE.json configs[1]: ResNet-50 VOC, 8 images x 2000 mask proposals per GPU
 (512x512 images -> 1024x32x32 features, 512x512 bit-packed proposal masks, 20 classes).
 
@@ -28,7 +28,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "CIM-head images/s (ROIAlign fwd+bwd + mask IoU + scoring fwd+bwd + mining)"
+METRIC = "CIM-head images/s (ROIAlign fwd+bwd + mask IoU + scoring fwd+bwd + mining + losses)"
 WORKLOADS = {
     # name: backbone, images per GPU, proposals, classes, present classes, mask side
     "cfg2_r50_voc_8x2000": dict(backbone="resnet50", n_img=8, R=2000, C=20, present=2, mask=512),
@@ -60,6 +60,8 @@ def algorithmic_bytes(cfg, Cf, H, W):
         # scoring backward: x read, grad_x written, scores and grad_scores read, weights read and head
         # gradients written
         "score_heads_bwd": 2 * R * 4096 * 4 + 2 * 8 * R * (C + 1) * 4 + 2 * 8 * (C + 1) * 4097 * 4,
+        # loss block: scores read, pseudo labels / weights read, grad_scores written
+        "head_losses": 2 * 8 * R * (C + 1) * 4 + 3 * R * (C + 1) * 4 + 3 * R * 6,
     }
 
 
@@ -113,7 +115,7 @@ def cpu_reference(cfg, steps, warmup, sample_rois=128, head_grads=True):
     number of rows processed); scoring and the 3 mining layers at full R."""
     import torch
     from cim_b200 import synth
-    from oracle import heads_oracle, roi_oracle
+    from oracle import heads_oracle, loss_oracle, roi_oracle
     ncpu = os.cpu_count() or 1
     torch.set_num_threads(ncpu)
     R, C, S = cfg["R"], cfg["C"], min(sample_rois, cfg["R"])
@@ -129,7 +131,6 @@ def cpu_reference(cfg, steps, warmup, sample_rois=128, head_grads=True):
     b = [np.zeros(C + 1, np.float32) for _ in range(8)]
     x = np.random.RandomState(2).randn(R, 4096).astype(np.float32)
     labels = synth.image_labels(C, cfg["present"], 1234).numpy()
-    g_scores = [np.random.RandomState(20 + i).randn(R, C + 1).astype(np.float32) for i in range(8)]
     from oracle import mask_oracle
     iou16, asy16 = mask_oracle.mask_overlap_maps(masks[:, ::max(1, masks.shape[1] // 4096)])   # setup only
 
@@ -147,15 +148,25 @@ def cpu_reference(cfg, steps, warmup, sample_rois=128, head_grads=True):
         t_mask = time.perf_counter() - t0
         t0 = time.perf_counter()
         p_cls, p_det, r_cls, r_iou = heads_oracle.score_heads(x, w, b)
-        if head_grads:
-            heads_oracle.score_heads_bwd(x, w, b, g_scores)
         t_score = time.perf_counter() - t0
         t0 = time.perf_counter()
         cls_l, det_l = [p_cls, r_cls[0], r_cls[1]], [p_det, r_iou[0], r_iou[1]]
+        assigned = []
         for l in range(3):
-            heads_oracle.cim_layer_forward(cls_l[l], det_l[l], labels, iou16, asy16, 0.1, 0.25 + 0.1 * l,
-                                           0.5 + 0.1 * l, 0.85, True)
+            assigned.append(heads_oracle.cim_layer_forward(cls_l[l], det_l[l], labels, iou16, asy16, 0.1,
+                                                           0.25 + 0.1 * l, 0.5 + 0.1 * l, 0.85, True))
         t_mine = time.perf_counter() - t0
+        if head_grads:                                   # loss block fwd+bwd, then the scoring backward
+            t0 = time.perf_counter()
+            ok = [a[0] is not None for a in assigned]
+            pl = np.stack([a[0] if o else np.zeros((R, C + 1), np.float32) for a, o in zip(assigned, ok)])[:, None]
+            pi = np.stack([a[1] if o else np.zeros(R, np.float16) for a, o in zip(assigned, ok)])[:, None]
+            lw = np.stack([a[2] if o else np.zeros(R, np.float32) for a, o in zip(assigned, ok)])[:, None]
+            sc = np.stack([p_cls, p_det] + r_cls + r_iou)
+            _, g = loss_oracle.head_losses(sc, pl, pi, lw, np.array(ok, np.uint8)[:, None], labels.reshape(1, -1), 3,
+                                           dtype=torch.float32)
+            heads_oracle.score_heads_bwd(x, w, b, list(g))
+            t_score += time.perf_counter() - t0
         return (t_roi + t_mask) * (R / S) + t_score + t_mine, dict(roi=t_roi * R / S, mask=t_mask * R / S,
                                                                    score=t_score, mine=t_mine)
 
@@ -171,7 +182,7 @@ def cpu_reference(cfg, steps, warmup, sample_rois=128, head_grads=True):
     sec = float(np.mean(per_image))
     return dict(images_per_s=1.0 / sec, sec_per_image=sec, cores=ncpu, wall_s=wall, parts=parts,
                 sample=f"1 image of {cfg['R']} proposals; RoIAlign fwd+bwd and mask overlap on {S} proposal rows "
-                       f"(x{R / S:.1f}), scoring {'fwd+bwd' if head_grads else 'fwd'} + 3 mining layers at full size; "
+                       f"(x{R / S:.1f}), scoring {'fwd+bwd + loss block' if head_grads else 'fwd'} + 3 mining layers at full size; "
                        f"numpy/OpenMP on all host cores")
 
 
@@ -198,9 +209,7 @@ def build_inputs(cfg, dev, seed_base):
     model = heads.cls_iou_model(4096, C + 1, 3).to(dev)
     weight, bias = (t.detach().contiguous() for t in model._stacked())
     labels = torch.cat(labels)
-    grad_scores = torch.randn(8, n_img * R, C + 1, device=dev, generator=gen)
     return dict(feat=feat, rois=torch.cat(rois).to(dev), grad_out=grad_out, packed=torch.stack(packed),
-                grad_scores=grad_scores,
                 packed_flat=torch.stack(packed_flat), kb_per_row=kb_per_row,
                 seg_x=seg_x, weight=weight, bias=bias, labels=labels.to(dev), labels_host=labels.numpy(),
                 shape=(Cf, H, W, scale))
@@ -254,9 +263,13 @@ def time_stages(step, inp, iters=5):
                                                  n_img, R, step.D, step.C + 1, step.K, P(step.score_ws),
                                                  step.score_ws.numel(), st),
         "score_heads_bwd": lambda: L.cim_score_heads_bwd(P(inp["seg_x"]), P(inp["weight"]), P(step.scores),
-                                                         P(inp["grad_scores"]), P(step.grad_seg_x), P(step.grad_weight),
+                                                         P(step.grad_scores), P(step.grad_seg_x), P(step.grad_weight),
                                                          P(step.grad_bias), n_img, R, step.D, step.C + 1, step.K,
                                                          P(step.score_bwd_ws), step.score_bwd_ws.numel(), st),
+        "head_losses": lambda: L.cim_head_losses(P(step.scores), P(step.pseudo_labels), P(step.pseudo_iou),
+                                                 P(step.loss_weights), P(step.valid), P(inp["labels"]), P(step.losses),
+                                                 P(step.grad_scores), n_img, R, step.C, step.K, step.K, 3.0, 1.0, 3.0,
+                                                 1.0 / n_img, st),
         "mine": lambda: L.cim_mine(C.byref(p), step.cls_ptrs, step.det_ptrs, P(inp["labels"]), P(step.iou),
                                    P(step.asy), P(step.gt_count), P(step.gt_rows), P(step.gt_class),
                                    P(step.gt_weight), P(step.asy_flag), P(step.mine_ws), step.mine_ws.numel(), st),
@@ -265,7 +278,7 @@ def time_stages(step, inp, iters=5):
                                        P(step.loss_weights), P(step.valid), st),
     }
     if not step.head_grads:
-        del calls["score_heads_bwd"]
+        del calls["score_heads_bwd"], calls["head_losses"]
     out = {}
     for name, fn in calls.items():
         _lib.check(fn(), name)
@@ -290,7 +303,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-anti-noise", action="store_true")
     ap.add_argument("--no-head-grads", action="store_true",
-                    help="leave the scoring backward (+ the allreduce of the head gradients) out of the step")
+                    help="leave the loss block, the scoring backward and the allreduce of the head gradients out of the step")
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -332,9 +345,8 @@ def main():
     step = CIMHeadStep(cfg["n_img"], cfg["R"], cfg["C"], Cf, H, W, scale, words, anti_noise_sampling=not args.no_anti_noise,
                        max_present=max(4, 2 * cfg["present"]), device=dev, mask_kb_per_row=inp["kb_per_row"],
                        head_grads=not args.no_head_grads)
-    g_scores = None if args.no_head_grads else inp["grad_scores"]
     run = lambda: step.run(inp["feat"], inp["rois"], inp["grad_out"], inp["packed"], inp["seg_x"], inp["weight"],
-                           inp["bias"], inp["labels"], inp["labels_host"], grad_scores=g_scores)
+                           inp["bias"], inp["labels"], inp["labels_host"])
     np.random.seed(3)
     for _ in range(max(args.warmup, 3)):
         run()
@@ -366,8 +378,7 @@ def main():
     step.hi_rois.copy_(inp["rois"])
     step.hi_labels.copy_(inp["labels"])
     step.set_host_crops(crops)
-    run_host = lambda: step.run_host(inp["feat"], inp["grad_out"], inp["seg_x"], inp["weight"], inp["bias"],
-                                     grad_scores=g_scores)
+    run_host = lambda: step.run_host(inp["feat"], inp["grad_out"], inp["seg_x"], inp["weight"], inp["bias"])
     for _ in range(2):
         run_host()
     cdist.barrier()
@@ -388,7 +399,7 @@ def main():
 
     bytes_img = algorithmic_bytes(cfg, Cf, H, W)
     if args.no_head_grads:
-        del bytes_img["score_heads_bwd"]
+        del bytes_img["score_heads_bwd"], bytes_img["head_losses"]
     stage_ms = dict(stages)
     stage_ms["mine_assign"] = stage_ms.pop("mine") + stage_ms.pop("assign")
     table = {}

@@ -112,16 +112,24 @@ class cls_iou_model(nn.Module):
 def _anti_noise_keep(gt_cls, gt_w, present):
     """heads.py:451-466 on the host: per present class (ascending) with at least one pseudo GT,
     np.random.choice(class_idx, size=n, replace=True, p=w / w.sum()) from the GLOBAL numpy RNG;
-    the unique draws survive."""
+    the unique draws survive.
+
+    The draw is spelled out the way RandomState.choice makes it for replace=True with p given
+    (numpy/random/mtrand.pyx: cdf = p.cumsum(); cdf /= cdf[-1]; uniform = random_sample(n);
+    idx = cdf.searchsorted(uniform, side='right')): it consumes the same n doubles of the global stream and
+    returns the same indices, without choice()'s argument validation, which is 2/3 of its cost at these sizes
+    (this hop sits on the step's critical path).  tests/test_host_logic.py checks the equivalence."""
     keep = np.ones(gt_cls.shape[0], dtype=np.uint8)
     for c in present:
         class_idx = np.nonzero(gt_cls == c)[0]
         if len(class_idx) == 0:
             continue
         prob = gt_w[class_idx]
-        drawn = np.random.choice(class_idx, size=len(class_idx), replace=True, p=prob / prob.sum())
+        cdf = (prob / prob.sum()).astype(np.float64).cumsum()
+        cdf /= cdf[-1]
+        drawn = class_idx[cdf.searchsorted(np.random.random_sample(len(class_idx)), side="right")]
         keep[class_idx] = 0
-        keep[np.unique(drawn)] = 1
+        keep[drawn] = 1
     return keep
 
 

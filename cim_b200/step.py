@@ -31,8 +31,9 @@ from .heads import _anti_noise_keep
 #: kernels (not memsets / copies) libcimhead launches in one run(): roi_align fwd 3 + bwd 3,
 #: mask area + sort + overlap + 2 un-permutes = 5, scoring 3, mining 3, assignment 1
 KERNELS_PER_STEP = 18
-#: + with grad_scores: detector dot, activation backward, bias, W^T split, grad_x GEMM, grad_W GEMM, reduce
-KERNELS_HEAD_GRADS = 7
+#: + with head_grads: loss block (fwd + bwd), detector dot, activation backward, bias, W^T split, grad_x GEMM,
+#: grad_W GEMM, reduce
+KERNELS_HEAD_GRADS = 8
 
 
 class CIMHeadStep:
@@ -72,6 +73,8 @@ class CIMHeadStep:
                 self.grad_seg_x = e((n_img * R, feat_dim), torch.float32)
                 self.score_bwd_ws = e((self.L.cim_score_heads_bwd_workspace_bytes(n_img, R, feat_dim, C1, k),),
                                       torch.uint8)
+                self.losses = e((n_img, k + 1, 3), torch.float32)
+                self.grad_scores = e((nh, n_img * R, C1), torch.float32)
             p = _lib.MineParams()
             p.n_img, p.R, p.C, p.C1, p.n_layers = n_img, R, n_classes, C1, k
             p.det_cols, p.gt_cap, p.mode = C1, R, 0
@@ -114,10 +117,12 @@ class CIMHeadStep:
         f32, packed_masks [n_img,R,words] i32, seg_x [n_img*R,D] f32, weight [2+2K,C+1,D],
         bias [2+2K,C+1], labels [n_img,C] f32 (+ the same on the host as a numpy array).
         Results land in self.roi_out, grad_feat, iou, asy, scores, pseudo_labels, pseudo_iou,
-        loss_weights, valid.  With head_grads=True and grad_scores [2+2K, n_img*R, C+1] (dL/dscores, what
-        the losses' backward hands over) also grad_seg_x, grad_weight, grad_bias; in a multi-process run
-        the head-gradient bucket is averaged over the ranks (one NCCL allreduce, overlapped with the
-        RoIAlign kernels)."""
+        loss_weights, valid.  With head_grads=True also losses [n_img, K+1, 3], grad_scores (the loss
+        block's backward; pass grad_scores to supply dL/dscores yourself instead), grad_seg_x, grad_weight,
+        grad_bias; in a multi-process run the head-gradient bucket is averaged over the ranks (one NCCL
+        allreduce, overlapped with the RoIAlign backward).
+        Order: mask maps, scores, mining | host sampling hop, hidden behind the RoIAlign forward | assignment,
+        losses, scoring backward, [allreduce ||] RoIAlign backward."""
         L, p, dev = self.L, self.p, self.dev
         P, n_img, R, k = _lib.ptr, self.n_img, self.R, self.K
         st = _lib.stream_ptr(dev)
@@ -130,12 +135,6 @@ class CIMHeadStep:
         ck(L.cim_mine(C.byref(p), self.cls_ptrs, self.det_ptrs, P(labels), P(self.iou), P(self.asy),
                       P(self.gt_count), P(self.gt_rows), P(self.gt_class), P(self.gt_weight), P(self.asy_flag),
                       P(self.mine_ws), self.mine_ws.numel(), st), "cim_mine")
-        reduce_work = None
-        if self.head_grads and grad_scores is not None:
-            ck(L.cim_score_heads_bwd(P(seg_x), P(weight), P(self.scores), P(grad_scores), P(self.grad_seg_x),
-                                     P(self.grad_weight), P(self.grad_bias), n_img, R, self.D, self.C + 1, k,
-                                     P(self.score_bwd_ws), self.score_bwd_ws.numel(), st), "cim_score_heads_bwd")
-            reduce_work = cdist.allreduce_mean_async_(self.head_bucket)
         if self.anti:
             self.h_count.copy_(self.gt_count, non_blocking=True)
             self.h_class.copy_(self.gt_class[:, :, :self.cap], non_blocking=True)
@@ -144,9 +143,6 @@ class CIMHeadStep:
         ck(L.cim_roi_align_fwd(P(feat), P(rois), P(self.roi_out), n_img, self.Cf, self.H, self.W, n_img * R, 7, 7,
                                self.scale, self.sr, self.aligned, P(self.roi_ws), self.roi_ws.numel(), st),
            "cim_roi_align_fwd")
-        ck(L.cim_roi_align_bwd(P(grad_out), P(rois), P(self.grad_feat), n_img, self.Cf, self.H, self.W, n_img * R,
-                               7, 7, self.scale, self.sr, self.aligned, P(self.roi_ws), self.roi_ws.numel(), st),
-           "cim_roi_align_bwd")
         keep = None
         if self.anti:
             self.ev.synchronize()                               # mining is done; RoIAlign still runs
@@ -166,6 +162,22 @@ class CIMHeadStep:
         ck(L.cim_assign(C.byref(p), P(self.iou), P(self.gt_count), P(self.gt_rows), P(self.gt_class),
                         P(self.gt_weight), P(keep), P(self.pseudo_labels), P(self.pseudo_iou),
                         P(self.loss_weights), P(self.valid), st), "cim_assign")
+        reduce_work = None
+        if self.head_grads:
+            if grad_scores is None:
+                # losses forward + backward (model_builder.py:170-202): total of an image = sum_l cls + 3 iou + bag
+                # + mil_bag; the batch loss is the mean over this rank's images
+                ck(L.cim_head_losses(P(self.scores), P(self.pseudo_labels), P(self.pseudo_iou), P(self.loss_weights),
+                                     P(self.valid), P(labels), P(self.losses), P(self.grad_scores), n_img, R, self.C,
+                                     k, k, 3.0, 1.0, 3.0, 1.0 / n_img, st), "cim_head_losses")
+                grad_scores = self.grad_scores
+            ck(L.cim_score_heads_bwd(P(seg_x), P(weight), P(self.scores), P(grad_scores), P(self.grad_seg_x),
+                                     P(self.grad_weight), P(self.grad_bias), n_img, R, self.D, self.C + 1, k,
+                                     P(self.score_bwd_ws), self.score_bwd_ws.numel(), st), "cim_score_heads_bwd")
+            reduce_work = cdist.allreduce_mean_async_(self.head_bucket)         # overlaps the RoIAlign backward
+        ck(L.cim_roi_align_bwd(P(grad_out), P(rois), P(self.grad_feat), n_img, self.Cf, self.H, self.W, n_img * R,
+                               7, 7, self.scale, self.sr, self.aligned, P(self.roi_ws), self.roi_ws.numel(), st),
+           "cim_roi_align_bwd")
         if reduce_work is not None:
             reduce_work()                                       # current stream waits for the allreduce
         return self

@@ -1,0 +1,108 @@
+"""CIMHeadStep (the fused per-batch call bench.py times) end to end against the oracle: every result buffer of
+one step -- RoIAlign fwd/bwd, maps, scores, pseudo labels, losses, head gradients -- at a small size."""
+import numpy as np
+import pytest
+import torch
+
+from cim_b200 import heads, mask_ops, synth
+from cim_b200.step import CIMHeadStep
+from oracle import heads_oracle, loss_oracle, mask_oracle, roi_oracle
+from conftest import assert_f16_bits_equal
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def rel(got, want):
+    return float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-3))
+
+
+@pytest.mark.parametrize("anti", [True, False])
+def test_step_matches_oracle_stage_by_stage(anti):
+    n_img, R, C, k, D = 2, 192, 20, 3, 256
+    size, Cf = 128, 64
+    H = W = size // 16
+    gen = torch.Generator().manual_seed(5)
+    feat = torch.randn(n_img, Cf, H, W, generator=gen)
+    grad_out = torch.randn(n_img * R, Cf, 7, 7, generator=gen)
+    seg_x = torch.randn(n_img * R, D, generator=gen) * 3
+    rois, masks, labels = [], [], []
+    for b in range(n_img):
+        params = synth.proposal_params(R, size, 40 + b)
+        rois.append(synth.rois_from_params(params, b))
+        masks.append(synth.rasterize(params))
+        labels.append(synth.image_labels(C, 2, 40 + b))
+    rois, labels = torch.cat(rois), torch.cat(labels)
+    packed = torch.stack([mask_ops.mask_pack(m.to(DEV)) for m in masks])
+    torch.manual_seed(1)
+    model = heads.cls_iou_model(D, C + 1, k).to(DEV)
+    weight, bias = (t.detach().contiguous() for t in model._stacked())
+    step = CIMHeadStep(n_img, R, C, Cf, H, W, 1.0 / 16, packed.shape[-1], feat_dim=D, anti_noise_sampling=anti,
+                       device=DEV, mask_kb_per_row=size // 16 if mask_ops.tiled_ok(size, size) else 0, head_grads=True)
+    np.random.seed(3)
+    step.run(feat.to(DEV), rois.to(DEV), grad_out.to(DEV), packed, seg_x.to(DEV), weight, bias, labels.to(DEV),
+             labels.numpy())
+    torch.cuda.synchronize()
+
+    want = roi_oracle.roi_align_fwd(feat.numpy(), rois.numpy(), 7, 7, 1.0 / 16, 0, True)
+    assert rel(step.roi_out.cpu().numpy(), want) < 1e-5
+    want = roi_oracle.roi_align_bwd(grad_out.numpy(), rois.numpy(), feat.shape, 1.0 / 16, 0, True)
+    assert rel(step.grad_feat.cpu().numpy(), want) < 1e-5
+
+    maps = [mask_oracle.mask_overlap_maps(m.numpy()) for m in masks]
+    for b in range(n_img):
+        assert_f16_bits_equal(step.iou[b].cpu().numpy().view(np.uint16), maps[b][0].view(np.uint16))
+        assert_f16_bits_equal(step.asy[b].cpu().numpy().view(np.uint16), maps[b][1].view(np.uint16))
+
+    w_np, b_np = weight.cpu().numpy(), bias.cpu().numpy()
+    scores = step.scores.cpu().numpy()
+    for b in range(n_img):
+        o = heads_oracle.score_heads(seg_x[b * R:(b + 1) * R].numpy(), list(w_np), list(b_np))
+        np.testing.assert_allclose(scores[:, b * R:(b + 1) * R], np.stack([o[0], o[1]] + o[2] + o[3]), rtol=1e-5,
+                                   atol=1e-7)
+
+    # mining + assignment: the oracle consumes the GPU scores (bit-exact decisions need identical inputs) and the
+    # same numpy stream in the reference's order (image, layer)
+    s4 = scores.reshape(2 + 2 * k, n_img, R, C + 1)
+    cls_l, det_l = [s4[0], s4[2], s4[3]], [s4[1], s4[5], s4[6]]
+    np.random.seed(3)
+    pl = np.zeros((k, n_img, R, C + 1), np.float32)
+    pi = np.zeros((k, n_img, R), np.float16)
+    lw = np.zeros((k, n_img, R), np.float32)
+    valid = np.zeros((k, n_img), np.uint8)
+    for b in range(n_img):
+        for l in range(k):
+            o = heads_oracle.cim_layer_forward(cls_l[l][b], det_l[l][b], labels[b:b + 1].numpy(), maps[b][0], maps[b][1],
+                                               0.1, 0.25 + 0.1 * l, 0.5 + 0.1 * l, 0.85, anti)
+            if o[0] is None:
+                continue
+            valid[l, b], pl[l, b], pi[l, b], lw[l, b] = 1, o[0], o[1], o[2]
+    np.testing.assert_array_equal(step.valid.cpu().numpy(), valid)
+    assert valid.any()
+    for l in range(k):
+        for b in range(n_img):
+            if valid[l, b]:
+                np.testing.assert_array_equal(step.pseudo_labels[l, b].cpu().numpy(), pl[l, b])
+                assert_f16_bits_equal(step.pseudo_iou[l, b].cpu().numpy().view(np.uint16), pi[l, b].view(np.uint16))
+                np.testing.assert_array_equal(step.loss_weights[l, b].cpu().numpy(), lw[l, b])
+
+    # losses + head gradients (batch loss = mean over the images)
+    o_loss, o_grad = loss_oracle.head_losses(scores, pl, pi, lw, valid, labels.numpy(), k, grad_scale=1.0 / n_img)
+    got_loss = step.losses.cpu().numpy()
+    np.testing.assert_array_equal(np.isnan(got_loss), np.isnan(o_loss))
+    np.testing.assert_allclose(np.nan_to_num(got_loss), np.nan_to_num(o_loss), rtol=2e-5, atol=1e-7)
+    fin = np.isfinite(o_grad)
+    if fin.all():
+        assert rel(step.grad_scores.cpu().numpy(), o_grad) < 1e-5
+        gx = np.zeros((n_img * R, D), np.float64)
+        gw = np.zeros(w_np.shape, np.float64)
+        gb = np.zeros(b_np.shape, np.float64)
+        for b in range(n_img):
+            sl = slice(b * R, (b + 1) * R)
+            ox, ow, ob = heads_oracle.score_heads_bwd(seg_x[sl].numpy(), list(w_np), list(b_np), list(o_grad[:, sl]))
+            gx[sl] = ox
+            gw += np.stack(ow)
+            gb += np.stack(ob)
+        assert rel(step.grad_seg_x.cpu().numpy(), gx) < 2e-5
+        assert rel(step.grad_weight.cpu().numpy(), gw) < 2e-5
+        assert rel(step.grad_bias.cpu().numpy(), gb) < 2e-5

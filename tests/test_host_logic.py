@@ -62,6 +62,29 @@ def test_anti_noise_sampling_consumes_rng_like_the_oracle():
     assert a[gt_cls == 1].all()
 
 
+def test_anti_noise_draw_equals_numpy_choice_on_many_cases():
+    """The spelled-out draw of heads._anti_noise_keep against np.random.choice itself (what the reference calls,
+    heads.py:459, and what the oracle calls): same survivors, same RNG state afterwards, over sizes from one
+    pseudo GT to several hundred, skewed and near-degenerate weights included."""
+    rng = np.random.RandomState(17)
+    for case in range(300):
+        g = int(rng.choice([1, 2, 3, 7, 40, 200, 800]))
+        n_cls = int(rng.randint(1, 6))
+        gt_cls = rng.randint(0, n_cls, g)
+        gt_w = rng.rand(g).astype(np.float32) ** int(rng.choice([1, 4, 12]))
+        gt_w = np.maximum(gt_w, np.float32(1e-30))
+        labels = np.zeros(20, np.float32)
+        labels[:n_cls] = 1
+        np.random.seed(case)
+        a = heads._anti_noise_keep(gt_cls, gt_w, np.nonzero(labels)[0])
+        state_a = np.random.get_state()[1].copy(), np.random.get_state()[2]
+        np.random.seed(case)
+        b = heads_oracle.anti_noise_keep(gt_cls, gt_w, labels)
+        state_b = np.random.get_state()[1].copy(), np.random.get_state()[2]
+        assert a.astype(bool).tolist() == b.tolist(), case
+        assert state_a[1] == state_b[1] and np.array_equal(state_a[0], state_b[0]), case
+
+
 def test_host_evaluated_parameters():
     for r in (64, 300, 2000, 4000, 257):
         assert int(np.ceil(0.1 * r)) == {64: 7, 300: 30, 2000: 200, 4000: 400, 257: 26}[r]
