@@ -53,6 +53,7 @@ struct RoiWs {
     int *hdr;          // [64]
     int *img_start;    // [B+1]
     int *desc;         // [K][DESC_WORDS]
+    float *maskpad;    // [K][52]  fused MaskFuse backward: the ROI masks padded to 208 B rows
 };
 
 __host__ __device__ inline size_t ws_img_off() { return WS_HDR_BYTES; }
@@ -353,7 +354,8 @@ constexpr int FWD_DESC_WORDS = DESC_WORDS;
 __global__ void __launch_bounds__(FWD_MAX_WARPS * 32, 1)
 roi_align_fwd_tile_kernel(const float *__restrict__ feat, const int *__restrict__ hdr,
                           const int *__restrict__ img_start, const int *__restrict__ descs,
-                          float *__restrict__ out, int B, int C, int H, int W, int pitch, int wyd_floats) {
+                          const float *__restrict__ mask7, float *__restrict__ out, int B, int C, int H, int W,
+                          int pitch, int wyd_floats) {
     extern __shared__ __align__(128) float smem[];
     const int nw = blockDim.x >> 5;
     float *tile = smem;
@@ -419,9 +421,28 @@ roi_align_fwd_tile_kernel(const float *__restrict__ feat, const int *__restrict_
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
+                // MaskFuse prologue (mask7 != null): out is [K][2C][49], channels [0, C) = the pooled features,
+                // [C, 2C) = the same times the ROI's 7 x 7 mask (lib/modeling/resnet50.py:131-134)
+                const size_t orow = mask7 ? (size_t)roi * 2 * C : (size_t)roi * C;
                 if (lane == 0) {
-                    bulk_s2g(out + ((size_t)roi * C + c0) * NBIN, stage_w, STAGE_FLOATS * 4);
+                    bulk_s2g(out + (orow + c0) * NBIN, stage_w, STAGE_FLOATS * 4);
                     bulk_commit();
+                }
+                if (mask7) {
+                    float m[NBIN];
+                    const float *mp = mask7 + (size_t)roi * NBIN;
+#pragma unroll
+                    for (int i = 0; i < NBIN; ++i) m[i] = __ldg(mp + i);
+                    if (lane == 0) bulk_wait_read<0>();        // the stage has been read by the store above
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < NBIN; ++i) stage_c[i] *= m[i];
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        bulk_s2g(out + (orow + C + c0) * NBIN, stage_w, STAGE_FLOATS * 4);
+                        bulk_commit();
+                    }
                 }
             }
             __syncwarp();                      // slot is re-filled two iterations from now
@@ -439,13 +460,22 @@ constexpr int NWB = 16;             // consumer warps of the backward CTA; warp 
 constexpr int NBR = 4;              // ROIs per ring slot: one full/empty barrier round per 4 ROIs
 constexpr int NS = 3;               // ring slots
 constexpr int SLOT_FLOATS = NBR * (STAGE_FLOATS + DESC_WORDS);
+// fused MaskFuse backward: two gradient blocks per ROI (d/d pooled, d/d pooled*mask)
+// and the ROI's 7 x 7 mask (padded to 52 floats = 208 B so that it can travel by cp.async.bulk); the owners fold
+// g + g2 * mask while they read the gradient in their y pass
+constexpr int MASK_PAD = 52;
+constexpr int NBR_F = 2, NS_F = 3;
+constexpr int SLOT_FLOATS_F = NBR_F * (2 * STAGE_FLOATS + DESC_WORDS + MASK_PAD);
 
 // One ROI x 32 channels x the row pairs this warp owns.  Per owned pair p:
 //   y pass: r[pw] = sum_ph (wy[ph][2p], wy[ph][2p+1]) * g[ph][pw]   over the bins D_PHR lists for the pair
 //   x pass: (t[2p][xo+l], t[2p+1][xo+l]) += wx[pw][l] * r[pw]       7T x (LDS.64, FFMA2, STS.64)
-template <int T, bool XINC>
+// FUSED (MaskFuse prologue): the gradient of the pooled value is g[ph][pw] + g2[ph][pw] * m[ph][pw] with g2 the
+// gradient block of the masked copy (STAGE_FLOATS further on in the slot) and m the ROI's 7 x 7 mask (smem).
+template <int T, bool XINC, bool FUSED>
 __device__ __forceinline__ void bwd_pairs(float *__restrict__ tile_c, int W, const int *d,
-                                          const float *__restrict__ g, int warp, int y0, int y1) {
+                                          const float *__restrict__ g, const float *__restrict__ m, int warp, int y0,
+                                          int y1) {
     float wx[PW][T];
     int xo[PW];
     const float *dwx = reinterpret_cast<const float *>(d + D_WX);
@@ -481,7 +511,11 @@ __device__ __forceinline__ void bwd_pairs(float *__restrict__ tile_c, int W, con
             const float2 w = make_float2(dwy[ph * WYP + dd + 1], dwy[ph * WYP + dd + 2]);
             const float *gp = g + ph * PW;
 #pragma unroll
-            for (int pw = 0; pw < PW; ++pw) r[pw] = __ffma2_rn(bcast2(gp[pw]), w, r[pw]);
+            for (int pw = 0; pw < PW; ++pw) {
+                float gv = gp[pw];
+                if (FUSED) gv = fmaf(gp[STAGE_FLOATS + pw], m[ph * PW + pw], gv);
+                r[pw] = __ffma2_rn(bcast2(gv), w, r[pw]);
+            }
         }
         float2 *row = tile2 + p * W;
         if (XINC) {
@@ -536,13 +570,23 @@ __device__ __forceinline__ void red_add4(float *gptr, float a, float b, float c,
 // smem tile, apply the ROIs of the segment, add the tile to grad_feat with red.global.add.  grad_feat
 // is zeroed beforehand and every tile is touched by at most TWO CTAs (a CTA's share is larger than one
 // tile), i.e. each element is 0 + a (+ b): exact and independent of the order -> still bit-reproducible.
+// FUSED (MaskFuse prologue): grad_out is [K][2C][49]; the effective gradient of the pooled features is
+// g[c] + g[C + c] * mask[roi].  Both gradient blocks and the (padded) mask of a ROI travel in the ring slot;
+// mask7 points at the PADDED masks [K][MASK_PAD] in the workspace.
+template <bool FUSED>
 __global__ void __launch_bounds__(NWB * 32, 1)
 roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restrict__ hdr,
                           const int *__restrict__ img_start, const int *__restrict__ descs,
-                          float *__restrict__ grad_feat, int B, int C, int H, int W, int pitch) {
+                          const float *__restrict__ mask7, float *__restrict__ grad_feat, int B, int C, int H, int W,
+                          int pitch) {
+    constexpr int NBR = FUSED ? NBR_F : ::NBR;               // ROIs per slot
+    constexpr int NS = FUSED ? NS_F : ::NS;                  // ring slots
+    constexpr int GSTRIDE = FUSED ? 2 * STAGE_FLOATS : STAGE_FLOATS;      // gradient floats per ROI in a slot
+    constexpr int SLOT_FLOATS = NBR * (GSTRIDE + DESC_WORDS + (FUSED ? MASK_PAD : 0));
+    const int Cg = FUSED ? 2 * C : C;                         // channels of grad_out
     extern __shared__ __align__(128) float smem[];
     float *tile = smem;
-    float *ring = smem + (size_t)CH * pitch;                 // [NS][NBR x 1568 grads | NBR x DESC_WORDS]
+    float *ring = smem + (size_t)CH * pitch;                 // [NS][NBR x grads | NBR x DESC_WORDS]
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)NS * SLOT_FLOATS);
     uint64_t *empty = full + NS;
     if (__ldg(hdr) != 0) return;              // rois not grouped by image: the generic kernel does it all
@@ -612,12 +656,17 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
                 }
                 float *slot = ring + (size_t)s * SLOT_FLOATS;
                 const int first = (issued - gb0) * NBR, cnt = min(NBR, n - first);
-                mbar_expect_tx(&full[s], (uint32_t)cnt * (STAGE_FLOATS + DESC_WORDS) * 4);
-                for (int j = 0; j < cnt; ++j)
-                    bulk_g2s(slot + j * STAGE_FLOATS, grad_out + ((size_t)(first_roi + first + j) * C + c0) * NBIN,
-                             STAGE_FLOATS * 4, &full[s]);
-                bulk_g2s(slot + NBR * STAGE_FLOATS, descs + (size_t)(first_roi + first) * DESC_WORDS,
+                mbar_expect_tx(&full[s], (uint32_t)cnt * (GSTRIDE + DESC_WORDS + (FUSED ? MASK_PAD : 0)) * 4);
+                for (int j = 0; j < cnt; ++j) {
+                    const float *src = grad_out + ((size_t)(first_roi + first + j) * Cg + c0) * NBIN;
+                    bulk_g2s(slot + j * GSTRIDE, src, STAGE_FLOATS * 4, &full[s]);
+                    if (FUSED) bulk_g2s(slot + j * GSTRIDE + STAGE_FLOATS, src + (size_t)C * NBIN, STAGE_FLOATS * 4, &full[s]);
+                }
+                bulk_g2s(slot + NBR * GSTRIDE, descs + (size_t)(first_roi + first) * DESC_WORDS,
                          (uint32_t)cnt * DESC_WORDS * 4, &full[s]);
+                if (FUSED)
+                    bulk_g2s(slot + NBR * (GSTRIDE + DESC_WORDS), mask7 + (size_t)(first_roi + first) * MASK_PAD,
+                             (uint32_t)cnt * MASK_PAD * 4, &full[s]);
                 ++issued;
             }
         };
@@ -630,7 +679,7 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
             const float *slot = ring + (size_t)s * SLOT_FLOATS;
             const int cnt = min(NBR, n - bi * NBR);
             // which of the slot's ROIs touch a row pair of this warp (lane j looks at ROI j)
-            const int *dbase = reinterpret_cast<const int *>(slot + NBR * STAGE_FLOATS);
+            const int *dbase = reinterpret_cast<const int *>(slot + NBR * GSTRIDE);
             bool mine = false;
             if (lane < cnt) {
                 const int2 ff = *reinterpret_cast<const int2 *>(dbase + lane * DESC_WORDS + D_XINC);   // (xinc, own)
@@ -643,23 +692,24 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
                 const int *d = dbase + j * DESC_WORDS;
                 const int2 yr = *reinterpret_cast<const int2 *>(d + D_Y0);
                 const int y0 = yr.x, y1 = yr.y;
-                const float *g = slot + j * STAGE_FLOATS + lane * NBIN;
+                const float *g = slot + j * GSTRIDE + lane * NBIN;
+                const float *m = slot + NBR * (GSTRIDE + DESC_WORDS) + j * MASK_PAD;
                 const int T = d[D_TX];
                 if (d[D_XINC]) {
                     switch (T) {
-                        case 2: bwd_pairs<2, true>(tile_c, W, d, g, warp, y0, y1); break;
-                        case 3: bwd_pairs<3, true>(tile_c, W, d, g, warp, y0, y1); break;
-                        case 4: bwd_pairs<4, true>(tile_c, W, d, g, warp, y0, y1); break;
-                        case 6: bwd_pairs<6, true>(tile_c, W, d, g, warp, y0, y1); break;
-                        default: bwd_pairs<8, true>(tile_c, W, d, g, warp, y0, y1); break;
+                        case 2: bwd_pairs<2, true, FUSED>(tile_c, W, d, g, m, warp, y0, y1); break;
+                        case 3: bwd_pairs<3, true, FUSED>(tile_c, W, d, g, m, warp, y0, y1); break;
+                        case 4: bwd_pairs<4, true, FUSED>(tile_c, W, d, g, m, warp, y0, y1); break;
+                        case 6: bwd_pairs<6, true, FUSED>(tile_c, W, d, g, m, warp, y0, y1); break;
+                        default: bwd_pairs<8, true, FUSED>(tile_c, W, d, g, m, warp, y0, y1); break;
                     }
                 } else {
                     switch (T) {
-                        case 2: bwd_pairs<2, false>(tile_c, W, d, g, warp, y0, y1); break;
-                        case 3: bwd_pairs<3, false>(tile_c, W, d, g, warp, y0, y1); break;
-                        case 4: bwd_pairs<4, false>(tile_c, W, d, g, warp, y0, y1); break;
-                        case 6: bwd_pairs<6, false>(tile_c, W, d, g, warp, y0, y1); break;
-                        default: bwd_pairs<8, false>(tile_c, W, d, g, warp, y0, y1); break;
+                        case 2: bwd_pairs<2, false, FUSED>(tile_c, W, d, g, m, warp, y0, y1); break;
+                        case 3: bwd_pairs<3, false, FUSED>(tile_c, W, d, g, m, warp, y0, y1); break;
+                        case 4: bwd_pairs<4, false, FUSED>(tile_c, W, d, g, m, warp, y0, y1); break;
+                        case 6: bwd_pairs<6, false, FUSED>(tile_c, W, d, g, m, warp, y0, y1); break;
+                        default: bwd_pairs<8, false, FUSED>(tile_c, W, d, g, m, warp, y0, y1); break;
                     }
                 }
             }
@@ -723,11 +773,14 @@ __device__ __forceinline__ bool corners(int H, int W, float y, float x, int &y0,
 }
 
 // mode: 0 = every ROI; 1 = only ROIs the tile kernel skipped (flagged, or all if ungrouped)
+// mask7 != null: the fused MaskFuse layout -- the ROI-side tensor is [K][2C][oh][ow] (second half = first half
+// times the ROI's oh x ow mask)
 template <bool BWD>
 __global__ void roi_align_generic_kernel(const float *__restrict__ in, const float *__restrict__ rois,
                                          float *__restrict__ outp, const int *__restrict__ hdr,
-                                         const int *__restrict__ descs, int mode, int B, int C, int H,
-                                         int W, int K, int oh, int ow, float scale, int sr, int aligned) {
+                                         const int *__restrict__ descs, const float *__restrict__ mask7, int mode,
+                                         int B, int C, int H, int W, int K, int oh, int ow, float scale, int sr,
+                                         int aligned) {
     const int k = blockIdx.x;
     if (mode == 1 && __ldg(hdr) == 0) {
         const int *d = descs + (size_t)k * DESC_WORDS;
@@ -738,11 +791,16 @@ __global__ void roi_align_generic_kernel(const float *__restrict__ in, const flo
     const bool valid_b = g.b >= 0 && g.b < B;
     for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < per_roi; e += gridDim.y * blockDim.x) {
         const int pw = e % ow, ph = (e / ow) % oh, c = e / (ow * oh);
-        const size_t oidx = (size_t)k * per_roi + e;
-        if (!valid_b) { if (!BWD) outp[oidx] = 0.f; continue; }
+        const size_t oidx = mask7 ? (size_t)k * 2 * per_roi + e : (size_t)k * per_roi + e;
+        const float mk = mask7 ? __ldg(mask7 + (size_t)k * oh * ow + ph * ow + pw) : 0.f;
+        if (!valid_b) {
+            if (!BWD) { outp[oidx] = 0.f; if (mask7) outp[oidx + per_roi] = 0.f; }
+            continue;
+        }
         const size_t plane = ((size_t)g.b * C + c) * H * W;
         float acc = 0.f;
-        const float top = BWD ? in[oidx] : 0.f;
+        float top = BWD ? in[oidx] : 0.f;
+        if (BWD && mask7) top = fmaf(in[oidx + per_roi], mk, top);
         for (int iy = 0; iy < g.gh; ++iy) {
             const float y = sample_coord(g.ys, g.bh, ph, iy, g.gh);
             for (int ix = 0; ix < g.gw; ++ix) {
@@ -762,15 +820,27 @@ __global__ void roi_align_generic_kernel(const float *__restrict__ in, const flo
                 }
             }
         }
-        if (!BWD) outp[oidx] = acc / g.count;
+        if (!BWD) {
+            const float v = acc / g.count;
+            outp[oidx] = v;
+            if (mask7) outp[oidx + per_roi] = v * mk;
+        }
     }
+}
+
+// masks [K][n] -> [K][MASK_PAD] (zero padded) for the fused backward's bulk copies
+__global__ void roi_mask_pad_kernel(const float *__restrict__ m, float *__restrict__ out, int K, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K * MASK_PAD) return;
+    const int k = i / MASK_PAD, j = i - k * MASK_PAD;
+    out[i] = j < n ? m[(size_t)k * n + j] : 0.f;
 }
 
 // ------------------------------------------------------------------------------------- host
 struct Plan {
     bool tile;
     int pitch, fwd_warps, wyd_floats;
-    size_t smem_fwd, smem_bwd;
+    size_t smem_fwd, smem_bwd, smem_bwd_fused;
 };
 static Plan make_plan(int C, int H, int W, int oh, int ow) {
     Plan p{};
@@ -785,8 +855,9 @@ static Plan make_plan(int C, int H, int W, int oh, int ow) {
     while (p.fwd_warps > 4 && (size_t)CH * p.pitch * 4 + p.fwd_warps * per_warp > cap) --p.fwd_warps;
     p.smem_fwd = (size_t)CH * p.pitch * 4 + p.fwd_warps * per_warp;
     p.smem_bwd = (size_t)CH * p.pitch * 4 + (size_t)NS * SLOT_FLOATS * 4 + 2 * NS * 8;
+    p.smem_bwd_fused = (size_t)CH * p.pitch * 4 + (size_t)NS_F * SLOT_FLOATS_F * 4 + 2 * NS_F * 8;
     p.tile = oh == PH && ow == PW && (C % CH) == 0 && W >= MAXT && p.smem_fwd <= cap &&
-             p.smem_bwd <= cap && (((size_t)CH * p.pitch * 4) % 16 == 0);
+             p.smem_bwd <= cap && p.smem_bwd_fused <= cap && (((size_t)CH * p.pitch * 4) % 16 == 0);
     return p;
 }
 
@@ -800,12 +871,13 @@ static int check_args(const void *a, const void *rois, const void *c, int B, int
     return CIM_OK;
 }
 
-static RoiWs carve(void *ws, int B) {
+static RoiWs carve(void *ws, int B, int K) {
     RoiWs w;
     char *p = (char *)ws;
     w.hdr = (int *)p;
     w.img_start = (int *)(p + ws_img_off());
     w.desc = (int *)(p + ws_desc_off(B));
+    w.maskpad = (float *)(p + ws_desc_off(4096) + (size_t)(K > 0 ? K : 0) * DESC_WORDS * 4);
     return w;
 }
 
@@ -824,23 +896,23 @@ static int run_prep(const float *rois, int B, int H, int W, int K, int oh, int o
 
 CIM_API size_t cim_roi_align_workspace_bytes(int K) {
     // header + image ranges (up to 4096 images) + descriptors
-    return WS_HDR_BYTES + 4097 * sizeof(int) + 64 + (size_t)(K > 0 ? K : 0) * DESC_WORDS * 4;
+    return WS_HDR_BYTES + 4097 * sizeof(int) + 64 + (size_t)(K > 0 ? K : 0) * (DESC_WORDS + MASK_PAD) * 4;
 }
 
-CIM_API int cim_roi_align_fwd(const float *feat, const float *rois, float *out, int B, int C, int H, int W,
-                              int K, int oh, int ow, float scale, int sr, int aligned, void *ws,
-                              size_t ws_bytes, cim_stream_t stream) {
+static int roi_fwd_impl(const float *feat, const float *rois, const float *mask7, float *out, int B, int C, int H,
+                        int W, int K, int oh, int ow, float scale, int sr, int aligned, void *ws, size_t ws_bytes,
+                        cim_stream_t stream) {
     if (B > 4096) return CIM_ERR_SHAPE;
     if (K == 0 && feat && B > 0 && C > 0 && H > 0 && W > 0 && oh > 0 && ow > 0) return CIM_OK;   // empty output
     int rc = check_args(feat, rois, out, B, C, H, W, K, oh, ow, ws, ws_bytes);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const Plan p = make_plan(C, H, W, oh, ow);
-    const RoiWs w = carve(ws, B);
+    const RoiWs w = carve(ws, B, K);
     const int per_roi = C * oh * ow;
     dim3 ggrid((unsigned)K, (unsigned)min(64, (per_roi + 255) / 256));
     if (!p.tile) {
-        roi_align_generic_kernel<false><<<ggrid, 256, 0, st>>>(feat, rois, out, nullptr, nullptr, 0, B, C, H, W,
+        roi_align_generic_kernel<false><<<ggrid, 256, 0, st>>>(feat, rois, out, nullptr, nullptr, mask7, 0, B, C, H, W,
                                                                K, oh, ow, scale, sr, aligned);
         return cim_launch_status();
     }
@@ -848,18 +920,18 @@ CIM_API int cim_roi_align_fwd(const float *feat, const float *rois, float *out, 
     cudaFuncSetAttribute(roi_align_fwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_fwd);
     const long long units = (long long)(C / CH) * K;
     const int grid = (int)min((long long)cim_num_sms(), units);
-    roi_align_fwd_tile_kernel<<<grid, p.fwd_warps * 32, p.smem_fwd, st>>>(feat, w.hdr, w.img_start, w.desc, out, B,
-                                                                           C, H, W, p.pitch, p.wyd_floats);
+    roi_align_fwd_tile_kernel<<<grid, p.fwd_warps * 32, p.smem_fwd, st>>>(feat, w.hdr, w.img_start, w.desc, mask7, out,
+                                                                           B, C, H, W, p.pitch, p.wyd_floats);
     if ((rc = cim_launch_status())) return rc;
     // leftover pass: one CTA per ROI, which exits at once unless the tile kernel skipped that ROI
-    roi_align_generic_kernel<false><<<dim3((unsigned)K, 1), 256, 0, st>>>(feat, rois, out, w.hdr, w.desc, 1, B, C, H,
-                                                                          W, K, oh, ow, scale, sr, aligned);
+    roi_align_generic_kernel<false><<<dim3((unsigned)K, 1), 256, 0, st>>>(feat, rois, out, w.hdr, w.desc, mask7, 1, B,
+                                                                          C, H, W, K, oh, ow, scale, sr, aligned);
     return cim_launch_status();
 }
 
-CIM_API int cim_roi_align_bwd(const float *grad_out, const float *rois, float *grad_feat, int B, int C, int H,
-                              int W, int K, int oh, int ow, float scale, int sr, int aligned, void *ws,
-                              size_t ws_bytes, cim_stream_t stream) {
+static int roi_bwd_impl(const float *grad_out, const float *rois, const float *mask7, float *grad_feat, int B, int C,
+                        int H, int W, int K, int oh, int ow, float scale, int sr, int aligned, void *ws,
+                        size_t ws_bytes, cim_stream_t stream) {
     if (B > 4096) return CIM_ERR_SHAPE;
     if (K == 0 && grad_feat && B > 0 && C > 0 && H > 0 && W > 0) {                // no ROI: zero gradient
         cudaMemsetAsync(grad_feat, 0, sizeof(float) * (size_t)B * C * H * W, (cudaStream_t)stream);
@@ -869,13 +941,13 @@ CIM_API int cim_roi_align_bwd(const float *grad_out, const float *rois, float *g
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const Plan p = make_plan(C, H, W, oh, ow);
-    const RoiWs w = carve(ws, B);
+    const RoiWs w = carve(ws, B, K);
     const int per_roi = C * oh * ow;
     dim3 ggrid((unsigned)max(K, 1), (unsigned)min(64, (per_roi + 255) / 256));
     if (!p.tile || K == 0) {
         cudaMemsetAsync(grad_feat, 0, sizeof(float) * (size_t)B * C * H * W, st);
         if (K > 0)
-            roi_align_generic_kernel<true><<<ggrid, 256, 0, st>>>(grad_out, rois, grad_feat, nullptr, nullptr, 0,
+            roi_align_generic_kernel<true><<<ggrid, 256, 0, st>>>(grad_out, rois, grad_feat, nullptr, nullptr, mask7, 0,
                                                                   B, C, H, W, K, oh, ow, scale, sr, aligned);
         return cim_launch_status();
     }
@@ -883,11 +955,52 @@ CIM_API int cim_roi_align_bwd(const float *grad_out, const float *rois, float *g
     cudaMemsetAsync(grad_feat, 0, sizeof(float) * (size_t)B * C * H * W, st);
     const long long units = (long long)(C / CH) * K;
     const int grid = (int)min((long long)cim_num_sms(), units);
-    cudaFuncSetAttribute(roi_align_bwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bwd);
-    roi_align_bwd_tile_kernel<<<grid, NWB * 32, p.smem_bwd, st>>>(grad_out, w.hdr, w.img_start, w.desc, grad_feat,
-                                                                   B, C, H, W, p.pitch);
+    if (mask7) {
+        roi_mask_pad_kernel<<<(K * MASK_PAD + 255) / 256, 256, 0, st>>>(mask7, w.maskpad, K, NBIN);
+        if ((rc = cim_launch_status())) return rc;
+        cudaFuncSetAttribute(roi_align_bwd_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)p.smem_bwd_fused);
+        roi_align_bwd_tile_kernel<true><<<grid, NWB * 32, p.smem_bwd_fused, st>>>(grad_out, w.hdr, w.img_start, w.desc,
+                                                                                   w.maskpad, grad_feat, B, C, H, W,
+                                                                                   p.pitch);
+    } else {
+        cudaFuncSetAttribute(roi_align_bwd_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)p.smem_bwd);
+        roi_align_bwd_tile_kernel<false><<<grid, NWB * 32, p.smem_bwd, st>>>(grad_out, w.hdr, w.img_start, w.desc,
+                                                                              nullptr, grad_feat, B, C, H, W, p.pitch);
+    }
     if ((rc = cim_launch_status())) return rc;
-    roi_align_generic_kernel<true><<<dim3((unsigned)K, 1), 256, 0, st>>>(grad_out, rois, grad_feat, w.hdr, w.desc, 1,
-                                                                         B, C, H, W, K, oh, ow, scale, sr, aligned);
+    roi_align_generic_kernel<true><<<dim3((unsigned)K, 1), 256, 0, st>>>(grad_out, rois, grad_feat, w.hdr, w.desc,
+                                                                         mask7, 1, B, C, H, W, K, oh, ow, scale, sr,
+                                                                         aligned);
     return cim_launch_status();
+}
+
+CIM_API int cim_roi_align_fwd(const float *feat, const float *rois, float *out, int B, int C, int H, int W,
+                              int K, int oh, int ow, float scale, int sr, int aligned, void *ws,
+                              size_t ws_bytes, cim_stream_t stream) {
+    return roi_fwd_impl(feat, rois, nullptr, out, B, C, H, W, K, oh, ow, scale, sr, aligned, ws, ws_bytes, stream);
+}
+
+CIM_API int cim_roi_align_bwd(const float *grad_out, const float *rois, float *grad_feat, int B, int C, int H,
+                              int W, int K, int oh, int ow, float scale, int sr, int aligned, void *ws,
+                              size_t ws_bytes, cim_stream_t stream) {
+    return roi_bwd_impl(grad_out, rois, nullptr, grad_feat, B, C, H, W, K, oh, ow, scale, sr, aligned, ws, ws_bytes,
+                        stream);
+}
+
+CIM_API int cim_roi_align_maskfuse_fwd(const float *feat, const float *rois, const float *masks7, float *out, int B,
+                                       int C, int H, int W, int K, int oh, int ow, float scale, int sr, int aligned,
+                                       void *ws, size_t ws_bytes, cim_stream_t stream) {
+    if (!masks7 && K > 0) return CIM_ERR_ARG;
+    return roi_fwd_impl(feat, rois, masks7, out, B, C, H, W, K, oh, ow, scale, sr, aligned, ws, ws_bytes, stream);
+}
+
+CIM_API int cim_roi_align_maskfuse_bwd(const float *grad_out, const float *rois, const float *masks7,
+                                       float *grad_feat, int B, int C, int H, int W, int K, int oh, int ow,
+                                       float scale, int sr, int aligned, void *ws, size_t ws_bytes,
+                                       cim_stream_t stream) {
+    if (!masks7 && K > 0) return CIM_ERR_ARG;
+    return roi_bwd_impl(grad_out, rois, masks7, grad_feat, B, C, H, W, K, oh, ow, scale, sr, aligned, ws, ws_bytes,
+                        stream);
 }

@@ -110,6 +110,56 @@ class RoIPoolFunction(Function):
         return grad_feat, None, None, None
 
 
+class RoIAlignMaskFuseFunction(Function):
+    """RoIAlign + the MaskFuse prologue in one kernel: concat(box_x, box_x * masks) of
+    lib/modeling/resnet50.py:121-134 (vgg16.py:172-175, HRNet.py:625-628).  masks [K, oh, ow] carry no gradient
+    (the reference passes masks.detach(), model_builder.py:136)."""
+
+    @staticmethod
+    def forward(ctx, feat, rois, masks, output_size, spatial_scale=1.0, sampling_ratio=0, aligned=True):
+        _check_inputs(feat, rois)
+        _lib.require_cuda(masks, "masks", torch.float32)
+        oh, ow = _pair(output_size)
+        feat, rois = feat.contiguous(), rois.contiguous()
+        B, Cc, H, W = feat.shape
+        K = rois.size(0)
+        masks = masks.reshape(K, oh, ow).contiguous()
+        L = _lib.lib()
+        with torch.cuda.device(feat.device):
+            ws = torch.empty(L.cim_roi_align_workspace_bytes(K), dtype=torch.uint8, device=feat.device)
+            out = torch.empty((K, 2 * Cc, oh, ow), dtype=torch.float32, device=feat.device)
+            rc = L.cim_roi_align_maskfuse_fwd(_lib.ptr(feat), _lib.ptr(rois), _lib.ptr(masks), _lib.ptr(out), B, Cc, H,
+                                              W, K, oh, ow, float(spatial_scale), int(sampling_ratio),
+                                              int(bool(aligned)), _lib.ptr(ws), ws.numel(),
+                                              _lib.stream_ptr(feat.device))
+        _lib.check(rc, "cim_roi_align_maskfuse_fwd")
+        ctx.save_for_backward(rois, masks)
+        ctx.cfg = (tuple(feat.shape), oh, ow, float(spatial_scale), int(sampling_ratio), int(bool(aligned)))
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        rois, masks = ctx.saved_tensors
+        (B, Cc, H, W), oh, ow, scale, sr, aligned = ctx.cfg
+        grad_out = grad_out.contiguous()
+        K = rois.size(0)
+        L = _lib.lib()
+        with torch.cuda.device(grad_out.device):
+            ws = torch.empty(L.cim_roi_align_workspace_bytes(K), dtype=torch.uint8, device=grad_out.device)
+            grad_feat = torch.empty((B, Cc, H, W), dtype=torch.float32, device=grad_out.device)
+            rc = L.cim_roi_align_maskfuse_bwd(_lib.ptr(grad_out), _lib.ptr(rois), _lib.ptr(masks), _lib.ptr(grad_feat),
+                                              B, Cc, H, W, K, oh, ow, scale, sr, aligned, _lib.ptr(ws), ws.numel(),
+                                              _lib.stream_ptr(grad_out.device))
+        _lib.check(rc, "cim_roi_align_maskfuse_bwd")
+        return grad_feat, None, None, None, None, None, None
+
+
+def roi_align_maskfuse(input, rois, masks, output_size, spatial_scale=1.0, sampling_ratio=0, aligned=True):
+    """[K, 2C, oh, ow] = concat(RoIAlign(input, rois), RoIAlign(input, rois) * masks[:, None]) in one pass."""
+    return RoIAlignMaskFuseFunction.apply(input, rois, masks, output_size, spatial_scale, sampling_ratio, aligned)
+
+
 def roi_align(input, rois, output_size, spatial_scale=1.0, sampling_ratio=0, pool_mode="avg", aligned=True):
     return RoIAlignFunction.apply(input, rois, output_size, spatial_scale, sampling_ratio, pool_mode, aligned)
 

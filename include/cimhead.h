@@ -61,6 +61,23 @@ int cim_roi_align_bwd(const float *grad_out, const float *rois, float *grad_feat
                       float spatial_scale, int sampling_ratio, int aligned,
                       void *workspace, size_t workspace_bytes, cim_stream_t stream);
 
+/* RoIAlign fused with the MaskFuse prologue (lib/modeling/resnet50.py:121-134, vgg16.py:172-175, HRNet.py:625-628:
+ * `mask_x = box_x * masks.expand(...)`, `torch.concat((box_x, mask_x), dim=1)`): the pooled features and their
+ * product with the ROI's oh x ow mask leave the kernel side by side, so the [K,C,oh,ow] tensor is never re-read
+ * and the concat never materialised separately.
+ *   masks7 [K, oh, ow] fp32 (the 7x7 proposal masks of tools/pre/generate_7_7_voc.py; no gradient, the
+ *   reference passes masks.detach());  out / grad_out [K, 2C, oh, ow] fp32: channels [0,C) = RoIAlign,
+ *   [C,2C) = RoIAlign * mask.  The backward feeds grad_out[:, :C] + grad_out[:, C:] * mask into the RoIAlign
+ *   backward.  Same workspace as cim_roi_align_fwd / _bwd. */
+int cim_roi_align_maskfuse_fwd(const float *feat, const float *rois, const float *masks7, float *out,
+                               int B, int C, int H, int W, int K, int oh, int ow,
+                               float spatial_scale, int sampling_ratio, int aligned,
+                               void *workspace, size_t workspace_bytes, cim_stream_t stream);
+int cim_roi_align_maskfuse_bwd(const float *grad_out, const float *rois, const float *masks7, float *grad_feat,
+                               int B, int C, int H, int W, int K, int oh, int ow,
+                               float spatial_scale, int sampling_ratio, int aligned,
+                               void *workspace, size_t workspace_bytes, cim_stream_t stream);
+
 /* RoIPool: lib/model/roi_pooling/src/roi_pooling_kernel.cu:24-93 (fwd), :128-203 (bwd).
  * argmax [K,C,oh,ow] int32 = index inside the H*W plane, -1 for an empty bin. */
 int cim_roi_pool_fwd(const float *feat, const float *rois, float *out, int32_t *argmax,

@@ -188,3 +188,89 @@ def test_errors_are_raised_not_printed():
         ops.roi_align(f.half(), torch.zeros(4, 5, device=DEV), 7)
     with pytest.raises(NotImplementedError):
         ops.roi_align(f, torch.zeros(4, 5, device=DEV), 7, 1.0, 0, "max")
+
+
+# ------------------------------------------------------------------ fused MaskFuse prologue
+def maskfuse_oracle(feat, rois, masks, scale, sr, aligned, g, out_size=(7, 7)):
+    """lib/modeling/resnet50.py:121-134 on top of the RoIAlign oracle: box_x, mask_x = box_x * masks,
+    concat((box_x, mask_x), 1); backward: d box_x = g[:, :C] + g[:, C:] * masks."""
+    oh, ow = out_size
+    C = feat.shape[1]
+    box = roi_oracle.roi_align_fwd(feat.numpy(), rois.numpy(), oh, ow, scale, sr, aligned)
+    m = masks.numpy()[:, None]
+    want = np.concatenate([box, box * m], 1)
+    g_box = np.ascontiguousarray(g[:, :C] + g[:, C:] * m)
+    want_g = roi_oracle.roi_align_bwd(g_box, rois.numpy(), feat.shape, scale, sr, aligned)
+    return want, want_g
+
+
+def run_maskfuse(feat, rois, masks, scale, sr, aligned, out_size=7):
+    f = feat.to(DEV).requires_grad_(True)
+    out = ops.roi_align_maskfuse(f, rois.to(DEV), masks.to(DEV), out_size, scale, sr, aligned)
+    g = torch.randn(out.shape, generator=torch.Generator().manual_seed(78))
+    out.backward(g.to(DEV))
+    return out.detach().cpu().numpy(), f.grad.cpu().numpy(), g.numpy()
+
+
+@pytest.mark.parametrize("wild", [False, True])
+@pytest.mark.parametrize("aligned", [True, False])
+def test_maskfuse_tile_path(aligned, wild):
+    feat = torch.randn(3, 64, 16, 20, generator=torch.Generator().manual_seed(1))
+    rois = random_rois(2, 3, 91, 16, 20, 0.25, wild)          # odd count: a ring slot with one ROI
+    masks = (torch.rand(91, 7, 7, generator=torch.Generator().manual_seed(3)) > 0.4).float()
+    out, gf, g = run_maskfuse(feat, rois, masks, 0.25, 0, aligned)
+    want, want_g = maskfuse_oracle(feat, rois, masks, 0.25, 0, aligned, g)
+    close(out, want)
+    close(gf, want_g)
+
+
+def test_maskfuse_equals_unfused_ops_bitwise_forward():
+    """The fused output is the unfused RoIAlign output and its product with the mask, bit for bit."""
+    C, H, W, scale = synth.feature_shape("resnet50")
+    feat = torch.randn(1, C, H, W, generator=torch.Generator().manual_seed(12)).to(DEV)
+    rois = synth.rois_from_params(synth.proposal_params(300, 512, 12)).to(DEV)
+    masks = (torch.rand(300, 7, 7, generator=torch.Generator().manual_seed(4)) > 0.5).float().to(DEV)
+    fused = ops.roi_align_maskfuse(feat, rois, masks, 7, scale, 0, True)
+    box = ops.roi_align(feat, rois, 7, scale, 0, "avg", True)
+    assert torch.equal(fused[:, :C], box)
+    assert torch.equal(fused[:, C:], box * masks[:, None])
+
+
+@pytest.mark.parametrize("case", ["unsorted", "odd_channels", "out3x5", "big_map"])
+def test_maskfuse_generic_paths(case):
+    B, C, H, W, K, size, sort = 2, 32, 12, 12, 50, 7, True
+    if case == "unsorted":
+        sort = False
+    elif case == "odd_channels":
+        C = 5
+    elif case == "out3x5":
+        size = (3, 5)
+    elif case == "big_map":
+        H, W = 100, 120
+    oh, ow = (size, size) if isinstance(size, int) else size
+    feat = torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(5))
+    rois = random_rois(6, B, K, H, W, 0.5, wild=True, sort=sort)
+    masks = torch.rand(K, oh, ow, generator=torch.Generator().manual_seed(6))          # soft masks work too
+    out, gf, g = run_maskfuse(feat, rois, masks, 0.5, 0, True, size)
+    want, want_g = maskfuse_oracle(feat, rois, masks, 0.5, 0, True, g, (oh, ow))
+    close(out, want)
+    close(gf, want_g)
+
+
+def test_maskfuse_full_size_adjoint():
+    """cfg2-sized (2000 proposals, R-50 features): <fused(f), g> == <f, fused_bwd(g)> (the pair is an adjoint
+    pair, a size-independent property), and the backward is bit-reproducible."""
+    C, H, W, scale = synth.feature_shape("resnet50")
+    K = 2000
+    gen = torch.Generator(device=DEV).manual_seed(9)
+    feat = torch.randn(1, C, H, W, device=DEV, generator=gen, requires_grad=True)
+    rois = synth.rois_from_params(synth.proposal_params(K, 512, 9)).to(DEV)
+    masks = (torch.rand(K, 7, 7, device=DEV, generator=gen) > 0.5).float()
+    out = ops.roi_align_maskfuse(feat, rois, masks, 7, scale, 0, True)
+    g = torch.randn(out.shape, device=DEV, generator=gen)
+    (gf,) = torch.autograd.grad(out, feat, g, retain_graph=True)
+    (gf2,) = torch.autograd.grad(out, feat, g)
+    assert torch.equal(gf, gf2)
+    lhs = (out.double() * g.double()).sum().item()
+    rhs = (feat.detach().double() * gf.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), 1.0)

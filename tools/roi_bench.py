@@ -21,6 +21,9 @@ def main():
     ap.add_argument("--backbone", default="resnet50")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--profile-fused-bwd", action="store_true", help="run only the fused backward 3 times (for ncu)")
+    ap.add_argument("--fused", action="store_true", help="also time the fused MaskFuse prologue and the unfused "
+                    "torch expression it replaces (box * mask, concat)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     Cf, H, W, scale = synth.feature_shape(a.backbone)
@@ -59,9 +62,45 @@ def main():
         ts.sort()
         return ts[len(ts) // 2]
 
+    if a.profile_fused_bwd:
+        masks = (torch.rand(K, 7, 7, device=dev, generator=g) > 0.5).float()
+        gout2 = torch.randn(K, 2 * Cf, 7, 7, device=dev, generator=g)
+        for _ in range(3):
+            _lib.check(L.cim_roi_align_maskfuse_bwd(_lib.ptr(gout2), _lib.ptr(rois), _lib.ptr(masks), _lib.ptr(gfeat),
+                                                    B, Cf, H, W, K, 7, 7, scale, 0, 1, _lib.ptr(ws), ws.numel(), st),
+                       "fbwd")
+        torch.cuda.synchronize()
+        return
     mb = (K * Cf * 49 * 4 + B * Cf * H * W * 4 + 20 * K) / 1e6
     tf, tb = timeit(fwd), timeit(bwd)
     print(f"roi_align fwd {tf:.3f} ms  {mb / tf:.1f} GB/s   bwd {tb:.3f} ms  {mb / tb:.1f} GB/s   ({mb:.0f} MB each)")
+
+    if a.fused:
+        masks = (torch.rand(K, 7, 7, device=dev, generator=g) > 0.5).float()
+        out2 = torch.empty(K, 2 * Cf, 7, 7, device=dev)
+        gout2 = torch.randn(K, 2 * Cf, 7, 7, device=dev, generator=g)
+
+        def ffwd():
+            _lib.check(L.cim_roi_align_maskfuse_fwd(_lib.ptr(feat), _lib.ptr(rois), _lib.ptr(masks), _lib.ptr(out2), B,
+                                                    Cf, H, W, K, 7, 7, scale, 0, 1, _lib.ptr(ws), ws.numel(), st), "ffwd")
+
+        def fbwd():
+            _lib.check(L.cim_roi_align_maskfuse_bwd(_lib.ptr(gout2), _lib.ptr(rois), _lib.ptr(masks), _lib.ptr(gfeat),
+                                                    B, Cf, H, W, K, 7, 7, scale, 0, 1, _lib.ptr(ws), ws.numel(), st),
+                       "fbwd")
+
+        def unfused_fwd():                       # lib/modeling/resnet50.py:131-134 after the plain kernel
+            fwd()
+            torch.cat((out, out * masks[:, None]), 1, out=out2)
+
+        def unfused_bwd():
+            torch.add(gout2[:, :Cf], gout2[:, Cf:] * masks[:, None], out=gout)
+            bwd()
+
+        mb2 = (2 * K * Cf * 49 * 4 + B * Cf * H * W * 4 + 20 * K + K * 196) / 1e6
+        t1, t2, t3, t4 = timeit(ffwd), timeit(fbwd), timeit(unfused_fwd), timeit(unfused_bwd)
+        print(f"maskfuse fused  fwd {t1:.3f} ms  {mb2 / t1:.1f} GB/s   bwd {t2:.3f} ms  {mb2 / t2:.1f} GB/s   ({mb2:.0f} MB each)")
+        print(f"maskfuse unfused (kernel + torch mul/cat)  fwd {t3:.3f} ms   bwd {t4:.3f} ms")
 
     if a.check:
         from torchvision.ops import roi_align as tv
