@@ -203,3 +203,106 @@ def mask_overlap_maps(masks):
     """Convenience: uint8 masks [N, H, W] -> (iou_map, asy_iou_map), i.e. what the reference
     un-pickles from cfg.iou_dir / cfg.asy_iou_dir for one image."""
     return mask_overlap(mask_pack(masks))
+
+
+# ------------------------------------------------------------------ offline callers of lib/utils/mask_utils.py
+_RATIO_MODES = {"iou": 0, "asymmetric": 1, "inside": 2, "outside": 3}
+
+
+def _as_packed_flat(m, name):
+    """uint8/bool [N, H, W] -> flat bit masks [N, words] (already packed int32 [N, words] passes through)."""
+    _lib.require_cuda(m, name)
+    if m.dtype == torch.int32 and m.dim() == 2:
+        return m.contiguous(), None
+    if m.dim() != 3:
+        raise ValueError(f"{name} must be [N, H, W] masks or [N, words] packed int32")
+    return mask_pack(m, layout="flat"), tuple(m.shape[1:])
+
+
+def mask_pair_ratio(mask_a, mask_b, mode="iou", return_counts=False):
+    """float32 [Na, Nb] ratio between every mask of a and every mask of b: the four functions of
+    lib/utils/mask_utils.py in one kernel (cim_mask_pair_ratio).  Inputs: uint8/bool [N, H, W] CUDA tensors or
+    flat bit masks [N, words] from mask_pack(layout="flat")."""
+    pa, sa = _as_packed_flat(mask_a, "mask_a")
+    pb, sb = _as_packed_flat(mask_b, "mask_b")
+    if (sa is not None and sb is not None and sa != sb) or pa.shape[1] != pb.shape[1]:
+        raise IndexError("mask shapes differ")                   # mask_utils.py:7-8
+    na, nb, words = pa.shape[0], pb.shape[0], pa.shape[1]
+    dev = pa.device
+    with torch.cuda.device(dev):
+        ratio = torch.empty((na, nb), dtype=torch.float32, device=dev)
+        inter = torch.empty((na, nb), dtype=torch.int32, device=dev) if return_counts else None
+        area_a = torch.empty((na,), dtype=torch.int32, device=dev)
+        area_b = torch.empty((nb,), dtype=torch.int32, device=dev)
+        rc = _lib.lib().cim_mask_pair_ratio(_lib.ptr(pa), _lib.ptr(pb), na, nb, words, _RATIO_MODES[mode],
+                                            _lib.ptr(ratio), _lib.ptr(inter), _lib.ptr(area_a), _lib.ptr(area_b),
+                                            _lib.stream_ptr(dev))
+    _lib.check(rc, "cim_mask_pair_ratio")
+    return (ratio, inter, area_a, area_b) if return_counts else ratio
+
+
+def mask_iou(mask_a, mask_b):
+    """lib/utils/mask_utils.py:6-18."""
+    return mask_pair_ratio(mask_a, mask_b, "iou")
+
+
+def mask_asymmetric_iou(mask_a, mask_b):
+    """lib/utils/mask_utils.py:20-32 (the denominator is mask_b.sum() over ALL masks of b, as written there)."""
+    return mask_pair_ratio(mask_a, mask_b, "asymmetric")
+
+
+def mask_inside(mask_a, mask_b):
+    """lib/utils/mask_utils.py:35-47."""
+    return mask_pair_ratio(mask_a, mask_b, "inside")
+
+
+def mask_outside(mask_a, mask_b):
+    """lib/utils/mask_utils.py:50-62."""
+    return mask_pair_ratio(mask_a, mask_b, "outside")
+
+
+# ------------------------------------------------------------------ on-disk formats
+def load_map_pickle(path, device="cuda:0", index=None):
+    """Read a cob_iou / cob_asy_iou pickle written by the reference's tools/pre/create_cob_iou.py:48-49 /
+    create_cob_asy_iou.py (one float16 [N, N] numpy array, pickle.HIGHEST_PROTOCOL) the way
+    lib/modeling/model_builder.py:148-156 does: tensor on `device`, re-indexed [index][:, index] when given.
+    Lets maps computed by the reference be replayed against the mining kernels, or compared with cim_mask_overlap."""
+    import pickle
+    with open(path, "rb") as f:
+        arr = pickle.load(f)
+    t = torch.as_tensor(arr, device=device)
+    if t.dtype != torch.float16 or t.dim() != 2 or t.shape[0] != t.shape[1]:
+        raise ValueError(f"{path}: expected a float16 [N, N] map, got {t.dtype} {tuple(t.shape)}")
+    if index is not None:
+        index = torch.as_tensor(index, device=device).long()
+        t = t[index][:, index]
+    return t.contiguous()
+
+
+def save_map_pickle(path, map_f16):
+    """Write a map in the reference's format (create_cob_iou.py:48-49), e.g. the output of mask_overlap, so the
+    reference's training loop can consume maps produced here."""
+    import pickle
+    arr = map_f16.detach().cpu().numpy()
+    if arr.dtype.name != "float16" or arr.ndim != 2:
+        raise ValueError("expected a float16 [N, N] map")
+    with open(path, "wb") as f:
+        pickle.dump(arr, f, pickle.HIGHEST_PROTOCOL)
+
+
+def save_packed_masks(path, packed, height, width, layout="flat"):
+    """Bit-packed proposal-mask store (1 bit / pixel instead of the uint8 [N, H, W] arrays the reference keeps in
+    COB .mat files: 8x smaller on disk and on the PCIe bus).  .npz with the words, the image size and the pixel
+    order; load_packed_masks() returns what mask_overlap() takes."""
+    import numpy as np
+    np.savez_compressed(path, words=packed.detach().cpu().numpy(), height=np.int64(height), width=np.int64(width),
+                        layout=np.bytes_(layout))
+
+
+def load_packed_masks(path, device="cuda:0"):
+    import numpy as np
+    z = np.load(path)
+    height, width = int(z["height"]), int(z["width"])
+    layout = bytes(z["layout"]).decode()
+    packed = torch.from_numpy(z["words"]).to(device)
+    return _tag(packed, width // 16 if layout == "tiled" else 0), height, width, layout

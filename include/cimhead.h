@@ -147,6 +147,17 @@ int cim_mask_overlap_ex(const uint32_t *packed, int n_img, int n, int64_t words,
                         int32_t *inter, int32_t *area, void *iou_f16, void *asy_f16,
                         void *workspace, size_t workspace_bytes, int algo, cim_stream_t stream);
 
+/* Rectangular ratios between two mask sets: the offline callers of lib/utils/mask_utils.py
+ * (tools/pre/AGPL_label_assign.py:84,165, tools/pre/point_level_label_assign.py:79,
+ * tools/generate_mask_for_MaskRCNN.py, tools/pre/create_cob_iou.py:45, create_cob_asy_iou.py:46).
+ *   packed_a [na, words], packed_b [nb, words]: bit masks in the same pixel order (cim_mask_pack);
+ *   mode 0 mask_iou (mask_utils.py:6-18), 1 mask_asymmetric_iou (I / mask_b.sum() over ALL of b, :20-32),
+ *        2 mask_inside (I / |b_k|, :35-47), 3 mask_outside (I / |a_n|, :50-62);
+ *   ratio [na, nb] fp32 (the reference's float32 result array; 0/0 -> NaN), inter [na, nb] int32 (optional),
+ *   area_a [na], area_b [nb] int32 (outputs: the row popcounts).  words * 32 <= 2^24. */
+int cim_mask_pair_ratio(const uint32_t *packed_a, const uint32_t *packed_b, int na, int nb, int64_t words, int mode,
+                        float *ratio, int32_t *inter, int32_t *area_a, int32_t *area_b, cim_stream_t stream);
+
 /* ------------------------------------------------------------------ scoring heads
  * Replace heads.cls_iou_model.forward (lib/modeling/heads.py:194-219): n_heads = 2 + 2*K
  * linear layers over the same features, ordered [classifier, detector, refine_cls.0..K-1,

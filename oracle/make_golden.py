@@ -306,6 +306,28 @@ def make_nms_fixture():
     np.savez_compressed(os.path.join(GOLD, "box_nms.npz"), **out)
 
 
+def make_pair_fixture(ref_mu):
+    """Rectangular ratios: the reference's own mask_iou / mask_asymmetric_iou / mask_inside / mask_outside
+    (lib/utils/mask_utils.py through the numpy shim) on two small mask sets, incl. an empty mask (0/0 -> NaN)."""
+    rs = np.random.RandomState(31)
+    out = {}
+    for name, na, nb, h, w in [("n12x3", 12, 3, 24, 20), ("n9x1", 9, 1, 17, 23)]:
+        a = (rs.rand(na, h, w) < rs.uniform(0.1, 0.8, (na, 1, 1))).astype(np.uint8)
+        b = (rs.rand(nb, h, w) < rs.uniform(0.2, 0.7, (nb, 1, 1))).astype(np.uint8)
+        a[0] = 0                                   # empty mask
+        a[1] = b[0]                                # identical masks: iou 1
+        out[name + "/a"], out[name + "/b"] = a, b
+        with np.errstate(divide="ignore", invalid="ignore"), contextlib.redirect_stderr(io.StringIO()):
+            for mode, fn in (("iou", ref_mu.mask_iou), ("asymmetric", ref_mu.mask_asymmetric_iou),
+                             ("inside", ref_mu.mask_inside), ("outside", ref_mu.mask_outside)):
+                ref = fn(a, b)
+                ora = mask_oracle.pair_ratio(a, b, mode)
+                assert ref.dtype == np.float32 and np.array_equal(ref, ora, equal_nan=True), (name, mode)
+                out[f"{name}/{mode}"] = ref
+        print(f"mask pair {name}: oracle == reference for iou / asymmetric / inside / outside")
+    np.savez_compressed(os.path.join(GOLD, "mask_pair.npz"), **out)
+
+
 def make_loss_fixture(ref_heads):
     """Loss block: the reference's own heads.cls_iou_loss / heads.mil_bag_loss (imported unmodified) with
     autograd, wired as model_builder.py:170-202, on the inputs + CIM_layer outputs of stored cim_layer cases."""
@@ -368,6 +390,9 @@ def main():
     if "--only-nms" in sys.argv:
         make_nms_fixture()
         return
+    if "--only-pair" in sys.argv:
+        make_pair_fixture(load_reference()[1])
+        return
     if "--only-losses" in sys.argv:
         make_loss_fixture(load_reference()[0])
         return
@@ -378,6 +403,7 @@ def main():
     make_scoring_fixture(ref_heads)
     make_nms_fixture()
     make_loss_fixture(ref_heads)
+    make_pair_fixture(ref_mu)
     if "--fuzz" in sys.argv:
         fuzz(ref_heads, ref_mu, int(sys.argv[sys.argv.index("--fuzz") + 1]))
     print("golden fixtures written to", GOLD)

@@ -76,3 +76,25 @@ def mask_overlap_maps_literal(masks):
                 iou[i, k] = inter / union
                 asy[i, k] = inter / col_area
     return iou.astype(np.float16), asy.astype(np.float16)
+
+
+def pair_ratio(mask_a, mask_b, mode="iou"):
+    """The four rectangular functions of lib/utils/mask_utils.py between two mask sets -> float32 [Na, Nb]:
+    "iou" (:6-18), "asymmetric" (:20-32, denominator mask_b.sum() over ALL of b), "inside" (:35-47, |b_k|),
+    "outside" (:50-62, |a_n|).  int / int in float64, stored to float32, like the reference's result array.
+    Pinned by tests/golden/mask_pair.npz (reference's own mask_utils.py through the numpy shim)."""
+    a, b = _as_bool(mask_a), _as_bool(mask_b)
+    inter = a.astype(np.float64) @ b.astype(np.float64).T
+    area_a, area_b = a.sum(1).astype(np.float64), b.sum(1).astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if mode == "iou":
+            out = inter / (area_a[:, None] + area_b[None, :] - inter)
+        elif mode == "asymmetric":
+            out = inter / np.float64(b.sum())
+        elif mode == "inside":
+            out = inter / area_b[None, :]
+        elif mode == "outside":
+            out = inter / area_a[:, None]
+        else:
+            raise ValueError(mode)
+    return out.astype(np.float32)

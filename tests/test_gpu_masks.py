@@ -1,12 +1,14 @@
 """mask_pack / mask_overlap kernels against the reference-generated fixture and the oracle:
 integer intersection counts and the fp16 maps are compared bit for bit."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
 from cim_b200 import mask_ops, synth
 from oracle import mask_oracle
-from conftest import assert_f16_bits_equal
+from conftest import GOLDEN, assert_f16_bits_equal
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -191,3 +193,53 @@ def test_crop_wire_format_round_trip(n, h, w):
         again = mask_ops.crops_from_packed_host(want.cpu(), h, w)
         assert torch.equal(again.words, crops.words) and torch.equal(again.meta, crops.meta)
     assert crops.nbytes < masks.numel()        # smaller than byte masks by construction
+
+
+# ------------------------------------------------------------- rectangular ratios + on-disk formats (8f-4)
+@pytest.mark.parametrize("name", ["n12x3", "n9x1"])
+def test_pair_ratio_reference_fixture_bit_exact(name):
+    z = np.load(os.path.join(GOLDEN, "mask_pair.npz"))
+    a, b = torch.from_numpy(z[f"{name}/a"]).to(DEV), torch.from_numpy(z[f"{name}/b"]).to(DEV)
+    for mode, fn in (("iou", mask_ops.mask_iou), ("asymmetric", mask_ops.mask_asymmetric_iou),
+                     ("inside", mask_ops.mask_inside), ("outside", mask_ops.mask_outside)):
+        got, want = fn(a, b).cpu().numpy(), z[f"{name}/{mode}"]
+        np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
+        np.testing.assert_array_equal(np.nan_to_num(got).view(np.uint32), np.nan_to_num(want).view(np.uint32))
+
+
+def test_pair_ratio_n_by_one_like_agpl_label_assign():
+    """tools/pre/AGPL_label_assign.py:82-86: 2000 proposals against one averaged peak mask, full resolution."""
+    params = synth.proposal_params(2000, 512, 77)
+    masks = synth.rasterize(params, device=DEV)
+    avg = (masks[masks[:, 200, 260] > 0].float().mean(0) > 0.7).to(torch.uint8)[None]
+    got = mask_ops.mask_iou(masks, avg).cpu().numpy()
+    want = mask_oracle.pair_ratio(masks.cpu().numpy(), avg.cpu().numpy(), "iou")
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
+    np.testing.assert_array_equal(np.nan_to_num(got).view(np.uint32), np.nan_to_num(want).view(np.uint32))
+    # and the square case agrees with the training-path maps (fp32 here, fp16 there)
+    sq = mask_ops.mask_iou(masks[:300], masks[:300])
+    iou16, _ = mask_ops.mask_overlap(mask_ops.mask_pack(masks[:300]))
+    assert torch.equal(sq.to(torch.float16), iou16)
+
+
+def test_map_pickle_and_packed_store_round_trip(tmp_path):
+    """The reference's cob_iou pickle format (create_cob_iou.py:48-49, read at model_builder.py:148-156) and the
+    bit-packed mask store."""
+    import pickle
+    masks = synth.rasterize(synth.proposal_params(150, 128, 5), device=DEV)
+    packed = mask_ops.mask_pack(masks)
+    iou, asy = mask_ops.mask_overlap(packed)
+    p = tmp_path / "2007_000032.pkl"
+    mask_ops.save_map_pickle(p, iou)
+    raw = pickle.load(open(p, "rb"))                      # what the reference would read
+    assert raw.dtype == np.float16 and raw.shape == (150, 150)
+    assert torch.equal(mask_ops.load_map_pickle(p, DEV).view(torch.int16), iou.view(torch.int16))
+    idx = torch.arange(149, -1, -1)
+    assert torch.equal(mask_ops.load_map_pickle(p, DEV, idx).view(torch.int16),
+                       iou[idx.to(DEV)][:, idx.to(DEV)].contiguous().view(torch.int16))
+    q = tmp_path / "masks.npz"
+    mask_ops.save_packed_masks(q, packed, 128, 128, "tiled" if mask_ops.tiled_ok(128, 128) else "flat")
+    back, h, w, layout = mask_ops.load_packed_masks(q, DEV)
+    assert (h, w) == (128, 128) and torch.equal(back, packed)
+    iou2, asy2 = mask_ops.mask_overlap(back)
+    assert torch.equal(iou2.view(torch.int16), iou.view(torch.int16)) and torch.equal(asy2.view(torch.int16), asy.view(torch.int16))

@@ -1,7 +1,11 @@
 """oracle/mask_oracle.py against the fixture produced by the reference's own mask_utils.py."""
+import os
+
 import numpy as np
+import pytest
 
 from oracle import mask_oracle, roi_oracle
+from conftest import GOLDEN
 
 
 def unpack(golden_masks):
@@ -57,3 +61,14 @@ def test_known_answers():
     iou, asy = mask_oracle.mask_overlap_maps(m)
     assert iou[0, 3] == 1 and iou[0, 2] == 0 and iou[0, 1] == np.float16(0.25)
     assert asy[0, 1] == 1 and asy[1, 0] == np.float16(0.25)      # asy[i,j] = |i&j| / |j|
+
+
+@pytest.mark.parametrize("name", ["n12x3", "n9x1"])
+@pytest.mark.parametrize("mode", ["iou", "asymmetric", "inside", "outside"])
+def test_pair_ratio_matches_reference_mask_utils(name, mode):
+    """tests/golden/mask_pair.npz: outputs of the reference's own lib/utils/mask_utils.py."""
+    z = np.load(os.path.join(GOLDEN, "mask_pair.npz"))
+    got = mask_oracle.pair_ratio(z[f"{name}/a"], z[f"{name}/b"], mode)
+    assert got.dtype == np.float32
+    np.testing.assert_array_equal(got.view(np.uint32) * ~np.isnan(got), z[f"{name}/{mode}"].view(np.uint32) * ~np.isnan(got))
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(z[f"{name}/{mode}"]))
