@@ -440,6 +440,9 @@ def main():
                 "d2h_bytes_per_step": int(step.d2h_bytes),
                 "host_inputs": "rois, labels, bbox-cropped bit-packed proposal masks (unpacked on the device); "
                                "features/seg_x/grad_out are device-produced",
+                "host_outputs": "per-image losses [n_img, K+1, 3], valid flags, two checksums of the RoIAlign outputs, "
+                                "plus the pseudo-GT lists of the sampling hop" if not args.no_head_grads else
+                                "pseudo labels / IoU labels / loss weights, valid flags, checksums, sampling-hop lists",
                 "pipelining": "H2D of step i+1 on a copy stream overlaps the kernels of step i; results are read "
                               "back and the host synchronises every step"},
         "gpu_launches": (KERNELS_PER_STEP + (0 if args.no_head_grads else KERNELS_HEAD_GRADS)) * args.steps,

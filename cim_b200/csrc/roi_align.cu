@@ -257,9 +257,14 @@ __device__ __forceinline__ float2 bcast2(float w) { return make_float2(w, w); } 
 //           56 FFMA2 with r_y as the scalar-broadcast operand; the weights (mostly zero) come from the warp's
 //           dense per-row table wyd[y][8] -- no data-dependent branch in the loop, 28 float2 accumulators.
 // All control flow depends only on the descriptor (warp-uniform).  T >= 6 keeps the x weights in smem.
-template <int T>
-__device__ __forceinline__ void fwd_pairs(const float *__restrict__ tile_c, int W, const int *__restrict__ d,
+// GLB: the feature map does not fit in shared memory (VGG-16: 64 x 64 x 32 ch = 512 KB); the same sweep reads a
+// channel-last copy of the map in global memory instead -- element (p, x, c) = (f[2p][x], f[2p+1][x]) of channel c
+// at float2 index (p * W + x) * C + c, so the 32 lanes (= channels) of a warp read 256 contiguous bytes per tap
+// (L1 / L2 resident: a map is a few MB).  xs = float2 stride between neighbouring columns (1 in smem, C in global).
+template <int T, bool GLB>
+__device__ __forceinline__ void fwd_pairs(const float *__restrict__ tile_c, int W, int xs_rt, const int *__restrict__ d,
                                           float *__restrict__ stage_c, const float4 *__restrict__ wyd, int lane) {
+    const int xs = GLB ? xs_rt : 1;
     constexpr bool WREG = T <= 4;
     constexpr int TR = WREG ? T : 1;
     float wx[PW][TR];
@@ -287,21 +292,25 @@ __device__ __forceinline__ void fwd_pairs(const float *__restrict__ tile_c, int 
     const int p0 = d[D_Y0] >> 1, p1 = (d[D_Y1] + 1) >> 1;
     const float2 *tile2 = reinterpret_cast<const float2 *>(tile_c);
 #pragma unroll 1
+    if (GLB) {
+#pragma unroll
+        for (int pw = 0; pw < PW; ++pw) xo[pw] *= xs;
+    }
     for (int p = p0; p < p1; ++p) {
-        const float2 *row = tile2 + p * W;
+        const float2 *row = tile2 + (size_t)p * W * xs;
         float2 r[PW];
 #pragma unroll
         for (int pw = 0; pw < PW; ++pw) {
             float2 t = make_float2(0.f, 0.f);
             if (WREG) {
 #pragma unroll
-                for (int l = 0; l < T; ++l) t = __ffma2_rn(bcast2(wx[pw][l]), row[xo[pw] + l], t);
+                for (int l = 0; l < T; ++l) t = __ffma2_rn(bcast2(wx[pw][l]), row[xo[pw] + l * xs], t);
             } else {
                 const float4 a = *reinterpret_cast<const float4 *>(dwx + pw * MAXT);
                 const float4 b = *reinterpret_cast<const float4 *>(dwx + pw * MAXT + 4);
                 const float t8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-                for (int l = 0; l < T; ++l) t = __ffma2_rn(bcast2(t8[l]), row[xo[pw] + l], t);
+                for (int l = 0; l < T; ++l) t = __ffma2_rn(bcast2(t8[l]), row[xo[pw] + l * xs], t);
             }
             r[pw] = t;
         }
@@ -351,7 +360,9 @@ __device__ __forceinline__ void build_wyd(float *wyd, const int *__restrict__ d,
 constexpr int FWD_MAX_WARPS = 11;
 constexpr int FWD_DESC_WORDS = DESC_WORDS;
 
-__global__ void __launch_bounds__(FWD_MAX_WARPS * 32, 1)
+constexpr int FWD_GLOB_WARPS = 8;   // the global-memory variant trades warps for registers (64-bit addressing)
+template <bool GLB>
+__global__ void __launch_bounds__((GLB ? FWD_GLOB_WARPS : FWD_MAX_WARPS) * 32, 1)
 roi_align_fwd_tile_kernel(const float *__restrict__ feat, const int *__restrict__ hdr,
                           const int *__restrict__ img_start, const int *__restrict__ descs,
                           const float *__restrict__ mask7, float *__restrict__ out, int B, int C, int H, int W,
@@ -359,7 +370,7 @@ roi_align_fwd_tile_kernel(const float *__restrict__ feat, const int *__restrict_
     extern __shared__ __align__(128) float smem[];
     const int nw = blockDim.x >> 5;
     float *tile = smem;
-    float *stage = smem + (size_t)CH * pitch;                                    // [nw][1568]
+    float *stage = smem + (GLB ? 0 : (size_t)CH * pitch);                        // [nw][1568]
     int *dslots = reinterpret_cast<int *>(stage + (size_t)nw * STAGE_FLOATS);   // [nw][2][FWD_DESC_WORDS]
     float *wyds = reinterpret_cast<float *>(dslots + (size_t)nw * 2 * FWD_DESC_WORDS);   // [nw][wyd_floats]
     if (__ldg(hdr) != 0) return;              // rois not grouped by image: generic kernel runs
@@ -398,11 +409,15 @@ roi_align_fwd_tile_kernel(const float *__restrict__ feat, const int *__restrict_
 
         int r = r0 + warp, slot = 0;
         if (r < r1) prefetch(is + r, 0);       // overlaps the tile load below
-        __syncthreads();                       // everyone is done with the previous tile
-        load_tile(tile, feat + ((size_t)b * C + c0) * HW, H, W, pitch, tid, blockDim.x);
-        __syncthreads();
-
-        const float *tile_c = tile + lane * pitch;
+        const float *tile_c;
+        if (GLB) {                             // feat = the channel-last pair copy [B][Hp/2][W][C][2]
+            tile_c = feat + (((size_t)b * ((H + 1) >> 1) * W) * C + c0 + lane) * 2;
+        } else {
+            __syncthreads();                   // everyone is done with the previous tile
+            load_tile(tile, feat + ((size_t)b * C + c0) * HW, H, W, pitch, tid, blockDim.x);
+            __syncthreads();
+            tile_c = tile + lane * pitch;
+        }
         while (r < r1) {
             const int rn = r + nw;
             if (rn < r1) { prefetch(is + rn, slot ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
@@ -413,11 +428,11 @@ roi_align_fwd_tile_kernel(const float *__restrict__ feat, const int *__restrict_
                 build_wyd(my_wyd, d, lane);
                 const float4 *wyd4 = reinterpret_cast<const float4 *>(my_wyd);
                 switch (d[D_TX]) {
-                    case 2: fwd_pairs<2>(tile_c, W, d, stage_c, wyd4, lane); break;
-                    case 3: fwd_pairs<3>(tile_c, W, d, stage_c, wyd4, lane); break;
-                    case 4: fwd_pairs<4>(tile_c, W, d, stage_c, wyd4, lane); break;
-                    case 6: fwd_pairs<6>(tile_c, W, d, stage_c, wyd4, lane); break;
-                    default: fwd_pairs<8>(tile_c, W, d, stage_c, wyd4, lane); break;
+                    case 2: fwd_pairs<2, GLB>(tile_c, W, C, d, stage_c, wyd4, lane); break;
+                    case 3: fwd_pairs<3, GLB>(tile_c, W, C, d, stage_c, wyd4, lane); break;
+                    case 4: fwd_pairs<4, GLB>(tile_c, W, C, d, stage_c, wyd4, lane); break;
+                    case 6: fwd_pairs<6, GLB>(tile_c, W, C, d, stage_c, wyd4, lane); break;
+                    default: fwd_pairs<8, GLB>(tile_c, W, C, d, stage_c, wyd4, lane); break;
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -736,6 +751,187 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
     }
 }
 
+// ------------------------------------------------------------------- large maps: channel-last global copy
+// NCHW -> pairs layout [B][Hp/2][W][C] of float2 = (f[2p][x], f[2p+1][x]) and back (fwd_pairs GLB comment).
+__global__ void __launch_bounds__(256)
+nchw_to_pairs_kernel(const float *__restrict__ src, float2 *__restrict__ dst, int C, int H, int W) {
+    __shared__ float t0[32][33], t1[32][33];
+    const int hp2 = (H + 1) >> 1;
+    const int b = blockIdx.z / hp2, p = blockIdx.z - b * hp2;
+    const int x0 = blockIdx.x * 32, c0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int c = ty; c < 32; c += 8) {
+        const int cc = c0 + c, x = x0 + tx;
+        float a = 0.f, bb = 0.f;
+        if (cc < C && x < W) {
+            const float *r = src + (((size_t)b * C + cc) * H + 2 * p) * W + x;
+            a = __ldg(r);
+            if (2 * p + 1 < H) bb = __ldg(r + W);
+        }
+        t0[c][tx] = a;
+        t1[c][tx] = bb;
+    }
+    __syncthreads();
+    for (int x = ty; x < 32; x += 8) {
+        const int xx = x0 + x, cc = c0 + tx;
+        if (xx < W && cc < C) dst[(((size_t)b * hp2 + p) * W + xx) * C + cc] = make_float2(t0[tx][x], t1[tx][x]);
+    }
+}
+__global__ void __launch_bounds__(256)
+pairs_to_nchw_kernel(const float2 *__restrict__ src, float *__restrict__ dst, int C, int H, int W) {
+    __shared__ float t0[32][33], t1[32][33];
+    const int hp2 = (H + 1) >> 1;
+    const int b = blockIdx.z / hp2, p = blockIdx.z - b * hp2;
+    const int x0 = blockIdx.x * 32, c0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int x = ty; x < 32; x += 8) {
+        const int xx = x0 + x, cc = c0 + tx;
+        float2 v = make_float2(0.f, 0.f);
+        if (xx < W && cc < C) v = src[(((size_t)b * hp2 + p) * W + xx) * C + cc];
+        t0[tx][x] = v.x;
+        t1[tx][x] = v.y;
+    }
+    __syncthreads();
+    for (int c = ty; c < 32; c += 8) {
+        const int cc = c0 + c, x = x0 + tx;
+        if (cc < C && x < W) {
+            float *r = dst + (((size_t)b * C + cc) * H + 2 * p) * W + x;
+            r[0] = t0[c][tx];
+            if (2 * p + 1 < H) r[W] = t1[c][tx];
+        }
+    }
+}
+
+__device__ __forceinline__ void red_add2(float2 *gptr, float2 v) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gptr), "f"(v.x), "f"(v.y) : "memory");
+}
+
+// Backward over the global pairs copy: one ROI x 32 channels x ALL its row pairs per warp; the x pass is a
+// red.global.add.v2.f32 per tap (256 contiguous bytes per warp instruction).  Summation order across ROIs is
+// not fixed, like the reference's atomicAdd backward (roi_align_kernel.cu:237-267).
+template <int T, bool FUSED>
+__device__ __forceinline__ void bwd_pairs_glob(float2 *__restrict__ base2, int W, int xs, const int *d,
+                                               const float *__restrict__ g, const float *__restrict__ m) {
+    float wx[PW][T];
+    int xo[PW];
+    const float *dwx = reinterpret_cast<const float *>(d + D_WX);
+    const float *dwy = reinterpret_cast<const float *>(d + D_WY);
+    const unsigned char *phr = reinterpret_cast<const unsigned char *>(d + D_PHR);
+    {
+        int4 a = *reinterpret_cast<const int4 *>(d + D_XLO), b = *reinterpret_cast<const int4 *>(d + D_XLO + 4);
+        xo[0] = a.x * xs; xo[1] = a.y * xs; xo[2] = a.z * xs; xo[3] = a.w * xs;
+        xo[4] = b.x * xs; xo[5] = b.y * xs; xo[6] = b.z * xs;
+    }
+#pragma unroll
+    for (int pw = 0; pw < PW; ++pw) {
+        float4 a = *reinterpret_cast<const float4 *>(dwx + pw * MAXT);
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (T > 4) b = *reinterpret_cast<const float4 *>(dwx + pw * MAXT + 4);
+        float t8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int l = 0; l < T; ++l) wx[pw][l] = t8[l];
+    }
+    const int pb = d[D_Y0] >> 1, p1 = (d[D_Y1] + 1) >> 1;
+#pragma unroll 1
+    for (int p = pb; p < p1; ++p) {
+        float2 r[PW];
+#pragma unroll
+        for (int pw = 0; pw < PW; ++pw) r[pw] = make_float2(0.f, 0.f);
+        const int code = phr[p - pb];
+        const int ph_end = (code & 15) + (code >> 4);
+#pragma unroll 1
+        for (int ph = code & 15; ph < ph_end; ++ph) {
+            const int dd = 2 * p - d[D_YLO + ph];
+            const float2 w = make_float2(dwy[ph * WYP + dd + 1], dwy[ph * WYP + dd + 2]);
+            const float *gp = g + ph * PW;
+#pragma unroll
+            for (int pw = 0; pw < PW; ++pw) {
+                float gv = gp[pw];
+                if (FUSED) gv = fmaf(gp[STAGE_FLOATS + pw], __ldg(m + ph * PW + pw), gv);
+                r[pw] = __ffma2_rn(bcast2(gv), w, r[pw]);
+            }
+        }
+        float2 *row = base2 + (size_t)p * W * xs;
+#pragma unroll
+        for (int pw = 0; pw < PW; ++pw)
+#pragma unroll
+            for (int l = 0; l < T; ++l)
+                red_add2(row + xo[pw] + l * xs, make_float2(wx[pw][l] * r[pw].x, wx[pw][l] * r[pw].y));
+    }
+}
+
+constexpr int BWG_MAX_WARPS = 11;
+
+template <bool FUSED>
+__global__ void __launch_bounds__(BWG_MAX_WARPS * 32, 1)
+roi_align_bwd_glob_kernel(const float *__restrict__ grad_out, const int *__restrict__ hdr,
+                          const int *__restrict__ img_start, const int *__restrict__ descs,
+                          const float *__restrict__ mask7, float *__restrict__ gradP, int B, int C, int H, int W) {
+    constexpr int GST = FUSED ? 2 * STAGE_FLOATS : STAGE_FLOATS;     // gradient floats per (roi, chunk)
+    extern __shared__ __align__(128) float smem[];
+    const int nw = blockDim.x >> 5;
+    float *stages = smem;                                             // [nw][2][GST]
+    int *dslots = reinterpret_cast<int *>(stages + (size_t)nw * 2 * GST);   // [nw][2][DESC_WORDS]
+    if (__ldg(hdr) != 0) return;              // rois not grouped by image: the generic kernel does it all
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nchunks = C / CH, Cg = FUSED ? 2 * C : C;
+    const int s0 = __ldg(img_start), sB = __ldg(img_start + B);
+    const long long U = (long long)nchunks * (sB - s0);
+    long long u = U * blockIdx.x / gridDim.x;
+    const long long u_end = U * (blockIdx.x + 1) / gridDim.x;
+    float *my_stage = stages + (size_t)warp * 2 * GST;
+    int *my_slots = dslots + warp * 2 * DESC_WORDS;
+    const int hp2 = (H + 1) >> 1;
+
+    auto prefetch = [&](int roi, int c0, int slot) {
+        const int *src = descs + (size_t)roi * DESC_WORDS;
+        int *dst = my_slots + slot * DESC_WORDS;
+        cp_async16(dst + lane * 4, src + lane * 4);
+        if (lane < DESC_WORDS / 4 - 32) cp_async16(dst + (32 + lane) * 4, src + (32 + lane) * 4);
+        const float *gs = grad_out + ((size_t)roi * Cg + c0) * NBIN;
+        float *gd = my_stage + slot * GST;
+        for (int i = lane; i < STAGE_FLOATS / 4; i += 32) {
+            cp_async16(gd + i * 4, gs + i * 4);
+            if (FUSED) cp_async16(gd + STAGE_FLOATS + i * 4, gs + (size_t)C * NBIN + i * 4);
+        }
+        cp_async_commit();
+    };
+
+    int b = 0;
+    while (u < u_end) {
+        while (b < B && (long long)nchunks * (__ldg(img_start + b + 1) - s0) <= u) ++b;
+        const int is = __ldg(img_start + b), nroi = __ldg(img_start + b + 1) - is;
+        const long long base = (long long)nchunks * (is - s0);
+        const int ch = (int)((u - base) / nroi);
+        const int r0 = (int)((u - base) - (long long)ch * nroi);
+        const int r1 = (int)min((long long)nroi, r0 + (u_end - u));
+        const int c0 = ch * CH;
+        float2 *base2 = reinterpret_cast<float2 *>(gradP) + ((size_t)b * hp2 * W) * C + c0 + lane;
+
+        int r = r0 + warp, slot = 0;
+        if (r < r1) prefetch(is + r, c0, 0);
+        while (r < r1) {
+            const int rn = r + nw;
+            if (rn < r1) { prefetch(is + rn, c0, slot ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+            __syncwarp();
+            const int *d = my_slots + slot * DESC_WORDS;
+            if ((d[D_FLAGY] | d[D_FLAGX]) == 0) {
+                const float *g = my_stage + slot * GST + lane * NBIN;
+                const float *m = FUSED ? mask7 + (size_t)(is + r) * NBIN : nullptr;
+                switch (d[D_TX]) {
+                    case 2: bwd_pairs_glob<2, FUSED>(base2, W, C, d, g, m); break;
+                    case 3: bwd_pairs_glob<3, FUSED>(base2, W, C, d, g, m); break;
+                    case 4: bwd_pairs_glob<4, FUSED>(base2, W, C, d, g, m); break;
+                    case 6: bwd_pairs_glob<6, FUSED>(base2, W, C, d, g, m); break;
+                    default: bwd_pairs_glob<8, FUSED>(base2, W, C, d, g, m); break;
+                }
+            }
+            __syncwarp();
+            slot ^= 1;
+            r = rn;
+        }
+        u += r1 - r0;
+    }
+}
+
 // ------------------------------------------------------------------------------- generic path
 struct Geom {
     int b, gh, gw;
@@ -838,9 +1034,9 @@ __global__ void roi_mask_pad_kernel(const float *__restrict__ m, float *__restri
 
 // ------------------------------------------------------------------------------------- host
 struct Plan {
-    bool tile;
-    int pitch, fwd_warps, wyd_floats;
-    size_t smem_fwd, smem_bwd, smem_bwd_fused;
+    bool tile, glob;                 // glob: map too large for shared memory -> channel-last global copy
+    int pitch, fwd_warps, wyd_floats, glob_bwd_warps, glob_bwd_warps_fused;
+    size_t smem_fwd, smem_bwd, smem_bwd_fused, smem_fwd_glob, smem_bwd_glob, smem_bwd_glob_fused;
 };
 static Plan make_plan(int C, int H, int W, int oh, int ow) {
     Plan p{};
@@ -858,6 +1054,15 @@ static Plan make_plan(int C, int H, int W, int oh, int ow) {
     p.smem_bwd_fused = (size_t)CH * p.pitch * 4 + (size_t)NS_F * SLOT_FLOATS_F * 4 + 2 * NS_F * 8;
     p.tile = oh == PH && ow == PW && (C % CH) == 0 && W >= MAXT && p.smem_fwd <= cap &&
              p.smem_bwd <= cap && p.smem_bwd_fused <= cap && (((size_t)CH * p.pitch * 4) % 16 == 0);
+    // large maps (VGG-16: 64 x 64): same sweeps over a channel-last copy in global memory
+    p.smem_fwd_glob = FWD_GLOB_WARPS * per_warp;
+    const size_t bw = (size_t)2 * STAGE_FLOATS * 4 + 2 * DESC_WORDS * 4, bwf = bw + (size_t)2 * STAGE_FLOATS * 4;
+    p.glob_bwd_warps = BWG_MAX_WARPS;
+    p.glob_bwd_warps_fused = (int)std::min<size_t>(BWG_MAX_WARPS, cap / bwf);
+    p.smem_bwd_glob = p.glob_bwd_warps * bw;
+    p.smem_bwd_glob_fused = p.glob_bwd_warps_fused * bwf;
+    p.glob = !p.tile && oh == PH && ow == PW && (C % CH) == 0 && W >= MAXT && H <= 512 && p.smem_fwd_glob <= cap &&
+             p.smem_bwd_glob <= cap && p.glob_bwd_warps_fused >= 4;
     return p;
 }
 
@@ -894,6 +1099,15 @@ static int run_prep(const float *rois, int B, int H, int W, int K, int oh, int o
 
 }  // namespace
 
+static size_t glob_copy_bytes(int B, int C, int H, int W) { return sizeof(float) * (size_t)B * C * ((H + 1) & ~1) * W; }
+static size_t ws_glob_off(int K) { return (cim_roi_align_workspace_bytes(K) + 255) & ~(size_t)255; }
+
+CIM_API size_t cim_roi_align_workspace_bytes_ex(int B, int C, int H, int W, int K, int oh, int ow) {
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || oh <= 0 || ow <= 0) return cim_roi_align_workspace_bytes(K);
+    const Plan p = make_plan(C, H, W, oh, ow);
+    return p.glob ? ws_glob_off(K) + glob_copy_bytes(B, C, H, W) : cim_roi_align_workspace_bytes(K);
+}
+
 CIM_API size_t cim_roi_align_workspace_bytes(int K) {
     // header + image ranges (up to 4096 images) + descriptors
     return WS_HDR_BYTES + 4097 * sizeof(int) + 64 + (size_t)(K > 0 ? K : 0) * (DESC_WORDS + MASK_PAD) * 4;
@@ -911,17 +1125,30 @@ static int roi_fwd_impl(const float *feat, const float *rois, const float *mask7
     const RoiWs w = carve(ws, B, K);
     const int per_roi = C * oh * ow;
     dim3 ggrid((unsigned)K, (unsigned)min(64, (per_roi + 255) / 256));
-    if (!p.tile) {
+    const bool glob = !p.tile && p.glob && ws_bytes >= ws_glob_off(K) + glob_copy_bytes(B, C, H, W);
+    if (!p.tile && !glob) {
         roi_align_generic_kernel<false><<<ggrid, 256, 0, st>>>(feat, rois, out, nullptr, nullptr, mask7, 0, B, C, H, W,
                                                                K, oh, ow, scale, sr, aligned);
         return cim_launch_status();
     }
     if ((rc = run_prep(rois, B, H, W, K, oh, ow, scale, sr, aligned, w, st))) return rc;
-    cudaFuncSetAttribute(roi_align_fwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_fwd);
     const long long units = (long long)(C / CH) * K;
     const int grid = (int)min((long long)cim_num_sms(), units);
-    roi_align_fwd_tile_kernel<<<grid, p.fwd_warps * 32, p.smem_fwd, st>>>(feat, w.hdr, w.img_start, w.desc, mask7, out,
-                                                                           B, C, H, W, p.pitch, p.wyd_floats);
+    if (glob) {
+        float *featP = reinterpret_cast<float *>((char *)ws + ws_glob_off(K));
+        dim3 cg((unsigned)((W + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)(B * ((H + 1) >> 1)));
+        nchw_to_pairs_kernel<<<cg, 256, 0, st>>>(feat, reinterpret_cast<float2 *>(featP), C, H, W);
+        if ((rc = cim_launch_status())) return rc;
+        cudaFuncSetAttribute(roi_align_fwd_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)p.smem_fwd_glob);
+        roi_align_fwd_tile_kernel<true><<<grid, FWD_GLOB_WARPS * 32, p.smem_fwd_glob, st>>>(
+            featP, w.hdr, w.img_start, w.desc, mask7, out, B, C, H, W, p.pitch, p.wyd_floats);
+    } else {
+        cudaFuncSetAttribute(roi_align_fwd_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)p.smem_fwd);
+        roi_align_fwd_tile_kernel<false><<<grid, p.fwd_warps * 32, p.smem_fwd, st>>>(
+            feat, w.hdr, w.img_start, w.desc, mask7, out, B, C, H, W, p.pitch, p.wyd_floats);
+    }
     if ((rc = cim_launch_status())) return rc;
     // leftover pass: one CTA per ROI, which exits at once unless the tile kernel skipped that ROI
     roi_align_generic_kernel<false><<<dim3((unsigned)K, 1), 256, 0, st>>>(feat, rois, out, w.hdr, w.desc, mask7, 1, B,
@@ -944,7 +1171,8 @@ static int roi_bwd_impl(const float *grad_out, const float *rois, const float *m
     const RoiWs w = carve(ws, B, K);
     const int per_roi = C * oh * ow;
     dim3 ggrid((unsigned)max(K, 1), (unsigned)min(64, (per_roi + 255) / 256));
-    if (!p.tile || K == 0) {
+    const bool glob = !p.tile && p.glob && K > 0 && ws_bytes >= ws_glob_off(K) + glob_copy_bytes(B, C, H, W);
+    if ((!p.tile && !glob) || K == 0) {
         cudaMemsetAsync(grad_feat, 0, sizeof(float) * (size_t)B * C * H * W, st);
         if (K > 0)
             roi_align_generic_kernel<true><<<ggrid, 256, 0, st>>>(grad_out, rois, grad_feat, nullptr, nullptr, mask7, 0,
@@ -952,9 +1180,33 @@ static int roi_bwd_impl(const float *grad_out, const float *rois, const float *m
         return cim_launch_status();
     }
     if ((rc = run_prep(rois, B, H, W, K, oh, ow, scale, sr, aligned, w, st))) return rc;
-    cudaMemsetAsync(grad_feat, 0, sizeof(float) * (size_t)B * C * H * W, st);
     const long long units = (long long)(C / CH) * K;
     const int grid = (int)min((long long)cim_num_sms(), units);
+    if (glob) {
+        // gradients accumulate (red.global.add) in the channel-last pairs copy, which is then written out as NCHW
+        float *gradP = reinterpret_cast<float *>((char *)ws + ws_glob_off(K));
+        cudaMemsetAsync(gradP, 0, glob_copy_bytes(B, C, H, W), st);
+        if (mask7) {
+            cudaFuncSetAttribute(roi_align_bwd_glob_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)p.smem_bwd_glob_fused);
+            roi_align_bwd_glob_kernel<true><<<grid, p.glob_bwd_warps_fused * 32, p.smem_bwd_glob_fused, st>>>(
+                grad_out, w.hdr, w.img_start, w.desc, mask7, gradP, B, C, H, W);
+        } else {
+            cudaFuncSetAttribute(roi_align_bwd_glob_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)p.smem_bwd_glob);
+            roi_align_bwd_glob_kernel<false><<<grid, p.glob_bwd_warps * 32, p.smem_bwd_glob, st>>>(
+                grad_out, w.hdr, w.img_start, w.desc, nullptr, gradP, B, C, H, W);
+        }
+        if ((rc = cim_launch_status())) return rc;
+        dim3 cg((unsigned)((W + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)(B * ((H + 1) >> 1)));
+        pairs_to_nchw_kernel<<<cg, 256, 0, st>>>(reinterpret_cast<const float2 *>(gradP), grad_feat, C, H, W);
+        if ((rc = cim_launch_status())) return rc;
+        roi_align_generic_kernel<true><<<dim3((unsigned)K, 1), 256, 0, st>>>(grad_out, rois, grad_feat, w.hdr, w.desc,
+                                                                             mask7, 1, B, C, H, W, K, oh, ow, scale, sr,
+                                                                             aligned);
+        return cim_launch_status();
+    }
+    cudaMemsetAsync(grad_feat, 0, sizeof(float) * (size_t)B * C * H * W, st);
     if (mask7) {
         roi_mask_pad_kernel<<<(K * MASK_PAD + 255) / 256, 256, 0, st>>>(mask7, w.maskpad, K, NBIN);
         if ((rc = cim_launch_status())) return rc;

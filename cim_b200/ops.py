@@ -48,7 +48,8 @@ class RoIAlignFunction(Function):
         K = rois.size(0)
         L = _lib.lib()
         with torch.cuda.device(feat.device):
-            ws = torch.empty(L.cim_roi_align_workspace_bytes(K), dtype=torch.uint8, device=feat.device)
+            ws = torch.empty(L.cim_roi_align_workspace_bytes_ex(B, Cc, H, W, K, oh, ow), dtype=torch.uint8,
+                             device=feat.device)
             out = torch.empty((K, Cc, oh, ow), dtype=torch.float32, device=feat.device)
             rc = L.cim_roi_align_fwd(_lib.ptr(feat), _lib.ptr(rois), _lib.ptr(out), B, Cc, H, W, K, oh, ow,
                                      float(spatial_scale), int(sampling_ratio), int(bool(aligned)),
@@ -67,7 +68,8 @@ class RoIAlignFunction(Function):
         K = rois.size(0)
         L = _lib.lib()
         with torch.cuda.device(grad_out.device):
-            ws = torch.empty(L.cim_roi_align_workspace_bytes(K), dtype=torch.uint8, device=grad_out.device)
+            ws = torch.empty(L.cim_roi_align_workspace_bytes_ex(B, Cc, H, W, K, oh, ow), dtype=torch.uint8,
+                             device=grad_out.device)
             grad_feat = torch.empty((B, Cc, H, W), dtype=torch.float32, device=grad_out.device)
             rc = L.cim_roi_align_bwd(_lib.ptr(grad_out), _lib.ptr(rois), _lib.ptr(grad_feat), B, Cc, H, W, K, oh,
                                      ow, scale, sr, aligned, _lib.ptr(ws), ws.numel(),
@@ -126,7 +128,8 @@ class RoIAlignMaskFuseFunction(Function):
         masks = masks.reshape(K, oh, ow).contiguous()
         L = _lib.lib()
         with torch.cuda.device(feat.device):
-            ws = torch.empty(L.cim_roi_align_workspace_bytes(K), dtype=torch.uint8, device=feat.device)
+            ws = torch.empty(L.cim_roi_align_workspace_bytes_ex(B, Cc, H, W, K, oh, ow), dtype=torch.uint8,
+                             device=feat.device)
             out = torch.empty((K, 2 * Cc, oh, ow), dtype=torch.float32, device=feat.device)
             rc = L.cim_roi_align_maskfuse_fwd(_lib.ptr(feat), _lib.ptr(rois), _lib.ptr(masks), _lib.ptr(out), B, Cc, H,
                                               W, K, oh, ow, float(spatial_scale), int(sampling_ratio),
@@ -146,7 +149,8 @@ class RoIAlignMaskFuseFunction(Function):
         K = rois.size(0)
         L = _lib.lib()
         with torch.cuda.device(grad_out.device):
-            ws = torch.empty(L.cim_roi_align_workspace_bytes(K), dtype=torch.uint8, device=grad_out.device)
+            ws = torch.empty(L.cim_roi_align_workspace_bytes_ex(B, Cc, H, W, K, oh, ow), dtype=torch.uint8,
+                             device=grad_out.device)
             grad_feat = torch.empty((B, Cc, H, W), dtype=torch.float32, device=grad_out.device)
             rc = L.cim_roi_align_maskfuse_bwd(_lib.ptr(grad_out), _lib.ptr(rois), _lib.ptr(masks), _lib.ptr(grad_feat),
                                               B, Cc, H, W, K, oh, ow, scale, sr, aligned, _lib.ptr(ws), ws.numel(),

@@ -57,7 +57,8 @@ class CIMHeadStep:
         with torch.cuda.device(dev):
             self.roi_out = e((n_img * R, feat_channels, 7, 7), torch.float32)
             self.grad_feat = e((n_img, feat_channels, feat_h, feat_w), torch.float32)
-            self.roi_ws = e((self.L.cim_roi_align_workspace_bytes(n_img * R),), torch.uint8)
+            self.roi_ws = e((self.L.cim_roi_align_workspace_bytes_ex(n_img, feat_channels, feat_h, feat_w, n_img * R,
+                                                                     7, 7),), torch.uint8)
             self.iou = e((n_img, R, R), torch.float16)
             self.asy = e((n_img, R, R), torch.float16)
             self.area = e((n_img, R), torch.int32)
@@ -205,10 +206,18 @@ class CIMHeadStep:
             self.n_crop_words = 0
         else:
             self.hi_masks = pin((n_img, R, self.words), torch.int32)
-        self.ho_labels = pin((k, n_img, R, C1), torch.float32)
-        self.ho_iou = pin((k, n_img, R), torch.float16)
-        self.ho_weights = pin((k, n_img, R), torch.float32)
+        # what the host reads back every step: with the loss block in the step (head_grads) the step's result
+        # is its losses -- the pseudo labels stay on the device, where the reference keeps them too
+        # (model_builder.py:192-196); without it, the pseudo labels themselves
         self.ho_valid = pin((k, n_img), torch.uint8)
+        if self.head_grads:
+            self.ho_losses = pin((n_img, k + 1, 3), torch.float32)
+            results = (self.ho_losses, self.ho_valid)
+        else:
+            self.ho_labels = pin((k, n_img, R, C1), torch.float32)
+            self.ho_iou = pin((k, n_img, R), torch.float16)
+            self.ho_weights = pin((k, n_img, R), torch.float32)
+            results = (self.ho_labels, self.ho_iou, self.ho_weights, self.ho_valid)
         self.ho_checksum = pin((2,), torch.float32)
         with torch.cuda.device(self.dev):
             dv = lambda shape, dt: torch.empty(shape, dtype=dt, device=self.dev)
@@ -224,8 +233,7 @@ class CIMHeadStep:
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in (self.hi_rois, self.hi_labels))
         if not self.crop_cap:
             self.h2d_bytes += self.hi_masks.numel() * 4
-        self.d2h_bytes = sum(t.numel() * t.element_size() for t in
-                             (self.ho_labels, self.ho_iou, self.ho_weights, self.ho_valid, self.ho_checksum))
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in results + (self.ho_checksum,))
         self.d2h_bytes += sum(t.numel() * t.element_size() for t in (self.h_count, self.h_class, self.h_weight))
         self.h2d_bytes += self.h_keep.numel()
         self._slot = 0
@@ -288,9 +296,12 @@ class CIMHeadStep:
         buf["free"].record(cur_stream)
         self.d_checksum[0] = self.roi_out.view(-1)[::4099].sum()
         self.d_checksum[1] = self.grad_feat.view(-1)[::127].sum()
-        self.ho_labels.copy_(self.pseudo_labels, non_blocking=True)
-        self.ho_iou.copy_(self.pseudo_iou, non_blocking=True)
-        self.ho_weights.copy_(self.loss_weights, non_blocking=True)
+        if self.head_grads:
+            self.ho_losses.copy_(self.losses, non_blocking=True)
+        else:
+            self.ho_labels.copy_(self.pseudo_labels, non_blocking=True)
+            self.ho_iou.copy_(self.pseudo_iou, non_blocking=True)
+            self.ho_weights.copy_(self.loss_weights, non_blocking=True)
         self.ho_valid.copy_(self.valid, non_blocking=True)
         self.ho_checksum.copy_(self.d_checksum, non_blocking=True)
         cur_stream.synchronize()                               # the host reads the results every step

@@ -52,6 +52,13 @@ const char *cim_error_string(int code);
  * workspace: cim_roi_align_workspace_bytes(K) bytes, 16-byte aligned; contents are private.
  * The forward and the backward of one autograd node may share the workspace. */
 size_t cim_roi_align_workspace_bytes(int K);
+/* Feature maps too large for the shared-memory tile (32 channels x H x W fp32 > ~130 KB, e.g. VGG-16's 64 x 64 at
+ * stride 8) are swept through a channel-last copy of the map kept in the workspace; that needs
+ * cim_roi_align_workspace_bytes_ex() bytes (>= cim_roi_align_workspace_bytes(K); equal for maps that fit).  With
+ * the smaller workspace such maps fall back to the generic one-thread-per-element kernels.  On this path the
+ * backward accumulates with red.global.add, so its summation order is not fixed (the reference's atomicAdd
+ * backward is not either). */
+size_t cim_roi_align_workspace_bytes_ex(int B, int C, int H, int W, int K, int oh, int ow);
 int cim_roi_align_fwd(const float *feat, const float *rois, float *out,
                       int B, int C, int H, int W, int K, int oh, int ow,
                       float spatial_scale, int sampling_ratio, int aligned,

@@ -274,3 +274,39 @@ def test_maskfuse_full_size_adjoint():
     lhs = (out.double() * g.double()).sum().item()
     rhs = (feat.detach().double() * gf.double()).sum().item()
     assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), 1.0)
+
+
+# ------------------------------------------------------------------ large maps: channel-last global path
+@pytest.mark.parametrize("fused", [False, True])
+def test_vgg16_sized_map_uses_the_global_path_and_matches_oracle(fused):
+    """BASELINE.json configs[2]: VGG-16, stride 8 -> a 64 x 64 map that does not fit the shared-memory tile.
+    With the _ex workspace the sweep runs over a channel-last copy in global memory."""
+    C, H, W, scale = 64, 64, 64, 1.0 / 8
+    feat = torch.randn(2, C, H, W, generator=torch.Generator().manual_seed(21))
+    rois = torch.cat([synth.rois_from_params(synth.proposal_params(150, 512, 21 + b), b) for b in range(2)])
+    if fused:
+        masks = (torch.rand(300, 7, 7, generator=torch.Generator().manual_seed(22)) > 0.5).float()
+        out, gf, g = run_maskfuse(feat, rois, masks, scale, 0, True)
+        want, want_g = maskfuse_oracle(feat, rois, masks, scale, 0, True, g)
+    else:
+        out, gf, want, want_g = run_both(feat, rois, scale, 0, True)
+    close(out, want)
+    close(gf, want_g)
+
+
+def test_large_map_small_workspace_falls_back_to_generic():
+    """The plain cim_roi_align_workspace_bytes(K) workspace is still accepted: the generic kernels run."""
+    import ctypes as C_
+    from cim_b200 import _lib
+    L = _lib.lib()
+    B, C, H, W, K, scale = 1, 32, 64, 64, 40, 1.0 / 8
+    feat = torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(23))
+    rois = synth.rois_from_params(synth.proposal_params(K, 512, 23))
+    f, r = feat.to(DEV), rois.to(DEV)
+    assert L.cim_roi_align_workspace_bytes_ex(B, C, H, W, K, 7, 7) > L.cim_roi_align_workspace_bytes(K)
+    assert L.cim_roi_align_workspace_bytes_ex(B, 1024, 32, 32, K, 7, 7) == L.cim_roi_align_workspace_bytes(K)
+    ws = torch.empty(L.cim_roi_align_workspace_bytes(K), dtype=torch.uint8, device=DEV)
+    out = torch.empty(K, C, 7, 7, device=DEV)
+    _lib.check(L.cim_roi_align_fwd(_lib.ptr(f), _lib.ptr(r), _lib.ptr(out), B, C, H, W, K, 7, 7, scale, 0, 1,
+                                   _lib.ptr(ws), ws.numel(), _lib.stream_ptr(torch.device(DEV))), "fwd")
+    close(out.cpu().numpy(), roi_oracle.roi_align_fwd(feat.numpy(), rois.numpy(), 7, 7, scale, 0, True))

@@ -36,7 +36,7 @@ def main():
     gout = torch.randn(K, Cf, 7, 7, device=dev, generator=g)
     gfeat = torch.empty_like(feat)
     L = _lib.lib()
-    ws = torch.empty(L.cim_roi_align_workspace_bytes(K), dtype=torch.uint8, device=dev)
+    ws = torch.empty(L.cim_roi_align_workspace_bytes_ex(B, Cf, H, W, K, 7, 7), dtype=torch.uint8, device=dev)
     st = _lib.stream_ptr(dev)
 
     def fwd():
