@@ -3,7 +3,7 @@
 
 A step = one pass of the hot path over one batch of synthetic images:
 RoIAlign fwd + RoIAlign bwd + mask IoU/containment + scoring heads fwd + 3 x (mining + assignment) + the loss
-block (fwd + bwd) + scoring heads bwd (head gradients, averaged over the ranks with one NCCL allreduce when N > 1).
+block incl. PCL_loss (fwd + bwd) + scoring heads bwd (head gradients, averaged over the ranks with one NCCL allreduce when N > 1).
 Workload = BASELINE.json configs[1]: ResNet-50 VOC, 8 images x 2000 mask proposals per GPU
 (512x512 images -> 1024x32x32 features, 512x512 bit-packed proposal masks, 20 classes).
 
@@ -28,7 +28,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "CIM-head images/s (ROIAlign fwd+bwd + mask IoU + scoring fwd+bwd + mining + losses)"
+METRIC = "CIM-head images/s (ROIAlign fwd+bwd + mask IoU + scoring fwd+bwd + mining + losses incl. PCL)"
 WORKLOADS = {
     # name: backbone, images per GPU, proposals, classes, present classes, mask side
     "cfg2_r50_voc_8x2000": dict(backbone="resnet50", n_img=8, R=2000, C=20, present=2, mask=512),
@@ -61,7 +61,7 @@ def algorithmic_bytes(cfg, Cf, H, W):
         # gradients written
         "score_heads_bwd": 2 * R * 4096 * 4 + 2 * 8 * R * (C + 1) * 4 + 2 * 8 * (C + 1) * 4097 * 4,
         # loss block: scores read, pseudo labels / weights read, grad_scores written
-        "head_losses": 2 * 8 * R * (C + 1) * 4 + 3 * R * (C + 1) * 4 + 3 * R * 6,
+        "head_losses": 2 * 8 * R * (C + 1) * 4 + 3 * R * (C + 1) * 4 + 3 * R * 6 + R * (C + 1) * 4,
     }
 
 
@@ -131,6 +131,7 @@ def cpu_reference(cfg, steps, warmup, sample_rois=128, head_grads=True):
     b = [np.zeros(C + 1, np.float32) for _ in range(8)]
     x = np.random.RandomState(2).randn(R, 4096).astype(np.float32)
     labels = synth.image_labels(C, cfg["present"], 1234).numpy()
+    cmat = synth.cluster_mat(R, C, np.nonzero(labels[0])[0], 6, 1234).numpy()
     from oracle import mask_oracle
     iou16, asy16 = mask_oracle.mask_overlap_maps(masks[:, ::max(1, masks.shape[1] // 4096)])   # setup only
 
@@ -165,6 +166,8 @@ def cpu_reference(cfg, steps, warmup, sample_rois=128, head_grads=True):
             sc = np.stack([p_cls, p_det] + r_cls + r_iou)
             _, g = loss_oracle.head_losses(sc, pl, pi, lw, np.array(ok, np.uint8)[:, None], labels.reshape(1, -1), 3,
                                            dtype=torch.float32)
+            _, g_pcl = loss_oracle.pcl_losses(p_cls, cmat[None], dtype=torch.float32)
+            g[0] += g_pcl
             heads_oracle.score_heads_bwd(x, w, b, list(g))
             t_score += time.perf_counter() - t0
         return (t_roi + t_mask) * (R / S) + t_score + t_mine, dict(roi=t_roi * R / S, mask=t_mask * R / S,
@@ -196,7 +199,7 @@ def build_inputs(cfg, dev, seed_base):
     feat = torch.randn(n_img, Cf, H, W, device=dev, generator=gen)
     grad_out = torch.randn(n_img * R, Cf, 7, 7, device=dev, generator=gen)
     seg_x = torch.randn(n_img * R, 4096, device=dev, generator=gen)
-    rois, packed, packed_flat, labels = [], [], [], []
+    rois, packed, packed_flat, labels, mats = [], [], [], [], []
     kb_per_row = cfg["mask"] // 16 if mask_ops.tiled_ok(cfg["mask"], cfg["mask"]) else 0
     for b in range(n_img):
         params = synth.proposal_params(R, 512, seed_base + b)
@@ -205,12 +208,13 @@ def build_inputs(cfg, dev, seed_base):
         packed.append(mask_ops.mask_pack(m))                         # tiled 8 x 16 patches when the size allows
         packed_flat.append(mask_ops.mask_pack(m, layout="flat").cpu())   # only to derive the host wire format
         labels.append(synth.image_labels(C, cfg["present"], seed_base + b))
+        mats.append(synth.cluster_mat(R, C, np.nonzero(labels[-1][0].numpy())[0], 6, seed_base + b))
     torch.manual_seed(0)
     model = heads.cls_iou_model(4096, C + 1, 3).to(dev)
     weight, bias = (t.detach().contiguous() for t in model._stacked())
     labels = torch.cat(labels)
     return dict(feat=feat, rois=torch.cat(rois).to(dev), grad_out=grad_out, packed=torch.stack(packed),
-                packed_flat=torch.stack(packed_flat), kb_per_row=kb_per_row,
+                packed_flat=torch.stack(packed_flat), kb_per_row=kb_per_row, mat=torch.stack(mats).to(dev),
                 seg_x=seg_x, weight=weight, bias=bias, labels=labels.to(dev), labels_host=labels.numpy(),
                 shape=(Cf, H, W, scale))
 
@@ -266,10 +270,12 @@ def time_stages(step, inp, iters=5):
                                                          P(step.grad_scores), P(step.grad_seg_x), P(step.grad_weight),
                                                          P(step.grad_bias), n_img, R, step.D, step.C + 1, step.K,
                                                          P(step.score_bwd_ws), step.score_bwd_ws.numel(), st),
-        "head_losses": lambda: L.cim_head_losses(P(step.scores), P(step.pseudo_labels), P(step.pseudo_iou),
-                                                 P(step.loss_weights), P(step.valid), P(inp["labels"]), P(step.losses),
-                                                 P(step.grad_scores), n_img, R, step.C, step.K, step.K, 3.0, 1.0, 3.0,
-                                                 1.0 / n_img, st),
+        "head_losses": lambda: (L.cim_head_losses(P(step.scores), P(step.pseudo_labels), P(step.pseudo_iou),
+                                                  P(step.loss_weights), P(step.valid), P(inp["labels"]), P(step.losses),
+                                                  P(step.grad_scores), n_img, R, step.C, step.K, step.K, 3.0, 1.0, 3.0,
+                                                  1.0 / n_img, st) or
+                                L.cim_pcl_loss(P(step.scores), P(inp["mat"]), P(step.pcl_loss), P(step.grad_scores), n_img,
+                                               R, step.C + 1, 127, 1.0 / n_img, 1, st)),
         "mine": lambda: L.cim_mine(C.byref(p), step.cls_ptrs, step.det_ptrs, P(inp["labels"]), P(step.iou),
                                    P(step.asy), P(step.gt_count), P(step.gt_rows), P(step.gt_class),
                                    P(step.gt_weight), P(step.asy_flag), P(step.mine_ws), step.mine_ws.numel(), st),
@@ -331,7 +337,7 @@ def main():
 
     import torch
     from cim_b200 import dist as cdist
-    from cim_b200.step import CIMHeadStep, KERNELS_HEAD_GRADS, KERNELS_PER_STEP
+    from cim_b200.step import CIMHeadStep, KERNELS_HEAD_GRADS, KERNELS_PCL, KERNELS_PER_STEP
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     rank, world, local = cdist.init_from_env()
@@ -345,8 +351,9 @@ def main():
     step = CIMHeadStep(cfg["n_img"], cfg["R"], cfg["C"], Cf, H, W, scale, words, anti_noise_sampling=not args.no_anti_noise,
                        max_present=max(4, 2 * cfg["present"]), device=dev, mask_kb_per_row=inp["kb_per_row"],
                        head_grads=not args.no_head_grads)
+    mat = None if args.no_head_grads else inp["mat"]
     run = lambda: step.run(inp["feat"], inp["rois"], inp["grad_out"], inp["packed"], inp["seg_x"], inp["weight"],
-                           inp["bias"], inp["labels"], inp["labels_host"])
+                           inp["bias"], inp["labels"], inp["labels_host"], mat=mat)
     np.random.seed(3)
     for _ in range(max(args.warmup, 3)):
         run()
@@ -378,7 +385,7 @@ def main():
     step.hi_rois.copy_(inp["rois"])
     step.hi_labels.copy_(inp["labels"])
     step.set_host_crops(crops)
-    run_host = lambda: step.run_host(inp["feat"], inp["grad_out"], inp["seg_x"], inp["weight"], inp["bias"])
+    run_host = lambda: step.run_host(inp["feat"], inp["grad_out"], inp["seg_x"], inp["weight"], inp["bias"], mat=mat)
     for _ in range(2):
         run_host()
     cdist.barrier()
@@ -445,7 +452,7 @@ def main():
                                 "pseudo labels / IoU labels / loss weights, valid flags, checksums, sampling-hop lists",
                 "pipelining": "H2D of step i+1 on a copy stream overlaps the kernels of step i; results are read "
                               "back and the host synchronises every step"},
-        "gpu_launches": (KERNELS_PER_STEP + (0 if args.no_head_grads else KERNELS_HEAD_GRADS)) * args.steps,
+        "gpu_launches": (KERNELS_PER_STEP + (0 if args.no_head_grads else KERNELS_HEAD_GRADS + KERNELS_PCL)) * args.steps,
         "collective": ("none (single process)" if world == 1 else
                        f"NCCL allreduce (avg) of the {step.head_bucket.numel() * 4} B head-gradient bucket per step, "
                        "inside the timed region, overlapped with the RoIAlign kernels") if not args.no_head_grads

@@ -56,6 +56,7 @@ _SIGNATURES = {
     "cim_score_heads_bwd_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I]),
     "cim_score_heads_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _SZ, _P]),
     "cim_head_losses": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _F, _P]),
+    "cim_pcl_loss": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
     "cim_test_scores": (_I, [_P, _P, _I64, _I, _I, _P]),
     "cim_box_nms": (_I, [_P, _P, _I, _I, _I, _F, _F, _P, _P]),
     "cim_sizeof_mine_params": (_SZ, []),

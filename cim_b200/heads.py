@@ -307,6 +307,44 @@ def head_losses(scores, assigned, labels, k, lmda=(3.0, 1.0), iou_weight=3.0):
                 bag_loss=losses[:, :, 2].sum(1))
 
 
+class PCLLossFunction(Function):
+    """cim_pcl_loss: heads.PCL_loss (heads.py:10-41) forward + backward in one launch, n_img images at once."""
+
+    @staticmethod
+    def forward(ctx, predict_cls, mat, n_img, max_id):
+        _lib.require_cuda(predict_cls, "predict_cls", torch.float32)
+        _lib.require_cuda(mat, "mat", torch.float32)
+        predict_cls, mat = predict_cls.contiguous(), mat.contiguous()
+        m, c1 = predict_cls.shape
+        R = m // n_img
+        if mat.numel() != m * c1 or m % n_img:
+            raise ValueError("mat must be [n_img, R, C+1] matching predict_cls [n_img*R, C+1]")
+        with torch.cuda.device(predict_cls.device):
+            loss = torch.empty((n_img,), dtype=torch.float32, device=predict_cls.device)
+            grad = torch.empty_like(predict_cls)
+            rc = _lib.lib().cim_pcl_loss(_lib.ptr(predict_cls), _lib.ptr(mat), _lib.ptr(loss), _lib.ptr(grad), n_img, R,
+                                         c1, int(max_id), 1.0, 0, _lib.stream_ptr(predict_cls.device))
+        _lib.check(rc, "cim_pcl_loss")
+        ctx.save_for_backward(grad)
+        ctx.shape = (n_img, R)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        n_img, R = ctx.shape
+        return (grad.view(n_img, R, -1) * g.view(n_img, 1, 1)).view_as(grad), None, None, None
+
+
+def PCL_loss(predict_cls, mat, labels=None, n_img=1, max_id=128):
+    """heads.PCL_loss(predict_cls, mat, labels) (heads.py:10-41; `labels` only supplied the device there).
+    n_img = 1 returns a 0-d loss like the reference; n_img > 1 (predict_cls [n_img*R, C+1], mat [n_img, R, C+1])
+    returns one loss per image."""
+    loss = PCLLossFunction.apply(predict_cls, mat, n_img, max_id)
+    return loss[0] if n_img == 1 else loss
+
+
 def refine_scores(ref_cls_score, ref_iou_score):
     """testing_function of lib/modeling/model_builder.py:60-68: per head (cls * iou)[:, 1:]."""
     return [(c * i)[:, 1:] for c, i in zip(ref_cls_score, ref_iou_score)]

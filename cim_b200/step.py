@@ -34,6 +34,8 @@ KERNELS_PER_STEP = 18
 #: + with head_grads: loss block (fwd + bwd), detector dot, activation backward, bias, W^T split, grad_x GEMM,
 #: grad_W GEMM, reduce
 KERNELS_HEAD_GRADS = 8
+#: + with a cluster matrix: PCL_loss forward + backward
+KERNELS_PCL = 1
 
 
 class CIMHeadStep:
@@ -75,6 +77,7 @@ class CIMHeadStep:
                 self.score_bwd_ws = e((self.L.cim_score_heads_bwd_workspace_bytes(n_img, R, feat_dim, C1, k),),
                                       torch.uint8)
                 self.losses = e((n_img, k + 1, 3), torch.float32)
+                self.pcl_loss = torch.zeros((n_img,), dtype=torch.float32, device=dev)
                 self.grad_scores = e((nh, n_img * R, C1), torch.float32)
             p = _lib.MineParams()
             p.n_img, p.R, p.C, p.C1, p.n_layers = n_img, R, n_classes, C1, k
@@ -113,7 +116,8 @@ class CIMHeadStep:
         self.det_ptrs = PtrArr(*[t.data_ptr() for t in det_src])
 
     # -------------------------------------------------------------------------------------
-    def run(self, feat, rois, grad_out, packed_masks, seg_x, weight, bias, labels, labels_host, grad_scores=None):
+    def run(self, feat, rois, grad_out, packed_masks, seg_x, weight, bias, labels, labels_host, grad_scores=None,
+            mat=None):
         """feat [n_img,Cf,H,W] f32, rois [n_img*R,5] f32 grouped by image, grad_out [n_img*R,Cf,7,7]
         f32, packed_masks [n_img,R,words] i32, seg_x [n_img*R,D] f32, weight [2+2K,C+1,D],
         bias [2+2K,C+1], labels [n_img,C] f32 (+ the same on the host as a numpy array).
@@ -121,7 +125,8 @@ class CIMHeadStep:
         loss_weights, valid.  With head_grads=True also losses [n_img, K+1, 3], grad_scores (the loss
         block's backward; pass grad_scores to supply dL/dscores yourself instead), grad_seg_x, grad_weight,
         grad_bias; in a multi-process run the head-gradient bucket is averaged over the ranks (one NCCL
-        allreduce, overlapped with the RoIAlign backward).
+        allreduce, overlapped with the RoIAlign backward).  mat [n_img, R, C+1] (the dataset's proposal-cluster
+        matrix, model_builder.py:125,203) adds PCL_loss: pcl_loss [n_img] and its gradient on the classifier head.
         Order: mask maps, scores, mining | host sampling hop, hidden behind the RoIAlign forward | assignment,
         losses, scoring backward, [allreduce ||] RoIAlign backward."""
         L, p, dev = self.L, self.p, self.dev
@@ -171,6 +176,9 @@ class CIMHeadStep:
                 ck(L.cim_head_losses(P(self.scores), P(self.pseudo_labels), P(self.pseudo_iou), P(self.loss_weights),
                                      P(self.valid), P(labels), P(self.losses), P(self.grad_scores), n_img, R, self.C,
                                      k, k, 3.0, 1.0, 3.0, 1.0 / n_img, st), "cim_head_losses")
+                if mat is not None:                                  # + PCL_loss on predict_cls (model_builder.py:203)
+                    ck(L.cim_pcl_loss(P(self.scores), P(mat), P(self.pcl_loss), P(self.grad_scores), n_img, R,
+                                      self.C + 1, 127, 1.0 / n_img, 1, st), "cim_pcl_loss")
                 grad_scores = self.grad_scores
             ck(L.cim_score_heads_bwd(P(seg_x), P(weight), P(self.scores), P(grad_scores), P(self.grad_seg_x),
                                      P(self.grad_weight), P(self.grad_bias), n_img, R, self.D, self.C + 1, k,
@@ -276,7 +284,7 @@ class CIMHeadStep:
             buf["ready"].record(self.copy_stream)
         return self
 
-    def run_host(self, feat, grad_out, seg_x, weight, bias, prefetch_next=True, grad_scores=None):
+    def run_host(self, feat, grad_out, seg_x, weight, bias, prefetch_next=True, grad_scores=None, mat=None):
         """End-to-end step: host rois / labels / bit-packed masks -> device, the step, results ->
         host.  feat / seg_x / grad_out are produced on the device by the backbone, MaskFuse and
         autograd in the real pipeline and therefore stay device tensors.
@@ -292,7 +300,7 @@ class CIMHeadStep:
             self.stage_host_inputs()                           # goes to the other buffer
         cur_stream.wait_event(buf["ready"])
         self.run(feat, buf["rois"], grad_out, buf["masks"], seg_x, weight, bias, buf["labels"],
-                 buf["labels_host"], grad_scores=grad_scores)
+                 buf["labels_host"], grad_scores=grad_scores, mat=mat)
         buf["free"].record(cur_stream)
         self.d_checksum[0] = self.roi_out.view(-1)[::4099].sum()
         self.d_checksum[1] = self.grad_feat.view(-1)[::127].sum()

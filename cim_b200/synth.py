@@ -86,6 +86,24 @@ def image_labels(num_classes=20, num_present=2, seed=1234):
     return torch.from_numpy(lab)
 
 
+def cluster_mat(num_props, num_classes=20, present=(0, 1), n_fg=6, seed=1234):
+    """float32 [R, C+1] proposal-cluster matrix shaped like tools/pre/AGPL_label_assign.py:60-96 writes it (the `mat`
+    blob PCL_loss consumes): n_fg foreground clusters, each in the column of a present class for ~5 % of the
+    proposals (a later cluster takes over shared rows), then the background cluster's id in column 0 of about half
+    of the untouched rows."""
+    rng = np.random.RandomState(seed + 104729)
+    mat = np.zeros((num_props, num_classes + 1), dtype=np.float32)
+    k = 1
+    for _ in range(n_fg):
+        rows = rng.rand(num_props) < 0.05
+        mat[rows, :] = 0
+        mat[rows, 1 + int(present[rng.randint(len(present))])] = k
+        k += 1
+    free = (mat.sum(1) == 0) & (rng.rand(num_props) < 0.5)
+    mat[free, 0] = k
+    return torch.from_numpy(mat)
+
+
 # Feature-map shapes of a 512x512 image for the reference backbones
 # (lib/modeling/resnet50.py:42-44, vgg16.py:80-81, HRNet.py:316-318).
 BACKBONES = {

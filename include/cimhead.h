@@ -263,6 +263,17 @@ int cim_head_losses(const float *scores, const float *pseudo_labels, const void 
                     float *grad_scores, int n_img, int R, int C, int K, int n_layers, float lmda0,
                     float lmda_rest, float iou_weight, float grad_scale, cim_stream_t stream);
 
+/* cim_pcl_loss: heads.PCL_loss (lib/modeling/heads.py:10-41; called at lib/modeling/model_builder.py:203) forward and
+ *   backward for n_img images.  predict_cls [n_img*R, C1] fp32 (head 0 of the score tensor); mat [n_img, R, C1] fp32
+ *   cluster ids as tools/pre/AGPL_label_assign.py writes them (integers in [0, max_id], 0 = none; the background
+ *   cluster's id lives in column 0).  loss [n_img] fp32 = 12 * loss / (1e-6 + sum of cluster sizes) per image (NaN for
+ *   ids that are not integers in range, or two different ids in column 0 -- the reference asserts there).
+ *   grad_cls [n_img*R, C1] (may be NULL) = grad_scale * d loss / d predict_cls, overwritten, or added to when
+ *   accumulate != 0 (so it can land on top of cim_head_losses' gradient of the same head).  Deterministic.
+ *   C1 <= 128, max_id <= 255, R <= 16384. */
+int cim_pcl_loss(const float *predict_cls, const float *mat, float *loss, float *grad_cls, int n_img, int R, int C1,
+                 int max_id, float grad_scale, int accumulate, cim_stream_t stream);
+
 /* ------------------------------------------------------------------ test-time post-processing
  * cim_test_scores: lib/core/test.py:130-133 over lib/modeling/model_builder.py:60-68 -- the K refinement
  *   heads' (cls * iou)[:, 1:] summed in head order and divided by K.

@@ -6,6 +6,7 @@ is what loss.backward() does in the reference, tools/train.py:436):
   * heads.loss_weight_bag_loss   lib/modeling/heads.py:43-74
   * heads.cls_iou_loss           lib/modeling/heads.py:78-138 (class-specific IoU branch)
   * heads.mil_bag_loss           lib/modeling/heads.py:149-166
+  * heads.PCL_loss               lib/modeling/heads.py:10-41
   * the wiring of lib/modeling/model_builder.py:170-202 (lmda = 3 for layer 0, iou_loss x 3, skipped layers)
 Pinned: oracle/make_golden.py runs the reference's own heads.cls_iou_loss / heads.mil_bag_loss (imported
 unmodified) with autograd on seeded inputs and stores losses + gradients in tests/golden/head_losses.npz; this
@@ -86,3 +87,44 @@ def head_losses(scores, pseudo_labels, pseudo_iou, loss_weights, valid, labels, 
         total = total + mil
     (total * grad_scale).backward()
     return losses.numpy(), scores.grad.numpy()
+
+
+def pcl_loss(predict_cls, mat):
+    """heads.py:10-41 for one image.  predict_cls [R,C1] (requires_grad allowed), mat [R,C1] cluster ids."""
+    mat = torch.as_tensor(mat)
+    col0 = np.setdiff1d(mat[:, 0].numpy(), [0])                         # :13
+    if len(col0) > 1:
+        raise AssertionError("more than one background cluster id")      # :20
+    bg = col0[0] if len(col0) else None
+    loss = torch.zeros((), dtype=predict_cls.dtype)
+    count = 1e-6                                                         # :22
+    for k in np.unique(mat.numpy()):                                     # :23, ascending
+        if k == 0:
+            continue
+        hit = mat == float(k)
+        rows = hit.sum(1) != 0
+        sel = predict_cls[rows]
+        n = sel.shape[0]
+        count += n
+        if bg is None or k != bg:                                        # foreground cluster, :25-32
+            v = sel.mean(0).clamp(LO, HI)
+            t = (hit.sum(0) != 0).to(predict_cls.dtype)
+            loss = loss + n * (-(t * torch.log(v) + (1 - t) * torch.log(1 - v))).mean()
+        else:                                                            # background cluster, :34-39
+            p = sel.clamp(LO, HI)
+            t = (mat[rows] != 0).to(predict_cls.dtype)
+            loss = loss + n * (-(t * torch.log(p) + (1 - t) * torch.log(1 - p))).mean()
+    return 12 * (loss / count)                                           # :40-41
+
+
+def pcl_losses(predict_cls, mat, grad_scale=1.0, dtype=torch.float64):
+    """n_img images: predict_cls [n_img*R, C1], mat [n_img, R, C1] -> (loss [n_img], grad like predict_cls)."""
+    n_img, R, c1 = np.asarray(mat).shape
+    p = torch.as_tensor(np.asarray(predict_cls), dtype=dtype).clone().requires_grad_(True)
+    m = torch.as_tensor(np.asarray(mat), dtype=dtype)
+    losses = [pcl_loss(p[b * R:(b + 1) * R], m[b]) for b in range(n_img)]
+    total = sum(losses) * grad_scale
+    if total.requires_grad:                           # images without any cluster contribute a constant 0
+        total.backward()
+    grad = p.grad.numpy() if p.grad is not None else np.zeros(tuple(p.shape))
+    return np.array([float(l.detach()) for l in losses]), grad

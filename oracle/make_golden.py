@@ -328,6 +328,56 @@ def make_pair_fixture(ref_mu):
     np.savez_compressed(os.path.join(GOLD, "mask_pair.npz"), **out)
 
 
+def synth_cluster_mat(R, c1, n_fg, seed, with_bg=True):
+    """A cluster matrix shaped like tools/pre/AGPL_label_assign.py:60-96 writes it: n_fg foreground clusters, each in
+    one class column for a random subset of rows (later clusters overwrite earlier ones on shared rows), then the
+    background cluster's id in column 0 of some of the untouched rows."""
+    rs = np.random.RandomState(seed)
+    mat = np.zeros((R, c1), np.float32)
+    k = 1
+    for _ in range(n_fg):
+        rows = rs.rand(R) < rs.uniform(0.03, 0.15)
+        mat[rows, :] = 0
+        mat[rows, 1 + rs.randint(c1 - 1)] = k
+        k += 1
+    if with_bg:
+        free = (mat.sum(1) == 0) & (rs.rand(R) < 0.5)
+        mat[free, 0] = k
+    return mat
+
+
+def make_pcl_fixture(ref_heads):
+    """PCL_loss: the reference's own heads.PCL_loss (imported unmodified; its hard `.cuda()` at heads.py:11 is
+    neutralised by making Tensor.cuda the identity for the duration of the call) with autograd."""
+    from oracle import loss_oracle
+    out = {}
+    real_cuda = torch.Tensor.cuda
+    for name, R, c1, n_fg, seed, bg in [("voc_r300", 300, 21, 5, 41, True), ("coco_r257", 257, 81, 9, 42, True),
+                                        ("voc_nobg", 120, 21, 3, 43, False), ("voc_empty", 64, 21, 0, 44, False)]:
+        torch.manual_seed(seed)
+        model = ref_heads.cls_iou_model(64, c1, 3)
+        p = model(torch.randn(R, 64) * 3)[0].detach().clone()
+        p[0, 0], p[1, 1] = 0.0, 1.0                                          # outside the clamp range
+        mat = synth_cluster_mat(R, c1, n_fg, seed, bg)
+        leaf = p.clone().requires_grad_(True)
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        try:
+            loss = ref_heads.PCL_loss(leaf, torch.from_numpy(mat), torch.zeros(1, c1 - 1))
+        finally:
+            torch.Tensor.cuda = real_cuda
+        if loss.requires_grad:                       # no cluster at all: the loss is the constant 0
+            loss.backward()
+        grad = leaf.grad.numpy() if leaf.grad is not None else np.zeros_like(p.numpy())
+        o_loss, o_grad = loss_oracle.pcl_losses(p.numpy(), mat[None])
+        e_l = abs(o_loss[0] - float(loss)) / max(abs(float(loss)), 1e-3)
+        e_g = np.abs(o_grad - grad).max() / max(np.abs(grad).max(), 1e-3)
+        assert e_l < 1e-5 and e_g < 1e-5, (name, e_l, e_g)
+        print(f"pcl {name}: loss {float(loss):.5f}, oracle vs reference loss err {e_l:.1e}, grad err {e_g:.1e}")
+        out[name + "/predict_cls"], out[name + "/mat"] = p.numpy(), mat
+        out[name + "/loss"], out[name + "/grad"] = np.float32(float(loss)), grad
+    np.savez_compressed(os.path.join(GOLD, "pcl_loss.npz"), **out)
+
+
 def make_loss_fixture(ref_heads):
     """Loss block: the reference's own heads.cls_iou_loss / heads.mil_bag_loss (imported unmodified) with
     autograd, wired as model_builder.py:170-202, on the inputs + CIM_layer outputs of stored cim_layer cases."""
@@ -393,6 +443,9 @@ def main():
     if "--only-pair" in sys.argv:
         make_pair_fixture(load_reference()[1])
         return
+    if "--only-pcl" in sys.argv:
+        make_pcl_fixture(load_reference()[0])
+        return
     if "--only-losses" in sys.argv:
         make_loss_fixture(load_reference()[0])
         return
@@ -403,6 +456,7 @@ def main():
     make_scoring_fixture(ref_heads)
     make_nms_fixture()
     make_loss_fixture(ref_heads)
+    make_pcl_fixture(ref_heads)
     make_pair_fixture(ref_mu)
     if "--fuzz" in sys.argv:
         fuzz(ref_heads, ref_mu, int(sys.argv[sys.argv.index("--fuzz") + 1]))

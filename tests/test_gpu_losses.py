@@ -123,3 +123,65 @@ def test_losses_feed_the_scoring_backward():
     for n, p in m64.named_parameters():
         want = p.grad.numpy()
         assert np.abs(got[n] - want).max() <= 2e-5 * max(np.abs(want).max(), 1e-2), n
+
+
+# ----------------------------------------------------------------------------------- PCL_loss
+PCL = np.load(os.path.join(GOLDEN, "pcl_loss.npz"))
+
+
+@pytest.mark.parametrize("name", cim_case_names(PCL))
+def test_pcl_loss_reference_fixtures(name):
+    p = cuda(PCL[f"{name}/predict_cls"]).requires_grad_(True)
+    loss = heads.PCL_loss(p, cuda(PCL[f"{name}/mat"]), None)
+    assert loss.dim() == 0
+    loss.backward()
+    want_l, want_g = float(PCL[f"{name}/loss"]), PCL[f"{name}/grad"]
+    assert abs(float(loss.detach()) - want_l) <= 1e-5 * max(abs(want_l), 1e-3)
+    close(p.grad.cpu().numpy(), want_g)
+
+
+def test_pcl_loss_batched_accumulate_and_errors():
+    """3 images at cfg2 size in one launch against the oracle; accumulate mode adds on top of an existing
+    gradient; ids the reference would choke on give NaN."""
+    import ctypes as C
+    from cim_b200 import _lib
+    n_img, R, c1 = 3, 2000, 21
+    rs = np.random.RandomState(8)
+    z = rs.randn(n_img * R, c1).astype(np.float32) * 2
+    e = np.exp(z - z.max(-1, keepdims=True))
+    p = (e / e.sum(-1, keepdims=True)).astype(np.float32)
+    mat = np.zeros((n_img, R, c1), np.float32)
+    for b in range(n_img):
+        k = 1
+        for _ in range(6 + b):
+            rows = rs.rand(R) < 0.05
+            mat[b, rows, :] = 0
+            mat[b, rows, 1 + rs.randint(c1 - 1)] = k
+            k += 1
+        free = (mat[b].sum(1) == 0) & (rs.rand(R) < 0.4)
+        mat[b, free, 0] = k
+    mat[1, 5, 3], mat[1, 5, 7] = 2, 3                       # a row in two clusters
+    up = np.array([0.5, 2.0, 1.0], np.float32)
+    pt = cuda(p).requires_grad_(True)
+    loss = heads.PCL_loss(pt, cuda(mat), None, n_img=n_img)
+    (loss * cuda(up)).sum().backward()
+    o_loss, o_grad = loss_oracle.pcl_losses(p, mat)
+    o_grad = (o_grad.reshape(n_img, R, c1) * up[:, None, None]).reshape(n_img * R, c1)
+    close(loss.detach().cpu().numpy(), o_loss.astype(np.float32))
+    close(pt.grad.cpu().numpy(), o_grad.astype(np.float32))
+    # accumulate on top of ones
+    L = _lib.lib()
+    g = torch.ones(n_img * R, c1, device=DEV)
+    lo = torch.empty(n_img, device=DEV)
+    dp, dm = cuda(p), cuda(mat)                              # keep the device inputs alive across the raw call
+    _lib.check(L.cim_pcl_loss(_lib.ptr(dp), _lib.ptr(dm), _lib.ptr(lo), _lib.ptr(g), n_img, R, c1, 128, 1.0,
+                              1, _lib.stream_ptr(torch.device(DEV))), "cim_pcl_loss")
+    torch.cuda.synchronize()
+    o_loss1, o_grad1 = loss_oracle.pcl_losses(p, mat)
+    close(g.cpu().numpy() - 1.0, o_grad1.astype(np.float32), tol=1e-4)      # 1 + x - 1 costs a few ulps of 1
+    # two background ids (heads.py:20 asserts) and a non-integer id -> NaN
+    bad = mat.copy()
+    bad[0, 0, 0], bad[0, 1, 0] = 40, 41
+    bad[2, 0, 4] = 1.5
+    lo2 = heads.PCL_loss(cuda(p), cuda(bad), None, n_img=n_img).cpu().numpy()
+    assert np.isnan(lo2[0]) and np.isnan(lo2[2]) and abs(lo2[1] - o_loss[1]) < 1e-4

@@ -39,9 +39,10 @@ def test_step_matches_oracle_stage_by_stage(anti):
     weight, bias = (t.detach().contiguous() for t in model._stacked())
     step = CIMHeadStep(n_img, R, C, Cf, H, W, 1.0 / 16, packed.shape[-1], feat_dim=D, anti_noise_sampling=anti,
                        device=DEV, mask_kb_per_row=size // 16 if mask_ops.tiled_ok(size, size) else 0, head_grads=True)
+    mat = torch.stack([synth.cluster_mat(R, C, np.nonzero(labels[b].numpy())[0], 4, 40 + b) for b in range(n_img)])
     np.random.seed(3)
     step.run(feat.to(DEV), rois.to(DEV), grad_out.to(DEV), packed, seg_x.to(DEV), weight, bias, labels.to(DEV),
-             labels.numpy())
+             labels.numpy(), mat=mat.to(DEV))
     torch.cuda.synchronize()
 
     want = roi_oracle.roi_align_fwd(feat.numpy(), rois.numpy(), 7, 7, 1.0 / 16, 0, True)
@@ -88,6 +89,9 @@ def test_step_matches_oracle_stage_by_stage(anti):
 
     # losses + head gradients (batch loss = mean over the images)
     o_loss, o_grad = loss_oracle.head_losses(scores, pl, pi, lw, valid, labels.numpy(), k, grad_scale=1.0 / n_img)
+    o_pcl, g_pcl = loss_oracle.pcl_losses(scores[0], mat.numpy(), grad_scale=1.0 / n_img)      # model_builder.py:203
+    o_grad[0] += g_pcl
+    np.testing.assert_allclose(step.pcl_loss.cpu().numpy(), o_pcl, rtol=2e-5)
     got_loss = step.losses.cpu().numpy()
     np.testing.assert_array_equal(np.isnan(got_loss), np.isnan(o_loss))
     np.testing.assert_allclose(np.nan_to_num(got_loss), np.nan_to_num(o_loss), rtol=2e-5, atol=1e-7)

@@ -34,3 +34,15 @@ def test_skipped_layers_contribute_nothing():
     assert not c["valid"].any()
     assert (c["losses"][:, :3] == 0).all() and c["losses"][0, 3, 2] > 0
     assert (c["grad"][2:] == 0).all() and (c["grad"][:2] != 0).any()
+
+
+PCL = np.load(os.path.join(GOLDEN, "pcl_loss.npz"))
+
+
+@pytest.mark.parametrize("name", cim_case_names(PCL))
+def test_pcl_loss_matches_reference(name):
+    """tests/golden/pcl_loss.npz: the reference's own heads.PCL_loss + autograd."""
+    loss, grad = loss_oracle.pcl_losses(PCL[f"{name}/predict_cls"], PCL[f"{name}/mat"][None])
+    assert abs(loss[0] - float(PCL[f"{name}/loss"])) <= 1e-5 * max(abs(float(PCL[f"{name}/loss"])), 1e-3)
+    want = PCL[f"{name}/grad"]
+    assert np.abs(grad - want).max() <= 1e-5 * max(np.abs(want).max(), 1e-3)
