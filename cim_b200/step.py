@@ -107,6 +107,7 @@ class CIMHeadStep:
         self.h_weight = pin((k, n_img, self.cap), torch.float32)
         self.h_keep = pin((k, n_img, self.cap), torch.uint8)
         self.ev = torch.cuda.Event()
+        self.side = torch.cuda.Stream(device=self.dev)
         # layer l reads (cls, det) = (predict_cls, predict_det) for l = 0, else (ref_cls[l-1], ref_iou[l-1])
         s = self.scores.view(nh, n_img, R, C1)
         cls_src = [s[0]] + [s[2 + l - 1] for l in range(1, k)]
@@ -133,11 +134,17 @@ class CIMHeadStep:
         P, n_img, R, k = _lib.ptr, self.n_img, self.R, self.K
         st = _lib.stream_ptr(dev)
         ck = _lib.check
+        # the scoring GEMM (independent of the maps) runs on a side stream next to the overlap stage, whose small
+        # serial helpers (mask sort: 8 CTAs, tile order: 1 CTA) leave most of the GPU idle
+        cur = torch.cuda.current_stream(dev)
+        self.side.wait_stream(cur)
+        ck(L.cim_score_heads(P(seg_x), P(weight), P(bias), P(self.scores), n_img, R, self.D, self.C + 1, k,
+                             P(self.score_ws), self.score_ws.numel(), C.c_void_p(self.side.cuda_stream)),
+           "cim_score_heads")
         ck(L.cim_mask_overlap_ex(P(packed_masks), n_img, R, self.words, self.kb_per_row, None, P(self.area),
                                  P(self.iou), P(self.asy), P(self.overlap_ws), self.overlap_ws.numel(), 0, st),
            "cim_mask_overlap_ex")
-        ck(L.cim_score_heads(P(seg_x), P(weight), P(bias), P(self.scores), n_img, R, self.D, self.C + 1, k,
-                             P(self.score_ws), self.score_ws.numel(), st), "cim_score_heads")
+        cur.wait_stream(self.side)
         ck(L.cim_mine(C.byref(p), self.cls_ptrs, self.det_ptrs, P(labels), P(self.iou), P(self.asy),
                       P(self.gt_count), P(self.gt_rows), P(self.gt_class), P(self.gt_weight), P(self.asy_flag),
                       P(self.mine_ws), self.mine_ws.numel(), st), "cim_mine")
