@@ -977,7 +977,10 @@ __global__ void roi_align_generic_kernel(const float *__restrict__ in, const flo
                                          const int *__restrict__ descs, const float *__restrict__ mask7, int mode,
                                          int B, int C, int H, int W, int K, int oh, int ow, float scale, int sr,
                                          int aligned) {
-    const int k = blockIdx.x;
+    // mode 0: one CTA column per ROI.  mode 1 (leftover pass): one WARP per ROI, 8 ROIs per CTA -- almost every warp
+    // exits at once, and 8x fewer CTAs have to be scheduled for nothing
+    const int k = mode == 1 ? blockIdx.x * 8 + (threadIdx.x >> 5) : blockIdx.x;
+    if (k >= K) return;
     if (mode == 1 && __ldg(hdr) == 0) {
         const int *d = descs + (size_t)k * DESC_WORDS;
         if ((__ldg(d + D_FLAGY) | __ldg(d + D_FLAGX)) == 0) return;
@@ -985,7 +988,9 @@ __global__ void roi_align_generic_kernel(const float *__restrict__ in, const flo
     const Geom g = roi_geom(rois + 5 * (size_t)k, scale, oh, ow, sr, aligned);
     const int per_roi = C * oh * ow;
     const bool valid_b = g.b >= 0 && g.b < B;
-    for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < per_roi; e += gridDim.y * blockDim.x) {
+    const int e0 = mode == 1 ? (threadIdx.x & 31) : blockIdx.y * blockDim.x + threadIdx.x;
+    const int estep = mode == 1 ? 32 : gridDim.y * blockDim.x;
+    for (int e = e0; e < per_roi; e += estep) {
         const int pw = e % ow, ph = (e / ow) % oh, c = e / (ow * oh);
         const size_t oidx = mask7 ? (size_t)k * 2 * per_roi + e : (size_t)k * per_roi + e;
         const float mk = mask7 ? __ldg(mask7 + (size_t)k * oh * ow + ph * ow + pw) : 0.f;
@@ -1151,7 +1156,7 @@ static int roi_fwd_impl(const float *feat, const float *rois, const float *mask7
     }
     if ((rc = cim_launch_status())) return rc;
     // leftover pass: one CTA per ROI, which exits at once unless the tile kernel skipped that ROI
-    roi_align_generic_kernel<false><<<dim3((unsigned)K, 1), 256, 0, st>>>(feat, rois, out, w.hdr, w.desc, mask7, 1, B,
+    roi_align_generic_kernel<false><<<dim3((unsigned)((K + 7) / 8), 1), 256, 0, st>>>(feat, rois, out, w.hdr, w.desc, mask7, 1, B,
                                                                           C, H, W, K, oh, ow, scale, sr, aligned);
     return cim_launch_status();
 }
@@ -1201,7 +1206,7 @@ static int roi_bwd_impl(const float *grad_out, const float *rois, const float *m
         dim3 cg((unsigned)((W + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)(B * ((H + 1) >> 1)));
         pairs_to_nchw_kernel<<<cg, 256, 0, st>>>(reinterpret_cast<const float2 *>(gradP), grad_feat, C, H, W);
         if ((rc = cim_launch_status())) return rc;
-        roi_align_generic_kernel<true><<<dim3((unsigned)K, 1), 256, 0, st>>>(grad_out, rois, grad_feat, w.hdr, w.desc,
+        roi_align_generic_kernel<true><<<dim3((unsigned)((K + 7) / 8), 1), 256, 0, st>>>(grad_out, rois, grad_feat, w.hdr, w.desc,
                                                                              mask7, 1, B, C, H, W, K, oh, ow, scale, sr,
                                                                              aligned);
         return cim_launch_status();
@@ -1222,7 +1227,7 @@ static int roi_bwd_impl(const float *grad_out, const float *rois, const float *m
                                                                               nullptr, grad_feat, B, C, H, W, p.pitch);
     }
     if ((rc = cim_launch_status())) return rc;
-    roi_align_generic_kernel<true><<<dim3((unsigned)K, 1), 256, 0, st>>>(grad_out, rois, grad_feat, w.hdr, w.desc,
+    roi_align_generic_kernel<true><<<dim3((unsigned)((K + 7) / 8), 1), 256, 0, st>>>(grad_out, rois, grad_feat, w.hdr, w.desc,
                                                                          mask7, 1, B, C, H, W, K, oh, ow, scale, sr,
                                                                          aligned);
     return cim_launch_status();
