@@ -28,10 +28,11 @@ KEYS = [
 
 
 def raw(rep):
+    """One dict per kernel of the report."""
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    hdr, units, vals = rows[0], rows[1], rows[2]
-    return {h: (v, u) for h, u, v in zip(hdr, units, vals)}
+    hdr, units = rows[0], rows[1]
+    return [{h: (v, u) for h, u, v in zip(hdr, units, vals)} for vals in rows[2:] if vals]
 
 
 STALLS = ["stall_barrier", "stall_branch_resolving", "stall_dispatch", "stall_drain", "stall_lg", "stall_long_sb",
@@ -70,17 +71,21 @@ def source(rep, top=16):
 
 
 for rep in sys.argv[1:]:
-    m = raw(rep)
-    name = m.get("Kernel Name", ("?", ""))[0]
-    print("=" * 100)
-    print(rep, "|", name[:90])
-    for k in KEYS:
-        if k in m:
-            print(f"  {k:85s} {m[k][0]:>16s} {m[k][1]}")
-    totals, src = source(rep)
-    if totals:
-        print("  -- warp-state samples by reason (share of all samples) --")
-        print("  " + "  ".join(f"{k[6:]}={v:.1%}" for k, v in sorted(totals.items(), key=lambda kv: -kv[1]) if v >= 0.01))
-        print("  -- top sampled SASS lines --")
-        for n, f, s, d in src:
-            print(f"  {n:8d} {f:6.1%}  {d[6:]:14s} {s[:100]}")
+    kernels = raw(rep)
+    for ki, m in enumerate(kernels):
+        name = m.get("Kernel Name", ("?", ""))[0]
+        print("=" * 100)
+        print(rep, "|", name[:90])
+        for k in KEYS:
+            if k in m:
+                print(f"  {k:85s} {m[k][0]:>16s} {m[k][1]}")
+        if ki > 0:
+            continue                      # the source page of a multi-kernel report covers its first kernel only
+        totals, src = source(rep)
+        if totals:
+            top = sorted(totals.items(), key=lambda kv: -kv[1])[:10]
+            print("  -- warp-state samples by reason (share of all samples) --")
+            print("  " + "  ".join(f"{k.replace('stall_', '')}={v * 100:.1f}%" for k, v in top))
+            print("  -- top sampled SASS lines --")
+            for n, share, line, dom in src:
+                print(f"  {n:8d} {share * 100:5.1f}%  {dom.replace('stall_', ''):14s} {line[:90]}")
