@@ -51,14 +51,25 @@ constexpr int THREADS = (NEXP + 2) * 32;
 constexpr int KMAP_WORDS = 512;         // smem copy of a tile's K-block bitmap (16384 K-blocks = 2 Mpixel masks)
 constexpr size_t SI_BYTES = (size_t)(TM + TN) * 4 + 3 * (size_t)TM * 130 * 2;   // epilogue staging (aliases the rings)
 
-template <int STAGES_>
+constexpr int KLIST = 8192;             // direct variant: smem list of a tile's visited K-blocks (1 Mpixel masks)
+constexpr int PF = 4;                   // direct variant: K-blocks (of its parity) a thread keeps in flight
+
+// DIRECT_ = false: a loader warp streams packed rows into a staging ring with cp.async (any mask size).
+// DIRECT_ = true:  no loader and no staging -- every expander thread prefetches the 16 B of ITS row(s) PF K-blocks
+//                  ahead straight into registers (ld.global.nc, L1 no-allocate); the visited K-blocks come from a
+//                  list in smem built once per tile.  The single loader warp was the pipeline's bottleneck (~850
+//                  dependent instructions per 4 K-blocks against 2048 MMA cycles); without the staging ring there
+//                  is room for 6 expanded-B stages.
+template <int STAGES_, bool DIRECT_ = false>
 struct Cfg {
     static constexpr int STAGES = STAGES_;
-    static constexpr size_t RING_BYTES = (size_t)STAGES * B_BYTES + (size_t)NBUF * BUF_BYTES;
+    static constexpr bool DIRECT = DIRECT_;
+    static constexpr size_t RING_BYTES = (size_t)STAGES * B_BYTES + (DIRECT ? (size_t)KLIST * 2 : (size_t)NBUF * BUF_BYTES);
     static constexpr size_t BODY_BYTES = SI_BYTES > RING_BYTES ? SI_BYTES : RING_BYTES;
     static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + BODY_BYTES + 256 + KMAP_WORDS * 4;
     static_assert(STAGES % 2 == 0, "the two expander groups own alternate stages");
     static_assert(TN + STAGES * A_COLS <= TMEM_COLS, "TMEM budget");
+    static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
 };
 
 // tcgen05 instruction descriptor (cute::UMMA::InstrDescriptor): S32 accumulate, INT8 x INT8, both
@@ -142,18 +153,40 @@ __device__ __forceinline__ void expand_row_to_smem(const uint4 &p, unsigned char
     }
 }
 
+__device__ __forceinline__ uint4 ldg_stream16(const uint32_t *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void sts16(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// one operand row of a K-block -> the swizzled smem row, explicit shared-space stores (stage = 32-bit smem address)
+__device__ __forceinline__ void expand_row_to_smem_s(const uint4 &p, uint32_t stage, const uint32_t (&choff)[8]) {
+    const uint32_t pw[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t o[8];
+        expand32(pw[q], o);
+        sts16(stage + choff[2 * q], o[0], o[1], o[2], o[3]);
+        sts16(stage + choff[2 * q + 1], o[4], o[5], o[6], o[7]);
+    }
+}
+
 __device__ __forceinline__ __half2 pack_ratio2(int i0, int d0, int i1, int d1) {
     return __halves2half2(__float2half_rn(__fdiv_rn((float)i0, (float)d0)),
                           __float2half_rn(__fdiv_rn((float)i1, (float)d1)));
 }
 
 template <class K>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __maxnreg__(112)
 mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__restrict__ area_all,
                        const int32_t *__restrict__ perm_all, const uint32_t *__restrict__ umap_a,
                        const uint32_t *__restrict__ umap_b, int bw, unsigned long long *__restrict__ visited,
                        const int32_t *__restrict__ tile_order, int n, long long words, int n_img, int32_t *__restrict__ inter_all, __half *__restrict__ iou_all,
-                       __half *__restrict__ asy_all) {
+                       __half *__restrict__ asy_all, int abl) {
     constexpr int STAGES = K::STAGES;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -166,6 +199,7 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
     uint64_t *consumed = loaded + NBUF;            // [NBUF] staging buffer read by every expander warp
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(consumed + NBUF);
     uint32_t *kmap = tmem_slot + 2;                // [KMAP_WORDS] AND of the two union bitmaps (loader)
+    uint16_t *klist = reinterpret_cast<uint16_t *>(staging);   // direct variant: [KLIST] visited K-blocks
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // tile id -> (d, img, ti), tj = ti / 2 + d: tiles are ordered by their distance d from the diagonal,
@@ -201,10 +235,6 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
     // All indices below are SORTED positions (mask_sort_kernel); perm maps them to the stored masks.
     // K-blocks of this tile: those where BOTH operand blocks have a non-zero row (AND of the two union
     // bitmaps).  Every warp counts them; only the loader needs their indices.
@@ -214,7 +244,7 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
     for (int j = lane; j < bw; j += 32) {
         const uint32_t mj = __ldg(ua + j) & __ldg(ub + j);
         nkb += __popc(mj);
-        if (warp == LOAD_WARP && j < KMAP_WORDS) kmap[j] = mj;      // the loader's private copy
+        if (!K::DIRECT && warp == LOAD_WARP && j < KMAP_WORDS) kmap[j] = mj;      // the loader's private copy
     }
     __syncwarp();
 #pragma unroll
@@ -222,6 +252,35 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
     const int ngroups = (nkb + GK - 1) / GK;
     if (tid == 0 && visited) atomicAdd(visited, (unsigned long long)nkb);
 
+    if (K::DIRECT) {
+        // list of the visited K-blocks, in ascending order: warp w takes the bitmap words 32 c .. 32 c + 31 for
+        // c = w, w + 18, ...; the offset of a chunk is the popcount of everything before it
+        for (int c = warp; c * 32 < bw; c += THREADS / 32) {
+            int pre = 0;
+            for (int j = lane; j < c * 32; j += 32) pre += __popc(__ldg(ua + j) & __ldg(ub + j));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, o);
+            const int j = c * 32 + lane;
+            uint32_t mj = j < bw ? (__ldg(ua + j) & __ldg(ub + j)) : 0u;
+            int incl = __popc(mj);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            int off = pre + incl - __popc(mj);
+            while (mj) {
+                const int b = __ffs(mj) - 1;
+                mj &= mj - 1;
+                if (off < KLIST) klist[off] = (uint16_t)(j * 32 + b);
+                ++off;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
     if (warp < NEXP) {
         // ------------------------------------------------------------------ expanders
         const bool is_a = warp < 8;
@@ -237,6 +296,63 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
             ch0[c] = (rb0 >> 3) * 1024 + (rb0 & 7) * 128 + ((c ^ (rb0 & 7)) << 4);
             ch1[c] = (rb1 >> 3) * 1024 + (rb1 & 7) * 128 + ((c ^ (rb1 & 7)) << 4);
         }
+        if (K::DIRECT) {
+            const uint32_t *img_base = packed + (size_t)img * n * words;
+            const int g0 = is_a ? row0 + ra : col0 + rb0, g1 = col0 + rb1;
+            const bool v0 = g0 < n, v1 = !is_a && g1 < n;
+            const uint32_t *r0p = img_base + (size_t)(v0 ? __ldg(perm + g0) : 0) * words;
+            const uint32_t *r1p = img_base + (size_t)(v1 ? __ldg(perm + g1) : 0) * words;
+            const uint32_t stages_s = smem_u32(stages);
+            const int nj = (nkb - grp + 1) >> 1;              // this group's K-blocks: i = 2 j + grp < nkb
+            uint4 q0[PF], q1[PF];
+            auto fetch = [&](int j, uint4 &a, uint4 &b) {
+                const int kbi = klist[2 * j + grp];
+                a = make_uint4(0u, 0u, 0u, 0u);
+                b = a;
+                if (v0 && !(abl & 16)) a = ldg_stream16(r0p + (size_t)kbi * 4);
+                if (v1 && !(abl & 16)) b = ldg_stream16(r1p + (size_t)kbi * 4);
+            };
+#pragma unroll
+            for (int d = 0; d < PF; ++d) {
+                q0[d] = make_uint4(0u, 0u, 0u, 0u);
+                q1[d] = q0[d];
+                if (d < nj) fetch(d, q0[d], q1[d]);
+            }
+            for (int j0 = 0; j0 < nj; j0 += PF) {
+#pragma unroll
+                for (int d = 0; d < PF; ++d) {
+                    const int j = j0 + d;
+                    if (j < nj) {
+                        const uint4 p0 = q0[d], p1 = q1[d];
+                        if (j + PF < nj) fetch(j + PF, q0[d], q1[d]);
+                        const int i = 2 * j + grp, u = i / STAGES, s = i - u * STAGES;
+                        if (u > 0) mbar_wait(&empty[s], (u - 1) & 1);
+                        if (is_a ? (abl & 2) : (abl & 1)) {
+                            // tuning aid (CIM_OVERLAP_ABL): this operand is not expanded, timing only
+                        } else if (is_a) {
+                            const uint32_t pw[4] = {p0.x, p0.y, p0.z, p0.w};
+                            uint32_t o[32];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                uint32_t t[8];
+                                expand32(pw[q], t);
+#pragma unroll
+                                for (int gg = 0; gg < 8; ++gg) o[q * 8 + gg] = t[gg];
+                            }
+                            tc_st32(a_lane + (uint32_t)(s * A_COLS), o);      // includes tcgen05.wait::st
+                            tc_fence_before();
+                        } else {
+                            const uint32_t stg = stages_s + (uint32_t)s * B_BYTES;
+                            expand_row_to_smem_s(p0, stg, ch0);
+                            expand_row_to_smem_s(p1, stg, ch1);
+                            fence_proxy_async_smem();
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&full[s]);
+                    }
+                }
+            }
+        } else {
         const int srow0 = is_a ? ra : TM + rb0, srow1 = TM + rb1;     // rows inside a staging buffer
         for (int g = 0; g < ngroups; ++g) {
             const int buf = g % NBUF;
@@ -281,6 +397,7 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
                 if (lane == 0) mbar_arrive(&full[s]);
             }
         }
+        }
     } else if (warp == LOAD_WARP) {
         // ------------------------------------------------------------------ loader
         // lane l streams rows l, l + 32, ...; staging layout [kk][row][16 B] keeps both the LDGSTS
@@ -289,7 +406,7 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
         const uint32_t *img_base = packed + (size_t)img * n * words;
         int bj = -1;                       // bitmap word being scanned and its bits not yet taken
         uint32_t bm = 0;
-        for (int g = 0; g < ngroups; ++g) {
+        for (int g = 0; g < (K::DIRECT ? 0 : ngroups); ++g) {
             const int buf = g % NBUF;
             if (g >= NBUF) mbar_wait(&consumed[buf], ((g / NBUF) - 1) & 1);
             unsigned char *dst = staging + (size_t)buf * BUF_BYTES;
@@ -331,9 +448,11 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
             if (lane == 0) {
                 const uint64_t bd = smem_desc(smem_u32(stages + (size_t)s * B_BYTES));
                 const uint32_t a_t = tmem_base + TMEM_A0 + (uint32_t)(s * A_COLS);
+                if (!(abl & 4)) {
 #pragma unroll
-                for (int k = 0; k < KB / 32; ++k)       // K = 32 bytes: 8 TMEM columns of A, +2 (x16 B) of B
-                    tc_mma_i8_ts(tmem_base, a_t + 8 * k, bd + 2 * k, (kb | k) != 0);
+                    for (int k = 0; k < KB / 32; ++k)       // K = 32 bytes: 8 TMEM columns of A, +2 (x16 B) of B
+                        tc_mma_i8_ts(tmem_base, a_t + 8 * k, bd + 2 * k, (kb | k) != 0);
+                }
                 tc_commit(&empty[s]);                    // arrives when the MMAs above have read the stage
                 if (kb == nkb - 1) tc_commit(accum_full);
             }
@@ -453,9 +572,13 @@ static int launch(const uint32_t *packed, const int32_t *area, const int32_t *pe
     const int nrb = (n + TM - 1) / TM, ncb = (n + TN - 1) / TN;
     int tiles = 0;
     for (int i = 0; i < nrb; ++i) tiles += ncb - (i >> 1);
+    // CIM_OVERLAP_ABL (tuning aid, direct variants): bit 0 / 1 skip the B / A expansion, 2 the MMAs,
+    // 4 the operand loads -- results are garbage, only the timing of what remains means something
+    const char *ab = getenv("CIM_OVERLAP_ABL");
+    const int abl = ab ? atoi(ab) : 0;
     cudaFuncSetAttribute(mask_overlap_tc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES);
     mask_overlap_tc_kernel<K><<<(unsigned)(tiles * n_img), THREADS, K::SMEM_BYTES, st>>>(
-        packed, area, perm, umap_a, umap_b, bw, visited, tile_order, n, words, n_img, inter, iou, asy);
+        packed, area, perm, umap_a, umap_b, bw, visited, tile_order, n, words, n_img, inter, iou, asy, abl);
     return cim_launch_status();
 }
 
@@ -470,10 +593,19 @@ int cim_mask_overlap_tc_launch(const uint32_t *packed, const int32_t *area, cons
                                const uint32_t *umap_a, const uint32_t *umap_b, int bw, unsigned long long *visited,
                                const int32_t *tile_order, int n_img, int n, long long words, int32_t *inter,
                                __half *iou, __half *asy, cudaStream_t st) {
-    // CIM_OVERLAP_VARIANT is a tuning aid (pipeline-depth experiments); unset = the default
+    // CIM_OVERLAP_VARIANT is a tuning aid (pipeline experiments); unset = the default.  The direct variants need
+    // the tile's K-block list to fit its smem array (masks up to 1 Mpixel); larger masks take the loader-warp kernel.
+#define CIM_OV_ARGS packed, area, perm, umap_a, umap_b, bw, visited, tile_order, n_img, n, words, inter, iou, asy, st
     const char *v = getenv("CIM_OVERLAP_VARIANT");
-    switch (v ? atoi(v) : 0) {
-        case 1: return launch<Cfg<2>>(packed, area, perm, umap_a, umap_b, bw, visited, tile_order, n_img, n, words, inter, iou, asy, st);
-        default: return launch<CfgDefault>(packed, area, perm, umap_a, umap_b, bw, visited, tile_order, n_img, n, words, inter, iou, asy, st);
+    const bool direct_ok = (words + 3) / 4 <= KLIST;
+    int variant = v ? atoi(v) : 0;
+    if (variant == 0) variant = direct_ok ? 3 : 2;
+    if (!direct_ok && variant >= 3) variant = 2;
+    switch (variant) {
+        case 1: return launch<Cfg<2>>(CIM_OV_ARGS);
+        case 2: return launch<CfgDefault>(CIM_OV_ARGS);
+        case 4: return launch<Cfg<4, true>>(CIM_OV_ARGS);
+        default: return launch<Cfg<6, true>>(CIM_OV_ARGS);
     }
+#undef CIM_OV_ARGS
 }

@@ -269,19 +269,24 @@ score_dx_tc_kernel(const __grid_constant__ CUtensorMap tm_dzh, const __grid_cons
 constexpr int DW_NT = 176;                            // logit columns per CTA (UMMA N), 8 x 21 = 168 for VOC
 constexpr int DW_B_TILE = DW_NT * BK * 4;             // 22 KB
 constexpr int DW_RAW = 32 * BM * 4;                   // raw x tile [32 m][128 d], 16 KB
-constexpr int DW_STAGE = DW_RAW + 2 * A_TILE + 2 * DW_B_TILE;     // 92 KB
+constexpr int DW_STAGE = 2 * A_TILE + 2 * DW_B_TILE;     // x^T_hi | x^T_lo | dz^T_hi | dz^T_lo = 76 KB
 constexpr int DW_NSTAGE = 2;
+constexpr int DW_NRAW = 4;                            // raw x tiles in flight ahead of the transpose (HBM latency)
+constexpr int DW_THREADS = 7 * 32;                    // x producer, MMA issuer, 4 transpose/epilogue warps, dz^T producer
 constexpr int DW_CHK = 4;                             // k-blocks per accumulation chunk (128 proposals)
 constexpr int DW_LAG = 2;
 
-__global__ void __launch_bounds__(THREADS_TC, 1)
+__global__ void __launch_bounds__(DW_THREADS, 1)
 score_dw_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_bh,
                    const __grid_constant__ CUtensorMap tm_bl, float *__restrict__ partial, int M, int N, int D,
                    int kb_per_split) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t *tma_full = reinterpret_cast<uint64_t *>(smem + (size_t)DW_NSTAGE * DW_STAGE);
-    uint64_t *lo_ready = tma_full + DW_NSTAGE;
+    unsigned char *rawring = smem + (size_t)DW_NSTAGE * DW_STAGE;                     // [DW_NRAW][DW_RAW]
+    uint64_t *tma_full = reinterpret_cast<uint64_t *>(rawring + (size_t)DW_NRAW * DW_RAW);   // [NSTAGE] dz^T tiles landed
+    uint64_t *raw_full = tma_full + DW_NSTAGE;                   // [DW_NRAW] raw x tile landed
+    uint64_t *raw_empty = raw_full + DW_NRAW;                    // [DW_NRAW] raw x tile read by the 4 transpose warps
+    uint64_t *lo_ready = raw_empty + DW_NRAW;
     uint64_t *empty = lo_ready + DW_NSTAGE;
     uint64_t *chunk_full = empty + DW_NSTAGE;
     uint64_t *chunk_empty = chunk_full + 2;
@@ -297,6 +302,7 @@ score_dw_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     if (tid == 0) {
         for (int s = 0; s < DW_NSTAGE; ++s) { mbar_init(&tma_full[s], 1); mbar_init(&lo_ready[s], 4); mbar_init(&empty[s], 1); }
         for (int p = 0; p < 2; ++p) { mbar_init(&chunk_full[p], 1); mbar_init(&chunk_empty[p], 4); }
+        for (int r = 0; r < DW_NRAW; ++r) { mbar_init(&raw_full[r], 1); mbar_init(&raw_empty[r], 4); }
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -312,15 +318,23 @@ score_dw_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     const uint32_t idesc = tf32_idesc(DW_NT);
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (lane == 0) {                                   // x producer: the HBM stream, DW_NRAW tiles ahead
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int r = kb % DW_NRAW;
+                if (kb >= DW_NRAW) mbar_wait(&raw_empty[r], ((kb / DW_NRAW) - 1) & 1);
+                mbar_expect_tx(&raw_full[r], (uint32_t)DW_RAW);
+                tma_load_2d(rawring + (size_t)r * DW_RAW, &tm_x, d0, (kb0 + kb) * BK, &raw_full[r]);   // [32 m][128 d]
+            }
+        }
+    } else if (warp == 6) {
+        if (lane == 0) {                                   // dz^T producer (L2 hits), tied to the MMA stage
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % DW_NSTAGE;
                 if (kb >= DW_NSTAGE) mbar_wait(&empty[s], ((kb / DW_NSTAGE) - 1) & 1);
                 unsigned char *st = smem + (size_t)s * DW_STAGE;
-                mbar_expect_tx(&tma_full[s], (uint32_t)(DW_RAW + 2 * DW_B_TILE));
-                tma_load_2d(st, &tm_x, d0, (kb0 + kb) * BK, &tma_full[s]);                  // [32 m][128 d]
-                tma_load_2d(st + DW_RAW + 2 * A_TILE, &tm_bh, (kb0 + kb) * BK, n0, &tma_full[s]);
-                tma_load_2d(st + DW_RAW + 2 * A_TILE + DW_B_TILE, &tm_bl, (kb0 + kb) * BK, n0, &tma_full[s]);
+                mbar_expect_tx(&tma_full[s], (uint32_t)(2 * DW_B_TILE));
+                tma_load_2d(st + 2 * A_TILE, &tm_bh, (kb0 + kb) * BK, n0, &tma_full[s]);
+                tma_load_2d(st + 2 * A_TILE + DW_B_TILE, &tm_bl, (kb0 + kb) * BK, n0, &tma_full[s]);
             }
         }
     } else if (warp == 1) {
@@ -331,7 +345,7 @@ score_dw_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             mbar_wait(&lo_ready[s], (kb / DW_NSTAGE) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
-                const uint32_t base = smem_u32(smem + (size_t)s * DW_STAGE) + DW_RAW, acc = tmem_base + 256u * p;
+                const uint32_t base = smem_u32(smem + (size_t)s * DW_STAGE), acc = tmem_base + 256u * p;
                 const uint64_t ah = smem_desc128(base), al = smem_desc128(base + A_TILE);
                 const uint64_t bh = smem_desc128(base + 2 * A_TILE), bl = smem_desc128(base + 2 * A_TILE + DW_B_TILE);
 #pragma unroll
@@ -377,11 +391,12 @@ score_dw_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         };
         int next_drain = 0;
         for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % DW_NSTAGE;
-            mbar_wait(&tma_full[s], (kb / DW_NSTAGE) & 1);
+            const int s = kb % DW_NSTAGE, r = kb % DW_NRAW;
+            mbar_wait(&raw_full[r], (kb / DW_NRAW) & 1);
+            if (kb >= DW_NSTAGE) mbar_wait(&empty[s], ((kb / DW_NSTAGE) - 1) & 1);     // the stage's last MMAs are done
             unsigned char *st = smem + (size_t)s * DW_STAGE;
-            const float *raw = reinterpret_cast<const float *>(st) + t;              // raw[mm * 128]
-            unsigned char *xh = st + DW_RAW + row_off, *xl = xh + A_TILE;
+            const float *raw = reinterpret_cast<const float *>(rawring + (size_t)r * DW_RAW) + t;      // raw[mm * 128]
+            unsigned char *xh = st + row_off, *xl = xh + A_TILE;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {                    // 4 proposals per 16 B chunk of the operand row
                 float h[4], l[4];
@@ -393,7 +408,7 @@ score_dw_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive1(&lo_ready[s]);
+            if (lane == 0) { mbar_arrive1(&lo_ready[s]); mbar_arrive1(&raw_empty[r]); }
             while (next_drain < nchunks && min((next_drain + 1) * DW_CHK, nkb) - 1 + DW_LAG <= kb) drain(next_drain++);
         }
         while (next_drain < nchunks) drain(next_drain++);
@@ -524,7 +539,7 @@ CIM_API int cim_score_heads_bwd(const float *x, const float *weight, const float
     }
     const char *force = getenv("CIM_SCORE_FFMA");
     const bool tc = !(force && force[0] == '1') && M >= BM && (D % 4) == 0 && D >= BK && encode_tiled() != nullptr &&
-                    cim_max_smem_optin() >= 200 * 1024;
+                    (size_t)cim_max_smem_optin() >= 1024 + (size_t)DW_NSTAGE * DW_STAGE + (size_t)DW_NRAW * DW_RAW + 256;
     if (grad_x) {
         if (tc) {
             score_wT_split_kernel<<<dim3((unsigned)((D + 31) / 32), (unsigned)((N + 31) / 32)), 256, 0, st>>>(
@@ -552,10 +567,10 @@ CIM_API int cim_score_heads_bwd(const float *x, const float *weight, const float
             if (!make_map_ex(&tx, x, M, D, D, 32, BM, false) || !make_map_ex(&tb, dth, N, M, L.MP, DW_NT, BK, true) ||
                 !make_map_ex(&tl, dtl, N, M, L.MP, DW_NT, BK, true))
                 return CIM_ERR_ARG;
-            const size_t smem = 1024 + (size_t)DW_NSTAGE * DW_STAGE + 256;
+            const size_t smem = 1024 + (size_t)DW_NSTAGE * DW_STAGE + (size_t)DW_NRAW * DW_RAW + 256;
             cudaFuncSetAttribute(score_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             float *out = S == 1 ? grad_weight : part;
-            score_dw_tc_kernel<<<dim3((unsigned)L.dtiles, (unsigned)S, (unsigned)L.ntiles), THREADS_TC, smem, st>>>(
+            score_dw_tc_kernel<<<dim3((unsigned)L.dtiles, (unsigned)S, (unsigned)L.ntiles), DW_THREADS, smem, st>>>(
                 tx, tb, tl, out, M, N, D, per);
             if ((rc = cim_launch_status())) return rc;
             if (S > 1) score_dw_reduce_kernel<<<592, 256, 0, st>>>(part, grad_weight, (long long)N * D, S);

@@ -15,10 +15,13 @@
 // the next chunk is being multiplied.
 //
 // One CTA per 128 rows of x and per group of heads (all 8 heads at once when 8 (C+1) <= 256).
-//   warp 0      TMA producer: cp.async.bulk.tensor (SWIZZLE_128B) of the x tile [128 x 32 fp32] and
-//               of the W_hi / W_lo tiles [NT x 32] per k-block; mbarrier complete_tx.
-//   warps 2..5  split: read the raw x tile, write x_hi in place and x_lo next to it (generic
-//               proxy -> fence.proxy.async); later the epilogue (TMEM lane quarter = warp % 4).
+//   warp 0      x producer: cp.async.bulk.tensor (SWIZZLE_128B) of the raw x tile [128 x 32 fp32] into a ring of
+//               NRAW buffers that runs ahead of everything else -- x comes from HBM (the 262 MB stream that
+//               bounds the kernel), its latency must not sit inside the 2-stage MMA ring.
+//   warp 6      W producer: the W_hi / W_lo tiles [NT x 32] of a k-block (L2 hits) into the MMA stage, as soon as
+//               the MMAs that read the stage before have completed.
+//   warps 2..5  split: read the raw x tile, write x_hi and x_lo into the MMA stage (generic proxy ->
+//               fence.proxy.async); later the epilogue (TMEM lane quarter = warp % 4).
 //   warp 1      MMA issuer: 3 products x 4 k-steps per k-block, tcgen05.commit frees the stage.
 // Epilogue: tcgen05.ld per head, bias, softmax over classes / sigmoid in registers, one contiguous
 // store per (head, row).  The detector head keeps its logits (softmax over the proposals of an
@@ -32,7 +35,8 @@ constexpr int BM = 128;                  // rows of x per CTA (UMMA M)
 constexpr int BK = 32;                   // fp32 elements per k-block = 128 B = one SW128 atom row
 constexpr int NSTAGE = 2;
 constexpr int A_TILE = BM * BK * 4;      // 16 KB
-constexpr int THREADS_TC = 6 * 32;
+constexpr int THREADS_TC = 7 * 32;
+constexpr int NRAW = 4;                  // raw x tiles in flight ahead of the split (HBM latency)
 constexpr int NT = 176;                  // UMMA N = logit columns per CTA (8 heads x 21 = 168 for VOC)
 constexpr int W_TILE = NT * BK * 4;      // 22 KB
 constexpr int STAGE = 2 * A_TILE + 2 * W_TILE;            // x_hi | x_lo | W_hi | W_lo
@@ -57,8 +61,11 @@ score_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                      float *__restrict__ scores, int M, int D, int C1, int n_ref, int heads_per_tile) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t *tma_full = reinterpret_cast<uint64_t *>(smem + (size_t)NSTAGE * STAGE);
-    uint64_t *lo_ready = tma_full + NSTAGE;
+    unsigned char *raw = smem + (size_t)NSTAGE * STAGE;                 // [NRAW][A_TILE]
+    uint64_t *tma_full = reinterpret_cast<uint64_t *>(raw + (size_t)NRAW * A_TILE);   // [NSTAGE] W tiles landed
+    uint64_t *raw_full = tma_full + NSTAGE;                     // [NRAW] raw x tile landed
+    uint64_t *raw_empty = raw_full + NRAW;                      // [NRAW] raw x tile read by the 4 split warps
+    uint64_t *lo_ready = raw_empty + NRAW;
     uint64_t *empty = lo_ready + NSTAGE;
     uint64_t *chunk_full = empty + NSTAGE;                      // [2] accumulator p holds a finished chunk
     uint64_t *chunk_empty = chunk_full + 2;                     // [2] accumulator p has been drained
@@ -76,6 +83,7 @@ score_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(&tma_full[s], 1); mbar_init(&lo_ready[s], 4); mbar_init(&empty[s], 1); }
         for (int p = 0; p < 2; ++p) { mbar_init(&chunk_full[p], 1); mbar_init(&chunk_empty[p], 4); }
+        for (int r = 0; r < NRAW; ++r) { mbar_init(&raw_full[r], 1); mbar_init(&raw_empty[r], 4); }
         fence_mbar_init();
     }
     for (int i = tid; i < nh * C1; i += THREADS_TC) s_bias[i] = bias[n0 + i];
@@ -93,14 +101,23 @@ score_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
+        // ------------------------------------------------------------------ x producer (HBM stream)
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int r = kb % NRAW;
+                if (kb >= NRAW) mbar_wait(&raw_empty[r], ((kb / NRAW) - 1) & 1);
+                mbar_expect_tx(&raw_full[r], (uint32_t)A_TILE);
+                tma_load_2d(raw + (size_t)r * A_TILE, &tm_x, kb * BK, m0, &raw_full[r]);
+            }
+        }
+    } else if (warp == 6) {
+        // ------------------------------------------------------------------ W producer (L2 hits)
         if (lane == 0) {
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % NSTAGE;
                 if (kb >= NSTAGE) mbar_wait(&empty[s], ((kb / NSTAGE) - 1) & 1);
                 unsigned char *st = smem + (size_t)s * STAGE;
-                mbar_expect_tx(&tma_full[s], (uint32_t)(A_TILE + 2 * W_TILE));
-                tma_load_2d(st, &tm_x, kb * BK, m0, &tma_full[s]);                       // raw x -> the x_hi slot
+                mbar_expect_tx(&tma_full[s], (uint32_t)(2 * W_TILE));
                 tma_load_2d(st + 2 * A_TILE, &tm_whi, kb * BK, n0, &tma_full[s]);
                 tma_load_2d(st + 2 * A_TILE + W_TILE, &tm_wlo, kb * BK, n0, &tma_full[s]);
             }
@@ -165,13 +182,15 @@ score_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         };
         int next_drain = 0;
         for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % NSTAGE;
-            mbar_wait(&tma_full[s], (kb / NSTAGE) & 1);
+            const int s = kb % NSTAGE, r = kb % NRAW;
+            mbar_wait(&raw_full[r], (kb / NRAW) & 1);
+            if (kb >= NSTAGE) mbar_wait(&empty[s], ((kb / NSTAGE) - 1) & 1);       // the stage's last MMAs are done
+            const unsigned char *xr = raw + (size_t)r * A_TILE + row_off;
             unsigned char *xh = smem + (size_t)s * STAGE + row_off, *xl = xh + A_TILE;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {                      // the row's eight 16 B chunks (swizzled position)
                 const uint32_t o = (uint32_t)((c ^ sw) << 4);
-                const uint4 v = *reinterpret_cast<const uint4 *>(xh + o);
+                const uint4 v = *reinterpret_cast<const uint4 *>(xr + o);
                 const uint4 h = make_uint4(v.x & 0xFFFFE000u, v.y & 0xFFFFE000u, v.z & 0xFFFFE000u, v.w & 0xFFFFE000u);
                 float4 l;
                 l.x = __uint_as_float(v.x) - __uint_as_float(h.x);
@@ -183,7 +202,7 @@ score_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive1(&lo_ready[s]);
+            if (lane == 0) { mbar_arrive1(&lo_ready[s]); mbar_arrive1(&raw_empty[r]); }
             // drain the chunks whose last k-block was split LAG iterations ago (their MMAs are done or
             // nearly done by now, so this does not hold up the split of the next stages)
             while (next_drain < nchunks && min((next_drain + 1) * CHK, nkb) - 1 + LAG <= kb) drain(next_drain++);
@@ -230,11 +249,17 @@ score_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 
 }  // namespace
 
+static size_t score_tc_smem_bytes(int bias_floats) {
+    const size_t ring = (size_t)NSTAGE * STAGE + (size_t)NRAW * A_TILE;
+    static_assert((size_t)NSTAGE * STAGE + (size_t)NRAW * A_TILE >= (size_t)BM * ZP * 4, "the epilogue staging aliases the rings");
+    return 1024 + ring + 256 + sizeof(float) * (size_t)bias_floats;
+}
+
 // can the tensor-core path take this shape?  (else score_heads.cu's FFMA kernel runs)
 bool cim_score_tc_eligible(long long M, int D, int C1, int n_ref) {
     (void)n_ref;
     return M >= BM && (D % BK) == 0 && D >= BK && C1 >= 1 && C1 <= NT && encode_tiled() != nullptr &&
-           cim_max_smem_optin() >= 200 * 1024;
+           (size_t)cim_max_smem_optin() >= score_tc_smem_bytes(NT);
 }
 size_t cim_score_tc_workspace_bytes(int D, int C1, int n_ref) {
     return 2 * sizeof(float) * (size_t)(2 + 2 * n_ref) * C1 * D + 512;
@@ -254,8 +279,7 @@ int cim_score_tc_launch(const float *x, const float *weight, const float *bias, 
     CUtensorMap tx, twh, twl;
     if (!make_map(&tx, x, M, D, BM) || !make_map(&twh, w_hi, N, D, NT) || !make_map(&twl, w_lo, N, D, NT))
         return CIM_ERR_ARG;
-    const size_t body = (size_t)NSTAGE * STAGE > (size_t)BM * ZP * 4 ? (size_t)NSTAGE * STAGE : (size_t)BM * ZP * 4;
-    const size_t smem = 1024 + body + 256 + sizeof(float) * (size_t)heads_per_tile * C1;
+    const size_t smem = score_tc_smem_bytes(heads_per_tile * C1);
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)ntiles);
     cudaFuncSetAttribute(score_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     score_gemm_tc_kernel<<<grid, THREADS_TC, smem, st>>>(tx, twh, twl, bias, scores, (int)M, D, C1, n_ref,

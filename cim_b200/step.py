@@ -79,6 +79,7 @@ class CIMHeadStep:
                 self.losses = e((n_img, k + 1, 3), torch.float32)
                 self.pcl_loss = torch.zeros((n_img,), dtype=torch.float32, device=dev)
                 self.grad_scores = e((nh, n_img * R, C1), torch.float32)
+                self.pcl_grad = e((n_img * R, C1), torch.float32)
             p = _lib.MineParams()
             p.n_img, p.R, p.C, p.C1, p.n_layers = n_img, R, n_classes, C1, k
             p.det_cols, p.gt_cap, p.mode = C1, R, 0
@@ -118,7 +119,7 @@ class CIMHeadStep:
 
     # -------------------------------------------------------------------------------------
     def run(self, feat, rois, grad_out, packed_masks, seg_x, weight, bias, labels, labels_host, grad_scores=None,
-            mat=None):
+            mat=None, mid_hook=None):
         """feat [n_img,Cf,H,W] f32, rois [n_img*R,5] f32 grouped by image, grad_out [n_img*R,Cf,7,7]
         f32, packed_masks [n_img,R,words] i32, seg_x [n_img*R,D] f32, weight [2+2K,C+1,D],
         bias [2+2K,C+1], labels [n_img,C] f32 (+ the same on the host as a numpy array).
@@ -141,6 +142,12 @@ class CIMHeadStep:
         ck(L.cim_score_heads(P(seg_x), P(weight), P(bias), P(self.scores), n_img, R, self.D, self.C + 1, k,
                              P(self.score_ws), self.score_ws.numel(), C.c_void_p(self.side.cuda_stream)),
            "cim_score_heads")
+        pcl_early = self.head_grads and grad_scores is None and mat is not None
+        if pcl_early:
+            # PCL_loss (model_builder.py:203) needs predict_cls and the cluster matrix only: 8 CTAs of pure latency
+            # that fit next to the overlap stage as well; its gradient is added to head 0's after the loss block
+            ck(L.cim_pcl_loss(P(self.scores), P(mat), P(self.pcl_loss), P(self.pcl_grad), n_img, R, self.C + 1, 127,
+                              1.0 / n_img, 0, C.c_void_p(self.side.cuda_stream)), "cim_pcl_loss")
         ck(L.cim_mask_overlap_ex(P(packed_masks), n_img, R, self.words, self.kb_per_row, None, P(self.area),
                                  P(self.iou), P(self.asy), P(self.overlap_ws), self.overlap_ws.numel(), 0, st),
            "cim_mask_overlap_ex")
@@ -156,6 +163,8 @@ class CIMHeadStep:
         ck(L.cim_roi_align_fwd(P(feat), P(rois), P(self.roi_out), n_img, self.Cf, self.H, self.W, n_img * R, 7, 7,
                                self.scale, self.sr, self.aligned, P(self.roi_ws), self.roi_ws.numel(), st),
            "cim_roi_align_fwd")
+        if mid_hook is not None:
+            mid_hook()                                          # host work that should hide behind the RoIAlign forward
         keep = None
         if self.anti:
             self.ev.synchronize()                               # mining is done; RoIAlign still runs
@@ -183,9 +192,8 @@ class CIMHeadStep:
                 ck(L.cim_head_losses(P(self.scores), P(self.pseudo_labels), P(self.pseudo_iou), P(self.loss_weights),
                                      P(self.valid), P(labels), P(self.losses), P(self.grad_scores), n_img, R, self.C,
                                      k, k, 3.0, 1.0, 3.0, 1.0 / n_img, st), "cim_head_losses")
-                if mat is not None:                                  # + PCL_loss on predict_cls (model_builder.py:203)
-                    ck(L.cim_pcl_loss(P(self.scores), P(mat), P(self.pcl_loss), P(self.grad_scores), n_img, R,
-                                      self.C + 1, 127, 1.0 / n_img, 1, st), "cim_pcl_loss")
+                if pcl_early:                                        # + PCL_loss on predict_cls
+                    self.grad_scores[0].add_(self.pcl_grad)
                 grad_scores = self.grad_scores
             ck(L.cim_score_heads_bwd(P(seg_x), P(weight), P(self.scores), P(grad_scores), P(self.grad_seg_x),
                                      P(self.grad_weight), P(self.grad_bias), n_img, R, self.D, self.C + 1, k,
@@ -253,6 +261,9 @@ class CIMHeadStep:
         self.h2d_bytes += self.h_keep.numel()
         self._slot = 0
         self._staged = False
+        self.res_ev = torch.cuda.Event()
+        self._pending = False
+        self.results_host = None
 
     def set_host_crops(self, crops):
         """Copy a MaskCrops (CPU) of the n_img * R proposal masks into the pinned input buffers."""
@@ -291,7 +302,24 @@ class CIMHeadStep:
             buf["ready"].record(self.copy_stream)
         return self
 
-    def run_host(self, feat, grad_out, seg_x, weight, bias, prefetch_next=True, grad_scores=None, mat=None):
+    def _collect_results(self):
+        """Host side of the result read-back: wait for the D2H copies of the last enqueued step and keep a
+        host copy of what the training loop logs (losses / valid flags / checksums)."""
+        if not self._pending:
+            return
+        self.res_ev.synchronize()
+        self.results_host = {"valid": self.ho_valid.numpy().copy(), "checksum": self.ho_checksum.numpy().copy()}
+        if self.head_grads:
+            self.results_host["losses"] = self.ho_losses.numpy().copy()
+        self._pending = False
+
+    def flush_results(self):
+        """With lag_results: wait for the results of the last run_host() call (self.results_host)."""
+        self._collect_results()
+        return self.results_host
+
+    def run_host(self, feat, grad_out, seg_x, weight, bias, prefetch_next=True, grad_scores=None, mat=None,
+                 lag_results=False):
         """End-to-end step: host rois / labels / bit-packed masks -> device, the step, results ->
         host.  feat / seg_x / grad_out are produced on the device by the backbone, MaskFuse and
         autograd in the real pipeline and therefore stay device tensors.
@@ -307,7 +335,8 @@ class CIMHeadStep:
             self.stage_host_inputs()                           # goes to the other buffer
         cur_stream.wait_event(buf["ready"])
         self.run(feat, buf["rois"], grad_out, buf["masks"], seg_x, weight, bias, buf["labels"],
-                 buf["labels_host"], grad_scores=grad_scores, mat=mat)
+                 buf["labels_host"], grad_scores=grad_scores, mat=mat,
+                 mid_hook=self._collect_results if lag_results else None)
         buf["free"].record(cur_stream)
         self.d_checksum[0] = self.roi_out.view(-1)[::4099].sum()
         self.d_checksum[1] = self.grad_feat.view(-1)[::127].sum()
@@ -319,7 +348,10 @@ class CIMHeadStep:
             self.ho_weights.copy_(self.loss_weights, non_blocking=True)
         self.ho_valid.copy_(self.valid, non_blocking=True)
         self.ho_checksum.copy_(self.d_checksum, non_blocking=True)
-        cur_stream.synchronize()                               # the host reads the results every step
+        self.res_ev.record(cur_stream)
+        self._pending = True
+        if not lag_results:
+            self._collect_results()                            # the host reads the results every step
         if prefetch_next:
             self._slot ^= 1
         else:

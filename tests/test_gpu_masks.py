@@ -162,6 +162,25 @@ def test_tensor_core_path_equals_popc_and_oracle(n, side, n_img):
         assert_f16_bits_equal(u16(t_asy[b]), o_asy.view(np.uint16))
 
 
+@pytest.mark.parametrize("variant", ["2", "4", "3"])
+def test_tensor_core_pipeline_variants_agree(variant, monkeypatch):
+    """CIM_OVERLAP_VARIANT: 2 = loader warp + cp.async staging ring (what masks above 1 Mpixel take), 3 / 4 = every
+    expander thread prefetches its own rows into registers (6 / 4 expanded-B stages; 3 is the default).  All
+    bit-identical to the popcount kernel."""
+    n, side = 600, 128
+    m = synth.rasterize(synth.proposal_params(n, side, 4242))
+    m[5] = 0
+    m[n - 1] = m[3]
+    packed = mask_ops.mask_pack(m[None].to(DEV))
+    want = mask_ops.mask_overlap(packed, return_counts=True, algo="popc")
+    monkeypatch.setenv("CIM_OVERLAP_VARIANT", variant)
+    for _ in range(3):                       # repeated launches: barrier phases, TMEM alloc / dealloc
+        got = mask_ops.mask_overlap(packed, return_counts=True, algo="tensor")
+    assert torch.equal(got[2], want[2]) and torch.equal(got[3], want[3])
+    assert_f16_bits_equal(u16(got[0]), u16(want[0]))
+    assert_f16_bits_equal(u16(got[1]), u16(want[1]))
+
+
 def test_tensor_path_rejects_what_it_cannot_take():
     packed = mask_ops.mask_pack(torch.ones(70, 5, 5, dtype=torch.uint8, device=DEV))      # 1 word per mask
     with pytest.raises(RuntimeError, match="shape"):

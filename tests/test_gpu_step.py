@@ -110,3 +110,67 @@ def test_step_matches_oracle_stage_by_stage(anti):
         assert rel(step.grad_seg_x.cpu().numpy(), gx) < 2e-5
         assert rel(step.grad_weight.cpu().numpy(), gw) < 2e-5
         assert rel(step.grad_bias.cpu().numpy(), gb) < 2e-5
+
+
+def _small_problem(seed=11):
+    n_img, R, C, k, D = 2, 160, 20, 3, 256
+    size, Cf = 128, 32
+    H = W = size // 16
+    gen = torch.Generator().manual_seed(seed)
+    feat = torch.randn(n_img, Cf, H, W, generator=gen)
+    grad_out = torch.randn(n_img * R, Cf, 7, 7, generator=gen)
+    seg_x = torch.randn(n_img * R, D, generator=gen) * 3
+    rois, masks, labels = [], [], []
+    for b in range(n_img):
+        params = synth.proposal_params(R, size, seed + b)
+        rois.append(synth.rois_from_params(params, b))
+        masks.append(synth.rasterize(params))
+        labels.append(synth.image_labels(C, 2, seed + b))
+    torch.manual_seed(1)
+    model = heads.cls_iou_model(D, C + 1, k).to(DEV)
+    weight, bias = (t.detach().contiguous() for t in model._stacked())
+    packed = torch.stack([mask_ops.mask_pack(m.to(DEV)) for m in masks])
+    return dict(n_img=n_img, R=R, C=C, D=D, Cf=Cf, H=H, W=W, size=size, feat=feat.to(DEV), grad_out=grad_out.to(DEV),
+                seg_x=seg_x.to(DEV), rois=torch.cat(rois), labels=torch.cat(labels), packed=packed, weight=weight,
+                bias=bias)
+
+
+@pytest.mark.parametrize("lag", [False, True])
+def test_run_host_equals_run_and_lagged_results_arrive_one_call_later(lag):
+    """run_host() (host rois / labels / packed masks, results read back) gives what run() gives on the same inputs;
+    with lag_results the host copy of step i's losses appears during call i + 1 (or flush_results())."""
+    pr = _small_problem()
+    kb = pr["size"] // 16 if mask_ops.tiled_ok(pr["size"], pr["size"]) else 0
+    mk = lambda: CIMHeadStep(pr["n_img"], pr["R"], pr["C"], pr["Cf"], pr["H"], pr["W"], 1.0 / 16, pr["packed"].shape[-1],
+                             feat_dim=pr["D"], device=DEV, mask_kb_per_row=kb, head_grads=True)
+    ref = mk()
+    want = []
+    np.random.seed(3)
+    for i in range(3):
+        ref.run(pr["feat"], pr["rois"].to(DEV), pr["grad_out"], pr["packed"], pr["seg_x"], pr["weight"], pr["bias"],
+                pr["labels"].to(DEV), pr["labels"].numpy())
+        torch.cuda.synchronize()
+        want.append((ref.losses.cpu().numpy().copy(), ref.valid.cpu().numpy().copy()))
+    step = mk()
+    step.alloc_host_io()
+    step.hi_rois.copy_(pr["rois"])
+    step.hi_labels.copy_(pr["labels"])
+    step.hi_masks.copy_(pr["packed"].cpu())
+    np.random.seed(3)
+    got = []
+    for i in range(3):
+        step.run_host(pr["feat"], pr["grad_out"], pr["seg_x"], pr["weight"], pr["bias"], lag_results=lag)
+        if lag:
+            if i == 0:
+                assert step.results_host is None            # nothing has been read back yet
+            else:
+                got.append(step.results_host)
+        else:
+            got.append(step.results_host)
+    if lag:
+        got.append(step.flush_results())
+    assert len(got) == 3
+    for (w_loss, w_valid), g in zip(want, got):
+        np.testing.assert_array_equal(g["valid"], w_valid)
+        np.testing.assert_array_equal(np.nan_to_num(g["losses"], nan=-7.0), np.nan_to_num(w_loss, nan=-7.0))
+    assert torch.equal(step.grad_feat, ref.grad_feat) and torch.equal(step.roi_out, ref.roi_out)

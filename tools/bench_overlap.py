@@ -21,7 +21,8 @@ for lay in layouts:
         ref = out
     same = lambda a, b: torch.equal(a.view(torch.int16) if a.dtype == torch.float16 else a,
                                     b.view(torch.int16) if b.dtype == torch.float16 else b)
-    assert all(same(a, b) for a, b in zip(out[:4], ref[:4])), f"layout {lay} differs"
+    if not os.environ.get("CIM_OVERLAP_NOCHECK"):
+        assert all(same(a, b) for a, b in zip(out[:4], ref[:4])), f"layout {lay} differs"
     best = 1e9
     for rnd in range(3):
         torch.cuda.synchronize()
