@@ -52,6 +52,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// elect.sync over the full (converged) warp: true in exactly one lane.  Branching on THIS predicate (instead of
+// lane == 0) tells the compiler that a single thread is active, so tcgen05 / TMA instructions in the branch take
+// their uniform-register operands from one R2UR each instead of an ELECT / vote / R2UR.BROADCAST loop per instruction.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+    return leader != 0;
+}
 // make mbarrier.init visible to the async proxy
 __device__ __forceinline__ void fence_mbar_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

@@ -51,23 +51,28 @@ constexpr int THREADS = (NEXP + 2) * 32;
 constexpr int KMAP_WORDS = 512;         // smem copy of a tile's K-block bitmap (16384 K-blocks = 2 Mpixel masks)
 constexpr size_t SI_BYTES = (size_t)(TM + TN) * 4 + 3 * (size_t)TM * 130 * 2;   // epilogue staging (aliases the rings)
 
-constexpr int KLIST = 8192;             // direct variant: smem list of a tile's visited K-blocks (1 Mpixel masks)
-constexpr int PF = 4;                   // direct variant: K-blocks (of its parity) a thread keeps in flight
+constexpr int KLIST = 4096;             // direct variants: smem list of a tile's visited K-blocks (512 Kpixel masks)
+constexpr int SLOT_BYTES = (8 * 32 + 2 * 8 * 32) * 16;  // cp.async variant: 16 B per (A thread) / 2 x 16 B per (B thread), private
 
-// DIRECT_ = false: a loader warp streams packed rows into a staging ring with cp.async (any mask size).
-// DIRECT_ = true:  no loader and no staging -- every expander thread prefetches the 16 B of ITS row(s) PF K-blocks
-//                  ahead straight into registers (ld.global.nc, L1 no-allocate); the visited K-blocks come from a
-//                  list in smem built once per tile.  The single loader warp was the pipeline's bottleneck (~850
-//                  dependent instructions per 4 K-blocks against 2048 MMA cycles); without the staging ring there
-//                  is room for 6 expanded-B stages.
-template <int STAGES_, bool DIRECT_ = false>
+// MODE_ 0: a loader warp streams packed rows into a staging ring with cp.async (any mask size).
+// MODE_ 1: no loader and no staging -- every expander thread prefetches the 16 B of ITS row(s) PF_ K-blocks (of its
+//          parity) ahead straight into registers (ld.global.nc, L1 no-allocate); the visited K-blocks come from a list
+//          in smem built once per tile.  Needs L1 for its outstanding misses: with 6 stages (12 KB of L1 left) the
+//          loads crawl (measured 1.99 ms against 1.22 ms with 4 stages).
+// MODE_ 2: as 1, but the prefetch is a cp.async (LDGSTS, L1 bypass) into 16-byte smem slots private to the thread
+//          (cp.async.wait_group, no barrier), so the stage count is not tied to what is left of L1.
+template <int STAGES_, int MODE_ = 0, int PF_ = 4>
 struct Cfg {
     static constexpr int STAGES = STAGES_;
-    static constexpr bool DIRECT = DIRECT_;
-    static constexpr size_t RING_BYTES = (size_t)STAGES * B_BYTES + (DIRECT ? (size_t)KLIST * 2 : (size_t)NBUF * BUF_BYTES);
+    static constexpr int MODE = MODE_;
+    static constexpr int PF = PF_;
+    static constexpr bool DIRECT = MODE_ != 0;
+    static constexpr size_t LOAD_BYTES = MODE_ == 0 ? (size_t)NBUF * BUF_BYTES
+                                       : MODE_ == 1 ? (size_t)KLIST * 2 : (size_t)KLIST * 2 + (size_t)PF_ * SLOT_BYTES;
+    static constexpr size_t RING_BYTES = (size_t)STAGES * B_BYTES + LOAD_BYTES;
     static constexpr size_t BODY_BYTES = SI_BYTES > RING_BYTES ? SI_BYTES : RING_BYTES;
-    static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + BODY_BYTES + 256 + KMAP_WORDS * 4;
-    static_assert(STAGES % 2 == 0, "the two expander groups own alternate stages");
+    static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + BODY_BYTES + 256 + (DIRECT ? 0 : KMAP_WORDS * 4);
+    static_assert(MODE_ != 0 || STAGES % 2 == 0, "loader variant: the two expander groups own alternate stages");
     static_assert(TN + STAGES * A_COLS <= TMEM_COLS, "TMEM budget");
     static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
 };
@@ -181,7 +186,7 @@ __device__ __forceinline__ __half2 pack_ratio2(int i0, int d0, int i1, int d1) {
 }
 
 template <class K>
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(THREADS, 1)   // 18 warps = 5 on one SM sub-partition: 16384 / (5 * 32) -> 96 registers
 mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__restrict__ area_all,
                        const int32_t *__restrict__ perm_all, const uint32_t *__restrict__ umap_a,
                        const uint32_t *__restrict__ umap_b, int bw, unsigned long long *__restrict__ visited,
@@ -304,53 +309,103 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
             const uint32_t *r1p = img_base + (size_t)(v1 ? __ldg(perm + g1) : 0) * words;
             const uint32_t stages_s = smem_u32(stages);
             const int nj = (nkb - grp + 1) >> 1;              // this group's K-blocks: i = 2 j + grp < nkb
-            uint4 q0[PF], q1[PF];
-            auto fetch = [&](int j, uint4 &a, uint4 &b) {
-                const int kbi = klist[2 * j + grp];
-                a = make_uint4(0u, 0u, 0u, 0u);
-                b = a;
-                if (v0 && !(abl & 16)) a = ldg_stream16(r0p + (size_t)kbi * 4);
-                if (v1 && !(abl & 16)) b = ldg_stream16(r1p + (size_t)kbi * 4);
-            };
+            constexpr int PF = K::PF;
+            // one K-block of this thread: wait for its stage, expand the row(s), hand the stage to the MMA issuer
+            auto process = [&](int j, const uint4 &p0, const uint4 &p1) {
+                const int i = 2 * j + grp, u = i / STAGES, s = i - u * STAGES;
+                const bool skip = is_a ? (abl & 2) : (abl & 1);       // tuning aid (CIM_OVERLAP_ABL): timing only
+                // the ALU part (bits -> bytes in registers) happens BEFORE the wait for the stage, so that only the
+                // stores, the fence and the arrive sit between the stage's release and its next MMAs
+                uint32_t o[32];
+                {
+                    const uint32_t pw[4] = {p0.x, p0.y, p0.z, p0.w};
 #pragma unroll
-            for (int d = 0; d < PF; ++d) {
-                q0[d] = make_uint4(0u, 0u, 0u, 0u);
-                q1[d] = q0[d];
-                if (d < nj) fetch(d, q0[d], q1[d]);
-            }
-            for (int j0 = 0; j0 < nj; j0 += PF) {
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t t[8];
+                        expand32(pw[q], t);
 #pragma unroll
-                for (int d = 0; d < PF; ++d) {
-                    const int j = j0 + d;
-                    if (j < nj) {
-                        const uint4 p0 = q0[d], p1 = q1[d];
-                        if (j + PF < nj) fetch(j + PF, q0[d], q1[d]);
-                        const int i = 2 * j + grp, u = i / STAGES, s = i - u * STAGES;
-                        if (u > 0) mbar_wait(&empty[s], (u - 1) & 1);
-                        if (is_a ? (abl & 2) : (abl & 1)) {
-                            // tuning aid (CIM_OVERLAP_ABL): this operand is not expanded, timing only
-                        } else if (is_a) {
-                            const uint32_t pw[4] = {p0.x, p0.y, p0.z, p0.w};
-                            uint32_t o[32];
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                uint32_t t[8];
-                                expand32(pw[q], t);
-#pragma unroll
-                                for (int gg = 0; gg < 8; ++gg) o[q * 8 + gg] = t[gg];
-                            }
-                            tc_st32(a_lane + (uint32_t)(s * A_COLS), o);      // includes tcgen05.wait::st
-                            tc_fence_before();
-                        } else {
-                            const uint32_t stg = stages_s + (uint32_t)s * B_BYTES;
-                            expand_row_to_smem_s(p0, stg, ch0);
-                            expand_row_to_smem_s(p1, stg, ch1);
-                            fence_proxy_async_smem();
-                        }
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&full[s]);
+                        for (int gg = 0; gg < 8; ++gg) o[q * 8 + gg] = t[gg];
                     }
                 }
+                if (u > 0) mbar_wait(&empty[s], (u - 1) & 1);
+                if (skip) {
+                } else if (is_a) {
+                    tc_st32(a_lane + (uint32_t)(s * A_COLS), o);      // includes tcgen05.wait::st
+                    tc_fence_before();
+                } else {
+                    const uint32_t stg = stages_s + (uint32_t)s * B_BYTES;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) sts16(stg + ch0[q], o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+                    expand_row_to_smem_s(p1, stg, ch1);
+                    fence_proxy_async_smem();
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[s]);
+            };
+            if (K::MODE == 1) {
+                uint4 q0[PF], q1[PF];
+                auto fetch = [&](int j, uint4 &a, uint4 &b) {
+                    const int kbi = klist[2 * j + grp];
+                    a = make_uint4(0u, 0u, 0u, 0u);
+                    b = a;
+                    if (v0 && !(abl & 16)) a = ldg_stream16(r0p + (size_t)kbi * 4);
+                    if (v1 && !(abl & 16)) b = ldg_stream16(r1p + (size_t)kbi * 4);
+                };
+#pragma unroll
+                for (int d = 0; d < PF; ++d) {
+                    q0[d] = make_uint4(0u, 0u, 0u, 0u);
+                    q1[d] = q0[d];
+                    if (d < nj) fetch(d, q0[d], q1[d]);
+                }
+                for (int j0 = 0; j0 < nj; j0 += PF) {
+#pragma unroll
+                    for (int d = 0; d < PF; ++d) {
+                        const int j = j0 + d;
+                        if (j < nj) {
+                            const uint4 p0 = q0[d], p1 = q1[d];
+                            if (j + PF < nj) fetch(j + PF, q0[d], q1[d]);
+                            process(j, p0, p1);
+                        }
+                    }
+                }
+            } else {
+                // slot d of this thread: [d][A threads 256 x 16 B | B threads' first rows 256 x 16 B | second rows]
+                const uint32_t slot0 = smem_u32(staging) + KLIST * 2 +
+                                       (is_a ? (uint32_t)tid * 16u : 4096u + (uint32_t)(tid - 256) * 16u);
+                auto fetch = [&](int j, int d) {       // one cp.async group per call, also when there is nothing to load
+                    if (j < nj && !(abl & 16)) {
+                        const int kbi = klist[2 * j + grp];
+                        const uint32_t dst = slot0 + (uint32_t)d * SLOT_BYTES;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst),
+                                     "l"(r0p + (size_t)kbi * 4), "r"(v0 ? 16u : 0u) : "memory");
+                        if (!is_a)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 4096u),
+                                         "l"(r1p + (size_t)kbi * 4), "r"(v1 ? 16u : 0u) : "memory");
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                };
+#pragma unroll
+                for (int d = 0; d < PF; ++d) fetch(d, d);
+                for (int j0 = 0; j0 < nj; j0 += PF) {
+#pragma unroll
+                    for (int d = 0; d < PF; ++d) {
+                        const int j = j0 + d;
+                        if (j < nj) {
+                            asm volatile("cp.async.wait_group %0;" ::"n"(PF - 1) : "memory");
+                            const uint32_t src = slot0 + (uint32_t)d * SLOT_BYTES;
+                            uint4 p0, p1 = make_uint4(0u, 0u, 0u, 0u);
+                            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(p0.x), "=r"(p0.y), "=r"(p0.z), "=r"(p0.w) : "r"(src) : "memory");
+                            if (!is_a)
+                                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                             : "=r"(p1.x), "=r"(p1.y), "=r"(p1.z), "=r"(p1.w) : "r"(src + 4096u) : "memory");
+                            if (abl & 16) { p0 = make_uint4(0u, 0u, 0u, 0u); p1 = p0; }
+                            process(j, p0, p1);                  // consumes p0 / p1: the slot may be refilled now
+                            fetch(j + PF, d);
+                        }
+                    }
+                }
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
             }
         } else {
         const int srow0 = is_a ? ra : TM + rb0, srow1 = TM + rb1;     // rows inside a staging buffer
@@ -441,23 +496,38 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
         }
     } else {
         // ------------------------------------------------------------------ MMA issuer
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % STAGES;
-            mbar_wait(&full[s], (kb / STAGES) & 1);
-            tc_fence_after();
-            if (lane == 0) {
-                const uint64_t bd = smem_desc(smem_u32(stages + (size_t)s * B_BYTES));
-                const uint32_t a_t = tmem_base + TMEM_A0 + (uint32_t)(s * A_COLS);
-                if (!(abl & 4)) {
+        // ONE thread runs the whole loop (waits included): with the loop around an `if (lane == 0)` the compiler
+        // wraps every tcgen05 instruction into ELECT / R2UR / vote sequences and the ~100 dependent instructions
+        // per K-block of this single warp were what bounded the kernel (ncu: the issuer never waits on `full`,
+        // the 16 expander warps wait on `empty` 40 % of all samples, tensor pipe 50 %).  Stage index and phase
+        // are compile-time / incremental, descriptors are one add away from a per-tile base.
+        if (elect_one() && nkb > 0) {        // elect.sync, not lane == 0: see common.cuh
+            const uint64_t bd0 = smem_desc(smem_u32(stages));
+            const uint32_t a0 = tmem_base + TMEM_A0;
+            uint32_t ph = 0;
+            for (int kb0 = 0; kb0 < nkb; kb0 += STAGES) {
 #pragma unroll
-                    for (int k = 0; k < KB / 32; ++k)       // K = 32 bytes: 8 TMEM columns of A, +2 (x16 B) of B
-                        tc_mma_i8_ts(tmem_base, a_t + 8 * k, bd + 2 * k, (kb | k) != 0);
+                for (int s = 0; s < STAGES; ++s) {
+                    const int kb = kb0 + s;
+                    if (kb < nkb) {
+                        mbar_wait(&full[s], ph);
+                        tc_fence_after();
+                        if (!(abl & 4)) {
+                            const uint64_t bd = bd0 + (uint64_t)(s * (B_BYTES >> 4));
+                            const uint32_t a_t = a0 + (uint32_t)(s * A_COLS);
+                            tc_mma_i8_ts(tmem_base, a_t, bd, kb != 0);
+#pragma unroll
+                            for (int k = 1; k < KB / 32; ++k)   // K = 32 bytes: 8 TMEM columns of A, +2 (x16 B) of B
+                                tc_mma_i8_ts(tmem_base, a_t + 8 * k, bd + 2 * k, 1u);
+                        }
+                        tc_commit(&empty[s]);                    // arrives when the MMAs above have read the stage
+                    }
                 }
-                tc_commit(&empty[s]);                    // arrives when the MMAs above have read the stage
-                if (kb == nkb - 1) tc_commit(accum_full);
+                ph ^= 1;
             }
-            __syncwarp();
+            tc_commit(accum_full);                               // ... when every MMA of the tile has completed
         }
+        __syncwarp();
     }
 
     // ---------------------------------------------------------------------- epilogue
@@ -576,6 +646,7 @@ static int launch(const uint32_t *packed, const int32_t *area, const int32_t *pe
     // 4 the operand loads -- results are garbage, only the timing of what remains means something
     const char *ab = getenv("CIM_OVERLAP_ABL");
     const int abl = ab ? atoi(ab) : 0;
+    if (abl & 32) return CIM_OK;        // bit 5: no tensor kernel at all (times the helper kernels around it)
     cudaFuncSetAttribute(mask_overlap_tc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES);
     mask_overlap_tc_kernel<K><<<(unsigned)(tiles * n_img), THREADS, K::SMEM_BYTES, st>>>(
         packed, area, perm, umap_a, umap_b, bw, visited, tile_order, n, words, n_img, inter, iou, asy, abl);
@@ -599,13 +670,16 @@ int cim_mask_overlap_tc_launch(const uint32_t *packed, const int32_t *area, cons
     const char *v = getenv("CIM_OVERLAP_VARIANT");
     const bool direct_ok = (words + 3) / 4 <= KLIST;
     int variant = v ? atoi(v) : 0;
-    if (variant == 0) variant = direct_ok ? 3 : 2;
+    if (variant == 0) variant = direct_ok ? 6 : 2;
     if (!direct_ok && variant >= 3) variant = 2;
     switch (variant) {
         case 1: return launch<Cfg<2>>(CIM_OV_ARGS);
         case 2: return launch<CfgDefault>(CIM_OV_ARGS);
-        case 4: return launch<Cfg<4, true>>(CIM_OV_ARGS);
-        default: return launch<Cfg<6, true>>(CIM_OV_ARGS);
+        case 3: return launch<Cfg<6, 1, 4>>(CIM_OV_ARGS);
+        case 5: return launch<Cfg<6, 2, 2>>(CIM_OV_ARGS);
+        case 6: return launch<Cfg<4, 2, 4>>(CIM_OV_ARGS);
+        case 7: return launch<Cfg<5, 2, 3>>(CIM_OV_ARGS);
+        default: return launch<Cfg<4, 1, 4>>(CIM_OV_ARGS);
     }
 #undef CIM_OV_ARGS
 }

@@ -185,7 +185,7 @@ score_dx_tc_kernel(const __grid_constant__ CUtensorMap tm_dzh, const __grid_cons
     const uint32_t idesc = tf32_idesc(DX_BN);
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             int it = 0;
             for (int nt = 0; nt < ntiles; ++nt)
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -200,15 +200,15 @@ score_dx_tc_kernel(const __grid_constant__ CUtensorMap tm_dzh, const __grid_cons
                 }
         }
     } else if (warp == 1) {
-        int it = 0, g = 0;                            // g: running chunk index, accumulator g & 1
-        for (int nt = 0; nt < ntiles; ++nt)
-            for (int kb = 0; kb < nkb; ++kb, ++it) {
-                const int s = it % DX_NSTAGE, p = g & 1;
-                const bool first = (kb % DX_CH) == 0, last = (kb % DX_CH) == DX_CH - 1 || kb == nkb - 1;
-                if (first && g >= 2) mbar_wait(&chunk_empty[p], ((g >> 1) - 1) & 1);
-                mbar_wait(&full[s], (it / DX_NSTAGE) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
+        if (elect_one()) {                            // one elected thread runs the whole issue loop (common.cuh)
+            int it = 0, g = 0;                        // g: running chunk index, accumulator g & 1
+            for (int nt = 0; nt < ntiles; ++nt)
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % DX_NSTAGE, p = g & 1;
+                    const bool first = (kb % DX_CH) == 0, last = (kb % DX_CH) == DX_CH - 1 || kb == nkb - 1;
+                    if (first && g >= 2) mbar_wait(&chunk_empty[p], ((g >> 1) - 1) & 1);
+                    mbar_wait(&full[s], (it / DX_NSTAGE) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t base = smem_u32(smem + (size_t)s * DX_STAGE), acc = tmem_base + (uint32_t)DX_BN * p;
                     const uint64_t ah = smem_desc128(base), al = smem_desc128(base + A_TILE);
                     const uint64_t bh = smem_desc128(base + 2 * A_TILE), bl = smem_desc128(base + 2 * A_TILE + DX_B_TILE);
@@ -219,11 +219,10 @@ score_dx_tc_kernel(const __grid_constant__ CUtensorMap tm_dzh, const __grid_cons
                         mma_tf32(acc, al + 2 * k, bh + 2 * k, idesc, 1u);
                     }
                     commit_to(&empty[s]);
-                    if (last) commit_to(&chunk_full[p]);
+                    if (last) { commit_to(&chunk_full[p]); ++g; }
                 }
-                __syncwarp();
-                if (last) ++g;
-            }
+        }
+        __syncwarp();
     } else {
         const int q4 = warp & 3;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q4) << 16);
@@ -318,7 +317,7 @@ score_dw_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     const uint32_t idesc = tf32_idesc(DW_NT);
 
     if (warp == 0) {
-        if (lane == 0) {                                   // x producer: the HBM stream, DW_NRAW tiles ahead
+        if (elect_one()) {                                 // x producer: the HBM stream, DW_NRAW tiles ahead
             for (int kb = 0; kb < nkb; ++kb) {
                 const int r = kb % DW_NRAW;
                 if (kb >= DW_NRAW) mbar_wait(&raw_empty[r], ((kb / DW_NRAW) - 1) & 1);
@@ -327,7 +326,7 @@ score_dw_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             }
         }
     } else if (warp == 6) {
-        if (lane == 0) {                                   // dz^T producer (L2 hits), tied to the MMA stage
+        if (elect_one()) {                                 // dz^T producer (L2 hits), tied to the MMA stage
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % DW_NSTAGE;
                 if (kb >= DW_NSTAGE) mbar_wait(&empty[s], ((kb / DW_NSTAGE) - 1) & 1);
@@ -338,13 +337,13 @@ score_dw_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % DW_NSTAGE, c = kb / DW_CHK, p = c & 1;
-            if (kb % DW_CHK == 0 && c >= 2) mbar_wait(&chunk_empty[p], ((c >> 1) - 1) & 1);
-            mbar_wait(&tma_full[s], (kb / DW_NSTAGE) & 1);
-            mbar_wait(&lo_ready[s], (kb / DW_NSTAGE) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
+        if (elect_one()) {                                 // one elected thread runs the whole issue loop
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % DW_NSTAGE, c = kb / DW_CHK, p = c & 1;
+                if (kb % DW_CHK == 0 && c >= 2) mbar_wait(&chunk_empty[p], ((c >> 1) - 1) & 1);
+                mbar_wait(&tma_full[s], (kb / DW_NSTAGE) & 1);
+                mbar_wait(&lo_ready[s], (kb / DW_NSTAGE) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t base = smem_u32(smem + (size_t)s * DW_STAGE), acc = tmem_base + 256u * p;
                 const uint64_t ah = smem_desc128(base), al = smem_desc128(base + A_TILE);
                 const uint64_t bh = smem_desc128(base + 2 * A_TILE), bl = smem_desc128(base + 2 * A_TILE + DW_B_TILE);
@@ -357,8 +356,8 @@ score_dw_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                 commit_to(&empty[s]);
                 if (kb % DW_CHK == DW_CHK - 1 || kb == nkb - 1) commit_to(&chunk_full[p]);
             }
-            __syncwarp();
         }
+        __syncwarp();
     } else {
         // transpose + split warps: thread t owns column d0 + t of x = row t of the A operand
         const int t = tid - 64;

@@ -102,7 +102,7 @@ score_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 
     if (warp == 0) {
         // ------------------------------------------------------------------ x producer (HBM stream)
-        if (lane == 0) {
+        if (elect_one()) {
             for (int kb = 0; kb < nkb; ++kb) {
                 const int r = kb % NRAW;
                 if (kb >= NRAW) mbar_wait(&raw_empty[r], ((kb / NRAW) - 1) & 1);
@@ -112,7 +112,7 @@ score_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         }
     } else if (warp == 6) {
         // ------------------------------------------------------------------ W producer (L2 hits)
-        if (lane == 0) {
+        if (elect_one()) {
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % NSTAGE;
                 if (kb >= NSTAGE) mbar_wait(&empty[s], ((kb / NSTAGE) - 1) & 1);
@@ -123,14 +123,14 @@ score_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % NSTAGE, c = kb / CHK, p = c & 1;
-            if (kb % CHK == 0 && c >= 2) mbar_wait(&chunk_empty[p], ((c >> 1) - 1) & 1);   // accumulator p drained
-            mbar_wait(&tma_full[s], (kb / NSTAGE) & 1);
-            mbar_wait(&lo_ready[s], (kb / NSTAGE) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
+        // ------------------------------------------------------------------ MMA issuer (one elected thread)
+        if (elect_one()) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % NSTAGE, c = kb / CHK, p = c & 1;
+                if (kb % CHK == 0 && c >= 2) mbar_wait(&chunk_empty[p], ((c >> 1) - 1) & 1);   // accumulator p drained
+                mbar_wait(&tma_full[s], (kb / NSTAGE) & 1);
+                mbar_wait(&lo_ready[s], (kb / NSTAGE) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t base = smem_u32(smem + (size_t)s * STAGE), acc = tmem_base + 256u * p;
                 const uint64_t xh = smem_desc128(base), xl = smem_desc128(base + A_TILE);
                 const uint64_t wh = smem_desc128(base + 2 * A_TILE), wl = smem_desc128(base + 2 * A_TILE + W_TILE);
@@ -148,8 +148,8 @@ score_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                                      smem_u32(&chunk_full[p]))
                                  : "memory");
             }
-            __syncwarp();
         }
+        __syncwarp();
     } else {
         // ------------------------------------------------------------------ split warps (+ chunk drains)
         const int row = tid - 64;                              // 0..127: one x row per thread
