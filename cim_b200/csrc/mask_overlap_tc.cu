@@ -54,21 +54,20 @@ constexpr size_t SI_BYTES = (size_t)(TM + TN) * 4 + 3 * (size_t)TM * 130 * 2;   
 constexpr int KLIST = 4096;             // direct variants: smem list of a tile's visited K-blocks (512 Kpixel masks)
 constexpr int SLOT_BYTES = (8 * 32 + 2 * 8 * 32) * 16;  // cp.async variant: 16 B per (A thread) / 2 x 16 B per (B thread), private
 
-// MODE_ 0: a loader warp streams packed rows into a staging ring with cp.async (any mask size).
-// MODE_ 1: no loader and no staging -- every expander thread prefetches the 16 B of ITS row(s) PF_ K-blocks (of its
-//          parity) ahead straight into registers (ld.global.nc, L1 no-allocate); the visited K-blocks come from a list
-//          in smem built once per tile.  Needs L1 for its outstanding misses: with 6 stages (12 KB of L1 left) the
-//          loads crawl (measured 1.99 ms against 1.22 ms with 4 stages).
-// MODE_ 2: as 1, but the prefetch is a cp.async (LDGSTS, L1 bypass) into 16-byte smem slots private to the thread
-//          (cp.async.wait_group, no barrier), so the stage count is not tied to what is left of L1.
+// MODE_ 0: a loader warp streams packed rows into a staging ring with cp.async; K-blocks come from the tile's bitmap
+//          (any mask size).
+// MODE_ 2: no loader warp and no staging ring -- every expander thread prefetches the 16 B of ITS row(s) PF_ K-blocks
+//          (of its parity) ahead with cp.async (LDGSTS, L1 bypass) into 16-byte smem slots private to the thread
+//          (cp.async.wait_group, no barrier); the visited K-blocks come from a list in smem built once per tile.
+//          (A register prefetch with ld.global.nc was measured too: it needs L1 for its outstanding misses and
+//          crawls once the stages leave little of it -- 1.99 ms with 6 stages against 1.22 ms with 4.)
 template <int STAGES_, int MODE_ = 0, int PF_ = 4>
 struct Cfg {
     static constexpr int STAGES = STAGES_;
     static constexpr int MODE = MODE_;
     static constexpr int PF = PF_;
     static constexpr bool DIRECT = MODE_ != 0;
-    static constexpr size_t LOAD_BYTES = MODE_ == 0 ? (size_t)NBUF * BUF_BYTES
-                                       : MODE_ == 1 ? (size_t)KLIST * 2 : (size_t)KLIST * 2 + (size_t)PF_ * SLOT_BYTES;
+    static constexpr size_t LOAD_BYTES = MODE_ == 0 ? (size_t)NBUF * BUF_BYTES : (size_t)KLIST * 2 + (size_t)PF_ * SLOT_BYTES;
     static constexpr size_t RING_BYTES = (size_t)STAGES * B_BYTES + LOAD_BYTES;
     static constexpr size_t BODY_BYTES = SI_BYTES > RING_BYTES ? SI_BYTES : RING_BYTES;
     static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + BODY_BYTES + 256 + (DIRECT ? 0 : KMAP_WORDS * 4);
@@ -158,26 +157,13 @@ __device__ __forceinline__ void expand_row_to_smem(const uint4 &p, unsigned char
     }
 }
 
-__device__ __forceinline__ uint4 ldg_stream16(const uint32_t *p) {
-    uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "l"(p));
-    return v;
-}
 __device__ __forceinline__ void sts16(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-// one operand row of a K-block -> the swizzled smem row, explicit shared-space stores (stage = 32-bit smem address)
-__device__ __forceinline__ void expand_row_to_smem_s(const uint4 &p, uint32_t stage, const uint32_t (&choff)[8]) {
-    const uint32_t pw[4] = {p.x, p.y, p.z, p.w};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        uint32_t o[8];
-        expand32(pw[q], o);
-        sts16(stage + choff[2 * q], o[0], o[1], o[2], o[3]);
-        sts16(stage + choff[2 * q + 1], o[4], o[5], o[6], o[7]);
-    }
+template <int OFF>
+__device__ __forceinline__ void sts16_off(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0+%5], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d), "n"(OFF)
+                 : "memory");
 }
 
 __device__ __forceinline__ __half2 pack_ratio2(int i0, int d0, int i1, int d1) {
@@ -191,7 +177,7 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
                        const int32_t *__restrict__ perm_all, const uint32_t *__restrict__ umap_a,
                        const uint32_t *__restrict__ umap_b, int bw, unsigned long long *__restrict__ visited,
                        const int32_t *__restrict__ tile_order, int n, long long words, int n_img, int32_t *__restrict__ inter_all, __half *__restrict__ iou_all,
-                       __half *__restrict__ asy_all, int abl) {
+                       __half *__restrict__ asy_all) {
     constexpr int STAGES = K::STAGES;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -307,15 +293,18 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
             const bool v0 = g0 < n, v1 = !is_a && g1 < n;
             const uint32_t *r0p = img_base + (size_t)(v0 ? __ldg(perm + g0) : 0) * words;
             const uint32_t *r1p = img_base + (size_t)(v1 ? __ldg(perm + g1) : 0) * words;
-            const uint32_t stages_s = smem_u32(stages);
             const int nj = (nkb - grp + 1) >> 1;              // this group's K-blocks: i = 2 j + grp < nkb
             constexpr int PF = K::PF;
-            // one K-block of this thread: wait for its stage, expand the row(s), hand the stage to the MMA issuer
+            // smem addresses of the first B row's 8 swizzled 16-byte chunks in stage 0; the second row (+ 32 rows,
+            // same row % 8) sits 4096 B further on, a stage is B_BYTES further on
+            uint32_t chunk[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) chunk[c] = smem_u32(stages) + ch0[c];
+            // one K-block of this thread: expand, wait for the stage, store, hand the stage to the MMA issuer.
+            // The first row's ALU part (bits -> bytes in registers) happens BEFORE the wait, so that less sits
+            // between the stage's release and its next MMAs.
             auto process = [&](int j, const uint4 &p0, const uint4 &p1) {
                 const int i = 2 * j + grp, u = i / STAGES, s = i - u * STAGES;
-                const bool skip = is_a ? (abl & 2) : (abl & 1);       // tuning aid (CIM_OVERLAP_ABL): timing only
-                // the ALU part (bits -> bytes in registers) happens BEFORE the wait for the stage, so that only the
-                // stores, the fence and the arrive sit between the stage's release and its next MMAs
                 uint32_t o[32];
                 {
                     const uint32_t pw[4] = {p0.x, p0.y, p0.z, p0.w};
@@ -328,85 +317,63 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
                     }
                 }
                 if (u > 0) mbar_wait(&empty[s], (u - 1) & 1);
-                if (skip) {
-                } else if (is_a) {
+                if (is_a) {
                     tc_st32(a_lane + (uint32_t)(s * A_COLS), o);      // includes tcgen05.wait::st
                     tc_fence_before();
                 } else {
-                    const uint32_t stg = stages_s + (uint32_t)s * B_BYTES;
+                    const uint32_t so = (uint32_t)s * B_BYTES;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) sts16(stg + ch0[q], o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-                    expand_row_to_smem_s(p1, stg, ch1);
-                    fence_proxy_async_smem();
+                    for (int q = 0; q < 8; ++q)
+                        sts16(chunk[q] + so, o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+                    const uint32_t pw[4] = {p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t t[8];
+                        expand32(pw[q], t);
+                        sts16_off<4096>(chunk[2 * q] + so, t[0], t[1], t[2], t[3]);
+                        sts16_off<4096>(chunk[2 * q + 1] + so, t[4], t[5], t[6], t[7]);
+                    }
+                    fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full[s]);
             };
-            if (K::MODE == 1) {
-                uint4 q0[PF], q1[PF];
-                auto fetch = [&](int j, uint4 &a, uint4 &b) {
+            // slot d of this thread: [d][A threads 256 x 16 B | B threads' first rows 256 x 16 B | second rows]
+            const uint32_t slot0 = smem_u32(staging) + KLIST * 2 +
+                                   (is_a ? (uint32_t)tid * 16u : 4096u + (uint32_t)(tid - 256) * 16u);
+            auto fetch = [&](int j, int d) {       // one cp.async group per call, also when there is nothing to load
+                if (j < nj) {
                     const int kbi = klist[2 * j + grp];
-                    a = make_uint4(0u, 0u, 0u, 0u);
-                    b = a;
-                    if (v0 && !(abl & 16)) a = ldg_stream16(r0p + (size_t)kbi * 4);
-                    if (v1 && !(abl & 16)) b = ldg_stream16(r1p + (size_t)kbi * 4);
-                };
+                    const uint32_t dst = slot0 + (uint32_t)d * SLOT_BYTES;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst),
+                                 "l"(r0p + (size_t)kbi * 4), "r"(v0 ? 16u : 0u) : "memory");
+                    if (!is_a)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 4096u),
+                                     "l"(r1p + (size_t)kbi * 4), "r"(v1 ? 16u : 0u) : "memory");
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
+#pragma unroll
+            for (int d = 0; d < PF; ++d) fetch(d, d);
+            for (int j0 = 0; j0 < nj; j0 += PF) {
 #pragma unroll
                 for (int d = 0; d < PF; ++d) {
-                    q0[d] = make_uint4(0u, 0u, 0u, 0u);
-                    q1[d] = q0[d];
-                    if (d < nj) fetch(d, q0[d], q1[d]);
-                }
-                for (int j0 = 0; j0 < nj; j0 += PF) {
-#pragma unroll
-                    for (int d = 0; d < PF; ++d) {
-                        const int j = j0 + d;
-                        if (j < nj) {
-                            const uint4 p0 = q0[d], p1 = q1[d];
-                            if (j + PF < nj) fetch(j + PF, q0[d], q1[d]);
-                            process(j, p0, p1);
-                        }
-                    }
-                }
-            } else {
-                // slot d of this thread: [d][A threads 256 x 16 B | B threads' first rows 256 x 16 B | second rows]
-                const uint32_t slot0 = smem_u32(staging) + KLIST * 2 +
-                                       (is_a ? (uint32_t)tid * 16u : 4096u + (uint32_t)(tid - 256) * 16u);
-                auto fetch = [&](int j, int d) {       // one cp.async group per call, also when there is nothing to load
-                    if (j < nj && !(abl & 16)) {
-                        const int kbi = klist[2 * j + grp];
-                        const uint32_t dst = slot0 + (uint32_t)d * SLOT_BYTES;
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst),
-                                     "l"(r0p + (size_t)kbi * 4), "r"(v0 ? 16u : 0u) : "memory");
+                    const int j = j0 + d;
+                    if (j < nj) {
+                        asm volatile("cp.async.wait_group %0;" ::"n"(PF - 1) : "memory");
+                        const uint32_t src = slot0 + (uint32_t)d * SLOT_BYTES;
+                        uint4 p0, p1 = make_uint4(0u, 0u, 0u, 0u);
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(p0.x), "=r"(p0.y), "=r"(p0.z), "=r"(p0.w) : "r"(src) : "memory");
                         if (!is_a)
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 4096u),
-                                         "l"(r1p + (size_t)kbi * 4), "r"(v1 ? 16u : 0u) : "memory");
-                    }
-                    asm volatile("cp.async.commit_group;" ::: "memory");
-                };
-#pragma unroll
-                for (int d = 0; d < PF; ++d) fetch(d, d);
-                for (int j0 = 0; j0 < nj; j0 += PF) {
-#pragma unroll
-                    for (int d = 0; d < PF; ++d) {
-                        const int j = j0 + d;
-                        if (j < nj) {
-                            asm volatile("cp.async.wait_group %0;" ::"n"(PF - 1) : "memory");
-                            const uint32_t src = slot0 + (uint32_t)d * SLOT_BYTES;
-                            uint4 p0, p1 = make_uint4(0u, 0u, 0u, 0u);
                             asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                                         : "=r"(p0.x), "=r"(p0.y), "=r"(p0.z), "=r"(p0.w) : "r"(src) : "memory");
-                            if (!is_a)
-                                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                                             : "=r"(p1.x), "=r"(p1.y), "=r"(p1.z), "=r"(p1.w) : "r"(src + 4096u) : "memory");
-                            if (abl & 16) { p0 = make_uint4(0u, 0u, 0u, 0u); p1 = p0; }
-                            process(j, p0, p1);                  // consumes p0 / p1: the slot may be refilled now
-                            fetch(j + PF, d);
-                        }
+                                         : "=r"(p1.x), "=r"(p1.y), "=r"(p1.z), "=r"(p1.w) : "r"(src + 4096u) : "memory");
+                        process(j, p0, p1);                  // consumes p0 / p1: the slot may be refilled now
+                        fetch(j + PF, d);
                     }
                 }
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
             }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         } else {
         const int srow0 = is_a ? ra : TM + rb0, srow1 = TM + rb1;     // rows inside a staging buffer
         for (int g = 0; g < ngroups; ++g) {
@@ -512,14 +479,12 @@ mask_overlap_tc_kernel(const uint32_t *__restrict__ packed, const int32_t *__res
                     if (kb < nkb) {
                         mbar_wait(&full[s], ph);
                         tc_fence_after();
-                        if (!(abl & 4)) {
-                            const uint64_t bd = bd0 + (uint64_t)(s * (B_BYTES >> 4));
-                            const uint32_t a_t = a0 + (uint32_t)(s * A_COLS);
-                            tc_mma_i8_ts(tmem_base, a_t, bd, kb != 0);
+                        const uint64_t bd = bd0 + (uint64_t)(s * (B_BYTES >> 4));
+                        const uint32_t a_t = a0 + (uint32_t)(s * A_COLS);
+                        tc_mma_i8_ts(tmem_base, a_t, bd, kb != 0);
 #pragma unroll
-                            for (int k = 1; k < KB / 32; ++k)   // K = 32 bytes: 8 TMEM columns of A, +2 (x16 B) of B
-                                tc_mma_i8_ts(tmem_base, a_t + 8 * k, bd + 2 * k, 1u);
-                        }
+                        for (int k = 1; k < KB / 32; ++k)       // K = 32 bytes: 8 TMEM columns of A, +2 (x16 B) of B
+                            tc_mma_i8_ts(tmem_base, a_t + 8 * k, bd + 2 * k, 1u);
                         tc_commit(&empty[s]);                    // arrives when the MMAs above have read the stage
                     }
                 }
@@ -642,14 +607,9 @@ static int launch(const uint32_t *packed, const int32_t *area, const int32_t *pe
     const int nrb = (n + TM - 1) / TM, ncb = (n + TN - 1) / TN;
     int tiles = 0;
     for (int i = 0; i < nrb; ++i) tiles += ncb - (i >> 1);
-    // CIM_OVERLAP_ABL (tuning aid, direct variants): bit 0 / 1 skip the B / A expansion, 2 the MMAs,
-    // 4 the operand loads -- results are garbage, only the timing of what remains means something
-    const char *ab = getenv("CIM_OVERLAP_ABL");
-    const int abl = ab ? atoi(ab) : 0;
-    if (abl & 32) return CIM_OK;        // bit 5: no tensor kernel at all (times the helper kernels around it)
     cudaFuncSetAttribute(mask_overlap_tc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES);
     mask_overlap_tc_kernel<K><<<(unsigned)(tiles * n_img), THREADS, K::SMEM_BYTES, st>>>(
-        packed, area, perm, umap_a, umap_b, bw, visited, tile_order, n, words, n_img, inter, iou, asy, abl);
+        packed, area, perm, umap_a, umap_b, bw, visited, tile_order, n, words, n_img, inter, iou, asy);
     return cim_launch_status();
 }
 
@@ -664,22 +624,12 @@ int cim_mask_overlap_tc_launch(const uint32_t *packed, const int32_t *area, cons
                                const uint32_t *umap_a, const uint32_t *umap_b, int bw, unsigned long long *visited,
                                const int32_t *tile_order, int n_img, int n, long long words, int32_t *inter,
                                __half *iou, __half *asy, cudaStream_t st) {
-    // CIM_OVERLAP_VARIANT is a tuning aid (pipeline experiments); unset = the default.  The direct variants need
-    // the tile's K-block list to fit its smem array (masks up to 1 Mpixel); larger masks take the loader-warp kernel.
+    // The direct kernel needs the tile's K-block list to fit its smem array (masks up to 512 Kpixel); larger masks
+    // take the loader-warp kernel.  CIM_OVERLAP_VARIANT=2 forces the loader-warp kernel (tests, A/B timing).
 #define CIM_OV_ARGS packed, area, perm, umap_a, umap_b, bw, visited, tile_order, n_img, n, words, inter, iou, asy, st
     const char *v = getenv("CIM_OVERLAP_VARIANT");
     const bool direct_ok = (words + 3) / 4 <= KLIST;
-    int variant = v ? atoi(v) : 0;
-    if (variant == 0) variant = direct_ok ? 6 : 2;
-    if (!direct_ok && variant >= 3) variant = 2;
-    switch (variant) {
-        case 1: return launch<Cfg<2>>(CIM_OV_ARGS);
-        case 2: return launch<CfgDefault>(CIM_OV_ARGS);
-        case 3: return launch<Cfg<6, 1, 4>>(CIM_OV_ARGS);
-        case 5: return launch<Cfg<6, 2, 2>>(CIM_OV_ARGS);
-        case 6: return launch<Cfg<4, 2, 4>>(CIM_OV_ARGS);
-        case 7: return launch<Cfg<5, 2, 3>>(CIM_OV_ARGS);
-        default: return launch<Cfg<4, 1, 4>>(CIM_OV_ARGS);
-    }
+    if (!direct_ok || (v && atoi(v) == 2)) return launch<CfgDefault>(CIM_OV_ARGS);
+    return launch<Cfg<4, 2, 4>>(CIM_OV_ARGS);
 #undef CIM_OV_ARGS
 }

@@ -470,7 +470,7 @@ roi_align_fwd_tile_kernel(const float *__restrict__ feat, const int *__restrict_
 }
 
 // ----------------------------------------------------------------------------- tile: backward
-constexpr int NWB = 16;             // consumer warps of the backward CTA; warp w owns row pairs
+constexpr int NWB_DEFAULT = 16;     // consumer warps of the backward CTA; warp w owns row pairs
                                     // {y : (y >> 1) % 16 == w}  (D_OWN is computed for exactly this map)
 constexpr int NBR = 4;              // ROIs per ring slot: one full/empty barrier round per 4 ROIs
 constexpr int NS = 3;               // ring slots
@@ -487,7 +487,7 @@ constexpr int SLOT_FLOATS_F = NBR_F * (2 * STAGE_FLOATS + DESC_WORDS + MASK_PAD)
 //   x pass: (t[2p][xo+l], t[2p+1][xo+l]) += wx[pw][l] * r[pw]       7T x (LDS.64, FFMA2, STS.64)
 // FUSED (MaskFuse prologue): the gradient of the pooled value is g[ph][pw] + g2[ph][pw] * m[ph][pw] with g2 the
 // gradient block of the masked copy (STAGE_FLOATS further on in the slot) and m the ROI's 7 x 7 mask (smem).
-template <int T, bool XINC, bool FUSED>
+template <int T, bool XINC, bool FUSED, int NW>
 __device__ __forceinline__ void bwd_pairs(float *__restrict__ tile_c, int W, const int *d,
                                           const float *__restrict__ g, const float *__restrict__ m, int warp, int y0,
                                           int y1) {
@@ -511,10 +511,10 @@ __device__ __forceinline__ void bwd_pairs(float *__restrict__ tile_c, int W, con
     }
     float2 *tile2 = reinterpret_cast<float2 *>(tile_c);
     const int pb = y0 >> 1, p1 = (y1 + 1) >> 1;
-    // first owned pair >= pb: pairs p with p % NWB == warp
-    int p = pb + ((warp - pb) & (NWB - 1));
+    // first owned pair >= pb: pairs p with p % NW == warp
+    int p = pb + ((warp - pb) & (NW - 1));
 #pragma unroll 1
-    for (; p < p1; p += NWB) {
+    for (; p < p1; p += NW) {
         float2 r[PW];
 #pragma unroll
         for (int pw = 0; pw < PW; ++pw) r[pw] = make_float2(0.f, 0.f);
@@ -588,7 +588,7 @@ __device__ __forceinline__ void red_add4(float *gptr, float a, float b, float c,
 // FUSED (MaskFuse prologue): grad_out is [K][2C][49]; the effective gradient of the pooled features is
 // g[c] + g[C + c] * mask[roi].  Both gradient blocks and the (padded) mask of a ROI travel in the ring slot;
 // mask7 points at the PADDED masks [K][MASK_PAD] in the workspace.
-template <bool FUSED>
+template <bool FUSED, int NWB>
 __global__ void __launch_bounds__(NWB * 32, 1)
 roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restrict__ hdr,
                           const int *__restrict__ img_start, const int *__restrict__ descs,
@@ -698,7 +698,8 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
             bool mine = false;
             if (lane < cnt) {
                 const int2 ff = *reinterpret_cast<const int2 *>(dbase + lane * DESC_WORDS + D_XINC);   // (xinc, own)
-                mine = ((ff.y >> warp) & 1) != 0 && dbase[lane * DESC_WORDS + D_FLAGX] == 0;
+                const int own = NWB == 16 ? ff.y : (ff.y | (ff.y >> 8));       // D_OWN: bit (pair & 15)
+                mine = ((own >> warp) & 1) != 0 && dbase[lane * DESC_WORDS + D_FLAGX] == 0;
             }
             unsigned todo = __ballot_sync(0xffffffffu, mine);
             while (todo) {
@@ -712,19 +713,19 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
                 const int T = d[D_TX];
                 if (d[D_XINC]) {
                     switch (T) {
-                        case 2: bwd_pairs<2, true, FUSED>(tile_c, W, d, g, m, warp, y0, y1); break;
-                        case 3: bwd_pairs<3, true, FUSED>(tile_c, W, d, g, m, warp, y0, y1); break;
-                        case 4: bwd_pairs<4, true, FUSED>(tile_c, W, d, g, m, warp, y0, y1); break;
-                        case 6: bwd_pairs<6, true, FUSED>(tile_c, W, d, g, m, warp, y0, y1); break;
-                        default: bwd_pairs<8, true, FUSED>(tile_c, W, d, g, m, warp, y0, y1); break;
+                        case 2: bwd_pairs<2, true, FUSED, NWB>(tile_c, W, d, g, m, warp, y0, y1); break;
+                        case 3: bwd_pairs<3, true, FUSED, NWB>(tile_c, W, d, g, m, warp, y0, y1); break;
+                        case 4: bwd_pairs<4, true, FUSED, NWB>(tile_c, W, d, g, m, warp, y0, y1); break;
+                        case 6: bwd_pairs<6, true, FUSED, NWB>(tile_c, W, d, g, m, warp, y0, y1); break;
+                        default: bwd_pairs<8, true, FUSED, NWB>(tile_c, W, d, g, m, warp, y0, y1); break;
                     }
                 } else {
                     switch (T) {
-                        case 2: bwd_pairs<2, false, FUSED>(tile_c, W, d, g, m, warp, y0, y1); break;
-                        case 3: bwd_pairs<3, false, FUSED>(tile_c, W, d, g, m, warp, y0, y1); break;
-                        case 4: bwd_pairs<4, false, FUSED>(tile_c, W, d, g, m, warp, y0, y1); break;
-                        case 6: bwd_pairs<6, false, FUSED>(tile_c, W, d, g, m, warp, y0, y1); break;
-                        default: bwd_pairs<8, false, FUSED>(tile_c, W, d, g, m, warp, y0, y1); break;
+                        case 2: bwd_pairs<2, false, FUSED, NWB>(tile_c, W, d, g, m, warp, y0, y1); break;
+                        case 3: bwd_pairs<3, false, FUSED, NWB>(tile_c, W, d, g, m, warp, y0, y1); break;
+                        case 4: bwd_pairs<4, false, FUSED, NWB>(tile_c, W, d, g, m, warp, y0, y1); break;
+                        case 6: bwd_pairs<6, false, FUSED, NWB>(tile_c, W, d, g, m, warp, y0, y1); break;
+                        default: bwd_pairs<8, false, FUSED, NWB>(tile_c, W, d, g, m, warp, y0, y1); break;
                     }
                 }
             }
@@ -1212,19 +1213,19 @@ static int roi_bwd_impl(const float *grad_out, const float *rois, const float *m
         return cim_launch_status();
     }
     cudaMemsetAsync(grad_feat, 0, sizeof(float) * (size_t)B * C * H * W, st);
+    // 16 consumer warps, one row pair each.  (8 warps owning two pairs half a map apart balance the centre-heavy
+    // row load better -- max / mean 1.06 instead of 1.21 on the synthetic proposals -- but lose more to the halved
+    // thread-level parallelism: 2.10 ms against 1.81 ms at cfg2.)
+    auto go = [&](auto kern, int nw, size_t smem, const float *mk) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<grid, nw * 32, smem, st>>>(grad_out, w.hdr, w.img_start, w.desc, mk, grad_feat, B, C, H, W, p.pitch);
+    };
     if (mask7) {
         roi_mask_pad_kernel<<<(K * MASK_PAD + 255) / 256, 256, 0, st>>>(mask7, w.maskpad, K, NBIN);
         if ((rc = cim_launch_status())) return rc;
-        cudaFuncSetAttribute(roi_align_bwd_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)p.smem_bwd_fused);
-        roi_align_bwd_tile_kernel<true><<<grid, NWB * 32, p.smem_bwd_fused, st>>>(grad_out, w.hdr, w.img_start, w.desc,
-                                                                                   w.maskpad, grad_feat, B, C, H, W,
-                                                                                   p.pitch);
+        go(roi_align_bwd_tile_kernel<true, NWB_DEFAULT>, NWB_DEFAULT, p.smem_bwd_fused, w.maskpad);
     } else {
-        cudaFuncSetAttribute(roi_align_bwd_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)p.smem_bwd);
-        roi_align_bwd_tile_kernel<false><<<grid, NWB * 32, p.smem_bwd, st>>>(grad_out, w.hdr, w.img_start, w.desc,
-                                                                              nullptr, grad_feat, B, C, H, W, p.pitch);
+        go(roi_align_bwd_tile_kernel<false, NWB_DEFAULT>, NWB_DEFAULT, p.smem_bwd, nullptr);
     }
     if ((rc = cim_launch_status())) return rc;
     roi_align_generic_kernel<true><<<dim3((unsigned)((K + 7) / 8), 1), 256, 0, st>>>(grad_out, rois, grad_feat, w.hdr, w.desc,

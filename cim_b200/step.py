@@ -20,6 +20,8 @@ host hop is the anti-noise sampling (heads.py:451-466, numpy global RNG); it is 
 the RoIAlign kernels, which do not depend on it.
 """
 import ctypes as C
+import os
+import time
 
 import numpy as np
 import torch
@@ -108,7 +110,8 @@ class CIMHeadStep:
         self.h_weight = pin((k, n_img, self.cap), torch.float32)
         self.h_keep = pin((k, n_img, self.cap), torch.uint8)
         self.ev = torch.cuda.Event()
-        self.side = torch.cuda.Stream(device=self.dev)
+        self.side = torch.cuda.Stream(device=self.dev, priority=-1)     # scoring GEMM next to the overlap helpers
+        self.trace = [] if os.environ.get("CIM_STEP_TRACE") else None
         # layer l reads (cls, det) = (predict_cls, predict_det) for l = 0, else (ref_cls[l-1], ref_iou[l-1])
         s = self.scores.view(nh, n_img, R, C1)
         cls_src = [s[0]] + [s[2 + l - 1] for l in range(1, k)]
@@ -133,6 +136,9 @@ class CIMHeadStep:
         losses, scoring backward, [allreduce ||] RoIAlign backward."""
         L, p, dev = self.L, self.p, self.dev
         P, n_img, R, k = _lib.ptr, self.n_img, self.R, self.K
+        tr = self.trace                                         # host timeline (CIM_STEP_TRACE=1), else None
+        if tr is not None:
+            tr.append(("run", time.perf_counter()))
         st = _lib.stream_ptr(dev)
         ck = _lib.check
         # the scoring GEMM (independent of the maps) runs on a side stream next to the overlap stage, whose small
@@ -166,8 +172,12 @@ class CIMHeadStep:
         if mid_hook is not None:
             mid_hook()                                          # host work that should hide behind the RoIAlign forward
         keep = None
+        if tr is not None:
+            tr.append(("launched_phase1", time.perf_counter()))
         if self.anti:
             self.ev.synchronize()                               # mining is done; RoIAlign still runs
+            if tr is not None:
+                tr.append(("mining_done", time.perf_counter()))
             counts = self.h_count.numpy()
             cls_h, w_h, keep_h = self.h_class.numpy(), self.h_weight.numpy(), self.h_keep.numpy()
             keep_h[:] = 1
@@ -181,6 +191,8 @@ class CIMHeadStep:
                         keep_h[l, b, :g] = _anti_noise_keep(cls_h[l, b, :g], w_h[l, b, :g], present)
             self.gt_keep[:, :, :self.cap].copy_(self.h_keep, non_blocking=True)
             keep = self.gt_keep
+            if tr is not None:
+                tr.append(("sampled", time.perf_counter()))
         ck(L.cim_assign(C.byref(p), P(self.iou), P(self.gt_count), P(self.gt_rows), P(self.gt_class),
                         P(self.gt_weight), P(keep), P(self.pseudo_labels), P(self.pseudo_iou),
                         P(self.loss_weights), P(self.valid), st), "cim_assign")
@@ -204,6 +216,8 @@ class CIMHeadStep:
            "cim_roi_align_bwd")
         if reduce_work is not None:
             reduce_work()                                       # current stream waits for the allreduce
+        if tr is not None:
+            tr.append(("launched_phase2", time.perf_counter()))
         return self
 
     # -------------------------------------------------------------------------------------

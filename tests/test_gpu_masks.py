@@ -162,11 +162,11 @@ def test_tensor_core_path_equals_popc_and_oracle(n, side, n_img):
         assert_f16_bits_equal(u16(t_asy[b]), o_asy.view(np.uint16))
 
 
-@pytest.mark.parametrize("variant", ["2", "3", "4", "5", "6", "7"])
+@pytest.mark.parametrize("variant", ["2", "0"])
 def test_tensor_core_pipeline_variants_agree(variant, monkeypatch):
-    """CIM_OVERLAP_VARIANT: 2 = loader warp + cp.async staging ring (what masks above 512 Kpixel take), 3 / 4 = every
-    expander thread prefetches its own rows into registers (6 / 4 expanded-B stages), 5 / 6 / 7 = the same prefetch
-    as cp.async into thread-private smem slots (6 / 4 / 5 stages).  All bit-identical to the popcount kernel."""
+    """CIM_OVERLAP_VARIANT=2: the loader-warp kernel (cp.async staging ring; what masks above 512 Kpixel take);
+    default: every expander thread prefetches its own rows (cp.async into thread-private slots, K-block list in
+    smem).  Both bit-identical to the popcount kernel, also over repeated launches."""
     n, side = 600, 128
     m = synth.rasterize(synth.proposal_params(n, side, 4242))
     m[5] = 0
