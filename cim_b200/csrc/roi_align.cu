@@ -978,19 +978,35 @@ __global__ void roi_align_generic_kernel(const float *__restrict__ in, const flo
                                          const int *__restrict__ descs, const float *__restrict__ mask7, int mode,
                                          int B, int C, int H, int W, int K, int oh, int ow, float scale, int sr,
                                          int aligned) {
-    // mode 0: one CTA column per ROI.  mode 1 (leftover pass): one WARP per ROI, 8 ROIs per CTA -- almost every warp
-    // exits at once, and 8x fewer CTAs have to be scheduled for nothing
-    const int k = mode == 1 ? blockIdx.x * 8 + (threadIdx.x >> 5) : blockIdx.x;
-    if (k >= K) return;
-    if (mode == 1 && __ldg(hdr) == 0) {
-        const int *d = descs + (size_t)k * DESC_WORDS;
-        if ((__ldg(d + D_FLAGY) | __ldg(d + D_FLAGX)) == 0) return;
+    // mode 0: one CTA column per ROI.  mode 1 (leftover pass): 8 ROIs per CTA -- warp w checks ROI 8 blockIdx.x + w
+    // (almost every one was done by the tile kernel: 8x fewer CTAs scheduled for nothing), then the WHOLE CTA works
+    // through the ROIs that are left, one after the other (a VGG-size ROI with bins wider than 8 taps is 25 000
+    // outputs x up to 100 samples: far too much for a single warp)
+    __shared__ int s_todo;
+    int todo = 1, kbase = blockIdx.x;
+    if (mode == 1) {
+        if (threadIdx.x == 0) s_todo = 0;
+        __syncthreads();
+        const int kw = blockIdx.x * 8 + (threadIdx.x >> 5);
+        if ((threadIdx.x & 31) == 0 && kw < K) {
+            bool left = true;
+            if (__ldg(hdr) == 0) {
+                const int *d = descs + (size_t)kw * DESC_WORDS;
+                left = (__ldg(d + D_FLAGY) | __ldg(d + D_FLAGX)) != 0;
+            }
+            if (left) atomicOr(&s_todo, 1 << (threadIdx.x >> 5));
+        }
+        __syncthreads();
+        todo = s_todo;
+        kbase = blockIdx.x * 8;
     }
+    for (; todo; todo &= todo - 1) {
+    const int k = kbase + (mode == 1 ? __ffs(todo) - 1 : 0);
     const Geom g = roi_geom(rois + 5 * (size_t)k, scale, oh, ow, sr, aligned);
     const int per_roi = C * oh * ow;
     const bool valid_b = g.b >= 0 && g.b < B;
-    const int e0 = mode == 1 ? (threadIdx.x & 31) : blockIdx.y * blockDim.x + threadIdx.x;
-    const int estep = mode == 1 ? 32 : gridDim.y * blockDim.x;
+    const int e0 = mode == 1 ? threadIdx.x : blockIdx.y * blockDim.x + threadIdx.x;
+    const int estep = mode == 1 ? blockDim.x : gridDim.y * blockDim.x;
     for (int e = e0; e < per_roi; e += estep) {
         const int pw = e % ow, ph = (e / ow) % oh, c = e / (ow * oh);
         const size_t oidx = mask7 ? (size_t)k * 2 * per_roi + e : (size_t)k * per_roi + e;
@@ -1027,6 +1043,7 @@ __global__ void roi_align_generic_kernel(const float *__restrict__ in, const flo
             outp[oidx] = v;
             if (mask7) outp[oidx + per_roi] = v * mk;
         }
+    }
     }
 }
 
