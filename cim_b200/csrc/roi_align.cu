@@ -37,14 +37,27 @@
 namespace {
 
 constexpr int PH = 7, PW = 7, NBIN = 49;
-constexpr int MAXT = 8;             // max collapsed taps per bin and axis in a descriptor
-constexpr int WYP = MAXT + 2;       // row weights of a bin, padded: [0, w_0 .. w_7, 0]
-constexpr int DESC_WORDS = 168;     // 672 B per ROI
+// Descriptor layouts.  NARROW (tile kernels: the map sits in shared memory, every byte next to it counts): up to 8
+// collapsed taps per bin and axis, 672 B per ROI.  WIDE (global-pairs kernels, large maps such as VGG-16's 64 x 64 at
+// stride 8, where a bin of a full-image ROI spans 11 taps): up to 12 taps, 896 B per ROI.  Words 0..39 are common.
+template <bool WIDE>
+struct DescL {
+    static constexpr int MT = WIDE ? 12 : 8;        // max collapsed taps per bin and axis
+    static constexpr int WYP = MT + 2;              // row weights of a bin, padded: [0, w_0 .. w_{MT-1}, 0]
+    static constexpr int WX = WIDE ? 140 : 112;     // first word of the column weights [7][MT]
+    static constexpr int WORDS = WX + 7 * MT;       // 224 : 168
+};
+constexpr int MAXT = DescL<false>::MT;
+constexpr int WYP = DescL<false>::WYP;
+constexpr int DESC_WORDS = DescL<false>::WORDS;     // 672 B per ROI (tile kernels)
+constexpr int DESC_WORDS_MAX = DescL<true>::WORDS;  // what the workspace reserves per ROI
 enum {
     D_B = 0, D_FLAGY = 1, D_FLAGX = 2, D_TX = 3, D_Y0 = 4, D_Y1 = 5, D_XINC = 6, D_OWN = 7,
-    D_YLO = 8, D_YN = 16, D_XLO = 24, D_PHR = 32 /* 32 bytes */, D_WY = 40 /* [7][WYP] */, D_WX = 112 /* [7][MAXT] */
+    D_YLO = 8, D_YN = 16, D_XLO = 24, D_PHR = 32 /* 32 bytes */, D_WY = 40 /* [7][WYP] */, D_WX = DescL<false>::WX
 };
-static_assert(D_WY + 7 * WYP <= D_WX && D_WX + 7 * MAXT == DESC_WORDS && (DESC_WORDS % 4) == 0, "descriptor layout");
+static_assert(D_WY + 7 * DescL<false>::WYP <= DescL<false>::WX && DescL<false>::WORDS == 168, "narrow descriptor");
+static_assert(D_WY + 7 * DescL<true>::WYP <= DescL<true>::WX && (DescL<true>::WX % 4) == 0 &&
+              (DescL<true>::WORDS % 4) == 0 && DescL<true>::WORDS / 4 <= 64, "wide descriptor");
 constexpr int WS_HDR_BYTES = 256;   // word 0: "rois not grouped by image" flag
 constexpr int CH = 32;              // channels per tile (= lanes)
 constexpr int STAGE_FLOATS = CH * NBIN;          // 1568 floats = 6272 B
@@ -73,6 +86,7 @@ __device__ __forceinline__ float sample_coord(float start, float bin, int p, int
     return __fadd_rn(a, b);
 }
 
+template <bool WIDE>
 __global__ void roi_prep_kernel(const float *__restrict__ rois, int K, int B, int H, int W,
                                 int oh, int ow, float scale, int sampling_ratio, int aligned,
                                 int *__restrict__ hdr, int *__restrict__ img_start,
@@ -81,7 +95,8 @@ __global__ void roi_prep_kernel(const float *__restrict__ rois, int K, int B, in
     int k = gid >> 1, axis = gid & 1;          // axis 0 = y (rows), 1 = x (columns)
     if (k >= K) return;
     const float *r = rois + 5 * (size_t)k;
-    int *d = desc + (size_t)k * DESC_WORDS;
+    constexpr int MAXT = DescL<WIDE>::MT, WYP = DescL<WIDE>::WYP, D_WX = DescL<WIDE>::WX;
+    int *d = desc + (size_t)k * DescL<WIDE>::WORDS;
     int b = (int)r[0];
 
     if (axis == 0) {
@@ -182,8 +197,8 @@ __global__ void roi_prep_kernel(const float *__restrict__ rois, int K, int B, in
             phr[j] = (unsigned char)(first | (cnt << 4));
         }
     } else {
-        // tap class T in {2,3,4,6,8}: the x loops of the tile kernels are unrolled T times.
-        int T = nmax <= 2 ? 2 : nmax <= 3 ? 3 : nmax <= 4 ? 4 : nmax <= 6 ? 6 : 8;
+        // tap class T in {2,3,4,6,8(,12)}: the x loops of the tile kernels are unrolled T times.
+        int T = nmax <= 2 ? 2 : nmax <= 3 ? 3 : nmax <= 4 ? 4 : nmax <= 6 ? 6 : nmax <= 8 ? 8 : 12;
         if (W < T) flag = 1;
         d[D_FLAGX] = flag;
         d[D_TX] = T;
@@ -267,9 +282,10 @@ __device__ __forceinline__ void fwd_pairs(const float *__restrict__ tile_c, int 
     const int xs = GLB ? xs_rt : 1;
     constexpr bool WREG = T <= 4;
     constexpr int TR = WREG ? T : 1;
+    constexpr int MAXT = DescL<GLB>::MT;                  // GLB kernels read WIDE descriptors
     float wx[PW][TR];
     int xo[PW];
-    const float *dwx = reinterpret_cast<const float *>(d + D_WX);
+    const float *dwx = reinterpret_cast<const float *>(d + DescL<GLB>::WX);
     {
         int4 a = *reinterpret_cast<const int4 *>(d + D_XLO), b = *reinterpret_cast<const int4 *>(d + D_XLO + 4);
         xo[0] = a.x; xo[1] = a.y; xo[2] = a.z; xo[3] = a.w; xo[4] = b.x; xo[5] = b.y; xo[6] = b.z;
@@ -308,9 +324,11 @@ __device__ __forceinline__ void fwd_pairs(const float *__restrict__ tile_c, int 
             } else {
                 const float4 a = *reinterpret_cast<const float4 *>(dwx + pw * MAXT);
                 const float4 b = *reinterpret_cast<const float4 *>(dwx + pw * MAXT + 4);
-                const float t8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (T > 8) c = *reinterpret_cast<const float4 *>(dwx + pw * MAXT + 8);
+                const float t12[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
 #pragma unroll
-                for (int l = 0; l < T; ++l) t = __ffma2_rn(bcast2(t8[l]), row[xo[pw] + l * xs], t);
+                for (int l = 0; l < T; ++l) t = __ffma2_rn(bcast2(t12[l]), row[xo[pw] + l * xs], t);
             }
             r[pw] = t;
         }
@@ -341,14 +359,16 @@ __device__ __forceinline__ void fwd_pairs(const float *__restrict__ tile_c, int 
 
 // The warp's dense y-weight table for one ROI: wyd[(y - 2 p0) * 8 + ph] = weight of tile row y in output row
 // ph (0 where row y is outside the bin's window; word 7 of a row is 0, it feeds the unused half of acc[3]).
+template <bool WIDE>
 __device__ __forceinline__ void build_wyd(float *wyd, const int *__restrict__ d, int lane) {
+    constexpr int MAXT = DescL<WIDE>::MT, WYP = DescL<WIDE>::WYP;
     const int p0 = d[D_Y0] >> 1, np = ((d[D_Y1] + 1) >> 1) - p0;
     float4 *w4 = reinterpret_cast<float4 *>(wyd);
     for (int i = lane; i < np * 4; i += 32) w4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
     const float *dwy = reinterpret_cast<const float *>(d + D_WY);
     for (int t = lane; t < PH * MAXT; t += 32) {
-        const int ph = t >> 3, i = t & 7;
+        const int ph = t / MAXT, i = t - ph * MAXT;
         if (i < d[D_YN + ph]) {
             const int y = d[D_YLO + ph] + i;
             wyd[(y - 2 * p0) * 8 + ph] = dwy[ph * WYP + 1 + i];
@@ -358,7 +378,6 @@ __device__ __forceinline__ void build_wyd(float *wyd, const int *__restrict__ d,
 }
 
 constexpr int FWD_MAX_WARPS = 11;
-constexpr int FWD_DESC_WORDS = DESC_WORDS;
 
 constexpr int FWD_GLOB_WARPS = 8;   // the global-memory variant trades warps for registers (64-bit addressing)
 template <bool GLB>
@@ -367,6 +386,7 @@ roi_align_fwd_tile_kernel(const float *__restrict__ feat, const int *__restrict_
                           const int *__restrict__ img_start, const int *__restrict__ descs,
                           const float *__restrict__ mask7, float *__restrict__ out, int B, int C, int H, int W,
                           int pitch, int wyd_floats) {
+    constexpr int FWD_DESC_WORDS = DescL<GLB>::WORDS;          // GLB kernels read WIDE descriptors
     extern __shared__ __align__(128) float smem[];
     const int nw = blockDim.x >> 5;
     float *tile = smem;
@@ -389,7 +409,7 @@ roi_align_fwd_tile_kernel(const float *__restrict__ feat, const int *__restrict_
 
     // descriptor prefetch: 672 B = 42 x 16 B per ROI, lanes 0..31 + lanes 0..9 again
     auto prefetch = [&](int roi, int slot) {
-        const int *src = descs + (size_t)roi * DESC_WORDS;
+        const int *src = descs + (size_t)roi * FWD_DESC_WORDS;
         int *dst = my_slots + slot * FWD_DESC_WORDS;
         cp_async16(dst + lane * 4, src + lane * 4);
         if (lane < FWD_DESC_WORDS / 4 - 32) cp_async16(dst + (32 + lane) * 4, src + (32 + lane) * 4);
@@ -425,14 +445,15 @@ roi_align_fwd_tile_kernel(const float *__restrict__ feat, const int *__restrict_
             const int *d = my_slots + slot * FWD_DESC_WORDS;
             const int roi = is + r;
             if ((d[D_FLAGY] | d[D_FLAGX]) == 0) {
-                build_wyd(my_wyd, d, lane);
+                build_wyd<GLB>(my_wyd, d, lane);
                 const float4 *wyd4 = reinterpret_cast<const float4 *>(my_wyd);
                 switch (d[D_TX]) {
                     case 2: fwd_pairs<2, GLB>(tile_c, W, C, d, stage_c, wyd4, lane); break;
                     case 3: fwd_pairs<3, GLB>(tile_c, W, C, d, stage_c, wyd4, lane); break;
                     case 4: fwd_pairs<4, GLB>(tile_c, W, C, d, stage_c, wyd4, lane); break;
                     case 6: fwd_pairs<6, GLB>(tile_c, W, C, d, stage_c, wyd4, lane); break;
-                    default: fwd_pairs<8, GLB>(tile_c, W, C, d, stage_c, wyd4, lane); break;
+                    case 8: fwd_pairs<8, GLB>(tile_c, W, C, d, stage_c, wyd4, lane); break;
+                    default: fwd_pairs<GLB ? 12 : 8, GLB>(tile_c, W, C, d, stage_c, wyd4, lane); break;
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -811,9 +832,13 @@ __device__ __forceinline__ void red_add2(float2 *gptr, float2 v) {
 template <int T, bool FUSED>
 __device__ __forceinline__ void bwd_pairs_glob(float2 *__restrict__ base2, int W, int xs, const int *d,
                                                const float *__restrict__ g, const float *__restrict__ m) {
-    float wx[PW][T];
+    // WIDE descriptors.  T <= 8: column weights in registers; T = 12 (bins of near-full-image ROIs on a 64-wide map):
+    // read from the descriptor (smem) inside the loop, 84 registers would not fit
+    constexpr int MAXT = DescL<true>::MT, WYP = DescL<true>::WYP;
+    constexpr bool WREG = T <= 8;
+    float wx[PW][WREG ? T : 1];
     int xo[PW];
-    const float *dwx = reinterpret_cast<const float *>(d + D_WX);
+    const float *dwx = reinterpret_cast<const float *>(d + DescL<true>::WX);
     const float *dwy = reinterpret_cast<const float *>(d + D_WY);
     const unsigned char *phr = reinterpret_cast<const unsigned char *>(d + D_PHR);
     {
@@ -821,14 +846,16 @@ __device__ __forceinline__ void bwd_pairs_glob(float2 *__restrict__ base2, int W
         xo[0] = a.x * xs; xo[1] = a.y * xs; xo[2] = a.z * xs; xo[3] = a.w * xs;
         xo[4] = b.x * xs; xo[5] = b.y * xs; xo[6] = b.z * xs;
     }
+    if (WREG) {
 #pragma unroll
-    for (int pw = 0; pw < PW; ++pw) {
-        float4 a = *reinterpret_cast<const float4 *>(dwx + pw * MAXT);
-        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (T > 4) b = *reinterpret_cast<const float4 *>(dwx + pw * MAXT + 4);
-        float t8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        for (int pw = 0; pw < PW; ++pw) {
+            float4 a = *reinterpret_cast<const float4 *>(dwx + pw * MAXT);
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (T > 4) b = *reinterpret_cast<const float4 *>(dwx + pw * MAXT + 4);
+            float t8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-        for (int l = 0; l < T; ++l) wx[pw][l] = t8[l];
+            for (int l = 0; l < (WREG ? T : 1); ++l) wx[pw][l] = t8[l];
+        }
     }
     const int pb = d[D_Y0] >> 1, p1 = (d[D_Y1] + 1) >> 1;
 #pragma unroll 1
@@ -854,8 +881,10 @@ __device__ __forceinline__ void bwd_pairs_glob(float2 *__restrict__ base2, int W
 #pragma unroll
         for (int pw = 0; pw < PW; ++pw)
 #pragma unroll
-            for (int l = 0; l < T; ++l)
-                red_add2(row + xo[pw] + l * xs, make_float2(wx[pw][l] * r[pw].x, wx[pw][l] * r[pw].y));
+            for (int l = 0; l < T; ++l) {
+                const float wv = WREG ? wx[pw][WREG ? l : 0] : dwx[pw * MAXT + l];
+                red_add2(row + xo[pw] + l * xs, make_float2(wv * r[pw].x, wv * r[pw].y));
+            }
     }
 }
 
@@ -867,6 +896,7 @@ roi_align_bwd_glob_kernel(const float *__restrict__ grad_out, const int *__restr
                           const int *__restrict__ img_start, const int *__restrict__ descs,
                           const float *__restrict__ mask7, float *__restrict__ gradP, int B, int C, int H, int W) {
     constexpr int GST = FUSED ? 2 * STAGE_FLOATS : STAGE_FLOATS;     // gradient floats per (roi, chunk)
+    constexpr int DESC_WORDS = DescL<true>::WORDS;                   // WIDE descriptors
     extern __shared__ __align__(128) float smem[];
     const int nw = blockDim.x >> 5;
     float *stages = smem;                                             // [nw][2][GST]
@@ -922,7 +952,8 @@ roi_align_bwd_glob_kernel(const float *__restrict__ grad_out, const int *__restr
                     case 3: bwd_pairs_glob<3, FUSED>(base2, W, C, d, g, m); break;
                     case 4: bwd_pairs_glob<4, FUSED>(base2, W, C, d, g, m); break;
                     case 6: bwd_pairs_glob<6, FUSED>(base2, W, C, d, g, m); break;
-                    default: bwd_pairs_glob<8, FUSED>(base2, W, C, d, g, m); break;
+                    case 8: bwd_pairs_glob<8, FUSED>(base2, W, C, d, g, m); break;
+                    default: bwd_pairs_glob<12, FUSED>(base2, W, C, d, g, m); break;
                 }
             }
             __syncwarp();
@@ -977,7 +1008,7 @@ __global__ void roi_align_generic_kernel(const float *__restrict__ in, const flo
                                          float *__restrict__ outp, const int *__restrict__ hdr,
                                          const int *__restrict__ descs, const float *__restrict__ mask7, int mode,
                                          int B, int C, int H, int W, int K, int oh, int ow, float scale, int sr,
-                                         int aligned) {
+                                         int aligned, int desc_words = DESC_WORDS) {
     // mode 0: one CTA column per ROI.  mode 1 (leftover pass): 8 ROIs per CTA -- warp w checks ROI 8 blockIdx.x + w
     // (almost every one was done by the tile kernel: 8x fewer CTAs scheduled for nothing), then the WHOLE CTA works
     // through the ROIs that are left, one after the other (a VGG-size ROI with bins wider than 8 taps is 25 000
@@ -991,7 +1022,7 @@ __global__ void roi_align_generic_kernel(const float *__restrict__ in, const flo
         if ((threadIdx.x & 31) == 0 && kw < K) {
             bool left = true;
             if (__ldg(hdr) == 0) {
-                const int *d = descs + (size_t)kw * DESC_WORDS;
+                const int *d = descs + (size_t)kw * desc_words;
                 left = (__ldg(d + D_FLAGY) | __ldg(d + D_FLAGX)) != 0;
             }
             if (left) atomicOr(&s_todo, 1 << (threadIdx.x >> 5));
@@ -1069,7 +1100,8 @@ static Plan make_plan(int C, int H, int W, int oh, int ow) {
     const size_t cap = (size_t)cim_max_smem_optin();
     // forward: as many warps (11 ... 4) as fit next to the tile: per warp one output stage, two
     // descriptor slots and the y-weight table
-    const size_t per_warp = (size_t)STAGE_FLOATS * 4 + 2 * FWD_DESC_WORDS * 4 + (size_t)p.wyd_floats * 4;
+    const size_t per_warp = (size_t)STAGE_FLOATS * 4 + 2 * DESC_WORDS * 4 + (size_t)p.wyd_floats * 4;
+    const size_t per_warp_wide = per_warp + 2 * (DESC_WORDS_MAX - DESC_WORDS) * 4;
     p.fwd_warps = FWD_MAX_WARPS;
     while (p.fwd_warps > 4 && (size_t)CH * p.pitch * 4 + p.fwd_warps * per_warp > cap) --p.fwd_warps;
     p.smem_fwd = (size_t)CH * p.pitch * 4 + p.fwd_warps * per_warp;
@@ -1078,8 +1110,8 @@ static Plan make_plan(int C, int H, int W, int oh, int ow) {
     p.tile = oh == PH && ow == PW && (C % CH) == 0 && W >= MAXT && p.smem_fwd <= cap &&
              p.smem_bwd <= cap && p.smem_bwd_fused <= cap && (((size_t)CH * p.pitch * 4) % 16 == 0);
     // large maps (VGG-16: 64 x 64): same sweeps over a channel-last copy in global memory
-    p.smem_fwd_glob = FWD_GLOB_WARPS * per_warp;
-    const size_t bw = (size_t)2 * STAGE_FLOATS * 4 + 2 * DESC_WORDS * 4, bwf = bw + (size_t)2 * STAGE_FLOATS * 4;
+    p.smem_fwd_glob = FWD_GLOB_WARPS * per_warp_wide;
+    const size_t bw = (size_t)2 * STAGE_FLOATS * 4 + 2 * DESC_WORDS_MAX * 4, bwf = bw + (size_t)2 * STAGE_FLOATS * 4;
     p.glob_bwd_warps = BWG_MAX_WARPS;
     p.glob_bwd_warps_fused = (int)std::min<size_t>(BWG_MAX_WARPS, cap / bwf);
     p.smem_bwd_glob = p.glob_bwd_warps * bw;
@@ -1105,17 +1137,21 @@ static RoiWs carve(void *ws, int B, int K) {
     w.hdr = (int *)p;
     w.img_start = (int *)(p + ws_img_off());
     w.desc = (int *)(p + ws_desc_off(B));
-    w.maskpad = (float *)(p + ws_desc_off(4096) + (size_t)(K > 0 ? K : 0) * DESC_WORDS * 4);
+    w.maskpad = (float *)(p + ws_desc_off(4096) + (size_t)(K > 0 ? K : 0) * DESC_WORDS_MAX * 4);
     return w;
 }
 
 static int run_prep(const float *rois, int B, int H, int W, int K, int oh, int ow, float scale, int sr,
-                    int aligned, const RoiWs &w, cudaStream_t st) {
+                    int aligned, const RoiWs &w, bool wide, cudaStream_t st) {
     cudaMemsetAsync(w.hdr, 0, WS_HDR_BYTES + sizeof(int) * (size_t)(B + 1), st);
     if (K > 0) {
         int threads = 128, blocks = (2 * K + threads - 1) / threads;
-        roi_prep_kernel<<<blocks, threads, 0, st>>>(rois, K, B, H, W, oh, ow, scale, sr, aligned, w.hdr,
-                                                    w.img_start, w.desc);
+        if (wide)
+            roi_prep_kernel<true><<<blocks, threads, 0, st>>>(rois, K, B, H, W, oh, ow, scale, sr, aligned, w.hdr,
+                                                              w.img_start, w.desc);
+        else
+            roi_prep_kernel<false><<<blocks, threads, 0, st>>>(rois, K, B, H, W, oh, ow, scale, sr, aligned, w.hdr,
+                                                               w.img_start, w.desc);
     }
     return cim_launch_status();
 }
@@ -1133,7 +1169,7 @@ CIM_API size_t cim_roi_align_workspace_bytes_ex(int B, int C, int H, int W, int 
 
 CIM_API size_t cim_roi_align_workspace_bytes(int K) {
     // header + image ranges (up to 4096 images) + descriptors
-    return WS_HDR_BYTES + 4097 * sizeof(int) + 64 + (size_t)(K > 0 ? K : 0) * (DESC_WORDS + MASK_PAD) * 4;
+    return WS_HDR_BYTES + 4097 * sizeof(int) + 64 + (size_t)(K > 0 ? K : 0) * (DESC_WORDS_MAX + MASK_PAD) * 4;
 }
 
 static int roi_fwd_impl(const float *feat, const float *rois, const float *mask7, float *out, int B, int C, int H,
@@ -1154,7 +1190,7 @@ static int roi_fwd_impl(const float *feat, const float *rois, const float *mask7
                                                                K, oh, ow, scale, sr, aligned);
         return cim_launch_status();
     }
-    if ((rc = run_prep(rois, B, H, W, K, oh, ow, scale, sr, aligned, w, st))) return rc;
+    if ((rc = run_prep(rois, B, H, W, K, oh, ow, scale, sr, aligned, w, glob, st))) return rc;
     const long long units = (long long)(C / CH) * K;
     const int grid = (int)min((long long)cim_num_sms(), units);
     if (glob) {
@@ -1174,8 +1210,9 @@ static int roi_fwd_impl(const float *feat, const float *rois, const float *mask7
     }
     if ((rc = cim_launch_status())) return rc;
     // leftover pass: one CTA per ROI, which exits at once unless the tile kernel skipped that ROI
-    roi_align_generic_kernel<false><<<dim3((unsigned)((K + 7) / 8), 1), 256, 0, st>>>(feat, rois, out, w.hdr, w.desc, mask7, 1, B,
-                                                                          C, H, W, K, oh, ow, scale, sr, aligned);
+    roi_align_generic_kernel<false><<<dim3((unsigned)((K + 7) / 8), 1), 256, 0, st>>>(
+        feat, rois, out, w.hdr, w.desc, mask7, 1, B, C, H, W, K, oh, ow, scale, sr, aligned,
+        glob ? DESC_WORDS_MAX : DESC_WORDS);
     return cim_launch_status();
 }
 
@@ -1202,7 +1239,7 @@ static int roi_bwd_impl(const float *grad_out, const float *rois, const float *m
                                                                   B, C, H, W, K, oh, ow, scale, sr, aligned);
         return cim_launch_status();
     }
-    if ((rc = run_prep(rois, B, H, W, K, oh, ow, scale, sr, aligned, w, st))) return rc;
+    if ((rc = run_prep(rois, B, H, W, K, oh, ow, scale, sr, aligned, w, glob, st))) return rc;
     const long long units = (long long)(C / CH) * K;
     const int grid = (int)min((long long)cim_num_sms(), units);
     if (glob) {
@@ -1224,9 +1261,8 @@ static int roi_bwd_impl(const float *grad_out, const float *rois, const float *m
         dim3 cg((unsigned)((W + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)(B * ((H + 1) >> 1)));
         pairs_to_nchw_kernel<<<cg, 256, 0, st>>>(reinterpret_cast<const float2 *>(gradP), grad_feat, C, H, W);
         if ((rc = cim_launch_status())) return rc;
-        roi_align_generic_kernel<true><<<dim3((unsigned)((K + 7) / 8), 1), 256, 0, st>>>(grad_out, rois, grad_feat, w.hdr, w.desc,
-                                                                             mask7, 1, B, C, H, W, K, oh, ow, scale, sr,
-                                                                             aligned);
+        roi_align_generic_kernel<true><<<dim3((unsigned)((K + 7) / 8), 1), 256, 0, st>>>(
+            grad_out, rois, grad_feat, w.hdr, w.desc, mask7, 1, B, C, H, W, K, oh, ow, scale, sr, aligned, DESC_WORDS_MAX);
         return cim_launch_status();
     }
     cudaMemsetAsync(grad_feat, 0, sizeof(float) * (size_t)B * C * H * W, st);

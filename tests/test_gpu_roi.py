@@ -294,6 +294,32 @@ def test_vgg16_sized_map_uses_the_global_path_and_matches_oracle(fused):
     close(gf, want_g)
 
 
+@pytest.mark.parametrize("fused", [False, True])
+def test_vgg16_sized_map_wide_bins_stay_on_the_sweep_kernels(fused):
+    """ROIs spanning most of a 64 x 64 map: 9 .. 12 collapsed taps per bin and axis.  The global-path kernels
+    read WIDE descriptors (12 taps, T = 12 instance), so these no longer drop to the sample-by-sample kernel; a
+    few ROIs larger than the map (> 12 taps) still do.  Same results either way."""
+    C, H, W, scale = 64, 64, 64, 1.0 / 8
+    feat = torch.randn(2, C, H, W, generator=torch.Generator().manual_seed(31))
+    g = torch.Generator().manual_seed(32)
+    K = 48
+    b = torch.randint(0, 2, (K,), generator=g).float().sort().values
+    w = 8 * (56 + 27 * torch.rand(K, generator=g))          # 56 .. 83 feature columns -> bins of 8 .. 11.9
+    h = 8 * (40 + 43 * torch.rand(K, generator=g))
+    x1 = (512 - w).clamp(min=-60) * torch.rand(K, generator=g)
+    y1 = (512 - h).clamp(min=-60) * torch.rand(K, generator=g)
+    w[5], h[7] = 8 * 120.0, 8 * 100.0                        # > 12 taps: generic leftover pass
+    rois = torch.stack([b, x1, y1, x1 + w, y1 + h], 1)
+    if fused:
+        masks = (torch.rand(K, 7, 7, generator=torch.Generator().manual_seed(33)) > 0.5).float()
+        out, gf, gg = run_maskfuse(feat, rois, masks, scale, 0, True)
+        want, want_g = maskfuse_oracle(feat, rois, masks, scale, 0, True, gg)
+    else:
+        out, gf, want, want_g = run_both(feat, rois, scale, 0, True)
+    close(out, want)
+    close(gf, want_g)
+
+
 def test_large_map_small_workspace_falls_back_to_generic():
     """The plain cim_roi_align_workspace_bytes(K) workspace is still accepted: the generic kernels run."""
     import ctypes as C_
