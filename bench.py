@@ -32,6 +32,7 @@ METRIC = "CIM-head images/s (ROIAlign fwd+bwd + mask IoU + scoring fwd+bwd + min
 WORKLOADS = {
     # name: backbone, images per GPU, proposals, classes, present classes, mask side
     "cfg2_r50_voc_8x2000": dict(backbone="resnet50", n_img=8, R=2000, C=20, present=2, mask=512),
+    "cfg3_vgg16_voc_8x2000": dict(backbone="vgg16", n_img=8, R=2000, C=20, present=2, mask=512),
     "cfg4_r50_coco_8x2000_q": dict(backbone="resnet50", n_img=8, R=2000, C=80, present=4, mask=128),
     "cfg1_r50_voc_1x300": dict(backbone="resnet50", n_img=1, R=300, C=20, present=2, mask=512),
     "tiny": dict(backbone="resnet50", n_img=2, R=200, C=20, present=2, mask=128),

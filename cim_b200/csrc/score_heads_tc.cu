@@ -73,8 +73,10 @@ score_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     float *s_bias = reinterpret_cast<float *>(tmem_slot + 2);   // [heads_per_tile * C1]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int m0 = blockIdx.x * BM;
-    const int h0 = blockIdx.y * heads_per_tile;                 // first head of this CTA
+    // head groups vary FASTEST over the grid: the CTAs that read the same 2 MB x row-block (one per head group, 4 at
+    // COCO's 81 classes) run side by side and share it through L2 instead of streaming it from HBM once each
+    const int m0 = blockIdx.y * BM;
+    const int h0 = blockIdx.x * heads_per_tile;                 // first head of this CTA
     const int nheads = 2 + 2 * n_ref;
     const int nh = min(heads_per_tile, nheads - h0);
     const int n0 = h0 * C1;                                     // first row of W / first logit column
@@ -280,7 +282,8 @@ int cim_score_tc_launch(const float *x, const float *weight, const float *bias, 
     if (!make_map(&tx, x, M, D, BM) || !make_map(&twh, w_hi, N, D, NT) || !make_map(&twl, w_lo, N, D, NT))
         return CIM_ERR_ARG;
     const size_t smem = score_tc_smem_bytes(heads_per_tile * C1);
-    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)ntiles);
+    if ((M + BM - 1) / BM > 65535) return CIM_ERR_SHAPE;
+    dim3 grid((unsigned)ntiles, (unsigned)((M + BM - 1) / BM));
     cudaFuncSetAttribute(score_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     score_gemm_tc_kernel<<<grid, THREADS_TC, smem, st>>>(tx, twh, twl, bias, scores, (int)M, D, C1, n_ref,
                                                          heads_per_tile);

@@ -110,7 +110,7 @@ class CIMHeadStep:
         self.h_weight = pin((k, n_img, self.cap), torch.float32)
         self.h_keep = pin((k, n_img, self.cap), torch.uint8)
         self.ev = torch.cuda.Event()
-        self.side = torch.cuda.Stream(device=self.dev, priority=-1)     # scoring GEMM next to the overlap helpers
+        self.side = torch.cuda.Stream(device=self.dev, priority=-2)     # scoring GEMM next to the overlap helpers: above the step
         self.trace = [] if os.environ.get("CIM_STEP_TRACE") else None
         # layer l reads (cls, det) = (predict_cls, predict_det) for l = 0, else (ref_cls[l-1], ref_iou[l-1])
         s = self.scores.view(nh, n_img, R, C1)
