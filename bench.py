@@ -312,6 +312,15 @@ def main():
     ap.add_argument("--no-head-grads", action="store_true",
                     help="leave the loss block, the scoring backward and the allreduce of the head gradients out of the step")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON result: everything else a library may write to fd 1 (NCCL prints its
+    # version banner there on the first collective) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     cfg = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -324,7 +333,7 @@ def main():
             return
         steps, warmup = max(1, min(args.steps, 3)), 1          # bounded; one untimed pass warms BLAS / pages
         r = cpu_reference(cfg, steps, warmup, head_grads=not args.no_head_grads)
-        print(json.dumps({
+        emit(({
             "impl": "reference", "metric": METRIC, "value": r["images_per_s"], "unit": "images/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * r["sec_per_image"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -480,7 +489,7 @@ def main():
         r = cpu_reference(cfg, 1, 0, head_grads=not args.no_head_grads)
         result["cpu_baseline"] = {"value": r["images_per_s"], "unit": "images/s", "cores": r["cores"], "kind": "port",
                                   "sample": r["sample"], "parts_s_per_image": r["parts"]}
-    print(json.dumps(result))
+    emit(result)
 
 
 if __name__ == "__main__":
