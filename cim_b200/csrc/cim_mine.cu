@@ -110,12 +110,24 @@ cim_seed_kernel(LayerPtrs ptrs, const float *__restrict__ labels, const __half *
     const __half *iou = iou_all + (size_t)img * R * R;
     const __half thr = __float2half_rn(p.cls_thr[l]);
     const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
-    for (int e = warp; e < k * kw; e += nwarp) {
-        const int a = e / kw, w = e - a * kw, b = w * 32 + lane;
-        bool s = false;
-        if (b < k && b > a) s = !__hlt(iou[(size_t)seeds[a] * R + seeds[b]], thr);
-        const uint32_t word = __ballot_sync(0xffffffffu, s);
-        if (lane == 0) supp[e] = word;
+    // 4 (seed a, word w) entries per warp and round: the gathers are dependent loads of L2 latency, so they are all
+    // issued before the first ballot (one entry at a time this loop was half of the kernel)
+    constexpr int SU = 4;
+    for (int e0 = warp * SU; e0 < k * kw; e0 += nwarp * SU) {
+        __half v[SU];
+        bool ok[SU];
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            const int e = e0 + u, a = e / kw, w = e - a * kw, b = w * 32 + lane;
+            ok[u] = e < k * kw && b < k && b > a;
+            v[u] = ok[u] ? iou[(size_t)seeds[a] * R + seeds[b]] : __float2half_rn(0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            const bool s = ok[u] && !__hlt(v[u], thr);
+            const uint32_t word = __ballot_sync(0xffffffffu, s);
+            if (lane == 0 && e0 + u < k * kw) supp[e0 + u] = word;
+        }
     }
     __syncthreads();
     if (warp == 0) {
