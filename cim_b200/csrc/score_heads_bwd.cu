@@ -67,39 +67,62 @@ score_det_dot_kernel(const float *__restrict__ g, const float *__restrict__ y, f
     if (tid == 0) dot[img * C1 + c] = red[0];
 }
 
-// one thread per (head, row): dz, written hi/lo-split as dz [M][NP] (row = proposal) and dz^T [N][MP]
+// dz for 32 proposals x one head per warp (lane = proposal), written hi/lo-split as dz [M][NP] (row = proposal) and
+// dz^T [N][MP].  The warp parks its 32 x C1 values in a private smem tile so that both layouts leave in contiguous
+// runs: dz rows in C1-float runs, dz^T rows as 128 B (32 proposals) per class -- one thread per (head, row) writing
+// its row with a 768-byte stride took 57 us at cfg2 for 43 MB.
 __global__ void __launch_bounds__(256)
 score_act_bwd_kernel(const float *__restrict__ y_all, const float *__restrict__ g_all,
                      const float *__restrict__ det_dot, float *__restrict__ dz_hi, float *__restrict__ dz_lo,
                      float *__restrict__ dzT_hi, float *__restrict__ dzT_lo, int M, int R, int C1, int K, int NP,
                      long long MP) {
-    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    extern __shared__ float act_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int pitch = C1 | 1;                                  // odd: lane = row reads / writes conflict-free
+    float *tile = act_smem + (size_t)warp * 32 * pitch;
     const int nheads = 2 + 2 * K;
-    if (idx >= (long long)nheads * M) return;
-    const int h = (int)(idx / M), m = (int)(idx - (long long)h * M);
-    const float *y = y_all + (size_t)idx * C1, *g = g_all + (size_t)idx * C1;
-    float dot = 0.f;
-    const bool row_softmax = (h == 0) || (h >= 2 && h < 2 + K);
-    if (row_softmax)
-        for (int c = 0; c < C1; ++c) dot = fmaf(g[c], y[c], dot);
-    const float *ddot = det_dot + (size_t)(m / R) * C1;
-    for (int c = 0; c < C1; ++c) {
-        const float yy = y[c], gg = g[c];
-        float v;
-        if (row_softmax) v = yy * (gg - dot);
-        else if (h == 1) v = yy * (gg - ddot[c]);
-        else v = gg * yy * (1.f - yy);
-        float hi, lo;
-        split_tf32(v, hi, lo);
-        const int n = h * C1 + c;
+    const int m0 = blockIdx.x * 32;
+    for (int h = warp; h < nheads; h += nw) {
+        const int m = m0 + lane;
+        if (m < M) {
+            const size_t row = (size_t)h * M + m;
+            const float *y = y_all + row * C1, *g = g_all + row * C1;
+            float dot = 0.f;
+            const bool row_softmax = (h == 0) || (h >= 2 && h < 2 + K);
+            if (row_softmax)
+                for (int c = 0; c < C1; ++c) dot = fmaf(g[c], y[c], dot);
+            const float *ddot = det_dot + (size_t)(m / R) * C1;
+            for (int c = 0; c < C1; ++c) {
+                const float yy = y[c], gg = g[c];
+                float v;
+                if (row_softmax) v = yy * (gg - dot);
+                else if (h == 1) v = yy * (gg - ddot[c]);
+                else v = gg * yy * (1.f - yy);
+                tile[lane * pitch + c] = v;
+            }
+        }
+        __syncwarp();
+        const int rows = min(32, M - m0);
         if (dz_hi) {
-            dz_hi[(size_t)m * NP + n] = hi;
-            dz_lo[(size_t)m * NP + n] = lo;
+            for (int i = lane; i < rows * C1; i += 32) {
+                const int r = i / C1, c = i - r * C1;
+                float hi, lo;
+                split_tf32(tile[r * pitch + c], hi, lo);
+                const size_t o = (size_t)(m0 + r) * NP + h * C1 + c;
+                dz_hi[o] = hi;
+                dz_lo[o] = lo;
+            }
         }
-        if (dzT_hi) {
-            dzT_hi[(size_t)n * MP + m] = hi;
-            dzT_lo[(size_t)n * MP + m] = lo;
+        if (dzT_hi && lane < rows) {
+            for (int c = 0; c < C1; ++c) {
+                float hi, lo;
+                split_tf32(tile[lane * pitch + c], hi, lo);
+                const size_t o = (size_t)(h * C1 + c) * MP + m0 + lane;
+                dzT_hi[o] = hi;
+                dzT_lo[o] = lo;
+            }
         }
+        __syncwarp();
     }
 }
 
@@ -528,7 +551,13 @@ CIM_API int cim_score_heads_bwd(const float *x, const float *weight, const float
     int rc = cim_launch_status();
     if (rc) return rc;
     const long long rows = (long long)nheads * M;
-    score_act_bwd_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(scores, grad_scores, dot, grad_x ? dzh : nullptr,
+    int act_warps = 8;                                           // one head per warp, 32 proposals per CTA
+    while (act_warps > 1 && (size_t)act_warps * 32 * (C1 | 1) * sizeof(float) > 96 * 1024) act_warps >>= 1;
+    const size_t act_smem = (size_t)act_warps * 32 * (C1 | 1) * sizeof(float);
+    if (act_smem > (size_t)cim_max_smem_optin()) return CIM_ERR_SHAPE;         // C1 > ~1700
+    if (act_smem > 48 * 1024)
+        cudaFuncSetAttribute(score_act_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)act_smem);
+    score_act_bwd_kernel<<<(unsigned)((M + 31) / 32), act_warps * 32, act_smem, st>>>(scores, grad_scores, dot, grad_x ? dzh : nullptr,
                                                                         dzl, want_t ? dth : nullptr, dtl, M, R, C1, K,
                                                                         L.NP, L.MP);
     if ((rc = cim_launch_status())) return rc;
