@@ -190,7 +190,8 @@ int cim_score_heads(const float *x, const float *weight, const float *bias, floa
  * Activation backward: y (g - sum_classes g y) for classifier / refine_cls, y (g - sum over the proposals of
  * the image of g y) for the detector, g y (1 - y) for refine_iou.  The two GEMMs run as 3xTF32 on the tensor
  * cores (fp32-accurate) when n_img*R >= 128 and D % 4 == 0, as plain fp32 otherwise.  Deterministic (the
- * split-M partial sums of grad_weight are added in a fixed order).
+ * split-M partial sums of grad_weight are added in a fixed order).  C1 <= 1700 (one proposal row block of dz is
+ * staged in shared memory), CIM_ERR_SHAPE above.
  * workspace: cim_score_heads_bwd_workspace_bytes() bytes, required. */
 size_t cim_score_heads_bwd_workspace_bytes(int n_img, int R, int D, int C1, int K);
 int cim_score_heads_bwd(const float *x, const float *weight, const float *scores, const float *grad_scores,
