@@ -1174,7 +1174,7 @@ CIM_API size_t cim_roi_align_workspace_bytes(int K) {
 
 static int roi_fwd_impl(const float *feat, const float *rois, const float *mask7, float *out, int B, int C, int H,
                         int W, int K, int oh, int ow, float scale, int sr, int aligned, void *ws, size_t ws_bytes,
-                        cim_stream_t stream) {
+                        cim_stream_t stream, bool prepared = false) {
     if (B > 4096) return CIM_ERR_SHAPE;
     if (K == 0 && feat && B > 0 && C > 0 && H > 0 && W > 0 && oh > 0 && ow > 0) return CIM_OK;   // empty output
     int rc = check_args(feat, rois, out, B, C, H, W, K, oh, ow, ws, ws_bytes);
@@ -1190,7 +1190,7 @@ static int roi_fwd_impl(const float *feat, const float *rois, const float *mask7
                                                                K, oh, ow, scale, sr, aligned);
         return cim_launch_status();
     }
-    if ((rc = run_prep(rois, B, H, W, K, oh, ow, scale, sr, aligned, w, glob, st))) return rc;
+    if (!prepared && (rc = run_prep(rois, B, H, W, K, oh, ow, scale, sr, aligned, w, glob, st))) return rc;
     const long long units = (long long)(C / CH) * K;
     const int grid = (int)min((long long)cim_num_sms(), units);
     if (glob) {
@@ -1218,7 +1218,7 @@ static int roi_fwd_impl(const float *feat, const float *rois, const float *mask7
 
 static int roi_bwd_impl(const float *grad_out, const float *rois, const float *mask7, float *grad_feat, int B, int C,
                         int H, int W, int K, int oh, int ow, float scale, int sr, int aligned, void *ws,
-                        size_t ws_bytes, cim_stream_t stream) {
+                        size_t ws_bytes, cim_stream_t stream, bool prepared = false) {
     if (B > 4096) return CIM_ERR_SHAPE;
     if (K == 0 && grad_feat && B > 0 && C > 0 && H > 0 && W > 0) {                // no ROI: zero gradient
         cudaMemsetAsync(grad_feat, 0, sizeof(float) * (size_t)B * C * H * W, (cudaStream_t)stream);
@@ -1239,7 +1239,7 @@ static int roi_bwd_impl(const float *grad_out, const float *rois, const float *m
                                                                   B, C, H, W, K, oh, ow, scale, sr, aligned);
         return cim_launch_status();
     }
-    if ((rc = run_prep(rois, B, H, W, K, oh, ow, scale, sr, aligned, w, glob, st))) return rc;
+    if (!prepared && (rc = run_prep(rois, B, H, W, K, oh, ow, scale, sr, aligned, w, glob, st))) return rc;
     const long long units = (long long)(C / CH) * K;
     const int grid = (int)min((long long)cim_num_sms(), units);
     if (glob) {
@@ -1285,6 +1285,36 @@ static int roi_bwd_impl(const float *grad_out, const float *rois, const float *m
                                                                          mask7, 1, B, C, H, W, K, oh, ow, scale, sr,
                                                                          aligned);
     return cim_launch_status();
+}
+
+// Descriptors once for several calls on the same rois (forward + backward of one step share them): the same plan /
+// layout decision as the _impl functions, which then skip their own prep launch.
+CIM_API int cim_roi_align_prepare(const float *rois, int B, int C, int H, int W, int K, int oh, int ow, float scale,
+                                  int sr, int aligned, void *ws, size_t ws_bytes, cim_stream_t stream) {
+    if (B > 4096) return CIM_ERR_SHAPE;
+    if (K == 0) return CIM_OK;
+    if (!rois || B <= 0 || C <= 0 || H <= 0 || W <= 0 || K < 0 || oh <= 0 || ow <= 0) return CIM_ERR_ARG;
+    if ((long long)H * W > (1 << 24) || (long long)C * oh * ow > (1LL << 30)) return CIM_ERR_SHAPE;
+    if (!ws || ws_bytes < cim_roi_align_workspace_bytes(K)) return CIM_ERR_WORKSPACE;
+    if (!cim_aligned(ws, 16)) return CIM_ERR_ALIGN;
+    const Plan p = make_plan(C, H, W, oh, ow);
+    const bool glob = !p.tile && p.glob && ws_bytes >= ws_glob_off(K) + glob_copy_bytes(B, C, H, W);
+    if (!p.tile && !glob) return CIM_OK;                   // generic kernels: no descriptors
+    return run_prep(rois, B, H, W, K, oh, ow, scale, sr, aligned, carve(ws, B, K), glob, (cudaStream_t)stream);
+}
+
+CIM_API int cim_roi_align_fwd_prepared(const float *feat, const float *rois, const float *masks7, float *out, int B,
+                                       int C, int H, int W, int K, int oh, int ow, float scale, int sr, int aligned,
+                                       void *ws, size_t ws_bytes, cim_stream_t stream) {
+    return roi_fwd_impl(feat, rois, masks7, out, B, C, H, W, K, oh, ow, scale, sr, aligned, ws, ws_bytes, stream, true);
+}
+
+CIM_API int cim_roi_align_bwd_prepared(const float *grad_out, const float *rois, const float *masks7,
+                                       float *grad_feat, int B, int C, int H, int W, int K, int oh, int ow,
+                                       float scale, int sr, int aligned, void *ws, size_t ws_bytes,
+                                       cim_stream_t stream) {
+    return roi_bwd_impl(grad_out, rois, masks7, grad_feat, B, C, H, W, K, oh, ow, scale, sr, aligned, ws, ws_bytes,
+                        stream, true);
 }
 
 CIM_API int cim_roi_align_fwd(const float *feat, const float *rois, float *out, int B, int C, int H, int W,

@@ -56,6 +56,7 @@ class RoIAlignFunction(Function):
                                      _lib.ptr(ws), ws.numel(), _lib.stream_ptr(feat.device))
         _lib.check(rc, "cim_roi_align_fwd")
         ctx.save_for_backward(rois)
+        ctx.ws = ws                 # the backward reuses the forward's ROI descriptors (cim_roi_align_bwd_prepared)
         ctx.cfg = (tuple(feat.shape), oh, ow, float(spatial_scale), int(sampling_ratio), int(bool(aligned)))
         return out
 
@@ -67,13 +68,12 @@ class RoIAlignFunction(Function):
         grad_out = grad_out.contiguous()
         K = rois.size(0)
         L = _lib.lib()
+        ws = ctx.ws
         with torch.cuda.device(grad_out.device):
-            ws = torch.empty(L.cim_roi_align_workspace_bytes_ex(B, Cc, H, W, K, oh, ow), dtype=torch.uint8,
-                             device=grad_out.device)
             grad_feat = torch.empty((B, Cc, H, W), dtype=torch.float32, device=grad_out.device)
-            rc = L.cim_roi_align_bwd(_lib.ptr(grad_out), _lib.ptr(rois), _lib.ptr(grad_feat), B, Cc, H, W, K, oh,
-                                     ow, scale, sr, aligned, _lib.ptr(ws), ws.numel(),
-                                     _lib.stream_ptr(grad_out.device))
+            rc = L.cim_roi_align_bwd_prepared(_lib.ptr(grad_out), _lib.ptr(rois), None, _lib.ptr(grad_feat), B, Cc, H,
+                                              W, K, oh, ow, scale, sr, aligned, _lib.ptr(ws), ws.numel(),
+                                              _lib.stream_ptr(grad_out.device))
         _lib.check(rc, "cim_roi_align_bwd")
         return grad_feat, None, None, None, None, None, None
 
@@ -137,6 +137,7 @@ class RoIAlignMaskFuseFunction(Function):
                                               _lib.stream_ptr(feat.device))
         _lib.check(rc, "cim_roi_align_maskfuse_fwd")
         ctx.save_for_backward(rois, masks)
+        ctx.ws = ws
         ctx.cfg = (tuple(feat.shape), oh, ow, float(spatial_scale), int(sampling_ratio), int(bool(aligned)))
         return out
 
@@ -148,11 +149,10 @@ class RoIAlignMaskFuseFunction(Function):
         grad_out = grad_out.contiguous()
         K = rois.size(0)
         L = _lib.lib()
+        ws = ctx.ws
         with torch.cuda.device(grad_out.device):
-            ws = torch.empty(L.cim_roi_align_workspace_bytes_ex(B, Cc, H, W, K, oh, ow), dtype=torch.uint8,
-                             device=grad_out.device)
             grad_feat = torch.empty((B, Cc, H, W), dtype=torch.float32, device=grad_out.device)
-            rc = L.cim_roi_align_maskfuse_bwd(_lib.ptr(grad_out), _lib.ptr(rois), _lib.ptr(masks), _lib.ptr(grad_feat),
+            rc = L.cim_roi_align_bwd_prepared(_lib.ptr(grad_out), _lib.ptr(rois), _lib.ptr(masks), _lib.ptr(grad_feat),
                                               B, Cc, H, W, K, oh, ow, scale, sr, aligned, _lib.ptr(ws), ws.numel(),
                                               _lib.stream_ptr(grad_out.device))
         _lib.check(rc, "cim_roi_align_maskfuse_bwd")

@@ -30,9 +30,9 @@ from . import _lib
 from . import dist as cdist
 from .heads import _anti_noise_keep
 
-#: kernels (not memsets / copies) libcimhead launches in one run(): roi_align fwd 3 + bwd 3,
+#: kernels (not memsets / copies) libcimhead launches in one run(): roi_align prep 1 + fwd 2 + bwd 2,
 #: mask area + sort + overlap + 2 un-permutes = 5, scoring 3, mining 3, assignment 1
-KERNELS_PER_STEP = 18
+KERNELS_PER_STEP = 17
 #: + with head_grads: loss block (fwd + bwd), detector dot, activation backward, bias, W^T split, grad_x GEMM,
 #: grad_W GEMM, reduce
 KERNELS_HEAD_GRADS = 8
@@ -148,6 +148,10 @@ class CIMHeadStep:
         ck(L.cim_score_heads(P(seg_x), P(weight), P(bias), P(self.scores), n_img, R, self.D, self.C + 1, k,
                              P(self.score_ws), self.score_ws.numel(), C.c_void_p(self.side.cuda_stream)),
            "cim_score_heads")
+        # RoI descriptors once per step (forward and backward see the same rois), also off the critical path
+        ck(L.cim_roi_align_prepare(P(rois), n_img, self.Cf, self.H, self.W, n_img * R, 7, 7, self.scale, self.sr,
+                                   self.aligned, P(self.roi_ws), self.roi_ws.numel(),
+                                   C.c_void_p(self.side.cuda_stream)), "cim_roi_align_prepare")
         pcl_early = self.head_grads and grad_scores is None and mat is not None
         if pcl_early:
             # PCL_loss (model_builder.py:203) needs predict_cls and the cluster matrix only: 8 CTAs of pure latency
@@ -166,9 +170,9 @@ class CIMHeadStep:
             self.h_class.copy_(self.gt_class[:, :, :self.cap], non_blocking=True)
             self.h_weight.copy_(self.gt_weight[:, :, :self.cap], non_blocking=True)
             self.ev.record(torch.cuda.current_stream(dev))
-        ck(L.cim_roi_align_fwd(P(feat), P(rois), P(self.roi_out), n_img, self.Cf, self.H, self.W, n_img * R, 7, 7,
-                               self.scale, self.sr, self.aligned, P(self.roi_ws), self.roi_ws.numel(), st),
-           "cim_roi_align_fwd")
+        ck(L.cim_roi_align_fwd_prepared(P(feat), P(rois), None, P(self.roi_out), n_img, self.Cf, self.H, self.W,
+                                        n_img * R, 7, 7, self.scale, self.sr, self.aligned, P(self.roi_ws),
+                                        self.roi_ws.numel(), st), "cim_roi_align_fwd")
         if mid_hook is not None:
             mid_hook()                                          # host work that should hide behind the RoIAlign forward
         keep = None
@@ -211,9 +215,9 @@ class CIMHeadStep:
                                      P(self.grad_weight), P(self.grad_bias), n_img, R, self.D, self.C + 1, k,
                                      P(self.score_bwd_ws), self.score_bwd_ws.numel(), st), "cim_score_heads_bwd")
             reduce_work = cdist.allreduce_mean_async_(self.head_bucket)         # overlaps the RoIAlign backward
-        ck(L.cim_roi_align_bwd(P(grad_out), P(rois), P(self.grad_feat), n_img, self.Cf, self.H, self.W, n_img * R,
-                               7, 7, self.scale, self.sr, self.aligned, P(self.roi_ws), self.roi_ws.numel(), st),
-           "cim_roi_align_bwd")
+        ck(L.cim_roi_align_bwd_prepared(P(grad_out), P(rois), None, P(self.grad_feat), n_img, self.Cf, self.H, self.W,
+                                        n_img * R, 7, 7, self.scale, self.sr, self.aligned, P(self.roi_ws),
+                                        self.roi_ws.numel(), st), "cim_roi_align_bwd")
         if reduce_work is not None:
             reduce_work()                                       # current stream waits for the allreduce
         if tr is not None:

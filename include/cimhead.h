@@ -85,6 +85,24 @@ int cim_roi_align_maskfuse_bwd(const float *grad_out, const float *rois, const f
                                float spatial_scale, int sampling_ratio, int aligned,
                                void *workspace, size_t workspace_bytes, cim_stream_t stream);
 
+/* The ROI descriptors (collapsed bilinear taps per bin) depend on the rois and the geometry only.  Every call above
+ * builds them itself (one small kernel); when several calls see the SAME rois -- the forward and the backward of one
+ * training step -- cim_roi_align_prepare() builds them once into the workspace and the _prepared entry points skip
+ * their own pass.  The caller guarantees that rois, B, C, H, W, K, oh, ow, spatial_scale, sampling_ratio, aligned,
+ * workspace and workspace_bytes are those of the prepare call and that the workspace was not used with other rois
+ * in between.  masks7 == NULL: plain RoIAlign, else the MaskFuse variants. */
+int cim_roi_align_prepare(const float *rois, int B, int C, int H, int W, int K, int oh, int ow,
+                          float spatial_scale, int sampling_ratio, int aligned,
+                          void *workspace, size_t workspace_bytes, cim_stream_t stream);
+int cim_roi_align_fwd_prepared(const float *feat, const float *rois, const float *masks7, float *out,
+                               int B, int C, int H, int W, int K, int oh, int ow,
+                               float spatial_scale, int sampling_ratio, int aligned,
+                               void *workspace, size_t workspace_bytes, cim_stream_t stream);
+int cim_roi_align_bwd_prepared(const float *grad_out, const float *rois, const float *masks7, float *grad_feat,
+                               int B, int C, int H, int W, int K, int oh, int ow,
+                               float spatial_scale, int sampling_ratio, int aligned,
+                               void *workspace, size_t workspace_bytes, cim_stream_t stream);
+
 /* RoIPool: lib/model/roi_pooling/src/roi_pooling_kernel.cu:24-93 (fwd), :128-203 (bwd).
  * argmax [K,C,oh,ow] int32 = index inside the H*W plane, -1 for an empty bin. */
 int cim_roi_pool_fwd(const float *feat, const float *rois, float *out, int32_t *argmax,

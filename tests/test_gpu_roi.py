@@ -336,3 +336,49 @@ def test_large_map_small_workspace_falls_back_to_generic():
     _lib.check(L.cim_roi_align_fwd(_lib.ptr(f), _lib.ptr(r), _lib.ptr(out), B, C, H, W, K, 7, 7, scale, 0, 1,
                                    _lib.ptr(ws), ws.numel(), _lib.stream_ptr(torch.device(DEV))), "fwd")
     close(out.cpu().numpy(), roi_oracle.roi_align_fwd(feat.numpy(), rois.numpy(), 7, 7, scale, 0, True))
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 32, 32, 1.0 / 16), (1, 32, 64, 64, 1.0 / 8)])
+@pytest.mark.parametrize("fused", [False, True])
+def test_prepared_entry_points_equal_the_self_preparing_ones(shape, fused):
+    """cim_roi_align_prepare once + the _prepared forward / backward (what CIMHeadStep and the autograd backward use)
+    give bit-identical results to the calls that build their descriptors themselves -- tile path and global path."""
+    from cim_b200 import _lib
+    L = _lib.lib()
+    B, C, H, W, scale = shape
+    K = 60 * B
+    dev = torch.device(DEV)
+    feat = torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(41)).to(dev)
+    rois = torch.cat([synth.rois_from_params(synth.proposal_params(60, 512, 41 + b), b) for b in range(B)]).to(dev)
+    masks = (torch.rand(K, 7, 7, generator=torch.Generator().manual_seed(42)) > 0.5).float().to(dev)
+    Co = 2 * C if fused else C
+    gout = torch.randn(K, Co, 7, 7, generator=torch.Generator().manual_seed(43)).to(dev)
+    mk = masks if fused else None
+    P, st = _lib.ptr, _lib.stream_ptr(dev)
+    nbytes = L.cim_roi_align_workspace_bytes_ex(B, C, H, W, K, 7, 7)
+    geo = (B, C, H, W, K, 7, 7, scale, 0, 1)
+
+    def run(prepared):
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        out = torch.empty(K, Co, 7, 7, device=dev)
+        gf = torch.empty(B, C, H, W, device=dev)
+        if prepared:
+            _lib.check(L.cim_roi_align_prepare(P(rois), *geo, P(ws), nbytes, st), "prepare")
+            _lib.check(L.cim_roi_align_fwd_prepared(P(feat), P(rois), P(mk), P(out), *geo, P(ws), nbytes, st), "fwd")
+            _lib.check(L.cim_roi_align_bwd_prepared(P(gout), P(rois), P(mk), P(gf), *geo, P(ws), nbytes, st), "bwd")
+        elif fused:
+            _lib.check(L.cim_roi_align_maskfuse_fwd(P(feat), P(rois), P(mk), P(out), *geo, P(ws), nbytes, st), "fwd")
+            _lib.check(L.cim_roi_align_maskfuse_bwd(P(gout), P(rois), P(mk), P(gf), *geo, P(ws), nbytes, st), "bwd")
+        else:
+            _lib.check(L.cim_roi_align_fwd(P(feat), P(rois), P(out), *geo, P(ws), nbytes, st), "fwd")
+            _lib.check(L.cim_roi_align_bwd(P(gout), P(rois), P(gf), *geo, P(ws), nbytes, st), "bwd")
+        torch.cuda.synchronize()
+        return out, gf
+
+    o1, g1 = run(False)
+    o2, g2 = run(True)
+    assert torch.equal(o1, o2)
+    if H * W <= 1024:
+        assert torch.equal(g1, g2)                      # tile path: bit-reproducible
+    else:
+        close(g2.cpu().numpy(), g1.cpu().numpy())       # global path: red.global.add order is not fixed
