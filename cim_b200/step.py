@@ -84,8 +84,14 @@ class CIMHeadStep:
                 self.pcl_grad = e((n_img * R, C1), torch.float32)
             p = _lib.MineParams()
             p.n_img, p.R, p.C, p.C1, p.n_layers = n_img, R, n_classes, C1, k
-            p.det_cols, p.gt_cap, p.mode = C1, R, 0
+            p.det_cols, p.mode = C1, 0
             p.keep_count = int(np.ceil(p_seed * R))                 # heads.py:332
+            # host side of the sampling hop: at most max_present * keep_count pseudo GTs per (layer, image).  With the
+            # hop the device lists get exactly that capacity (+ 1 slot, so that an overflow is seen and not silently
+            # clamped): the lists then cross PCIe as plain contiguous copies, no strided slice to stage first
+            self.cap = min(R, max_present * p.keep_count)
+            gcap = min(R, self.cap + 1) if anti_noise_sampling else R
+            p.gt_cap = gcap
             p.big_thr = float(np.float32(0.9 * R))                  # heads.py:338
             p.con_thr = con_thr
             for l in range(k):                                      # model_builder.py:90-93
@@ -93,22 +99,20 @@ class CIMHeadStep:
             self.p = p
             self.mine_ws = e((max(256, self.L.cim_mine_workspace_bytes(C.byref(p))),), torch.uint8)
             self.gt_count = e((k, n_img), torch.int32)
-            self.gt_rows = e((k, n_img, R), torch.int32)
-            self.gt_class = e((k, n_img, R), torch.int32)
-            self.gt_weight = e((k, n_img, R), torch.float32)
+            self.gt_rows = e((k, n_img, gcap), torch.int32)
+            self.gt_class = e((k, n_img, gcap), torch.int32)
+            self.gt_weight = e((k, n_img, gcap), torch.float32)
             self.asy_flag = e((n_img, R), torch.uint8)
-            self.gt_keep = torch.ones((k, n_img, R), dtype=torch.uint8, device=dev)
+            self.gt_keep = torch.ones((k, n_img, gcap), dtype=torch.uint8, device=dev)
             self.pseudo_labels = e((k, n_img, R, C1), torch.float32)
             self.pseudo_iou = e((k, n_img, R), torch.float16)
             self.loss_weights = e((k, n_img, R), torch.float32)
             self.valid = e((k, n_img), torch.uint8)
-        # host side of the sampling hop: at most max_present * keep_count pseudo GTs per (layer, image)
-        self.cap = min(R, max_present * p.keep_count)
         pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
         self.h_count = pin((k, n_img), torch.int32)
-        self.h_class = pin((k, n_img, self.cap), torch.int32)
-        self.h_weight = pin((k, n_img, self.cap), torch.float32)
-        self.h_keep = pin((k, n_img, self.cap), torch.uint8)
+        self.h_class = pin((k, n_img, gcap), torch.int32)
+        self.h_weight = pin((k, n_img, gcap), torch.float32)
+        self.h_keep = pin((k, n_img, gcap), torch.uint8)
         self.ev = torch.cuda.Event()
         self.side = torch.cuda.Stream(device=self.dev, priority=-2)     # scoring GEMM next to the overlap helpers: above the step
         self.trace = [] if os.environ.get("CIM_STEP_TRACE") else None
@@ -167,8 +171,8 @@ class CIMHeadStep:
                       P(self.mine_ws), self.mine_ws.numel(), st), "cim_mine")
         if self.anti:
             self.h_count.copy_(self.gt_count, non_blocking=True)
-            self.h_class.copy_(self.gt_class[:, :, :self.cap], non_blocking=True)
-            self.h_weight.copy_(self.gt_weight[:, :, :self.cap], non_blocking=True)
+            self.h_class.copy_(self.gt_class, non_blocking=True)
+            self.h_weight.copy_(self.gt_weight, non_blocking=True)
             self.ev.record(torch.cuda.current_stream(dev))
         ck(L.cim_roi_align_fwd_prepared(P(feat), P(rois), None, P(self.roi_out), n_img, self.Cf, self.H, self.W,
                                         n_img * R, 7, 7, self.scale, self.sr, self.aligned, P(self.roi_ws),
@@ -193,7 +197,7 @@ class CIMHeadStep:
                         raise RuntimeError("more pseudo GTs than max_present * keep_count; raise max_present")
                     if g:
                         keep_h[l, b, :g] = _anti_noise_keep(cls_h[l, b, :g], w_h[l, b, :g], present)
-            self.gt_keep[:, :, :self.cap].copy_(self.h_keep, non_blocking=True)
+            self.gt_keep.copy_(self.h_keep, non_blocking=True)
             keep = self.gt_keep
             if tr is not None:
                 tr.append(("sampled", time.perf_counter()))
