@@ -55,7 +55,10 @@ cim_box_nms_kernel(const float *__restrict__ boxes, const float *__restrict__ sc
     unsigned char *supp = reinterpret_cast<unsigned char *>(box + npad);             // [npad]
     __shared__ int s_count;
     const int c = blockIdx.x, tid = threadIdx.x;
-    uint8_t *kout = keep + (size_t)c * n;
+    // blockIdx.y = image of a batch: boxes [n_img][n][4], scores [n_img][n][score_stride], keep [n_img][ncls][n]
+    boxes += (size_t)blockIdx.y * n * 4;
+    scores += (size_t)blockIdx.y * n * score_stride;
+    uint8_t *kout = keep + ((size_t)blockIdx.y * ncls + c) * n;
 
     // candidates: score > thresh (mask_eval_utils.py:64).  Key = (orderable score bits << 32) | index, sorted
     // descending; non-candidates get key 0 and sink to the end.
@@ -147,16 +150,22 @@ CIM_API int cim_test_scores(const float *scores, float *out, int64_t M, int C1, 
 
 CIM_API int cim_box_nms(const float *boxes, const float *scores, int n, int n_classes, int score_stride,
                         float score_thresh, float nms_thresh, uint8_t *keep, cim_stream_t stream) {
+    return cim_box_nms_batched(boxes, scores, 1, n, n_classes, score_stride, score_thresh, nms_thresh, keep, stream);
+}
+
+CIM_API int cim_box_nms_batched(const float *boxes, const float *scores, int n_img, int n, int n_classes,
+                                int score_stride, float score_thresh, float nms_thresh, uint8_t *keep,
+                                cim_stream_t stream) {
     if (!boxes || !scores || !keep) return CIM_ERR_ARG;
-    if (n < 0 || n_classes < 0 || score_stride < n_classes) return CIM_ERR_ARG;
-    if (n == 0 || n_classes == 0) return CIM_OK;
-    if (n > 8192 || n_classes > 65535) return CIM_ERR_SHAPE;
+    if (n_img < 0 || n < 0 || n_classes < 0 || score_stride < n_classes) return CIM_ERR_ARG;
+    if (n_img == 0 || n == 0 || n_classes == 0) return CIM_OK;
+    if (n > 8192 || n_classes > 65535 || n_img > 65535) return CIM_ERR_SHAPE;
     if (!cim_aligned(boxes, 16)) return CIM_ERR_ALIGN;
     const int npad = next_pow2(n);
     const size_t smem = (size_t)npad * (8 + 16 + 1);
     if ((int)smem > cim_max_smem_optin()) return CIM_ERR_SHAPE;
     cudaFuncSetAttribute(cim_box_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cim_box_nms_kernel<<<(unsigned)n_classes, NMS_THREADS, smem, (cudaStream_t)stream>>>(
+    cim_box_nms_kernel<<<dim3((unsigned)n_classes, (unsigned)n_img), NMS_THREADS, smem, (cudaStream_t)stream>>>(
         boxes, scores, n, n_classes, score_stride, score_thresh, nms_thresh, npad, keep);
     return cim_launch_status();
 }

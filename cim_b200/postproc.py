@@ -44,6 +44,22 @@ def box_nms(boxes, scores, score_thresh=1e-5, nms_thresh=0.3):
     return keep
 
 
+def box_nms_batched(boxes, scores, score_thresh=1e-5, nms_thresh=0.3):
+    """boxes [B,n,4], scores [B,n,C] -> keep [B,C,n] uint8: box_nms for every image of a batch in one launch."""
+    _lib.require_cuda(boxes, "boxes", torch.float32)
+    _lib.require_cuda(scores, "scores", torch.float32)
+    boxes, scores = boxes.contiguous(), scores.contiguous()
+    b, n, c = scores.shape
+    if boxes.shape != (b, n, 4):
+        raise ValueError("boxes must be [B, n, 4]")
+    with torch.cuda.device(boxes.device):
+        keep = torch.empty((b, c, n), dtype=torch.uint8, device=boxes.device)
+        rc = _lib.lib().cim_box_nms_batched(_lib.ptr(boxes), _lib.ptr(scores), b, n, c, c, float(score_thresh),
+                                            float(nms_thresh), _lib.ptr(keep), _lib.stream_ptr(boxes.device))
+    _lib.check(rc, "cim_box_nms_batched")
+    return keep
+
+
 def results_with_nms_and_limit(scores, boxes, score_thresh=1e-5, nms_thresh=0.3, detections_per_im=100):
     """mask_results_with_nms_and_limit_get_index (mask_eval_utils.py:57-110) for one image.
     scores [n,C], boxes [n,4] CUDA tensors.  Returns (scores, boxes, cls_boxes, cls_inds) with the reference's

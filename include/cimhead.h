@@ -306,6 +306,10 @@ int cim_pcl_loss(const float *predict_cls, const float *mat, float *loss, float 
 int cim_test_scores(const float *scores, float *out, int64_t M, int C1, int K, cim_stream_t stream);
 int cim_box_nms(const float *boxes, const float *scores, int n, int n_classes, int score_stride,
                 float score_thresh, float nms_thresh, uint8_t *keep, cim_stream_t stream);
+/* The same for n_img images in one launch: boxes [n_img, n, 4], scores [n_img, n, score_stride],
+ * keep [n_img, n_classes, n] (one CTA per (class, image): 80 CTAs of one image leave half a B200 idle). */
+int cim_box_nms_batched(const float *boxes, const float *scores, int n_img, int n, int n_classes, int score_stride,
+                        float score_thresh, float nms_thresh, uint8_t *keep, cim_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -79,3 +79,18 @@ def test_errors():
         postproc.box_nms(torch.zeros(4, 4), torch.zeros(4, 2))                    # CPU tensors: no CPU path
     with pytest.raises(ValueError):
         postproc.box_nms(torch.zeros(4, 5, device=DEV), torch.zeros(4, 2, device=DEV))
+
+
+def test_box_nms_batched_equals_per_image():
+    """cim_box_nms_batched (one CTA per (class, image)) keeps exactly what the per-image call keeps."""
+    B, n, c = 3, 700, 12
+    g = torch.Generator().manual_seed(9)
+    xy = torch.rand(B, n, 2, generator=g) * 400
+    wh = torch.rand(B, n, 2, generator=g) * 120 + 4
+    boxes = torch.cat([xy, xy + wh], 2).to(DEV)
+    scores = torch.rand(B, n, c, generator=g).to(DEV)
+    scores[1, :, 3] = 0                                  # a class without candidates
+    keep = postproc.box_nms_batched(boxes, scores, 0.05, 0.3)
+    assert keep.shape == (B, c, n)
+    for b in range(B):
+        assert torch.equal(keep[b], postproc.box_nms(boxes[b], scores[b], 0.05, 0.3))

@@ -41,6 +41,8 @@ def main():
     scores = torch.empty(nh, B * R, C1, device=dev)
     sws = torch.empty(max(256, L.cim_score_heads_workspace_bytes(B, R, D, C1, K)), dtype=torch.uint8, device=dev)
 
+    boxes = rois[:, 1:].reshape(B, R, 4).contiguous()
+
     def roi():
         _lib.check(L.cim_roi_align_fwd(P(feat), P(rois), P(out), B, Cf, H, W, B * R, 7, 7, scale, 0, 1, P(ws), ws.numel(),
                                        st), "roi")
@@ -51,8 +53,7 @@ def main():
 
     def post():
         s = postproc.test_scores(scores, K)                       # [B*R, C]
-        for b in range(B):
-            postproc.box_nms(rois[b * R:(b + 1) * R, 1:].contiguous(), s[b * R:(b + 1) * R], 1e-5, 0.3)
+        postproc.box_nms_batched(boxes, s.view(B, R, -1), 1e-5, 0.3)
 
     def timeit(fn):
         for _ in range(3):
