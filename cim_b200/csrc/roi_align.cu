@@ -346,7 +346,7 @@ __device__ __forceinline__ void fwd_pairs(const float *__restrict__ tile_c, int 
                 acc[q][pw] = __ffma2_rn(bcast2(r[pw].y), wo[q], acc[q][pw]);
             }
     }
-    if (lane == 0) bulk_wait_read<0>();            // the previous bulk store has drained this stage
+    if (elect_one()) bulk_wait_read<0>();            // the previous bulk store has drained this stage
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -460,7 +460,7 @@ roi_align_fwd_tile_kernel(const float *__restrict__ feat, const int *__restrict_
                 // MaskFuse prologue (mask7 != null): out is [K][2C][49], channels [0, C) = the pooled features,
                 // [C, 2C) = the same times the ROI's 7 x 7 mask (lib/modeling/resnet50.py:131-134)
                 const size_t orow = mask7 ? (size_t)roi * 2 * C : (size_t)roi * C;
-                if (lane == 0) {
+                if (elect_one()) {
                     bulk_s2g(out + (orow + c0) * NBIN, stage_w, STAGE_FLOATS * 4);
                     bulk_commit();
                 }
@@ -469,13 +469,13 @@ roi_align_fwd_tile_kernel(const float *__restrict__ feat, const int *__restrict_
                     const float *mp = mask7 + (size_t)roi * NBIN;
 #pragma unroll
                     for (int i = 0; i < NBIN; ++i) m[i] = __ldg(mp + i);
-                    if (lane == 0) bulk_wait_read<0>();        // the stage has been read by the store above
+                    if (elect_one()) bulk_wait_read<0>();        // the stage has been read by the store above
                     __syncwarp();
 #pragma unroll
                     for (int i = 0; i < NBIN; ++i) stage_c[i] *= m[i];
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) {
+                    if (elect_one()) {
                         bulk_s2g(out + (orow + C + c0) * NBIN, stage_w, STAGE_FLOATS * 4);
                         bulk_commit();
                     }
@@ -487,7 +487,7 @@ roi_align_fwd_tile_kernel(const float *__restrict__ feat, const int *__restrict_
         }
         u += r1 - r0;
     }
-    if (lane == 0) bulk_wait_read<0>();
+    if (elect_one()) bulk_wait_read<0>();
 }
 
 // ----------------------------------------------------------------------------- tile: backward
