@@ -508,10 +508,28 @@ constexpr int SLOT_FLOATS_F = NBR_F * (2 * STAGE_FLOATS + DESC_WORDS + MASK_PAD)
 //   x pass: (t[2p][xo+l], t[2p+1][xo+l]) += wx[pw][l] * r[pw]       7T x (LDS.64, FFMA2, STS.64)
 // FUSED (MaskFuse prologue): the gradient of the pooled value is g[ph][pw] + g2[ph][pw] * m[ph][pw] with g2 the
 // gradient block of the masked copy (STAGE_FLOATS further on in the slot) and m the ROI's 7 x 7 mask (smem).
-template <int T, bool XINC, bool FUSED, int NW>
+// tensor-memory accessors of the backward's TM variant: lane = channel, 2 columns = (g[2p][x], g[2p+1][x])
+__device__ __forceinline__ float2 tm_ld2(uint32_t taddr) {
+    uint32_t a, b;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr) : "memory");
+    return make_float2(__uint_as_float(a), __uint_as_float(b));
+}
+__device__ __forceinline__ void tm_st2(uint32_t taddr, float2 v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(__float_as_uint(v.x)),
+                 "r"(__float_as_uint(v.y))
+                 : "memory");
+}
+__device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// TM: the gradient tile lives in TENSOR MEMORY instead of shared memory (tmem_w = first column of this warp's
+// region, pair p of the warp at columns 2 W (p / NW) ..): the x pass becomes tcgen05.ld / FFMA2 / tcgen05.st.
+// tools/micro/tmem_rmw.cu: this read-modify-write pattern runs at 98 B/clk/SM in tensor memory against the 64 B/clk
+// of shared memory (128 B/clk port, read + write), and the port stays free for the y pass.
+template <int T, bool XINC, bool FUSED, int NW, bool TM = false>
 __device__ __forceinline__ void bwd_pairs(float *__restrict__ tile_c, int W, const int *d,
                                           const float *__restrict__ g, const float *__restrict__ m, int warp, int y0,
-                                          int y1) {
+                                          int y1, uint32_t tmem_w = 0) {
     float wx[PW][T];
     int xo[PW];
     const float *dwx = reinterpret_cast<const float *>(d + D_WX);
@@ -552,6 +570,35 @@ __device__ __forceinline__ void bwd_pairs(float *__restrict__ tile_c, int W, con
                 if (FUSED) gv = fmaf(gp[STAGE_FLOATS + pw], m[ph * PW + pw], gv);
                 r[pw] = __ffma2_rn(bcast2(gv), w, r[pw]);
             }
+        }
+        if (TM) {
+            const uint32_t trow = tmem_w + (uint32_t)((p / NW) * W) * 2u;
+            if (XINC) {
+#pragma unroll
+                for (int l = 0; l < T; ++l) {
+                    float2 v[PW];
+#pragma unroll
+                    for (int pw = 0; pw < PW; ++pw) v[pw] = tm_ld2(trow + 2u * (uint32_t)(xo[pw] + l));
+                    tm_wait_ld();
+#pragma unroll
+                    for (int pw = 0; pw < PW; ++pw)
+                        tm_st2(trow + 2u * (uint32_t)(xo[pw] + l), __ffma2_rn(bcast2(wx[pw][l]), r[pw], v[pw]));
+                    tm_wait_st();                       // the next l (and the next ROI) may read these columns
+                }
+            } else {
+#pragma unroll
+                for (int pw = 0; pw < PW; ++pw) {
+                    float2 v[T];
+#pragma unroll
+                    for (int l = 0; l < T; ++l) v[l] = tm_ld2(trow + 2u * (uint32_t)(xo[pw] + l));
+                    tm_wait_ld();
+#pragma unroll
+                    for (int l = 0; l < T; ++l)
+                        tm_st2(trow + 2u * (uint32_t)(xo[pw] + l), __ffma2_rn(bcast2(wx[pw][l]), r[pw], v[l]));
+                    tm_wait_st();                       // the next bin may alias these columns
+                }
+            }
+            continue;
         }
         float2 *row = tile2 + p * W;
         if (XINC) {
@@ -609,7 +656,8 @@ __device__ __forceinline__ void red_add4(float *gptr, float a, float b, float c,
 // FUSED (MaskFuse prologue): grad_out is [K][2C][49]; the effective gradient of the pooled features is
 // g[c] + g[C + c] * mask[roi].  Both gradient blocks and the (padded) mask of a ROI travel in the ring slot;
 // mask7 points at the PADDED masks [K][MASK_PAD] in the workspace.
-template <bool FUSED, int NWB>
+// TM: the gradient tile is kept in tensor memory (see bwd_pairs); shared memory then only holds the ring.
+template <bool FUSED, int NWB, bool TM>
 __global__ void __launch_bounds__(NWB * 32, 1)
 roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restrict__ hdr,
                           const int *__restrict__ img_start, const int *__restrict__ descs,
@@ -622,7 +670,8 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
     const int Cg = FUSED ? 2 * C : C;                         // channels of grad_out
     extern __shared__ __align__(128) float smem[];
     float *tile = smem;
-    float *ring = smem + (size_t)CH * pitch;                 // [NS][NBR x grads | NBR x DESC_WORDS]
+    float *ring = smem + (TM ? 0 : (size_t)CH * pitch);      // [NS][NBR x grads | NBR x DESC_WORDS]
+    __shared__ uint32_t tmem_slot;
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)NS * SLOT_FLOATS);
     uint64_t *empty = full + NS;
     if (__ldg(hdr) != 0) return;              // rois not grouped by image: the generic kernel does it all
@@ -633,7 +682,20 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
         for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWB); }
         fence_mbar_init();
     }
+    if (TM && warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (TM) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (TM) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // TM: warp w reaches the TMEM lanes of its quarter (w % 4) only; lane = channel.  Its region holds the row
+    // pairs it owns (p % NWB == w), 2 W columns each; the 4 warps of a quarter sit side by side.
+    const int npw = (((H + 1) >> 1) + NWB - 1) / NWB;        // row pairs per warp
+    const uint32_t tmem_cols_w = (uint32_t)(npw * W * 2);
+    const uint32_t tmem_w = TM ? tmem_slot + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(warp >> 2) * tmem_cols_w : 0u;
 
     const int s0 = __ldg(img_start), sB = __ldg(img_start + B);
     const long long U = (long long)nchunks * (sB - s0);
@@ -676,7 +738,12 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
         const int first_roi = is + r0, n = r1 - r0;
         const int nbatch = (n + NBR - 1) / NBR, gb0 = gb;
 
-        for (int e = tid; e < CH * pitch; e += NWB * 32) tile[e] = 0.f;
+        if (TM) {
+            for (uint32_t cc = 0; cc < tmem_cols_w; cc += 2) tm_st2(tmem_w + cc, make_float2(0.f, 0.f));
+            tm_wait_st();
+        } else {
+            for (int e = tid; e < CH * pitch; e += NWB * 32) tile[e] = 0.f;
+        }
         __syncthreads();
 
         // producer duty (lane 0 of warp 0): batch j of this segment (NBR consecutive ROIs: gradients +
@@ -734,19 +801,19 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
                 const int T = d[D_TX];
                 if (d[D_XINC]) {
                     switch (T) {
-                        case 2: bwd_pairs<2, true, FUSED, NWB>(tile_c, W, d, g, m, warp, y0, y1); break;
-                        case 3: bwd_pairs<3, true, FUSED, NWB>(tile_c, W, d, g, m, warp, y0, y1); break;
-                        case 4: bwd_pairs<4, true, FUSED, NWB>(tile_c, W, d, g, m, warp, y0, y1); break;
-                        case 6: bwd_pairs<6, true, FUSED, NWB>(tile_c, W, d, g, m, warp, y0, y1); break;
-                        default: bwd_pairs<8, true, FUSED, NWB>(tile_c, W, d, g, m, warp, y0, y1); break;
+                        case 2: bwd_pairs<2, true, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
+                        case 3: bwd_pairs<3, true, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
+                        case 4: bwd_pairs<4, true, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
+                        case 6: bwd_pairs<6, true, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
+                        default: bwd_pairs<8, true, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
                     }
                 } else {
                     switch (T) {
-                        case 2: bwd_pairs<2, false, FUSED, NWB>(tile_c, W, d, g, m, warp, y0, y1); break;
-                        case 3: bwd_pairs<3, false, FUSED, NWB>(tile_c, W, d, g, m, warp, y0, y1); break;
-                        case 4: bwd_pairs<4, false, FUSED, NWB>(tile_c, W, d, g, m, warp, y0, y1); break;
-                        case 6: bwd_pairs<6, false, FUSED, NWB>(tile_c, W, d, g, m, warp, y0, y1); break;
-                        default: bwd_pairs<8, false, FUSED, NWB>(tile_c, W, d, g, m, warp, y0, y1); break;
+                        case 2: bwd_pairs<2, false, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
+                        case 3: bwd_pairs<3, false, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
+                        case 4: bwd_pairs<4, false, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
+                        case 6: bwd_pairs<6, false, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
+                        default: bwd_pairs<8, false, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
                     }
                 }
             }
@@ -757,7 +824,38 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
 
         // tile -> grad_feat (+=): the slab is zero or holds the other CTA's partial sum
         float *dst = grad_feat + ((size_t)b * C + c0) * HW;
-        if ((W & 3) == 0) {
+        if (TM) {
+            // every warp drains its own row pairs: lane = channel, 8 columns = 4 x-positions x (row 2p, row 2p+1)
+            float *dl = dst + (size_t)lane * HW;
+            for (int pl = 0; pl < npw; ++pl) {
+                const int pp = warp + NWB * pl, y = 2 * pp;
+                if (y >= H) break;
+                const uint32_t trow = tmem_w + (uint32_t)(pl * W) * 2u;
+                if ((W & 3) == 0) {
+                    for (int x = 0; x < W; x += 4) {
+                        uint32_t v[8];
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+                                       "=r"(v[7])
+                                     : "r"(trow + 2u * (uint32_t)x)
+                                     : "memory");
+                        tm_wait_ld();
+                        red_add4(dl + (size_t)y * W + x, __uint_as_float(v[0]), __uint_as_float(v[2]),
+                                 __uint_as_float(v[4]), __uint_as_float(v[6]));
+                        if (y + 1 < H)
+                            red_add4(dl + (size_t)(y + 1) * W + x, __uint_as_float(v[1]), __uint_as_float(v[3]),
+                                     __uint_as_float(v[5]), __uint_as_float(v[7]));
+                    }
+                } else {
+                    for (int x = 0; x < W; ++x) {
+                        const float2 v = tm_ld2(trow + 2u * (uint32_t)x);
+                        tm_wait_ld();
+                        atomicAdd(dl + (size_t)y * W + x, v.x);
+                        if (y + 1 < H) atomicAdd(dl + (size_t)(y + 1) * W + x, v.y);
+                    }
+                }
+            }
+        } else if ((W & 3) == 0) {
             for (int e = tid * 4; e < CH * HW; e += NWB * 32 * 4) {
                 const int c = e / HW, rem = e - c * HW, y = rem / W, x = rem - y * W;
                 const float *t = tile + c * pitch + tile_off(y, x, W);
@@ -770,6 +868,14 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
             }
         }
         __syncthreads();
+    }
+    if (TM) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        }
     }
 }
 
@@ -1089,6 +1195,8 @@ __global__ void roi_mask_pad_kernel(const float *__restrict__ m, float *__restri
 // ------------------------------------------------------------------------------------- host
 struct Plan {
     bool tile, glob;                 // glob: map too large for shared memory -> channel-last global copy
+    bool bwd_tm;                     // backward tile kernel keeps its gradient tile in tensor memory
+    size_t smem_bwd_tm, smem_bwd_fused_tm;
     int pitch, fwd_warps, wyd_floats, glob_bwd_warps, glob_bwd_warps_fused;
     size_t smem_fwd, smem_bwd, smem_bwd_fused, smem_fwd_glob, smem_bwd_glob, smem_bwd_glob_fused;
 };
@@ -1109,6 +1217,10 @@ static Plan make_plan(int C, int H, int W, int oh, int ow) {
     p.smem_bwd_fused = (size_t)CH * p.pitch * 4 + (size_t)NS_F * SLOT_FLOATS_F * 4 + 2 * NS_F * 8;
     p.tile = oh == PH && ow == PW && (C % CH) == 0 && W >= MAXT && p.smem_fwd <= cap &&
              p.smem_bwd <= cap && p.smem_bwd_fused <= cap && (((size_t)CH * p.pitch * 4) % 16 == 0);
+    // tensor-memory variant of the backward: 4 warps of a lane quarter x their row pairs x 2 W columns <= 512
+    p.bwd_tm = p.tile && 4 * ((((H + 1) >> 1) + NWB_DEFAULT - 1) / NWB_DEFAULT) * W * 2 <= 512;
+    p.smem_bwd_tm = (size_t)NS * SLOT_FLOATS * 4 + 2 * NS * 8;
+    p.smem_bwd_fused_tm = (size_t)NS_F * SLOT_FLOATS_F * 4 + 2 * NS_F * 8;
     // large maps (VGG-16: 64 x 64): same sweeps over a channel-last copy in global memory
     p.smem_fwd_glob = FWD_GLOB_WARPS * per_warp_wide;
     const size_t bw = (size_t)2 * STAGE_FLOATS * 4 + 2 * DESC_WORDS_MAX * 4, bwf = bw + (size_t)2 * STAGE_FLOATS * 4;
@@ -1273,12 +1385,17 @@ static int roi_bwd_impl(const float *grad_out, const float *rois, const float *m
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         kern<<<grid, nw * 32, smem, st>>>(grad_out, w.hdr, w.img_start, w.desc, mk, grad_feat, B, C, H, W, p.pitch);
     };
+    // CIM_ROI_BWD_TMEM=0 keeps the gradient tile in shared memory (A/B timing, tests)
+    const char *tmv = getenv("CIM_ROI_BWD_TMEM");
+    const bool tm = p.bwd_tm && !(tmv && atoi(tmv) == 0);
     if (mask7) {
         roi_mask_pad_kernel<<<(K * MASK_PAD + 255) / 256, 256, 0, st>>>(mask7, w.maskpad, K, NBIN);
         if ((rc = cim_launch_status())) return rc;
-        go(roi_align_bwd_tile_kernel<true, NWB_DEFAULT>, NWB_DEFAULT, p.smem_bwd_fused, w.maskpad);
+        if (tm) go(roi_align_bwd_tile_kernel<true, NWB_DEFAULT, true>, NWB_DEFAULT, p.smem_bwd_fused_tm, w.maskpad);
+        else go(roi_align_bwd_tile_kernel<true, NWB_DEFAULT, false>, NWB_DEFAULT, p.smem_bwd_fused, w.maskpad);
     } else {
-        go(roi_align_bwd_tile_kernel<false, NWB_DEFAULT>, NWB_DEFAULT, p.smem_bwd, nullptr);
+        if (tm) go(roi_align_bwd_tile_kernel<false, NWB_DEFAULT, true>, NWB_DEFAULT, p.smem_bwd_tm, nullptr);
+        else go(roi_align_bwd_tile_kernel<false, NWB_DEFAULT, false>, NWB_DEFAULT, p.smem_bwd, nullptr);
     }
     if ((rc = cim_launch_status())) return rc;
     roi_align_generic_kernel<true><<<dim3((unsigned)((K + 7) / 8), 1), 256, 0, st>>>(grad_out, rois, grad_feat, w.hdr, w.desc,
