@@ -382,3 +382,27 @@ def test_prepared_entry_points_equal_the_self_preparing_ones(shape, fused):
         assert torch.equal(g1, g2)                      # tile path: bit-reproducible
     else:
         close(g2.cpu().numpy(), g1.cpu().numpy())       # global path: red.global.add order is not fixed
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 32, 32, 1.0 / 16), (1, 64, 16, 16, 1.0 / 32), (1, 32, 25, 38, 1.0 / 16)])
+@pytest.mark.parametrize("fused", [False, True])
+def test_backward_tile_in_tensor_memory_equals_shared_memory_bitwise(shape, fused, monkeypatch):
+    """The default backward keeps its gradient tile in tensor memory (tcgen05.ld / st read-modify-write);
+    CIM_ROI_BWD_TMEM=0 selects the shared-memory tile.  Same owners, same order: bit-identical, also for odd
+    map sizes (last row pair half empty, W not a multiple of 4) and the fused MaskFuse variant."""
+    B, C, H, W, scale = shape
+    feat = torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(51))
+    rois = random_rois(52, B, 90, H, W, scale)          # no leftover ROIs: their atomics have no fixed order
+    masks = (torch.rand(90, 7, 7, generator=torch.Generator().manual_seed(53)) > 0.5).float()
+
+    def grad():
+        if fused:
+            _, gf, _ = run_maskfuse(feat, rois, masks, scale, 0, True)
+        else:
+            _, gf, _, _ = run_both(feat, rois, scale, 0, True)
+        return gf
+
+    g_tm = grad()
+    monkeypatch.setenv("CIM_ROI_BWD_TMEM", "0")
+    g_sm = grad()
+    np.testing.assert_array_equal(g_tm, g_sm)
