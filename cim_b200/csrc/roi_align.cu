@@ -495,10 +495,11 @@ constexpr int NWB_DEFAULT = 16;     // consumer warps of the backward CTA; warp 
                                     // {y : (y >> 1) % 16 == w}  (D_OWN is computed for exactly this map)
 constexpr int NBR = 4;              // ROIs per ring slot: one full/empty barrier round per 4 ROIs
 constexpr int NS = 3;               // ring slots
-#ifndef NS_TM_EXTRA_V
-#define NS_TM_EXTRA_V 3
-#endif
-constexpr int NS_TM_EXTRA = NS_TM_EXTRA_V;   // more slots for the tensor-memory variant
+// tensor-memory variant: the tile's 128 KB of shared memory go to the ring -- as LARGER slots (16 ROIs per barrier
+// round, 2 slots) rather than more of them: cfg2 backward 1.57 ms (4 ROIs x 3 slots) -> 1.49 (4 x 6) -> 1.385 (8 x 4)
+// -> 1.34 (16 x 2)
+constexpr int NS_TM_EXTRA = -1;
+constexpr int NBR_TM_MUL = 4;
 constexpr int SLOT_FLOATS = NBR * (STAGE_FLOATS + DESC_WORDS);
 // fused MaskFuse backward: two gradient blocks per ROI (d/d pooled, d/d pooled*mask)
 // and the ROI's 7 x 7 mask (padded to 52 floats = 208 B so that it can travel by cp.async.bulk); the owners fold
@@ -667,7 +668,7 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
                           const int *__restrict__ img_start, const int *__restrict__ descs,
                           const float *__restrict__ mask7, float *__restrict__ grad_feat, int B, int C, int H, int W,
                           int pitch) {
-    constexpr int NBR = FUSED ? NBR_F : ::NBR;               // ROIs per slot
+    constexpr int NBR = (FUSED ? NBR_F : ::NBR) * (TM ? NBR_TM_MUL : 1);   // ROIs per slot
     constexpr int NS = (FUSED ? NS_F : ::NS) + (TM ? NS_TM_EXTRA : 0);   // ring slots (TM: the tile's smem is free)
     constexpr int GSTRIDE = FUSED ? 2 * STAGE_FLOATS : STAGE_FLOATS;      // gradient floats per ROI in a slot
     constexpr int SLOT_FLOATS = NBR * (GSTRIDE + DESC_WORDS + (FUSED ? MASK_PAD : 0));
@@ -1223,8 +1224,8 @@ static Plan make_plan(int C, int H, int W, int oh, int ow) {
              p.smem_bwd <= cap && p.smem_bwd_fused <= cap && (((size_t)CH * p.pitch * 4) % 16 == 0);
     // tensor-memory variant of the backward: 4 warps of a lane quarter x their row pairs x 2 W columns <= 512
     p.bwd_tm = p.tile && 4 * ((((H + 1) >> 1) + NWB_DEFAULT - 1) / NWB_DEFAULT) * W * 2 <= 512;
-    p.smem_bwd_tm = (size_t)(NS + NS_TM_EXTRA) * SLOT_FLOATS * 4 + 2 * (NS + NS_TM_EXTRA) * 8;
-    p.smem_bwd_fused_tm = (size_t)(NS_F + NS_TM_EXTRA) * SLOT_FLOATS_F * 4 + 2 * (NS_F + NS_TM_EXTRA) * 8;
+    p.smem_bwd_tm = (size_t)(NS + NS_TM_EXTRA) * NBR_TM_MUL * SLOT_FLOATS * 4 + 2 * (NS + NS_TM_EXTRA) * 8;
+    p.smem_bwd_fused_tm = (size_t)(NS_F + NS_TM_EXTRA) * NBR_TM_MUL * SLOT_FLOATS_F * 4 + 2 * (NS_F + NS_TM_EXTRA) * 8;
     // large maps (VGG-16: 64 x 64): same sweeps over a channel-last copy in global memory
     p.smem_fwd_glob = FWD_GLOB_WARPS * per_warp_wide;
     const size_t bw = (size_t)2 * STAGE_FLOATS * 4 + 2 * DESC_WORDS_MAX * 4, bwf = bw + (size_t)2 * STAGE_FLOATS * 4;
