@@ -23,6 +23,13 @@ import sys
 import threading
 import time
 
+# The CPU arm uses every host core whatever the launcher exported: torchrun sets OMP_NUM_THREADS=1 for its workers,
+# which made the N > 1 reference lines 3.5x slower than the N = 1 line in round 1.  BLAS / OpenMP read these when
+# numpy / torch load, so they are set before either is imported.
+if "reference" in sys.argv[1:] and "--impl" in sys.argv[1:] or any(a.startswith("--impl=reference") for a in sys.argv[1:]):
+    for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -109,6 +116,22 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ CPU arm
+def literal_mask_utils(cfg):
+    """The reference's LITERAL mask_utils double loop (one Python-level pair at a time, create_cob_iou.py:43-48)
+    extrapolated to this workload by its pair count from the us/pair measured in the build container with the
+    unmodified reference file (tools/literal_mask_utils_timing.py -> profiles/literal_mask_utils.json; the reference
+    tree does not travel to the GPU box).  The CPU arm itself times the vectorised restatement (M . M^T)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "literal_mask_utils.json")) as f:
+            t = json.load(f)
+        us = t["sizes"][str(cfg["mask"])]["us_per_pair_both_maps"]
+    except (OSError, ValueError, KeyError):
+        return None
+    return {"s_per_image": us * 1e-6 * cfg["R"] ** 2, "us_per_pair_iou_plus_asy": us,
+            "measured_on": f"build container, 1 of {t['host_cores']} cores (the loop is single-threaded numpy), "
+                           f"{t['n_masks']} masks of {cfg['mask']}^2", "pairs_per_image": cfg["R"] ** 2}
+
+
 def cpu_reference(cfg, steps, warmup, sample_rois=128, head_grads=True):
     """The reference's algorithm for the path, restated for CPU (oracle/), timed on the host cores
     on a BOUNDED sample of the workload: one image; RoIAlign fwd+bwd and the mask overlap on
@@ -185,6 +208,7 @@ def cpu_reference(cfg, steps, warmup, sample_rois=128, head_grads=True):
     wall = time.perf_counter() - t_wall
     sec = float(np.mean(per_image))
     return dict(images_per_s=1.0 / sec, sec_per_image=sec, cores=ncpu, wall_s=wall, parts=parts,
+                literal=literal_mask_utils(cfg),
                 sample=f"1 image of {cfg['R']} proposals; RoIAlign fwd+bwd and mask overlap on {S} proposal rows "
                        f"(x{R / S:.1f}), scoring {'fwd+bwd + loss block' if head_grads else 'fwd'} + 3 mining layers at full size; "
                        f"numpy/OpenMP on all host cores")
@@ -339,7 +363,8 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config,
             "cpu_baseline": {"value": r["images_per_s"], "unit": "images/s", "cores": r["cores"], "kind": "port",
-                             "sample": r["sample"], "parts_s_per_image": r["parts"]},
+                             "sample": r["sample"], "parts_s_per_image": r["parts"],
+                             "literal_mask_utils_s_per_image": r["literal"]},
             "e2e": {"value": r["images_per_s"], "unit": "images/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
             "gpu_launches": 0}))
@@ -488,7 +513,8 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference(cfg, 1, 0, head_grads=not args.no_head_grads)
         result["cpu_baseline"] = {"value": r["images_per_s"], "unit": "images/s", "cores": r["cores"], "kind": "port",
-                                  "sample": r["sample"], "parts_s_per_image": r["parts"]}
+                                  "sample": r["sample"], "parts_s_per_image": r["parts"],
+                                  "literal_mask_utils_s_per_image": r["literal"]}
     emit(result)
 
 

@@ -15,6 +15,8 @@ LIB_PATH = os.path.join(_HERE, "libcimhead.so")
 ABI_VERSION = 3
 MAX_LAYERS = 4
 OVERLAP_ALGOS = {"auto": 0, "popc": 1, "tensor": 2}
+#: cim_set_debug_flags bits (include/cimhead.h): diagnostic kernel selection for A/B timing and bit-identity tests
+DBG_ROI_BWD_SMEM_TILE, DBG_OVERLAP_LOADER_WARP, DBG_SCORE_FFMA, DBG_ROI_NO_WINDOWS = 1, 2, 4, 8
 
 _lock = threading.Lock()
 _lib = None
@@ -34,6 +36,8 @@ _P, _I, _F, _SZ, _I64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_int64
 _SIGNATURES = {
     "cim_abi_version": (C.c_int, []),
     "cim_error_string": (C.c_char_p, [_I]),
+    "cim_set_debug_flags": (None, [C.c_uint]),
+    "cim_get_debug_flags": (C.c_uint, []),
     "cim_roi_align_workspace_bytes": (_SZ, [_I]),
     "cim_roi_align_workspace_bytes_ex": (_SZ, [_I, _I, _I, _I, _I, _I, _I]),
     "cim_roi_align_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P, _SZ, _P]),
@@ -92,6 +96,23 @@ def lib():
                     raise RuntimeError("cim_mine_params layout mismatch between cimhead.h and _lib.py")
                 _lib = handle
     return _lib
+
+
+class debug_flags:
+    """with _lib.debug_flags(_lib.DBG_...): the library's diagnostic kernel selection for the calls inside the
+    block (process-wide; tests and A/B timing only).  The library never reads the environment."""
+
+    def __init__(self, flags):
+        self.flags = int(flags)
+
+    def __enter__(self):
+        self.prev = lib().cim_get_debug_flags()
+        lib().cim_set_debug_flags(self.flags)
+        return self
+
+    def __exit__(self, *exc):
+        lib().cim_set_debug_flags(self.prev)
+        return False
 
 
 def check(rc, what):

@@ -1,6 +1,12 @@
 // api.cu -- version and error strings of libcimhead.so.
 #include "common.cuh"
 
+#include <atomic>
+
+static std::atomic<unsigned> g_debug_flags{0u};
+CIM_API void cim_set_debug_flags(unsigned flags) { g_debug_flags.store(flags, std::memory_order_relaxed); }
+CIM_API unsigned cim_get_debug_flags(void) { return g_debug_flags.load(std::memory_order_relaxed); }
+
 CIM_API int cim_abi_version(void) { return CIM_ABI_VERSION; }
 CIM_API size_t cim_sizeof_mine_params(void) { return sizeof(cim_mine_params); }
 

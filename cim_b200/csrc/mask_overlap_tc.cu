@@ -31,7 +31,6 @@
 // the caller un-permutes the maps afterwards.
 // History of this kernel, with the ncu evidence, is in DESIGN.md section 4.3.
 #include "common.cuh"
-#include <cstdlib>
 
 namespace {
 
@@ -625,11 +624,10 @@ int cim_mask_overlap_tc_launch(const uint32_t *packed, const int32_t *area, cons
                                const int32_t *tile_order, int n_img, int n, long long words, int32_t *inter,
                                __half *iou, __half *asy, cudaStream_t st) {
     // The direct kernel needs the tile's K-block list to fit its smem array (masks up to 512 Kpixel); larger masks
-    // take the loader-warp kernel.  CIM_OVERLAP_VARIANT=2 forces the loader-warp kernel (tests, A/B timing).
+    // take the loader-warp kernel.  CIM_DBG_OVERLAP_LOADER_WARP forces the loader-warp kernel (tests, A/B timing).
 #define CIM_OV_ARGS packed, area, perm, umap_a, umap_b, bw, visited, tile_order, n_img, n, words, inter, iou, asy, st
-    const char *v = getenv("CIM_OVERLAP_VARIANT");
     const bool direct_ok = (words + 3) / 4 <= KLIST;
-    if (!direct_ok || (v && atoi(v) == 2)) return launch<CfgDefault>(CIM_OV_ARGS);
+    if (!direct_ok || (cim_get_debug_flags() & CIM_DBG_OVERLAP_LOADER_WARP)) return launch<CfgDefault>(CIM_OV_ARGS);
     return launch<Cfg<4, 2, 4>>(CIM_OV_ARGS);
 #undef CIM_OV_ARGS
 }

@@ -32,7 +32,6 @@
 //      bins wider than 8 taps, ROIs not grouped by image.
 #include "common.cuh"
 #include <algorithm>
-#include <cstdlib>
 
 namespace {
 
@@ -1390,9 +1389,8 @@ static int roi_bwd_impl(const float *grad_out, const float *rois, const float *m
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         kern<<<grid, nw * 32, smem, st>>>(grad_out, w.hdr, w.img_start, w.desc, mk, grad_feat, B, C, H, W, p.pitch);
     };
-    // CIM_ROI_BWD_TMEM=0 keeps the gradient tile in shared memory (A/B timing, tests)
-    const char *tmv = getenv("CIM_ROI_BWD_TMEM");
-    const bool tm = p.bwd_tm && !(tmv && atoi(tmv) == 0);
+    // CIM_DBG_ROI_BWD_SMEM_TILE keeps the gradient tile in shared memory (A/B timing, tests)
+    const bool tm = p.bwd_tm && !(cim_get_debug_flags() & CIM_DBG_ROI_BWD_SMEM_TILE);
     if (mask7) {
         roi_mask_pad_kernel<<<(K * MASK_PAD + 255) / 256, 256, 0, st>>>(mask7, w.maskpad, K, NBIN);
         if ((rc = cim_launch_status())) return rc;

@@ -9,7 +9,6 @@
 //   heads 2+K..2+2K-1 (refine_iou): sigmoid                                      (heads.py:216)
 // fp32 FFMA accumulation (TF32 would miss the 1e-5 parity bar).
 #include "common.cuh"
-#include <cstdlib>
 
 // score_heads_tc.cu: 3xTF32 tcgen05 + TMA path
 bool cim_score_tc_eligible(long long M, int D, int C1, int n_ref);
@@ -176,9 +175,8 @@ CIM_API int cim_score_heads(const float *x, const float *weight, const float *bi
     if (M > (1LL << 30)) return CIM_ERR_SHAPE;
     const int nheads = 2 + 2 * K, N = nheads * C1;
     // tensor cores (3xTF32, fp32-accurate) when the shape allows and the caller gave the workspace;
-    // CIM_SCORE_FFMA=1 forces the FFMA kernel (tuning / A-B aid)
-    const char *force = getenv("CIM_SCORE_FFMA");
-    if (!(force && force[0] == '1') && cim_score_tc_eligible(M, D, C1, K) && workspace &&
+    // CIM_DBG_SCORE_FFMA forces the FFMA kernel (tuning / A-B aid)
+    if (!(cim_get_debug_flags() & CIM_DBG_SCORE_FFMA) && cim_score_tc_eligible(M, D, C1, K) && workspace &&
         ws_bytes >= cim_score_tc_workspace_bytes(D, C1, K)) {
         int rc2 = cim_score_tc_launch(x, weight, bias, scores, M, D, C1, K, workspace, st);
         if (rc2) return rc2;

@@ -27,7 +27,6 @@
 // kernels (correctness path for tiny problems).
 #include "common.cuh"
 #include "score_tc.cuh"
-#include <cstdlib>
 
 namespace {
 
@@ -565,8 +564,7 @@ CIM_API int cim_score_heads_bwd(const float *x, const float *weight, const float
         score_bias_grad_kernel<<<(unsigned)N, 256, 0, st>>>(dth, dtl, grad_bias, M, L.MP);
         if ((rc = cim_launch_status())) return rc;
     }
-    const char *force = getenv("CIM_SCORE_FFMA");
-    const bool tc = !(force && force[0] == '1') && M >= BM && (D % 4) == 0 && D >= BK && encode_tiled() != nullptr &&
+    const bool tc = !(cim_get_debug_flags() & CIM_DBG_SCORE_FFMA) && M >= BM && (D % 4) == 0 && D >= BK && encode_tiled() != nullptr &&
                     (size_t)cim_max_smem_optin() >= 1024 + (size_t)DW_NSTAGE * DW_STAGE + (size_t)DW_NRAW * DW_RAW + 256;
     if (grad_x) {
         if (tc) {

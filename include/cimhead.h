@@ -41,6 +41,18 @@ int cim_abi_version(void);
 /* Static string for a return code of this library (negative: CIM_ERR_*, positive: CUDA). */
 const char *cim_error_string(int code);
 
+/* Diagnostic kernel selection (A/B timing, the bit-identity tests of alternative kernels).  The library reads NOTHING
+ * from the process environment; these flags are the only process-wide state it has, they default to 0 (every op
+ * takes its production kernel), and a launch samples them once on entry.  Not meant for production code. */
+enum {
+    CIM_DBG_ROI_BWD_SMEM_TILE = 1u,   /* RoIAlign backward: gradient tile in shared memory, not tensor memory       */
+    CIM_DBG_OVERLAP_LOADER_WARP = 2u, /* mask overlap: loader-warp kernel (what masks above 512 Kpixel take anyway) */
+    CIM_DBG_SCORE_FFMA = 4u,          /* scoring GEMMs fwd / bwd: plain fp32 FFMA kernels, not 3xTF32 tcgen05       */
+    CIM_DBG_ROI_NO_WINDOWS = 8u       /* RoIAlign on maps larger than the smem tile: global-pairs kernels           */
+};
+void cim_set_debug_flags(unsigned flags);
+unsigned cim_get_debug_flags(void);
+
 /* ------------------------------------------------------------------ ROI operators
  * Replace mmcv.ops.RoIAlign / RoIPool as imported by lib/ops/__init__.py:6 and called at
  * lib/modeling/model_builder.py:227-231 (`RoIAlign(resolution, spatial_scale,

@@ -39,6 +39,27 @@ def golden_scores():
     return np.load(os.path.join(GOLDEN, "score_heads.npz"))
 
 
+def assert_close_elementwise(got, want, rtol=1e-5, atol_rms=1e-5, what=""):
+    """ELEMENT-WISE tolerance next to the max-norm bounds of the test modules (which divide by max|want| and would
+    let elements far below the maximum be wrong by large factors): |got - want| <= rtol * |want| + atol_rms * rms(want)
+    for every element.  The rms term is what a sum of O(10..1000) fp32 products can lose to cancellation; NaN must
+    match NaN."""
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    assert got.shape == want.shape, f"{what}: shape {got.shape} != {want.shape}"
+    nan = np.isnan(want)
+    assert np.array_equal(np.isnan(got), nan), f"{what}: NaN positions differ"
+    w = np.where(nan, 0.0, want)
+    rms = float(np.sqrt(np.mean(w * w))) if w.size else 0.0
+    err = np.abs(np.where(nan, 0.0, got) - w)
+    bound = rtol * np.abs(w) + atol_rms * rms
+    bad = err > bound
+    if bad.any():
+        i = np.unravel_index(np.argmax(err - bound), err.shape)
+        raise AssertionError(f"{what}: {int(bad.sum())} of {err.size} elements outside rtol={rtol:g} + {atol_rms:g}*rms "
+                             f"(rms {rms:.3e}); worst at {i}: got {got[i]!r}, want {want[i]!r}, err {err[i]:.3e}, "
+                             f"bound {bound[i]:.3e}")
+
+
 def cim_case_names(npz):
     return sorted({k.split("/")[0] for k in npz.files})
 

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from cim_b200 import mask_ops, synth
+from cim_b200 import _lib, mask_ops, synth
 from oracle import mask_oracle
 from conftest import GOLDEN, assert_f16_bits_equal
 
@@ -162,9 +162,9 @@ def test_tensor_core_path_equals_popc_and_oracle(n, side, n_img):
         assert_f16_bits_equal(u16(t_asy[b]), o_asy.view(np.uint16))
 
 
-@pytest.mark.parametrize("variant", ["2", "0"])
-def test_tensor_core_pipeline_variants_agree(variant, monkeypatch):
-    """CIM_OVERLAP_VARIANT=2: the loader-warp kernel (cp.async staging ring; what masks above 512 Kpixel take);
+@pytest.mark.parametrize("variant", [_lib.DBG_OVERLAP_LOADER_WARP, 0])
+def test_tensor_core_pipeline_variants_agree(variant):
+    """CIM_DBG_OVERLAP_LOADER_WARP: the loader-warp kernel (cp.async staging ring; what masks above 512 Kpixel take);
     default: every expander thread prefetches its own rows (cp.async into thread-private slots, K-block list in
     smem).  Both bit-identical to the popcount kernel, also over repeated launches."""
     n, side = 600, 128
@@ -173,9 +173,9 @@ def test_tensor_core_pipeline_variants_agree(variant, monkeypatch):
     m[n - 1] = m[3]
     packed = mask_ops.mask_pack(m[None].to(DEV))
     want = mask_ops.mask_overlap(packed, return_counts=True, algo="popc")
-    monkeypatch.setenv("CIM_OVERLAP_VARIANT", variant)
-    for _ in range(3):                       # repeated launches: barrier phases, TMEM alloc / dealloc
-        got = mask_ops.mask_overlap(packed, return_counts=True, algo="tensor")
+    with _lib.debug_flags(variant):
+        for _ in range(3):                   # repeated launches: barrier phases, TMEM alloc / dealloc
+            got = mask_ops.mask_overlap(packed, return_counts=True, algo="tensor")
     assert torch.equal(got[2], want[2]) and torch.equal(got[3], want[3])
     assert_f16_bits_equal(u16(got[0]), u16(want[0]))
     assert_f16_bits_equal(u16(got[1]), u16(want[1]))

@@ -6,8 +6,9 @@ import pytest
 import torch
 from torchvision.ops import roi_align as tv_roi_align
 
-from cim_b200 import ops, synth
+from cim_b200 import _lib, ops, synth
 from oracle import roi_oracle
+from conftest import assert_close_elementwise
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -18,6 +19,7 @@ def close(got, want, rel=1e-5):
     scale = max(np.abs(want).max(), 1e-30)
     err = np.abs(got - want).max() / scale
     assert err <= rel, f"max err / max|ref| = {err:.3e}"
+    assert_close_elementwise(got, want, rtol=rel, atol_rms=rel)     # and element by element
 
 
 def random_rois(seed, B, K, H, W, scale, wild=False, sort=True):
@@ -386,9 +388,9 @@ def test_prepared_entry_points_equal_the_self_preparing_ones(shape, fused):
 
 @pytest.mark.parametrize("shape", [(2, 64, 32, 32, 1.0 / 16), (1, 64, 16, 16, 1.0 / 32), (1, 32, 25, 38, 1.0 / 16)])
 @pytest.mark.parametrize("fused", [False, True])
-def test_backward_tile_in_tensor_memory_equals_shared_memory_bitwise(shape, fused, monkeypatch):
+def test_backward_tile_in_tensor_memory_equals_shared_memory_bitwise(shape, fused):
     """The default backward keeps its gradient tile in tensor memory (tcgen05.ld / st read-modify-write);
-    CIM_ROI_BWD_TMEM=0 selects the shared-memory tile.  Same owners, same order: bit-identical, also for odd
+    cim_set_debug_flags(CIM_DBG_ROI_BWD_SMEM_TILE) selects the shared-memory tile.  Same owners, same order: bit-identical, also for odd
     map sizes (last row pair half empty, W not a multiple of 4) and the fused MaskFuse variant."""
     B, C, H, W, scale = shape
     feat = torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(51))
@@ -403,6 +405,6 @@ def test_backward_tile_in_tensor_memory_equals_shared_memory_bitwise(shape, fuse
         return gf
 
     g_tm = grad()
-    monkeypatch.setenv("CIM_ROI_BWD_TMEM", "0")
-    g_sm = grad()
+    with _lib.debug_flags(_lib.DBG_ROI_BWD_SMEM_TILE):
+        g_sm = grad()
     np.testing.assert_array_equal(g_tm, g_sm)

@@ -1,10 +1,12 @@
 #!/usr/bin/env python
 """Time cim_mask_overlap alone at cfg2 size (8 images x 2000 proposals, 512x512 masks) for the flat and the
 tiled (8 x 16 patch) pixel order, check that both give identical maps and counts, and print the fraction of
-K-blocks the tensor-core kernel visits.  CIM_OVERLAP_VARIANT selects a pipeline variant (tuning aid)."""
+K-blocks the tensor-core kernel visits.  OVERLAP_DEBUG_FLAGS=2 (this TOOL's switch, handed to cim_set_debug_flags)
+selects the loader-warp pipeline variant (tuning aid)."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from cim_b200 import mask_ops, synth
+from cim_b200 import _lib, mask_ops, synth
+_lib.lib().cim_set_debug_flags(int(os.environ.get("OVERLAP_DEBUG_FLAGS", 0)))
 n_img, R, S = int(os.environ.get("N_IMG", 8)), 2000, 512
 dev = "cuda:0"
 masks = [synth.rasterize(synth.proposal_params(R, S, 1234 + b), device=dev) for b in range(n_img)]

@@ -1,6 +1,6 @@
 import os, sys, numpy as np, torch
 sys.path.insert(0, os.getcwd())
-from cim_b200 import heads
+from cim_b200 import _lib, heads
 from oracle import heads_oracle
 dev="cuda:0"
 for D in (128, 512, 2048, 4096, 8192):
@@ -13,8 +13,7 @@ for D in (128, 512, 2048, 4096, 8192):
     want = np.stack([o[0],o[1]]+o[2]+o[3]).astype(np.float64)
     res = {}
     for mode in ("tc","ffma"):
-        os.environ["CIM_SCORE_FFMA"] = "1" if mode=="ffma" else "0"
-        with torch.no_grad():
+        with torch.no_grad(), _lib.debug_flags(_lib.DBG_SCORE_FFMA if mode == "ffma" else 0):
             s = m.forward_batched(x, 1).cpu().numpy().astype(np.float64)
         rel = np.abs(s-want)/np.abs(want)
         res[mode] = (rel.max(), rel.mean())
