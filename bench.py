@@ -40,6 +40,11 @@ WORKLOADS = {
     # name: backbone, images per GPU, proposals, classes, present classes, mask side
     "cfg2_r50_voc_8x2000": dict(backbone="resnet50", n_img=8, R=2000, C=20, present=2, mask=512),
     "cfg3_vgg16_voc_8x2000": dict(backbone="vgg16", n_img=8, R=2000, C=20, present=2, mask=512),
+    # BASELINE.json configs[2]: a batch of 64 images sharded per image over 2/4/8 GPUs (64 / N per rank; N = 1: 8)
+    "cfg3_vgg16_voc_64": dict(backbone="vgg16", n_img=8, total_images=64, R=2000, C=20, present=2, mask=512),
+    # configs[4]: HRNet-W48 COCO pseudo-label generation, forward only
+    "cfg5_hrnet48_coco_infer_8x4000": dict(backbone="hrnet48", n_img=8, R=4000, C=80, present=4, mask=128,
+                                           inference=True),
     "cfg4_r50_coco_8x2000_q": dict(backbone="resnet50", n_img=8, R=2000, C=80, present=4, mask=128),
     "cfg1_r50_voc_1x300": dict(backbone="resnet50", n_img=1, R=300, C=20, present=2, mask=512),
     "tiny": dict(backbone="resnet50", n_img=2, R=200, C=20, present=2, mask=128),
@@ -250,8 +255,8 @@ def measured_traffic(workload, stage):
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f)
-        if t.get("workload") != workload or stage not in t:
-            return None
+        if t.get("workload") != workload or stage not in t or t.get("kernel_source_sha16") != source_sha16():
+            return None                                  # no capture of THESE kernels on this workload: not a number
         return int(t[stage]["dram_read"] + t[stage]["dram_write"])
     except (OSError, ValueError, KeyError):
         return None
@@ -300,7 +305,7 @@ def time_stages(step, inp, iters=5):
                                                   P(step.grad_scores), n_img, R, step.C, step.K, step.K, 3.0, 1.0, 3.0,
                                                   1.0 / n_img, st) or
                                 L.cim_pcl_loss(P(step.scores), P(inp["mat"]), P(step.pcl_loss), P(step.grad_scores), n_img,
-                                               R, step.C + 1, 127, 1.0 / n_img, 1, st)),
+                                               R, step.C + 1, 255, 1.0 / n_img, 1, st)),
         "mine": lambda: L.cim_mine(C.byref(p), step.cls_ptrs, step.det_ptrs, P(inp["labels"]), P(step.iou),
                                    P(step.asy), P(step.gt_count), P(step.gt_rows), P(step.gt_class),
                                    P(step.gt_weight), P(step.asy_flag), P(step.mine_ws), step.mine_ws.numel(), st),
@@ -324,6 +329,255 @@ def time_stages(step, inp, iters=5):
     return out
 
 
+def source_sha16():
+    """sha256[:16] over the CUDA sources: profiles/traffic.json records the value it was captured with, so a number
+    measured on other kernels reads as stale instead of being copied into the bench line."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, "cim_b200", "csrc", "*.cu*"))):
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def timed(fn, steps, warmup, dev, cdist=None):
+    """CUDA events on the launching stream around `steps` calls, barrier + synchronize on both sides, max over ranks
+    (cdist=None: this rank alone, no barrier)."""
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if cdist is not None:
+        cdist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if cdist is None:
+        return e0.elapsed_time(e1) / steps
+    cdist.barrier()
+    return cdist.max_over_ranks(e0.elapsed_time(e1) / steps, dev)
+
+
+def stage_table(stage_ms, bytes_img, n_img, peaks):
+    table = {}
+    for name, ms in stage_ms.items():
+        gbs = bytes_img[name] * n_img / (ms * 1e-3) / 1e9
+        table[name] = dict(ms=round(ms, 4), algorithmic_mb=round(bytes_img[name] * n_img / 1e6, 2),
+                           gb_per_s=round(gbs, 1), hbm_frac=round(gbs / peaks["hbm_gbs"], 4))
+    return table
+
+
+def images_per_rank(name, cfg, world):
+    """cfg3 (BASELINE.json configs[2]) is a FIXED batch of 64 images sharded per image over 2/4/8 GPUs: 64 / N images
+    per rank (strong scaling); at N = 1 it runs the 8-GPU per-rank batch.  Every other workload is weak: its own
+    n_img per rank."""
+    if cfg.get("total_images") and world > 1:
+        return max(1, cfg["total_images"] // world)
+    return cfg["n_img"]
+
+
+def measure_training(name, cfg, args, dev, rank, world, peaks, cdist, headline):
+    """One training workload: the step in the model's dependency order (and, for the headline, in the overlapped
+    order and end to end with host inputs), the per-stage table and the roofline of its dominant stage."""
+    import torch
+    from cim_b200 import mask_ops
+    from cim_b200.step import CIMHeadStep, KERNELS_HEAD_GRADS, KERNELS_PCL, KERNELS_PER_STEP
+    cfg = dict(cfg, n_img=images_per_rank(name, cfg, world))
+    inp = build_inputs(cfg, dev, 1234 + 1000 * rank)
+    Cf, H, W, scale = inp["shape"]
+    words = inp["packed"].shape[-1]
+    step = CIMHeadStep(cfg["n_img"], cfg["R"], cfg["C"], Cf, H, W, scale, words,
+                       anti_noise_sampling=not args.no_anti_noise, device=dev, mask_kb_per_row=inp["kb_per_row"],
+                       head_grads=not args.no_head_grads, order="graph")
+    mat = None if args.no_head_grads else inp["mat"]
+    run = lambda order: step.run(inp["feat"], inp["rois"], inp["grad_out"], inp["packed"], inp["seg_x"], inp["weight"],
+                                 inp["bias"], inp["labels"], mat=mat, order=order)
+    steps, warmup = (args.steps, max(args.warmup, 3)) if headline else (max(3, min(args.steps, 10)), 3)
+    np.random.seed(3)
+    sampler = ClockSampler(dev.index or 0)
+    if headline and rank == 0:
+        sampler.start()
+    ms_graph = timed(lambda: run("graph"), steps, warmup, dev, cdist)
+    clocks = sampler.stop() if headline and rank == 0 else None
+    ms_over = timed(lambda: run("overlapped"), steps, 2, dev, cdist)
+    n_images = cfg["n_img"] * world
+    res = {"workload": name, "images_per_gpu": cfg["n_img"], "steps": steps, "warmup": warmup,
+           "ms_per_step": ms_graph, "images_per_s": n_images / (ms_graph * 1e-3),
+           "order": "graph: RoIAlign fwd -> scoring -> mining -> sampling hop -> assignment -> losses -> scoring bwd -> "
+                    "RoIAlign bwd (model_builder.py:136-204); mask maps on a side stream next to the RoIAlign forward",
+           "ms_per_step_overlapped_order": ms_over,
+           "overlapped_order_note": "round-1 order: maps, scoring and mining first, the sampling hop hidden behind the "
+                                    "RoIAlign forward; needs seg_x independent of this step's RoIAlign output",
+           "sampling_hop": "pseudo-GT counts D2H, one np.random.random_sample call, uniforms H2D, cim_anti_noise"}
+    if headline:
+        res["clocks"] = clocks
+        # end to end through the public call with HOST inputs (rois, labels, bbox-cropped bit-packed masks) and
+        # results read back to the host every step
+        crops = mask_ops.crops_from_packed_host(inp.pop("packed_flat").view(cfg["n_img"] * cfg["R"], -1), cfg["mask"],
+                                                cfg["mask"])
+        step.alloc_host_io(mask_hw=(cfg["mask"], cfg["mask"]),
+                           crop_capacity_words=int(crops.words.numel() * 1.25) + 1024)
+        step.hi_rois.copy_(inp["rois"])
+        step.hi_labels.copy_(inp["labels"])
+        step.set_host_crops(crops)
+        run_host = lambda: step.run_host(inp["feat"], inp["grad_out"], inp["seg_x"], inp["weight"], inp["bias"],
+                                         mat=mat, lag_results=True)
+        # the step runs on a HIGH-priority stream: the prefetch of the next step's inputs (H2D + the crop-unpack kernel
+        # on the step's low-priority copy stream) then only takes SMs the step's own kernels are not waiting for
+        hp = torch.cuda.Stream(device=dev, priority=-1)
+        hp.wait_stream(torch.cuda.current_stream(dev))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(hp):
+            for _ in range(3):
+                run_host()
+            step.flush_results()
+            cdist.barrier()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(steps):
+                run_host()             # reads the previous step's results on the host while this step computes
+            step.flush_results()       # ... and the last step's: every timed step's H2D, D2H and host wait are inside
+            e1.record()
+            torch.cuda.synchronize()
+        ms_e2e = cdist.max_over_ranks(e0.elapsed_time(e1) / steps, dev)
+        res["e2e"] = {"value": n_images / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
+                      "h2d_bytes_per_step": int(step.h2d_bytes + step.last_mask_h2d_bytes + step.last_uniform_bytes),
+                      "d2h_bytes_per_step": int(step.d2h_bytes),
+                      "host_inputs": "rois, labels, bbox-cropped bit-packed proposal masks (unpacked on the device), the "
+                                     "uniform doubles of the sampling hop; features/seg_x/grad_out are device-produced",
+                      "host_outputs": "per-image losses [n_img, K+1, 3], valid flags, two checksums of the RoIAlign outputs, "
+                                      "the pseudo-GT counts of the sampling hop" if not args.no_head_grads else
+                                      "pseudo labels / IoU labels / loss weights, valid flags, checksums, pseudo-GT counts",
+                      "pipelining": "H2D of step i+1 on a copy stream overlaps the kernels of step i; the results of step i "
+                                    "are copied D2H at its end and read by the host (one event wait per step) while step "
+                                    "i+1 runs; the last step's wait is inside the timed region",
+                      "order": "graph"}
+        if step.trace is not None and rank == 0:             # host timeline of the last e2e steps (CIM_STEP_TRACE=1)
+            ev = step.trace[-5 * 3:]
+            for nm, t in ev:
+                print(f"trace {nm:16s} {(t - ev[0][1]) * 1e3:8.3f} ms", file=sys.stderr)
+        res["gpu_launches"] = (KERNELS_PER_STEP + (0 if args.no_head_grads else KERNELS_HEAD_GRADS + KERNELS_PCL)) * steps
+        res["collective"] = (("none (single process)" if world == 1 else
+                              f"NCCL allreduce (avg) of the {step.head_bucket.numel() * 4} B head-gradient bucket per "
+                              "step, inside the timed region, overlapped with the RoIAlign backward")
+                             if not args.no_head_grads else "none (head gradients excluded)")
+    stages = time_stages(step, inp) if rank == 0 else None
+    cdist.barrier()
+    if rank == 0:
+        bytes_img = algorithmic_bytes(cfg, Cf, H, W)
+        if args.no_head_grads:
+            del bytes_img["score_heads_bwd"], bytes_img["head_losses"]
+        stage_ms = dict(stages)
+        stage_ms["mine_assign"] = stage_ms.pop("mine") + stage_ms.pop("assign")
+        table = stage_table(stage_ms, bytes_img, cfg["n_img"], peaks)
+        dominant = max(stage_ms, key=stage_ms.get)
+        total_bytes = sum(bytes_img.values())
+        roofline = {"kernel": dominant, "bound": "hbm", "achieved": table[dominant]["gb_per_s"],
+                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": table[dominant]["hbm_frac"],
+                    "traffic": measured_traffic(name, dominant), "peak_source": peaks["source"],
+                    "share_of_step": round(stage_ms[dominant] / sum(stage_ms.values()), 3)}
+        visited, total = visited_kblocks(step, cfg)
+        ov = {"executed_kblock_fraction": round(visited / max(total, 1), 4)}
+        if visited:
+            # a dense R x HW x R contraction of 0/1 operands (SURVEY 8d): tensor-pipe bound.  `executed` = the MMA
+            # flops actually issued (visited K-blocks x 2*128*256*128); the peak is the int8 rate measured on this
+            # chip by tools/micro/imma_peak.cu when its result is committed, else 2 x the measured bf16 burst
+            secs = stage_ms["mask_overlap"] * 1e-3
+            executed = visited * 2.0 * 128 * 256 * 128
+            peak_i8, note = int8_peak(peaks)
+            ov.update({"executed_tops": round(executed / secs / 1e12, 1), "int8_peak_tops": round(peak_i8, 1),
+                       "int8_peak_source": note, "tensor_frac": round(executed / secs / 1e12 / peak_i8, 4),
+                       "algorithmic_equivalent_tops": round(float(cfg["R"]) ** 2 * cfg["mask"] ** 2 * cfg["n_img"]
+                                                            / secs / 1e12, 1)})
+        table["mask_overlap"].update(ov)
+        if dominant == "mask_overlap" and visited:
+            roofline.update({"bound": "tensor", "achieved": ov["executed_tops"], "peak": ov["int8_peak_tops"],
+                             "unit": "TFLOP/s", "frac": ov["tensor_frac"], "peak_note": ov["int8_peak_source"]})
+        res.update({"roofline": roofline, "stages": table,
+                    "step_roofline": {"algorithmic_mb_per_image": round(total_bytes / 1e6, 1),
+                                      "hbm_frac": round(res["images_per_s"] / world * total_bytes / 1e9 / peaks["hbm_gbs"], 4)}})
+    del step, inp
+    torch.cuda.empty_cache()
+    return res
+
+
+def int8_peak(peaks):
+    """Dense int8 tensor peak of THIS chip: tools/micro/imma_peak.cu's measurement when committed
+    (profiles/imma_peak.json), else the assumption 2 x measured bf16 burst, labelled as such."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "imma_peak.json")) as f:
+            t = json.load(f)
+        return float(t["int8_tops"]), f"measured, tools/micro/imma_peak.cu ({t.get('how', '')})"
+    except (OSError, ValueError, KeyError):
+        return 2 * peaks["bf16_tflops"], "ASSUMED 2 x measured bf16 burst (no committed int8 measurement)"
+
+
+def measure_inference(name, cfg, args, dev, rank, world, peaks, cdist):
+    """BASELINE.json configs[4]: HRNet-W48 COCO pseudo-label generation, forward only (model_builder.py:209-211 returns
+    after the heads in eval mode; tools/generate_mask_for_MaskRCNN.py:124-190): RoIAlign forward, scoring heads
+    forward, K-head score mean (core/test.py:130-133) + per-class box NMS (mask_eval_utils.py:57-79)."""
+    import torch
+    from cim_b200 import _lib, postproc, synth
+    Cf, H, W, scale = synth.feature_shape(cfg["backbone"])
+    B, R, C1, K, D = cfg["n_img"], cfg["R"], cfg["C"] + 1, 3, 4096
+    L = _lib.lib()
+    P, st = _lib.ptr, _lib.stream_ptr(dev)
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    rois = torch.cat([synth.rois_from_params(synth.proposal_params(R, 512, 1234 + 1000 * rank + b), b)
+                      for b in range(B)]).to(dev)
+    feat = torch.randn(B, Cf, H, W, device=dev, generator=g)
+    out = torch.empty(B * R, Cf, 7, 7, device=dev)
+    ws = torch.empty(L.cim_roi_align_workspace_bytes_ex(B, Cf, H, W, B * R, 7, 7), dtype=torch.uint8, device=dev)
+    seg_x = torch.randn(B * R, D, device=dev, generator=g)
+    nh = 2 + 2 * K
+    weight = torch.randn(nh, C1, D, device=dev, generator=g) * 0.02
+    bias = torch.zeros(nh, C1, device=dev)
+    scores = torch.empty(nh, B * R, C1, device=dev)
+    sws = torch.empty(max(256, L.cim_score_heads_workspace_bytes(B, R, D, C1, K)), dtype=torch.uint8, device=dev)
+    boxes = rois[:, 1:].reshape(B, R, 4).contiguous()
+
+    def roi():
+        _lib.check(L.cim_roi_align_fwd(P(feat), P(rois), P(out), B, Cf, H, W, B * R, 7, 7, scale, 0, 1, P(ws),
+                                       ws.numel(), st), "roi")
+
+    def score():
+        _lib.check(L.cim_score_heads(P(seg_x), P(weight), P(bias), P(scores), B, R, D, C1, K, P(sws), sws.numel(), st),
+                   "score")
+
+    def post():
+        s = postproc.test_scores(scores, K)                       # [B*R, C]
+        postproc.box_nms_batched(boxes, s.view(B, R, -1), 1e-5, 0.3)
+
+    steps = max(3, min(args.steps, 10))
+    ms = timed(lambda: (roi(), score(), post()), steps, 3, dev, cdist)
+    res = {"workload": name, "images_per_gpu": B, "steps": steps, "warmup": 3, "ms_per_step": ms,
+           "images_per_s": B * world / (ms * 1e-3), "order": "forward only: RoIAlign fwd -> scoring fwd -> K-head mean + "
+           "per-class box NMS (80 classes x 4000 candidates with random-init scores: the NMS's worst case)"}
+    if rank == 0:
+        one = lambda fn: timed(fn, 5, 2, dev)
+        stage_ms = {"roi_align_fwd": one(roi), "score_heads": one(score), "postproc": one(post)}
+        F, O = Cf * H * W * 4, R * Cf * 49 * 4
+        bytes_img = {"roi_align_fwd": F + 20 * R + O,
+                     "score_heads": R * D * 4 + nh * C1 * (D + 1) * 4 + nh * R * C1 * 4,
+                     "postproc": nh * R * C1 * 4 // 2 + R * 16 + R * (C1 - 1) * 5}
+        table = stage_table(stage_ms, bytes_img, B, peaks)
+        dominant = max(stage_ms, key=stage_ms.get)
+        total_bytes = sum(bytes_img.values())
+        res.update({"stages": table,
+                    "roofline": {"kernel": dominant, "bound": "hbm", "achieved": table[dominant]["gb_per_s"],
+                                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": table[dominant]["hbm_frac"],
+                                 "traffic": None, "peak_source": peaks["source"]},
+                    "step_roofline": {"algorithmic_mb_per_image": round(total_bytes / 1e6, 1),
+                                      "hbm_frac": round(res["images_per_s"] / world * total_bytes / 1e9 / peaks["hbm_gbs"], 4)}})
+    cdist.barrier()
+    del out, seg_x, scores, feat
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -331,6 +585,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2_r50_voc_8x2000", choices=sorted(WORKLOADS))
+    ap.add_argument("--also", default="cfg3_vgg16_voc_64,cfg4_r50_coco_8x2000_q,cfg5_hrnet48_coco_infer_8x4000",
+                    help="comma-separated workloads measured after the headline one and reported under `workloads` "
+                         "('' for none)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-anti-noise", action="store_true")
     ap.add_argument("--no-head-grads", action="store_true",
@@ -372,7 +629,6 @@ def main():
 
     import torch
     from cim_b200 import dist as cdist
-    from cim_b200.step import CIMHeadStep, KERNELS_HEAD_GRADS, KERNELS_PCL, KERNELS_PER_STEP
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     rank, world, local = cdist.init_from_env()
@@ -380,135 +636,34 @@ def main():
     torch.cuda.set_device(dev)
     peaks = load_peaks()
 
-    inp = build_inputs(cfg, dev, 1234 + 1000 * rank)
-    Cf, H, W, scale = inp["shape"]
-    words = inp["packed"].shape[-1]
-    step = CIMHeadStep(cfg["n_img"], cfg["R"], cfg["C"], Cf, H, W, scale, words, anti_noise_sampling=not args.no_anti_noise,
-                       max_present=max(4, 2 * cfg["present"]), device=dev, mask_kb_per_row=inp["kb_per_row"],
-                       head_grads=not args.no_head_grads)
-    mat = None if args.no_head_grads else inp["mat"]
-    run = lambda: step.run(inp["feat"], inp["rois"], inp["grad_out"], inp["packed"], inp["seg_x"], inp["weight"],
-                           inp["bias"], inp["labels"], inp["labels_host"], mat=mat)
-    np.random.seed(3)
-    for _ in range(max(args.warmup, 3)):
-        run()
-    torch.cuda.synchronize()
-    cdist.barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(args.steps):
-        run()
-    e1.record()
-    torch.cuda.synchronize()
-    cdist.barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms_step = cdist.max_over_ranks(e0.elapsed_time(e1) / args.steps, dev)
-    n_images = cfg["n_img"] * world
-    value = n_images / (ms_step * 1e-3)
-
-    # end to end through the public call with HOST inputs (rois, labels, bit-packed masks) and
-    # results read back to the host every step
-    # host wire format of the proposal masks: bounding-box crops, bit-packed (mask_ops.MaskCrops)
-    from cim_b200 import mask_ops
-    crops = mask_ops.crops_from_packed_host(inp.pop("packed_flat").view(cfg["n_img"] * cfg["R"], -1), cfg["mask"],
-                                            cfg["mask"])
-    step.alloc_host_io(mask_hw=(cfg["mask"], cfg["mask"]), crop_capacity_words=int(crops.words.numel() * 1.25) + 1024)
-    step.hi_rois.copy_(inp["rois"])
-    step.hi_labels.copy_(inp["labels"])
-    step.set_host_crops(crops)
-    run_host = lambda: step.run_host(inp["feat"], inp["grad_out"], inp["seg_x"], inp["weight"], inp["bias"], mat=mat,
-                                     lag_results=True)
-    # the step runs on a HIGH-priority stream: the prefetch of the next step's inputs (H2D + the crop-unpack kernel on
-    # the step's low-priority copy stream) then only takes SMs the step's own kernels are not waiting for
-    hp = torch.cuda.Stream(device=dev, priority=-1)
-    hp.wait_stream(torch.cuda.current_stream(dev))
-    with torch.cuda.stream(hp):
-        for _ in range(3):
-            run_host()
-        step.flush_results()
-        cdist.barrier()
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(args.steps):
-            run_host()                 # reads the previous step's results on the host while this step computes
-        step.flush_results()           # ... and the last step's: every timed step's H2D, D2H and host wait are inside
-        e1.record()
-        torch.cuda.synchronize()
-    ms_e2e = cdist.max_over_ranks(e0.elapsed_time(e1) / args.steps, dev)
-    e2e_value = n_images / (ms_e2e * 1e-3)
-
-    if step.trace is not None and rank == 0:                 # host timeline of the last e2e steps (CIM_STEP_TRACE=1)
-        ev = step.trace[-5 * 3:]
-        for name, t in ev:
-            print(f"trace {name:16s} {(t - ev[0][1]) * 1e3:8.3f} ms", file=sys.stderr)
-    stages = time_stages(step, inp) if rank == 0 else None
+    head = measure_training(args.workload, cfg, args, dev, rank, world, peaks, cdist, headline=True)
+    others = {}
+    for name in [n for n in args.also.split(",") if n and n != args.workload]:
+        c = WORKLOADS[name]
+        try:
+            if c.get("inference"):
+                others[name] = measure_inference(name, c, args, dev, rank, world, peaks, cdist)
+            else:
+                others[name] = measure_training(name, c, args, dev, rank, world, peaks, cdist, headline=False)
+        except RuntimeError as exc:                              # e.g. out of memory on a smaller part: say so, go on
+            others[name] = {"workload": name, "error": str(exc)[:300]}
+            torch.cuda.empty_cache()
     cdist.barrier()
     cdist.shutdown()
     if rank != 0:
         return
 
-    bytes_img = algorithmic_bytes(cfg, Cf, H, W)
-    if args.no_head_grads:
-        del bytes_img["score_heads_bwd"], bytes_img["head_losses"]
-    stage_ms = dict(stages)
-    stage_ms["mine_assign"] = stage_ms.pop("mine") + stage_ms.pop("assign")
-    table = {}
-    for name, ms in stage_ms.items():
-        gbs = bytes_img[name] * cfg["n_img"] / (ms * 1e-3) / 1e9
-        table[name] = dict(ms=round(ms, 4), algorithmic_mb=round(bytes_img[name] * cfg["n_img"] / 1e6, 2),
-                           gb_per_s=round(gbs, 1), hbm_frac=round(gbs / peaks["hbm_gbs"], 4))
-    dominant = max(stage_ms, key=stage_ms.get)
-    total_bytes = sum(bytes_img.values())
-    roofline = {"kernel": dominant, "bound": "hbm", "achieved": table[dominant]["gb_per_s"], "peak": peaks["hbm_gbs"],
-                "unit": "GB/s", "frac": table[dominant]["hbm_frac"], "traffic": measured_traffic(args.workload, dominant),
-                "peak_source": peaks["source"],
-                "share_of_step": round(stage_ms[dominant] / sum(stage_ms.values()), 3)}
-    if dominant == "mask_overlap":
-        # a dense R x HW x R contraction of 0/1 operands: tensor-pipe bound.  Algorithmic
-        # work = the symmetric half, R^2 * HW MAC-flops per image.  The kernel sorts the masks by
-        # position and skips K-blocks where one operand block is all zero, so `achieved` counts the
-        # MMA flops actually EXECUTED (visited K-blocks x 2*128*256*128); the algorithmic-equivalent
-        # rate is given next to it.  Peak: int8 runs at twice the bf16 rate on sm_100;
-        # MEASURED_PEAKS.json only has bf16, so peak = 2 x measured bf16 (burst: kernel timed alone).
-        alg = float(cfg["R"]) ** 2 * cfg["mask"] ** 2 * cfg["n_img"]
-        visited, total = visited_kblocks(step, cfg)
-        executed = visited * 2.0 * 128 * 256 * 128
-        secs = stage_ms[dominant] * 1e-3
-        roofline.update({"bound": "tensor", "achieved": round(executed / secs / 1e12, 1),
-                         "peak": round(2 * peaks["bf16_tflops"], 1), "unit": "TFLOP/s",
-                         "frac": round(executed / secs / 1e12 / (2 * peaks["bf16_tflops"]), 4),
-                         "peak_note": "int8 = 2 x measured bf16 burst",
-                         "executed_kblock_fraction": round(visited / total, 4),
-                         "algorithmic_equivalent_tflops": round(alg / secs / 1e12, 1),
-                         "algorithmic": "R^2*HW MACs per image counted as flops (upper triangle only)"})
     result = {
-        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "metric": METRIC, "value": head["images_per_s"], "unit": "images/s", "n_gpus": world, "steps": head["steps"],
+        "warmup": head["warmup"], "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-        "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(step.h2d_bytes + step.last_mask_h2d_bytes),
-                "d2h_bytes_per_step": int(step.d2h_bytes),
-                "host_inputs": "rois, labels, bbox-cropped bit-packed proposal masks (unpacked on the device); "
-                               "features/seg_x/grad_out are device-produced",
-                "host_outputs": "per-image losses [n_img, K+1, 3], valid flags, two checksums of the RoIAlign outputs, "
-                                "plus the pseudo-GT lists of the sampling hop" if not args.no_head_grads else
-                                "pseudo labels / IoU labels / loss weights, valid flags, checksums, sampling-hop lists",
-                "pipelining": "H2D of step i+1 on a copy stream overlaps the kernels of step i; the results of step i "
-                              "are copied D2H at its end and read by the host (one event wait per step) while step "
-                              "i+1 runs its RoIAlign forward; the last step's wait is inside the timed region"},
-        "gpu_launches": (KERNELS_PER_STEP + (0 if args.no_head_grads else KERNELS_HEAD_GRADS + KERNELS_PCL)) * args.steps,
-        "collective": ("none (single process)" if world == 1 else
-                       f"NCCL allreduce (avg) of the {step.head_bucket.numel() * 4} B head-gradient bucket per step, "
-                       "inside the timed region, overlapped with the RoIAlign kernels") if not args.no_head_grads
-        else "none (head gradients excluded)",
-        "roofline": roofline,
-        "step_roofline": {"algorithmic_mb_per_image": round(total_bytes / 1e6, 1),
-                          "hbm_frac": round(value / world * total_bytes / 1e9 / peaks["hbm_gbs"], 4)},
-        "stages": table, "clocks": clocks,
+        "step_order": head["order"], "ms_per_step_graph_order": head["ms_per_step"],
+        "ms_per_step_overlapped_order": head["ms_per_step_overlapped_order"],
+        "overlapped_order_note": head["overlapped_order_note"], "sampling_hop": head["sampling_hop"],
+        "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "collective": head["collective"],
+        "roofline": head["roofline"], "step_roofline": head["step_roofline"], "stages": head["stages"],
+        "clocks": head["clocks"], "kernel_source_sha16": source_sha16(),
+        "workloads": others,
     }
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference(cfg, 1, 0, head_grads=not args.no_head_grads)

@@ -71,6 +71,8 @@ _SIGNATURES = {
     "cim_mine_workspace_bytes": (_SZ, [C.POINTER(MineParams)]),
     "cim_mine": (_I, [C.POINTER(MineParams), C.POINTER(_P), C.POINTER(_P), _P, _P, _P, _P, _P, _P, _P, _P,
                       _P, _SZ, _P]),
+    "cim_anti_noise_uniform_count_max": (_SZ, [C.POINTER(MineParams)]),
+    "cim_anti_noise": (_I, [C.POINTER(MineParams), _P, _P, _P, _P, _P, _P, _P]),
     "cim_assign": (_I, [C.POINTER(MineParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -332,6 +332,107 @@ cim_assign_kernel(cim_mine_params p, const __half *__restrict__ iou_all, const i
     }
 }
 
+
+// ------------------------------------------------------------------------------ anti-noise sampling
+// heads.py:440-473 with the arithmetic of numpy's RandomState.choice(replace=True, p=...) on the device; only the
+// uniform doubles come from the host (numpy's GLOBAL RNG, so that the stream stays in step with the reference).
+// numpy's float32 add.reduce (pairwise summation, loops_utils.h.src): n < 8 sequential from 0; n <= 128 eight
+// running sums + the rest sequentially; above that halves, the left one a multiple of 8.
+__device__ float np_pairwise_sum_f32(const float *a, int n) {
+    if (n < 8) {
+        float r = 0.f;
+        for (int i = 0; i < n; ++i) r = __fadd_rn(r, a[i]);
+        return r;
+    }
+    if (n <= 128) {
+        float r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = a[j];
+        int i = 8;
+        for (; i < n - (n % 8); i += 8)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], a[i + j]);
+        float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                              __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+        for (; i < n; ++i) res = __fadd_rn(res, a[i]);
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return __fadd_rn(np_pairwise_sum_f32(a, n2), np_pairwise_sum_f32(a + n2, n - n2));
+}
+
+// One warp per (layer, image).  For every present class c (ascending) with n > 0 pseudo GTs at list positions
+// idx[0..n): p = w[idx] / sum(w[idx]) (float32) -> float64 cumsum -> / last -> j_t = #{cdf <= u_t} for the class's n
+// uniforms; keep[idx] = 0, keep[idx[j_t]] = 1.  The uniforms of (image b, layer l, class c) follow those of every
+// earlier (image, layer) -- image-major, the order in which the reference's training loop reaches np.random.choice --
+// and of the smaller present classes of the same list.
+__global__ void __launch_bounds__(32)
+cim_anti_noise_kernel(cim_mine_params p, const float *__restrict__ labels, const int *__restrict__ gt_count,
+                      const int *__restrict__ gt_class, const float *__restrict__ gt_weight,
+                      const double *__restrict__ uniforms, unsigned char *__restrict__ gt_keep) {
+    extern __shared__ __align__(16) unsigned char an_smem[];
+    const int l = blockIdx.x, img = blockIdx.y, lane = threadIdx.x;
+    const int g = min(gt_count[l * p.n_img + img], p.gt_cap);
+    double *cdf = reinterpret_cast<double *>(an_smem);                 // [gt_cap]
+    int *idx = reinterpret_cast<int *>(cdf + p.gt_cap);                // [gt_cap]
+    float *prob = reinterpret_cast<float *>(idx + p.gt_cap);           // [gt_cap]
+    const size_t base = ((size_t)l * p.n_img + img) * p.gt_cap;
+    for (int i = lane; i < p.gt_cap; i += 32) gt_keep[base + i] = 1;
+    if (g == 0) return;
+    // first uniform of this list: lists of earlier images (all layers) and of earlier layers of this image
+    long long off = 0;
+    for (int t = lane; t < img * p.n_layers + l; t += 32) {
+        const int bb = t / p.n_layers, ll = t - bb * p.n_layers;
+        off += min(gt_count[ll * p.n_img + bb], p.gt_cap);
+    }
+#pragma unroll
+    for (int s = 16; s; s >>= 1) off += __shfl_xor_sync(0xffffffffu, off, s);
+    __syncwarp();
+    for (int c = 0; c < p.C; ++c) {
+        if (labels[(size_t)img * p.C + c] == 0.f) continue;            // warp-uniform
+        int n = 0;
+        for (int i0 = 0; i0 < g; i0 += 32) {                           // stable compaction of the class's positions
+            const int i = i0 + lane;
+            const bool hit = i < g && gt_class[base + i] == c;
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (hit) {
+                const int pos = n + __popc(m & ((1u << lane) - 1u));
+                idx[pos] = i;
+                prob[pos] = gt_weight[base + i];
+            }
+            n += __popc(m);
+        }
+        __syncwarp();
+        if (n == 0) continue;
+        if (lane == 0) {
+            const float s = np_pairwise_sum_f32(prob, n);
+            double acc = 0.0;
+            for (int i = 0; i < n; ++i) {                              // np.cumsum: sequential, float64
+                const double v = (double)__fdiv_rn(prob[i], s);
+                acc = i == 0 ? v : __dadd_rn(acc, v);
+                cdf[i] = acc;
+            }
+            const double last = cdf[n - 1];
+            for (int i = 0; i < n; ++i) cdf[i] = __ddiv_rn(cdf[i], last);
+        }
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) gt_keep[base + idx[i]] = 0;
+        __syncwarp();
+        for (int t = lane; t < n; t += 32) {
+            const double u = uniforms[off + t];
+            int lo = 0, hi = n;                                        // searchsorted(side='right'): first cdf > u
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (cdf[mid] <= u) lo = mid + 1; else hi = mid;
+            }
+            gt_keep[base + idx[min(lo, n - 1)]] = 1;
+        }
+        __syncwarp();
+        off += n;
+    }
+}
+
 int check_params(const cim_mine_params *p) {
     if (!p) return CIM_ERR_ARG;
     if (p->n_img <= 0 || p->R <= 0 || p->C <= 0 || p->n_layers <= 0 || p->gt_cap <= 0) return CIM_ERR_ARG;
@@ -409,5 +510,25 @@ CIM_API int cim_assign(const cim_mine_params *p, const void *iou_f16, const int3
     cim_assign_kernel<<<dim3((p->R + 7) / 8, p->n_layers, p->n_img), 256, 0, (cudaStream_t)stream>>>(
         *p, reinterpret_cast<const __half *>(iou_f16), gt_count, gt_rows, gt_class, gt_weight, gt_keep,
         pseudo_labels, reinterpret_cast<__half *>(pseudo_iou_f16), loss_weights, valid);
+    return cim_launch_status();
+}
+
+CIM_API size_t cim_anti_noise_uniform_count_max(const cim_mine_params *p) {
+    if (check_params(p)) return 0;
+    return (size_t)p->n_layers * p->n_img * p->gt_cap;
+}
+
+CIM_API int cim_anti_noise(const cim_mine_params *p, const float *labels, const int32_t *gt_count,
+                           const int32_t *gt_class, const float *gt_weight, const double *uniforms,
+                           uint8_t *gt_keep, cim_stream_t stream) {
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (!labels || !gt_count || !gt_class || !gt_weight || !uniforms || !gt_keep) return CIM_ERR_ARG;
+    if (!cim_aligned(uniforms, 8)) return CIM_ERR_ALIGN;
+    const size_t smem = (size_t)p->gt_cap * 16;
+    if (smem > (size_t)cim_max_smem_optin()) return CIM_ERR_SHAPE;
+    cudaFuncSetAttribute(cim_anti_noise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cim_anti_noise_kernel<<<dim3(p->n_layers, p->n_img), 32, smem, (cudaStream_t)stream>>>(
+        *p, labels, gt_count, gt_class, gt_weight, uniforms, gt_keep);
     return cim_launch_status();
 }

@@ -12,9 +12,12 @@ Mirrors lib/modeling/heads.py of the reference:
     that model_builder.py:170-187 would call instead of looping over CIM_layer objects.
 
 Anti-noise sampling (heads.py:440-473) draws from numpy's GLOBAL RandomState on the host in the
-reference.  To reproduce its pseudo labels bit for bit the same np.random.choice calls are made
-here, in the same order (image-major, then layer, then ascending class), between the two device
-phases; that costs one small device->host->device hop per step.
+reference.  To reproduce its pseudo labels bit for bit the same uniform doubles are drawn here from
+the same global stream (one random_sample call per step, the reference's order: image-major, then
+layer, then ascending class) between the two device phases, and cim_anti_noise restates
+RandomState.choice's arithmetic on the device; that costs one small device->host->device hop per
+step (the pseudo-GT counts down, the uniforms up).  _anti_noise_keep is the host restatement of the
+same draw the tests compare the kernel with.
 """
 import ctypes as C
 
@@ -133,6 +136,29 @@ def _anti_noise_keep(gt_cls, gt_w, present):
     return keep
 
 
+def draw_uniforms(counts):
+    """The host half of the sampling hop: ONE np.random.random_sample(T) call from numpy's GLOBAL RandomState with
+    T = total number of pseudo GTs.  The reference calls np.random.choice(idx, size=n, p=...) once per (image, layer,
+    present class) (heads.py:459); each of those consumes exactly n doubles of the stream (mtrand.pyx: uniform =
+    random_sample(n)), n summing to T over the step, so one call of T doubles leaves the global stream where the
+    reference leaves it and hands out the same numbers in the same order (tests/test_host_logic.py)."""
+    return np.random.random_sample(int(counts.sum()))
+
+
+def anti_noise_device(p, labels, gt_count, gt_class, gt_weight, gt_keep, stream=None):
+    """Anti-noise sampling (heads.py:440-473) with only the random numbers coming from the host: read the pseudo-GT
+    counts (sync point; the reference syncs per class, heads.py:453,457), draw the uniforms, run cim_anti_noise."""
+    dev = gt_count.device
+    counts = gt_count.cpu().numpy()
+    u = draw_uniforms(np.minimum(counts, p.gt_cap))
+    uni = torch.from_numpy(u if u.size else np.zeros(1)).to(dev)
+    rc = _lib.lib().cim_anti_noise(C.byref(p), _lib.ptr(labels), _lib.ptr(gt_count), _lib.ptr(gt_class),
+                                   _lib.ptr(gt_weight), _lib.ptr(uni), _lib.ptr(gt_keep),
+                                   stream if stream is not None else _lib.stream_ptr(dev))
+    _lib.check(rc, "cim_anti_noise")
+    return gt_keep
+
+
 def mine_and_assign(cls_scores, det_scores, labels, iou_map, asy_iou_map, cls_thr, iou_thr, p_seed=0.1,
                     con_thr=0.85, anti_noise_sampling=True, using_cim=True):
     """All images x all refinement layers of CIM_layer.forward in two device phases.
@@ -198,20 +224,8 @@ def mine_and_assign(cls_scores, det_scores, labels, iou_map, asy_iou_map, cls_th
 
         gt_keep = None
         if anti_noise_sampling:
-            counts = gt_count.cpu().numpy()                      # sync point (heads.py:453,457 sync too)
-            cap = int(counts.max()) if counts.size else 0
-            keep_host = np.ones((n_layers, n_img, R), dtype=np.uint8)
-            if cap > 0:
-                cls_h = gt_class[:, :, :cap].cpu().numpy()
-                w_h = gt_weight[:, :, :cap].cpu().numpy()
-                lab_h = labels.cpu().numpy()
-                for b in range(n_img):                            # the reference runs image by image,
-                    present = np.nonzero(lab_h[b])[0]             # layer by layer (model_builder.py:170)
-                    for l in range(n_layers):
-                        g = int(counts[l, b])
-                        if g:
-                            keep_host[l, b, :g] = _anti_noise_keep(cls_h[l, b, :g], w_h[l, b, :g], present)
-            gt_keep = torch.from_numpy(keep_host).to(dev, non_blocking=False)
+            gt_keep = torch.empty((n_layers, n_img, R), dtype=torch.uint8, device=dev)
+            anti_noise_device(p, labels, gt_count, gt_class, gt_weight, gt_keep)
 
         pseudo_labels = torch.empty((n_layers, n_img, R, n_cls + 1), dtype=torch.float32, device=dev)
         pseudo_iou = torch.empty((n_layers, n_img, R), dtype=torch.float16, device=dev)
@@ -337,11 +351,20 @@ class PCLLossFunction(Function):
         return (grad.view(n_img, R, -1) * g.view(n_img, 1, 1)).view_as(grad), None, None, None
 
 
-def PCL_loss(predict_cls, mat, labels=None, n_img=1, max_id=128):
+#: cluster ids cim_pcl_loss accepts (its per-row id lists hold 8-bit ids); CIMHeadStep passes the same constant
+PCL_MAX_ID = 255
+
+
+def PCL_loss(predict_cls, mat, labels=None, n_img=1, max_id=PCL_MAX_ID, strict=False):
     """heads.PCL_loss(predict_cls, mat, labels) (heads.py:10-41; `labels` only supplied the device there).
     n_img = 1 returns a 0-d loss like the reference; n_img > 1 (predict_cls [n_img*R, C+1], mat [n_img, R, C+1])
-    returns one loss per image."""
+    returns one loss per image.  A cluster matrix the kernel cannot take (an id above max_id, a non-integer id, more
+    than four distinct ids in a row, two background ids -- the reference asserts on the last) gives a NaN loss and a
+    zero gradient for that image; strict=True turns that into a RuntimeError (one host sync)."""
     loss = PCLLossFunction.apply(predict_cls, mat, n_img, max_id)
+    if strict and bool(torch.isnan(loss.detach()).any()):
+        raise RuntimeError("cim_pcl_loss: cluster matrix outside what the kernel supports (ids must be integers in "
+                           f"[0, {max_id}], at most 4 distinct ids per row, one background id), or NaN scores")
     return loss[0] if n_img == 1 else loss
 
 

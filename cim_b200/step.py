@@ -28,11 +28,26 @@ import torch
 
 from . import _lib
 from . import dist as cdist
-from .heads import _anti_noise_keep
+from .heads import PCL_MAX_ID, draw_uniforms
+
+
+class _nvtx:
+    """NVTX range around a stage of the step (shows up in nsys / ncu --nvtx timelines of the REAL step)."""
+    __slots__ = ("name",)
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        torch.cuda.nvtx.range_pop()
+        return False
 
 #: kernels (not memsets / copies) libcimhead launches in one run(): roi_align prep 1 + fwd 2 + bwd 2,
-#: mask area + sort + overlap + 2 un-permutes = 5, scoring 3, mining 3, assignment 1
-KERNELS_PER_STEP = 17
+#: mask area + sort + overlap + 2 un-permutes = 5, scoring 3, mining 3, anti-noise sampling 1, assignment 1
+KERNELS_PER_STEP = 18
 #: + with head_grads: loss block (fwd + bwd), detector dot, activation backward, bias, W^T split, grad_x GEMM,
 #: grad_W GEMM, reduce
 KERNELS_HEAD_GRADS = 8
@@ -43,8 +58,8 @@ KERNELS_PCL = 1
 class CIMHeadStep:
     def __init__(self, n_img, n_props, n_classes, feat_channels, feat_h, feat_w, spatial_scale, mask_words,
                  feat_dim=4096, refine_times=3, p_seed=0.1, step_rate=0.1, con_thr=0.85, anti_noise_sampling=True,
-                 max_present=4, device="cuda:0", sampling_ratio=0, aligned=True, mask_kb_per_row=0,
-                 head_grads=False):
+                 max_present=None, device="cuda:0", sampling_ratio=0, aligned=True, mask_kb_per_row=0,
+                 head_grads=False, order="graph"):
         self.dev = torch.device(device)
         self.n_img, self.R, self.C, self.K = n_img, n_props, n_classes, refine_times
         self.Cf, self.H, self.W, self.scale = feat_channels, feat_h, feat_w, float(spatial_scale)
@@ -54,6 +69,7 @@ class CIMHeadStep:
         self.kb_per_row = int(mask_kb_per_row)
         self.sr, self.aligned = int(sampling_ratio), int(bool(aligned))
         self.anti = anti_noise_sampling
+        self.order = order
         self.L = _lib.lib()
         R, C1, nh, k = n_props, n_classes + 1, 2 + 2 * refine_times, refine_times
         dev = self.dev
@@ -86,11 +102,9 @@ class CIMHeadStep:
             p.n_img, p.R, p.C, p.C1, p.n_layers = n_img, R, n_classes, C1, k
             p.det_cols, p.mode = C1, 0
             p.keep_count = int(np.ceil(p_seed * R))                 # heads.py:332
-            # host side of the sampling hop: at most max_present * keep_count pseudo GTs per (layer, image).  With the
-            # hop the device lists get exactly that capacity (+ 1 slot, so that an overflow is seen and not silently
-            # clamped): the lists then cross PCIe as plain contiguous copies, no strided slice to stage first
-            self.cap = min(R, max_present * p.keep_count)
-            gcap = min(R, self.cap + 1) if anti_noise_sampling else R
+            # the pseudo-GT lists stay on the device (the sampling runs there, cim_anti_noise), so they get the full
+            # capacity R: no overflow whatever the number of present classes (max_present is accepted and ignored)
+            gcap = R
             p.gt_cap = gcap
             p.big_thr = float(np.float32(0.9 * R))                  # heads.py:338
             p.con_thr = con_thr
@@ -110,10 +124,11 @@ class CIMHeadStep:
             self.valid = e((k, n_img), torch.uint8)
         pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
         self.h_count = pin((k, n_img), torch.int32)
-        self.h_class = pin((k, n_img, gcap), torch.int32)
-        self.h_weight = pin((k, n_img, gcap), torch.float32)
-        self.h_keep = pin((k, n_img, gcap), torch.uint8)
+        self.h_uniform = pin((k * n_img * gcap,), torch.float64)       # one double per pseudo GT at most
+        with torch.cuda.device(dev):
+            self.d_uniform = e((k * n_img * gcap,), torch.float64)
         self.ev = torch.cuda.Event()
+        self.last_uniform_bytes = 0
         self.side = torch.cuda.Stream(device=self.dev, priority=-2)     # scoring GEMM next to the overlap helpers: above the step
         self.trace = [] if os.environ.get("CIM_STEP_TRACE") else None
         # layer l reads (cls, det) = (predict_cls, predict_det) for l = 0, else (ref_cls[l-1], ref_iou[l-1])
@@ -125,103 +140,144 @@ class CIMHeadStep:
         self.det_ptrs = PtrArr(*[t.data_ptr() for t in det_src])
 
     # -------------------------------------------------------------------------------------
-    def run(self, feat, rois, grad_out, packed_masks, seg_x, weight, bias, labels, labels_host, grad_scores=None,
-            mat=None, mid_hook=None):
+    def run(self, feat, rois, grad_out, packed_masks, seg_x, weight, bias, labels, labels_host=None, grad_scores=None,
+            mat=None, mid_hook=None, order=None):
         """feat [n_img,Cf,H,W] f32, rois [n_img*R,5] f32 grouped by image, grad_out [n_img*R,Cf,7,7]
         f32, packed_masks [n_img,R,words] i32, seg_x [n_img*R,D] f32, weight [2+2K,C+1,D],
-        bias [2+2K,C+1], labels [n_img,C] f32 (+ the same on the host as a numpy array).
+        bias [2+2K,C+1], labels [n_img,C] f32 (labels_host is no longer needed: the sampling runs on the device).
         Results land in self.roi_out, grad_feat, iou, asy, scores, pseudo_labels, pseudo_iou,
         loss_weights, valid.  With head_grads=True also losses [n_img, K+1, 3], grad_scores (the loss
         block's backward; pass grad_scores to supply dL/dscores yourself instead), grad_seg_x, grad_weight,
         grad_bias; in a multi-process run the head-gradient bucket is averaged over the ranks (one NCCL
         allreduce, overlapped with the RoIAlign backward).  mat [n_img, R, C+1] (the dataset's proposal-cluster
         matrix, model_builder.py:125,203) adds PCL_loss: pcl_loss [n_img] and its gradient on the classifier head.
-        Order: mask maps, scores, mining | host sampling hop, hidden behind the RoIAlign forward | assignment,
-        losses, scoring backward, [allreduce ||] RoIAlign backward."""
+
+        order (default: the constructor's):
+          "graph"      the model's dependency order (model_builder.py:136-204): RoIAlign forward -> scoring heads ->
+                       mining -> sampling hop -> assignment -> losses -> scoring backward -> RoIAlign backward.  In
+                       the real graph seg_x = Box_Head(RoIAlign output) feeds the heads, so nothing of the step can
+                       hide the hop; the mask maps (which depend on the proposals only) run on the side stream next to
+                       the RoIAlign forward and the scoring GEMM.
+          "overlapped" mask maps, scoring and mining first, the RoIAlign forward launched BEFORE the host waits for
+                       the mining result, so the hop hides behind it.  Only possible when seg_x does not depend on
+                       this step's RoIAlign output (a bench with synthetic seg_x; features cached from an earlier
+                       pass)."""
         L, p, dev = self.L, self.p, self.dev
         P, n_img, R, k = _lib.ptr, self.n_img, self.R, self.K
+        order = order or self.order
+        if order not in ("graph", "overlapped"):
+            raise ValueError("order must be 'graph' or 'overlapped'")
         tr = self.trace                                         # host timeline (CIM_STEP_TRACE=1), else None
         if tr is not None:
             tr.append(("run", time.perf_counter()))
         st = _lib.stream_ptr(dev)
+        side_st = C.c_void_p(self.side.cuda_stream)
         ck = _lib.check
-        # the scoring GEMM (independent of the maps) runs on a side stream next to the overlap stage, whose small
-        # serial helpers (mask sort: 8 CTAs, tile order: 1 CTA) leave most of the GPU idle
         cur = torch.cuda.current_stream(dev)
-        self.side.wait_stream(cur)
-        ck(L.cim_score_heads(P(seg_x), P(weight), P(bias), P(self.scores), n_img, R, self.D, self.C + 1, k,
-                             P(self.score_ws), self.score_ws.numel(), C.c_void_p(self.side.cuda_stream)),
-           "cim_score_heads")
-        # RoI descriptors once per step (forward and backward see the same rois), also off the critical path
-        ck(L.cim_roi_align_prepare(P(rois), n_img, self.Cf, self.H, self.W, n_img * R, 7, 7, self.scale, self.sr,
-                                   self.aligned, P(self.roi_ws), self.roi_ws.numel(),
-                                   C.c_void_p(self.side.cuda_stream)), "cim_roi_align_prepare")
         pcl_early = self.head_grads and grad_scores is None and mat is not None
-        if pcl_early:
-            # PCL_loss (model_builder.py:203) needs predict_cls and the cluster matrix only: 8 CTAs of pure latency
-            # that fit next to the overlap stage as well; its gradient is added to head 0's after the loss block
-            ck(L.cim_pcl_loss(P(self.scores), P(mat), P(self.pcl_loss), P(self.pcl_grad), n_img, R, self.C + 1, 127,
-                              1.0 / n_img, 0, C.c_void_p(self.side.cuda_stream)), "cim_pcl_loss")
-        ck(L.cim_mask_overlap_ex(P(packed_masks), n_img, R, self.words, self.kb_per_row, None, P(self.area),
-                                 P(self.iou), P(self.asy), P(self.overlap_ws), self.overlap_ws.numel(), 0, st),
-           "cim_mask_overlap_ex")
-        cur.wait_stream(self.side)
-        ck(L.cim_mine(C.byref(p), self.cls_ptrs, self.det_ptrs, P(labels), P(self.iou), P(self.asy),
-                      P(self.gt_count), P(self.gt_rows), P(self.gt_class), P(self.gt_weight), P(self.asy_flag),
-                      P(self.mine_ws), self.mine_ws.numel(), st), "cim_mine")
-        if self.anti:
-            self.h_count.copy_(self.gt_count, non_blocking=True)
-            self.h_class.copy_(self.gt_class, non_blocking=True)
-            self.h_weight.copy_(self.gt_weight, non_blocking=True)
-            self.ev.record(torch.cuda.current_stream(dev))
-        ck(L.cim_roi_align_fwd_prepared(P(feat), P(rois), None, P(self.roi_out), n_img, self.Cf, self.H, self.W,
-                                        n_img * R, 7, 7, self.scale, self.sr, self.aligned, P(self.roi_ws),
-                                        self.roi_ws.numel(), st), "cim_roi_align_fwd")
+
+        def score_fwd(stream):
+            with _nvtx("cim/score_heads"):
+                ck(L.cim_score_heads(P(seg_x), P(weight), P(bias), P(self.scores), n_img, R, self.D, self.C + 1, k,
+                                     P(self.score_ws), self.score_ws.numel(), stream), "cim_score_heads")
+                if pcl_early:
+                    # PCL_loss (model_builder.py:203) needs predict_cls and the cluster matrix only: 8 CTAs of pure
+                    # latency; its gradient is added to head 0's after the loss block
+                    ck(L.cim_pcl_loss(P(self.scores), P(mat), P(self.pcl_loss), P(self.pcl_grad), n_img, R,
+                                      self.C + 1, PCL_MAX_ID, 1.0 / n_img, 0, stream), "cim_pcl_loss")
+
+        def overlap(stream):
+            with _nvtx("cim/mask_overlap"):
+                ck(L.cim_mask_overlap_ex(P(packed_masks), n_img, R, self.words, self.kb_per_row, None, P(self.area),
+                                         P(self.iou), P(self.asy), P(self.overlap_ws), self.overlap_ws.numel(), 0,
+                                         stream), "cim_mask_overlap_ex")
+
+        def roi_fwd():
+            with _nvtx("cim/roi_align_fwd"):
+                ck(L.cim_roi_align_fwd_prepared(P(feat), P(rois), None, P(self.roi_out), n_img, self.Cf, self.H,
+                                                self.W, n_img * R, 7, 7, self.scale, self.sr, self.aligned,
+                                                P(self.roi_ws), self.roi_ws.numel(), st), "cim_roi_align_fwd")
+
+        def mine():
+            with _nvtx("cim/mine"):
+                ck(L.cim_mine(C.byref(p), self.cls_ptrs, self.det_ptrs, P(labels), P(self.iou), P(self.asy),
+                              P(self.gt_count), P(self.gt_rows), P(self.gt_class), P(self.gt_weight),
+                              P(self.asy_flag), P(self.mine_ws), self.mine_ws.numel(), st), "cim_mine")
+                if self.anti:
+                    self.h_count.copy_(self.gt_count, non_blocking=True)
+                    self.ev.record(cur)
+
+        self.side.wait_stream(cur)
+        if order == "graph":
+            # the mask maps depend on the proposals only: side stream, next to the RoIAlign forward + scoring GEMM
+            overlap(side_st)
+            with _nvtx("cim/roi_prepare"):
+                ck(L.cim_roi_align_prepare(P(rois), n_img, self.Cf, self.H, self.W, n_img * R, 7, 7, self.scale,
+                                           self.sr, self.aligned, P(self.roi_ws), self.roi_ws.numel(), st),
+                   "cim_roi_align_prepare")
+            roi_fwd()
+            score_fwd(st)
+            cur.wait_stream(self.side)
+            mine()
+        else:
+            # the scoring GEMM (independent of the maps) runs on a side stream next to the overlap stage, whose small
+            # serial helpers leave most of the GPU idle; RoI descriptors once per step, also off the critical path
+            score_fwd(side_st)
+            ck(L.cim_roi_align_prepare(P(rois), n_img, self.Cf, self.H, self.W, n_img * R, 7, 7, self.scale, self.sr,
+                                       self.aligned, P(self.roi_ws), self.roi_ws.numel(), side_st),
+               "cim_roi_align_prepare")
+            overlap(st)
+            cur.wait_stream(self.side)
+            mine()
+            roi_fwd()
         if mid_hook is not None:
-            mid_hook()                                          # host work that should hide behind the RoIAlign forward
+            mid_hook()                                          # host work that should hide behind the kernels in flight
         keep = None
         if tr is not None:
             tr.append(("launched_phase1", time.perf_counter()))
         if self.anti:
-            self.ev.synchronize()                               # mining is done; RoIAlign still runs
-            if tr is not None:
-                tr.append(("mining_done", time.perf_counter()))
-            counts = self.h_count.numpy()
-            cls_h, w_h, keep_h = self.h_class.numpy(), self.h_weight.numpy(), self.h_keep.numpy()
-            keep_h[:] = 1
-            for b in range(n_img):                              # reference order: image, layer, class
-                present = np.nonzero(labels_host[b])[0]
-                for l in range(k):
-                    g = int(counts[l, b])
-                    if g > self.cap:
-                        raise RuntimeError("more pseudo GTs than max_present * keep_count; raise max_present")
-                    if g:
-                        keep_h[l, b, :g] = _anti_noise_keep(cls_h[l, b, :g], w_h[l, b, :g], present)
-            self.gt_keep.copy_(self.h_keep, non_blocking=True)
+            # the sampling hop: pseudo-GT counts down (K * n_img ints), one random_sample call from numpy's global
+            # RNG (heads.draw_uniforms), the uniforms up, cim_anti_noise on the device
+            with _nvtx("cim/sampling_hop"):
+                self.ev.synchronize()                           # mining is done
+                if tr is not None:
+                    tr.append(("mining_done", time.perf_counter()))
+                u = draw_uniforms(self.h_count.numpy())
+                self.last_uniform_bytes = int(u.size) * 8
+                if u.size:
+                    self.h_uniform.numpy()[:u.size] = u
+                    self.d_uniform[:u.size].copy_(self.h_uniform[:u.size], non_blocking=True)
+                ck(L.cim_anti_noise(C.byref(p), P(labels), P(self.gt_count), P(self.gt_class), P(self.gt_weight),
+                                    P(self.d_uniform), P(self.gt_keep), st), "cim_anti_noise")
             keep = self.gt_keep
             if tr is not None:
                 tr.append(("sampled", time.perf_counter()))
-        ck(L.cim_assign(C.byref(p), P(self.iou), P(self.gt_count), P(self.gt_rows), P(self.gt_class),
-                        P(self.gt_weight), P(keep), P(self.pseudo_labels), P(self.pseudo_iou),
-                        P(self.loss_weights), P(self.valid), st), "cim_assign")
+        with _nvtx("cim/assign"):
+            ck(L.cim_assign(C.byref(p), P(self.iou), P(self.gt_count), P(self.gt_rows), P(self.gt_class),
+                            P(self.gt_weight), P(keep), P(self.pseudo_labels), P(self.pseudo_iou),
+                            P(self.loss_weights), P(self.valid), st), "cim_assign")
         reduce_work = None
         if self.head_grads:
             if grad_scores is None:
                 # losses forward + backward (model_builder.py:170-202): total of an image = sum_l cls + 3 iou + bag
                 # + mil_bag; the batch loss is the mean over this rank's images
-                ck(L.cim_head_losses(P(self.scores), P(self.pseudo_labels), P(self.pseudo_iou), P(self.loss_weights),
-                                     P(self.valid), P(labels), P(self.losses), P(self.grad_scores), n_img, R, self.C,
-                                     k, k, 3.0, 1.0, 3.0, 1.0 / n_img, st), "cim_head_losses")
-                if pcl_early:                                        # + PCL_loss on predict_cls
-                    self.grad_scores[0].add_(self.pcl_grad)
+                with _nvtx("cim/head_losses"):
+                    ck(L.cim_head_losses(P(self.scores), P(self.pseudo_labels), P(self.pseudo_iou),
+                                         P(self.loss_weights), P(self.valid), P(labels), P(self.losses),
+                                         P(self.grad_scores), n_img, R, self.C, k, k, 3.0, 1.0, 3.0, 1.0 / n_img, st),
+                       "cim_head_losses")
+                    if pcl_early:                                    # + PCL_loss on predict_cls
+                        self.grad_scores[0].add_(self.pcl_grad)
                 grad_scores = self.grad_scores
-            ck(L.cim_score_heads_bwd(P(seg_x), P(weight), P(self.scores), P(grad_scores), P(self.grad_seg_x),
-                                     P(self.grad_weight), P(self.grad_bias), n_img, R, self.D, self.C + 1, k,
-                                     P(self.score_bwd_ws), self.score_bwd_ws.numel(), st), "cim_score_heads_bwd")
-            reduce_work = cdist.allreduce_mean_async_(self.head_bucket)         # overlaps the RoIAlign backward
-        ck(L.cim_roi_align_bwd_prepared(P(grad_out), P(rois), None, P(self.grad_feat), n_img, self.Cf, self.H, self.W,
-                                        n_img * R, 7, 7, self.scale, self.sr, self.aligned, P(self.roi_ws),
-                                        self.roi_ws.numel(), st), "cim_roi_align_bwd")
+            with _nvtx("cim/score_heads_bwd"):
+                ck(L.cim_score_heads_bwd(P(seg_x), P(weight), P(self.scores), P(grad_scores), P(self.grad_seg_x),
+                                         P(self.grad_weight), P(self.grad_bias), n_img, R, self.D, self.C + 1, k,
+                                         P(self.score_bwd_ws), self.score_bwd_ws.numel(), st), "cim_score_heads_bwd")
+                reduce_work = cdist.allreduce_mean_async_(self.head_bucket)     # overlaps the RoIAlign backward
+        with _nvtx("cim/roi_align_bwd"):
+            ck(L.cim_roi_align_bwd_prepared(P(grad_out), P(rois), None, P(self.grad_feat), n_img, self.Cf, self.H,
+                                            self.W, n_img * R, 7, 7, self.scale, self.sr, self.aligned,
+                                            P(self.roi_ws), self.roi_ws.numel(), st), "cim_roi_align_bwd")
         if reduce_work is not None:
             reduce_work()                                       # current stream waits for the allreduce
         if tr is not None:
@@ -279,8 +335,8 @@ class CIMHeadStep:
         if not self.crop_cap:
             self.h2d_bytes += self.hi_masks.numel() * 4
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in results + (self.ho_checksum,))
-        self.d2h_bytes += sum(t.numel() * t.element_size() for t in (self.h_count, self.h_class, self.h_weight))
-        self.h2d_bytes += self.h_keep.numel()
+        # the sampling hop: pseudo-GT counts down, one double per pseudo GT up (self.last_uniform_bytes, set by run())
+        self.d2h_bytes += self.h_count.numel() * 4
         self._slot = 0
         self._staged = False
         self.res_ev = torch.cuda.Event()
@@ -303,7 +359,6 @@ class CIMHeadStep:
         into the idle device buffer, on the copy stream.  Call it for step i+1 before (or while)
         step i computes; run_host() consumes the staged buffer."""
         buf = self.di[self._slot ^ 1] if self._staged else self.di[self._slot]
-        buf["labels_host"] = self.hi_labels.numpy().copy()    # the sampling hop needs them on the host
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(buf["free"])          # its previous consumer has finished
             buf["rois"].copy_(self.hi_rois, non_blocking=True)
@@ -357,7 +412,7 @@ class CIMHeadStep:
             self.stage_host_inputs()                           # goes to the other buffer
         cur_stream.wait_event(buf["ready"])
         self.run(feat, buf["rois"], grad_out, buf["masks"], seg_x, weight, bias, buf["labels"],
-                 buf["labels_host"], grad_scores=grad_scores, mat=mat,
+                 None, grad_scores=grad_scores, mat=mat,
                  mid_hook=self._collect_results if lag_results else None)
         buf["free"].record(cur_stream)
         self.d_checksum[0] = self.roi_out.view(-1)[::4099].sum()

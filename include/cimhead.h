@@ -266,6 +266,20 @@ int cim_mine(const cim_mine_params *p, const float *const *cls, const float *con
              const float *labels /* [n_img, C] */, const void *iou_f16, const void *asy_f16,
              int32_t *gt_count, int32_t *gt_rows, int32_t *gt_class, float *gt_weight,
              uint8_t *asy_flag, void *workspace, size_t workspace_bytes, cim_stream_t stream);
+/* Anti-noise sampling between the phases ON THE DEVICE (heads.py:440-473): per (layer, image) list and present class,
+ * np.random.choice(class_idx, size=n, replace=True, p=w / w.sum()) with numpy's arithmetic restated bit for bit
+ * (float32 pairwise sum, float32 p, float64 cumsum normalised by its last element, searchsorted side='right'); the
+ * drawn pseudo GTs keep gt_keep = 1, the other pseudo GTs of the class get 0.  `uniforms` are the doubles the host
+ * drew from numpy's GLOBAL RandomState with ONE np.random.random_sample(T) call, T = sum of gt_count: the call
+ * consumes the same stream as the reference's per-class calls, in the reference's order (image, then layer, then
+ * ascending class, then position), which is the order the kernel reads them in.  So the host hop shrinks to: read
+ * gt_count (n_layers * n_img ints), draw T doubles, copy them over -- the lists themselves never leave the device.
+ * gt_keep [L, n_img, gt_cap] is fully written.  (choice()'s argument checks -- negative / NaN p -- are not
+ * reproduced: the weights are products of softmax outputs.) */
+size_t cim_anti_noise_uniform_count_max(const cim_mine_params *p);   /* L * n_img * gt_cap */
+int cim_anti_noise(const cim_mine_params *p, const float *labels /* [n_img, C] */, const int32_t *gt_count,
+                   const int32_t *gt_class, const float *gt_weight, const double *uniforms, uint8_t *gt_keep,
+                   cim_stream_t stream);
 int cim_assign(const cim_mine_params *p, const void *iou_f16,
                const int32_t *gt_count, const int32_t *gt_rows, const int32_t *gt_class,
                const float *gt_weight, const uint8_t *gt_keep /* may be NULL = keep all */,

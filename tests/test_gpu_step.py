@@ -137,6 +137,34 @@ def _small_problem(seed=11):
                 bias=bias)
 
 
+def test_graph_order_and_overlapped_order_give_identical_results():
+    """order="graph" (the model's dependency order, model_builder.py:136-204) and order="overlapped" (round 1's:
+    the sampling hop hidden behind the RoIAlign forward) run the same kernels on the same data: every output is
+    bit-identical, and both leave numpy's global RNG in the same state."""
+    pr = _small_problem(21)
+    kb = pr["size"] // 16 if mask_ops.tiled_ok(pr["size"], pr["size"]) else 0
+    outs, states = [], []
+    mat = torch.stack([synth.cluster_mat(pr["R"], pr["C"], np.nonzero(pr["labels"][b].numpy())[0], 4, 5 + b)
+                       for b in range(pr["n_img"])]).to(DEV)
+    for order in ("graph", "overlapped"):
+        step = CIMHeadStep(pr["n_img"], pr["R"], pr["C"], pr["Cf"], pr["H"], pr["W"], 1.0 / 16, pr["packed"].shape[-1],
+                           feat_dim=pr["D"], device=DEV, mask_kb_per_row=kb, head_grads=True, order=order)
+        np.random.seed(3)
+        for _ in range(2):
+            step.run(pr["feat"], pr["rois"].to(DEV), pr["grad_out"], pr["packed"], pr["seg_x"], pr["weight"],
+                     pr["bias"], pr["labels"].to(DEV), mat=mat)
+        torch.cuda.synchronize()
+        states.append(np.random.get_state()[1].copy())
+        outs.append([t.clone() for t in (step.roi_out, step.grad_feat, step.iou.view(torch.int16),
+                                         step.asy.view(torch.int16), step.scores, step.pseudo_labels,
+                                         step.pseudo_iou.view(torch.int16), step.loss_weights, step.valid, step.losses,
+                                         step.grad_seg_x, step.grad_weight, step.grad_bias, step.gt_keep)])
+        assert int(step.gt_count.sum()) > 0
+    assert np.array_equal(states[0], states[1])
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("lag", [False, True])
 def test_run_host_equals_run_and_lagged_results_arrive_one_call_later(lag):
     """run_host() (host rois / labels / packed masks, results read back) gives what run() gives on the same inputs;

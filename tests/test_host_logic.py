@@ -85,6 +85,41 @@ def test_anti_noise_draw_equals_numpy_choice_on_many_cases():
         assert state_a[1] == state_b[1] and np.array_equal(state_a[0], state_b[0]), case
 
 
+def test_one_random_sample_call_is_the_stream_of_the_per_class_choice_calls():
+    """heads.draw_uniforms: ONE random_sample(T) call hands out the doubles the reference's per-(image, layer, class)
+    np.random.choice calls consume, in the same order, and leaves the global RNG in the same state; with those doubles
+    the device algorithm (restated here: float32 p, float64 cumsum / last, searchsorted right) picks what choice picks."""
+    rng = np.random.RandomState(23)
+    lists = []
+    for _ in range(12):                                        # (image, layer) lists in the reference's order
+        g = int(rng.choice([0, 1, 5, 60, 300]))
+        lists.append((rng.randint(0, 3, g), np.maximum(rng.rand(g).astype(np.float32) ** 3, np.float32(1e-20))))
+    present = np.array([0, 1, 2])
+    np.random.seed(11)
+    want = [heads._anti_noise_keep(c, w, present) for c, w in lists]
+    state_want = np.random.get_state()
+    np.random.seed(11)
+    u = heads.draw_uniforms(np.array([len(c) for c, _ in lists]))
+    state_got = np.random.get_state()
+    assert state_want[2] == state_got[2] and np.array_equal(state_want[1], state_got[1])
+    off = 0
+    for (cls, w), keep_want in zip(lists, want):
+        keep = np.ones(len(cls), np.uint8)
+        for c in present:
+            idx = np.nonzero(cls == c)[0]
+            if len(idx) == 0:
+                continue
+            p = w[idx] / w[idx].sum()
+            cdf = p.astype(np.float64).cumsum()
+            cdf /= cdf[-1]
+            drawn = idx[np.searchsorted(cdf, u[off:off + len(idx)], side="right")]
+            off += len(idx)
+            keep[idx] = 0
+            keep[drawn] = 1
+        assert keep.tolist() == keep_want.tolist()
+    assert off == len(u)
+
+
 def test_host_evaluated_parameters():
     for r in (64, 300, 2000, 4000, 257):
         assert int(np.ceil(0.1 * r)) == {64: 7, 300: 30, 2000: 200, 4000: 400, 257: 26}[r]

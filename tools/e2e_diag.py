@@ -13,7 +13,7 @@ dev = torch.device("cuda:0")
 inp = bench.build_inputs(cfg, dev, 1234)
 Cf, H, W, scale = inp["shape"]
 step = CIMHeadStep(cfg["n_img"], cfg["R"], cfg["C"], Cf, H, W, scale, inp["packed"].shape[-1],
-                   max_present=max(4, 2 * cfg["present"]), device=dev, mask_kb_per_row=inp["kb_per_row"], head_grads=True)
+                   device=dev, mask_kb_per_row=inp["kb_per_row"], head_grads=True)
 crops = mask_ops.crops_from_packed_host(inp.pop("packed_flat").view(cfg["n_img"] * cfg["R"], -1), cfg["mask"], cfg["mask"])
 step.alloc_host_io(mask_hw=(cfg["mask"], cfg["mask"]), crop_capacity_words=int(crops.words.numel() * 1.25) + 1024)
 step.hi_rois.copy_(inp["rois"]); step.hi_labels.copy_(inp["labels"]); step.set_host_crops(crops)
@@ -35,7 +35,7 @@ def timed(fn, n=10, flush=None):
 
 np.random.seed(3)
 run = lambda: step.run(inp["feat"], inp["rois"], inp["grad_out"], inp["packed"], inp["seg_x"], inp["weight"], inp["bias"],
-                       inp["labels"], inp["labels_host"], mat=mat)
+                       inp["labels"], mat=mat)
 hp = torch.cuda.Stream(device=dev, priority=-1)
 print(f"run() default stream          {timed(run):.3f} ms")
 with torch.cuda.stream(hp):
@@ -46,7 +46,7 @@ with torch.cuda.stream(hp):
     print(f"run_host lag, no prefetch     {timed(lambda: host(lag_results=True, prefetch_next=False), flush=step.flush_results):.3f} ms")
     # no crop unpack: full packed masks over PCIe instead
     step2 = CIMHeadStep(cfg["n_img"], cfg["R"], cfg["C"], Cf, H, W, scale, inp["packed"].shape[-1],
-                        max_present=max(4, 2 * cfg["present"]), device=dev, mask_kb_per_row=inp["kb_per_row"], head_grads=True)
+                        device=dev, mask_kb_per_row=inp["kb_per_row"], head_grads=True)
     step2.alloc_host_io()
     step2.hi_rois.copy_(inp["rois"]); step2.hi_labels.copy_(inp["labels"]); step2.hi_masks.copy_(inp["packed"].cpu())
     host2 = lambda: step2.run_host(inp["feat"], inp["grad_out"], inp["seg_x"], inp["weight"], inp["bias"], mat=mat, lag_results=True)
