@@ -38,6 +38,7 @@ _SIGNATURES = {
     "cim_error_string": (C.c_char_p, [_I]),
     "cim_set_debug_flags": (None, [C.c_uint]),
     "cim_get_debug_flags": (C.c_uint, []),
+    "cim_debug_roi_window_plan": (_I, [_P, _I, _I, _I, _I, _F, _I, _I, _P, _P, _I, _P, _P]),
     "cim_roi_align_workspace_bytes": (_SZ, [_I]),
     "cim_roi_align_workspace_bytes_ex": (_SZ, [_I, _I, _I, _I, _I, _I, _I]),
     "cim_roi_align_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P, _SZ, _P]),

@@ -61,6 +61,10 @@ constexpr int WS_HDR_BYTES = 256;   // word 0: "rois not grouped by image" flag
 constexpr int CH = 32;              // channels per tile (= lanes)
 constexpr int STAGE_FLOATS = CH * NBIN;          // 1568 floats = 6272 B
 
+}  // namespace
+#include "roi_window.cuh"
+namespace {
+
 struct RoiWs {
     int *hdr;          // [64]
     int *img_start;    // [B+1]
@@ -489,6 +493,174 @@ roi_align_fwd_tile_kernel(const float *__restrict__ feat, const int *__restrict_
     if (elect_one()) bulk_wait_read<0>();
 }
 
+// ------------------------------------------------------------------------- window tiles: forward
+// Window (b, oy, ox) x 32 channels of the map -> the row-pair interleaved smem tile (rows beyond H: zero).
+__device__ __forceinline__ void load_window(float *tile, const float *__restrict__ src /* (b, c0) plane */, int H, int W,
+                                            int oy, int ox, int wh, int ww, int pitch, int tid, int nthr) {
+    const size_t HW = (size_t)H * W;
+    const int area = wh * ww;
+    if (((W | ox | ww) & 3) == 0) {
+        const int q = ww >> 2, n4 = CH * wh * q;
+        for (int e = tid; e < n4; e += nthr) {
+            const int c = e / (wh * q), rem = e - c * wh * q, y = rem / q, x = (rem - y * q) << 2;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (oy + y < H) v = __ldg(reinterpret_cast<const float4 *>(src + c * HW + (size_t)(oy + y) * W + ox + x));
+            float *dst = tile + c * pitch + tile_off(y, x, ww);
+            dst[0] = v.x; dst[2] = v.y; dst[4] = v.z; dst[6] = v.w;
+        }
+    } else {
+        for (int e = tid; e < CH * area; e += nthr) {
+            const int c = e / area, rem = e - c * area, y = rem / ww, x = rem - y * ww;
+            tile[c * pitch + tile_off(y, x, ww)] = oy + y < H ? __ldg(src + c * HW + (size_t)(oy + y) * W + ox + x) : 0.f;
+        }
+    }
+}
+
+// bucket (image * NW + window) that holds sorted position s: the last k with bucket[k] <= s
+__device__ __forceinline__ int win_find_bucket(const int *__restrict__ bucket, int lo, int hi, int s) {
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(bucket + mid) <= s) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// Epilogue of a sub-ROI that is NOT the whole ROI: sum the virtual outputs (slots) of each bin and write the bins this
+// sub-ROI owns.  stage_c: this lane's 49 virtual outputs [row slot][column slot]; lane = channel.
+__device__ __forceinline__ void win_store_partial(float *stage_c, const int *d, float *__restrict__ out_c,
+                                                  const float *__restrict__ mask, float *__restrict__ out2_c) {
+    const unsigned ym = (unsigned)d[DW_YMAP], xm = (unsigned)d[DW_XMAP];
+    const int ny = (ym >> 28) & 7, nx = (xm >> 28) & 7;
+    for (int ys = 0; ys < ny; ++ys) {                       // column slots of one bin -> its first slot
+        int first = 0;
+        for (int xs = 1; xs < nx; ++xs) {
+            if (((xm >> (4 * xs)) & 15u) == ((xm >> (4 * (xs - 1))) & 15u)) stage_c[ys * PW + first] += stage_c[ys * PW + xs];
+            else first = xs;
+        }
+    }
+    int firsty = 0;
+    for (int ys = 1; ys < ny; ++ys) {                       // row slots of one bin -> its first slot
+        if (((ym >> (4 * ys)) & 15u) == ((ym >> (4 * (ys - 1))) & 15u)) {
+            for (int xs = 0; xs < nx; ++xs) stage_c[firsty * PW + xs] += stage_c[ys * PW + xs];
+        } else firsty = ys;
+    }
+    for (int ys = 0; ys < ny; ++ys) {
+        const int by = (ym >> (4 * ys)) & 15;
+        if (ys > 0 && (int)((ym >> (4 * (ys - 1))) & 15u) == by) continue;
+        for (int xs = 0; xs < nx; ++xs) {
+            const int bx = (xm >> (4 * xs)) & 15;
+            if (xs > 0 && (int)((xm >> (4 * (xs - 1))) & 15u) == bx) continue;
+            const float v = stage_c[ys * PW + xs];
+            out_c[by * PW + bx] = v;
+            if (mask) out2_c[by * PW + bx] = v * __ldg(mask + by * PW + bx);
+        }
+    }
+}
+
+// Forward over WINDOW tiles (roi_window.cuh): units = (sub-ROI, channel chunk) in the order image -> chunk -> window ->
+// sub-ROI, split evenly over the persistent CTAs; per (window, chunk) segment the CTA stages the window in shared
+// memory and its warps sweep the segment's sub-ROIs with the same fwd_pairs as the whole-map tile kernel.
+__global__ void __launch_bounds__(FWD_MAX_WARPS * 32, 1)
+roi_align_fwd_win_kernel(const float *__restrict__ feat, const int *__restrict__ bucket, const int *__restrict__ descs,
+                         const float *__restrict__ mask7, float *__restrict__ out, int B, int C, int H, int W,
+                         WinGeom g, int pitch, int wyd_floats) {
+    extern __shared__ __align__(128) float smem[];
+    const int nw = blockDim.x >> 5;
+    float *tile = smem;
+    float *stage = smem + (size_t)CH * pitch;                                    // [nw][1568]
+    int *dslots = reinterpret_cast<int *>(stage + (size_t)nw * STAGE_FLOATS);   // [nw][2][DESC_WORDS]
+    float *wyds = reinterpret_cast<float *>(dslots + (size_t)nw * 2 * DESC_WORDS);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nchunks = C / CH, NW = g.nwy * g.nwx;
+    const size_t HW = (size_t)H * W;
+    const long long U = (long long)nchunks * __ldg(bucket + B * NW);
+    long long u = U * blockIdx.x / gridDim.x;
+    const long long u_end = U * (blockIdx.x + 1) / gridDim.x;
+    float *stage_w = stage + warp * STAGE_FLOATS;
+    float *stage_c = stage_w + lane * NBIN;
+    int *my_slots = dslots + warp * 2 * DESC_WORDS;
+    float *my_wyd = wyds + (size_t)warp * wyd_floats;
+
+    auto prefetch = [&](int pos, int slot) {
+        const int *src = descs + (size_t)pos * DESC_WORDS;
+        int *dst = my_slots + slot * DESC_WORDS;
+        cp_async16(dst + lane * 4, src + lane * 4);
+        if (lane < DESC_WORDS / 4 - 32) cp_async16(dst + (32 + lane) * 4, src + (32 + lane) * 4);
+        cp_async_commit();
+    };
+
+    int b = 0;
+    while (u < u_end) {
+        while (b < B && (long long)nchunks * __ldg(bucket + (b + 1) * NW) <= u) ++b;
+        const int ib0 = __ldg(bucket + b * NW), nit = __ldg(bucket + (b + 1) * NW) - ib0;
+        const long long base = (long long)nchunks * ib0;
+        const int ch = (int)((u - base) / nit);
+        const int s0 = ib0 + (int)((u - base) - (long long)ch * nit);          // sorted position of the first unit
+        const int k = win_find_bucket(bucket, b * NW, (b + 1) * NW, s0);
+        const int s1 = (int)min((long long)__ldg(bucket + k + 1), s0 + (u_end - u));
+        const int wy = (k - b * NW) / g.nwx, wx = (k - b * NW) - wy * g.nwx;
+        const int oy = win_origin(wy, g.Hp, g.wh), ox = win_origin(wx, W, g.ww);
+        const int c0 = ch * CH;
+
+        int r = s0 + warp, slot = 0;
+        if (r < s1) prefetch(r, 0);            // overlaps the window load below
+        __syncthreads();                       // everyone is done with the previous window
+        load_window(tile, feat + ((size_t)b * C + c0) * HW, H, W, oy, ox, g.wh, g.ww, pitch, tid, blockDim.x);
+        __syncthreads();
+        const float *tile_c = tile + lane * pitch;
+        while (r < s1) {
+            const int rn = r + nw;
+            if (rn < s1) { prefetch(rn, slot ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+            __syncwarp();
+            const int *d = my_slots + slot * DESC_WORDS;
+            const int roi = d[DW_ROI];
+            build_wyd<false>(my_wyd, d, lane);
+            const float4 *wyd4 = reinterpret_cast<const float4 *>(my_wyd);
+            switch (d[D_TX]) {
+                case 2: fwd_pairs<2, false>(tile_c, g.ww, C, d, stage_c, wyd4, lane); break;
+                case 3: fwd_pairs<3, false>(tile_c, g.ww, C, d, stage_c, wyd4, lane); break;
+                case 4: fwd_pairs<4, false>(tile_c, g.ww, C, d, stage_c, wyd4, lane); break;
+                case 6: fwd_pairs<6, false>(tile_c, g.ww, C, d, stage_c, wyd4, lane); break;
+                default: fwd_pairs<8, false>(tile_c, g.ww, C, d, stage_c, wyd4, lane); break;
+            }
+            const size_t orow = mask7 ? (size_t)roi * 2 * C : (size_t)roi * C;
+            if (d[DW_FLAGS] & 1) {             // the sub-ROI is the whole ROI: one bulk store, as on the whole-map path
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (elect_one()) {
+                    bulk_s2g(out + (orow + c0) * NBIN, stage_w, STAGE_FLOATS * 4);
+                    bulk_commit();
+                }
+                if (mask7) {
+                    float m[NBIN];
+                    const float *mp = mask7 + (size_t)roi * NBIN;
+#pragma unroll
+                    for (int i = 0; i < NBIN; ++i) m[i] = __ldg(mp + i);
+                    if (elect_one()) bulk_wait_read<0>();
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < NBIN; ++i) stage_c[i] *= m[i];
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (elect_one()) {
+                        bulk_s2g(out + (orow + C + c0) * NBIN, stage_w, STAGE_FLOATS * 4);
+                        bulk_commit();
+                    }
+                }
+            } else {
+                win_store_partial(stage_c, d, out + (orow + c0 + lane) * NBIN,
+                                  mask7 ? mask7 + (size_t)roi * NBIN : nullptr, out + (orow + C + c0 + lane) * NBIN);
+            }
+            __syncwarp();                      // slot is re-filled two iterations from now
+            slot ^= 1;
+            r = rn;
+        }
+        u += s1 - s0;
+    }
+    if (elect_one()) bulk_wait_read<0>();
+}
+
 // ----------------------------------------------------------------------------- tile: backward
 constexpr int NWB_DEFAULT = 16;     // consumer warps of the backward CTA; warp w owns row pairs
                                     // {y : (y >> 1) % 16 == w}  (D_OWN is computed for exactly this map)
@@ -530,12 +702,18 @@ __device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sy
 // region, pair p of the warp at columns 2 W (p / NW) ..): the x pass becomes tcgen05.ld / FFMA2 / tcgen05.st.
 // tools/micro/tmem_rmw.cu: this read-modify-write pattern runs at 98 B/clk/SM in tensor memory against the 64 B/clk
 // of shared memory (128 B/clk port, read + write), and the port stays free for the y pass.
-template <int T, bool XINC, bool FUSED, int NW, bool TM = false>
+// WIN (window tiles, roi_window.cuh): the descriptor's 7 x 7 "bins" are SLOTS of a sub-ROI; slot (ys, xs) takes the
+// gradient of bin (ymap[ys], xmap[xs]) of the ROI, and only the first nx column slots exist.
+template <int T, bool XINC, bool FUSED, int NW, bool TM = false, bool WIN = false>
 __device__ __forceinline__ void bwd_pairs(float *__restrict__ tile_c, int W, const int *d,
                                           const float *__restrict__ g, const float *__restrict__ m, int warp, int y0,
                                           int y1, uint32_t tmem_w = 0) {
-    float wx[PW][T];
+    constexpr bool WREG = !WIN || T <= 4;               // WIN: wide slots read their column weights from the descriptor
+    float wx[PW][WREG ? T : 1];
     int xo[PW];
+    // WIN: nibble s of ymap / xmap = bin of slot s (kept packed: the kernel sits at its register limit)
+    const unsigned ymap = WIN ? (unsigned)d[DW_YMAP] : 0u, xmap = WIN ? (unsigned)d[DW_XMAP] : 0u;
+    const int nx = WIN ? (int)((xmap >> 28) & 7u) : PW;
     const float *dwx = reinterpret_cast<const float *>(d + D_WX);
     const float *dwy = reinterpret_cast<const float *>(d + D_WY);
     const unsigned char *phr = reinterpret_cast<const unsigned char *>(d + D_PHR);
@@ -543,15 +721,18 @@ __device__ __forceinline__ void bwd_pairs(float *__restrict__ tile_c, int W, con
         int4 a = *reinterpret_cast<const int4 *>(d + D_XLO), b = *reinterpret_cast<const int4 *>(d + D_XLO + 4);
         xo[0] = a.x; xo[1] = a.y; xo[2] = a.z; xo[3] = a.w; xo[4] = b.x; xo[5] = b.y; xo[6] = b.z;
     }
+    if (WREG) {
 #pragma unroll
-    for (int pw = 0; pw < PW; ++pw) {
-        float4 a = *reinterpret_cast<const float4 *>(dwx + pw * MAXT);
-        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (T > 4) b = *reinterpret_cast<const float4 *>(dwx + pw * MAXT + 4);
-        float t8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        for (int pw = 0; pw < PW; ++pw) {
+            float4 a = *reinterpret_cast<const float4 *>(dwx + pw * MAXT);
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (T > 4) b = *reinterpret_cast<const float4 *>(dwx + pw * MAXT + 4);
+            float t8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-        for (int l = 0; l < T; ++l) wx[pw][l] = t8[l];
+            for (int l = 0; l < (WREG ? T : 1); ++l) wx[pw][l] = t8[l];
+        }
     }
+#define WXV(pw, l) (WREG ? wx[pw][WREG ? (l) : 0] : dwx[(pw) * MAXT + (l)])
     float2 *tile2 = reinterpret_cast<float2 *>(tile_c);
     const int pb = y0 >> 1, p1 = (y1 + 1) >> 1;
     // first owned pair >= pb: pairs p with p % NW == warp
@@ -567,11 +748,13 @@ __device__ __forceinline__ void bwd_pairs(float *__restrict__ tile_c, int W, con
         for (int ph = code & 15; ph < ph_end; ++ph) {
             const int dd = 2 * p - d[D_YLO + ph];    // window index of row 2p, in [-1, yn): padded weights
             const float2 w = make_float2(dwy[ph * WYP + dd + 1], dwy[ph * WYP + dd + 2]);
-            const float *gp = g + ph * PW;
+            const int phb = WIN ? (int)((ymap >> (4 * ph)) & 7u) : ph;
+            const float *gp = g + phb * PW;
 #pragma unroll
             for (int pw = 0; pw < PW; ++pw) {
-                float gv = gp[pw];
-                if (FUSED) gv = fmaf(gp[STAGE_FLOATS + pw], m[ph * PW + pw], gv);
+                const int pwb = WIN ? (int)((xmap >> (4 * pw)) & 7u) : pw;     // (unused slots: any valid column)
+                float gv = gp[pwb];
+                if (FUSED) gv = fmaf(gp[STAGE_FLOATS + pwb], m[phb * PW + pwb], gv);
                 r[pw] = __ffma2_rn(bcast2(gv), w, r[pw]);
             }
         }
@@ -582,23 +765,26 @@ __device__ __forceinline__ void bwd_pairs(float *__restrict__ tile_c, int W, con
                 for (int l = 0; l < T; ++l) {
                     float2 v[PW];
 #pragma unroll
-                    for (int pw = 0; pw < PW; ++pw) v[pw] = tm_ld2(trow + 2u * (uint32_t)(xo[pw] + l));
+                    for (int pw = 0; pw < PW; ++pw)
+                        if (!WIN || pw < nx) v[pw] = tm_ld2(trow + 2u * (uint32_t)(xo[pw] + l));
                     tm_wait_ld();
 #pragma unroll
                     for (int pw = 0; pw < PW; ++pw)
-                        tm_st2(trow + 2u * (uint32_t)(xo[pw] + l), __ffma2_rn(bcast2(wx[pw][l]), r[pw], v[pw]));
+                        if (!WIN || pw < nx)
+                            tm_st2(trow + 2u * (uint32_t)(xo[pw] + l), __ffma2_rn(bcast2(WXV(pw, l)), r[pw], v[pw]));
                     tm_wait_st();                       // the next l (and the next ROI) may read these columns
                 }
             } else {
 #pragma unroll
                 for (int pw = 0; pw < PW; ++pw) {
+                    if (WIN && pw >= nx) break;
                     float2 v[T];
 #pragma unroll
                     for (int l = 0; l < T; ++l) v[l] = tm_ld2(trow + 2u * (uint32_t)(xo[pw] + l));
                     tm_wait_ld();
 #pragma unroll
                     for (int l = 0; l < T; ++l)
-                        tm_st2(trow + 2u * (uint32_t)(xo[pw] + l), __ffma2_rn(bcast2(wx[pw][l]), r[pw], v[l]));
+                        tm_st2(trow + 2u * (uint32_t)(xo[pw] + l), __ffma2_rn(bcast2(WXV(pw, l)), r[pw], v[l]));
                     tm_wait_st();                       // the next bin may alias these columns
                 }
             }
@@ -612,20 +798,23 @@ __device__ __forceinline__ void bwd_pairs(float *__restrict__ tile_c, int W, con
             for (int l = 0; l < T; ++l) {
                 float2 v[PW];
 #pragma unroll
-                for (int pw = 0; pw < PW; ++pw) v[pw] = row[xo[pw] + l];
+                for (int pw = 0; pw < PW; ++pw)
+                    if (!WIN || pw < nx) v[pw] = row[xo[pw] + l];
 #pragma unroll
-                for (int pw = 0; pw < PW; ++pw) row[xo[pw] + l] = __ffma2_rn(bcast2(wx[pw][l]), r[pw], v[pw]);
+                for (int pw = 0; pw < PW; ++pw)
+                    if (!WIN || pw < nx) row[xo[pw] + l] = __ffma2_rn(bcast2(WXV(pw, l)), r[pw], v[pw]);
             }
         } else {
             // windows may coincide (tiny ROIs): bins strictly in program order; the T taps of one bin
             // are distinct columns
 #pragma unroll
             for (int pw = 0; pw < PW; ++pw) {
+                if (WIN && pw >= nx) break;
                 float2 v[T];
 #pragma unroll
                 for (int l = 0; l < T; ++l) v[l] = row[xo[pw] + l];
 #pragma unroll
-                for (int l = 0; l < T; ++l) row[xo[pw] + l] = __ffma2_rn(bcast2(wx[pw][l]), r[pw], v[l]);
+                for (int l = 0; l < T; ++l) row[xo[pw] + l] = __ffma2_rn(bcast2(WXV(pw, l)), r[pw], v[l]);
                 asm volatile("" ::: "memory");          // the next bin may alias these columns
             }
         }
@@ -661,12 +850,17 @@ __device__ __forceinline__ void red_add4(float *gptr, float a, float b, float c,
 // g[c] + g[C + c] * mask[roi].  Both gradient blocks and the (padded) mask of a ROI travel in the ring slot;
 // mask7 points at the PADDED masks [K][MASK_PAD] in the workspace.
 // TM: the gradient tile is kept in tensor memory (see bwd_pairs); shared memory then only holds the ring.
-template <bool FUSED, int NWB, bool TM>
+// WIN (window tiles, roi_window.cuh): the tile is a wg.wh x wg.ww WINDOW of the map; img_start is the bucket table
+// [B * NW + 1] of the sorted sub-ROI descriptors `descs`, the segments are (image, chunk, window, sub-ROI range), a
+// sub-ROI's gradient block is its ROI's (descriptor word DW_ROI), and the tile is added to its window of grad_feat
+// (windows overlap, so on this path the order of the global additions is not fixed).
+template <bool FUSED, int NWB, bool TM, bool WIN = false>
 __global__ void __launch_bounds__(NWB * 32, 1)
 roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restrict__ hdr,
                           const int *__restrict__ img_start, const int *__restrict__ descs,
-                          const float *__restrict__ mask7, float *__restrict__ grad_feat, int B, int C, int H, int W,
-                          int pitch) {
+                          const float *__restrict__ mask7, float *__restrict__ grad_feat, int B, int C, int Hmap, int Wmap,
+                          int pitch, WinGeom wg = WinGeom()) {
+    const int H = WIN ? wg.wh : Hmap, W = WIN ? wg.ww : Wmap;          // tile rows / columns
     constexpr int NBR = (FUSED ? NBR_F : ::NBR) * (TM ? NBR_TM_MUL : 1);   // ROIs per slot
     constexpr int NS = (FUSED ? NS_F : ::NS) + (TM ? NS_TM_EXTRA : 0);   // ring slots (TM: the tile's smem is free)
     constexpr int GSTRIDE = FUSED ? 2 * STAGE_FLOATS : STAGE_FLOATS;      // gradient floats per ROI in a slot
@@ -678,10 +872,11 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
     __shared__ uint32_t tmem_slot;
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)NS * SLOT_FLOATS);
     uint64_t *empty = full + NS;
-    if (__ldg(hdr) != 0) return;              // rois not grouped by image: the generic kernel does it all
+    if (!WIN && __ldg(hdr) != 0) return;      // rois not grouped by image: the generic kernel does it all
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int HW = H * W, nchunks = C / CH;
+    const int HW = Hmap * Wmap, nchunks = C / CH;
+    const int NWIN = WIN ? wg.nwy * wg.nwx : 1;
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWB); }
         fence_mbar_init();
@@ -701,13 +896,14 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
     const uint32_t tmem_cols_w = (uint32_t)(npw * W * 2);
     const uint32_t tmem_w = TM ? tmem_slot + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(warp >> 2) * tmem_cols_w : 0u;
 
-    const int s0 = __ldg(img_start), sB = __ldg(img_start + B);
+    const int s0 = __ldg(img_start), sB = __ldg(img_start + B * NWIN);
     const long long U = (long long)nchunks * (sB - s0);
     // Even split of the units only if a CTA's share covers the largest tile (then a tile is shared by
     // at most two CTAs and the merge is order-independent); otherwise whole tiles, round-robin.
     int maxroi = 0;
-    for (int i = 0; i < B; ++i) maxroi = max(maxroi, __ldg(img_start + i + 1) - __ldg(img_start + i));
-    const bool split = U / gridDim.x >= maxroi;
+    if (!WIN)
+        for (int i = 0; i < B; ++i) maxroi = max(maxroi, __ldg(img_start + i + 1) - __ldg(img_start + i));
+    const bool split = WIN || U / gridDim.x >= maxroi;
     long long u = split ? U * blockIdx.x / gridDim.x : 0;
     const long long u_end = split ? U * (blockIdx.x + 1) / gridDim.x : 0;
     int tile_id = blockIdx.x;                 // whole-tile mode: tiles blockIdx.x, + gridDim.x, ...
@@ -715,9 +911,24 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
     int gb = 0;                               // batches consumed so far (all segments): slot / phase bookkeeping
     int issued = 0;                           // batches issued so far (producer thread only)
     int b = 0;
+    int oy = 0, ox = 0;                       // WIN: origin of the segment's window
     while (true) {
         int is, nroi, ch, r0, r1;
-        if (split) {
+        if (WIN) {
+            if (u >= u_end) break;
+            while (b < B && (long long)nchunks * (__ldg(img_start + (b + 1) * NWIN) - s0) <= u) ++b;
+            const int ib0 = __ldg(img_start + b * NWIN), nit = __ldg(img_start + (b + 1) * NWIN) - ib0;
+            const long long base = (long long)nchunks * (ib0 - s0);
+            ch = (int)((u - base) / nit);
+            const int p0 = ib0 + (int)((u - base) - (long long)ch * nit);        // sorted position of the first unit
+            const int k = win_find_bucket(img_start, b * NWIN, (b + 1) * NWIN, p0);
+            const int p1 = (int)min((long long)__ldg(img_start + k + 1), p0 + (u_end - u));
+            const int wy = (k - b * NWIN) / wg.nwx, wx = (k - b * NWIN) - wy * wg.nwx;
+            oy = win_origin(wy, wg.Hp, wg.wh);
+            ox = win_origin(wx, Wmap, wg.ww);
+            is = 0; r0 = p0; r1 = p1; nroi = p1 - p0;                             // "ROIs" = sorted positions
+            u += p1 - p0;
+        } else if (split) {
             if (u >= u_end) break;
             while (b < B && (long long)nchunks * (__ldg(img_start + b + 1) - s0) <= u) ++b;
             is = __ldg(img_start + b);
@@ -764,14 +975,28 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
                 float *slot = ring + (size_t)s * SLOT_FLOATS;
                 const int first = (issued - gb0) * NBR, cnt = min(NBR, n - first);
                 mbar_expect_tx(&full[s], (uint32_t)cnt * (GSTRIDE + DESC_WORDS + (FUSED ? MASK_PAD : 0)) * 4);
-                for (int j = 0; j < cnt; ++j) {
-                    const float *src = grad_out + ((size_t)(first_roi + first + j) * Cg + c0) * NBIN;
-                    bulk_g2s(slot + j * GSTRIDE, src, STAGE_FLOATS * 4, &full[s]);
-                    if (FUSED) bulk_g2s(slot + j * GSTRIDE + STAGE_FLOATS, src + (size_t)C * NBIN, STAGE_FLOATS * 4, &full[s]);
+                int rois_j[NBR];
+                if (WIN) {                    // the ROI of each sub-ROI: word DW_ROI of its descriptor (loads in flight together)
+#pragma unroll
+                    for (int j = 0; j < NBR; ++j)
+                        rois_j[j] = j < cnt ? __ldg(descs + (size_t)(first_roi + first + j) * DESC_WORDS + DW_ROI) : 0;
+                }
+#pragma unroll
+                for (int j = 0; j < NBR; ++j) {
+                    if (j < cnt) {
+                        const int roi = WIN ? rois_j[j] : first_roi + first + j;
+                        const float *src = grad_out + ((size_t)roi * Cg + c0) * NBIN;
+                        bulk_g2s(slot + j * GSTRIDE, src, STAGE_FLOATS * 4, &full[s]);
+                        if (FUSED)
+                            bulk_g2s(slot + j * GSTRIDE + STAGE_FLOATS, src + (size_t)C * NBIN, STAGE_FLOATS * 4, &full[s]);
+                        if (FUSED && WIN)
+                            bulk_g2s(slot + NBR * (GSTRIDE + DESC_WORDS) + j * MASK_PAD, mask7 + (size_t)roi * MASK_PAD,
+                                     MASK_PAD * 4, &full[s]);
+                    }
                 }
                 bulk_g2s(slot + NBR * GSTRIDE, descs + (size_t)(first_roi + first) * DESC_WORDS,
                          (uint32_t)cnt * DESC_WORDS * 4, &full[s]);
-                if (FUSED)
+                if (FUSED && !WIN)
                     bulk_g2s(slot + NBR * (GSTRIDE + DESC_WORDS), mask7 + (size_t)(first_roi + first) * MASK_PAD,
                              (uint32_t)cnt * MASK_PAD * 4, &full[s]);
                 ++issued;
@@ -791,7 +1016,7 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
             if (lane < cnt) {
                 const int2 ff = *reinterpret_cast<const int2 *>(dbase + lane * DESC_WORDS + D_XINC);   // (xinc, own)
                 const int own = NWB == 16 ? ff.y : (ff.y | (ff.y >> 8));       // D_OWN: bit (pair & 15)
-                mine = ((own >> warp) & 1) != 0 && dbase[lane * DESC_WORDS + D_FLAGX] == 0;
+                mine = ((own >> warp) & 1) != 0 && dbase[lane * DESC_WORDS + D_FLAGX] == 0;   // (WIN: always 0)
             }
             unsigned todo = __ballot_sync(0xffffffffu, mine);
             while (todo) {
@@ -805,19 +1030,19 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
                 const int T = d[D_TX];
                 if (d[D_XINC]) {
                     switch (T) {
-                        case 2: bwd_pairs<2, true, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
-                        case 3: bwd_pairs<3, true, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
-                        case 4: bwd_pairs<4, true, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
-                        case 6: bwd_pairs<6, true, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
-                        default: bwd_pairs<8, true, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
+                        case 2: bwd_pairs<2, true, FUSED, NWB, TM, WIN>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
+                        case 3: bwd_pairs<3, true, FUSED, NWB, TM, WIN>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
+                        case 4: bwd_pairs<4, true, FUSED, NWB, TM, WIN>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
+                        case 6: bwd_pairs<6, true, FUSED, NWB, TM, WIN>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
+                        default: bwd_pairs<8, true, FUSED, NWB, TM, WIN>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
                     }
                 } else {
                     switch (T) {
-                        case 2: bwd_pairs<2, false, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
-                        case 3: bwd_pairs<3, false, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
-                        case 4: bwd_pairs<4, false, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
-                        case 6: bwd_pairs<6, false, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
-                        default: bwd_pairs<8, false, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
+                        case 2: bwd_pairs<2, false, FUSED, NWB, TM, WIN>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
+                        case 3: bwd_pairs<3, false, FUSED, NWB, TM, WIN>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
+                        case 4: bwd_pairs<4, false, FUSED, NWB, TM, WIN>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
+                        case 6: bwd_pairs<6, false, FUSED, NWB, TM, WIN>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
+                        default: bwd_pairs<8, false, FUSED, NWB, TM, WIN>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
                     }
                 }
             }
@@ -828,7 +1053,49 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
 
         // tile -> grad_feat (+=): the slab is zero or holds the other CTA's partial sum
         float *dst = grad_feat + ((size_t)b * C + c0) * HW;
-        if (TM) {
+        if (WIN) {
+            // the window's rows [oy, oy + H) x columns [ox, ox + W) of the map; rows beyond the map are padding
+            float *dl = dst + (size_t)lane * HW + (size_t)oy * Wmap + ox;
+            const bool v4 = ((Wmap | ox | W) & 3) == 0;
+            for (int pl = 0; pl < npw; ++pl) {
+                const int pp = warp + NWB * pl, y = 2 * pp;
+                if (y >= H || oy + y >= Hmap) break;
+                const bool row1 = oy + y + 1 < Hmap;
+                if (TM) {
+                    const uint32_t trow = tmem_w + (uint32_t)(pl * W) * 2u;
+                    if (v4) {
+                        for (int x = 0; x < W; x += 4) {
+                            uint32_t v[8];
+                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]),
+                                           "=r"(v[6]), "=r"(v[7])
+                                         : "r"(trow + 2u * (uint32_t)x)
+                                         : "memory");
+                            tm_wait_ld();
+                            red_add4(dl + (size_t)y * Wmap + x, __uint_as_float(v[0]), __uint_as_float(v[2]),
+                                     __uint_as_float(v[4]), __uint_as_float(v[6]));
+                            if (row1)
+                                red_add4(dl + (size_t)(y + 1) * Wmap + x, __uint_as_float(v[1]), __uint_as_float(v[3]),
+                                         __uint_as_float(v[5]), __uint_as_float(v[7]));
+                        }
+                    } else {
+                        for (int x = 0; x < W; ++x) {
+                            const float2 v = tm_ld2(trow + 2u * (uint32_t)x);
+                            tm_wait_ld();
+                            atomicAdd(dl + (size_t)y * Wmap + x, v.x);
+                            if (row1) atomicAdd(dl + (size_t)(y + 1) * Wmap + x, v.y);
+                        }
+                    }
+                } else {
+                    const float2 *row = reinterpret_cast<const float2 *>(tile_c) + pp * W;
+                    for (int x = 0; x < W; ++x) {
+                        const float2 v = row[x];
+                        atomicAdd(dl + (size_t)y * Wmap + x, v.x);
+                        if (row1) atomicAdd(dl + (size_t)(y + 1) * Wmap + x, v.y);
+                    }
+                }
+            }
+        } else if (TM) {
             // every warp drains its own row pairs: lane = channel, 8 columns = 4 x-positions x (row 2p, row 2p+1)
             float *dl = dst + (size_t)lane * HW;
             for (int pl = 0; pl < npw; ++pl) {
@@ -1199,6 +1466,10 @@ __global__ void roi_mask_pad_kernel(const float *__restrict__ m, float *__restri
 // ------------------------------------------------------------------------------------- host
 struct Plan {
     bool tile, glob;                 // glob: map too large for shared memory -> channel-last global copy
+    bool win;                        // map too large for shared memory -> window tiles (roi_window.cuh), the default
+    WinGeom wg;
+    int win_pitch, win_wyd_floats, win_fwd_warps, win_seg_cap;     // win_seg_cap: sub-ROIs per ROI the workspace holds
+    size_t smem_fwd_win;
     bool bwd_tm;                     // backward tile kernel keeps its gradient tile in tensor memory
     size_t smem_bwd_tm, smem_bwd_fused_tm;
     int pitch, fwd_warps, wyd_floats, glob_bwd_warps, glob_bwd_warps_fused;
@@ -1234,6 +1505,24 @@ static Plan make_plan(int C, int H, int W, int oh, int ow) {
     p.smem_bwd_glob_fused = p.glob_bwd_warps_fused * bwf;
     p.glob = !p.tile && oh == PH && ow == PW && (C % CH) == 0 && W >= MAXT && H <= 512 && p.smem_fwd_glob <= cap &&
              p.smem_bwd_glob <= cap && p.glob_bwd_warps_fused >= 4;
+    // window tiles: a WIN_DIM x WIN_DIM window of the map in the same smem tile, ROIs cut into sub-ROIs per window
+    p.wg = win_geom(H, W);
+    const int wwords = p.wg.wh * p.wg.ww;
+    p.win_pitch = ((wwords >> 1) & 1) ? wwords : wwords + 2;
+    p.win_wyd_floats = (p.wg.wh / 2) * 16;
+    const size_t per_warp_win = (size_t)STAGE_FLOATS * 4 + 2 * DESC_WORDS * 4 + (size_t)p.win_wyd_floats * 4;
+    p.win_fwd_warps = FWD_MAX_WARPS;
+    while (p.win_fwd_warps > 4 && (size_t)CH * p.win_pitch * 4 + p.win_fwd_warps * per_warp_win > cap) --p.win_fwd_warps;
+    p.smem_fwd_win = (size_t)CH * p.win_pitch * 4 + p.win_fwd_warps * per_warp_win;
+    auto seg_max = [](int L, int wl) {           // most segments a ROI can need along an axis of L cells
+        if (L <= wl) return 1;
+        const int emax = L / 7 + 3, per = std::max(1, (wl - (WIN_G - 1)) / emax);
+        return std::min(7, (7 + per - 1) / per);
+    };
+    p.win_seg_cap = std::min(16, seg_max(H, p.wg.wh) * seg_max(W, p.wg.ww));
+    p.win = !p.tile && oh == PH && ow == PW && (C % CH) == 0 && W >= MAXT && H >= 2 && p.wg.nwy < (1 << WIN_KEYBITS) &&
+            p.wg.nwx < (1 << WIN_KEYBITS) && p.smem_fwd_win <= cap && (((size_t)CH * p.win_pitch * 4) % 16 == 0) &&
+            4 * (((p.wg.wh >> 1) + NWB_DEFAULT - 1) / NWB_DEFAULT) * p.wg.ww * 2 <= 512;
     return p;
 }
 
@@ -1277,10 +1566,52 @@ static int run_prep(const float *rois, int B, int H, int W, int K, int oh, int o
 static size_t glob_copy_bytes(int B, int C, int H, int W) { return sizeof(float) * (size_t)B * C * ((H + 1) & ~1) * W; }
 static size_t ws_glob_off(int K) { return (cim_roi_align_workspace_bytes(K) + 255) & ~(size_t)255; }
 
+// window path: records, keys, bucket table and the sorted sub-ROI descriptors, at ws_glob_off(K)
+static size_t a256(size_t n) { return (n + 255) & ~(size_t)255; }
+static size_t win_ws_bytes(const Plan &p, int B, int K) {
+    const size_t cap = (size_t)std::max(K, 1) * p.win_seg_cap, nb = (size_t)B * p.wg.nwy * p.wg.nwx;
+    return a256((size_t)K * 8 * 4) + a256(((size_t)K + 1) * 4) + a256((size_t)K * 4 * 4) + 2 * a256(cap * 4) +
+           a256((nb + 2) * 4) + a256(cap * DESC_WORDS * 4);
+}
+static WinWs carve_win(void *ws, const Plan &p, int B, int K) {
+    const size_t cap = (size_t)std::max(K, 1) * p.win_seg_cap, nb = (size_t)B * p.wg.nwy * p.wg.nwx;
+    char *q = (char *)ws + ws_glob_off(K);
+    WinWs w;
+    w.rec = (int *)q;        q += a256((size_t)K * 8 * 4);
+    w.item_base = (int *)q;  q += a256(((size_t)K + 1) * 4);
+    w.flags = (int *)q;      q += a256((size_t)K * 4 * 4);
+    w.keys = (int *)q;       q += a256(cap * 4);
+    w.slot = (int *)q;       q += a256(cap * 4);
+    w.bucket = (int *)q;     q += a256((nb + 2) * 4);
+    w.desc = (int *)q;
+    w.cap = (int)std::min<size_t>(cap, 0x7fffffff);
+    return w;
+}
+static bool use_win(const Plan &p, int B, int K, size_t ws_bytes) {
+    return p.win && K > 0 && !(cim_get_debug_flags() & CIM_DBG_ROI_NO_WINDOWS) &&
+           ws_bytes >= ws_glob_off(K) + win_ws_bytes(p, B, K);
+}
+static int run_prep_win(const float *rois, int B, int H, int W, int K, float scale, int sr, int aligned, const RoiWs &w,
+                        const WinWs &ww, const Plan &p, cudaStream_t st) {
+    const int nb = B * p.wg.nwy * p.wg.nwx;
+    cudaMemsetAsync(w.hdr, 0, WS_HDR_BYTES, st);
+    cudaMemsetAsync(ww.bucket, 0, sizeof(int) * ((size_t)nb + 2), st);
+    roi_win_plan_kernel<<<(2 * K + 127) / 128, 128, 0, st>>>(rois, K, B, H, W, scale, sr, aligned, ww);
+    roi_win_scan_kernel<<<1, 1024, 0, st>>>(K, ww);
+    roi_win_keys_kernel<<<(K + 127) / 128, 128, 0, st>>>(rois, K, p.wg.nwy * p.wg.nwx, p.wg.nwx, ww);
+    roi_win_bucket_kernel<<<1, 1024, 0, st>>>(nb, ww);
+    roi_win_place_kernel<<<nb, 256, 0, st>>>(K, ww);
+    roi_win_emit_kernel<<<(2 * K + 127) / 128, 128, 0, st>>>(rois, K, H, W, scale, sr, aligned, ww);
+    return cim_launch_status();
+}
+
 CIM_API size_t cim_roi_align_workspace_bytes_ex(int B, int C, int H, int W, int K, int oh, int ow) {
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || oh <= 0 || ow <= 0) return cim_roi_align_workspace_bytes(K);
     const Plan p = make_plan(C, H, W, oh, ow);
-    return p.glob ? ws_glob_off(K) + glob_copy_bytes(B, C, H, W) : cim_roi_align_workspace_bytes(K);
+    size_t extra = 0;
+    if (p.glob) extra = glob_copy_bytes(B, C, H, W);
+    if (p.win) extra = std::max(extra, win_ws_bytes(p, B, K));
+    return extra ? ws_glob_off(K) + extra : cim_roi_align_workspace_bytes(K);
 }
 
 CIM_API size_t cim_roi_align_workspace_bytes(int K) {
@@ -1300,6 +1631,18 @@ static int roi_fwd_impl(const float *feat, const float *rois, const float *mask7
     const RoiWs w = carve(ws, B, K);
     const int per_roi = C * oh * ow;
     dim3 ggrid((unsigned)K, (unsigned)min(64, (per_roi + 255) / 256));
+    if (!p.tile && use_win(p, B, K, ws_bytes)) {
+        const WinWs ww = carve_win(ws, p, B, K);
+        if (!prepared && (rc = run_prep_win(rois, B, H, W, K, scale, sr, aligned, w, ww, p, st))) return rc;
+        cudaFuncSetAttribute(roi_align_fwd_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_fwd_win);
+        roi_align_fwd_win_kernel<<<cim_num_sms(), p.win_fwd_warps * 32, p.smem_fwd_win, st>>>(
+            feat, ww.bucket, ww.desc, mask7, out, B, C, H, W, p.wg, p.win_pitch, p.win_wyd_floats);
+        if ((rc = cim_launch_status())) return rc;
+        // leftover pass: ROIs the window plan could not take (bins wider than WIN_MTB taps, batch index out of range)
+        roi_align_generic_kernel<false><<<dim3((unsigned)((K + 7) / 8), 1), 256, 0, st>>>(
+            feat, rois, out, w.hdr, ww.flags, mask7, 1, B, C, H, W, K, oh, ow, scale, sr, aligned, 4);
+        return cim_launch_status();
+    }
     const bool glob = !p.tile && p.glob && ws_bytes >= ws_glob_off(K) + glob_copy_bytes(B, C, H, W);
     if (!p.tile && !glob) {
         roi_align_generic_kernel<false><<<ggrid, 256, 0, st>>>(feat, rois, out, nullptr, nullptr, mask7, 0, B, C, H, W,
@@ -1347,6 +1690,29 @@ static int roi_bwd_impl(const float *grad_out, const float *rois, const float *m
     const RoiWs w = carve(ws, B, K);
     const int per_roi = C * oh * ow;
     dim3 ggrid((unsigned)max(K, 1), (unsigned)min(64, (per_roi + 255) / 256));
+    if (!p.tile && use_win(p, B, K, ws_bytes)) {
+        const WinWs ww = carve_win(ws, p, B, K);
+        if (!prepared && (rc = run_prep_win(rois, B, H, W, K, scale, sr, aligned, w, ww, p, st))) return rc;
+        cudaMemsetAsync(grad_feat, 0, sizeof(float) * (size_t)B * C * H * W, st);
+        const int grid = cim_num_sms();
+        if (mask7) {
+            roi_mask_pad_kernel<<<(K * MASK_PAD + 255) / 256, 256, 0, st>>>(mask7, w.maskpad, K, NBIN);
+            if ((rc = cim_launch_status())) return rc;
+            auto kern = roi_align_bwd_tile_kernel<true, NWB_DEFAULT, true, true>;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bwd_fused_tm);
+            kern<<<grid, NWB_DEFAULT * 32, p.smem_bwd_fused_tm, st>>>(grad_out, w.hdr, ww.bucket, ww.desc, w.maskpad,
+                                                                       grad_feat, B, C, H, W, p.win_pitch, p.wg);
+        } else {
+            auto kern = roi_align_bwd_tile_kernel<false, NWB_DEFAULT, true, true>;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bwd_tm);
+            kern<<<grid, NWB_DEFAULT * 32, p.smem_bwd_tm, st>>>(grad_out, w.hdr, ww.bucket, ww.desc, nullptr, grad_feat, B,
+                                                                C, H, W, p.win_pitch, p.wg);
+        }
+        if ((rc = cim_launch_status())) return rc;
+        roi_align_generic_kernel<true><<<dim3((unsigned)((K + 7) / 8), 1), 256, 0, st>>>(
+            grad_out, rois, grad_feat, w.hdr, ww.flags, mask7, 1, B, C, H, W, K, oh, ow, scale, sr, aligned, 4);
+        return cim_launch_status();
+    }
     const bool glob = !p.tile && p.glob && K > 0 && ws_bytes >= ws_glob_off(K) + glob_copy_bytes(B, C, H, W);
     if ((!p.tile && !glob) || K == 0) {
         cudaMemsetAsync(grad_feat, 0, sizeof(float) * (size_t)B * C * H * W, st);
@@ -1387,7 +1753,8 @@ static int roi_bwd_impl(const float *grad_out, const float *rois, const float *m
     // thread-level parallelism: 2.10 ms against 1.81 ms at cfg2.)
     auto go = [&](auto kern, int nw, size_t smem, const float *mk) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<grid, nw * 32, smem, st>>>(grad_out, w.hdr, w.img_start, w.desc, mk, grad_feat, B, C, H, W, p.pitch);
+        kern<<<grid, nw * 32, smem, st>>>(grad_out, w.hdr, w.img_start, w.desc, mk, grad_feat, B, C, H, W, p.pitch,
+                                          WinGeom());
     };
     // CIM_DBG_ROI_BWD_SMEM_TILE keeps the gradient tile in shared memory (A/B timing, tests)
     const bool tm = p.bwd_tm && !(cim_get_debug_flags() & CIM_DBG_ROI_BWD_SMEM_TILE);
@@ -1418,6 +1785,9 @@ CIM_API int cim_roi_align_prepare(const float *rois, int B, int C, int H, int W,
     if (!ws || ws_bytes < cim_roi_align_workspace_bytes(K)) return CIM_ERR_WORKSPACE;
     if (!cim_aligned(ws, 16)) return CIM_ERR_ALIGN;
     const Plan p = make_plan(C, H, W, oh, ow);
+    if (!p.tile && use_win(p, B, K, ws_bytes))
+        return run_prep_win(rois, B, H, W, K, scale, sr, aligned, carve(ws, B, K), carve_win(ws, p, B, K), p,
+                            (cudaStream_t)stream);
     const bool glob = !p.tile && p.glob && ws_bytes >= ws_glob_off(K) + glob_copy_bytes(B, C, H, W);
     if (!p.tile && !glob) return CIM_OK;                   // generic kernels: no descriptors
     return run_prep(rois, B, H, W, K, oh, ow, scale, sr, aligned, carve(ws, B, K), glob, (cudaStream_t)stream);
@@ -1464,4 +1834,41 @@ CIM_API int cim_roi_align_maskfuse_bwd(const float *grad_out, const float *rois,
     if (!masks7 && K > 0) return CIM_ERR_ARG;
     return roi_bwd_impl(grad_out, rois, masks7, grad_feat, B, C, H, W, K, oh, ow, scale, sr, aligned, ws, ws_bytes,
                         stream);
+}
+
+// Test hook (host only, no GPU): the window plan of roi_window.cuh evaluated on the CPU with the same
+// __host__ __device__ code the prep kernels run.  All pointers are HOST memory.  Sub-ROI descriptors come out in ROI
+// order (the device sorts them by window afterwards); key_out = window index wy * nwx + wx of each sub-ROI, flag_out[k]
+// = 1 for ROIs the window path leaves to the generic kernel, geom_out = {Hp, wh, ww, nwy, nwx, WIN_G}.
+// Returns the number of sub-ROIs, or a negative CIM_ERR_* code (CIM_ERR_WORKSPACE: more than `cap`).
+CIM_API int cim_debug_roi_window_plan(const float *rois, int K, int B, int H, int W, float scale, int sr, int aligned,
+                                      int *desc_out, int *key_out, int cap, int *flag_out, int *geom_out) {
+    if (!rois || !desc_out || !key_out || !flag_out || !geom_out || K < 0 || B <= 0 || H <= 0 || W < MAXT)
+        return CIM_ERR_ARG;
+    const WinGeom g = win_geom(H, W);
+    geom_out[0] = g.Hp; geom_out[1] = g.wh; geom_out[2] = g.ww; geom_out[3] = g.nwy; geom_out[4] = g.nwx;
+    geom_out[5] = WIN_G;
+    int n = 0;
+    for (int k = 0; k < K; ++k) {
+        const float *r = rois + 5 * (size_t)k;
+        const AxisGeom ay = win_axis_geom(r, 0, 7, scale, sr, aligned), ax = win_axis_geom(r, 1, 7, scale, sr, aligned);
+        AxisPlan py, px;
+        win_axis_plan(ay, H, g.Hp, g.wh, g.nwy, py);
+        win_axis_plan(ax, W, W, g.ww, g.nwx, px);
+        const int b = (int)r[0];
+        flag_out[k] = (b < 0 || b >= B || py.nseg == 0 || px.nseg == 0) ? 1 : 0;
+        if (flag_out[k]) continue;
+        const bool simple = py.nseg == 1 && px.nseg == 1 && py.nslots[0] == 7 && px.nslots[0] == 7;
+        for (int sy = 0; sy < py.nseg; ++sy)
+            for (int sx = 0; sx < px.nseg; ++sx) {
+                if (n >= cap) return CIM_ERR_WORKSPACE;
+                int *d = desc_out + (size_t)n * DESC_WORDS;
+                for (int i = 0; i < DESC_WORDS; ++i) d[i] = 0;
+                win_axis_emit(ay, py, sy, 0, H, g.Hp, g.wh, k, simple, d);
+                win_axis_emit(ax, px, sx, 1, W, W, g.ww, k, simple, d);
+                key_out[n] = py.wcoord[sy] * g.nwx + px.wcoord[sx];
+                ++n;
+            }
+    }
+    return n;
 }

@@ -52,6 +52,13 @@ enum {
 };
 void cim_set_debug_flags(unsigned flags);
 unsigned cim_get_debug_flags(void);
+/* Test hook, HOST memory only, no GPU needed: the window plan of the RoIAlign window-tile path (maps larger than the
+ * shared-memory tile, csrc/roi_window.cuh) evaluated on the CPU with the same code the prep kernels run.  desc_out
+ * [cap][168] ints: one tile descriptor per sub-ROI, ROI order; key_out [cap]: its window index; flag_out [K]: 1 = the
+ * ROI is left to the generic kernel; geom_out [6] = {Hp, wh, ww, nwy, nwx, origin granularity}.  Returns the number of
+ * sub-ROIs or a negative CIM_ERR_* code. */
+int cim_debug_roi_window_plan(const float *rois, int K, int B, int H, int W, float scale, int sampling_ratio,
+                              int aligned, int *desc_out, int *key_out, int cap, int *flag_out, int *geom_out);
 
 /* ------------------------------------------------------------------ ROI operators
  * Replace mmcv.ops.RoIAlign / RoIPool as imported by lib/ops/__init__.py:6 and called at
