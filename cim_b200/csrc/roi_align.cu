@@ -662,6 +662,7 @@ roi_align_fwd_win_kernel(const float *__restrict__ feat, const int *__restrict__
 }
 
 // ----------------------------------------------------------------------------- tile: backward
+constexpr int WIN_TM_PAD = 8;       // window path: spare tensor-memory columns per tile row (bwd_pairs_win)
 constexpr int NWB_DEFAULT = 16;     // consumer warps of the backward CTA; warp w owns row pairs
                                     // {y : (y >> 1) % 16 == w}  (D_OWN is computed for exactly this map)
 constexpr int NBR = 4;              // ROIs per ring slot: one full/empty barrier round per 4 ROIs
@@ -702,18 +703,12 @@ __device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sy
 // region, pair p of the warp at columns 2 W (p / NW) ..): the x pass becomes tcgen05.ld / FFMA2 / tcgen05.st.
 // tools/micro/tmem_rmw.cu: this read-modify-write pattern runs at 98 B/clk/SM in tensor memory against the 64 B/clk
 // of shared memory (128 B/clk port, read + write), and the port stays free for the y pass.
-// WIN (window tiles, roi_window.cuh): the descriptor's 7 x 7 "bins" are SLOTS of a sub-ROI; slot (ys, xs) takes the
-// gradient of bin (ymap[ys], xmap[xs]) of the ROI, and only the first nx column slots exist.
-template <int T, bool XINC, bool FUSED, int NW, bool TM = false, bool WIN = false>
+template <int T, bool XINC, bool FUSED, int NW, bool TM = false>
 __device__ __forceinline__ void bwd_pairs(float *__restrict__ tile_c, int W, const int *d,
                                           const float *__restrict__ g, const float *__restrict__ m, int warp, int y0,
                                           int y1, uint32_t tmem_w = 0) {
-    constexpr bool WREG = !WIN || T <= 4;               // WIN: wide slots read their column weights from the descriptor
-    float wx[PW][WREG ? T : 1];
+    float wx[PW][T];
     int xo[PW];
-    // WIN: nibble s of ymap / xmap = bin of slot s (kept packed: the kernel sits at its register limit)
-    const unsigned ymap = WIN ? (unsigned)d[DW_YMAP] : 0u, xmap = WIN ? (unsigned)d[DW_XMAP] : 0u;
-    const int nx = WIN ? (int)((xmap >> 28) & 7u) : PW;
     const float *dwx = reinterpret_cast<const float *>(d + D_WX);
     const float *dwy = reinterpret_cast<const float *>(d + D_WY);
     const unsigned char *phr = reinterpret_cast<const unsigned char *>(d + D_PHR);
@@ -721,18 +716,15 @@ __device__ __forceinline__ void bwd_pairs(float *__restrict__ tile_c, int W, con
         int4 a = *reinterpret_cast<const int4 *>(d + D_XLO), b = *reinterpret_cast<const int4 *>(d + D_XLO + 4);
         xo[0] = a.x; xo[1] = a.y; xo[2] = a.z; xo[3] = a.w; xo[4] = b.x; xo[5] = b.y; xo[6] = b.z;
     }
-    if (WREG) {
 #pragma unroll
-        for (int pw = 0; pw < PW; ++pw) {
-            float4 a = *reinterpret_cast<const float4 *>(dwx + pw * MAXT);
-            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (T > 4) b = *reinterpret_cast<const float4 *>(dwx + pw * MAXT + 4);
-            float t8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    for (int pw = 0; pw < PW; ++pw) {
+        float4 a = *reinterpret_cast<const float4 *>(dwx + pw * MAXT);
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (T > 4) b = *reinterpret_cast<const float4 *>(dwx + pw * MAXT + 4);
+        float t8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int l = 0; l < (WREG ? T : 1); ++l) wx[pw][l] = t8[l];
-        }
+        for (int l = 0; l < T; ++l) wx[pw][l] = t8[l];
     }
-#define WXV(pw, l) (WREG ? wx[pw][WREG ? (l) : 0] : dwx[(pw) * MAXT + (l)])
     float2 *tile2 = reinterpret_cast<float2 *>(tile_c);
     const int pb = y0 >> 1, p1 = (y1 + 1) >> 1;
     // first owned pair >= pb: pairs p with p % NW == warp
@@ -748,13 +740,11 @@ __device__ __forceinline__ void bwd_pairs(float *__restrict__ tile_c, int W, con
         for (int ph = code & 15; ph < ph_end; ++ph) {
             const int dd = 2 * p - d[D_YLO + ph];    // window index of row 2p, in [-1, yn): padded weights
             const float2 w = make_float2(dwy[ph * WYP + dd + 1], dwy[ph * WYP + dd + 2]);
-            const int phb = WIN ? (int)((ymap >> (4 * ph)) & 7u) : ph;
-            const float *gp = g + phb * PW;
+            const float *gp = g + ph * PW;
 #pragma unroll
             for (int pw = 0; pw < PW; ++pw) {
-                const int pwb = WIN ? (int)((xmap >> (4 * pw)) & 7u) : pw;     // (unused slots: any valid column)
-                float gv = gp[pwb];
-                if (FUSED) gv = fmaf(gp[STAGE_FLOATS + pwb], m[phb * PW + pwb], gv);
+                float gv = gp[pw];
+                if (FUSED) gv = fmaf(gp[STAGE_FLOATS + pw], m[ph * PW + pw], gv);
                 r[pw] = __ffma2_rn(bcast2(gv), w, r[pw]);
             }
         }
@@ -765,26 +755,23 @@ __device__ __forceinline__ void bwd_pairs(float *__restrict__ tile_c, int W, con
                 for (int l = 0; l < T; ++l) {
                     float2 v[PW];
 #pragma unroll
-                    for (int pw = 0; pw < PW; ++pw)
-                        if (!WIN || pw < nx) v[pw] = tm_ld2(trow + 2u * (uint32_t)(xo[pw] + l));
+                    for (int pw = 0; pw < PW; ++pw) v[pw] = tm_ld2(trow + 2u * (uint32_t)(xo[pw] + l));
                     tm_wait_ld();
 #pragma unroll
                     for (int pw = 0; pw < PW; ++pw)
-                        if (!WIN || pw < nx)
-                            tm_st2(trow + 2u * (uint32_t)(xo[pw] + l), __ffma2_rn(bcast2(WXV(pw, l)), r[pw], v[pw]));
+                        tm_st2(trow + 2u * (uint32_t)(xo[pw] + l), __ffma2_rn(bcast2(wx[pw][l]), r[pw], v[pw]));
                     tm_wait_st();                       // the next l (and the next ROI) may read these columns
                 }
             } else {
 #pragma unroll
                 for (int pw = 0; pw < PW; ++pw) {
-                    if (WIN && pw >= nx) break;
                     float2 v[T];
 #pragma unroll
                     for (int l = 0; l < T; ++l) v[l] = tm_ld2(trow + 2u * (uint32_t)(xo[pw] + l));
                     tm_wait_ld();
 #pragma unroll
                     for (int l = 0; l < T; ++l)
-                        tm_st2(trow + 2u * (uint32_t)(xo[pw] + l), __ffma2_rn(bcast2(WXV(pw, l)), r[pw], v[l]));
+                        tm_st2(trow + 2u * (uint32_t)(xo[pw] + l), __ffma2_rn(bcast2(wx[pw][l]), r[pw], v[l]));
                     tm_wait_st();                       // the next bin may alias these columns
                 }
             }
@@ -798,25 +785,131 @@ __device__ __forceinline__ void bwd_pairs(float *__restrict__ tile_c, int W, con
             for (int l = 0; l < T; ++l) {
                 float2 v[PW];
 #pragma unroll
-                for (int pw = 0; pw < PW; ++pw)
-                    if (!WIN || pw < nx) v[pw] = row[xo[pw] + l];
+                for (int pw = 0; pw < PW; ++pw) v[pw] = row[xo[pw] + l];
 #pragma unroll
-                for (int pw = 0; pw < PW; ++pw)
-                    if (!WIN || pw < nx) row[xo[pw] + l] = __ffma2_rn(bcast2(WXV(pw, l)), r[pw], v[pw]);
+                for (int pw = 0; pw < PW; ++pw) row[xo[pw] + l] = __ffma2_rn(bcast2(wx[pw][l]), r[pw], v[pw]);
             }
         } else {
             // windows may coincide (tiny ROIs): bins strictly in program order; the T taps of one bin
             // are distinct columns
 #pragma unroll
             for (int pw = 0; pw < PW; ++pw) {
-                if (WIN && pw >= nx) break;
                 float2 v[T];
 #pragma unroll
                 for (int l = 0; l < T; ++l) v[l] = row[xo[pw] + l];
 #pragma unroll
-                for (int l = 0; l < T; ++l) row[xo[pw] + l] = __ffma2_rn(bcast2(WXV(pw, l)), r[pw], v[l]);
+                for (int l = 0; l < T; ++l) row[xo[pw] + l] = __ffma2_rn(bcast2(wx[pw][l]), r[pw], v[l]);
                 asm volatile("" ::: "memory");          // the next bin may alias these columns
             }
+        }
+    }
+}
+
+// WIN (window tiles, roi_window.cuh): the descriptor's 7 x 7 "bins" are SLOTS of a sub-ROI; slot (ys, xs) takes the
+// gradient of bin (ymap[ys], xmap[xs]) of the ROI, and only the first nx column slots exist.  One instance for every
+// tap class (the ten unrolled T x XINC instances of bwd_pairs made this kernel 118 KB of SASS: a third of all warp
+// samples were instruction-fetch stalls).  The x pass goes SLOT BY SLOT: the 8 (T <= 4: 4) columns of a slot x 2 rows
+// are one 16- (8-) column tensor-memory load, 8 (4) FFMA2 with the slot's weights (two LDS.128 from the descriptor),
+// one store -- nx round trips per row pair instead of T rounds of 7 + 7 narrow accesses; consecutive slots may share
+// columns, so each store is waited for.  W = columns of a tile row in tensor memory = window width + WIN_TM_PAD: a slot
+// that starts fewer than 8 columns from the window's right edge runs into the (never drained, always zero) padding.
+__device__ __forceinline__ void tm_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tm_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+                   "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+                 : "memory");
+}
+__device__ __forceinline__ void tm_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tm_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+                 "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+
+template <bool FUSED, int NW>
+__device__ __forceinline__ void bwd_pairs_win(int W, const int *d, const float *__restrict__ g,
+                                              const float *__restrict__ m, int warp, int y0, int y1, uint32_t tmem_w) {
+    int xo[PW];
+    const unsigned ymap = (unsigned)d[DW_YMAP], xmap = (unsigned)d[DW_XMAP];
+    const int nx = (int)((xmap >> 28) & 7u);
+    const bool narrow = d[D_TX] <= 4;                 // every slot has its weights in taps 0..3
+    const float *dwx = reinterpret_cast<const float *>(d + D_WX);
+    const float *dwy = reinterpret_cast<const float *>(d + D_WY);
+    const unsigned char *phr = reinterpret_cast<const unsigned char *>(d + D_PHR);
+    {
+        int4 a = *reinterpret_cast<const int4 *>(d + D_XLO), b = *reinterpret_cast<const int4 *>(d + D_XLO + 4);
+        xo[0] = a.x; xo[1] = a.y; xo[2] = a.z; xo[3] = a.w; xo[4] = b.x; xo[5] = b.y; xo[6] = b.z;
+    }
+    const int pb = y0 >> 1, p1 = (y1 + 1) >> 1;
+    int p = pb + ((warp - pb) & (NW - 1));
+#pragma unroll 1
+    for (; p < p1; p += NW) {
+        float2 r[PW];
+#pragma unroll
+        for (int pw = 0; pw < PW; ++pw) r[pw] = make_float2(0.f, 0.f);
+        const int code = phr[p - pb];
+        const int ph_end = (code & 15) + (code >> 4);
+#pragma unroll 1
+        for (int ph = code & 15; ph < ph_end; ++ph) {
+            const int dd = 2 * p - d[D_YLO + ph];    // window index of row 2p, in [-1, yn): padded weights
+            const float2 w = make_float2(dwy[ph * WYP + dd + 1], dwy[ph * WYP + dd + 2]);
+            const int phb = (int)((ymap >> (4 * ph)) & 7u);
+            const float *gp = g + phb * PW;
+#pragma unroll
+            for (int pw = 0; pw < PW; ++pw) {
+                const int pwb = (int)((xmap >> (4 * pw)) & 7u);           // (unused slots: any valid column)
+                float gv = gp[pwb];
+                if (FUSED) gv = fmaf(gp[STAGE_FLOATS + pwb], m[phb * PW + pwb], gv);
+                r[pw] = __ffma2_rn(bcast2(gv), w, r[pw]);
+            }
+        }
+        const uint32_t trow = tmem_w + (uint32_t)((p / NW) * W) * 2u;
+#pragma unroll
+        for (int pw = 0; pw < PW; ++pw) {
+            if (pw >= nx) break;
+            const uint32_t ta = trow + 2u * (uint32_t)xo[pw];
+            const float4 wa = *reinterpret_cast<const float4 *>(dwx + pw * MAXT);
+            if (narrow) {
+                uint32_t v[8];
+                tm_ld8(ta, v);
+                tm_wait_ld();
+                const float wl[4] = {wa.x, wa.y, wa.z, wa.w};
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    const float2 t = __ffma2_rn(bcast2(wl[l]), r[pw],
+                                                make_float2(__uint_as_float(v[2 * l]), __uint_as_float(v[2 * l + 1])));
+                    v[2 * l] = __float_as_uint(t.x);
+                    v[2 * l + 1] = __float_as_uint(t.y);
+                }
+                tm_st8(ta, v);
+            } else {
+                const float4 wb = *reinterpret_cast<const float4 *>(dwx + pw * MAXT + 4);
+                uint32_t v[16];
+                tm_ld16(ta, v);
+                tm_wait_ld();
+                const float wl[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                for (int l = 0; l < 8; ++l) {
+                    const float2 t = __ffma2_rn(bcast2(wl[l]), r[pw],
+                                                make_float2(__uint_as_float(v[2 * l]), __uint_as_float(v[2 * l + 1])));
+                    v[2 * l] = __float_as_uint(t.x);
+                    v[2 * l + 1] = __float_as_uint(t.y);
+                }
+                tm_st16(ta, v);
+            }
+            tm_wait_st();                               // the next slot (and the next ROI) may share these columns
         }
     }
 }
@@ -870,6 +963,8 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
     float *tile = smem;
     float *ring = smem + (TM ? 0 : (size_t)CH * pitch);      // [NS][NBR x grads | NBR x DESC_WORDS]
     __shared__ uint32_t tmem_slot;
+    __shared__ int done_cnt[4];                                // LASTP: warps that have finished the batch in each slot
+    constexpr bool LASTP = WIN;
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)NS * SLOT_FLOATS);
     uint64_t *empty = full + NS;
     if (!WIN && __ldg(hdr) != 0) return;      // rois not grouped by image: the generic kernel does it all
@@ -878,7 +973,7 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
     const int HW = Hmap * Wmap, nchunks = C / CH;
     const int NWIN = WIN ? wg.nwy * wg.nwx : 1;
     if (tid == 0) {
-        for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWB); }
+        for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWB); done_cnt[s] = 0; }
         fence_mbar_init();
     }
     if (TM && warp == 0) {
@@ -893,7 +988,8 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
     // TM: warp w reaches the TMEM lanes of its quarter (w % 4) only; lane = channel.  Its region holds the row
     // pairs it owns (p % NWB == w), 2 W columns each; the 4 warps of a quarter sit side by side.
     const int npw = (((H + 1) >> 1) + NWB - 1) / NWB;        // row pairs per warp
-    const uint32_t tmem_cols_w = (uint32_t)(npw * W * 2);
+    const int TW = WIN ? W + WIN_TM_PAD : W;                 // columns of a tile row in tensor memory (bwd_pairs_win)
+    const uint32_t tmem_cols_w = (uint32_t)(npw * TW * 2);
     const uint32_t tmem_w = TM ? tmem_slot + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(warp >> 2) * tmem_cols_w : 0u;
 
     const int s0 = __ldg(img_start), sB = __ldg(img_start + B * NWIN);
@@ -964,16 +1060,11 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
         // producer duty (lane 0 of warp 0): batch j of this segment (NBR consecutive ROIs: gradients +
         // descriptors) goes to slot (gb0 + j) % NS once every warp has released the batch that used
         // the slot before.  `must` = the batch warp 0 itself is about to read: blocking wait.
-        auto produce = [&](int want, int must) {
-            while (issued < want && issued < gb0 + nbatch) {
-                const int s = issued % NS;
-                if (issued >= NS) {
-                    const uint32_t par = ((issued / NS) - 1) & 1;
-                    if (issued <= must) mbar_wait(&empty[s], par);
-                    else if (!mbar_test(&empty[s], par)) break;
-                }
+        auto issue_batch = [&](int gbatch) {              // one thread: the bulk copies of batch `gbatch` (global index)
+            {
+                const int s = gbatch % NS;
                 float *slot = ring + (size_t)s * SLOT_FLOATS;
-                const int first = (issued - gb0) * NBR, cnt = min(NBR, n - first);
+                const int first = (gbatch - gb0) * NBR, cnt = min(NBR, n - first);
                 mbar_expect_tx(&full[s], (uint32_t)cnt * (GSTRIDE + DESC_WORDS + (FUSED ? MASK_PAD : 0)) * 4);
                 int rois_j[NBR];
                 if (WIN) {                    // the ROI of each sub-ROI: word DW_ROI of its descriptor (loads in flight together)
@@ -999,13 +1090,30 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
                 if (FUSED && !WIN)
                     bulk_g2s(slot + NBR * (GSTRIDE + DESC_WORDS), mask7 + (size_t)(first_roi + first) * MASK_PAD,
                              (uint32_t)cnt * MASK_PAD * 4, &full[s]);
+            }
+        };
+        auto produce = [&](int want, int must) {
+            while (issued < want && issued < gb0 + nbatch) {
+                const int s = issued % NS;
+                if (issued >= NS) {
+                    const uint32_t par = ((issued / NS) - 1) & 1;
+                    if (issued <= must) mbar_wait(&empty[s], par);
+                    else if (!mbar_test(&empty[s], par)) break;
+                }
+                issue_batch(issued);
                 ++issued;
             }
         };
-        if (tid == 0) produce(gb0 + NS, -1);
+        // LASTP: the warp that finishes a batch LAST refills its slot (batch + NS) at once.  With the refill left to
+        // warp 0 (which owns the lightly loaded top row pair) its non-blocking look at the slot usually came too early,
+        // and the batch was only fetched when warp 0 needed it itself: every batch then waited for its data.
+        if (LASTP) {
+            if (tid == 0)
+                for (int j = 0; j < NS && j < nbatch; ++j) issue_batch(gb0 + j);      // all slots are free (CTA barrier above)
+        } else if (tid == 0) produce(gb0 + NS, -1);
 
         for (int bi = 0; bi < nbatch; ++bi, ++gb) {
-            if (tid == 0) produce(gb + NS, gb);
+            if (!LASTP && tid == 0) produce(gb + NS, gb);
             const int s = gb % NS;
             mbar_wait(&full[s], (gb / NS) & 1);
             const float *slot = ring + (size_t)s * SLOT_FLOATS;
@@ -1027,27 +1135,42 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
                 const int y0 = yr.x, y1 = yr.y;
                 const float *g = slot + j * GSTRIDE + lane * NBIN;
                 const float *m = slot + NBR * (GSTRIDE + DESC_WORDS) + j * MASK_PAD;
+                if constexpr (WIN) {
+                    bwd_pairs_win<FUSED, NWB>(TW, d, g, m, warp, y0, y1, tmem_w);
+                    continue;
+                }
                 const int T = d[D_TX];
                 if (d[D_XINC]) {
                     switch (T) {
-                        case 2: bwd_pairs<2, true, FUSED, NWB, TM, WIN>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
-                        case 3: bwd_pairs<3, true, FUSED, NWB, TM, WIN>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
-                        case 4: bwd_pairs<4, true, FUSED, NWB, TM, WIN>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
-                        case 6: bwd_pairs<6, true, FUSED, NWB, TM, WIN>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
-                        default: bwd_pairs<8, true, FUSED, NWB, TM, WIN>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
+                        case 2: bwd_pairs<2, true, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
+                        case 3: bwd_pairs<3, true, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
+                        case 4: bwd_pairs<4, true, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
+                        case 6: bwd_pairs<6, true, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
+                        default: bwd_pairs<8, true, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
                     }
                 } else {
                     switch (T) {
-                        case 2: bwd_pairs<2, false, FUSED, NWB, TM, WIN>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
-                        case 3: bwd_pairs<3, false, FUSED, NWB, TM, WIN>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
-                        case 4: bwd_pairs<4, false, FUSED, NWB, TM, WIN>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
-                        case 6: bwd_pairs<6, false, FUSED, NWB, TM, WIN>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
-                        default: bwd_pairs<8, false, FUSED, NWB, TM, WIN>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
+                        case 2: bwd_pairs<2, false, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
+                        case 3: bwd_pairs<3, false, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
+                        case 4: bwd_pairs<4, false, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
+                        case 6: bwd_pairs<6, false, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
+                        default: bwd_pairs<8, false, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
                     }
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive_cta(&empty[s]);       // this warp is done reading slot s
+            if (LASTP) {
+                if (lane == 0) {
+                    __threadfence_block();                   // this warp's reads of slot s are done
+                    if (atomicAdd(&done_cnt[s], 1) == NWB - 1) {
+                        done_cnt[s] = 0;
+                        if (bi + NS < nbatch) {
+                            fence_proxy_async_smem();
+                            issue_batch(gb + NS);
+                        }
+                    }
+                }
+            } else if (lane == 0) mbar_arrive_cta(&empty[s]);       // this warp is done reading slot s
         }
         __syncthreads();
 
@@ -1062,7 +1185,7 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
                 if (y >= H || oy + y >= Hmap) break;
                 const bool row1 = oy + y + 1 < Hmap;
                 if (TM) {
-                    const uint32_t trow = tmem_w + (uint32_t)(pl * W) * 2u;
+                    const uint32_t trow = tmem_w + (uint32_t)(pl * TW) * 2u;
                     if (v4) {
                         for (int x = 0; x < W; x += 4) {
                             uint32_t v[8];
@@ -1522,7 +1645,7 @@ static Plan make_plan(int C, int H, int W, int oh, int ow) {
     p.win_seg_cap = std::min(16, seg_max(H, p.wg.wh) * seg_max(W, p.wg.ww));
     p.win = !p.tile && oh == PH && ow == PW && (C % CH) == 0 && W >= MAXT && H >= 2 && p.wg.nwy < (1 << WIN_KEYBITS) &&
             p.wg.nwx < (1 << WIN_KEYBITS) && p.smem_fwd_win <= cap && (((size_t)CH * p.win_pitch * 4) % 16 == 0) &&
-            4 * (((p.wg.wh >> 1) + NWB_DEFAULT - 1) / NWB_DEFAULT) * p.wg.ww * 2 <= 512;
+            4 * (((p.wg.wh >> 1) + NWB_DEFAULT - 1) / NWB_DEFAULT) * (p.wg.ww + WIN_TM_PAD) * 2 <= 512;
     return p;
 }
 

@@ -248,6 +248,9 @@ __host__ __device__ inline void win_axis_emit(const AxisGeom &a, const AxisPlan 
             phr[j] = (unsigned char)(first | (cnt << 4));
         }
     } else {
+        // tap class T in {2,3,4,6,8}: the forward's x loops are unrolled T times.  (The backward updates a slot with one
+        // 8-tap-wide tensor-memory access whatever T is; its tile rows carry 8 spare columns for slots that start
+        // fewer than 8 columns from the window's right edge.)
         int nmax = 0;
         for (int s = 0; s < ns; ++s) nmax = nmax > s_n[s] ? nmax : s_n[s];
         const int T = nmax <= 2 ? 2 : nmax <= 3 ? 3 : nmax <= 4 ? 4 : nmax <= 6 ? 6 : 8;

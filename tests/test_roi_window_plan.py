@@ -62,7 +62,7 @@ def rebuild_forward(feat, rois, desc, keys, geom):
             rows.append((ylo, yn, wyv[1:1 + yn].astype(np.float64)))
             xlo = int(d[D_XLO + s])
             wxv = f32(d[D_WX + s * 8:D_WX + s * 8 + 8])
-            assert 0 <= xlo and xlo + T <= ww and not wxv[T:].any()           # the kernel reads exactly T taps
+            assert 0 <= xlo and xlo + T <= ww and not wxv[T:].any()           # the forward reads exactly T taps
             cols.append((xlo, wxv[:T].astype(np.float64)))
             if s >= ny:
                 assert yn == 0 and ((ym >> (4 * s)) & 15) == 15

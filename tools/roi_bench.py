@@ -21,14 +21,19 @@ def main():
     ap.add_argument("--backbone", default="resnet50")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--size", type=int, default=512, help="image side in pixels (map side = size / stride): the "
+                    "reference trains at scales 480 .. 1200 (configs/resnet50_voc.yaml:34)")
+    ap.add_argument("--debug-flags", type=int, default=0, help="cim_set_debug_flags (8 = global-pairs path instead "
+                    "of window tiles, 1 = shared-memory gradient tile)")
     ap.add_argument("--profile-fused-bwd", action="store_true", help="run only the fused backward 3 times (for ncu)")
     ap.add_argument("--fused", action="store_true", help="also time the fused MaskFuse prologue and the unfused "
                     "torch expression it replaces (box * mask, concat)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
-    Cf, H, W, scale = synth.feature_shape(a.backbone)
+    Cf, H, W, scale = synth.feature_shape(a.backbone, a.size)
     B, R = a.images, a.props
-    rois = torch.cat([synth.rois_from_params(synth.proposal_params(R, 512, 1234 + b), b) for b in range(B)]).to(dev)
+    _lib.lib().cim_set_debug_flags(a.debug_flags)
+    rois = torch.cat([synth.rois_from_params(synth.proposal_params(R, a.size, 1234 + b), b) for b in range(B)]).to(dev)
     g = torch.Generator(device=dev).manual_seed(1)
     feat = torch.randn(B, Cf, H, W, device=dev, generator=g)
     K = rois.size(0)
@@ -73,7 +78,7 @@ def main():
         return
     mb = (K * Cf * 49 * 4 + B * Cf * H * W * 4 + 20 * K) / 1e6
     tf, tb = timeit(fwd), timeit(bwd)
-    print(f"roi_align fwd {tf:.3f} ms  {mb / tf:.1f} GB/s   bwd {tb:.3f} ms  {mb / tb:.1f} GB/s   ({mb:.0f} MB each)")
+    print(f"{a.backbone} {H}x{W}x{Cf} flags={a.debug_flags}: roi_align fwd {tf:.3f} ms  {mb / tf:.1f} GB/s   bwd {tb:.3f} ms  {mb / tb:.1f} GB/s   ({mb:.0f} MB each)")
 
     if a.fused:
         masks = (torch.rand(K, 7, 7, device=dev, generator=g) > 0.5).float()
