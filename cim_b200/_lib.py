@@ -49,6 +49,7 @@ _SIGNATURES = {
     "cim_roi_align_maskfuse_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P, _SZ, _P]),
     "cim_roi_align_maskfuse_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P, _SZ, _P]),
     "cim_roi_pool_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P]),
+    "cim_roi_pool_fwd_ex": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P]),
     "cim_roi_pool_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "cim_mask_pack": (_I, [_P, _P, _I64, _I64, _I64, _P]),
     "cim_mask_unpack_crops": (_I, [_P, _P, _P, _P, _I64, _I, _I, _I64, _P]),

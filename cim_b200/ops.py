@@ -78,9 +78,17 @@ class RoIAlignFunction(Function):
         return grad_feat, None, None, None, None, None, None
 
 
+#: RoIPool bin conventions (cim_roi_pool_fwd_ex): "mmcv" = mmcv 1.x's RoIPool, the op the reference imports
+#: (lib/ops/__init__.py:6) and therefore the default of this drop-in; "legacy" = the reference's vendored
+#: lib/model/roi_pooling kernel == torchvision.ops.roi_pool.  They differ for most ROIs (float vs rounded corners).
+ROI_POOL_VARIANTS = {"legacy": 0, "mmcv": 1}
+
+
 class RoIPoolFunction(Function):
     @staticmethod
-    def forward(ctx, feat, rois, output_size, spatial_scale=1.0):
+    def forward(ctx, feat, rois, output_size, spatial_scale=1.0, variant="mmcv"):
+        if variant not in ROI_POOL_VARIANTS:
+            raise ValueError("variant must be 'mmcv' or 'legacy'")
         _check_inputs(feat, rois)
         oh, ow = _pair(output_size)
         feat, rois = feat.contiguous(), rois.contiguous()
@@ -90,8 +98,9 @@ class RoIPoolFunction(Function):
         with torch.cuda.device(feat.device):
             out = torch.empty((K, Cc, oh, ow), dtype=torch.float32, device=feat.device)
             argmax = torch.empty((K, Cc, oh, ow), dtype=torch.int32, device=feat.device)
-            rc = L.cim_roi_pool_fwd(_lib.ptr(feat), _lib.ptr(rois), _lib.ptr(out), _lib.ptr(argmax), B, Cc, H, W,
-                                    K, oh, ow, float(spatial_scale), _lib.stream_ptr(feat.device))
+            rc = L.cim_roi_pool_fwd_ex(_lib.ptr(feat), _lib.ptr(rois), _lib.ptr(out), _lib.ptr(argmax), B, Cc, H, W,
+                                       K, oh, ow, float(spatial_scale), ROI_POOL_VARIANTS[variant],
+                                       _lib.stream_ptr(feat.device))
         _lib.check(rc, "cim_roi_pool_fwd")
         ctx.save_for_backward(rois, argmax)
         ctx.cfg = (tuple(feat.shape), oh, ow)
@@ -109,7 +118,7 @@ class RoIPoolFunction(Function):
             rc = L.cim_roi_pool_bwd(_lib.ptr(grad_out), _lib.ptr(argmax), _lib.ptr(rois), _lib.ptr(grad_feat), B,
                                     Cc, H, W, rois.size(0), oh, ow, _lib.stream_ptr(grad_out.device))
         _lib.check(rc, "cim_roi_pool_bwd")
-        return grad_feat, None, None, None
+        return grad_feat, None, None, None, None
 
 
 class RoIAlignMaskFuseFunction(Function):
@@ -168,8 +177,8 @@ def roi_align(input, rois, output_size, spatial_scale=1.0, sampling_ratio=0, poo
     return RoIAlignFunction.apply(input, rois, output_size, spatial_scale, sampling_ratio, pool_mode, aligned)
 
 
-def roi_pool(input, rois, output_size, spatial_scale=1.0):
-    return RoIPoolFunction.apply(input, rois, output_size, spatial_scale)
+def roi_pool(input, rois, output_size, spatial_scale=1.0, variant="mmcv"):
+    return RoIPoolFunction.apply(input, rois, output_size, spatial_scale, variant)
 
 
 class RoIAlign(nn.Module):
@@ -197,15 +206,21 @@ class RoIAlign(nn.Module):
 
 
 class RoIPool(nn.Module):
-    """mmcv.ops.RoIPool(output_size, spatial_scale=1.0)."""
+    """mmcv.ops.RoIPool(output_size, spatial_scale=1.0), with mmcv 1.x's bins by default (float ROI corners
+    x1 * s .. (x2 + 1) * s, floor / ceil of p * bin + start; restated from mmcv's published kernel, parity unpinned
+    because mmcv is absent here); variant="legacy" gives the bins of the reference's vendored roi_pooling kernel
+    (== torchvision.ops.roi_pool), which is pinned against both."""
 
-    def __init__(self, output_size, spatial_scale=1.0):
+    def __init__(self, output_size, spatial_scale=1.0, variant="mmcv"):
         super().__init__()
+        if variant not in ROI_POOL_VARIANTS:
+            raise ValueError("variant must be 'mmcv' or 'legacy'")
         self.output_size = _pair(output_size)
         self.spatial_scale = float(spatial_scale)
+        self.variant = variant
 
     def forward(self, input, rois):
-        return roi_pool(input, rois, self.output_size, self.spatial_scale)
+        return roi_pool(input, rois, self.output_size, self.spatial_scale, self.variant)
 
     def __repr__(self):
         return f"{self.__class__.__name__}(output_size={self.output_size}, spatial_scale={self.spatial_scale})"

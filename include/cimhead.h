@@ -127,6 +127,15 @@ int cim_roi_align_bwd_prepared(const float *grad_out, const float *rois, const f
 int cim_roi_pool_fwd(const float *feat, const float *rois, float *out, int32_t *argmax,
                      int B, int C, int H, int W, int K, int oh, int ow,
                      float spatial_scale, cim_stream_t stream);
+/* variant: CIM_ROI_POOL_LEGACY = the bins of the reference's vendored kernel (== torchvision.ops.roi_pool; what
+ * cim_roi_pool_fwd computes), CIM_ROI_POOL_MMCV = the bins of mmcv 1.x's RoIPool, which is what lib/ops/__init__.py:6
+ * imports (float corners x1*s .. (x2+1)*s, floor / ceil of p*bin + start, degenerate ROIs pool nothing; restated from
+ * mmcv's published kernel -- mmcv is an un-vendored, un-pinned dependency: parity unpinned).  The backward is the same
+ * for both (it only reads argmax). */
+enum { CIM_ROI_POOL_LEGACY = 0, CIM_ROI_POOL_MMCV = 1 };
+int cim_roi_pool_fwd_ex(const float *feat, const float *rois, float *out, int32_t *argmax,
+                        int B, int C, int H, int W, int K, int oh, int ow,
+                        float spatial_scale, int variant, cim_stream_t stream);
 int cim_roi_pool_bwd(const float *grad_out, const int32_t *argmax, const float *rois,
                      float *grad_feat, int B, int C, int H, int W, int K, int oh, int ow,
                      cim_stream_t stream);

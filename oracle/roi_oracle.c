@@ -185,6 +185,49 @@ void oracle_roi_pool_fwd(const float *feat, const float *rois, float *out, int32
     }
 }
 
+/* RoIPool forward with the bins of mmcv 1.x (the module lib/ops/__init__.py:6 imports; mmcv-full is an un-vendored,
+ * un-pinned dependency that is absent here, so this restates its PUBLISHED kernel -- mmcv/ops/csrc/common/cuda/
+ * roi_pool_cuda_kernel.cuh, roi_pool_forward_cuda_kernel -- and is "parity unpinned"): float ROI corners
+ * x1 * s, y1 * s, (x2 + 1) * s, (y2 + 1) * s; a ROI with w <= 0 or h <= 0 is skipped (output stays 0; argmax is
+ * reported as -1 here, i.e. no gradient); bin edges floor(p * bin + start) .. ceil((p + 1) * bin + start) clipped to
+ * the map; empty bin -> 0 / -1; strict > keeps the first maximum in row-major order. */
+void oracle_roi_pool_fwd_mmcv(const float *feat, const float *rois, float *out, int32_t *argmax,
+                              int B, int C, int H, int W, int K, int oh, int ow, float scale)
+{
+    (void)B;
+    for (int k = 0; k < K; ++k) {
+        const float *r = rois + 5 * k;
+        int b = (int)r[0];
+        float x1 = r[1] * scale, y1 = r[2] * scale;
+        float x2 = (r[3] + 1.f) * scale, y2 = (r[4] + 1.f) * scale;
+        float rw = x2 - x1, rh = y2 - y1;
+        int skip = rw <= 0.f || rh <= 0.f;
+        float bw = rw / (float)ow, bh = rh / (float)oh;
+        for (int c = 0; c < C; ++c) {
+            const float *plane = feat + ((size_t)b * C + c) * H * W;
+            size_t ob = ((size_t)k * C + c) * oh * ow;
+            for (int ph = 0; ph < oh; ++ph)
+                for (int pw = 0; pw < ow; ++pw) {
+                    float best = 0.f;
+                    int besti = -1;
+                    if (!skip) {
+                        int ws = clampi((int)floorf((float)pw * bw + x1), 0, W);
+                        int hs = clampi((int)floorf((float)ph * bh + y1), 0, H);
+                        int we = clampi((int)ceilf((float)(pw + 1) * bw + x1), 0, W);
+                        int he = clampi((int)ceilf((float)(ph + 1) * bh + y1), 0, H);
+                        int empty = (he <= hs) || (we <= ws);
+                        best = empty ? 0.f : -FLT_MAX;
+                        for (int h = hs; h < he; ++h)
+                            for (int w = ws; w < we; ++w)
+                                if (plane[h * W + w] > best) { best = plane[h * W + w]; besti = h * W + w; }
+                    }
+                    out[ob + ph * ow + pw] = best;
+                    if (argmax) argmax[ob + ph * ow + pw] = besti;
+                }
+        }
+    }
+}
+
 void oracle_roi_pool_bwd(const float *grad_out, const int32_t *argmax, const float *rois,
                          float *grad_feat, int B, int C, int H, int W, int K, int oh, int ow)
 {

@@ -64,13 +64,16 @@ def roi_align_bwd(grad_out, rois, shape, scale, sampling_ratio=0, aligned=True):
     return gf
 
 
-def roi_pool_fwd(feat, rois, oh, ow, scale):
+def roi_pool_fwd(feat, rois, oh, ow, scale, variant="legacy"):
+    """variant "legacy": the reference's vendored kernel (== torchvision.ops.roi_pool); "mmcv": mmcv 1.x's bins
+    (restated from its published kernel; parity unpinned, see roi_oracle.c)."""
     feat, rois = _f(feat), _f(rois)
     B, Cc, H, W = feat.shape
     K = rois.shape[0]
     out = np.empty((K, Cc, oh, ow), np.float32)
     arg = np.empty((K, Cc, oh, ow), np.int32)
-    cpu_lib().oracle_roi_pool_fwd(_p(feat), _p(rois), _p(out), _p(arg), B, Cc, H, W, K, oh, ow, C.c_float(scale))
+    fn = cpu_lib().oracle_roi_pool_fwd_mmcv if variant == "mmcv" else cpu_lib().oracle_roi_pool_fwd
+    fn(_p(feat), _p(rois), _p(out), _p(arg), B, Cc, H, W, K, oh, ow, C.c_float(scale))
     return out, arg
 
 

@@ -170,17 +170,21 @@ def test_full_size_cfg2_linearity_and_adjoint():
     close(o1[idx.to(DEV)].cpu().numpy(), want)
 
 
-def test_roi_pool_exact_and_backward():
+@pytest.mark.parametrize("variant", ["mmcv", "legacy"])
+def test_roi_pool_exact_and_backward(variant):
+    """Both bin conventions: mmcv 1.x's (the default: it is what the reference imports) and the vendored kernel's."""
     feat = torch.randn(2, 48, 20, 24, generator=torch.Generator().manual_seed(8))
     rois = random_rois(9, 2, 70, 20, 24, 0.25, wild=True)
+    rois[5, 3] = rois[5, 1] - 2.0                                             # x2 + 1 < x1: mmcv pools nothing
     f = feat.to(DEV).requires_grad_(True)
-    out = ops.RoIPool(7, 0.25)(f, rois.to(DEV))
-    want, arg = roi_oracle.roi_pool_fwd(feat.numpy(), rois.numpy(), 7, 7, 0.25)
+    assert ops.RoIPool(7, 0.25).variant == "mmcv"
+    out = ops.RoIPool(7, 0.25, variant)(f, rois.to(DEV))
+    want, arg = roi_oracle.roi_pool_fwd(feat.numpy(), rois.numpy(), 7, 7, 0.25, variant)
     np.testing.assert_array_equal(out.detach().cpu().numpy(), want)          # max is exact
     g = torch.randn(out.shape, generator=torch.Generator().manual_seed(4))
     out.backward(g.to(DEV))
     close(f.grad.cpu().numpy(), roi_oracle.roi_pool_bwd(g.numpy(), arg, rois.numpy(), feat.shape))
-    if roi_oracle.ref_lib() is not None:                                      # the vendored kernel itself
+    if variant == "legacy" and roi_oracle.ref_lib() is not None:              # the vendored kernel itself
         ref_out, _ = roi_oracle.ref_roi_pool_fwd(feat.to(DEV), rois.to(DEV), 7, 7, 0.25)
         np.testing.assert_array_equal(out.detach().cpu().numpy(), ref_out.cpu().numpy())
 

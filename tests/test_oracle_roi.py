@@ -61,6 +61,33 @@ def test_roi_pool_matches_torchvision(wild):
     np.testing.assert_allclose(gf, feat.grad.numpy(), rtol=1e-5, atol=1e-6)
 
 
+def test_roi_pool_mmcv_variant_hand_computed_and_where_it_meets_the_legacy_bins():
+    """mmcv 1.x's RoIPool bins (what lib/ops/__init__.py:6 imports; mmcv is absent, so there is nothing to run it
+    against: the restatement is pinned by a hand-computed case and by the case where both conventions must agree).
+    ROI (1.3, 2.6, 5.2, 6.9) at scale 0.5 -> x in [0.65, 3.1], y in [1.3, 3.95]; 2 x 2 bins of 1.225 x 1.325:
+    columns [0, 2) and [1, 4), rows [1, 3) and [2, 4); on feat = arange(64) the maxima are the bins' last elements."""
+    feat = np.arange(64, dtype=np.float32).reshape(1, 1, 8, 8)
+    rois = np.array([[0, 1.3, 2.6, 5.2, 6.9]], np.float32)
+    out, arg = roi_oracle.roi_pool_fwd(feat, rois, 2, 2, 0.5, variant="mmcv")
+    assert out.reshape(-1).tolist() == [17, 19, 25, 27] and arg.reshape(-1).tolist() == [17, 19, 25, 27]
+    legacy, _ = roi_oracle.roi_pool_fwd(feat, rois, 2, 2, 0.5)
+    assert legacy.reshape(-1).tolist() != out.reshape(-1).tolist()          # rounded corners: other bins
+    # degenerate ROI (x2 + 1 <= x1): mmcv pools nothing, the legacy kernel forces a 1 x 1 ROI
+    deg = np.array([[0, 6, 2, 4.5, 5]], np.float32)
+    o, a = roi_oracle.roi_pool_fwd(feat, deg, 2, 2, 0.5, variant="mmcv")
+    assert not o.any() and (a == -1).all()
+    # integer corners at scale 1: (x2 + 1) - x1 == x2 - x1 + 1 and floor(p * bin + y1) == floor(p * bin) + y1
+    rng = np.random.RandomState(0)
+    f = rng.randn(2, 3, 20, 24).astype(np.float32)
+    x1, y1 = rng.randint(-3, 20, 40), rng.randint(-3, 16, 40)
+    r = np.stack([rng.randint(0, 2, 40), x1, y1, x1 + rng.randint(0, 12, 40), y1 + rng.randint(0, 12, 40)], 1).astype(np.float32)
+    om, am = roi_oracle.roi_pool_fwd(f, r, 7, 7, 1.0, variant="mmcv")
+    ol, al = roi_oracle.roi_pool_fwd(f, r, 7, 7, 1.0)
+    np.testing.assert_array_equal(om, ol)
+    np.testing.assert_array_equal(am, al)
+    np.testing.assert_array_equal(om, tv_roi_pool(torch.from_numpy(f), torch.from_numpy(r), (7, 7), 1.0).numpy())
+
+
 def test_roi_align_empty():
     feat, _ = make_case(1)
     out = roi_oracle.roi_align_fwd(feat.numpy(), np.zeros((0, 5), np.float32), 7, 7, 0.25)

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--backbone", default="resnet50")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--pool", action="store_true", help="also time RoIPool forward / backward (both bin conventions)")
     ap.add_argument("--size", type=int, default=512, help="image side in pixels (map side = size / stride): the "
                     "reference trains at scales 480 .. 1200 (configs/resnet50_voc.yaml:34)")
     ap.add_argument("--debug-flags", type=int, default=0, help="cim_set_debug_flags (8 = global-pairs path instead "
@@ -79,6 +80,21 @@ def main():
     mb = (K * Cf * 49 * 4 + B * Cf * H * W * 4 + 20 * K) / 1e6
     tf, tb = timeit(fwd), timeit(bwd)
     print(f"{a.backbone} {H}x{W}x{Cf} flags={a.debug_flags}: roi_align fwd {tf:.3f} ms  {mb / tf:.1f} GB/s   bwd {tb:.3f} ms  {mb / tb:.1f} GB/s   ({mb:.0f} MB each)")
+
+    if a.pool:
+        argmax = torch.empty(K, Cf, 7, 7, dtype=torch.int32, device=dev)
+        for variant, name in ((1, "mmcv"), (0, "legacy")):
+            def pfwd():
+                _lib.check(L.cim_roi_pool_fwd_ex(_lib.ptr(feat), _lib.ptr(rois), _lib.ptr(out), _lib.ptr(argmax), B, Cf,
+                                                 H, W, K, 7, 7, scale, variant, st), "pool fwd")
+
+            def pbwd():
+                _lib.check(L.cim_roi_pool_bwd(_lib.ptr(gout), _lib.ptr(argmax), _lib.ptr(rois), _lib.ptr(gfeat), B, Cf,
+                                              H, W, K, 7, 7, st), "pool bwd")
+            mbp = (2 * K * Cf * 49 * 4 + B * Cf * H * W * 4 + 20 * K) / 1e6          # values + argmax + map
+            tpf, tpb = timeit(pfwd), timeit(pbwd)
+            print(f"roi_pool[{name}] fwd {tpf:.3f} ms  {mbp / tpf:.1f} GB/s   bwd {tpb:.3f} ms  {mbp / tpb:.1f} GB/s   "
+                  f"({mbp:.0f} MB each: pooled values + int32 argmax + the map)")
 
     if a.fused:
         masks = (torch.rand(K, 7, 7, device=dev, generator=g) > 0.5).float()
