@@ -216,10 +216,14 @@ __global__ void mask_area_kernel(const uint32_t *__restrict__ packed, int32_t *_
 // perm[k] = original index of the k-th mask in sorted order, inv = inverse.  For every block of 128 (A
 // operand) and 256 (B operand) sorted masks the union of the masks' K-block bitmaps is stored; a tile only
 // has to visit the K-blocks set in BOTH unions: everywhere else one operand is all zero.
+// tile_order != null: the CTA also ranks ITS image's tiles by the number of K-blocks they visit (longest first) and
+// writes rank r to tile_order[r * n_img + img] -- the images' rankings interleaved, which starts the long tiles of
+// every image first without a second, single-CTA launch over all tiles (mask_tile_order_kernel: 28 us at cfg2).
 __global__ void __launch_bounds__(1024)
 mask_sort_kernel(const int4 *__restrict__ kinfo_all, const uint32_t *__restrict__ kbmap_all, int n, int npad, int bw,
                  int kb_per_row, int nkb, int32_t *__restrict__ perm_all, int32_t *__restrict__ inv_all,
-                 uint32_t *__restrict__ umap_a, uint32_t *__restrict__ umap_b, int nrb, int ncb) {
+                 uint32_t *__restrict__ umap_a, uint32_t *__restrict__ umap_b, int nrb, int ncb,
+                 int32_t *__restrict__ tile_order, int per_img, int tpad) {
     extern __shared__ __align__(16) unsigned char sort_smem[];
     int *key = reinterpret_cast<int *>(sort_smem);        // [npad]
     int *idx = key + npad;                                // [npad]
@@ -264,6 +268,37 @@ mask_sort_kernel(const int4 *__restrict__ kinfo_all, const uint32_t *__restrict_
         if (is_a) umap_a[((size_t)img * nrb + blk) * bw + j] = u;
         else umap_b[((size_t)img * ncb + (blk - nrb)) * bw + j] = u;
     }
+    if (!tile_order) return;
+    __threadfence_block();
+    __syncthreads();                                      // the unions are written; key / idx are free again
+    for (int t = tid; t < tpad; t += nthr) {
+        int k = 0x7fffffff, code = -1;
+        if (t < per_img) {
+            int rem = t, ti = 0;
+            while (rem >= ncb - (ti >> 1)) { rem -= ncb - (ti >> 1); ++ti; }
+            const int tj = (ti >> 1) + rem;
+            const uint32_t *ua = umap_a + ((size_t)img * nrb + ti) * bw, *ub = umap_b + ((size_t)img * ncb + tj) * bw;
+            int c = 0;
+            for (int j = 0; j < bw; ++j) c += __popc(ua[j] & ub[j]);
+            k = -c;
+            code = (img << 16) | (ti << 8) | tj;
+        }
+        key[t] = k;
+        idx[t] = code;
+    }
+    __syncthreads();
+    for (int size = 2; size <= tpad; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = tid; t < (tpad >> 1); t += nthr) {
+                const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                const bool asc = (lo & size) == 0;
+                const int ka = key[lo], kb = key[hi], ia = idx[lo], ib = idx[hi];
+                const bool a_first = ka < kb || (ka == kb && ia < ib);
+                if (asc ? !a_first : a_first) { key[lo] = kb; key[hi] = ka; idx[lo] = ib; idx[hi] = ia; }
+            }
+            __syncthreads();
+        }
+    for (int t = tid; t < per_img; t += nthr) tile_order[(size_t)t * gridDim.x + img] = idx[t];
 }
 
 // Longest tile first: the tiles of all images sorted by the number of K-blocks they visit (descending), so
@@ -527,6 +562,44 @@ OverlapWs carve_overlap_ws(void *base, int n_img, int n, long long words, int wa
 }
 }  // namespace
 
+namespace {
+struct MaskMeta {
+    int32_t *area;
+    int4 *kinfo;
+    uint32_t *kbmap;
+    size_t bytes;
+};
+MaskMeta carve_meta(void *base, int n_img, int n, long long words) {
+    MaskMeta m{};
+    const size_t nm = (size_t)(n_img > 0 ? n_img : 0) * (size_t)(n > 0 ? n : 0);
+    const int bw = (int)(((words + 3) / 4 + 31) / 32);
+    char *p = (char *)base;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { char *q = p ? p + o : nullptr; o += up256(bytes); return q; };
+    m.area = (int32_t *)take(nm * 4);
+    m.kinfo = (int4 *)take(nm * 16);
+    m.kbmap = (uint32_t *)take(nm * bw * 4);
+    m.bytes = o;
+    return m;
+}
+}  // namespace
+
+CIM_API size_t cim_mask_meta_bytes(int n_img, int n, int64_t words) { return carve_meta(nullptr, n_img, n, words).bytes; }
+
+CIM_API int cim_mask_meta(const uint32_t *packed, int n_img, int n, int64_t words, int kb_per_row, void *meta,
+                          size_t meta_bytes, cim_stream_t stream) {
+    if (!packed || !meta || n_img < 0 || n < 0 || words <= 0 || kb_per_row < 0) return CIM_ERR_ARG;
+    if ((words & 3) || !cim_aligned(packed, 16)) return CIM_ERR_ALIGN;
+    if (meta_bytes < cim_mask_meta_bytes(n_img, n, words) || !cim_aligned(meta, 256)) return CIM_ERR_WORKSPACE;
+    if (n_img == 0 || n == 0) return CIM_OK;
+    const MaskMeta m = carve_meta(meta, n_img, n, words);
+    const long long n_masks = (long long)n_img * n;
+    const int bw = (int)(((words + 3) / 4 + 31) / 32);
+    mask_area_kernel<<<(unsigned)((n_masks + 7) / 8), 256, 0, (cudaStream_t)stream>>>(packed, m.area, m.kbmap, m.kinfo,
+                                                                                       n_masks, words, bw, kb_per_row);
+    return cim_launch_status();
+}
+
 CIM_API size_t cim_mask_overlap_workspace_bytes(int n_img, int n, int64_t words, int want_inter) {
     return carve_overlap_ws(nullptr, n_img, n, words, want_inter).bytes;
 }
@@ -548,6 +621,13 @@ CIM_API int cim_mask_overlap_algo(const uint32_t *packed, int n_img, int n, int6
 CIM_API int cim_mask_overlap_ex(const uint32_t *packed, int n_img, int n, int64_t words, int kb_per_row,
                                 int32_t *inter, int32_t *area, void *iou_f16, void *asy_f16, void *workspace,
                                 size_t ws_bytes, int algo, cim_stream_t stream) {
+    return cim_mask_overlap_meta(packed, nullptr, n_img, n, words, kb_per_row, inter, area, iou_f16, asy_f16, workspace,
+                                 ws_bytes, algo, stream);
+}
+
+CIM_API int cim_mask_overlap_meta(const uint32_t *packed, const void *meta, int n_img, int n, int64_t words,
+                                  int kb_per_row, int32_t *inter, int32_t *area, void *iou_f16, void *asy_f16,
+                                  void *workspace, size_t ws_bytes, int algo, cim_stream_t stream) {
     if (algo != CIM_OVERLAP_AUTO && algo != CIM_OVERLAP_POPC && algo != CIM_OVERLAP_TENSOR) return CIM_ERR_ARG;
     if (!packed || !iou_f16 || !asy_f16 || n_img < 0 || n < 0 || words <= 0 || kb_per_row < 0) return CIM_ERR_ARG;
     if (words * 32 >= (1LL << 24)) return CIM_ERR_SHAPE;      // counts must stay exact in fp32
@@ -561,40 +641,44 @@ CIM_API int cim_mask_overlap_ex(const uint32_t *packed, int n_img, int n, int64_
     const size_t need = use_tc ? cim_mask_overlap_workspace_bytes(n_img, n, words, inter != nullptr)
                                : (area ? 0 : 2 * up256(sizeof(int32_t) * (size_t)n_img * n) + 512);
     if (need && (!workspace || ws_bytes < need || !cim_aligned(workspace, 256))) return CIM_ERR_WORKSPACE;
-    const OverlapWs w = carve_overlap_ws(workspace, n_img, n, words, inter != nullptr);
-    if (!area) area = w.area;
+    OverlapWs w = carve_overlap_ws(workspace, n_img, n, words, inter != nullptr);
     const long long n_masks = (long long)n_img * n;
-    mask_area_kernel<<<(unsigned)((n_masks + 7) / 8), 256, 0, st>>>(packed, area, use_tc ? w.kbmap : nullptr,
-                                                                    use_tc ? w.kinfo : nullptr, n_masks, words, w.bw,
-                                                                    kb_per_row);
-    int rc = cim_launch_status();
-    if (rc) return rc;
+    int rc;
+    if (meta) {
+        // areas, K-block occupancy bitmaps and sort keys were produced with the masks (cim_mask_meta): no pass over
+        // the packed masks here.  (meta must come from the same packed / words / kb_per_row; tensor-path layout.)
+        if (!cim_aligned(meta, 256) || (words & 3)) return CIM_ERR_ALIGN;
+        const MaskMeta mm = carve_meta(const_cast<void *>(meta), n_img, n, words);
+        if (area) cudaMemcpyAsync(area, mm.area, sizeof(int32_t) * (size_t)n_masks, cudaMemcpyDeviceToDevice, st);
+        area = mm.area;
+        w.kinfo = mm.kinfo;
+        w.kbmap = mm.kbmap;
+    } else {
+        if (!area) area = w.area;
+        mask_area_kernel<<<(unsigned)((n_masks + 7) / 8), 256, 0, st>>>(packed, area, use_tc ? w.kbmap : nullptr,
+                                                                        use_tc ? w.kinfo : nullptr, n_masks, words, w.bw,
+                                                                        kb_per_row);
+        if ((rc = cim_launch_status())) return rc;
+    }
     __half *iou = reinterpret_cast<__half *>(iou_f16), *asy = reinterpret_cast<__half *>(asy_f16);
     if (use_tc) {
         int npad = 1;
         while (npad < n) npad <<= 1;
         const int nrb = (n + 127) / 128, ncb = (n + 255) / 256;
+        int per_img = 0;
+        for (int i = 0; i < nrb; ++i) per_img += ncb - (i >> 1);
+        int tpad = 1;
+        while (tpad < per_img) tpad <<= 1;
+        // longest tiles first: ranked per image inside the sort kernel, the images' rankings interleaved
+        const bool ordered = n_img < 32768 && nrb < 256 && ncb < 256 && tpad <= npad;
         const size_t smem_sort = (size_t)npad * 8;
         cudaFuncSetAttribute(mask_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sort);
         mask_sort_kernel<<<n_img, 1024, smem_sort, st>>>(w.kinfo, w.kbmap, n, npad, w.bw, kb_per_row,
                                                          (int)((words + 3) / 4), w.perm, w.inv, w.umap_a, w.umap_b,
-                                                         nrb, ncb);
+                                                         nrb, ncb, ordered ? w.tile_order : nullptr, per_img, tpad);
         if ((rc = cim_launch_status())) return rc;
         cudaMemsetAsync(w.visited, 0, 8, st);
-        int per_img = 0;
-        for (int i = 0; i < nrb; ++i) per_img += ncb - (i >> 1);
-        const long long ntiles = (long long)per_img * n_img;
-        const int32_t *order = nullptr;
-        if (ntiles <= 8192 && n_img < 32768 && nrb < 256 && ncb < 256) {     // else: the kernel's built-in order
-            int tpad = 1;
-            while (tpad < ntiles) tpad <<= 1;
-            if ((size_t)tpad * 8 > 48 * 1024)
-                cudaFuncSetAttribute(mask_tile_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tpad * 8);
-            mask_tile_order_kernel<<<1, 1024, (size_t)tpad * 8, st>>>(w.umap_a, w.umap_b, w.bw, n_img, nrb, ncb,
-                                                                      (int)ntiles, tpad, w.tile_order);
-            if ((rc = cim_launch_status())) return rc;
-            order = w.tile_order;
-        }
+        const int32_t *order = ordered ? w.tile_order : nullptr;
         // the tensor kernel works in sorted index space and writes sorted-order maps
         rc = cim_mask_overlap_tc_launch(packed, area, w.perm, w.umap_a, w.umap_b, w.bw, w.visited, order, n_img, n,
                                         words, w.tmp_inter, w.tmp_iou, w.tmp_asy, st);

@@ -160,13 +160,38 @@ def mask_pack(masks, layout="auto"):
     return _tag(packed, width // 16 if tiled else 0)
 
 
-def mask_overlap(packed, return_counts=False, algo="auto", kb_per_row=None, return_visited=False):
+def mask_meta(packed, kb_per_row=None, out=None, stream=None):
+    """Per-mask metadata of bit masks [n_img, N, words] (areas, occupancy bitmaps over 128-pixel K-blocks, sort keys)
+    for mask_overlap(..., meta=...) / CIMHeadStep.run(mask_meta=...): produced once WITH the masks (when a data set is
+    packed, or on the copy stream right after cim_mask_unpack_crops) instead of by a pass over all packed masks inside
+    every overlap call.  Opaque uint8 tensor (cim_mask_meta_bytes)."""
+    _lib.require_cuda(packed, "packed", torch.int32)
+    if kb_per_row is None:
+        kb_per_row = int(getattr(packed, "cim_kb_per_row", 0))
+    if packed.dim() == 2:
+        packed = packed.unsqueeze(0)
+    packed = packed.contiguous()
+    n_img, n, words = packed.shape
+    L = _lib.lib()
+    with torch.cuda.device(packed.device):
+        nbytes = L.cim_mask_meta_bytes(n_img, n, words)
+        if out is None:
+            out = torch.empty(nbytes, dtype=torch.uint8, device=packed.device)
+        rc = L.cim_mask_meta(_lib.ptr(packed), n_img, n, words, int(kb_per_row), _lib.ptr(out), out.numel(),
+                             stream if stream is not None else _lib.stream_ptr(packed.device))
+    _lib.check(rc, "cim_mask_meta")
+    return out
+
+
+def mask_overlap(packed, return_counts=False, algo="auto", kb_per_row=None, return_visited=False, meta=None):
     """Bit masks [N, words] or [n_img, N, words] (int32) -> (iou_map, asy_iou_map) float16
     [.., N, N]; with return_counts also (inter int32 [.., N, N], area int32 [.., N]).
     algo: "auto" | "popc" (AND + POPC kernel) | "tensor" (tcgen05 int8 kernel).
     kb_per_row: W // 16 for masks in the tiled pixel order, 0 for flat; None = what mask_pack / unpack_crops
     recorded on the tensor (0 if nothing was).  It only steers the locality sort of the tensor path.
-    return_visited: also return the number of K-blocks the tensor path visited (int, 0 on the popc path)."""
+    return_visited: also return the number of K-blocks the tensor path visited (int, 0 on the popc path).
+    meta: the tensor mask_meta(packed) returned (same packed / kb_per_row): the call then skips its own pass over the
+    packed masks."""
     _lib.require_cuda(packed, "packed", torch.int32)
     if kb_per_row is None:
         kb_per_row = int(getattr(packed, "cim_kb_per_row", 0))
@@ -188,10 +213,10 @@ def mask_overlap(packed, return_counts=False, algo="auto", kb_per_row=None, retu
                          device=dev)
         if return_visited:
             ws[:8].zero_()
-        rc = L.cim_mask_overlap_ex(_lib.ptr(packed), n_img, n, words, int(kb_per_row), _lib.ptr(inter),
-                                   _lib.ptr(area), _lib.ptr(iou), _lib.ptr(asy), _lib.ptr(ws), ws.numel(),
-                                   _lib.OVERLAP_ALGOS[algo], _lib.stream_ptr(dev))
-    _lib.check(rc, "cim_mask_overlap_ex")
+        rc = L.cim_mask_overlap_meta(_lib.ptr(packed), _lib.ptr(meta), n_img, n, words, int(kb_per_row),
+                                     _lib.ptr(inter), _lib.ptr(area), _lib.ptr(iou), _lib.ptr(asy), _lib.ptr(ws),
+                                     ws.numel(), _lib.OVERLAP_ALGOS[algo], _lib.stream_ptr(dev))
+    _lib.check(rc, "cim_mask_overlap_meta")
     outs = (iou, asy, inter, area) if return_counts else (iou, asy)
     outs = tuple(o.squeeze(0) for o in outs) if squeeze else outs
     if return_visited:

@@ -141,7 +141,7 @@ class CIMHeadStep:
 
     # -------------------------------------------------------------------------------------
     def run(self, feat, rois, grad_out, packed_masks, seg_x, weight, bias, labels, labels_host=None, grad_scores=None,
-            mat=None, mid_hook=None, order=None):
+            mat=None, mid_hook=None, order=None, mask_meta=None):
         """feat [n_img,Cf,H,W] f32, rois [n_img*R,5] f32 grouped by image, grad_out [n_img*R,Cf,7,7]
         f32, packed_masks [n_img,R,words] i32, seg_x [n_img*R,D] f32, weight [2+2K,C+1,D],
         bias [2+2K,C+1], labels [n_img,C] f32 (labels_host is no longer needed: the sampling runs on the device).
@@ -151,6 +151,8 @@ class CIMHeadStep:
         grad_bias; in a multi-process run the head-gradient bucket is averaged over the ranks (one NCCL
         allreduce, overlapped with the RoIAlign backward).  mat [n_img, R, C+1] (the dataset's proposal-cluster
         matrix, model_builder.py:125,203) adds PCL_loss: pcl_loss [n_img] and its gradient on the classifier head.
+        mask_meta: mask_ops.mask_meta(packed_masks), produced with the masks (data-set packing / input prefetch): the
+        overlap stage then skips its own pass over the 524 MB of packed masks.
 
         order (default: the constructor's):
           "graph"      the model's dependency order (model_builder.py:136-204): RoIAlign forward -> scoring heads ->
@@ -188,9 +190,9 @@ class CIMHeadStep:
 
         def overlap(stream):
             with _nvtx("cim/mask_overlap"):
-                ck(L.cim_mask_overlap_ex(P(packed_masks), n_img, R, self.words, self.kb_per_row, None, P(self.area),
-                                         P(self.iou), P(self.asy), P(self.overlap_ws), self.overlap_ws.numel(), 0,
-                                         stream), "cim_mask_overlap_ex")
+                ck(L.cim_mask_overlap_meta(P(packed_masks), P(mask_meta), n_img, R, self.words, self.kb_per_row, None,
+                                           P(self.area), P(self.iou), P(self.asy), P(self.overlap_ws),
+                                           self.overlap_ws.numel(), 0, stream), "cim_mask_overlap_meta")
 
         def roi_fwd():
             with _nvtx("cim/roi_align_fwd"):
@@ -329,6 +331,11 @@ class CIMHeadStep:
                 for buf in self.di:
                     buf.update(crop_words=dv((self.crop_cap,), torch.int32), crop_meta=dv((n_img * R, 4), torch.int32),
                                crop_off=dv((n_img * R,), torch.int64))
+            # mask metadata (areas, K-block bitmaps) produced on the copy stream right after the masks land
+            self.use_meta = self.words % 4 == 0
+            if self.use_meta:
+                for buf in self.di:
+                    buf["meta"] = dv((self.L.cim_mask_meta_bytes(n_img, R, self.words),), torch.uint8)
             self.d_checksum = dv((2,), torch.float32)
             self.copy_stream = torch.cuda.Stream(device=self.dev)
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in (self.hi_rois, self.hi_labels))
@@ -376,6 +383,10 @@ class CIMHeadStep:
                 self.last_mask_h2d_bytes = n * 4 + self.hi_crop_meta.numel() * 4 + self.hi_crop_off.numel() * 8
             else:
                 buf["masks"].copy_(self.hi_masks, non_blocking=True)
+            if self.use_meta:
+                _lib.check(self.L.cim_mask_meta(_lib.ptr(buf["masks"]), self.n_img, self.R, self.words, self.kb_per_row,
+                                                _lib.ptr(buf["meta"]), buf["meta"].numel(),
+                                                C.c_void_p(self.copy_stream.cuda_stream)), "cim_mask_meta")
             buf["ready"].record(self.copy_stream)
         return self
 
@@ -412,7 +423,7 @@ class CIMHeadStep:
             self.stage_host_inputs()                           # goes to the other buffer
         cur_stream.wait_event(buf["ready"])
         self.run(feat, buf["rois"], grad_out, buf["masks"], seg_x, weight, bias, buf["labels"],
-                 None, grad_scores=grad_scores, mat=mat,
+                 None, grad_scores=grad_scores, mat=mat, mask_meta=buf.get("meta"),
                  mid_hook=self._collect_results if lag_results else None)
         buf["free"].record(cur_stream)
         self.d_checksum[0] = self.roi_out.view(-1)[::4099].sum()

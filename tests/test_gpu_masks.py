@@ -181,6 +181,29 @@ def test_tensor_core_pipeline_variants_agree(variant):
     assert_f16_bits_equal(u16(got[1]), u16(want[1]))
 
 
+@pytest.mark.parametrize("layout", ["tiled", "flat"])
+def test_overlap_with_precomputed_mask_meta_is_bit_identical(layout):
+    """cim_mask_meta + cim_mask_overlap_meta (areas / K-block bitmaps produced with the masks) == the self-contained
+    call, for 3 images at once (the per-image tile ranking is interleaved over the images), both pixel orders."""
+    n, side = 520, 128
+    ms = []
+    for b in range(3):
+        m = synth.rasterize(synth.proposal_params(n, side, 900 + b))
+        m[b + 1] = 0
+        ms.append(m)
+    packed = torch.stack([mask_ops.mask_pack(m.to(DEV), layout=layout) for m in ms])
+    kb = side // 16 if layout == "tiled" else 0
+    want = mask_ops.mask_overlap(packed, return_counts=True, algo="tensor", kb_per_row=kb)
+    meta = mask_ops.mask_meta(packed, kb)
+    got = mask_ops.mask_overlap(packed, return_counts=True, algo="tensor", kb_per_row=kb, meta=meta)
+    pop = mask_ops.mask_overlap(packed, return_counts=True, algo="popc")
+    for a, b_, c in zip(got, want, pop):
+        v = lambda t: t.view(torch.int16) if t.dtype == torch.float16 else t
+        assert torch.equal(v(a)[~torch.isnan(a.float())], v(b_)[~torch.isnan(b_.float())])
+        assert torch.equal(torch.isnan(a.float()), torch.isnan(c.float()))
+        assert torch.equal(v(a)[~torch.isnan(a.float())], v(c)[~torch.isnan(c.float())])
+
+
 def test_tensor_path_rejects_what_it_cannot_take():
     packed = mask_ops.mask_pack(torch.ones(70, 5, 5, dtype=torch.uint8, device=DEV))      # 1 word per mask
     with pytest.raises(RuntimeError, match="shape"):
