@@ -120,6 +120,67 @@ __global__ void mask_unpack_crops_tiled_kernel(const uint32_t *__restrict__ crop
     }
 }
 
+// Crops -> tiled bit masks AND their metadata in ONE pass, one warp per mask: a lane builds one K-block (an 8 x 16
+// pixel patch = 4 words = rows 2j, 2j + 1 of the patch per word) from the crop words that cover it (or zeros outside
+// the crop: no memset of the 524 MB beforehand), stores it with one 16-byte store, and keeps what mask_area_kernel
+// would have to re-read the masks for: popcount, the ballot of "patch not empty" (= one word of the K-block bitmap)
+// and the occupied block range (sort key).
+__global__ void mask_unpack_crops_tiled_meta_kernel(const uint32_t *__restrict__ crop_words, const int32_t *__restrict__ meta,
+                                                    const long long *__restrict__ off, uint32_t *__restrict__ packed,
+                                                    int32_t *__restrict__ area, uint32_t *__restrict__ kbmap,
+                                                    int4 *__restrict__ kinfo, long long n_masks, int H, int W,
+                                                    long long words, int bw) {
+    const long long m = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (m >= n_masks) return;
+    const int lane = threadIdx.x & 31;
+    const int wx0 = meta[4 * m], y0 = meta[4 * m + 1], ww = meta[4 * m + 2], h = meta[4 * m + 3];
+    const uint32_t *src = crop_words + off[m];
+    uint4 *row4 = reinterpret_cast<uint4 *>(packed + m * words);
+    const int bpr = W >> 4, nkb = (int)(words >> 2), nblk = (H >> 3) * bpr;
+    int s = 0, alo = 0x7fffffff, ahi = -1, blo = 0x7fffffff, bhi = -1;
+    for (int j = 0; j < bw; ++j) {
+        const int kb = j * 32 + lane;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (kb < nblk) {
+            const int by = kb / bpr, bx = kb - by * bpr;
+            const int k = (bx >> 1) - wx0;                       // crop word column holding these 16 pixels
+            if (k >= 0 && k < ww) {
+                const int sh = (bx & 1) * 16;
+                uint32_t o[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int r0 = 8 * by + 2 * q - y0, r1 = r0 + 1;
+                    const uint32_t lo = (r0 >= 0 && r0 < h) ? (__ldg(src + (long long)r0 * ww + k) >> sh) & 0xffffu : 0u;
+                    const uint32_t hi = (r1 >= 0 && r1 < h) ? (__ldg(src + (long long)r1 * ww + k) >> sh) & 0xffffu : 0u;
+                    o[q] = lo | (hi << 16);
+                }
+                v = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        }
+        if (kb < nkb) row4[kb] = v;
+        s += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+        const bool nz = (v.x | v.y | v.z | v.w) != 0u;
+        const uint32_t bm = __ballot_sync(0xffffffffu, nz);
+        if (lane == 0) kbmap[m * bw + j] = bm;
+        if (nz) {
+            const int by = kb / bpr, bx = kb - by * bpr;
+            alo = min(alo, bx); ahi = max(ahi, bx); blo = min(blo, by); bhi = max(bhi, by);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        alo = min(alo, __shfl_xor_sync(0xffffffffu, alo, o));
+        ahi = max(ahi, __shfl_xor_sync(0xffffffffu, ahi, o));
+        blo = min(blo, __shfl_xor_sync(0xffffffffu, blo, o));
+        bhi = max(bhi, __shfl_xor_sync(0xffffffffu, bhi, o));
+    }
+    if (lane == 0) {
+        area[m] = s;
+        kinfo[m] = ahi >= 0 ? make_int4(1, alo + ahi, blo + bhi, 0) : make_int4(0, 0, 0, 0);
+    }
+}
+
 // ------------------------------------------------------------------------------- unpack crops
 // Wire format for proposal masks (host -> device): only the bounding box of every mask is sent.
 // crop row r, word k holds pixels (y0 + r, 32 * wx0 + 32 k .. + 31); it is OR-ed into the flat
@@ -597,6 +658,24 @@ CIM_API int cim_mask_meta(const uint32_t *packed, int n_img, int n, int64_t word
     const int bw = (int)(((words + 3) / 4 + 31) / 32);
     mask_area_kernel<<<(unsigned)((n_masks + 7) / 8), 256, 0, (cudaStream_t)stream>>>(packed, m.area, m.kbmap, m.kinfo,
                                                                                        n_masks, words, bw, kb_per_row);
+    return cim_launch_status();
+}
+
+CIM_API int cim_mask_unpack_crops_tiled_meta(const uint32_t *crop_words, const int32_t *crop_meta, const int64_t *crop_off,
+                                             uint32_t *packed, void *meta, size_t meta_bytes, int n_img, int n, int H,
+                                             int W, int64_t words, cim_stream_t stream) {
+    if (!crop_words || !crop_meta || !crop_off || !packed || !meta || n_img < 0 || n < 0 || H <= 0 || W <= 0)
+        return CIM_ERR_ARG;
+    if ((H & 7) || (W & 15)) return CIM_ERR_SHAPE;
+    if (words * 32 != (int64_t)H * W || (words & 3) || !cim_aligned(packed, 16)) return CIM_ERR_ALIGN;
+    if (meta_bytes < cim_mask_meta_bytes(n_img, n, words) || !cim_aligned(meta, 256)) return CIM_ERR_WORKSPACE;
+    if (n_img == 0 || n == 0) return CIM_OK;
+    const MaskMeta mm = carve_meta(meta, n_img, n, words);
+    const long long n_masks = (long long)n_img * n;
+    const int bw = (int)(((words + 3) / 4 + 31) / 32);
+    mask_unpack_crops_tiled_meta_kernel<<<(unsigned)((n_masks + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+        crop_words, crop_meta, reinterpret_cast<const long long *>(crop_off), packed, mm.area, mm.kbmap, mm.kinfo,
+        n_masks, H, W, words, bw);
     return cim_launch_status();
 }
 

@@ -375,15 +375,27 @@ class CIMHeadStep:
                 buf["crop_words"][:n].copy_(self.hi_crop_words[:n], non_blocking=True)
                 buf["crop_meta"].copy_(self.hi_crop_meta, non_blocking=True)
                 buf["crop_off"].copy_(self.hi_crop_off, non_blocking=True)
-                unpack = self.L.cim_mask_unpack_crops_tiled if self.kb_per_row else self.L.cim_mask_unpack_crops
-                rc = unpack(_lib.ptr(buf["crop_words"]), _lib.ptr(buf["crop_meta"]), _lib.ptr(buf["crop_off"]),
-                            _lib.ptr(buf["masks"]), self.n_img * self.R, self.mask_hw[0], self.mask_hw[1], self.words,
-                            C.c_void_p(self.copy_stream.cuda_stream))
-                _lib.check(rc, "cim_mask_unpack_crops")
+                fused = bool(self.kb_per_row) and self.use_meta and self.words * 32 == self.mask_hw[0] * self.mask_hw[1]
+                if fused:
+                    # crops -> tiled bit masks + their metadata in one pass (every packed word written once)
+                    rc = self.L.cim_mask_unpack_crops_tiled_meta(
+                        _lib.ptr(buf["crop_words"]), _lib.ptr(buf["crop_meta"]), _lib.ptr(buf["crop_off"]),
+                        _lib.ptr(buf["masks"]), _lib.ptr(buf["meta"]), buf["meta"].numel(), self.n_img, self.R,
+                        self.mask_hw[0], self.mask_hw[1], self.words, C.c_void_p(self.copy_stream.cuda_stream))
+                    _lib.check(rc, "cim_mask_unpack_crops_tiled_meta")
+                    buf["meta_done"] = True
+                else:
+                    unpack = self.L.cim_mask_unpack_crops_tiled if self.kb_per_row else self.L.cim_mask_unpack_crops
+                    rc = unpack(_lib.ptr(buf["crop_words"]), _lib.ptr(buf["crop_meta"]), _lib.ptr(buf["crop_off"]),
+                                _lib.ptr(buf["masks"]), self.n_img * self.R, self.mask_hw[0], self.mask_hw[1],
+                                self.words, C.c_void_p(self.copy_stream.cuda_stream))
+                    _lib.check(rc, "cim_mask_unpack_crops")
+                    buf["meta_done"] = False
                 self.last_mask_h2d_bytes = n * 4 + self.hi_crop_meta.numel() * 4 + self.hi_crop_off.numel() * 8
             else:
                 buf["masks"].copy_(self.hi_masks, non_blocking=True)
-            if self.use_meta:
+                buf["meta_done"] = False
+            if self.use_meta and not buf["meta_done"]:
                 _lib.check(self.L.cim_mask_meta(_lib.ptr(buf["masks"]), self.n_img, self.R, self.words, self.kb_per_row,
                                                 _lib.ptr(buf["meta"]), buf["meta"].numel(),
                                                 C.c_void_p(self.copy_stream.cuda_stream)), "cim_mask_meta")

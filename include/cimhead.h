@@ -207,6 +207,12 @@ int cim_mask_overlap_ex(const uint32_t *packed, int n_img, int n, int64_t words,
  * cim_mask_meta_bytes() bytes, 256-byte aligned, tied to (packed, n_img, n, words, kb_per_row); words % 4 == 0 and a
  * 16-byte aligned `packed` (CIM_ERR_ALIGN otherwise).  meta == NULL: identical to cim_mask_overlap_ex. */
 size_t cim_mask_meta_bytes(int n_img, int n, int64_t words);
+/* cim_mask_unpack_crops_tiled and cim_mask_meta in one pass over the crops: every packed word is written exactly once
+ * (zeros outside the crop, so no memset of `packed` beforehand) and the metadata falls out of the same registers.
+ * words * 32 == H * W, H % 8 == 0, W % 16 == 0; crops must lie inside the image. */
+int cim_mask_unpack_crops_tiled_meta(const uint32_t *crop_words, const int32_t *crop_meta, const int64_t *crop_off,
+                                     uint32_t *packed, void *meta, size_t meta_bytes, int n_img, int n, int H, int W,
+                                     int64_t words, cim_stream_t stream);
 int cim_mask_meta(const uint32_t *packed, int n_img, int n, int64_t words, int kb_per_row, void *meta,
                   size_t meta_bytes, cim_stream_t stream);
 int cim_mask_overlap_meta(const uint32_t *packed, const void *meta, int n_img, int n, int64_t words, int kb_per_row,

@@ -204,6 +204,44 @@ def test_overlap_with_precomputed_mask_meta_is_bit_identical(layout):
         assert torch.equal(v(a)[~torch.isnan(a.float())], v(c)[~torch.isnan(c.float())])
 
 
+def test_fused_crop_unpack_and_meta_equals_the_two_separate_calls():
+    """cim_mask_unpack_crops_tiled_meta == cim_mask_unpack_crops_tiled (after a memset) + cim_mask_meta, bit for bit,
+    incl. empty masks, crops touching the borders and garbage in the destination beforehand."""
+    import ctypes as C
+    from cim_b200 import _lib
+    n_img, n, h, w = 2, 150, 64, 96
+    g = torch.Generator().manual_seed(7)
+    masks = torch.zeros(n_img * n, h, w, dtype=torch.uint8)
+    for i in range(n_img * n):
+        if i % 37 == 5:
+            continue                                                     # an empty mask
+        y0, x0 = int(torch.randint(0, h - 1, (1,), generator=g)), int(torch.randint(0, w - 1, (1,), generator=g))
+        y1, x1 = int(torch.randint(y0 + 1, h + 1, (1,), generator=g)), int(torch.randint(x0 + 1, w + 1, (1,), generator=g))
+        masks[i, y0:y1, x0:x1] = (torch.rand(y1 - y0, x1 - x0, generator=g) < 0.6).to(torch.uint8)
+    c = mask_ops.pack_crops_host(masks)
+    crops = mask_ops.MaskCrops(c.words.to(DEV), c.meta.to(DEV), c.off.to(DEV), c.height, c.width)
+    want = mask_ops.unpack_crops(crops, layout="tiled").view(n_img, n, -1)
+    words = want.shape[-1]
+    want_meta = mask_ops.mask_meta(want, w // 16)
+    L = _lib.lib()
+    got = torch.full_like(want, -1)
+    meta = torch.full_like(want_meta, 0x5A)
+    _lib.check(L.cim_mask_unpack_crops_tiled_meta(_lib.ptr(crops.words), _lib.ptr(crops.meta), _lib.ptr(crops.off),
+                                                  _lib.ptr(got), _lib.ptr(meta), meta.numel(), n_img, n, h, w, words,
+                                                  _lib.stream_ptr(torch.device(DEV))), "fused unpack")
+    assert torch.equal(got, want)
+    nm = n_img * n
+    bw = ((words // 4) + 31) // 32
+    up = lambda v: (v + 255) & ~255
+    a0, k0, b0 = 0, up(nm * 4), up(nm * 4) + up(nm * 16)
+    assert torch.equal(meta[a0:a0 + nm * 4], want_meta[a0:a0 + nm * 4])                    # areas
+    assert torch.equal(meta[k0:k0 + nm * 16], want_meta[k0:k0 + nm * 16])                  # sort keys
+    assert torch.equal(meta[b0:b0 + nm * bw * 4], want_meta[b0:b0 + nm * bw * 4])          # K-block bitmaps
+    iou1, asy1 = mask_ops.mask_overlap(got, algo="popc")
+    iou2, asy2 = mask_ops.mask_overlap(got, algo="popc", meta=meta, kb_per_row=w // 16)
+    assert_f16_bits_equal(u16(iou1), u16(iou2))
+
+
 def test_tensor_path_rejects_what_it_cannot_take():
     packed = mask_ops.mask_pack(torch.ones(70, 5, 5, dtype=torch.uint8, device=DEV))      # 1 word per mask
     with pytest.raises(RuntimeError, match="shape"):
