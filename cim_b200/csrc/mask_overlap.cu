@@ -277,14 +277,9 @@ __global__ void mask_area_kernel(const uint32_t *__restrict__ packed, int32_t *_
 // perm[k] = original index of the k-th mask in sorted order, inv = inverse.  For every block of 128 (A
 // operand) and 256 (B operand) sorted masks the union of the masks' K-block bitmaps is stored; a tile only
 // has to visit the K-blocks set in BOTH unions: everywhere else one operand is all zero.
-// tile_order != null: the CTA also ranks ITS image's tiles by the number of K-blocks they visit (longest first) and
-// writes rank r to tile_order[r * n_img + img] -- the images' rankings interleaved, which starts the long tiles of
-// every image first without a second, single-CTA launch over all tiles (mask_tile_order_kernel: 28 us at cfg2).
 __global__ void __launch_bounds__(1024)
-mask_sort_kernel(const int4 *__restrict__ kinfo_all, const uint32_t *__restrict__ kbmap_all, int n, int npad, int bw,
-                 int kb_per_row, int nkb, int32_t *__restrict__ perm_all, int32_t *__restrict__ inv_all,
-                 uint32_t *__restrict__ umap_a, uint32_t *__restrict__ umap_b, int nrb, int ncb,
-                 int32_t *__restrict__ tile_order, int per_img, int tpad) {
+mask_sort_kernel(const int4 *__restrict__ kinfo_all, int n, int npad, int kb_per_row, int nkb,
+                 int32_t *__restrict__ perm_all, int32_t *__restrict__ inv_all) {
     extern __shared__ __align__(16) unsigned char sort_smem[];
     int *key = reinterpret_cast<int *>(sort_smem);        // [npad]
     int *idx = key + npad;                                // [npad]
@@ -318,34 +313,51 @@ mask_sort_kernel(const int4 *__restrict__ kinfo_all, const uint32_t *__restrict_
         }
     int32_t *perm = perm_all + (size_t)img * n, *inv = inv_all + (size_t)img * n;
     for (int i = tid; i < n; i += nthr) { perm[i] = idx[i]; inv[idx[i]] = i; }
-    // union bitmaps: one (block, bitmap word) per thread
+}
+
+// union bitmaps of the sorted 128- (A operand) and 256-mask (B operand) blocks: one CTA per (block, image), one
+// thread per bitmap word (the sort kernel used to do this with its 8 CTAs: 55 us of the stage)
+__global__ void __launch_bounds__(128)
+mask_union_kernel(const uint32_t *__restrict__ kbmap_all, const int32_t *__restrict__ perm_all, int n, int bw,
+                  uint32_t *__restrict__ umap_a, uint32_t *__restrict__ umap_b, int nrb, int ncb) {
+    const int blk = blockIdx.x, img = blockIdx.y;
+    const bool is_a = blk < nrb;
+    const int bs = is_a ? 128 : 256, b0 = (is_a ? blk : blk - nrb) * bs, b1 = min(n, b0 + bs);
     const uint32_t *kbm = kbmap_all + (size_t)img * n * bw;
-    for (int e = tid; e < (nrb + ncb) * bw; e += nthr) {
-        const int blk = e / bw, j = e - blk * bw;
-        const bool is_a = blk < nrb;
-        const int bs = is_a ? 128 : 256, b0 = (is_a ? blk : blk - nrb) * bs;
+    const int32_t *perm = perm_all + (size_t)img * n;
+    __shared__ int s_idx[256];
+    for (int i = threadIdx.x; i < b1 - b0; i += blockDim.x) s_idx[i] = perm[b0 + i];
+    __syncthreads();
+    for (int j = threadIdx.x; j < bw; j += blockDim.x) {
         uint32_t u = 0;
-        for (int i = b0; i < min(n, b0 + bs); ++i) u |= kbm[(size_t)idx[i] * bw + j];
+#pragma unroll 8
+        for (int i = 0; i < b1 - b0; ++i) u |= __ldg(kbm + (size_t)s_idx[i] * bw + j);
         if (is_a) umap_a[((size_t)img * nrb + blk) * bw + j] = u;
         else umap_b[((size_t)img * ncb + (blk - nrb)) * bw + j] = u;
     }
-    if (!tile_order) return;
-    __threadfence_block();
-    __syncthreads();                                      // the unions are written; key / idx are free again
-    for (int t = tid; t < tpad; t += nthr) {
-        int k = 0x7fffffff, code = -1;
-        if (t < per_img) {
-            int rem = t, ti = 0;
-            while (rem >= ncb - (ti >> 1)) { rem -= ncb - (ti >> 1); ++ti; }
-            const int tj = (ti >> 1) + rem;
-            const uint32_t *ua = umap_a + ((size_t)img * nrb + ti) * bw, *ub = umap_b + ((size_t)img * ncb + tj) * bw;
-            int c = 0;
-            for (int j = 0; j < bw; ++j) c += __popc(ua[j] & ub[j]);
-            k = -c;
-            code = (img << 16) | (ti << 8) | tj;
-        }
-        key[t] = k;
-        idx[t] = code;
+}
+
+// Longest tile first, per image: the CTA ranks ITS image's tiles by the number of K-blocks they visit and writes rank
+// r to tile_order[r * n_img + img] -- the images' rankings interleaved, which starts the long tiles of every image
+// first without a single-CTA sort over all tiles (mask_tile_order_kernel: 28 us at cfg2).
+__global__ void __launch_bounds__(256)
+mask_rank_kernel(const uint32_t *__restrict__ umap_a, const uint32_t *__restrict__ umap_b, int bw, int nrb, int ncb,
+                 int per_img, int tpad, int32_t *__restrict__ tile_order) {
+    extern __shared__ __align__(16) unsigned char sort_smem[];
+    int *key = reinterpret_cast<int *>(sort_smem);        // [tpad]
+    int *idx = key + tpad;                                // [tpad]
+    const int img = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    for (int t = tid; t < tpad; t += nthr) { key[t] = t < per_img ? 0 : 0x7fffffff; idx[t] = -1; }
+    __syncthreads();
+    for (int e = tid; e < per_img * bw; e += nthr) {      // (tile, bitmap word): coalesced over the words
+        const int t = e / bw, j = e - t * bw;
+        int rem = t, ti = 0;
+        while (rem >= ncb - (ti >> 1)) { rem -= ncb - (ti >> 1); ++ti; }
+        const int tj = (ti >> 1) + rem;
+        const int c = __popc(__ldg(umap_a + ((size_t)img * nrb + ti) * bw + j) &
+                             __ldg(umap_b + ((size_t)img * ncb + tj) * bw + j));
+        if (c) atomicSub(&key[t], c);
+        if (j == 0) idx[t] = (img << 16) | (ti << 8) | tj;
     }
     __syncthreads();
     for (int size = 2; size <= tpad; size <<= 1)
@@ -360,48 +372,6 @@ mask_sort_kernel(const int4 *__restrict__ kinfo_all, const uint32_t *__restrict_
             __syncthreads();
         }
     for (int t = tid; t < per_img; t += nthr) tile_order[(size_t)t * gridDim.x + img] = idx[t];
-}
-
-// Longest tile first: the tiles of all images sorted by the number of K-blocks they visit (descending), so
-// that the 1-CTA-per-SM waves of the tensor kernel end together.  tile code = img << 16 | ti << 8 | tj.
-__global__ void __launch_bounds__(1024)
-mask_tile_order_kernel(const uint32_t *__restrict__ umap_a, const uint32_t *__restrict__ umap_b, int bw, int n_img,
-                       int nrb, int ncb, int ntiles, int npad, int32_t *__restrict__ order) {
-    extern __shared__ __align__(16) unsigned char sort_smem[];
-    int *key = reinterpret_cast<int *>(sort_smem);        // [npad] visited K-blocks (negated: ascending sort)
-    int *val = key + npad;                                // [npad] tile code
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    int per_img = 0;
-    for (int i = 0; i < nrb; ++i) per_img += ncb - (i >> 1);
-    for (int t = tid; t < npad; t += nthr) {
-        int k = 0x7fffffff, code = -1;
-        if (t < ntiles) {
-            const int img = t / per_img;
-            int rem = t - img * per_img, ti = 0;
-            while (rem >= ncb - (ti >> 1)) { rem -= ncb - (ti >> 1); ++ti; }
-            const int tj = (ti >> 1) + rem;
-            const uint32_t *ua = umap_a + ((size_t)img * nrb + ti) * bw, *ub = umap_b + ((size_t)img * ncb + tj) * bw;
-            int c = 0;
-            for (int j = 0; j < bw; ++j) c += __popc(ua[j] & ub[j]);
-            k = -c;
-            code = (img << 16) | (ti << 8) | tj;
-        }
-        key[t] = k;
-        val[t] = code;
-    }
-    __syncthreads();
-    for (int size = 2; size <= npad; size <<= 1)
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int t = tid; t < (npad >> 1); t += nthr) {
-                const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
-                const bool asc = (lo & size) == 0;
-                const int ka = key[lo], kb = key[hi], ia = val[lo], ib = val[hi];
-                const bool a_first = ka < kb || (ka == kb && ia < ib);
-                if (asc ? !a_first : a_first) { key[lo] = kb; key[hi] = ka; val[lo] = ib; val[hi] = ia; }
-            }
-            __syncthreads();
-        }
-    for (int t = tid; t < ntiles; t += nthr) order[t] = val[t];
 }
 
 // out[i][j] = tmp[inv[i]][inv[j]] for both fp16 maps: one CTA per output row, the source rows go through smem
@@ -749,12 +719,16 @@ CIM_API int cim_mask_overlap_meta(const uint32_t *packed, const void *meta, int 
         int tpad = 1;
         while (tpad < per_img) tpad <<= 1;
         // longest tiles first: ranked per image inside the sort kernel, the images' rankings interleaved
-        const bool ordered = n_img < 32768 && nrb < 256 && ncb < 256 && tpad <= npad;
+        const bool ordered = n_img < 32768 && nrb < 256 && ncb < 256 && (size_t)tpad * 8 <= 48 * 1024;
         const size_t smem_sort = (size_t)npad * 8;
         cudaFuncSetAttribute(mask_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sort);
-        mask_sort_kernel<<<n_img, 1024, smem_sort, st>>>(w.kinfo, w.kbmap, n, npad, w.bw, kb_per_row,
-                                                         (int)((words + 3) / 4), w.perm, w.inv, w.umap_a, w.umap_b,
-                                                         nrb, ncb, ordered ? w.tile_order : nullptr, per_img, tpad);
+        mask_sort_kernel<<<n_img, 1024, smem_sort, st>>>(w.kinfo, n, npad, kb_per_row, (int)((words + 3) / 4), w.perm,
+                                                         w.inv);
+        mask_union_kernel<<<dim3((unsigned)(nrb + ncb), (unsigned)n_img), 128, 0, st>>>(w.kbmap, w.perm, n, w.bw,
+                                                                                        w.umap_a, w.umap_b, nrb, ncb);
+        if (ordered)
+            mask_rank_kernel<<<n_img, 256, (size_t)tpad * 8, st>>>(w.umap_a, w.umap_b, w.bw, nrb, ncb, per_img, tpad,
+                                                                    w.tile_order);
         if ((rc = cim_launch_status())) return rc;
         cudaMemsetAsync(w.visited, 0, 8, st);
         const int32_t *order = ordered ? w.tile_order : nullptr;
