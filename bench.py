@@ -649,6 +649,11 @@ def main():
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     peaks = load_peaks()
+    # one slice of the host cores per rank (before any pinned buffer is allocated) and as many numpy / torch host
+    # threads as the slice has: eight ranks otherwise share cores for their launch loops and sampling hops
+    cores = cdist.pin_rank_to_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+    if cores:
+        torch.set_num_threads(max(1, min(4, len(cores))))
 
     head = measure_training(args.workload, cfg, args, dev, rank, world, peaks, cdist, headline=True)
     others = {}

@@ -32,6 +32,26 @@ def init_from_env(backend=None):
     return rank, world, local
 
 
+def pin_rank_to_cores(local_rank, local_world):
+    """Give every rank of a node its own slice of the host cores (Linux): the per-step host work of a rank -- kernel
+    launches, the sampling hop's wait + random draw, the staging of the next inputs -- then does not migrate or share a
+    core with another rank's.  Call before allocating pinned buffers.  Returns the core list, or None when the node
+    has fewer cores than ranks or affinity is not supported."""
+    try:
+        avail = sorted(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        return None
+    per = len(avail) // max(local_world, 1)
+    if local_world <= 1 or per < 1:
+        return None
+    cores = avail[local_rank * per:(local_rank + 1) * per]
+    try:
+        os.sched_setaffinity(0, cores)
+    except OSError:
+        return None
+    return cores
+
+
 def shard_images(n_images, rank, world):
     """Images rank `rank` owns: g, g + world, ... (image-level data parallel)."""
     return list(range(rank, n_images, world))
