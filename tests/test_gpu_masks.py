@@ -323,3 +323,31 @@ def test_map_pickle_and_packed_store_round_trip(tmp_path):
     assert (h, w) == (128, 128) and torch.equal(back, packed)
     iou2, asy2 = mask_ops.mask_overlap(back)
     assert torch.equal(iou2.view(torch.int16), iou.view(torch.int16)) and torch.equal(asy2.view(torch.int16), asy.view(torch.int16))
+
+
+def test_benchmarked_overlap_kernel_256_sampled_rows_against_oracle_counts():
+    """The production instance of the tensor kernel (Cfg<4,2,4>: 2048 K-blocks per row at 512 x 512, tiled pixel order,
+    precomputed metadata) on one cfg2 image: 256 sampled rows x all 2000 columns against the oracle's integer counts
+    (mask_oracle.overlap_counts on the byte masks), fp16 maps bit-exact from those counts."""
+    R = 2000
+    params = synth.proposal_params(R, 512, 4321)
+    masks = synth.rasterize(params, device=DEV)
+    packed = mask_ops.mask_pack(masks)[None]
+    meta = mask_ops.mask_meta(packed)
+    iou, asy, inter, area = mask_ops.mask_overlap(packed, return_counts=True, algo="tensor", meta=meta)
+    rows = np.sort(np.random.RandomState(1).choice(R, 256, replace=False))
+    m_np = masks.cpu().numpy().reshape(R, -1)
+    o_area = m_np.sum(1, dtype=np.int64)
+    np.testing.assert_array_equal(area[0].cpu().numpy(), o_area)
+    sub_inter = np.zeros((256, R), np.int64)
+    a = m_np[rows].astype(np.float32)
+    for s in range(0, R, 500):                                 # exact in fp32: counts < 2^24
+        sub_inter[:, s:s + 500] = a @ m_np[s:s + 500].astype(np.float32).T
+    small_i, small_a = mask_oracle.overlap_counts(m_np[rows[:16]].reshape(16, 512, 512))   # the oracle's own counting
+    np.testing.assert_array_equal(sub_inter[:16][:, rows[:16]], small_i)
+    np.testing.assert_array_equal(inter[0].cpu().numpy()[rows], sub_inter)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        want_iou = (sub_inter.astype(np.float32) / (o_area[rows, None] + o_area[None, :] - sub_inter).astype(np.float32)).astype(np.float16)
+        want_asy = (sub_inter.astype(np.float32) / o_area[None, :].astype(np.float32)).astype(np.float16)
+    assert_f16_bits_equal(u16(iou[0])[rows], want_iou.view(np.uint16))
+    assert_f16_bits_equal(u16(asy[0])[rows], want_asy.view(np.uint16))
