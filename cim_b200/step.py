@@ -130,6 +130,9 @@ class CIMHeadStep:
         self.ev = torch.cuda.Event()
         self.last_uniform_bytes = 0
         self.side = torch.cuda.Stream(device=self.dev, priority=-2)     # scoring GEMM next to the overlap helpers: above the step
+        self.side2 = torch.cuda.Stream(device=self.dev, priority=-2)    # graph order: PCL_loss next to the mining kernels
+        self.ev_score = torch.cuda.Event()
+        self.ev_premine = torch.cuda.Event()
         self.trace = [] if os.environ.get("CIM_STEP_TRACE") else None
         # layer l reads (cls, det) = (predict_cls, predict_det) for l = 0, else (ref_cls[l-1], ref_iou[l-1])
         s = self.scores.view(nh, n_img, R, C1)
@@ -178,15 +181,19 @@ class CIMHeadStep:
         cur = torch.cuda.current_stream(dev)
         pcl_early = self.head_grads and grad_scores is None and mat is not None
 
-        def score_fwd(stream):
+        def pcl(stream):
+            # PCL_loss (model_builder.py:203) needs predict_cls and the cluster matrix only: 8 CTAs of pure latency;
+            # its gradient is added to head 0's after the loss block
+            with _nvtx("cim/pcl_loss"):
+                ck(L.cim_pcl_loss(P(self.scores), P(mat), P(self.pcl_loss), P(self.pcl_grad), n_img, R,
+                                  self.C + 1, PCL_MAX_ID, 1.0 / n_img, 0, stream), "cim_pcl_loss")
+
+        def score_fwd(stream, with_pcl):
             with _nvtx("cim/score_heads"):
                 ck(L.cim_score_heads(P(seg_x), P(weight), P(bias), P(self.scores), n_img, R, self.D, self.C + 1, k,
                                      P(self.score_ws), self.score_ws.numel(), stream), "cim_score_heads")
-                if pcl_early:
-                    # PCL_loss (model_builder.py:203) needs predict_cls and the cluster matrix only: 8 CTAs of pure
-                    # latency; its gradient is added to head 0's after the loss block
-                    ck(L.cim_pcl_loss(P(self.scores), P(mat), P(self.pcl_loss), P(self.pcl_grad), n_img, R,
-                                      self.C + 1, PCL_MAX_ID, 1.0 / n_img, 0, stream), "cim_pcl_loss")
+            if with_pcl and pcl_early:
+                pcl(stream)
 
         def overlap(stream):
             with _nvtx("cim/mask_overlap"):
@@ -201,6 +208,7 @@ class CIMHeadStep:
                                                 P(self.roi_ws), self.roi_ws.numel(), st), "cim_roi_align_fwd")
 
         def mine():
+            self.ev_premine.record(cur)        # from here on the GPU is mostly idle until the hop is over
             with _nvtx("cim/mine"):
                 ck(L.cim_mine(C.byref(p), self.cls_ptrs, self.det_ptrs, P(labels), P(self.iou), P(self.asy),
                               P(self.gt_count), P(self.gt_rows), P(self.gt_class), P(self.gt_weight),
@@ -218,13 +226,18 @@ class CIMHeadStep:
                                            self.sr, self.aligned, P(self.roi_ws), self.roi_ws.numel(), st),
                    "cim_roi_align_prepare")
             roi_fwd()
-            score_fwd(st)
+            score_fwd(st, False)
+            if pcl_early:
+                # PCL on its own stream, next to the (equally latency-bound) mining kernels; joined before the losses
+                self.ev_score.record(cur)
+                self.side2.wait_event(self.ev_score)
+                pcl(C.c_void_p(self.side2.cuda_stream))
             cur.wait_stream(self.side)
             mine()
         else:
             # the scoring GEMM (independent of the maps) runs on a side stream next to the overlap stage, whose small
             # serial helpers leave most of the GPU idle; RoI descriptors once per step, also off the critical path
-            score_fwd(side_st)
+            score_fwd(side_st, True)
             ck(L.cim_roi_align_prepare(P(rois), n_img, self.Cf, self.H, self.W, n_img * R, 7, 7, self.scale, self.sr,
                                        self.aligned, P(self.roi_ws), self.roi_ws.numel(), side_st),
                "cim_roi_align_prepare")
@@ -269,6 +282,8 @@ class CIMHeadStep:
                                          P(self.grad_scores), n_img, R, self.C, k, k, 3.0, 1.0, 3.0, 1.0 / n_img, st),
                        "cim_head_losses")
                     if pcl_early:                                    # + PCL_loss on predict_cls
+                        if order == "graph":
+                            cur.wait_stream(self.side2)
                         self.grad_scores[0].add_(self.pcl_grad)
                 grad_scores = self.grad_scores
             with _nvtx("cim/score_heads_bwd"):
@@ -347,11 +362,22 @@ class CIMHeadStep:
         self._slot = 0
         self._staged = False
         self.res_ev = torch.cuda.Event()
+        self.h2d_ev = torch.cuda.Event()
+        self._h2d_pending = False
         self._pending = False
         self.results_host = None
 
+    def wait_inputs_consumed(self):
+        """Block until the last stage_host_inputs() has finished READING the pinned input buffers (hi_rois, hi_labels,
+        hi_masks / hi_crop_*).  The copies are asynchronous: refill those buffers for the following step only after
+        this returns (set_host_crops() calls it itself)."""
+        if getattr(self, "_h2d_pending", False):
+            self.h2d_ev.synchronize()
+            self._h2d_pending = False
+
     def set_host_crops(self, crops):
         """Copy a MaskCrops (CPU) of the n_img * R proposal masks into the pinned input buffers."""
+        self.wait_inputs_consumed()
         n = crops.words.numel()
         if n > self.crop_cap:
             raise ValueError(f"{n} crop words exceed the capacity {self.crop_cap}")
@@ -361,11 +387,44 @@ class CIMHeadStep:
         self.n_crop_words = n
         self.mask_hw = (crops.height, crops.width)
 
-    def stage_host_inputs(self):
+    def stage_host_inputs(self, defer_kernels=False):
         """Enqueue the host->device copy of the CURRENT contents of hi_rois / hi_labels / hi_masks
         into the idle device buffer, on the copy stream.  Call it for step i+1 before (or while)
-        step i computes; run_host() consumes the staged buffer."""
+        step i computes; run_host() consumes the staged buffer.
+        defer_kernels: only the copies (copy engine) are enqueued now; the returned callable enqueues the kernels that
+        turn them into the step's input (crop unpack + mask metadata) -- run_host() calls it from inside the step,
+        behind `ev_premine`, so that they run next to the mining kernels and the sampling hop, which leave most SMs idle,
+        instead of competing with the RoIAlign kernels (0.31 ms -> measured in tools/e2e_diag.py)."""
         buf = self.di[self._slot ^ 1] if self._staged else self.di[self._slot]
+
+        def kernels(after=None):
+            with torch.cuda.stream(self.copy_stream):
+                if after is not None:
+                    self.copy_stream.wait_event(after)
+                if self.crop_cap:
+                    fused = bool(self.kb_per_row) and self.use_meta and \
+                        self.words * 32 == self.mask_hw[0] * self.mask_hw[1]
+                    if fused:
+                        # crops -> tiled bit masks + their metadata in one pass (every packed word written once)
+                        rc = self.L.cim_mask_unpack_crops_tiled_meta(
+                            _lib.ptr(buf["crop_words"]), _lib.ptr(buf["crop_meta"]), _lib.ptr(buf["crop_off"]),
+                            _lib.ptr(buf["masks"]), _lib.ptr(buf["meta"]), buf["meta"].numel(), self.n_img, self.R,
+                            self.mask_hw[0], self.mask_hw[1], self.words, C.c_void_p(self.copy_stream.cuda_stream))
+                        _lib.check(rc, "cim_mask_unpack_crops_tiled_meta")
+                        buf["meta_done"] = True
+                    else:
+                        unpack = self.L.cim_mask_unpack_crops_tiled if self.kb_per_row else self.L.cim_mask_unpack_crops
+                        rc = unpack(_lib.ptr(buf["crop_words"]), _lib.ptr(buf["crop_meta"]), _lib.ptr(buf["crop_off"]),
+                                    _lib.ptr(buf["masks"]), self.n_img * self.R, self.mask_hw[0], self.mask_hw[1],
+                                    self.words, C.c_void_p(self.copy_stream.cuda_stream))
+                        _lib.check(rc, "cim_mask_unpack_crops")
+                        buf["meta_done"] = False
+                if self.use_meta and not buf["meta_done"]:
+                    _lib.check(self.L.cim_mask_meta(_lib.ptr(buf["masks"]), self.n_img, self.R, self.words,
+                                                    self.kb_per_row, _lib.ptr(buf["meta"]), buf["meta"].numel(),
+                                                    C.c_void_p(self.copy_stream.cuda_stream)), "cim_mask_meta")
+                buf["ready"].record(self.copy_stream)
+
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(buf["free"])          # its previous consumer has finished
             buf["rois"].copy_(self.hi_rois, non_blocking=True)
@@ -375,31 +434,15 @@ class CIMHeadStep:
                 buf["crop_words"][:n].copy_(self.hi_crop_words[:n], non_blocking=True)
                 buf["crop_meta"].copy_(self.hi_crop_meta, non_blocking=True)
                 buf["crop_off"].copy_(self.hi_crop_off, non_blocking=True)
-                fused = bool(self.kb_per_row) and self.use_meta and self.words * 32 == self.mask_hw[0] * self.mask_hw[1]
-                if fused:
-                    # crops -> tiled bit masks + their metadata in one pass (every packed word written once)
-                    rc = self.L.cim_mask_unpack_crops_tiled_meta(
-                        _lib.ptr(buf["crop_words"]), _lib.ptr(buf["crop_meta"]), _lib.ptr(buf["crop_off"]),
-                        _lib.ptr(buf["masks"]), _lib.ptr(buf["meta"]), buf["meta"].numel(), self.n_img, self.R,
-                        self.mask_hw[0], self.mask_hw[1], self.words, C.c_void_p(self.copy_stream.cuda_stream))
-                    _lib.check(rc, "cim_mask_unpack_crops_tiled_meta")
-                    buf["meta_done"] = True
-                else:
-                    unpack = self.L.cim_mask_unpack_crops_tiled if self.kb_per_row else self.L.cim_mask_unpack_crops
-                    rc = unpack(_lib.ptr(buf["crop_words"]), _lib.ptr(buf["crop_meta"]), _lib.ptr(buf["crop_off"]),
-                                _lib.ptr(buf["masks"]), self.n_img * self.R, self.mask_hw[0], self.mask_hw[1],
-                                self.words, C.c_void_p(self.copy_stream.cuda_stream))
-                    _lib.check(rc, "cim_mask_unpack_crops")
-                    buf["meta_done"] = False
                 self.last_mask_h2d_bytes = n * 4 + self.hi_crop_meta.numel() * 4 + self.hi_crop_off.numel() * 8
             else:
                 buf["masks"].copy_(self.hi_masks, non_blocking=True)
                 buf["meta_done"] = False
-            if self.use_meta and not buf["meta_done"]:
-                _lib.check(self.L.cim_mask_meta(_lib.ptr(buf["masks"]), self.n_img, self.R, self.words, self.kb_per_row,
-                                                _lib.ptr(buf["meta"]), buf["meta"].numel(),
-                                                C.c_void_p(self.copy_stream.cuda_stream)), "cim_mask_meta")
-            buf["ready"].record(self.copy_stream)
+            self.h2d_ev.record(self.copy_stream)               # the pinned input buffers have been read
+            self._h2d_pending = True
+        if defer_kernels:
+            return kernels
+        kernels()
         return self
 
     def _collect_results(self):
@@ -431,12 +474,14 @@ class CIMHeadStep:
             self.stage_host_inputs()
             self._staged = True
         buf = self.di[self._slot]
+        finish_stage = None
         if prefetch_next:
-            self.stage_host_inputs()                           # goes to the other buffer
+            finish_stage = self.stage_host_inputs(defer_kernels=True)      # copies now, the other buffer
         cur_stream.wait_event(buf["ready"])
         self.run(feat, buf["rois"], grad_out, buf["masks"], seg_x, weight, bias, buf["labels"],
                  None, grad_scores=grad_scores, mat=mat, mask_meta=buf.get("meta"),
-                 mid_hook=self._collect_results if lag_results else None)
+                 mid_hook=lambda: ((finish_stage(self.ev_premine) if finish_stage else None),
+                                   (self._collect_results() if lag_results else None)))
         buf["free"].record(cur_stream)
         self.d_checksum[0] = self.roi_out.view(-1)[::4099].sum()
         self.d_checksum[1] = self.grad_feat.view(-1)[::127].sum()

@@ -51,3 +51,50 @@ with torch.cuda.stream(hp):
     step2.hi_rois.copy_(inp["rois"]); step2.hi_labels.copy_(inp["labels"]); step2.hi_masks.copy_(inp["packed"].cpu())
     host2 = lambda: step2.run_host(inp["feat"], inp["grad_out"], inp["seg_x"], inp["weight"], inp["bias"], mat=mat, lag_results=True)
     print(f"run_host lag, full masks H2D  {timed(host2, flush=step2.flush_results):.3f} ms  ({step2.h2d_bytes / 1e6:.0f} MB / step)")
+    # ---- pieces of the host path switched off one at a time
+    real_stage = step.stage_host_inputs
+    step.stage_host_inputs = lambda defer_kernels=False: ((lambda after=None: None) if defer_kernels else step)   # no H2D, no unpack
+    print(f"run_host lag, NO staging      {timed(lambda: host(lag_results=True), flush=step.flush_results):.3f} ms   (host loop + result read-back only)")
+    step.stage_host_inputs = real_stage
+
+    def stage_only():
+        real_stage()
+        step._slot ^= 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(step.copy_stream)
+    for _ in range(5):
+        real_stage()
+    e1.record(step.copy_stream)
+    torch.cuda.synchronize()
+    print(f"staging alone (copy stream)   {e0.elapsed_time(e1) / 5:.3f} ms   (H2D of the crops + unpack/meta kernel, nothing else running)")
+    # ---- which half of the staging costs the 0.3 ms: the H2D copies or the unpack / metadata kernel?
+    def stage_copies_only(defer_kernels=False):
+        k = real_stage(defer_kernels=True)
+        buf = step.di[step._slot ^ 1] if step._staged else step.di[step._slot]
+        with torch.cuda.stream(step.copy_stream):
+            buf["ready"].record(step.copy_stream)
+        return (lambda after=None: None) if defer_kernels else step
+    step.stage_host_inputs = stage_copies_only
+    print(f"run_host lag, H2D copies only {timed(lambda: host(lag_results=True), flush=step.flush_results):.3f} ms")
+
+    def stage_kernels_only(defer_kernels=False):
+        buf = step.di[step._slot ^ 1] if step._staged else step.di[step._slot]
+        def kernels(after=None):
+            with torch.cuda.stream(step.copy_stream):
+                if after is not None:
+                    step.copy_stream.wait_event(after)
+                step.copy_stream.wait_event(buf["free"])
+                rc = step.L.cim_mask_unpack_crops_tiled_meta(
+                    step.di[0]["crop_words"].data_ptr(), step.di[0]["crop_meta"].data_ptr(), step.di[0]["crop_off"].data_ptr(),
+                    buf["masks"].data_ptr(), buf["meta"].data_ptr(), buf["meta"].numel(), step.n_img, step.R,
+                    step.mask_hw[0], step.mask_hw[1], step.words, step.copy_stream.cuda_stream)
+                assert rc == 0
+                buf["ready"].record(step.copy_stream)
+        if defer_kernels:
+            return kernels
+        kernels()
+        return step
+    step.stage_host_inputs = stage_kernels_only
+    print(f"run_host lag, kernels only    {timed(lambda: host(lag_results=True), flush=step.flush_results):.3f} ms")
+    step.stage_host_inputs = real_stage
