@@ -46,7 +46,7 @@ const char *cim_error_string(int code);
  * takes its production kernel), and a launch samples them once on entry.  Not meant for production code. */
 enum {
     CIM_DBG_ROI_BWD_SMEM_TILE = 1u,   /* RoIAlign backward: gradient tile in shared memory, not tensor memory       */
-    CIM_DBG_OVERLAP_LOADER_WARP = 2u, /* mask overlap: loader-warp kernel (what masks above 512 Kpixel take anyway) */
+    CIM_DBG_OVERLAP_LOADER_WARP = 2u, /* no effect any more (it selected the loader-warp pipeline of the int8 overlap kernel); kept so that callers still build */
     CIM_DBG_SCORE_FFMA = 4u,          /* scoring GEMMs fwd / bwd: plain fp32 FFMA kernels, not 3xTF32 tcgen05       */
     CIM_DBG_ROI_NO_WINDOWS = 8u       /* RoIAlign on maps larger than the smem tile: global-pairs kernels           */
 };

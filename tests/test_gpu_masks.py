@@ -163,10 +163,10 @@ def test_tensor_core_path_equals_popc_and_oracle(n, side, n_img):
 
 
 @pytest.mark.parametrize("variant", [_lib.DBG_OVERLAP_LOADER_WARP, 0])
-def test_tensor_core_pipeline_variants_agree(variant):
-    """CIM_DBG_OVERLAP_LOADER_WARP: the loader-warp kernel (cp.async staging ring; what masks above 512 Kpixel take);
-    default: every expander thread prefetches its own rows (cp.async into thread-private slots, K-block list in
-    smem).  Both bit-identical to the popcount kernel, also over repeated launches."""
+def test_tensor_core_kernel_repeated_launches(variant):
+    """The tensor-core kernel (tcgen05.mma.kind::mxf4, every expander thread prefetching its own row) is bit-identical
+    to the popcount kernel, also over repeated launches.  CIM_DBG_OVERLAP_LOADER_WARP selected the loader-warp
+    pipeline of the int8 kernel; that variant is gone (the K-block list now holds masks up to 2 Mpixel) and the flag must be harmless."""
     n, side = 600, 128
     m = synth.rasterize(synth.proposal_params(n, side, 4242))
     m[5] = 0
@@ -174,7 +174,7 @@ def test_tensor_core_pipeline_variants_agree(variant):
     packed = mask_ops.mask_pack(m[None].to(DEV))
     want = mask_ops.mask_overlap(packed, return_counts=True, algo="popc")
     with _lib.debug_flags(variant):
-        for _ in range(3):                   # repeated launches: barrier phases, TMEM alloc / dealloc
+        for _ in range(3):                   # repeated launches: barrier phases, TMEM alloc / dealloc, scale columns
             got = mask_ops.mask_overlap(packed, return_counts=True, algo="tensor")
     assert torch.equal(got[2], want[2]) and torch.equal(got[3], want[3])
     assert_f16_bits_equal(u16(got[0]), u16(want[0]))
