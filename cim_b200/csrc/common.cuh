@@ -41,15 +41,18 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
                  "r"(bytes)
                  : "memory");
 }
+// try_wait suspends the thread in hardware until the phase completes or a time limit passes; the default limit is
+// short (a warp waiting for a ring slot of the RoIAlign backward polled ~9 times per visit, and the try_wait / branch /
+// yield triples were a quarter of all issued instructions of an issue-bound kernel), so a generous hint (ns) is given.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(100000u)
         : "memory");
 }
 // elect.sync over the full (converged) warp: true in exactly one lane.  Branching on THIS predicate (instead of

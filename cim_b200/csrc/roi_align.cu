@@ -223,7 +223,16 @@ __global__ void roi_prep_kernel(const float *__restrict__ rois, int K, int B, in
             if (lo2 <= prev) inc = 0;
             prev = lo2;
         }
-        d[D_XINC] = inc;      // 1: window starts strictly increase -> taps of one l never alias
+        // 1: window starts strictly increase -> taps of one l never alias.  3: in addition the T-wide windows of bins
+        // p and p + 3 never overlap, so the bins can be updated in the three groups {0,3,6}, {1,4}, {2,5} with
+        // whole-window accesses (tensor-memory backward)
+        if (inc && !flag) {
+            int g3 = 1;
+            for (int p = 0; p + 3 < 7; ++p)
+                if (d[D_XLO + p + 3] - d[D_XLO + p] < T) g3 = 0;
+            if (g3) inc = 3;
+        }
+        d[D_XINC] = inc;
         d[D_XLO + 7] = 0;
     }
 }
@@ -708,6 +717,55 @@ __device__ __forceinline__ void tm_st2(uint32_t taddr, float2 v) {
                  "r"(__float_as_uint(v.y))
                  : "memory");
 }
+// N column pairs (row 2p, row 2p + 1) starting at taddr
+template <int N>
+__device__ __forceinline__ void tm_ld_n(uint32_t taddr, float2 *v) {
+    static_assert(N == 1 || N == 2 || N == 4 || N == 8, "tcgen05.ld.32x32b shapes");
+    uint32_t *u = reinterpret_cast<uint32_t *>(v);
+    if constexpr (N == 1)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(u[0]), "=r"(u[1]) : "r"(taddr) : "memory");
+    else if constexpr (N == 2)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]) : "r"(taddr) : "memory");
+    else if constexpr (N == 4)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+                     : "r"(taddr) : "memory");
+    else
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                     : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+                       "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+                     : "r"(taddr) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tm_st_n(uint32_t taddr, const float2 *v) {
+    const uint32_t *u = reinterpret_cast<const uint32_t *>(v);
+    if constexpr (N == 1)
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(u[0]), "r"(u[1]) : "memory");
+    else if constexpr (N == 2)
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(u[0]), "r"(u[1]),
+                     "r"(u[2]), "r"(u[3]) : "memory");
+    else if constexpr (N == 4)
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(u[0]),
+                     "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]) : "memory");
+    else
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                     ::"r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]), "r"(u[8]),
+                     "r"(u[9]), "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15]) : "memory");
+}
+// the T-wide column window of a bin: T = 2, 4, 8 one access, T = 3 and 6 two (a power of two and its half)
+template <int T>
+__device__ __forceinline__ void tm_ld_win(uint32_t taddr, float2 *v) {
+    if constexpr (T == 3) { tm_ld_n<2>(taddr, v); tm_ld_n<1>(taddr + 4u, v + 2); }
+    else if constexpr (T == 6) { tm_ld_n<4>(taddr, v); tm_ld_n<2>(taddr + 8u, v + 4); }
+    else tm_ld_n<T>(taddr, v);
+}
+template <int T>
+__device__ __forceinline__ void tm_st_win(uint32_t taddr, const float2 *v) {
+    if constexpr (T == 3) { tm_st_n<2>(taddr, v); tm_st_n<1>(taddr + 4u, v + 2); }
+    else if constexpr (T == 6) { tm_st_n<4>(taddr, v); tm_st_n<2>(taddr + 8u, v + 4); }
+    else tm_st_n<T>(taddr, v);
+}
 __device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -719,7 +777,10 @@ template <int T, bool XINC, bool FUSED, int NW, bool TM = false>
 __device__ __forceinline__ void bwd_pairs(float *__restrict__ tile_c, int W, const int *d,
                                           const float *__restrict__ g, const float *__restrict__ m, int warp, int y0,
                                           int y1, uint32_t tmem_w = 0) {
-    float wx[PW][T];
+    // column weights in registers -- except for the wide tap classes of the tensor-memory variant, whose 16-register
+    // accesses leave no room for 56 weights: those read a bin's weights (two LDS.128, broadcast) when they need them
+    constexpr bool WREG = !(TM && T > 4);
+    float wx[PW][WREG ? T : 1];
     int xo[PW];
     const float *dwx = reinterpret_cast<const float *>(d + D_WX);
     const float *dwy = reinterpret_cast<const float *>(d + D_WY);
@@ -728,14 +789,16 @@ __device__ __forceinline__ void bwd_pairs(float *__restrict__ tile_c, int W, con
         int4 a = *reinterpret_cast<const int4 *>(d + D_XLO), b = *reinterpret_cast<const int4 *>(d + D_XLO + 4);
         xo[0] = a.x; xo[1] = a.y; xo[2] = a.z; xo[3] = a.w; xo[4] = b.x; xo[5] = b.y; xo[6] = b.z;
     }
+    if constexpr (WREG) {
 #pragma unroll
-    for (int pw = 0; pw < PW; ++pw) {
-        float4 a = *reinterpret_cast<const float4 *>(dwx + pw * MAXT);
-        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (T > 4) b = *reinterpret_cast<const float4 *>(dwx + pw * MAXT + 4);
-        float t8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        for (int pw = 0; pw < PW; ++pw) {
+            float4 a = *reinterpret_cast<const float4 *>(dwx + pw * MAXT);
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (T > 4) b = *reinterpret_cast<const float4 *>(dwx + pw * MAXT + 4);
+            float t8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-        for (int l = 0; l < T; ++l) wx[pw][l] = t8[l];
+            for (int l = 0; l < T; ++l) wx[pw][l] = t8[l];
+        }
     }
     float2 *tile2 = reinterpret_cast<float2 *>(tile_c);
     const int pb = y0 >> 1, p1 = (y1 + 1) >> 1;
@@ -761,29 +824,68 @@ __device__ __forceinline__ void bwd_pairs(float *__restrict__ tile_c, int W, con
             }
         }
         if (TM) {
+            // whole-window accesses: the T columns x 2 rows of a bin are ONE (T = 3, 6: two) tensor-memory load and
+            // store, addressed off one base per bin.  (Per-tap .x2 accesses cost an R2UR per access on top of the
+            // LDTM / STTM: the address has to sit in a uniform register, and ptxas re-materialises it at every use --
+            // R2UR was 12 % of the issued instructions of this issue-bound kernel.)
             const uint32_t trow = tmem_w + (uint32_t)((p / NW) * W) * 2u;
             if (XINC) {
+                // descriptor flag 3: bins p and p + 3 never share a column -> three groups, each loaded, updated and
+                // stored as a whole (T <= 4), 6 waits per row pair
 #pragma unroll
-                for (int l = 0; l < T; ++l) {
-                    float2 v[PW];
+                for (int g0 = 0; g0 < 3; ++g0) {
+                    if (T <= 4) {
+                        float2 v[3][T];
 #pragma unroll
-                    for (int pw = 0; pw < PW; ++pw) v[pw] = tm_ld2(trow + 2u * (uint32_t)(xo[pw] + l));
-                    tm_wait_ld();
+                        for (int i = 0; i < 3; ++i)
+                            if (g0 + 3 * i < PW) tm_ld_win<T>(trow + 2u * (uint32_t)xo[g0 + 3 * i], v[i]);
+                        tm_wait_ld();
 #pragma unroll
-                    for (int pw = 0; pw < PW; ++pw)
-                        tm_st2(trow + 2u * (uint32_t)(xo[pw] + l), __ffma2_rn(bcast2(wx[pw][l]), r[pw], v[pw]));
-                    tm_wait_st();                       // the next l (and the next ROI) may read these columns
+                        for (int i = 0; i < 3; ++i) {
+                            const int pw = g0 + 3 * i;
+                            if (pw < PW) {
+#pragma unroll
+                                for (int l = 0; l < T; ++l) v[i][l] = __ffma2_rn(bcast2(wx[pw][l]), r[pw], v[i][l]);
+                                tm_st_win<T>(trow + 2u * (uint32_t)xo[pw], v[i]);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            const int pw = g0 + 3 * i;
+                            if (pw < PW) {
+                                float2 v[T];
+                                tm_ld_win<T>(trow + 2u * (uint32_t)xo[pw], v);
+                                const float4 a = *reinterpret_cast<const float4 *>(dwx + pw * MAXT);
+                                const float4 b = *reinterpret_cast<const float4 *>(dwx + pw * MAXT + 4);
+                                const float w8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                                tm_wait_ld();
+#pragma unroll
+                                for (int l = 0; l < T; ++l) v[l] = __ffma2_rn(bcast2(w8[l]), r[pw], v[l]);
+                                tm_st_win<T>(trow + 2u * (uint32_t)xo[pw], v);
+                            }
+                        }
+                    }
+                    tm_wait_st();                       // the next group (and the next ROI) may read these columns
                 }
             } else {
 #pragma unroll
                 for (int pw = 0; pw < PW; ++pw) {
                     float2 v[T];
+                    tm_ld_win<T>(trow + 2u * (uint32_t)xo[pw], v);
+                    float w8[8];
+                    if constexpr (WREG) {
 #pragma unroll
-                    for (int l = 0; l < T; ++l) v[l] = tm_ld2(trow + 2u * (uint32_t)(xo[pw] + l));
+                        for (int l = 0; l < T; ++l) w8[l] = wx[pw][l];
+                    } else {
+                        const float4 a = *reinterpret_cast<const float4 *>(dwx + pw * MAXT);
+                        const float4 b = *reinterpret_cast<const float4 *>(dwx + pw * MAXT + 4);
+                        w8[0] = a.x; w8[1] = a.y; w8[2] = a.z; w8[3] = a.w; w8[4] = b.x; w8[5] = b.y; w8[6] = b.z; w8[7] = b.w;
+                    }
                     tm_wait_ld();
 #pragma unroll
-                    for (int l = 0; l < T; ++l)
-                        tm_st2(trow + 2u * (uint32_t)(xo[pw] + l), __ffma2_rn(bcast2(wx[pw][l]), r[pw], v[l]));
+                    for (int l = 0; l < T; ++l) v[l] = __ffma2_rn(bcast2(w8[l]), r[pw], v[l]);
+                    tm_st_win<T>(trow + 2u * (uint32_t)xo[pw], v);
                     tm_wait_st();                       // the next bin may alias these columns
                 }
             }
@@ -791,15 +893,27 @@ __device__ __forceinline__ void bwd_pairs(float *__restrict__ tile_c, int W, con
         }
         float2 *row = tile2 + p * W;
         if (XINC) {
-            // window starts strictly increase: the 7 taps of one l hit 7 distinct columns,
-            // so they can be loaded, updated and stored as a group
+            // descriptor flag 3: the windows of bins p and p + 3 are disjoint, so the bins of a group {0,3,6}, {1,4},
+            // {2,5} can be loaded, updated and stored together; groups in this order = the order of the additions into
+            // an element, the same as in the tensor-memory variant (the two are bit-identical)
 #pragma unroll
-            for (int l = 0; l < T; ++l) {
-                float2 v[PW];
+            for (int g0 = 0; g0 < 3; ++g0) {
+                float2 v[3][T];
 #pragma unroll
-                for (int pw = 0; pw < PW; ++pw) v[pw] = row[xo[pw] + l];
+                for (int i = 0; i < 3; ++i)
+                    if (g0 + 3 * i < PW) {
 #pragma unroll
-                for (int pw = 0; pw < PW; ++pw) row[xo[pw] + l] = __ffma2_rn(bcast2(wx[pw][l]), r[pw], v[pw]);
+                        for (int l = 0; l < T; ++l) v[i][l] = row[xo[g0 + 3 * i] + l];
+                    }
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const int pw = g0 + 3 * i;
+                    if (pw < PW) {
+#pragma unroll
+                        for (int l = 0; l < T; ++l) row[xo[pw] + l] = __ffma2_rn(bcast2(wx[pw][l]), r[pw], v[i][l]);
+                    }
+                }
+                asm volatile("" ::: "memory");          // the next group may alias these columns
             }
         } else {
             // windows may coincide (tiny ROIs): bins strictly in program order; the T taps of one bin
@@ -1152,7 +1266,7 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
                     continue;
                 }
                 const int T = d[D_TX];
-                if (d[D_XINC]) {
+                if (d[D_XINC] == 3) {      // groups of bins with disjoint windows; otherwise bin by bin
                     switch (T) {
                         case 2: bwd_pairs<2, true, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
                         case 3: bwd_pairs<3, true, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
