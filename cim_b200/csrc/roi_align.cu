@@ -1073,16 +1073,21 @@ __device__ __forceinline__ void red_add4(float *gptr, float a, float b, float c,
 // [B * NW + 1] of the sorted sub-ROI descriptors `descs`, the segments are (image, chunk, window, sub-ROI range), a
 // sub-ROI's gradient block is its ROI's (descriptor word DW_ROI), and the tile is added to its window of grad_feat
 // (windows overlap, so on this path the order of the global additions is not fixed).
-template <bool FUSED, int NWB, bool TM, bool WIN = false>
+// NCH = 2 (tensor-memory variant, whole map, C % 64 == 0): a CTA carries TWO 32-channel chunks at once.  Warp w owns
+// row pair w of chunk 0 and row pair (w + 8) % 16 of chunk 1, so maps of 8 row pairs (HRNet, 16 x 16) keep all 16
+// warps busy instead of 8 (the host selects it for those).  Both chunks of a ROI's gradient are contiguous in
+// grad_out and travel with one bulk copy; a slot holds half as many ROIs.
+template <bool FUSED, int NWB, bool TM, bool WIN = false, int NCH = 1>
 __global__ void __launch_bounds__(NWB * 32, 1)
 roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restrict__ hdr,
                           const int *__restrict__ img_start, const int *__restrict__ descs,
                           const float *__restrict__ mask7, float *__restrict__ grad_feat, int B, int C, int Hmap, int Wmap,
                           int pitch, WinGeom wg = WinGeom()) {
     const int H = WIN ? wg.wh : Hmap, W = WIN ? wg.ww : Wmap;          // tile rows / columns
-    constexpr int NBR = (FUSED ? NBR_F : ::NBR) * (TM ? NBR_TM_MUL : 1);   // ROIs per slot
+    static_assert(NCH == 1 || (NCH == 2 && TM && !FUSED && !WIN && NWB == 16), "two chunks: whole-map tensor-memory variant");
+    constexpr int NBR = (FUSED ? NBR_F : ::NBR) * (TM ? NBR_TM_MUL : 1) / NCH;   // ROIs per slot
     constexpr int NS = (FUSED ? NS_F : ::NS) + (TM ? NS_TM_EXTRA : 0);   // ring slots (TM: the tile's smem is free)
-    constexpr int GSTRIDE = FUSED ? 2 * STAGE_FLOATS : STAGE_FLOATS;      // gradient floats per ROI in a slot
+    constexpr int GSTRIDE = (FUSED ? 2 : NCH) * STAGE_FLOATS;             // gradient floats per ROI in a slot
     constexpr int SLOT_FLOATS = NBR * (GSTRIDE + DESC_WORDS + (FUSED ? MASK_PAD : 0));
     const int Cg = FUSED ? 2 * C : C;                         // channels of grad_out
     extern __shared__ __align__(128) float smem[];
@@ -1090,13 +1095,13 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
     float *ring = smem + (TM ? 0 : (size_t)CH * pitch);      // [NS][NBR x grads | NBR x DESC_WORDS]
     __shared__ uint32_t tmem_slot;
     __shared__ int done_cnt[4];                                // LASTP: warps that have finished the batch in each slot
-    constexpr bool LASTP = WIN;
+    constexpr bool LASTP = WIN;     // (measured on the whole-map path too: 1.18 -> 1.38 ms, the fast warps no longer run ahead)
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)NS * SLOT_FLOATS);
     uint64_t *empty = full + NS;
     if (!WIN && __ldg(hdr) != 0) return;      // rois not grouped by image: the generic kernel does it all
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int HW = Hmap * Wmap, nchunks = C / CH;
+    const int HW = Hmap * Wmap, nchunks = C / (CH * NCH);
     const int NWIN = WIN ? wg.nwy * wg.nwx : 1;
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWB); done_cnt[s] = 0; }
@@ -1116,7 +1121,7 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
     const int npw = (((H + 1) >> 1) + NWB - 1) / NWB;        // row pairs per warp
     const int TW = WIN ? W + WIN_TM_PAD : W;                 // columns of a tile row in tensor memory (bwd_pairs_win)
     const uint32_t tmem_cols_w = (uint32_t)(npw * TW * 2);
-    const uint32_t tmem_w = TM ? tmem_slot + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(warp >> 2) * tmem_cols_w : 0u;
+    const uint32_t tmem_w = TM ? tmem_slot + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(warp >> 2) * tmem_cols_w * NCH : 0u;
 
     const int s0 = __ldg(img_start), sB = __ldg(img_start + B * NWIN);
     const long long U = (long long)nchunks * (sB - s0);
@@ -1171,12 +1176,12 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
             r1 = nroi;
             if (nroi == 0) continue;          // its slab stays zero
         }
-        const int c0 = ch * CH;
+        const int c0 = ch * CH * NCH;
         const int first_roi = is + r0, n = r1 - r0;
         const int nbatch = (n + NBR - 1) / NBR, gb0 = gb;
 
         if (TM) {
-            for (uint32_t cc = 0; cc < tmem_cols_w; cc += 2) tm_st2(tmem_w + cc, make_float2(0.f, 0.f));
+            for (uint32_t cc = 0; cc < tmem_cols_w * NCH; cc += 2) tm_st2(tmem_w + cc, make_float2(0.f, 0.f));
             tm_wait_st();
         } else {
             for (int e = tid; e < CH * pitch; e += NWB * 32) tile[e] = 0.f;
@@ -1203,7 +1208,7 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
                     if (j < cnt) {
                         const int roi = WIN ? rois_j[j] : first_roi + first + j;
                         const float *src = grad_out + ((size_t)roi * Cg + c0) * NBIN;
-                        bulk_g2s(slot + j * GSTRIDE, src, STAGE_FLOATS * 4, &full[s]);
+                        bulk_g2s(slot + j * GSTRIDE, src, NCH * STAGE_FLOATS * 4, &full[s]);   // NCH = 2: both chunks
                         if (FUSED)
                             bulk_g2s(slot + j * GSTRIDE + STAGE_FLOATS, src + (size_t)C * NBIN, STAGE_FLOATS * 4, &full[s]);
                         if (FUSED && WIN)
@@ -1250,7 +1255,8 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
             if (lane < cnt) {
                 const int2 ff = *reinterpret_cast<const int2 *>(dbase + lane * DESC_WORDS + D_XINC);   // (xinc, own)
                 const int own = NWB == 16 ? ff.y : (ff.y | (ff.y >> 8));       // D_OWN: bit (pair & 15)
-                mine = ((own >> warp) & 1) != 0 && dbase[lane * DESC_WORDS + D_FLAGX] == 0;   // (WIN: always 0)
+                const int mybits = NCH == 2 ? (1 << warp) | (1 << ((warp + 8) & 15)) : 1 << warp;
+                mine = (own & mybits) != 0 && dbase[lane * DESC_WORDS + D_FLAGX] == 0;   // (WIN: always 0)
             }
             unsigned todo = __ballot_sync(0xffffffffu, mine);
             while (todo) {
@@ -1265,22 +1271,31 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
                     bwd_pairs_win<FUSED, NWB>(TW, d, g, m, warp, y0, y1, tmem_w);
                     continue;
                 }
-                const int T = d[D_TX];
-                if (d[D_XINC] == 3) {      // groups of bins with disjoint windows; otherwise bin by bin
-                    switch (T) {
-                        case 2: bwd_pairs<2, true, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
-                        case 3: bwd_pairs<3, true, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
-                        case 4: bwd_pairs<4, true, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
-                        case 6: bwd_pairs<6, true, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
-                        default: bwd_pairs<8, true, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
-                    }
-                } else {
-                    switch (T) {
-                        case 2: bwd_pairs<2, false, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
-                        case 3: bwd_pairs<3, false, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
-                        case 4: bwd_pairs<4, false, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
-                        case 6: bwd_pairs<6, false, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
-                        default: bwd_pairs<8, false, FUSED, NWB, TM>(tile_c, W, d, g, m, warp, y0, y1, tmem_w); break;
+                const int own_j = NCH == 2 ? d[D_OWN] : 0;
+#pragma unroll 1
+                for (int cch = 0; cch < NCH; ++cch) {
+                    // chunk 1 of the two-chunk variant: this warp stands in for warp (w + 8) % 16 of the one-chunk layout
+                    const int vw = cch ? (warp + 8) & 15 : warp;
+                    if (NCH == 2 && !((own_j >> vw) & 1)) continue;
+                    const float *gc = g + cch * STAGE_FLOATS;
+                    const uint32_t tmem_c = tmem_w + (uint32_t)cch * tmem_cols_w;
+                    const int T = d[D_TX];
+                    if (d[D_XINC] == 3) {      // groups of bins with disjoint windows; otherwise bin by bin
+                        switch (T) {
+                            case 2: bwd_pairs<2, true, FUSED, NWB, TM>(tile_c, W, d, gc, m, vw, y0, y1, tmem_c); break;
+                            case 3: bwd_pairs<3, true, FUSED, NWB, TM>(tile_c, W, d, gc, m, vw, y0, y1, tmem_c); break;
+                            case 4: bwd_pairs<4, true, FUSED, NWB, TM>(tile_c, W, d, gc, m, vw, y0, y1, tmem_c); break;
+                            case 6: bwd_pairs<6, true, FUSED, NWB, TM>(tile_c, W, d, gc, m, vw, y0, y1, tmem_c); break;
+                            default: bwd_pairs<8, true, FUSED, NWB, TM>(tile_c, W, d, gc, m, vw, y0, y1, tmem_c); break;
+                        }
+                    } else {
+                        switch (T) {
+                            case 2: bwd_pairs<2, false, FUSED, NWB, TM>(tile_c, W, d, gc, m, vw, y0, y1, tmem_c); break;
+                            case 3: bwd_pairs<3, false, FUSED, NWB, TM>(tile_c, W, d, gc, m, vw, y0, y1, tmem_c); break;
+                            case 4: bwd_pairs<4, false, FUSED, NWB, TM>(tile_c, W, d, gc, m, vw, y0, y1, tmem_c); break;
+                            case 6: bwd_pairs<6, false, FUSED, NWB, TM>(tile_c, W, d, gc, m, vw, y0, y1, tmem_c); break;
+                            default: bwd_pairs<8, false, FUSED, NWB, TM>(tile_c, W, d, gc, m, vw, y0, y1, tmem_c); break;
+                        }
                     }
                 }
             }
@@ -1346,11 +1361,13 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
             }
         } else if (TM) {
             // every warp drains its own row pairs: lane = channel, 8 columns = 4 x-positions x (row 2p, row 2p+1)
-            float *dl = dst + (size_t)lane * HW;
+            for (int cch = 0; cch < NCH; ++cch) {
+            float *dl = dst + ((size_t)cch * CH + lane) * HW;
+            const int vw = cch ? (warp + 8) & 15 : warp;
             for (int pl = 0; pl < npw; ++pl) {
-                const int pp = warp + NWB * pl, y = 2 * pp;
+                const int pp = vw + NWB * pl, y = 2 * pp;
                 if (y >= H) break;
-                const uint32_t trow = tmem_w + (uint32_t)(pl * W) * 2u;
+                const uint32_t trow = tmem_w + (uint32_t)cch * tmem_cols_w + (uint32_t)(pl * W) * 2u;
                 if ((W & 3) == 0) {
                     for (int x = 0; x < W; x += 4) {
                         uint32_t v[8];
@@ -1374,6 +1391,7 @@ roi_align_bwd_tile_kernel(const float *__restrict__ grad_out, const int *__restr
                         if (y + 1 < H) atomicAdd(dl + (size_t)(y + 1) * W + x, v.y);
                     }
                 }
+            }
             }
         } else if ((W & 3) == 0) {
             for (int e = tid * 4; e < CH * HW; e += NWB * 32 * 4) {
@@ -1971,7 +1989,14 @@ static int roi_bwd_impl(const float *grad_out, const float *rois, const float *m
         return cim_launch_status();
     }
     if (!prepared && (rc = run_prep(rois, B, H, W, K, oh, ow, scale, sr, aligned, w, glob, st))) return rc;
-    const long long units = (long long)(C / CH) * K;
+    // two chunks per CTA (see the kernel): tensor-memory variant, an even number of chunks, no fused mask, and maps of
+    // at most 8 row pairs, where it is what keeps all 16 warps busy (HRNet 16 x 16 x 2048: 2.36 -> 1.74 ms).  On 16
+    // row pairs it only rebalances the centre-heavy load and loses more to its smaller batches (8 ROIs per barrier
+    // round): 2.54 against 2.36 ms for 16 images x 2000 proposals at 32 x 32 x 1024.
+    const bool tm_on = p.bwd_tm && !(cim_get_debug_flags() & CIM_DBG_ROI_BWD_SMEM_TILE);
+    const bool two_chunks = tm_on && !glob && !mask7 && (C % (2 * CH)) == 0 && H <= 16 && 16 * W <= 512 &&
+                            !(cim_get_debug_flags() & CIM_DBG_ROI_BWD_ONE_CHUNK);
+    const long long units = (long long)(C / (two_chunks ? 2 * CH : CH)) * K;
     const int grid = (int)min((long long)cim_num_sms(), units);
     if (glob) {
         // gradients accumulate (red.global.add) in the channel-last pairs copy, which is then written out as NCHW
@@ -2013,7 +2038,8 @@ static int roi_bwd_impl(const float *grad_out, const float *rois, const float *m
         if (tm) go(roi_align_bwd_tile_kernel<true, NWB_DEFAULT, true>, NWB_DEFAULT, p.smem_bwd_fused_tm, w.maskpad);
         else go(roi_align_bwd_tile_kernel<true, NWB_DEFAULT, false>, NWB_DEFAULT, p.smem_bwd_fused, w.maskpad);
     } else {
-        if (tm) go(roi_align_bwd_tile_kernel<false, NWB_DEFAULT, true>, NWB_DEFAULT, p.smem_bwd_tm, nullptr);
+        if (two_chunks) go(roi_align_bwd_tile_kernel<false, NWB_DEFAULT, true, false, 2>, NWB_DEFAULT, p.smem_bwd_tm, nullptr);
+        else if (tm) go(roi_align_bwd_tile_kernel<false, NWB_DEFAULT, true>, NWB_DEFAULT, p.smem_bwd_tm, nullptr);
         else go(roi_align_bwd_tile_kernel<false, NWB_DEFAULT, false>, NWB_DEFAULT, p.smem_bwd, nullptr);
     }
     if ((rc = cim_launch_status())) return rc;

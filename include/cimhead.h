@@ -48,7 +48,8 @@ enum {
     CIM_DBG_ROI_BWD_SMEM_TILE = 1u,   /* RoIAlign backward: gradient tile in shared memory, not tensor memory       */
     CIM_DBG_OVERLAP_LOADER_WARP = 2u, /* no effect any more (it selected the loader-warp pipeline of the int8 overlap kernel); kept so that callers still build */
     CIM_DBG_SCORE_FFMA = 4u,          /* scoring GEMMs fwd / bwd: plain fp32 FFMA kernels, not 3xTF32 tcgen05       */
-    CIM_DBG_ROI_NO_WINDOWS = 8u       /* RoIAlign on maps larger than the smem tile: global-pairs kernels           */
+    CIM_DBG_ROI_NO_WINDOWS = 8u,      /* RoIAlign on maps larger than the smem tile: global-pairs kernels           */
+    CIM_DBG_ROI_BWD_ONE_CHUNK = 16u   /* RoIAlign backward: one 32-channel chunk per CTA instead of two             */
 };
 void cim_set_debug_flags(unsigned flags);
 unsigned cim_get_debug_flags(void);
