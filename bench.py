@@ -496,20 +496,22 @@ def measure_training(name, cfg, args, dev, rank, world, peaks, cdist, headline):
         visited, total = visited_kblocks(step, cfg)
         ov = {"executed_kblock_fraction": round(visited / max(total, 1), 4)}
         if visited:
-            # a dense R x HW x R contraction of 0/1 operands: tensor-pipe bound.  `executed` = the MMA
-            # flops actually issued (visited K-blocks x 2*128*256*128); the peak is the int8 rate measured on this
-            # chip by tools/micro/imma_peak.cu when its result is committed, else 2 x the measured bf16 burst
+            # a dense R x HW x R contraction of 0/1 operands.  `executed` = the MMA flops actually issued
+            # (visited K-blocks x 2*128*256*128); the kernel's instruction is tcgen05.mma.kind::mxf4 (E2M1 nibbles),
+            # whose dense rate on this chip tools/micro/mxf4_check.cu measured (profiles/mxf4_peak.json).  The kernel is
+            # NOT tensor-bound any more (operand loads, expansion and epilogue bound it), so this fraction
+            # is reported for the record, next to the int8 rate the previous kernel was measured against.
             secs = stage_ms["mask_overlap"] * 1e-3
             executed = visited * 2.0 * 128 * 256 * 128
-            peak_i8, note = int8_peak(peaks)
-            ov.update({"executed_tops": round(executed / secs / 1e12, 1), "int8_peak_tops": round(peak_i8, 1),
-                       "int8_peak_source": note, "tensor_frac": round(executed / secs / 1e12 / peak_i8, 4),
+            peak_i8, note = tensor_peak(peaks)
+            ov.update({"executed_tops": round(executed / secs / 1e12, 1), "tensor_peak_tops": round(peak_i8, 1),
+                       "tensor_peak_source": note, "tensor_frac": round(executed / secs / 1e12 / peak_i8, 4),
                        "algorithmic_equivalent_tops": round(float(cfg["R"]) ** 2 * cfg["mask"] ** 2 * cfg["n_img"]
                                                             / secs / 1e12, 1)})
         table["mask_overlap"].update(ov)
         if dominant == "mask_overlap" and visited:
-            roofline.update({"bound": "tensor", "achieved": ov["executed_tops"], "peak": ov["int8_peak_tops"],
-                             "unit": "TFLOP/s", "frac": ov["tensor_frac"], "peak_note": ov["int8_peak_source"]})
+            roofline.update({"bound": "tensor", "achieved": ov["executed_tops"], "peak": ov["tensor_peak_tops"],
+                             "unit": "TFLOP/s", "frac": ov["tensor_frac"], "peak_note": ov["tensor_peak_source"]})
         res.update({"roofline": roofline, "stages": table,
                     "step_roofline": {"algorithmic_mb_per_image": round(total_bytes / 1e6, 1),
                                       "hbm_frac": round(res["images_per_s"] / world * total_bytes / 1e9 / peaks["hbm_gbs"], 4)}})
@@ -518,15 +520,16 @@ def measure_training(name, cfg, args, dev, rank, world, peaks, cdist, headline):
     return res
 
 
-def int8_peak(peaks):
-    """Dense int8 tensor peak of THIS chip: tools/micro/imma_peak.cu's measurement when committed
-    (profiles/imma_peak.json), else the assumption 2 x measured bf16 burst, labelled as such."""
+def tensor_peak(peaks):
+    """Dense tensor peak of THIS chip for the overlap kernel's instruction (tcgen05.mma.kind::mxf4, E2M1 operands):
+    tools/micro/mxf4_check.cu's measurement when committed (profiles/mxf4_peak.json), else 4 x the measured bf16
+    burst (the nominal fp4 : bf16 ratio), labelled as an assumption."""
     try:
-        with open(os.path.join(ROOT, "profiles", "imma_peak.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "mxf4_peak.json")) as f:
             t = json.load(f)
-        return float(t["int8_tops"]), f"measured, tools/micro/imma_peak.cu ({t.get('how', '')})"
+        return float(t["mxf4_tops"]), f"measured, tools/micro/mxf4_check.cu ({t.get('how', '')})"
     except (OSError, ValueError, KeyError):
-        return 2 * peaks["bf16_tflops"], "ASSUMED 2 x measured bf16 burst (no committed int8 measurement)"
+        return 4 * peaks["bf16_tflops"], "ASSUMED 4 x measured bf16 burst (no committed mxf4 measurement)"
 
 
 def measure_inference(name, cfg, args, dev, rank, world, peaks, cdist):

@@ -181,6 +181,77 @@ __global__ void mask_unpack_crops_tiled_meta_kernel(const uint32_t *__restrict__
     }
 }
 
+// The same, as a SPARSE UPDATE of a buffer that already holds an earlier batch of unpacked crops (and zeros everywhere
+// else): prev[m] = the crop rectangle (wx0, y0, ww, h) of the mask currently stored in row m, all zero for an empty row.
+// A warp only visits the patches of the bounding rectangle of the old and the new crop -- it writes the new patch
+// (zeros where only the old crop was) -- instead of all H * W / 128 of them: masks cover a few percent of the image, so
+// a step re-writes ~10 % of the 524 MB instead of all of it.  The K-block bitmap (64 words per mask) is rebuilt in
+// shared memory and written whole; prev[m] becomes the new rectangle.
+__global__ void mask_unpack_crops_tiled_meta_sparse_kernel(const uint32_t *__restrict__ crop_words,
+                                                           const int32_t *__restrict__ meta, const long long *__restrict__ off,
+                                                           uint32_t *__restrict__ packed, int4 *__restrict__ prev,
+                                                           int32_t *__restrict__ area, uint32_t *__restrict__ kbmap,
+                                                           int4 *__restrict__ kinfo, long long n_masks, int H, int W,
+                                                           long long words, int bw) {
+    extern __shared__ uint32_t s_bitmaps[];                      // [warps][bw]
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long m = blockIdx.x * (long long)(blockDim.x >> 5) + wib;
+    if (m >= n_masks) return;
+    uint32_t *bm = s_bitmaps + wib * bw;
+    for (int j = lane; j < bw; j += 32) bm[j] = 0u;
+    const int wx0 = meta[4 * m], y0 = meta[4 * m + 1], ww = meta[4 * m + 2], h = meta[4 * m + 3];
+    const int4 pv = prev[m];
+    const uint32_t *src = crop_words + off[m];
+    uint4 *row4 = reinterpret_cast<uint4 *>(packed + m * words);
+    const int bpr = W >> 4, nby = H >> 3;
+    // patch rectangles (16-pixel columns x 8-pixel rows) of the new and the old crop, clipped to the image
+    int bx_lo = bpr, bx_hi = 0, by_lo = nby, by_hi = 0;          // [lo, hi)
+    if (ww > 0 && h > 0) { bx_lo = min(bx_lo, 2 * wx0); bx_hi = max(bx_hi, 2 * (wx0 + ww)); by_lo = min(by_lo, y0 >> 3); by_hi = max(by_hi, ((y0 + h - 1) >> 3) + 1); }
+    if (pv.z > 0 && pv.w > 0) { bx_lo = min(bx_lo, 2 * pv.x); bx_hi = max(bx_hi, 2 * (pv.x + pv.z)); by_lo = min(by_lo, pv.y >> 3); by_hi = max(by_hi, ((pv.y + pv.w - 1) >> 3) + 1); }
+    bx_lo = max(bx_lo, 0); by_lo = max(by_lo, 0); bx_hi = min(bx_hi, bpr); by_hi = min(by_hi, nby);
+    const int nx = max(bx_hi - bx_lo, 0), cells = nx * max(by_hi - by_lo, 0);
+    int s = 0, alo = 0x7fffffff, ahi = -1, blo = 0x7fffffff, bhi = -1;
+    __syncwarp();
+    for (int e = lane; e < cells; e += 32) {
+        const int by = by_lo + e / nx, bx = bx_lo + e % nx, kb = by * bpr + bx;
+        const int k = (bx >> 1) - wx0;                           // crop word column holding these 16 pixels
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (k >= 0 && k < ww) {
+            const int sh = (bx & 1) * 16;
+            uint32_t o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int r0 = 8 * by + 2 * q - y0, r1 = r0 + 1;
+                const uint32_t lo = (r0 >= 0 && r0 < h) ? (__ldg(src + (long long)r0 * ww + k) >> sh) & 0xffffu : 0u;
+                const uint32_t hi = (r1 >= 0 && r1 < h) ? (__ldg(src + (long long)r1 * ww + k) >> sh) & 0xffffu : 0u;
+                o[q] = lo | (hi << 16);
+            }
+            v = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        row4[kb] = v;
+        s += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+        if ((v.x | v.y | v.z | v.w) != 0u) {
+            atomicOr(bm + (kb >> 5), 1u << (kb & 31));
+            alo = min(alo, bx); ahi = max(ahi, bx); blo = min(blo, by); bhi = max(bhi, by);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        alo = min(alo, __shfl_xor_sync(0xffffffffu, alo, o));
+        ahi = max(ahi, __shfl_xor_sync(0xffffffffu, ahi, o));
+        blo = min(blo, __shfl_xor_sync(0xffffffffu, blo, o));
+        bhi = max(bhi, __shfl_xor_sync(0xffffffffu, bhi, o));
+    }
+    __syncwarp();
+    for (int j = lane; j < bw; j += 32) kbmap[m * bw + j] = bm[j];
+    if (lane == 0) {
+        area[m] = s;
+        kinfo[m] = ahi >= 0 ? make_int4(1, alo + ahi, blo + bhi, 0) : make_int4(0, 0, 0, 0);
+        prev[m] = make_int4(wx0, y0, ww, h);
+    }
+}
+
 // ------------------------------------------------------------------------------- unpack crops
 // Wire format for proposal masks (host -> device): only the bounding box of every mask is sent.
 // crop row r, word k holds pixels (y0 + r, 32 * wx0 + 32 k .. + 31); it is OR-ed into the flat
@@ -646,6 +717,27 @@ CIM_API int cim_mask_unpack_crops_tiled_meta(const uint32_t *crop_words, const i
     mask_unpack_crops_tiled_meta_kernel<<<(unsigned)((n_masks + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
         crop_words, crop_meta, reinterpret_cast<const long long *>(crop_off), packed, mm.area, mm.kbmap, mm.kinfo,
         n_masks, H, W, words, bw);
+    return cim_launch_status();
+}
+
+CIM_API int cim_mask_unpack_crops_tiled_meta_sparse(const uint32_t *crop_words, const int32_t *crop_meta,
+                                                    const int64_t *crop_off, uint32_t *packed, int32_t *prev_rects,
+                                                    void *meta, size_t meta_bytes, int n_img, int n, int H, int W,
+                                                    int64_t words, cim_stream_t stream) {
+    if (!crop_words || !crop_meta || !crop_off || !packed || !prev_rects || !meta || n_img < 0 || n < 0 || H <= 0 || W <= 0)
+        return CIM_ERR_ARG;
+    if ((H & 7) || (W & 15)) return CIM_ERR_SHAPE;
+    if (words * 32 != (int64_t)H * W || (words & 3) || !cim_aligned(packed, 16) || !cim_aligned(prev_rects, 16))
+        return CIM_ERR_ALIGN;
+    if (meta_bytes < cim_mask_meta_bytes(n_img, n, words) || !cim_aligned(meta, 256)) return CIM_ERR_WORKSPACE;
+    if (n_img == 0 || n == 0) return CIM_OK;
+    const MaskMeta mm = carve_meta(meta, n_img, n, words);
+    const long long n_masks = (long long)n_img * n;
+    const int bw = (int)(((words + 3) / 4 + 31) / 32);
+    if ((size_t)bw * 8 * 4 > 48 * 1024) return CIM_ERR_SHAPE;          // bitmap of 8 masks in static-limit shared memory
+    mask_unpack_crops_tiled_meta_sparse_kernel<<<(unsigned)((n_masks + 7) / 8), 256, (size_t)bw * 8 * 4, (cudaStream_t)stream>>>(
+        crop_words, crop_meta, reinterpret_cast<const long long *>(crop_off), packed, reinterpret_cast<int4 *>(prev_rects),
+        mm.area, mm.kbmap, mm.kinfo, n_masks, H, W, words, bw);
     return cim_launch_status();
 }
 

@@ -339,13 +339,17 @@ class CIMHeadStep:
         self.ho_checksum = pin((2,), torch.float32)
         with torch.cuda.device(self.dev):
             dv = lambda shape, dt: torch.empty(shape, dtype=dt, device=self.dev)
+            # masks: ZERO-filled when they are produced from crops -- the fused unpack is a sparse update that only
+            # touches the rectangles of the crop a row held before (prev_rects) and of the new one
+            mk = torch.zeros if self.crop_cap else torch.empty
             self.di = [dict(rois=dv((n_img * R, 5), torch.float32), labels=dv((n_img, self.C), torch.float32),
-                            masks=dv((n_img, R, self.words), torch.int32), ready=torch.cuda.Event(),
-                            free=torch.cuda.Event()) for _ in range(2)]
+                            masks=mk((n_img, R, self.words), dtype=torch.int32, device=self.dev),
+                            ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
             if self.crop_cap:
                 for buf in self.di:
                     buf.update(crop_words=dv((self.crop_cap,), torch.int32), crop_meta=dv((n_img * R, 4), torch.int32),
-                               crop_off=dv((n_img * R,), torch.int64))
+                               crop_off=dv((n_img * R,), torch.int64),
+                               prev_rects=torch.zeros((n_img * R, 4), dtype=torch.int32, device=self.dev))
             # mask metadata (areas, K-block bitmaps) produced on the copy stream right after the masks land
             self.use_meta = self.words % 4 == 0
             if self.use_meta:
@@ -405,15 +409,18 @@ class CIMHeadStep:
                     fused = bool(self.kb_per_row) and self.use_meta and \
                         self.words * 32 == self.mask_hw[0] * self.mask_hw[1]
                     if fused:
-                        # crops -> tiled bit masks + their metadata in one pass (every packed word written once)
-                        rc = self.L.cim_mask_unpack_crops_tiled_meta(
+                        # crops -> tiled bit masks + their metadata in one pass, as a sparse update of the buffer:
+                        # the patches of the crops it held two steps ago are cleared, those of the new crops written
+                        rc = self.L.cim_mask_unpack_crops_tiled_meta_sparse(
                             _lib.ptr(buf["crop_words"]), _lib.ptr(buf["crop_meta"]), _lib.ptr(buf["crop_off"]),
-                            _lib.ptr(buf["masks"]), _lib.ptr(buf["meta"]), buf["meta"].numel(), self.n_img, self.R,
-                            self.mask_hw[0], self.mask_hw[1], self.words, C.c_void_p(self.copy_stream.cuda_stream))
-                        _lib.check(rc, "cim_mask_unpack_crops_tiled_meta")
+                            _lib.ptr(buf["masks"]), _lib.ptr(buf["prev_rects"]), _lib.ptr(buf["meta"]),
+                            buf["meta"].numel(), self.n_img, self.R, self.mask_hw[0], self.mask_hw[1], self.words,
+                            C.c_void_p(self.copy_stream.cuda_stream))
+                        _lib.check(rc, "cim_mask_unpack_crops_tiled_meta_sparse")
                         buf["meta_done"] = True
                     else:
                         unpack = self.L.cim_mask_unpack_crops_tiled if self.kb_per_row else self.L.cim_mask_unpack_crops
+                        buf["prev_rects"].zero_()     # (these entry points zero `masks` themselves; no rectangle list)
                         rc = unpack(_lib.ptr(buf["crop_words"]), _lib.ptr(buf["crop_meta"]), _lib.ptr(buf["crop_off"]),
                                     _lib.ptr(buf["masks"]), self.n_img * self.R, self.mask_hw[0], self.mask_hw[1],
                                     self.words, C.c_void_p(self.copy_stream.cuda_stream))

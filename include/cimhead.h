@@ -214,6 +214,14 @@ size_t cim_mask_meta_bytes(int n_img, int n, int64_t words);
 int cim_mask_unpack_crops_tiled_meta(const uint32_t *crop_words, const int32_t *crop_meta, const int64_t *crop_off,
                                      uint32_t *packed, void *meta, size_t meta_bytes, int n_img, int n, int H, int W,
                                      int64_t words, cim_stream_t stream);
+/* The same as a SPARSE UPDATE of a `packed` buffer that already holds an earlier batch of crops: prev_rects [n_img * n][4]
+ * int32 (16-byte aligned) = the crop rectangle (wx0, y0, ww, h) of the mask currently stored in each row, all zero for a
+ * row of zeros.  Only the patches of the old and the new rectangle are visited (the old ones are cleared), prev_rects is
+ * updated in place.  First use: a zero-filled `packed` and zero-filled prev_rects.  The input-prefetch path of a training
+ * loop re-writes ~10 % of the buffer per step this way instead of all of it. */
+int cim_mask_unpack_crops_tiled_meta_sparse(const uint32_t *crop_words, const int32_t *crop_meta, const int64_t *crop_off,
+                                            uint32_t *packed, int32_t *prev_rects, void *meta, size_t meta_bytes, int n_img,
+                                            int n, int H, int W, int64_t words, cim_stream_t stream);
 int cim_mask_meta(const uint32_t *packed, int n_img, int n, int64_t words, int kb_per_row, void *meta,
                   size_t meta_bytes, cim_stream_t stream);
 int cim_mask_overlap_meta(const uint32_t *packed, const void *meta, int n_img, int n, int64_t words, int kb_per_row,

@@ -242,6 +242,50 @@ def test_fused_crop_unpack_and_meta_equals_the_two_separate_calls():
     assert_f16_bits_equal(u16(iou1), u16(iou2))
 
 
+def test_sparse_crop_unpack_over_successive_batches_equals_the_dense_unpack():
+    """cim_mask_unpack_crops_tiled_meta_sparse updates a zero-initialised buffer batch after batch (clearing the rectangle
+    a row held before, writing the new one): after every batch masks and metadata are bit-identical to the dense fused
+    unpack of that batch alone -- incl. rows that become empty, rows that were empty, and shrinking / moving crops."""
+    from cim_b200 import _lib
+    n_img, n, h, w = 2, 120, 64, 96
+    L = _lib.lib()
+    st = _lib.stream_ptr(torch.device(DEV))
+    words = h * w // 32
+    packed = torch.zeros(n_img, n, words, dtype=torch.int32, device=DEV)
+    prev = torch.zeros(n_img * n, 4, dtype=torch.int32, device=DEV)
+    nbytes = L.cim_mask_meta_bytes(n_img, n, words)
+    meta = torch.zeros(nbytes, dtype=torch.uint8, device=DEV)
+    for batch in range(4):
+        g = torch.Generator().manual_seed(100 + batch)
+        masks = torch.zeros(n_img * n, h, w, dtype=torch.uint8)
+        for i in range(n_img * n):
+            if (i + batch) % 11 == 3:
+                continue                                                 # empty in this batch
+            y0, x0 = int(torch.randint(0, h - 1, (1,), generator=g)), int(torch.randint(0, w - 1, (1,), generator=g))
+            y1, x1 = int(torch.randint(y0 + 1, h + 1, (1,), generator=g)), int(torch.randint(x0 + 1, w + 1, (1,), generator=g))
+            masks[i, y0:y1, x0:x1] = (torch.rand(y1 - y0, x1 - x0, generator=g) < 0.5).to(torch.uint8)
+        c = mask_ops.pack_crops_host(masks)
+        crops = mask_ops.MaskCrops(c.words.to(DEV), c.meta.to(DEV), c.off.to(DEV), c.height, c.width)
+        want = torch.full_like(packed, -1)
+        want_meta = torch.full_like(meta, 0x33)
+        _lib.check(L.cim_mask_unpack_crops_tiled_meta(_lib.ptr(crops.words), _lib.ptr(crops.meta), _lib.ptr(crops.off),
+                                                      _lib.ptr(want), _lib.ptr(want_meta), want_meta.numel(), n_img, n, h,
+                                                      w, words, st), "dense unpack")
+        _lib.check(L.cim_mask_unpack_crops_tiled_meta_sparse(_lib.ptr(crops.words), _lib.ptr(crops.meta),
+                                                             _lib.ptr(crops.off), _lib.ptr(packed), _lib.ptr(prev),
+                                                             _lib.ptr(meta), meta.numel(), n_img, n, h, w, words, st),
+                   "sparse unpack")
+        assert torch.equal(packed, want), f"batch {batch}: masks differ"
+        nm = n_img * n
+        bw = ((words // 4) + 31) // 32
+        up = lambda v: (v + 255) & ~255
+        a0, k0, b0 = 0, up(nm * 4), up(nm * 4) + up(nm * 16)
+        assert torch.equal(meta[a0:a0 + nm * 4], want_meta[a0:a0 + nm * 4])                    # areas
+        assert torch.equal(meta[k0:k0 + nm * 16], want_meta[k0:k0 + nm * 16])                  # sort keys
+        assert torch.equal(meta[b0:b0 + nm * bw * 4], want_meta[b0:b0 + nm * bw * 4])          # K-block bitmaps
+        assert torch.equal(prev.cpu(), c.meta.view(-1, 4))
+
+
 def test_tensor_path_rejects_what_it_cannot_take():
     packed = mask_ops.mask_pack(torch.ones(70, 5, 5, dtype=torch.uint8, device=DEV))      # 1 word per mask
     with pytest.raises(RuntimeError, match="shape"):

@@ -85,10 +85,10 @@ with torch.cuda.stream(hp):
                 if after is not None:
                     step.copy_stream.wait_event(after)
                 step.copy_stream.wait_event(buf["free"])
-                rc = step.L.cim_mask_unpack_crops_tiled_meta(
+                rc = step.L.cim_mask_unpack_crops_tiled_meta_sparse(
                     step.di[0]["crop_words"].data_ptr(), step.di[0]["crop_meta"].data_ptr(), step.di[0]["crop_off"].data_ptr(),
-                    buf["masks"].data_ptr(), buf["meta"].data_ptr(), buf["meta"].numel(), step.n_img, step.R,
-                    step.mask_hw[0], step.mask_hw[1], step.words, step.copy_stream.cuda_stream)
+                    buf["masks"].data_ptr(), buf["prev_rects"].data_ptr(), buf["meta"].data_ptr(), buf["meta"].numel(),
+                    step.n_img, step.R, step.mask_hw[0], step.mask_hw[1], step.words, step.copy_stream.cuda_stream)
                 assert rc == 0
                 buf["ready"].record(step.copy_stream)
         if defer_kernels:
