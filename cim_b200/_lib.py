@@ -17,6 +17,7 @@ MAX_LAYERS = 4
 OVERLAP_ALGOS = {"auto": 0, "popc": 1, "tensor": 2}
 #: cim_set_debug_flags bits (include/cimhead.h): diagnostic kernel selection for A/B timing and bit-identity tests
 DBG_ROI_BWD_SMEM_TILE, DBG_OVERLAP_LOADER_WARP, DBG_SCORE_FFMA, DBG_ROI_NO_WINDOWS, DBG_ROI_BWD_ONE_CHUNK = 1, 2, 4, 8, 16
+DBG_ROI_POOL_SIMPLE = 32
 
 _lock = threading.Lock()
 _lib = None

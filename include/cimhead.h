@@ -49,7 +49,8 @@ enum {
     CIM_DBG_OVERLAP_LOADER_WARP = 2u, /* no effect any more (it selected the loader-warp pipeline of the int8 overlap kernel); kept so that callers still build */
     CIM_DBG_SCORE_FFMA = 4u,          /* scoring GEMMs fwd / bwd: plain fp32 FFMA kernels, not 3xTF32 tcgen05       */
     CIM_DBG_ROI_NO_WINDOWS = 8u,      /* RoIAlign on maps larger than the smem tile: global-pairs kernels           */
-    CIM_DBG_ROI_BWD_ONE_CHUNK = 16u   /* RoIAlign backward: one 32-channel chunk per CTA instead of two             */
+    CIM_DBG_ROI_BWD_ONE_CHUNK = 16u,  /* RoIAlign backward: one 32-channel chunk per CTA instead of two             */
+    CIM_DBG_ROI_POOL_SIMPLE = 32u     /* RoIPool fwd / bwd: thread-per-output kernels, not the shared-memory tile   */
 };
 void cim_set_debug_flags(unsigned flags);
 unsigned cim_get_debug_flags(void);

@@ -189,6 +189,74 @@ def test_roi_pool_exact_and_backward(variant):
         np.testing.assert_array_equal(out.detach().cpu().numpy(), ref_out.cpu().numpy())
 
 
+def _pool_raw(feat, rois, scale, variant, g=None):
+    """cim_roi_pool_fwd_ex (+ cim_roi_pool_bwd) through the C ABI: pooled values, int32 argmax, grad_feat."""
+    L, P = _lib.lib(), _lib.ptr
+    B, C, H, W = feat.shape
+    K = rois.shape[0]
+    out = torch.empty(K, C, 7, 7, device=DEV)
+    arg = torch.empty(K, C, 7, 7, dtype=torch.int32, device=DEV)
+    st = _lib.stream_ptr(feat.device)
+    _lib.check(L.cim_roi_pool_fwd_ex(P(feat), P(rois), P(out), P(arg), B, C, H, W, K, 7, 7, scale,
+                                     ops.ROI_POOL_VARIANTS[variant], st), "pool fwd")
+    gf = None
+    if g is not None:
+        gf = torch.full((B, C, H, W), float("nan"), device=DEV)       # the op must write every element
+        _lib.check(L.cim_roi_pool_bwd(P(g), P(arg), P(rois), P(gf), B, C, H, W, K, 7, 7, st), "pool bwd")
+    torch.cuda.synchronize()
+    return out, arg, gf
+
+
+@pytest.mark.parametrize("variant", ["mmcv", "legacy"])
+@pytest.mark.parametrize("shape", [(3, 64, 20, 24, 300), (2, 48, 15, 17, 200), (2, 24, 40, 40, 150),
+                                   (9, 32, 8, 8, 40), (1, 64, 12, 12, 9000)])
+def test_roi_pool_tile_kernels_equal_simple_kernels(variant, shape):
+    """The shared-memory tile kernels (32 / 16 / 8 channels per tile, odd map sizes, rois NOT grouped by image, an
+    out-of-range batch index, more ROIs than one compaction round) against the thread-per-output kernels: pooled
+    values and argmax bit for bit, gradients to fp32 summation order; and both against the oracle."""
+    B, C, H, W, K = shape
+    scale = 0.25
+    feat = torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(21))
+    feat[:, :, 3, 4] = feat[:, :, 3, 5]                                      # ties: the first maximum must win
+    rois = random_rois(31, B, K, H, W, scale, wild=True, sort=False)
+    rois[7, 0] = B + 3                                                       # invalid image: pools nothing
+    if K > 20:
+        rois[11, 0] = -1
+    f, r = feat.to(DEV), rois.to(DEV)
+    g = torch.randn(K, C, 7, 7, generator=torch.Generator().manual_seed(5)).to(DEV)
+    out_t, arg_t, gf_t = _pool_raw(f, r, scale, variant, g)
+    with _lib.debug_flags(_lib.DBG_ROI_POOL_SIMPLE):
+        out_s, arg_s, gf_s = _pool_raw(f, r, scale, variant, g)
+    assert torch.equal(out_t, out_s) and torch.equal(arg_t, arg_s)
+    close(gf_t.cpu().numpy(), gf_s.cpu().numpy(), rel=1e-5)
+    bad = (rois[:, 0] < 0) | (rois[:, 0] >= B)
+    assert (out_t[bad.to(DEV)] == 0).all() and (arg_t[bad.to(DEV)] == -1).all()
+    sel = torch.nonzero(~bad).flatten()[:400]                                # the oracle does not guard the image index
+    want, arg = roi_oracle.roi_pool_fwd(feat.numpy(), rois[sel].numpy(), 7, 7, scale, variant)
+    np.testing.assert_array_equal(out_t[sel.to(DEV)].cpu().numpy(), want)
+    np.testing.assert_array_equal(arg_t[sel.to(DEV)].cpu().numpy(), arg)
+
+
+def test_roi_pool_tile_kernels_benchmarked_shape():
+    """cfg2's shape (8 x 2000 proposals, 1024 x 32 x 32 map): tile kernels == simple kernels over the full output,
+    oracle on sampled ROIs."""
+    B, R = 8, 2000
+    C, H, W, scale = synth.feature_shape("resnet50")
+    rois = torch.cat([synth.rois_from_params(synth.proposal_params(R, 512, 77 + b), b) for b in range(B)]).to(DEV)
+    feat = torch.randn(B, C, H, W, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3))
+    g = torch.randn(B * R, C, 7, 7, device=DEV, generator=torch.Generator(device=DEV).manual_seed(4))
+    out_t, arg_t, gf_t = _pool_raw(feat, rois, scale, "mmcv", g)
+    with _lib.debug_flags(_lib.DBG_ROI_POOL_SIMPLE):
+        out_s, arg_s, gf_s = _pool_raw(feat, rois, scale, "mmcv", g)
+    assert torch.equal(out_t, out_s) and torch.equal(arg_t, arg_s)
+    del out_s, arg_s, g
+    close(gf_t.cpu().numpy(), gf_s.cpu().numpy(), rel=1e-5)
+    idx = torch.randperm(B * R, generator=torch.Generator().manual_seed(1))[:48].sort().values.to(DEV)
+    want, arg = roi_oracle.roi_pool_fwd(feat.cpu().numpy(), rois[idx].cpu().numpy(), 7, 7, scale, "mmcv")
+    np.testing.assert_array_equal(out_t[idx].cpu().numpy(), want)
+    np.testing.assert_array_equal(arg_t[idx].cpu().numpy(), arg)
+
+
 def test_errors_are_raised_not_printed():
     f = torch.zeros(1, 32, 8, 8, device=DEV)
     with pytest.raises(ValueError):
