@@ -348,12 +348,15 @@ def source_sha16():
     return h.hexdigest()[:16]
 
 
-def timed(fn, steps, warmup, dev, cdist=None):
+def timed(fn, steps, warmup, dev, cdist=None, finish=None):
     """CUDA events on the launching stream around `steps` calls, barrier + synchronize on both sides, max over ranks
-    (cdist=None: this rank alone, no barrier)."""
+    (cdist=None: this rank alone, no barrier).  finish: host work that belongs to the timed region's end (the RNG
+    commit of the sync-free sampling mode)."""
     import torch
     for _ in range(warmup):
         fn()
+    if finish is not None:
+        finish()
     torch.cuda.synchronize()
     if cdist is not None:
         cdist.barrier()
@@ -361,12 +364,23 @@ def timed(fn, steps, warmup, dev, cdist=None):
     e0.record()
     for _ in range(steps):
         fn()
+    if finish is not None:
+        finish()
     e1.record()
     torch.cuda.synchronize()
     if cdist is None:
         return e0.elapsed_time(e1) / steps
     cdist.barrier()
     return cdist.max_over_ranks(e0.elapsed_time(e1) / steps, dev)
+
+
+SAMPLING_NOTE = {
+    "stream": "anti-noise sampling without a host hop: the device reads numpy's random stream from a ring the host "
+              "fills ahead of time (cim_anti_noise_stream), pseudo-GT counts are read back with a lag, np.random is "
+              "advanced at the end of the timed region (CIMHeadStep.sync_rng); bit-identical to the hop "
+              "(tests/test_gpu_step.py); ms_per_step_sampling_hop = the same step with the hop",
+    "hop": "pseudo-GT counts D2H, one np.random.random_sample call, uniforms H2D, cim_anti_noise",
+}
 
 
 def stage_table(stage_ms, bytes_img, n_img, peaks):
@@ -399,7 +413,7 @@ def measure_training(name, cfg, args, dev, rank, world, peaks, cdist, headline):
     words = inp["packed"].shape[-1]
     step = CIMHeadStep(cfg["n_img"], cfg["R"], cfg["C"], Cf, H, W, scale, words,
                        anti_noise_sampling=not args.no_anti_noise, device=dev, mask_kb_per_row=inp["kb_per_row"],
-                       head_grads=not args.no_head_grads, order="graph")
+                       head_grads=not args.no_head_grads, order="graph", rng=args.sampling)
     mat = None if args.no_head_grads else inp["mat"]
     run = lambda order: step.run(inp["feat"], inp["rois"], inp["grad_out"], inp["packed"], inp["seg_x"], inp["weight"],
                                  inp["bias"], inp["labels"], mat=mat, order=order, mask_meta=inp["mask_meta"])
@@ -408,9 +422,14 @@ def measure_training(name, cfg, args, dev, rank, world, peaks, cdist, headline):
     sampler = ClockSampler(dev.index or 0)
     if headline and rank == 0:
         sampler.start()
-    ms_graph = timed(lambda: run("graph"), steps, warmup, dev, cdist)
+    ms_graph = timed(lambda: run("graph"), steps, warmup, dev, cdist, finish=step.sync_rng)
     clocks = sampler.stop() if headline and rank == 0 else None
-    ms_over = timed(lambda: run("overlapped"), steps, 2, dev, cdist)
+    ms_hop = None
+    if args.sampling == "stream" and not args.no_anti_noise:
+        step.rng = "hop"                       # same step, same buffers, the host hop instead of the device ring
+        ms_hop = timed(lambda: run("graph"), steps, 2, dev, cdist)
+        step.rng = "stream"
+    ms_over = timed(lambda: run("overlapped"), steps, 2, dev, cdist, finish=step.sync_rng)
     n_images = cfg["n_img"] * world
     res = {"workload": name, "images_per_gpu": cfg["n_img"], "steps": steps, "warmup": warmup,
            "ms_per_step": ms_graph, "images_per_s": n_images / (ms_graph * 1e-3),
@@ -419,7 +438,9 @@ def measure_training(name, cfg, args, dev, rank, world, peaks, cdist, headline):
            "ms_per_step_overlapped_order": ms_over,
            "overlapped_order_note": "round-1 order: maps, scoring and mining first, the sampling hop hidden behind the "
                                     "RoIAlign forward; needs seg_x independent of this step's RoIAlign output",
-           "sampling_hop": "pseudo-GT counts D2H, one np.random.random_sample call, uniforms H2D, cim_anti_noise"}
+           "sampling": SAMPLING_NOTE[args.sampling]}
+    if ms_hop is not None:
+        res["ms_per_step_sampling_hop"] = ms_hop
     if headline:
         res["clocks"] = clocks
         # end to end through the public call with HOST inputs (rois, labels, bbox-cropped bit-packed masks) and
@@ -442,12 +463,14 @@ def measure_training(name, cfg, args, dev, rank, world, peaks, cdist, headline):
             for _ in range(3):
                 run_host()
             step.flush_results()
+            step.sync_rng()
             cdist.barrier()
             torch.cuda.synchronize()
             e0.record()
             for _ in range(steps):
                 run_host()             # reads the previous step's results on the host while this step computes
             step.flush_results()       # ... and the last step's: every timed step's H2D, D2H and host wait are inside
+            step.sync_rng()            # sampling "stream": numpy's generator brought to where the steps left it
             e1.record()
             torch.cuda.synchronize()
         ms_e2e = cdist.max_over_ranks(e0.elapsed_time(e1) / steps, dev)
@@ -605,6 +628,9 @@ def main():
     ap.add_argument("--also", default="cfg3_vgg16_voc_64,cfg4_r50_coco_8x2000_q,cfg5_hrnet48_coco_infer_8x4000",
                     help="comma-separated workloads measured after the headline one and reported under `workloads` "
                          "('' for none)")
+    ap.add_argument("--sampling", default="stream", choices=["stream", "hop"],
+                    help="anti-noise sampling: uniforms from a device ring filled ahead (no host sync inside the step) "
+                         "or the host hop (counts down, draw, uniforms up)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-anti-noise", action="store_true")
     ap.add_argument("--no-head-grads", action="store_true",
@@ -681,7 +707,8 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
         "step_order": head["order"], "ms_per_step_graph_order": head["ms_per_step"],
         "ms_per_step_overlapped_order": head["ms_per_step_overlapped_order"],
-        "overlapped_order_note": head["overlapped_order_note"], "sampling_hop": head["sampling_hop"],
+        "overlapped_order_note": head["overlapped_order_note"], "sampling": head["sampling"],
+        "ms_per_step_sampling_hop": head.get("ms_per_step_sampling_hop"),
         "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "collective": head["collective"],
         "roofline": head["roofline"], "step_roofline": head["step_roofline"], "stages": head["stages"],
         "clocks": head["clocks"], "kernel_source_sha16": source_sha16(),

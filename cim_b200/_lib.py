@@ -81,6 +81,7 @@ _SIGNATURES = {
                       _P, _SZ, _P]),
     "cim_anti_noise_uniform_count_max": (_SZ, [C.POINTER(MineParams)]),
     "cim_anti_noise": (_I, [C.POINTER(MineParams), _P, _P, _P, _P, _P, _P, _P]),
+    "cim_anti_noise_stream": (_I, [C.POINTER(MineParams), _P, _P, _P, _P, _P, C.c_int64, _P, _P, _P, _P]),
     "cim_assign": (_I, [C.POINTER(MineParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

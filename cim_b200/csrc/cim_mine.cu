@@ -370,10 +370,22 @@ __device__ float np_pairwise_sum_f32(const float *a, int n) {
 __global__ void __launch_bounds__(32)
 cim_anti_noise_kernel(cim_mine_params p, const float *__restrict__ labels, const int *__restrict__ gt_count,
                       const int *__restrict__ gt_class, const float *__restrict__ gt_weight,
-                      const double *__restrict__ uniforms, unsigned char *__restrict__ gt_keep) {
+                      const double *__restrict__ uniforms, unsigned char *__restrict__ gt_keep,
+                      const long long *__restrict__ cursor_in, long long *__restrict__ cursor_out, long long ring_len) {
     extern __shared__ __align__(16) unsigned char an_smem[];
     const int l = blockIdx.x, img = blockIdx.y, lane = threadIdx.x;
     const int g = min(gt_count[l * p.n_img + img], p.gt_cap);
+    // stream mode (cim_anti_noise_stream): `uniforms` is a ring holding a stretch of the host's random stream, the
+    // step's first double sits at absolute position *cursor_in; the first block leaves *cursor_in + (doubles this
+    // step consumes) in *cursor_out for the next step (a different word: the other blocks still read *cursor_in)
+    const long long cbase = cursor_in ? *cursor_in : 0;
+    if (cursor_out && l == 0 && img == 0) {
+        long long tot = 0;
+        for (int t = lane; t < p.n_img * p.n_layers; t += 32) tot += min(gt_count[t], p.gt_cap);
+#pragma unroll
+        for (int s = 16; s; s >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, s);
+        if (lane == 0) *cursor_out = cbase + tot;
+    }
     double *cdf = reinterpret_cast<double *>(an_smem);                 // [gt_cap]
     int *idx = reinterpret_cast<int *>(cdf + p.gt_cap);                // [gt_cap]
     float *prob = reinterpret_cast<float *>(idx + p.gt_cap);           // [gt_cap]
@@ -420,7 +432,7 @@ cim_anti_noise_kernel(cim_mine_params p, const float *__restrict__ labels, const
         for (int i = lane; i < n; i += 32) gt_keep[base + idx[i]] = 0;
         __syncwarp();
         for (int t = lane; t < n; t += 32) {
-            const double u = uniforms[off + t];
+            const double u = ring_len ? uniforms[(cbase + off + t) % ring_len] : uniforms[off + t];
             int lo = 0, hi = n;                                        // searchsorted(side='right'): first cdf > u
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
@@ -529,6 +541,26 @@ CIM_API int cim_anti_noise(const cim_mine_params *p, const float *labels, const 
     if (smem > (size_t)cim_max_smem_optin()) return CIM_ERR_SHAPE;
     cudaFuncSetAttribute(cim_anti_noise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cim_anti_noise_kernel<<<dim3(p->n_layers, p->n_img), 32, smem, (cudaStream_t)stream>>>(
-        *p, labels, gt_count, gt_class, gt_weight, uniforms, gt_keep);
+        *p, labels, gt_count, gt_class, gt_weight, uniforms, gt_keep, nullptr, nullptr, 0);
+    return cim_launch_status();
+}
+
+CIM_API int cim_anti_noise_stream(const cim_mine_params *p, const float *labels, const int32_t *gt_count,
+                                  const int32_t *gt_class, const float *gt_weight, const double *ring,
+                                  int64_t ring_len, const int64_t *cursor_in, int64_t *cursor_out, uint8_t *gt_keep,
+                                  cim_stream_t stream) {
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (!labels || !gt_count || !gt_class || !gt_weight || !ring || !gt_keep || !cursor_in || !cursor_out)
+        return CIM_ERR_ARG;
+    if (cursor_in == cursor_out) return CIM_ERR_ARG;
+    if (ring_len < (int64_t)p->n_layers * p->n_img * p->gt_cap) return CIM_ERR_SHAPE;
+    if (!cim_aligned(ring, 8) || !cim_aligned(cursor_in, 8) || !cim_aligned(cursor_out, 8)) return CIM_ERR_ALIGN;
+    const size_t smem = (size_t)p->gt_cap * 16;
+    if (smem > (size_t)cim_max_smem_optin()) return CIM_ERR_SHAPE;
+    cudaFuncSetAttribute(cim_anti_noise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cim_anti_noise_kernel<<<dim3(p->n_layers, p->n_img), 32, smem, (cudaStream_t)stream>>>(
+        *p, labels, gt_count, gt_class, gt_weight, ring, gt_keep, reinterpret_cast<const long long *>(cursor_in),
+        reinterpret_cast<long long *>(cursor_out), (long long)ring_len);
     return cim_launch_status();
 }

@@ -145,6 +145,70 @@ def draw_uniforms(counts):
     return np.random.random_sample(int(counts.sum()))
 
 
+class UniformStream:
+    """Host half of the sync-free sampling mode (cim_anti_noise_stream, CIMHeadStep(rng="stream")): doubles of numpy's
+    GLOBAL RandomState stream drawn ahead of time through a clone of its state.
+
+    Positions are absolute indices into the stream numpy's global generator will produce from the moment of
+    attach(); `drawn` = first position not handed out yet, `consumed` = first position no FINISHED step has used
+    (learned from lagged read-backs of the pseudo-GT counts), `committed` = position the global generator itself
+    has been advanced to.  commit() advances the global generator by consumed - committed doubles -- after it
+    np.random is exactly where the reference's per-class np.random.choice calls (heads.py:459) would have left it --
+    and detaches: values drawn ahead but not consumed are dropped and the next step clones the global state again, so
+    draws other code makes from np.random BETWEEN commit() and the next step keep their place in the stream.  Other
+    code must not draw from np.random between a step and the following commit()."""
+
+    def __init__(self, ring_len, max_per_step):
+        if ring_len < 16 * max_per_step:
+            raise ValueError("ring_len must be >= 16 * max_per_step")
+        self.ring_len, self.max_per_step = int(ring_len), int(max_per_step)
+        self.rs = None
+        self.drawn = self.consumed = self.committed = 0
+
+    @property
+    def attached(self):
+        return self.rs is not None
+
+    def attach(self):
+        """Clone numpy's global state; the stream continues at `consumed`."""
+        assert self.consumed == self.committed, "commit() before attaching again"
+        self.rs = np.random.RandomState()
+        self.rs.set_state(np.random.get_state())
+        self.drawn = self.consumed
+
+    def need(self, steps_unknown):
+        """Doubles to draw now so that a step launched next cannot run past `drawn`, whatever the `steps_unknown`
+        steps in flight (consumption not read back yet) and the step itself consume; 0 if the reserve suffices.
+        Top-ups come in blocks of 4 * max_per_step (numpy draws ~8 ns per double: a rare burst, off the GPU's path)."""
+        want = (steps_unknown + 1) * self.max_per_step
+        have = self.drawn - self.consumed
+        if have >= want:
+            return 0
+        n = max(want - have, 4 * self.max_per_step)
+        assert have + n <= self.ring_len - self.max_per_step, "ring too small for the steps in flight"
+        return n
+
+    def draw(self, n):
+        """n more doubles of the stream -> (absolute position of the first, float64 array)."""
+        pos = self.drawn
+        out = self.rs.random_sample(int(n))
+        self.drawn += int(n)
+        return pos, out
+
+    def note_consumed(self, n):
+        self.consumed += int(n)
+        assert self.consumed <= self.drawn, "a step consumed more uniforms than were drawn ahead"
+
+    def commit(self):
+        """Every step's consumption is known (the caller waited for the read-backs): bring np.random there, detach."""
+        n = self.consumed - self.committed
+        if n:
+            np.random.random_sample(n)
+        self.committed = self.consumed
+        self.rs = None
+        self.drawn = self.consumed
+
+
 def anti_noise_device(p, labels, gt_count, gt_class, gt_weight, gt_keep, stream=None):
     """Anti-noise sampling (heads.py:440-473) with only the random numbers coming from the host: read the pseudo-GT
     counts (sync point; the reference syncs per class, heads.py:453,457), draw the uniforms, run cim_anti_noise."""

@@ -19,6 +19,7 @@ All device work goes through the C ABI (include/cimhead.h) on the current CUDA s
 host hop is the anti-noise sampling (heads.py:451-466, numpy global RNG); it is overlapped with
 the RoIAlign kernels, which do not depend on it.
 """
+import collections
 import ctypes as C
 import os
 import time
@@ -28,7 +29,7 @@ import torch
 
 from . import _lib
 from . import dist as cdist
-from .heads import PCL_MAX_ID, draw_uniforms
+from .heads import PCL_MAX_ID, UniformStream, draw_uniforms
 
 
 class _nvtx:
@@ -59,7 +60,7 @@ class CIMHeadStep:
     def __init__(self, n_img, n_props, n_classes, feat_channels, feat_h, feat_w, spatial_scale, mask_words,
                  feat_dim=4096, refine_times=3, p_seed=0.1, step_rate=0.1, con_thr=0.85, anti_noise_sampling=True,
                  max_present=None, device="cuda:0", sampling_ratio=0, aligned=True, mask_kb_per_row=0,
-                 head_grads=False, order="graph"):
+                 head_grads=False, order="graph", rng="hop"):
         self.dev = torch.device(device)
         self.n_img, self.R, self.C, self.K = n_img, n_props, n_classes, refine_times
         self.Cf, self.H, self.W, self.scale = feat_channels, feat_h, feat_w, float(spatial_scale)
@@ -70,6 +71,9 @@ class CIMHeadStep:
         self.sr, self.aligned = int(sampling_ratio), int(bool(aligned))
         self.anti = anti_noise_sampling
         self.order = order
+        if rng not in ("hop", "stream"):
+            raise ValueError("rng must be 'hop' or 'stream'")
+        self.rng = rng
         self.L = _lib.lib()
         R, C1, nh, k = n_props, n_classes + 1, 2 + 2 * refine_times, refine_times
         dev = self.dev
@@ -129,6 +133,22 @@ class CIMHeadStep:
             self.d_uniform = e((k * n_img * gcap,), torch.float64)
         self.ev = torch.cuda.Event()
         self.last_uniform_bytes = 0
+        if self.rng == "stream" and self.anti:
+            # sync-free sampling (cim_anti_noise_stream): a device ring of uniforms drawn ahead, two cursor words the
+            # steps alternate between, the pseudo-GT counts read back with a lag of up to 2 steps
+            self.max_uniforms = k * n_img * gcap
+            ring_len = 16 * self.max_uniforms
+            self.ustream = UniformStream(ring_len, self.max_uniforms)
+            with torch.cuda.device(dev):
+                self.d_ring = torch.zeros((ring_len,), dtype=torch.float64, device=dev)
+                self.d_cursor = torch.zeros((2,), dtype=torch.int64, device=dev)
+            self.h_ring = pin((8 * self.max_uniforms,), torch.float64)      # staging of one top-up
+            self.ring_ev = torch.cuda.Event()
+            self._ring_pending = False
+            self._cursor_idx = 0
+            self._cnt_slots = [(pin((k, n_img), torch.int32), torch.cuda.Event()) for _ in range(3)]
+            self._cnt_next = 0
+            self._cnt_q = collections.deque()
         self.side = torch.cuda.Stream(device=self.dev, priority=-2)     # scoring GEMM next to the overlap helpers: above the step
         self.side2 = torch.cuda.Stream(device=self.dev, priority=-2)    # graph order: PCL_loss next to the mining kernels
         self.ev_score = torch.cuda.Event()
@@ -213,7 +233,13 @@ class CIMHeadStep:
                 ck(L.cim_mine(C.byref(p), self.cls_ptrs, self.det_ptrs, P(labels), P(self.iou), P(self.asy),
                               P(self.gt_count), P(self.gt_rows), P(self.gt_class), P(self.gt_weight),
                               P(self.asy_flag), P(self.mine_ws), self.mine_ws.numel(), st), "cim_mine")
-                if self.anti:
+                if self.anti and self.rng == "stream":
+                    hbuf, hev = self._cnt_slots[self._cnt_next]
+                    self._cnt_next = (self._cnt_next + 1) % len(self._cnt_slots)
+                    hbuf.copy_(self.gt_count, non_blocking=True)
+                    hev.record(cur)
+                    self._cnt_q.append((hbuf, hev))
+                elif self.anti:
                     self.h_count.copy_(self.gt_count, non_blocking=True)
                     self.ev.record(cur)
 
@@ -250,7 +276,18 @@ class CIMHeadStep:
         keep = None
         if tr is not None:
             tr.append(("launched_phase1", time.perf_counter()))
-        if self.anti:
+        if self.anti and self.rng == "stream":
+            # no hop: the device takes its uniforms from the ring; the host only keeps the ring ahead of the steps
+            with _nvtx("cim/sampling_stream"):
+                self._ring_top_up(cur)
+                ci = self._cursor_idx
+                ck(L.cim_anti_noise_stream(C.byref(p), P(labels), P(self.gt_count), P(self.gt_class),
+                                           P(self.gt_weight), P(self.d_ring), self.d_ring.numel(),
+                                           P(self.d_cursor[ci:]), P(self.d_cursor[ci ^ 1:]), P(self.gt_keep), st),
+                   "cim_anti_noise_stream")
+                self._cursor_idx = ci ^ 1
+            keep = self.gt_keep
+        elif self.anti:
             # the sampling hop: pseudo-GT counts down (K * n_img ints), one random_sample call from numpy's global
             # RNG (heads.draw_uniforms), the uniforms up, cim_anti_noise on the device
             with _nvtx("cim/sampling_hop"):
@@ -300,6 +337,50 @@ class CIMHeadStep:
         if tr is not None:
             tr.append(("launched_phase2", time.perf_counter()))
         return self
+
+    # -------------------------------------------------------------------------------------
+    def _drain_counts(self, keep_unknown):
+        """Read the pseudo-GT counts of finished steps (rng="stream"); wait until at most `keep_unknown` steps are
+        left whose consumption is unknown."""
+        q, us = self._cnt_q, self.ustream
+        while q and (len(q) > keep_unknown or q[0][1].query()):
+            hbuf, hev = q.popleft()
+            hev.synchronize()
+            us.note_consumed(int(np.minimum(hbuf.numpy(), self.p.gt_cap).sum()))
+
+    def _ring_top_up(self, cur):
+        """Called once per step before cim_anti_noise_stream is enqueued (the step's own count copy is already in the
+        queue): learn what finished steps consumed, draw ahead if the reserve could run out, upload in stream order
+        (the ring slots overwritten belong to positions below `consumed`, i.e. to kernels that precede the copy)."""
+        us = self.ustream
+        self._drain_counts(keep_unknown=2)              # this step + at most one earlier step still running
+        if not us.attached:
+            us.attach()
+        n = us.need(len(self._cnt_q))
+        if n <= 0:
+            return
+        if self._ring_pending:
+            self.ring_ev.synchronize()                  # the staging buffer of the previous top-up has been read
+        pos, u = us.draw(n)
+        self.h_ring.numpy()[:n] = u
+        lo = pos % us.ring_len
+        first = min(n, us.ring_len - lo)
+        self.d_ring[lo:lo + first].copy_(self.h_ring[:first], non_blocking=True)
+        if first < n:
+            self.d_ring[:n - first].copy_(self.h_ring[first:n], non_blocking=True)
+        self.ring_ev.record(cur)
+        self._ring_pending = True
+        self.last_uniform_bytes = n * 8
+
+    def sync_rng(self):
+        """rng="stream": wait for the steps in flight, advance numpy's global RandomState by the doubles they consumed
+        (it is then where the reference's np.random.choice calls would have left it) and detach from it.  Call it
+        before anything else draws from np.random (epoch boundaries: lib/roi_data/loader.py:_shuffle_roidb_inds) and
+        before reading the generator's state.  No-op for rng="hop"."""
+        if self.rng != "stream" or not self.anti:
+            return
+        self._drain_counts(keep_unknown=0)
+        self.ustream.commit()
 
     # -------------------------------------------------------------------------------------
     def alloc_host_io(self, mask_hw=None, crop_capacity_words=0):

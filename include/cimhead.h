@@ -325,6 +325,17 @@ size_t cim_anti_noise_uniform_count_max(const cim_mine_params *p);   /* L * n_im
 int cim_anti_noise(const cim_mine_params *p, const float *labels /* [n_img, C] */, const int32_t *gt_count,
                    const int32_t *gt_class, const float *gt_weight, const double *uniforms, uint8_t *gt_keep,
                    cim_stream_t stream);
+/* The same sampling WITHOUT the host hop: `ring` [ring_len doubles, ring_len >= L * n_img * gt_cap] holds a stretch
+ * of the host's random stream drawn AHEAD of time (position q of the stream lives in ring[q % ring_len]); the step's
+ * first double is at absolute position *cursor_in, and the kernel leaves *cursor_in + T (T = the doubles this step
+ * consumed = sum of gt_count) in *cursor_out for the next step (cursor_in != cursor_out: callers alternate two
+ * words).  The host never waits for gt_count inside the step: it learns T from a lagged read-back, keeps the ring
+ * filled past every position a step in flight can reach, and advances numpy's RandomState by the consumed total at
+ * its next synchronisation point (cim_b200.heads.UniformStream; CIMHeadStep(rng="stream")).  Same draws, same
+ * gt_keep as cim_anti_noise given the same stream. */
+int cim_anti_noise_stream(const cim_mine_params *p, const float *labels, const int32_t *gt_count,
+                          const int32_t *gt_class, const float *gt_weight, const double *ring, int64_t ring_len,
+                          const int64_t *cursor_in, int64_t *cursor_out, uint8_t *gt_keep, cim_stream_t stream);
 int cim_assign(const cim_mine_params *p, const void *iou_f16,
                const int32_t *gt_count, const int32_t *gt_rows, const int32_t *gt_class,
                const float *gt_weight, const uint8_t *gt_keep /* may be NULL = keep all */,

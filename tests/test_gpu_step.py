@@ -206,3 +206,45 @@ def test_run_host_equals_run_and_lagged_results_arrive_one_call_later(lag):
         np.testing.assert_array_equal(g["valid"], w_valid)
         np.testing.assert_array_equal(np.nan_to_num(g["losses"], nan=-7.0), np.nan_to_num(w_loss, nan=-7.0))
     assert torch.equal(step.grad_feat, ref.grad_feat) and torch.equal(step.roi_out, ref.roi_out)
+
+
+@pytest.mark.parametrize("near_ring_end", [False, True])
+def test_stream_sampling_equals_the_host_hop(near_ring_end):
+    """rng="stream" (uniforms read from a device ring the host fills ahead of time, no host sync inside the step,
+    cim_anti_noise_stream) against rng="hop" over several back-to-back steps with a foreign np.random draw in the
+    middle: same draws, same outputs bit for bit, and numpy's generator in the same state after sync_rng().  The
+    second case starts the stream just before the end of the ring (the top-up and the kernel's reads wrap)."""
+    pr = _small_problem(23)
+    kb = pr["size"] // 16 if mask_ops.tiled_ok(pr["size"], pr["size"]) else 0
+    mat = torch.stack([synth.cluster_mat(pr["R"], pr["C"], np.nonzero(pr["labels"][b].numpy())[0], 4, 9 + b)
+                       for b in range(pr["n_img"])]).to(DEV)
+    res = {}
+    for mode in ("hop", "stream"):
+        step = CIMHeadStep(pr["n_img"], pr["R"], pr["C"], pr["Cf"], pr["H"], pr["W"], 1.0 / 16, pr["packed"].shape[-1],
+                           feat_dim=pr["D"], device=DEV, mask_kb_per_row=kb, head_grads=True, rng=mode)
+        if mode == "stream" and near_ring_end:
+            us = step.ustream
+            start = us.ring_len - 7
+            us.drawn = us.consumed = us.committed = start
+            step.d_cursor.fill_(start)
+        np.random.seed(5)
+        outs = []
+        for i in range(7):
+            step.run(pr["feat"], pr["rois"].to(DEV), pr["grad_out"], pr["packed"], pr["seg_x"], pr["weight"],
+                     pr["bias"], pr["labels"].to(DEV), mat=mat)
+            outs.append([t.clone() for t in (step.gt_keep, step.pseudo_labels, step.pseudo_iou.view(torch.int16),
+                                             step.loss_weights, step.valid, step.losses, step.grad_weight,
+                                             step.gt_count)])
+            if i == 3:
+                step.sync_rng()
+                foreign = np.random.random_sample(4)               # e.g. the sampler's permutation at an epoch boundary
+        step.sync_rng()
+        torch.cuda.synchronize()
+        res[mode] = (outs, foreign, np.random.get_state()[1].copy(), np.random.get_state()[2])
+    assert int(res["hop"][0][0][7].sum()) > 0                      # pseudo GTs exist: uniforms were consumed
+    assert not all(torch.equal(a[0], b[0]) for a, b in zip(res["hop"][0][:-1], res["hop"][0][1:]))   # draws differ by step
+    for a, b in zip(res["hop"][0], res["stream"][0]):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+    np.testing.assert_array_equal(res["hop"][1], res["stream"][1])
+    assert np.array_equal(res["hop"][2], res["stream"][2]) and res["hop"][3] == res["stream"][3]

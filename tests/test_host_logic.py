@@ -139,3 +139,54 @@ def test_synth_is_deterministic_and_nested():
     assert inter == min(a.sum(), b.sum())
     down = synth.rasterize(p, out_size=16)
     assert torch.equal(down, m1[:, ::4, ::4])
+
+
+def test_uniform_stream_hands_out_numpys_global_stream_and_commits_it():
+    """heads.UniformStream (the host half of the sync-free sampling mode): the doubles drawn ahead are numpy's global
+    stream in order, consumption is learned with a lag, commit() leaves np.random where per-step draws would have,
+    and foreign draws between commit() and the next step keep their place in the stream."""
+    from cim_b200.heads import UniformStream
+    M = 50
+    rng = np.random.RandomState(7)
+    counts = rng.randint(0, M + 1, size=40)
+    # reference: every step draws its own count from the global generator; a foreign draw after step 24
+    np.random.seed(11)
+    want = []
+    for i, c in enumerate(counts):
+        want.append(np.random.random_sample(c))
+        if i == 24:
+            foreign_want = np.random.random_sample(3)
+    state_want = np.random.get_state()[1].copy()
+
+    np.random.seed(11)
+    us = UniformStream(16 * M, M)
+    ring = np.full(us.ring_len, np.nan)
+    inflight, got, cursor = [], [], 0
+    for i, c in enumerate(counts):
+        while len(inflight) > 1:                               # lagged read-back: at most 2 steps unknown
+            us.note_consumed(inflight.pop(0))
+        if not us.attached:
+            us.attach()
+        inflight.append(int(c))
+        n = us.need(len(inflight))
+        if n:
+            pos, u = us.draw(n)
+            assert pos + n - us.ring_len <= us.consumed        # only consumed slots are overwritten
+            ring[(pos + np.arange(n)) % us.ring_len] = u
+        assert cursor + c <= us.drawn
+        got.append(ring[(cursor + np.arange(c)) % us.ring_len].copy())   # what the device kernel reads
+        cursor += c
+        if i == 24:
+            while inflight:
+                us.note_consumed(inflight.pop(0))
+            us.commit()
+            assert not us.attached
+            foreign = np.random.random_sample(3)
+            np.testing.assert_array_equal(foreign, foreign_want)
+    while inflight:
+        us.note_consumed(inflight.pop(0))
+    us.commit()
+    for g, w in zip(got, want):
+        np.testing.assert_array_equal(g, w)
+    assert np.array_equal(np.random.get_state()[1], state_want)
+    assert us.consumed == us.committed == cursor
