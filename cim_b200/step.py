@@ -339,11 +339,13 @@ class CIMHeadStep:
         return self
 
     # -------------------------------------------------------------------------------------
-    def _drain_counts(self, keep_unknown):
+    def _drain_counts(self, keep_unknown, keep_newest=0):
         """Read the pseudo-GT counts of finished steps (rng="stream"); wait until at most `keep_unknown` steps are
-        left whose consumption is unknown."""
+        left whose consumption is unknown.  keep_newest = 1 leaves the newest entry alone even if its copy has
+        already landed: inside a step that entry is the step's OWN count, whose uniforms are only provisioned after
+        this call."""
         q, us = self._cnt_q, self.ustream
-        while q and (len(q) > keep_unknown or q[0][1].query()):
+        while len(q) > keep_newest and (len(q) > keep_unknown or q[0][1].query()):
             hbuf, hev = q.popleft()
             hev.synchronize()
             us.note_consumed(int(np.minimum(hbuf.numpy(), self.p.gt_cap).sum()))
@@ -353,7 +355,7 @@ class CIMHeadStep:
         queue): learn what finished steps consumed, draw ahead if the reserve could run out, upload in stream order
         (the ring slots overwritten belong to positions below `consumed`, i.e. to kernels that precede the copy)."""
         us = self.ustream
-        self._drain_counts(keep_unknown=2)              # this step + at most one earlier step still running
+        self._drain_counts(keep_unknown=2, keep_newest=1)   # this step + at most one earlier step still running
         if not us.attached:
             us.attach()
         n = us.need(len(self._cnt_q))

@@ -208,12 +208,14 @@ def test_run_host_equals_run_and_lagged_results_arrive_one_call_later(lag):
     assert torch.equal(step.grad_feat, ref.grad_feat) and torch.equal(step.roi_out, ref.roi_out)
 
 
-@pytest.mark.parametrize("near_ring_end", [False, True])
-def test_stream_sampling_equals_the_host_hop(near_ring_end):
+@pytest.mark.parametrize("near_ring_end,slow_host", [(False, False), (True, False), (False, True)])
+def test_stream_sampling_equals_the_host_hop(near_ring_end, slow_host):
     """rng="stream" (uniforms read from a device ring the host fills ahead of time, no host sync inside the step,
     cim_anti_noise_stream) against rng="hop" over several back-to-back steps with a foreign np.random draw in the
     middle: same draws, same outputs bit for bit, and numpy's generator in the same state after sync_rng().  The
-    second case starts the stream just before the end of the ring (the top-up and the kernel's reads wrap)."""
+    second case starts the stream just before the end of the ring (the top-up and the kernel's reads wrap); the third
+    lets the GPU finish the mining phase before the host provisions the step's uniforms (a slow host: the step's own
+    count copy has landed by then)."""
     pr = _small_problem(23)
     kb = pr["size"] // 16 if mask_ops.tiled_ok(pr["size"], pr["size"]) else 0
     mat = torch.stack([synth.cluster_mat(pr["R"], pr["C"], np.nonzero(pr["labels"][b].numpy())[0], 4, 9 + b)
@@ -231,7 +233,8 @@ def test_stream_sampling_equals_the_host_hop(near_ring_end):
         outs = []
         for i in range(7):
             step.run(pr["feat"], pr["rois"].to(DEV), pr["grad_out"], pr["packed"], pr["seg_x"], pr["weight"],
-                     pr["bias"], pr["labels"].to(DEV), mat=mat)
+                     pr["bias"], pr["labels"].to(DEV), mat=mat,
+                     mid_hook=torch.cuda.synchronize if slow_host and i % 2 == 0 else None)
             outs.append([t.clone() for t in (step.gt_keep, step.pseudo_labels, step.pseudo_iou.view(torch.int16),
                                              step.loss_weights, step.valid, step.losses, step.grad_weight,
                                              step.gt_count)])
