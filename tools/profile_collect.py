@@ -27,6 +27,12 @@ if __name__ == "__main__":
     if os.path.exists(lc):
         open(os.path.join(pr, f"{tag}_launches.txt"), "w").write(run("python", "tools/launch_summary.py", lc, cmdline))
         subprocess.run(["cp", lc, os.path.join(pr, f"{tag}_launches.csv")])
+    li = os.path.join(go, f"{tag}_launches_infer.csv")
+    if os.path.exists(li):
+        open(os.path.join(pr, f"{tag}_launches_infer.txt"), "w").write(run(
+            "python", "tools/launch_summary.py", li,
+            "ncu --metrics gpu__time_duration.sum --clock-control none python tools/infer_bench.py --images 8 --iters 2   "
+            "(cfg5: HRNet-W48, 8 images x 4000 proposals, 80 classes, forward only)"))
     ln = os.path.join(go, f"{tag}_launches_nvtx.csv")
     if os.path.exists(ln):
         subprocess.run(["cp", ln, os.path.join(pr, f"{tag}_launches_nvtx.csv")])
