@@ -32,19 +32,84 @@ def init_from_env(backend=None):
     return rank, world, local
 
 
+def _parse_cpulist(text):
+    """'0-3,8,10-11' -> [0, 1, 2, 3, 8, 10, 11] (the format of /sys/devices/system/node/nodeN/cpulist)."""
+    out = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        out.extend(range(int(lo), int(hi or lo) + 1))
+    return out
+
+
+def gpu_numa_node(index):
+    """NUMA node of the host memory closest to CUDA device `index` (sysfs of its PCI function), or -1 when the
+    platform does not say (single-node hosts, containers without sysfs, no CUDA)."""
+    try:
+        p = torch.cuda.get_device_properties(index)
+        path = f"/sys/bus/pci/devices/{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0/numa_node"
+        with open(path) as f:
+            return int(f.read().strip())
+    except Exception:
+        return -1
+
+
+def plan_rank_cores(local_rank, local_world, avail, rank_nodes, node_cpus):
+    """Pure planning half of pin_rank_to_cores (unit-tested on the CPU): `avail` = the cores this process may use,
+    rank_nodes[r] = NUMA node of rank r's GPU (-1 unknown), node_cpus[n] = cores of node n.  A rank whose GPU's node is
+    known and has usable cores gets an equal slice of THAT node's cores among the ranks that share the node -- its
+    pinned staging buffers (first touch) and its copy engine's reads then stay on the socket the GPU hangs off.  If any
+    rank cannot be placed that way (unknown node, a cpuset that does not reach the other socket), ALL ranks take equal
+    slices of the usable cores by local rank, so the slices stay disjoint."""
+    avail = sorted(avail)
+    usable = set(avail)
+
+    def node_plan(r):
+        node = rank_nodes[r] if r < len(rank_nodes) else -1
+        if node < 0 or node not in node_cpus:
+            return None
+        cpus = [c for c in sorted(node_cpus[node]) if c in usable]
+        peers = [q for q in range(local_world) if rank_nodes[q] == node]
+        per = len(cpus) // max(len(peers), 1)
+        if per < 1:
+            return None
+        i = peers.index(r)
+        return cpus[i * per:(i + 1) * per]
+
+    plans = [node_plan(r) for r in range(local_world)]
+    if all(p is not None for p in plans):              # every rank can sit on its GPU's node: disjoint by construction
+        return plans[local_rank]
+    per = len(avail) // max(local_world, 1)
+    if per < 1:
+        return None
+    return avail[local_rank * per:(local_rank + 1) * per]
+
+
 def pin_rank_to_cores(local_rank, local_world):
-    """Give every rank of a node its own slice of the host cores (Linux): the per-step host work of a rank -- kernel
-    launches, the sampling hop's wait + random draw, the staging of the next inputs -- then does not migrate or share a
-    core with another rank's.  Call before allocating pinned buffers.  Returns the core list, or None when the node
-    has fewer cores than ranks or affinity is not supported."""
+    """Give every rank of a node its own slice of the host cores (Linux), on the NUMA node of its GPU when sysfs tells
+    (plan_rank_cores): the per-step host work of a rank -- kernel launches, the staging of the next inputs -- then does
+    not migrate or share a core with another rank's, and the pinned buffers it allocates afterwards (first touch) are
+    local to the GPU that reads them.  Call before allocating pinned buffers.  Returns the core list, or None when the
+    node has fewer cores than ranks or affinity is not supported."""
     try:
         avail = sorted(os.sched_getaffinity(0))
     except (AttributeError, OSError):
         return None
-    per = len(avail) // max(local_world, 1)
-    if local_world <= 1 or per < 1:
+    if local_world <= 1:
         return None
-    cores = avail[local_rank * per:(local_rank + 1) * per]
+    rank_nodes = [gpu_numa_node(r) for r in range(local_world)]
+    node_cpus = {}
+    for n in set(rank_nodes):
+        if n >= 0:
+            try:
+                with open(f"/sys/devices/system/node/node{n}/cpulist") as f:
+                    node_cpus[n] = _parse_cpulist(f.read())
+            except (OSError, ValueError):
+                pass
+    cores = plan_rank_cores(local_rank, local_world, avail, rank_nodes, node_cpus)
+    if not cores:
+        return None
     try:
         os.sched_setaffinity(0, cores)
     except OSError:

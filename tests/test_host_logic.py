@@ -190,3 +190,21 @@ def test_uniform_stream_hands_out_numpys_global_stream_and_commits_it():
         np.testing.assert_array_equal(g, w)
     assert np.array_equal(np.random.get_state()[1], state_want)
     assert us.consumed == us.committed == cursor
+
+
+def test_rank_core_plan_follows_the_gpus_numa_node():
+    """dist.plan_rank_cores: ranks take slices of the cores of THEIR GPU's NUMA node when it is known and usable,
+    else equal slices of all usable cores (containers whose cpuset does not reach the other socket)."""
+    from cim_b200 import dist as cdist
+    assert cdist._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    nodes = [0, 0, 0, 0, 1, 1, 1, 1]
+    cpus = {0: list(range(0, 32)), 1: list(range(32, 64))}
+    plan = [cdist.plan_rank_cores(r, 8, range(64), nodes, cpus) for r in range(8)]
+    assert plan[0] == list(range(0, 8)) and plan[3] == list(range(24, 32)) and plan[4] == list(range(32, 40))
+    assert sorted(sum(plan, [])) == list(range(64))                       # disjoint, complete
+    # the cpuset only holds node 0's cores: every rank falls back to disjoint slices of what is usable
+    plan = [cdist.plan_rank_cores(r, 8, range(16), nodes, cpus) for r in range(8)]
+    assert plan[1] == [2, 3] and plan[5] == [10, 11] and sorted(sum(plan, [])) == list(range(16))
+    # unknown nodes, fewer cores than ranks
+    assert cdist.plan_rank_cores(2, 4, range(8), [-1] * 4, {}) == [4, 5]
+    assert cdist.plan_rank_cores(0, 8, range(4), [-1] * 8, {}) is None
