@@ -448,10 +448,12 @@ def measure_training(name, cfg, args, dev, rank, world, peaks, cdist, headline):
         crops = mask_ops.crops_from_packed_host(inp.pop("packed_flat").view(cfg["n_img"] * cfg["R"], -1), cfg["mask"],
                                                 cfg["mask"])
         step.alloc_host_io(mask_hw=(cfg["mask"], cfg["mask"]),
-                           crop_capacity_words=int(crops.words.numel() * 1.25) + 1024)
+                           crop_capacity_words=int(crops.words.numel() * 1.25) + 1024, prefetch_depth=args.prefetch_depth)
         step.hi_rois.copy_(inp["rois"])
         step.hi_labels.copy_(inp["labels"])
         step.set_host_crops(crops)
+        if args.e2e_diag == "no-wait":         # diagnostic: the host never waits for a step's results
+            step._collect_results = lambda: None
         run_host = lambda: step.run_host(inp["feat"], inp["grad_out"], inp["seg_x"], inp["weight"], inp["bias"],
                                          mat=mat, lag_results=True)
         # the step runs on a HIGH-priority stream: the prefetch of the next step's inputs (H2D + the crop-unpack kernel
@@ -482,9 +484,16 @@ def measure_training(name, cfg, args, dev, rank, world, peaks, cdist, headline):
                       "host_outputs": "per-image losses [n_img, K+1, 3], valid flags, two checksums of the RoIAlign outputs, "
                                       "the pseudo-GT counts of the sampling hop" if not args.no_head_grads else
                                       "pseudo labels / IoU labels / loss weights, valid flags, checksums, pseudo-GT counts",
-                      "pipelining": "H2D of step i+1 on a copy stream overlaps the kernels of step i; the results of step i "
-                                    "are copied D2H at its end and read by the host (one event wait per step) while step "
-                                    "i+1 runs; the last step's wait is inside the timed region",
+                      "pipelining": ("every call copies one full set of inputs host->device on a copy stream while the "
+                                     "kernels of the current step run" +
+                                     (" -- two steps ahead (prefetch_depth 2: into a pre-stage buffer, moved device-to-"
+                                      "device into the next step's input buffer, whose crop unpack then always finds its "
+                                      "data when the mining phase leaves the SMs idle)" if args.prefetch_depth == 2 else
+                                      " -- one step ahead") +
+                                     "; the results of step i are copied D2H at its end and read by the host (one event "
+                                     "wait per step) while step i+1 runs; the last step's wait is inside the timed region"),
+                      "prefetch_depth": args.prefetch_depth,
+                      **({"DIAGNOSTIC": args.e2e_diag + ": not a result"} if args.e2e_diag else {}),
                       "order": "graph"}
         if step.trace is not None and rank == 0:             # host timeline of the last e2e steps (CIM_STEP_TRACE=1)
             ev = step.trace[-5 * 3:]
@@ -631,6 +640,10 @@ def main():
     ap.add_argument("--sampling", default="stream", choices=["stream", "hop"],
                     help="anti-noise sampling: uniforms from a device ring filled ahead (no host sync inside the step) "
                          "or the host hop (counts down, draw, uniforms up)")
+    ap.add_argument("--prefetch-depth", type=int, default=1, choices=[1, 2],
+                    help="e2e input pipeline: host->device copies one or two steps ahead of the step that uses them")
+    ap.add_argument("--e2e-diag", default="", choices=["", "no-wait"],
+                    help="DIAGNOSTIC ONLY (the e2e number is then not a result): switch a piece of the host path off")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-anti-noise", action="store_true")
     ap.add_argument("--no-head-grads", action="store_true",

@@ -385,13 +385,22 @@ class CIMHeadStep:
         self.ustream.commit()
 
     # -------------------------------------------------------------------------------------
-    def alloc_host_io(self, mask_hw=None, crop_capacity_words=0):
+    def alloc_host_io(self, mask_hw=None, crop_capacity_words=0, prefetch_depth=1):
         """Pinned host buffers of the end-to-end call: inputs that originate on the host in the
         reference's pipeline (rois, labels: lib/roi_data/minibatch.py:45-61; proposal masks:
         the COB .mat files of tools/pre) and the step's results.  Device-side input buffers are
         DOUBLE buffered and filled on a separate copy stream, so the host->device copy of step
-        i+1 overlaps the kernels of step i (what a prefetching data loader does)."""
+        i+1 overlaps the kernels of step i (what a prefetching data loader does).
+        prefetch_depth = 2 (crops only): the host->device copy runs TWO steps ahead, into a third set of (small) crop
+        buffers on its own stream; the copy into the step's input buffer is then a device-to-device copy at the start
+        of the previous step, so the crop unpack can always run in that step's idle mining phase -- with eight ranks
+        copying at once a rank's 60 MB take 2.5 ms instead of 1.3 (tools/h2d_bw.py) and the unpack used to slip behind
+        the RoIAlign backward.  What run_host() finds in the pinned buffers at call t is then the input of step t + 2
+        (the first call also uses it for steps t and t + 1)."""
         k, n_img, R, C1 = self.K, self.n_img, self.R, self.C + 1
+        if prefetch_depth not in (1, 2) or (prefetch_depth == 2 and not crop_capacity_words):
+            raise ValueError("prefetch_depth must be 1, or 2 with crop_capacity_words > 0")
+        self.prefetch_depth = prefetch_depth
         pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
         self.hi_rois = pin((n_img * R, 5), torch.float32)
         self.hi_labels = pin((n_img, self.C), torch.float32)
@@ -440,6 +449,12 @@ class CIMHeadStep:
                     buf["meta"] = dv((self.L.cim_mask_meta_bytes(n_img, R, self.words),), torch.uint8)
             self.d_checksum = dv((2,), torch.float32)
             self.copy_stream = torch.cuda.Stream(device=self.dev)
+            if prefetch_depth == 2:
+                self.pre = dict(rois=dv((n_img * R, 5), torch.float32), labels=dv((n_img, self.C), torch.float32),
+                                crop_words=dv((self.crop_cap,), torch.int32), crop_meta=dv((n_img * R, 4), torch.int32),
+                                crop_off=dv((n_img * R,), torch.int64), n_words=0, valid=False,
+                                filled=torch.cuda.Event())
+                self.copy_stream2 = torch.cuda.Stream(device=self.dev)
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in (self.hi_rois, self.hi_labels))
         if not self.crop_cap:
             self.h2d_bytes += self.hi_masks.numel() * 4
@@ -474,14 +489,16 @@ class CIMHeadStep:
         self.n_crop_words = n
         self.mask_hw = (crops.height, crops.width)
 
-    def stage_host_inputs(self, defer_kernels=False):
+    def stage_host_inputs(self, defer_kernels=False, direct=False):
         """Enqueue the host->device copy of the CURRENT contents of hi_rois / hi_labels / hi_masks
         into the idle device buffer, on the copy stream.  Call it for step i+1 before (or while)
         step i computes; run_host() consumes the staged buffer.
         defer_kernels: only the copies (copy engine) are enqueued now; the returned callable enqueues the kernels that
         turn them into the step's input (crop unpack + mask metadata) -- run_host() calls it from inside the step,
         behind `ev_premine`, so that they run next to the mining kernels and the sampling hop, which leave most SMs idle,
-        instead of competing with the RoIAlign kernels (0.31 ms -> measured in tools/e2e_diag.py)."""
+        instead of competing with the RoIAlign kernels (0.31 ms -> measured in tools/e2e_diag.py).
+        direct (prefetch_depth = 2 only): copy the pinned buffers straight into the device buffer, bypassing and
+        invalidating the pre-stage (a step that was not prefetched)."""
         buf = self.di[self._slot ^ 1] if self._staged else self.di[self._slot]
 
         def kernels(after=None):
@@ -515,21 +532,49 @@ class CIMHeadStep:
                                                     C.c_void_p(self.copy_stream.cuda_stream)), "cim_mask_meta")
                 buf["ready"].record(self.copy_stream)
 
-        with torch.cuda.stream(self.copy_stream):
-            self.copy_stream.wait_event(buf["free"])          # its previous consumer has finished
-            buf["rois"].copy_(self.hi_rois, non_blocking=True)
-            buf["labels"].copy_(self.hi_labels, non_blocking=True)
+        def h2d(dst, stream):
+            """pinned input buffers -> dst (a device input buffer or the pre-stage); returns the crop word count"""
+            dst["rois"].copy_(self.hi_rois, non_blocking=True)
+            dst["labels"].copy_(self.hi_labels, non_blocking=True)
+            n = 0
             if self.crop_cap:
                 n = self.n_crop_words
-                buf["crop_words"][:n].copy_(self.hi_crop_words[:n], non_blocking=True)
-                buf["crop_meta"].copy_(self.hi_crop_meta, non_blocking=True)
-                buf["crop_off"].copy_(self.hi_crop_off, non_blocking=True)
+                dst["crop_words"][:n].copy_(self.hi_crop_words[:n], non_blocking=True)
+                dst["crop_meta"].copy_(self.hi_crop_meta, non_blocking=True)
+                dst["crop_off"].copy_(self.hi_crop_off, non_blocking=True)
                 self.last_mask_h2d_bytes = n * 4 + self.hi_crop_meta.numel() * 4 + self.hi_crop_off.numel() * 8
             else:
-                buf["masks"].copy_(self.hi_masks, non_blocking=True)
-                buf["meta_done"] = False
-            self.h2d_ev.record(self.copy_stream)               # the pinned input buffers have been read
+                dst["masks"].copy_(self.hi_masks, non_blocking=True)
+                dst["meta_done"] = False
+            self.h2d_ev.record(stream)                         # the pinned input buffers have been read
             self._h2d_pending = True
+            return n
+
+        pre = getattr(self, "pre", None) if self.prefetch_depth == 2 else None
+        if pre is not None and direct:
+            pre["valid"] = False
+            pre = None
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(buf["free"])          # its previous consumer has finished
+            if pre is not None and pre["valid"]:
+                # the input of this buffer's step arrived a step ago: device-to-device
+                self.copy_stream.wait_event(pre["filled"])
+                n = pre["n_words"]
+                for key in ("rois", "labels", "crop_meta", "crop_off"):
+                    buf[key].copy_(pre[key], non_blocking=True)
+                buf["crop_words"][:n].copy_(pre["crop_words"][:n], non_blocking=True)
+            else:
+                h2d(buf, self.copy_stream)
+        if pre is not None:
+            # ... and the pinned buffers (the input of the step after that one) go to the pre-stage on their own stream,
+            # so that a slow copy never sits in front of the unpack kernel
+            with torch.cuda.stream(self.copy_stream2):
+                # after the device-to-device copy out of the pre-stage / after the copy stream's own read of the
+                # pinned buffers (h2d_ev, recorded below, then covers both readers)
+                self.copy_stream2.wait_stream(self.copy_stream)
+                pre["n_words"] = h2d(pre, self.copy_stream2)
+                pre["filled"].record(self.copy_stream2)
+                pre["valid"] = True
         if defer_kernels:
             return kernels
         kernels()
@@ -561,7 +606,7 @@ class CIMHeadStep:
         every call therefore moves one full set of inputs host->device."""
         cur_stream = torch.cuda.current_stream(self.dev)
         if not self._staged:                                   # first call: nothing was prefetched
-            self.stage_host_inputs()
+            self.stage_host_inputs(direct=True)
             self._staged = True
         buf = self.di[self._slot]
         finish_stage = None

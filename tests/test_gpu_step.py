@@ -136,7 +136,7 @@ def _small_problem(seed=11):
     packed = torch.stack([mask_ops.mask_pack(m.to(DEV)) for m in masks])
     return dict(n_img=n_img, R=R, C=C, D=D, Cf=Cf, H=H, W=W, size=size, feat=feat.to(DEV), grad_out=grad_out.to(DEV),
                 seg_x=seg_x.to(DEV), rois=torch.cat(rois), labels=torch.cat(labels), packed=packed, weight=weight,
-                bias=bias)
+                bias=bias, masks=masks)
 
 
 def test_graph_order_and_overlapped_order_give_identical_results():
@@ -251,3 +251,52 @@ def test_stream_sampling_equals_the_host_hop(near_ring_end, slow_host):
             assert torch.equal(x, y)
     np.testing.assert_array_equal(res["hop"][1], res["stream"][1])
     assert np.array_equal(res["hop"][2], res["stream"][2]) and res["hop"][3] == res["stream"][3]
+
+
+@pytest.mark.parametrize("depth", [1, 2])
+def test_run_host_with_crops_and_changing_inputs(depth):
+    """run_host() fed with bounding-box crops of the proposal masks (the bench's wire format; sparse unpack on the
+    device) whose rois / labels / masks CHANGE from call to call.  prefetch_depth = 1: what is in the pinned buffers at
+    call t is step t + 1's input (call 0 also serves step 0); prefetch_depth = 2: step t + 2's (call 0 also serves
+    steps 0 and 1).  Every step must equal run() on the inputs it was meant to see."""
+    probs = [_small_problem(31 + 7 * i) for i in range(3)]
+    pr0 = probs[0]
+    kb = pr0["size"] // 16 if mask_ops.tiled_ok(pr0["size"], pr0["size"]) else 0
+    assert kb, "the crop path of run_host needs the tiled mask layout"
+    mk = lambda: CIMHeadStep(pr0["n_img"], pr0["R"], pr0["C"], pr0["Cf"], pr0["H"], pr0["W"], 1.0 / 16,
+                             pr0["packed"].shape[-1], feat_dim=pr0["D"], device=DEV, mask_kb_per_row=kb, head_grads=True)
+    n_calls = 6
+    fed = [probs[t % 3] for t in range(n_calls)]                       # pinned-buffer contents at call t
+    seen = [fed[max(0, t - depth)] for t in range(n_calls)]            # what step t must compute on
+    ref = mk()
+    want = []
+    np.random.seed(3)
+    for pr in seen:
+        ref.run(pr0["feat"], pr["rois"].to(DEV), pr0["grad_out"], pr["packed"], pr0["seg_x"], pr0["weight"], pr0["bias"],
+                pr["labels"].to(DEV), pr["labels"].numpy())
+        torch.cuda.synchronize()
+        want.append((ref.losses.cpu().numpy().copy(), ref.valid.cpu().numpy().copy(), ref.iou.clone(),
+                     ref.roi_out.clone()))
+    assert not np.array_equal(np.nan_to_num(want[0][0]), np.nan_to_num(want[3][0]))     # the inputs do differ
+
+    def crops_of(pr):
+        flat = torch.stack([mask_ops.mask_pack(m.to(DEV), layout="flat").cpu() for m in pr["masks"]])
+        return mask_ops.crops_from_packed_host(flat.view(pr["n_img"] * pr["R"], -1), pr["size"], pr["size"])
+
+    crops = [crops_of(pr) for pr in probs]
+    step = mk()
+    cap = max(int(c.words.numel()) for c in crops) + 64
+    step.alloc_host_io(mask_hw=(pr0["size"], pr0["size"]), crop_capacity_words=cap, prefetch_depth=depth)
+    np.random.seed(3)
+    for t in range(n_calls):
+        pr = fed[t]
+        step.wait_inputs_consumed()
+        step.hi_rois.copy_(pr["rois"])
+        step.hi_labels.copy_(pr["labels"])
+        step.set_host_crops(crops[t % 3])
+        step.run_host(pr0["feat"], pr0["grad_out"], pr0["seg_x"], pr0["weight"], pr0["bias"])
+        got = step.results_host
+        w_loss, w_valid, w_iou, w_roi = want[t]
+        np.testing.assert_array_equal(got["valid"], w_valid)
+        np.testing.assert_array_equal(np.nan_to_num(got["losses"], nan=-7.0), np.nan_to_num(w_loss, nan=-7.0))
+        assert torch.equal(step.iou.view(torch.int16), w_iou.view(torch.int16)) and torch.equal(step.roi_out, w_roi)
