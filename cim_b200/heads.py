@@ -154,8 +154,9 @@ class UniformStream:
     (learned from lagged read-backs of the pseudo-GT counts), `committed` = position the global generator itself
     has been advanced to.  commit() advances the global generator by consumed - committed doubles -- after it
     np.random is exactly where the reference's per-class np.random.choice calls (heads.py:459) would have left it --
-    and detaches: values drawn ahead but not consumed are dropped and the next step clones the global state again, so
-    draws other code makes from np.random BETWEEN commit() and the next step keep their place in the stream.  Other
+    and detaches: if other code draws from np.random BETWEEN commit() and the next step, the values drawn ahead but not
+    consumed are dropped and the next step clones the global state again, so those draws keep their place in the stream
+    (if nobody drew, the reserve is still the stream's continuation and is kept).  Other
     code must not draw from np.random between a step and the following commit()."""
 
     def __init__(self, ring_len, max_per_step):
@@ -164,17 +165,25 @@ class UniformStream:
         self.ring_len, self.max_per_step = int(ring_len), int(max_per_step)
         self.rs = None
         self.drawn = self.consumed = self.committed = 0
+        self._left_at = None            # np.random's state right after the last commit()
 
     @property
     def attached(self):
-        return self.rs is not None
+        return self.rs is not None and self._left_at is None
 
     def attach(self):
-        """Clone numpy's global state; the stream continues at `consumed`."""
+        """Follow numpy's global generator from its CURRENT state; the stream continues at `consumed`.  If the
+        generator is still where the last commit() left it (nobody else drew from it), the reserve drawn ahead before
+        that commit is still the continuation of the stream and is kept; otherwise it is dropped and the state is
+        cloned again (the next draw() then refills the ring from position `consumed`)."""
         assert self.consumed == self.committed, "commit() before attaching again"
+        if self.rs is not None and self._left_at is not None and _same_state(np.random.get_state(), self._left_at):
+            self._left_at = None
+            return
         self.rs = np.random.RandomState()
         self.rs.set_state(np.random.get_state())
         self.drawn = self.consumed
+        self._left_at = None
 
     def need(self, steps_unknown):
         """Doubles to draw now so that a step launched next cannot run past `drawn`, whatever the `steps_unknown`
@@ -200,13 +209,17 @@ class UniformStream:
         assert self.consumed <= self.drawn, "a step consumed more uniforms than were drawn ahead"
 
     def commit(self):
-        """Every step's consumption is known (the caller waited for the read-backs): bring np.random there, detach."""
+        """Every step's consumption is known (the caller waited for the read-backs): bring np.random there and detach
+        (the reserve survives if the generator is found in this very state at the next attach())."""
         n = self.consumed - self.committed
         if n:
             np.random.random_sample(n)
         self.committed = self.consumed
-        self.rs = None
-        self.drawn = self.consumed
+        self._left_at = np.random.get_state() if self.rs is not None else None
+
+
+def _same_state(a, b):
+    return a[0] == b[0] and a[2:] == b[2:] and np.array_equal(a[1], b[1])
 
 
 def anti_noise_device(p, labels, gt_count, gt_class, gt_weight, gt_keep, stream=None):

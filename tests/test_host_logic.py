@@ -183,6 +183,14 @@ def test_uniform_stream_hands_out_numpys_global_stream_and_commits_it():
             assert not us.attached
             foreign = np.random.random_sample(3)
             np.testing.assert_array_equal(foreign, foreign_want)
+        if i == 10:                                            # a commit nobody draws after: the reserve is kept
+            while inflight:
+                us.note_consumed(inflight.pop(0))
+            drawn_before = us.drawn
+            us.commit()
+            assert not us.attached
+            us.attach()
+            assert us.attached and us.drawn == drawn_before
     while inflight:
         us.note_consumed(inflight.pop(0))
     us.commit()
