@@ -477,7 +477,12 @@ def measure_training(name, cfg, args, dev, rank, world, peaks, cdist, headline):
             torch.cuda.synchronize()
         ms_e2e = cdist.max_over_ranks(e0.elapsed_time(e1) / steps, dev)
         res["e2e"] = {"value": n_images / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
-                      "h2d_bytes_per_step": int(step.h2d_bytes + step.last_mask_h2d_bytes + step.last_uniform_bytes),
+                      "h2d_bytes_per_step": int(step.h2d_bytes + step.last_mask_h2d_bytes +
+                                                (step.last_uniform_bytes if step.rng == "hop" else 0)),
+                      "uniform_ring": (None if step.rng == "hop" or args.no_anti_noise else
+                                       f"{step.last_uniform_bytes} B per top-up of the device ring of random doubles; a top-up "
+                                       f"lasts for {step.max_uniforms * 4} consumed doubles (a step consumes one per pseudo GT), "
+                                       "not counted per step"),
                       "d2h_bytes_per_step": int(step.d2h_bytes),
                       "host_inputs": "rois, labels, bbox-cropped bit-packed proposal masks (unpacked on the device), the "
                                      "uniform doubles of the sampling hop; features/seg_x/grad_out are device-produced",
