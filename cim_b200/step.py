@@ -618,8 +618,11 @@ class CIMHeadStep:
                  mid_hook=lambda: ((finish_stage(self.ev_premine) if finish_stage else None),
                                    (self._collect_results() if lag_results else None)))
         buf["free"].record(cur_stream)
-        self.d_checksum[0] = self.roi_out.view(-1)[::4099].sum()
-        self.d_checksum[1] = self.grad_feat.view(-1)[::127].sum()
+        # two sparse checksums of the RoIAlign outputs ride along with the losses (a few hundred elements each, summed
+        # straight into the result buffer: two small kernels)
+        ro, gf = self.roi_out.view(-1), self.grad_feat.view(-1)
+        torch.sum(ro[::max(1, ro.numel() // 509)], dim=0, out=self.d_checksum[0])
+        torch.sum(gf[::max(1, gf.numel() // 251)], dim=0, out=self.d_checksum[1])
         if self.head_grads:
             self.ho_losses.copy_(self.losses, non_blocking=True)
         else:

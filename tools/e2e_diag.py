@@ -13,7 +13,7 @@ dev = torch.device("cuda:0")
 inp = bench.build_inputs(cfg, dev, 1234)
 Cf, H, W, scale = inp["shape"]
 step = CIMHeadStep(cfg["n_img"], cfg["R"], cfg["C"], Cf, H, W, scale, inp["packed"].shape[-1],
-                   device=dev, mask_kb_per_row=inp["kb_per_row"], head_grads=True)
+                   device=dev, mask_kb_per_row=inp["kb_per_row"], head_grads=True, rng="stream")
 crops = mask_ops.crops_from_packed_host(inp.pop("packed_flat").view(cfg["n_img"] * cfg["R"], -1), cfg["mask"], cfg["mask"])
 step.alloc_host_io(mask_hw=(cfg["mask"], cfg["mask"]), crop_capacity_words=int(crops.words.numel() * 1.25) + 1024)
 step.hi_rois.copy_(inp["rois"]); step.hi_labels.copy_(inp["labels"]); step.set_host_crops(crops)
@@ -53,7 +53,7 @@ with torch.cuda.stream(hp):
     print(f"run_host lag, full masks H2D  {timed(host2, flush=step2.flush_results):.3f} ms  ({step2.h2d_bytes / 1e6:.0f} MB / step)")
     # ---- pieces of the host path switched off one at a time
     real_stage = step.stage_host_inputs
-    step.stage_host_inputs = lambda defer_kernels=False: ((lambda after=None: None) if defer_kernels else step)   # no H2D, no unpack
+    step.stage_host_inputs = lambda defer_kernels=False, direct=False: ((lambda after=None: None) if defer_kernels else step)   # no H2D, no unpack
     print(f"run_host lag, NO staging      {timed(lambda: host(lag_results=True), flush=step.flush_results):.3f} ms   (host loop + result read-back only)")
     step.stage_host_inputs = real_stage
 
@@ -69,8 +69,8 @@ with torch.cuda.stream(hp):
     torch.cuda.synchronize()
     print(f"staging alone (copy stream)   {e0.elapsed_time(e1) / 5:.3f} ms   (H2D of the crops + unpack/meta kernel, nothing else running)")
     # ---- which half of the staging costs the 0.3 ms: the H2D copies or the unpack / metadata kernel?
-    def stage_copies_only(defer_kernels=False):
-        k = real_stage(defer_kernels=True)
+    def stage_copies_only(defer_kernels=False, direct=False):
+        k = real_stage(defer_kernels=True, direct=direct)
         buf = step.di[step._slot ^ 1] if step._staged else step.di[step._slot]
         with torch.cuda.stream(step.copy_stream):
             buf["ready"].record(step.copy_stream)
@@ -78,7 +78,7 @@ with torch.cuda.stream(hp):
     step.stage_host_inputs = stage_copies_only
     print(f"run_host lag, H2D copies only {timed(lambda: host(lag_results=True), flush=step.flush_results):.3f} ms")
 
-    def stage_kernels_only(defer_kernels=False):
+    def stage_kernels_only(defer_kernels=False, direct=False):
         buf = step.di[step._slot ^ 1] if step._staged else step.di[step._slot]
         def kernels(after=None):
             with torch.cuda.stream(step.copy_stream):
