@@ -304,6 +304,9 @@ class CIMHeadStep:
             keep = self.gt_keep
             if tr is not None:
                 tr.append(("sampled", time.perf_counter()))
+        if getattr(self, "_res_guard", False):
+            cur.wait_event(self.res_ev)                         # run_host: the previous step's results have been read
+            self._res_guard = False
         with _nvtx("cim/assign"):
             ck(L.cim_assign(C.byref(p), P(self.iou), P(self.gt_count), P(self.gt_rows), P(self.gt_class),
                             P(self.gt_weight), P(keep), P(self.pseudo_labels), P(self.pseudo_iou),
@@ -464,6 +467,10 @@ class CIMHeadStep:
         self._slot = 0
         self._staged = False
         self.res_ev = torch.cuda.Event()
+        self.ev_done = torch.cuda.Event()
+        with torch.cuda.device(self.dev):
+            self.res_stream = torch.cuda.Stream(device=self.dev)
+        self._res_guard = False
         self.h2d_ev = torch.cuda.Event()
         self._h2d_pending = False
         self._pending = False
@@ -619,19 +626,26 @@ class CIMHeadStep:
                                    (self._collect_results() if lag_results else None)))
         buf["free"].record(cur_stream)
         # two sparse checksums of the RoIAlign outputs ride along with the losses (a few hundred elements each, summed
-        # straight into the result buffer: two small kernels)
+        # straight into the result buffer).  roi_out is the first thing the next step overwrites, so its checksum stays on
+        # the step's stream; everything else of the read-back -- the other checksum and the device -> host copies --
+        # runs on a results stream behind `ev_done`, so the next step's first kernels do not queue behind the copies.
+        # The next step waits for `res_ev` right before the first kernel that overwrites a result (cim_assign).
         ro, gf = self.roi_out.view(-1), self.grad_feat.view(-1)
         torch.sum(ro[::max(1, ro.numel() // 509)], dim=0, out=self.d_checksum[0])
-        torch.sum(gf[::max(1, gf.numel() // 251)], dim=0, out=self.d_checksum[1])
-        if self.head_grads:
-            self.ho_losses.copy_(self.losses, non_blocking=True)
-        else:
-            self.ho_labels.copy_(self.pseudo_labels, non_blocking=True)
-            self.ho_iou.copy_(self.pseudo_iou, non_blocking=True)
-            self.ho_weights.copy_(self.loss_weights, non_blocking=True)
-        self.ho_valid.copy_(self.valid, non_blocking=True)
-        self.ho_checksum.copy_(self.d_checksum, non_blocking=True)
-        self.res_ev.record(cur_stream)
+        self.ev_done.record(cur_stream)
+        with torch.cuda.stream(self.res_stream):
+            self.res_stream.wait_event(self.ev_done)
+            torch.sum(gf[::max(1, gf.numel() // 251)], dim=0, out=self.d_checksum[1])
+            if self.head_grads:
+                self.ho_losses.copy_(self.losses, non_blocking=True)
+            else:
+                self.ho_labels.copy_(self.pseudo_labels, non_blocking=True)
+                self.ho_iou.copy_(self.pseudo_iou, non_blocking=True)
+                self.ho_weights.copy_(self.loss_weights, non_blocking=True)
+            self.ho_valid.copy_(self.valid, non_blocking=True)
+            self.ho_checksum.copy_(self.d_checksum, non_blocking=True)
+            self.res_ev.record(self.res_stream)
+        self._res_guard = True
         self._pending = True
         if not lag_results:
             self._collect_results()                            # the host reads the results every step
