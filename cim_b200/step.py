@@ -153,6 +153,7 @@ class CIMHeadStep:
         self.side2 = torch.cuda.Stream(device=self.dev, priority=-2)    # graph order: PCL_loss next to the mining kernels
         self.ev_score = torch.cuda.Event()
         self.ev_premine = torch.cuda.Event()
+        self.ev_prep = torch.cuda.Event()
         self.trace = [] if os.environ.get("CIM_STEP_TRACE") else None
         # layer l reads (cls, det) = (predict_cls, predict_det) for l = 0, else (ref_cls[l-1], ref_iou[l-1])
         s = self.scores.view(nh, n_img, R, C1)
@@ -245,13 +246,18 @@ class CIMHeadStep:
 
         self.side.wait_stream(cur)
         if order == "graph":
-            # the mask maps depend on the proposals only: side stream, next to the RoIAlign forward + scoring GEMM
-            overlap(side_st)
+            # the mask maps depend on the proposals only: side stream, next to the RoIAlign forward + scoring GEMM.
+            # The side stream starts behind the ROI descriptors (window plans on large maps: six small kernels), so
+            # the persistent RoIAlign forward is on the SMs before the overlap's tensor kernel asks for them -- which of
+            # the two went first used to depend on launch timing (cfg3: 5.67 or 5.85 ms)
             with _nvtx("cim/roi_prepare"):
                 ck(L.cim_roi_align_prepare(P(rois), n_img, self.Cf, self.H, self.W, n_img * R, 7, 7, self.scale,
                                            self.sr, self.aligned, P(self.roi_ws), self.roi_ws.numel(), st),
                    "cim_roi_align_prepare")
+            self.ev_prep.record(cur)
             roi_fwd()
+            self.side.wait_event(self.ev_prep)
+            overlap(side_st)
             score_fwd(st, False)
             if pcl_early:
                 # PCL on its own stream, next to the (equally latency-bound) mining kernels; joined before the losses
