@@ -67,3 +67,21 @@ def test_no_cpu_fallback():
         mask_ops.mask_pack(torch.zeros(2, 8, 8, dtype=torch.uint8))
     with pytest.raises(RuntimeError, match="no CPU path"):
         heads.cls_iou_model(16, 21, 3)(torch.zeros(4, 16))
+
+
+def test_debug_flag_constants_match_the_header():
+    """cim_b200/_lib.py mirrors the CIM_DBG_* enum of include/cimhead.h by value; the flags round-trip through the
+    library (cim_set_debug_flags / cim_get_debug_flags need no GPU)."""
+    src = open(os.path.join(ROOT, "include", "cimhead.h")).read()
+    header = {n: int(v) for n, v in re.findall(r"\bCIM_(DBG_[A-Z_]+)\s*=\s*(\d+)u", src)}
+    assert len(header) >= 6
+    for name, value in header.items():
+        assert getattr(_lib, name) == value, f"_lib.{name} != CIM_{name} of cimhead.h"
+    lib = _lib.lib()
+    prev = lib.cim_get_debug_flags()
+    try:
+        with _lib.debug_flags(_lib.DBG_ROI_POOL_SIMPLE | _lib.DBG_SCORE_FFMA):
+            assert lib.cim_get_debug_flags() == 36
+        assert lib.cim_get_debug_flags() == prev
+    finally:
+        lib.cim_set_debug_flags(prev)
